@@ -1,0 +1,110 @@
+"""Generate the committed golden fixtures by running the REFERENCE's own code
+from /root/reference in this container (it cannot travel to the GPU box).
+
+    python tests/golden/make_golden.py
+
+* perm_sampler.npz  - run.py:107-182 `my_swap_h/w` + `block_permutation` driven
+  exactly like run.py:436-507 / util_scripts.py:402-442 under np.random.seed(..),
+  reduced to argmax index vectors (the integer tile-index grid, bit-exact).
+* mattes.npz        - util_scripts.py:85-102 `linkern_for_weight_*`.
+* networks.npz      - networks.py `E_zg/E_zl/G_res/D_patch` executed unmodified
+  on oracle/tfshim (torch-backed TF stand-in) with the seeded parameters of
+  oracle.networks_ref.init_params; outputs stored (strided subsample for the
+  large ones) with the variable creation order.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import refload  # noqa: E402
+from oracle import networks_ref as R  # noqa: E402
+
+SUBSAMPLE = 37  # stride for large outputs
+
+
+def gen_perm():
+    f = refload.reference_functions('run.py', ['my_swap_h', 'my_swap_w', 'block_permutation'])
+    out = {}
+    # (tag, length, levels, count, seed): training config (run.py:440: int(log2(32)) = 5 levels, 96 long),
+    # inference quirk (util_scripts.py:405: int(np.log(32)) = 3 levels, 128 long), and small/edge sizes.
+    cases = [('train96', 96, 5, 3, 1000), ('interp128', 128, 3, 2, 1000), ('small8', 8, 3, 4, 7),
+             ('tiny2', 2, 1, 4, 3), ('wide256', 256, 5, 1, 11)]
+    for tag, length, levels, count, seed in cases:
+        np.random.seed(seed)
+        draws = 0
+        hs, ws = [], []
+        for _ in range(count):                       # h matrices first, like run.py:437-452
+            p = np.eye(length)
+            for idx in range(levels):
+                bs = int(2 ** idx)
+                perm = f['my_swap_h'](np.eye(length // bs))
+                p = np.matmul(p, f['block_permutation'](perm, bs))
+            assert (p.sum(0) == 1).all() and (p.sum(1) == 1).all()
+            hs.append(np.argmax(p, axis=1).astype(np.int32))
+        for _ in range(count):                       # then w matrices, run.py:453-469
+            p = np.eye(length)
+            for idx in range(levels):
+                bs = int(2 ** idx)
+                perm = f['my_swap_w'](np.eye(length // bs))
+                p = np.matmul(f['block_permutation'](perm, bs), p)
+            ws.append(np.argmax(p, axis=0).astype(np.int32))
+        out[tag + '_h'] = np.stack(hs)
+        out[tag + '_w'] = np.stack(ws)
+        out[tag + '_meta'] = np.array([length, levels, count, seed], np.int64)
+        out[tag + '_next_uniform'] = np.array([np.random.uniform()])   # pins the number of draws consumed
+    np.savez_compressed(os.path.join(HERE, 'perm_sampler.npz'), **out)
+    print('perm_sampler.npz', {k: v.shape for k, v in out.items() if not k.endswith('meta')})
+
+
+def gen_mattes():
+    f = refload.reference_functions('util_scripts.py',
+                                    ['linkern_for_weight_horizontal', 'linkern_for_weight_arbitrary_shape'])
+    out = {}
+    for (h, w, r) in [(128, 128, 32), (96, 256, 32), (72, 80, 8)]:
+        ul, ur, bl, br = f['linkern_for_weight_arbitrary_shape'](h, w, r)
+        out['arb_%d_%d_%d' % (h, w, r)] = np.stack([ul, ur, bl, br])           # float64
+    out['hor_1_2_4_256_32'] = f['linkern_for_weight_horizontal']([1, 2, 4, 256], 32)
+    np.savez_compressed(os.path.join(HERE, 'mattes.npz'), **out)
+    print('mattes.npz', {k: (v.shape, v.dtype) for k, v in out.items()})
+
+
+def network_inputs(func, rng, n):
+    if func == 'G_res':
+        return [rng.randn(n, 128, 32, 32).astype(np.float32), rng.randn(n, 128, 32, 32).astype(np.float32)]
+    return [rng.uniform(-1, 1, (n, 3, 128, 128)).astype(np.float32)]
+
+
+def gen_networks():
+    net, tf = refload.reference_networks()
+    out = {}
+    for func, n in [('E_zg', 2), ('E_zl', 2), ('G_res', 2), ('D_patch', 8)]:
+        rng = np.random.RandomState(1000)                       # config.py:75 random_seed
+        cfg = R.CONFIG[func]
+        params = R.init_params(func, rng, **cfg)
+        ins = network_inputs(func, rng, n)
+        tf.reset_default_graph(values={func + '/' + k: v for k, v in params.items()})
+        with tf.variable_scope(func):
+            res = getattr(net, func)(*[tf.convert_to_tensor(a) for a in ins], num_channels=3, resolution=128, **cfg)
+        res = res if isinstance(res, tuple) else (res,)
+        names = [k[len(func) + 1:] for k in tf.STORE.vars]
+        assert names == list(params.keys())
+        out[func + '_varnames'] = np.array(names)
+        for i, r in enumerate(res):
+            a = r.numpy()
+            out['%s_out%d_shape' % (func, i)] = np.array(a.shape, np.int64)
+            flat = a.reshape(-1)
+            out['%s_out%d' % (func, i)] = flat[::SUBSAMPLE] if flat.size > 4096 else flat
+            out['%s_out%d_absmax' % (func, i)] = np.array([np.abs(a).max()], np.float32)
+    np.savez_compressed(os.path.join(HERE, 'networks.npz'), **out)
+    print('networks.npz', {k: v.shape for k, v in out.items() if 'out' in k and 'shape' not in k})
+
+
+if __name__ == '__main__':
+    assert refload.reference_available(), 'needs /root/reference'
+    gen_perm()
+    gen_mattes()
+    gen_networks()
