@@ -1,0 +1,198 @@
+/* tmx.h — C ABI of libtmx.so: the B200 (sm_100a) implementation of the
+ * TextureMixer hot path (conv encoders E_zg/E_zl -> latent tile blend ->
+ * residual generator G_res, discriminator D_patch).
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own (it is
+ * pure Python on TF 1.12); each entry point names the reference op it stands
+ * in for (file:line into ningyu1991/TextureMixer).  INTEGRATION.md shows the
+ * ctypes stub a reference maintainer adds.
+ *
+ * Conventions
+ *  - every function returns int: 0 = OK, <0 = argument/shape/arch error,
+ *    >0 = cudaError_t; never throws, never aborts.  tmx_last_error() returns a
+ *    thread-local human readable message for the last non-zero return.
+ *  - the CALLER owns every buffer (device pointers, plain sizes); the library
+ *    allocates nothing persistent except the opaque handle.
+ *  - all work is enqueued asynchronously on the caller's cudaStream_t (passed
+ *    as void*); no hidden synchronisation.  One handle per (device, thread).
+ *  - activations are fp32.  API-side layout is the reference's NCHW; the
+ *    internal layouts are
+ *       NHWC f32         [N][H][W][C]
+ *       SPLIT_BF16_HALO  two bf16 planes hi, lo with x ~= hi + lo (16 mantissa
+ *                        bits), each [N][H+2][W+2][C] with the REFLECT halo of
+ *                        networks.py:55 materialised (row -1 = row 1, ...), so
+ *                        that TMA boxes can fetch shifted 3x3 taps.
+ */
+#ifndef TMX_H_
+#define TMX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMX_ABI_VERSION 1
+
+typedef struct tmx_ctx* tmx_handle_t;
+typedef void* tmx_stream_t; /* cudaStream_t */
+
+/* error codes (<0) */
+#define TMX_OK 0
+#define TMX_ERR_ARG (-1)      /* null pointer / bad enum */
+#define TMX_ERR_SHAPE (-2)    /* unsupported or inconsistent shape */
+#define TMX_ERR_ARCH (-3)     /* device is not sm_100 */
+#define TMX_ERR_UNSUPPORTED (-4)
+#define TMX_ERR_DRIVER (-5)   /* driver entry point (cuTensorMapEncodeTiled) failed */
+
+int tmx_abi_version(void);
+const char* tmx_last_error(void);
+/* Create/destroy the per-device context (queries SM count, resolves the
+ * tensor-map encoder).  Fails with TMX_ERR_ARCH on anything but sm_100. */
+int tmx_create(int device, tmx_handle_t* out);
+int tmx_destroy(tmx_handle_t h);
+int tmx_device_info(tmx_handle_t h, int* sm_count, int* cc_major, int* cc_minor);
+/* Number of kernel launches this handle has enqueued so far (bench.py's gpu_launches). */
+int tmx_launch_count(tmx_handle_t h, uint64_t* count);
+
+/* ------------------------------------------------------------------ conv2d
+ * networks.py:48-56 conv2d (+ :26-33 wscale, :61-67 apply_bias, :72-75
+ * leaky_relu, :80-88 upscale2d in front, residual add of :437 behind).
+ * y = [residual +] lrelu( wscale * xcorr(reflect_pad(up2?(x)), w) + bias )      */
+#define TMX_CONV_LRELU 1u    /* max(alpha*x, x) after bias */
+#define TMX_CONV_RESIDUAL 2u /* y += residual (after activation; G_res :437 has none) */
+#define TMX_CONV_UP2_IN 4u   /* logical input = nearest-neighbour x2 of the stored input (FFMA only) */
+#define TMX_CONV_UP2_OUT 8u  /* split-plane output is written x2 upsampled (TC producer side of :448) */
+
+#define TMX_ALGO_AUTO 0
+#define TMX_ALGO_FFMA 1 /* CUDA-core fp32 implicit GEMM, NHWC f32 in/out */
+#define TMX_ALGO_TC 2   /* tcgen05 bf16x3 implicit GEMM, SPLIT_BF16_HALO in (64-channel K chunks, 128B swizzle) */
+#define TMX_ALGO_TC_K32 3 /* same, 32-channel K chunks (64B swizzle, deeper pipeline) */
+
+typedef struct {
+  int32_t N, H, W;   /* output size == logical input size (stride 1, 'same') */
+  int32_t Cin, Cout;
+  int32_t k;         /* 1 (VALID) or 3 (REFLECT pad 1) */
+  uint32_t flags;    /* TMX_CONV_* */
+  int32_t algo;      /* TMX_ALGO_* */
+  float wscale;      /* gain / sqrt(k*k*Cin), networks.py:28-30 (FFMA applies it; TC expects it folded by tmx_conv_weights_prepare) */
+  float lrelu_alpha; /* 0.2 */
+} tmx_conv_desc_t;
+
+typedef struct {
+  const float* x_f32;    /* FFMA: NHWC f32 [N][H][W][Cin] ([N][H/2][W/2][Cin] with UP2_IN) */
+  const uint16_t* x_hi;  /* TC: SPLIT_BF16_HALO planes [N][H+2][W+2][Cin] */
+  const uint16_t* x_lo;
+  const float* w;        /* FFMA: raw variable, HWIO [k][k][Cin][Cout] */
+  const uint16_t* w_hi;  /* TC: prepared planes [Cout][k*k*Cin] */
+  const uint16_t* w_lo;
+  const float* bias;     /* [Cout] or NULL */
+  const float* residual; /* NHWC f32 [N][H][W][Cout] or NULL */
+  float* y_f32;          /* NHWC f32 [N][H][W][Cout] or NULL */
+  uint16_t* y_hi;        /* SPLIT_BF16_HALO out [N][H+2][W+2][Cout] ([N][2H+2][2W+2][Cout] with UP2_OUT) or NULL */
+  uint16_t* y_lo;
+} tmx_conv_io_t;
+
+int tmx_conv2d_fwd(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_io_t* io, tmx_stream_t s);
+
+/* get_weight (networks.py:26-33) for the tensor-core path: w_hwio * wscale ->
+ * bf16 hi/lo planes laid out K-major [Cout][k*k*Cin], K index = (u*k+v)*Cin + c. */
+int tmx_conv_weights_prepare(tmx_handle_t h, const float* w_hwio, float wscale, int k, int Cin, int Cout,
+                             uint16_t* w_hi, uint16_t* w_lo, tmx_stream_t s);
+
+/* NHWC f32 -> SPLIT_BF16_HALO (tf.pad REFLECT of networks.py:55 materialised). */
+int tmx_split_halo_pack(tmx_handle_t h, const float* x_nhwc, uint16_t* hi, uint16_t* lo, int N, int H, int W, int C,
+                        tmx_stream_t s);
+/* SPLIT_BF16_HALO interior -> NHWC f32 (hi + lo), for tests and FFMA consumers. */
+int tmx_split_halo_unpack(tmx_handle_t h, const uint16_t* hi, const uint16_t* lo, float* y_nhwc, int N, int H, int W,
+                          int C, tmx_stream_t s);
+
+/* ------------------------------------------------------------------ pointwise / layout
+ * FromRGB: 1x1 conv from NCHW images (networks.py:226-228 fromrgb): y NHWC f32. */
+int tmx_fromrgb_fwd(tmx_handle_t h, const float* x_nchw, const float* w /*[Cin][Cout]*/, const float* bias,
+                    float wscale, float* y_nhwc, int N, int Cin, int H, int W, int Cout, int lrelu, float alpha,
+                    tmx_stream_t s);
+/* ToRGB: 1x1 conv to NCHW images + optional tanh (networks.py:454-457, :483). */
+int tmx_torgb_fwd(tmx_handle_t h, const float* x_nhwc, const float* w /*[Cin][Cout]*/, const float* bias,
+                  float wscale, float* y_nchw, int N, int H, int W, int Cin, int Cout, int apply_tanh,
+                  tmx_stream_t s);
+/* downscale2d (networks.py:131-136): 2x2 mean, NHWC f32 [N][H][W][C] -> [N][H/2][W/2][C]. */
+int tmx_avgpool2_fwd(tmx_handle_t h, const float* x, float* y, int N, int H, int W, int C, tmx_stream_t s);
+/* Layout moves between the reference's NCHW and the internal NHWC.  The NHWC
+ * side may be a channel slice [c_off, c_off+C) of a tensor with C_total channels
+ * (tf.concat of networks.py:423; mu/log_sigma split of :289-290, :381-382).
+ * If bcast_hw != 0 the NCHW source is [N][C][1][1] broadcast over H x W
+ * (tf.tile of loss.py:130). */
+int tmx_nchw_to_nhwc(tmx_handle_t h, const float* x_nchw, float* y_nhwc, int N, int C, int H, int W, int c_off,
+                     int C_total, int bcast_hw, tmx_stream_t s);
+int tmx_nhwc_to_nchw(tmx_handle_t h, const float* x_nhwc, float* y_nchw, int N, int C, int H, int W, int c_off,
+                     int C_total, tmx_stream_t s);
+
+/* ------------------------------------------------------------------ latent tile blend (K6)
+ * loss.py:92-100 tiling_permutation + tfutil.py:41-43 lerp + the matte sums of
+ * util_scripts.py:496,525 in one pass.  For every canvas element
+ *    out[n][c][i][j] = sum_k  m_k(i,j) * src_k[n][c][sy_k(i)][sx_k(j)]
+ * with K <= 4 sources, sy_k(i) = idx_h[k][n][i] % h, sx_k(j) = idx_w[k][n][j] % w
+ * (identity i % h, j % w when the index pointer is NULL).  Re-pinned tiles:
+ * canvas positions whose tile row i/h is in the bit set pin_rows AND whose tile
+ * column j/w is in pin_cols read src[i % h][j % w] instead - the four corners
+ * of loss.py:96-100 / util_scripts.py:747-750 are rows {0,sh-1} x cols {0,sw-1};
+ * the interpolation app (util_scripts.py:1433-1437) pins row sh/2 x cols {0,sw-1}.
+ * Sources are NCHW f32 [N][C][h][w] ([N][C][1][1] if src_bcast: the tiled
+ * global code).
+ * Weights:
+ *   mode TMX_BLEND_MATTE: m_k(i,j) = ramp_h[k][i] * ramp_w[k][j] as float64
+ *       products/sums in the reference's left-to-right order, one final
+ *       rounding to f32 (numpy promotion in util_scripts.py:496) - bit exact.
+ *       With math_f32 the ramps hold float32 values and every op is a
+ *       separately rounded f32 op (the float32 matte of util_scripts.py:85-89
+ *       used at :1337-1342, :1438-1439).
+ *   mode TMX_BLEND_LERP : K == 2, out = a + (b - a) * t[n] in f32 with
+ *       separately rounded sub/mul/add (tfutil.py:41-43), a = source 0.
+ *   mode TMX_BLEND_COPY : K == 1, plain gather.
+ * Output: NCHW f32 [N][C][H][W] (the reference-facing canvas) when out_nchw !=
+ * NULL, and/or NHWC f32 slice (c_off, C_total) when out_nhwc != NULL. */
+#define TMX_BLEND_COPY 0
+#define TMX_BLEND_MATTE 1
+#define TMX_BLEND_LERP 2
+
+typedef struct {
+  int32_t N, C, h, w; /* source tile */
+  int32_t H, W;       /* canvas */
+  int32_t K;          /* sources, 1..4 */
+  int32_t mode;       /* TMX_BLEND_* */
+  int32_t math_f32;   /* MATTE: f32 arithmetic instead of f64 */
+  int32_t src_bcast;  /* sources are [N][C][1][1] */
+  uint32_t src_reverse; /* bit k: source k reads sample N-1-n (tf.reverse(axis=[0]) of loss.py:218,224,236) */
+  uint64_t pin_rows, pin_cols; /* tile-row / tile-column bit sets of re-pinned tiles (0 = none) */
+  int32_t c_off, C_total; /* NHWC output slice */
+} tmx_blend_desc_t;
+
+typedef struct {
+  const float* src[4];
+  const int32_t* idx_h[4]; /* [N][H] or NULL */
+  const int32_t* idx_w[4]; /* [N][W] or NULL */
+  const double* ramp_h[4]; /* [H] (MATTE) */
+  const double* ramp_w[4]; /* [W] (MATTE) */
+  const float* t;          /* [N]  (LERP) */
+  float* out_nchw;
+  float* out_nhwc;
+} tmx_blend_io_t;
+
+int tmx_latent_blend(tmx_handle_t h, const tmx_blend_desc_t* d, const tmx_blend_io_t* io, tmx_stream_t s);
+
+/* ------------------------------------------------------------------ permutation sampler (host)
+ * run.py:107-182 (my_swap_h / my_swap_w / block_permutation) as driven by
+ * run.py:436-507, in index-vector form: writes `count` int32 vectors of `length`
+ * entries; vector r means P_h[i, r[i]] = 1 (row map) or P_w[r[j], j] = 1
+ * (column map) - both obey the same recurrence.  `u` holds uniforms pre-drawn
+ * from the caller's RNG in the reference's draw order (2*(length>>l) per level l
+ * with length>>l > 1); *consumed returns how many were used.  Host only, no GPU. */
+int tmx_perm_indices_from_uniforms(const double* u, int64_t n_u, int length, int levels, int count, int32_t* out,
+                                   int64_t* consumed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMX_H_ */

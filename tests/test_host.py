@@ -1,0 +1,179 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every
+symbol include/tmx.h declares, the host permutation sampler (C) is bit-exact
+against the reference-generated goldens, mattes match, the `Network` boundary
+mirrors the reference's template-graph bookkeeping, and the product fails
+loudly without a GPU (no CPU fallback)."""
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+CFG = dict(
+    E_zg=dict(fmap_base=1024, fmap_max=512, latent_channels=128, use_pixelnorm=False, tanh_at_end=False),
+    E_zl=dict(fmap_base=1024, fmap_max=512, latent_res=32, latent_channels=128, use_pixelnorm=False,
+              tanh_at_end=False),
+    G_res=dict(fmap_base=1024, fmap_max=512, latent_res=32, latent_channels=128, use_pixelnorm=False,
+               tanh_at_end=True),
+    D_patch=dict(fmap_base=1024, fmap_max=512, latent_res=-1),
+)
+
+
+@pytest.fixture(scope='module')
+def built():
+    from texturemixer_b200 import build
+    return build.build_library()
+
+
+def test_library_exports_every_declared_symbol(built):
+    import ctypes
+    from texturemixer_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'tmx.h')).read()
+    declared = set(re.findall(r'\b(tmx_[a-z0-9_]+)\s*\(', hdr))
+    assert declared, 'no declarations found'
+    lib = ctypes.CDLL(built)
+    for name in sorted(declared):
+        assert hasattr(lib, name), 'libtmx.so does not export %s' % name
+    assert declared == set(_lib.EXPORTED_SYMBOLS), (declared ^ set(_lib.EXPORTED_SYMBOLS))
+    assert _lib.load().tmx_abi_version() == _lib.TMX_ABI_VERSION
+
+
+@pytest.mark.parametrize('tag', ['train96', 'interp128', 'small8', 'tiny2', 'wide256'])
+def test_c_sampler_bit_exact_vs_reference_golden(built, tag):
+    from texturemixer_b200 import interp
+    g = np.load(os.path.join(GOLDEN, 'perm_sampler.npz'))
+    length, levels, count, seed = (int(v) for v in g[tag + '_meta'])
+    np.random.seed(seed)
+    hs = interp.sample_permutation_indices(count, length, levels)
+    ws = interp.sample_permutation_indices(count, length, levels)
+    assert hs.dtype == np.int32 and np.array_equal(hs, g[tag + '_h'])
+    assert np.array_equal(ws, g[tag + '_w'])
+    assert np.random.uniform() == g[tag + '_next_uniform'][0]      # same number of draws consumed
+
+
+def test_c_sampler_schedule_order_and_errors(built):
+    from texturemixer_b200 import interp
+    from texturemixer_b200.runtime import perm_indices_from_uniforms, uniforms_per_matrix
+    assert uniforms_per_matrix(96, 5) == 372
+    np.random.seed(1000)
+    s = interp.sample_schedule_indices(2, latent_res=32, scale_h=3, scale_w=3)
+    assert list(s.keys()) == ['h_forward', 'w_forward', 'h_backward', 'w_backward']
+    g = np.load(os.path.join(GOLDEN, 'perm_sampler.npz'))
+    assert np.array_equal(s['h_forward'], g['train96_h'][:2])
+    with pytest.raises(RuntimeError, match='uniforms needed'):
+        perm_indices_from_uniforms(np.zeros(10), 96, 5, 1)
+    with pytest.raises(RuntimeError, match='divisible'):
+        perm_indices_from_uniforms(np.zeros(1000), 6, 3, 1)
+    idx, used = perm_indices_from_uniforms(np.zeros(0), 1, 1, 2)     # degenerate length: no draws
+    assert used == 0 and idx.tolist() == [[0], [0]]
+
+
+def test_indices_from_matrices():
+    from texturemixer_b200 import interp
+    r = np.array([[2, 0, 1]], np.int32)
+    c = np.array([[1, 2, 0]], np.int32)
+    ph = np.zeros((1, 1, 3, 3), np.float32)
+    pw = np.zeros((1, 1, 3, 3), np.float32)
+    ph[0, 0, np.arange(3), r[0]] = 1
+    pw[0, 0, c[0], np.arange(3)] = 1
+    r2, c2 = interp.indices_from_matrices(ph, pw)
+    assert np.array_equal(r, r2) and np.array_equal(c, c2)
+
+
+def test_mattes_bit_exact_vs_reference_golden():
+    from texturemixer_b200 import interp
+    g = np.load(os.path.join(GOLDEN, 'mattes.npz'))
+    for key in g.files:
+        parts = key.split('_')
+        if parts[0] == 'arb':
+            h, w, r = (int(p) for p in parts[1:])
+            mine = np.stack(interp.linkern_for_weight_arbitrary_shape(h, w, r))
+            assert mine.dtype == np.float64 and np.array_equal(mine, g[key])
+        else:
+            shape = [int(p) for p in parts[1:5]]
+            mine = interp.linkern_for_weight_horizontal(shape, int(parts[5]))
+            assert mine.dtype == np.float32 and np.array_equal(mine, g[key])
+
+
+@pytest.mark.parametrize('func', ['E_zg', 'E_zl', 'G_res', 'D_patch'])
+def test_template_graph_matches_reference_variables(func):
+    """Variable names + creation order equal those of the reference's networks.py
+    (golden minted by running it, tests/golden/make_golden.py)."""
+    from texturemixer_b200.network import Network
+    g = np.load(os.path.join(GOLDEN, 'networks.npz'))
+    net = Network(func, func='networks.' + func, device='cpu', seed=0, num_channels=3, resolution=128, **CFG[func])
+    assert list(net.vars.keys()) == [str(s) for s in g[func + '_varnames']]
+    assert 'lod' not in net.trainables and len(net.trainables) == len(net.vars) - 1
+    shapes = {'E_zg': ([[None, 3, 128, 128]], [[None, 128, 1, 1]] * 2, ['zg_mu', 'zg_log_sigma']),
+              'E_zl': ([[None, 3, 128, 128]], [[None, 128, 32, 32]] * 2, ['z_mu', 'z_log_sigma']),
+              'G_res': ([[None, 128, 32, 32]] * 2, [[None, 3, 128, 128]], ['images_out']),
+              'D_patch': ([[None, 3, 128, 128]], [[None, 1, 1, 1]], ['scores_out'])}[func]
+    assert net.input_shapes == shapes[0] and net.output_shapes == shapes[1] and net.output_names == shapes[2]
+
+
+def test_network_boundary_bookkeeping():
+    from texturemixer_b200.network import Network
+    G = Network('G', func='networks.G_res', device='cpu', seed=1, num_channels=3, resolution=128, **CFG['G_res'])
+    assert G.input_names == ['zg_latents_in', 'zl_latents_in'] and G.num_outputs == 1
+    n_train = sum(v.size for v in G.trainables.values())
+    assert n_train == 6119955 + (32 * 3 + 3) + (64 * 3 + 3)            # SURVEY a6 + unused lod heads
+    # fully-convolutional second view over the same scope (run.py:273)
+    G_fcn = Network('G', func='networks.G_res', reuse=True, share_vars_with=G, device='cpu', num_channels=3,
+                    resolution=128, scale_h=3, scale_w=3, **CFG['G_res'])
+    assert G_fcn.vars is G.vars and G_fcn.input_shape == [None, 128, 96, 96]
+    assert G_fcn.output_shape == [None, 3, 384, 384]
+    # clone + EMA (tfutil.py:579-589, 611-621)
+    Gs = G.clone('Gs')
+    assert Gs.name == 'Gs' and np.array_equal(Gs.get_var('32x32/Conv0/weight'), G.get_var('32x32/Conv0/weight'))
+    G.set_var('32x32/Conv0/bias', np.ones(64, np.float32))
+    Gs.setup_as_moving_average_of(G, beta=0.75)()
+    assert np.allclose(Gs.get_var('32x32/Conv0/bias'), 0.25)
+    # version-2 pickle state (tfutil.py:543-550) round trip
+    state = G.__getstate__()
+    assert state['version'] == 2 and state['build_func_name'] == 'G_res'
+    assert [k for k, _ in state['variables']] == list(G.vars.keys())
+    G2 = pickle.loads(pickle.dumps(G))
+    assert np.array_equal(G2.get_var('ToRGB_lod0/weight'), G.get_var('ToRGB_lod0/weight'))
+    with pytest.raises(AssertionError):
+        Network('bad', func='networks.G_res', device='cpu', num_channels=3, resolution=100, **CFG['G_res'])
+    with pytest.raises(NotImplementedError):
+        Network('bad', func='networks.G_res', device='cpu', num_channels=3, resolution=128, fused_scale=True,
+                **CFG['G_res'])
+
+
+def test_aliases_resolve():
+    from texturemixer_b200 import network
+    from texturemixer_b200 import networks
+    assert network.import_obj('networks.G_res') is networks.G_res
+    assert network.import_obj('networks.build_generator') is networks.build_generator
+    E = network.Network('E', func='networks.build_encoder', device='cpu', kind='zl', num_channels=3, resolution=128,
+                        **CFG['E_zl'])
+    assert E.output_names == ['z_mu', 'z_log_sigma']
+
+
+def test_no_cpu_fallback():
+    """Without CUDA the product path must raise, not compute."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from texturemixer_b200.network import Network
+    from texturemixer_b200.runtime import Runtime
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        Runtime.get()
+    G = Network('G', func='networks.G_res', device='cpu', seed=1, num_channels=3, resolution=128, **CFG['G_res'])
+    z = np.zeros((1, 128, 32, 32), np.float32)
+    with pytest.raises(RuntimeError):
+        G.run(z, z)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'texturemixer_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), f

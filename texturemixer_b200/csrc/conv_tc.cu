@@ -1,0 +1,525 @@
+// conv_tc.cu — tcgen05 implicit-GEMM convolution for sm_100a.
+//
+//   y = [residual +] lrelu(xcorr3x3_reflect(x, w) + bias)        (networks.py:48-75, :437)
+//
+// GEMM view per CTA tile: D[128 pixels][BN couts] += A[128][K] * B[BN][K]^T with
+// K = taps * Cin walked as (tap, 64- or 32-channel chunk).
+//   A  = activations in SPLIT_BF16_HALO layout ([N][H+2][W+2][C] bf16, hi and lo
+//        planes).  A tap (u,v) of a bw x bh x bn pixel patch is ONE 4-D TMA box at
+//        coordinates (c0, x0+v, y0+u, n0) - the reflect halo is materialised, so
+//        no boundary logic exists in the main loop.  The box lands in shared
+//        memory K-major with the 128B/64B hardware swizzle = the canonical UMMA
+//        operand layout.
+//   B  = weights prepared once as K-major [Cout][taps*Cin] bf16 hi/lo planes
+//        (tmx_conv_weights_prepare), one 2-D TMA box per step.
+//   D  = fp32 accumulators in TMEM (2 stages x BN columns) so the epilogue of
+//        tile i overlaps the main loop of tile i+1.
+// fp32 parity: x*w ~= xh*wh + xh*wl + xl*wh (bf16x3, fp32 accumulate): 16-17
+// mantissa bits per product, three kind::f16 MMAs per K step; measured error is
+// ~1e-5 relative on G_res vs 1.8e-3 for single-pass TF32.
+//
+// Warp roles (256 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0 lane 0 : TMA producer     warp 1 lane 0 : MMA issuer
+//   warp 2        : TMEM allocator   warps 4-7     : epilogue (TMEM -> regs -> HBM)
+// Epilogue fusions: bias, leaky-ReLU, residual add (fp32 stream), fp32 NHWC
+// store, re-split into bf16 hi/lo planes INCLUDING the reflect halo of the next
+// layer (edge threads store their pixel to the mirrored halo slots too) and
+// optional nearest-neighbour x2 upsampling of the written planes.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 inputs, fp32 accumulate.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when all previously issued MMAs of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------- descriptors
+// Shared-memory matrix descriptor, K-major operand, hardware swizzle:
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major: 1) | [32,46) SBO>>4
+//   [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+// SBO = byte distance between 8-row groups = 8 * row_bytes (rows are dense).
+template <int KC>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  constexpr uint64_t row_bytes = KC * 2;
+  constexpr uint64_t layout = (KC == 64) ? 2 : 4;
+  return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | (((8 * row_bytes) >> 4) << 32) | (1ull << 46) |
+         (layout << 61);
+}
+// Instruction descriptor (kind::f16): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+// A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+template <int BN>
+__host__ __device__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+struct ConvTcParams {
+  int N, H, W, Cin, Cout;
+  int taps, k, pad_off;   // pad_off = 1 - k/2: halo offset of tap 0
+  int bw, bh, bn;         // pixel patch of a tile: bw*bh*bn == 128
+  int tiles_x, tiles_y, tiles_n, tiles_c, num_tiles;
+  int lrelu, has_res, up2_out;
+  float alpha;
+  const float* bias;
+  const float* residual;
+  float* y_f32;
+  uint16_t* y_hi;
+  uint16_t* y_lo;
+};
+
+template <int BN, int KC>
+struct TcCfg {
+  static constexpr int kABytes = kTileM * KC * 2;
+  static constexpr int kBBytes = BN * KC * 2;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kSmemBudget = 200 * 1024;
+  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
+  static constexpr int kAuxBytes = 1024;  // barriers + tmem ptr
+  static constexpr int kSmemBytes = kStages * kStageBytes + kAuxBytes + 1024 /*align slack*/;
+  static_assert(kStages >= 2, "need at least a double buffer");
+  static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns: power of two <= 512");
+};
+
+template <int BN, int KC>
+__global__ void __launch_bounds__(kThreads, 1)
+    conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                   const ConvTcParams p) {
+  using Cfg = TcCfg<BN, KC>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* tfull_bar = empty_bar + S;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cchunks = p.Cin / KC;
+  const int ksteps = p.taps * cchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_b_hi);
+    tma_prefetch_desc(&tm_b_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int cblk = tile % p.tiles_c;
+        int t = tile / p.tiles_c;
+        const int x0 = (t % p.tiles_x) * p.bw;
+        t /= p.tiles_x;
+        const int y0 = (t % p.tiles_y) * p.bh;
+        const int n0 = (t / p.tiles_y) * p.bn;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int tap = ks / cchunks;
+          const int c0 = (ks - tap * cchunks) * KC;
+          const int u = tap / p.k, v = tap - u * p.k;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_4d(sa, &tm_a_hi, &full_bar[stage], c0, x0 + v + p.pad_off, y0 + u + p.pad_off, n0);
+          tma_load_4d(sa + Cfg::kABytes, &tm_a_lo, &full_bar[stage], c0, x0 + v + p.pad_off, y0 + u + p.pad_off, n0);
+          tma_load_2d(sa + 2 * Cfg::kABytes, &tm_b_hi, &full_bar[stage], tap * p.Cin + c0, cblk * BN);
+          tma_load_2d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tm_b_lo, &full_bar[stage], tap * p.Cin + c0, cblk * BN);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * Cfg::kStageBytes);
+          const uint64_t a_hi = make_smem_desc<KC>(sa);
+          const uint64_t a_lo = make_smem_desc<KC>(sa + Cfg::kABytes);
+          const uint64_t b_hi = make_smem_desc<KC>(sa + 2 * Cfg::kABytes);
+          const uint64_t b_lo = make_smem_desc<KC>(sa + 2 * Cfg::kABytes + Cfg::kBBytes);
+#pragma unroll
+          for (int kk = 0; kk < KC / 16; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 2);  // +32 B along K inside the swizzle row, >>4
+            // small terms first, then the dominant hi*hi product
+            umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, (ks | kk) != 0);
+            umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
+            umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, 1);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may read
+    const int r = quad * 32 + lane;       // row of the tile = pixel
+    const int in_ = r / (p.bh * p.bw);
+    const int rem = r - in_ * (p.bh * p.bw);
+    const int iy = rem / p.bw, ix = rem - iy * p.bw;
+    const int Ho = p.up2_out ? 2 * p.H : p.H, Wo = p.up2_out ? 2 * p.W : p.W;
+    const long long Hp = Ho + 2, Wp = Wo + 2;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int cblk = tile % p.tiles_c;
+      int t = tile / p.tiles_c;
+      const int x = (t % p.tiles_x) * p.bw + ix;
+      t /= p.tiles_x;
+      const int y = (t % p.tiles_y) * p.bh + iy;
+      const int n = (t / p.tiles_y) * p.bn + in_;
+      const bool valid = n < p.N;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+
+      // target rows / cols of the split planes (interior + mirrored halo slots)
+      int rows[4], cols[4], nrows = 0, ncols = 0;
+      if (p.y_hi != nullptr) {
+        const int reps = p.up2_out ? 2 : 1;
+        for (int d = 0; d < reps; ++d) {
+          const int Y = p.up2_out ? 2 * y + d : y;
+          rows[nrows++] = Y + 1;
+          if (Y == 1) rows[nrows++] = 0;
+          if (Y == Ho - 2) rows[nrows++] = Ho + 1;
+          const int X = p.up2_out ? 2 * x + d : x;
+          cols[ncols++] = X + 1;
+          if (X == 1) cols[ncols++] = 0;
+          if (X == Wo - 2) cols[ncols++] = Wo + 1;
+        }
+      }
+
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+      const long long pix = ((long long)n * p.H + y) * p.W + x;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t acc[32];
+        tmem_ld32(taddr0 + ch * 32, acc);
+        tmem_ld_wait();
+        if (valid) {
+          const int cbase = cblk * BN + ch * 32;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float f = __uint_as_float(acc[j]) + (p.bias ? __ldg(p.bias + cbase + j) : 0.f);
+            if (p.lrelu) f = fmaxf(f * p.alpha, f);
+            v[j] = f;
+          }
+          if (p.has_res) {
+            const float4* rp = reinterpret_cast<const float4*>(p.residual + pix * p.Cout + cbase);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 rr = __ldg(rp + j);
+              v[4 * j] += rr.x;
+              v[4 * j + 1] += rr.y;
+              v[4 * j + 2] += rr.z;
+              v[4 * j + 3] += rr.w;
+            }
+          }
+          if (p.y_f32 != nullptr) {
+            float4* op = reinterpret_cast<float4*>(p.y_f32 + pix * p.Cout + cbase);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (p.y_hi != nullptr) {
+            uint32_t ph[16], pl[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              uint32_t h0, l0, h1, l1;
+              tmx_split_bf16(v[2 * j], h0, l0);
+              tmx_split_bf16(v[2 * j + 1], h1, l1);
+              ph[j] = h0 | (h1 << 16);
+              pl[j] = l0 | (l1 << 16);
+            }
+            for (int a = 0; a < nrows; ++a) {
+              for (int b = 0; b < ncols; ++b) {
+                const long long o = (((long long)n * Hp + rows[a]) * Wp + cols[b]) * p.Cout + cbase;
+                uint4* oh = reinterpret_cast<uint4*>(p.y_hi + o);
+                uint4* ol = reinterpret_cast<uint4*>(p.y_lo + o);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  oh[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+                  ol[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+int encode_act_map(tmx_handle_t h, CUtensorMap* m, const uint16_t* base, int N, int Hp, int Wp, int C, int kc, int bw,
+                   int bh, int bn) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = h->encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return tmx_fail(TMX_ERR_DRIVER, "cuTensorMapEncodeTiled(activations) failed: CUresult %d (C=%d Wp=%d Hp=%d N=%d box %d,%d,%d,%d)",
+                    (int)r, C, Wp, Hp, N, kc, bw, bh, bn);
+  return TMX_OK;
+}
+
+int encode_wgt_map(tmx_handle_t h, CUtensorMap* m, const uint16_t* base, int Cout, int K, int kc, int bnc) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)bnc};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = h->encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return tmx_fail(TMX_ERR_DRIVER, "cuTensorMapEncodeTiled(weights) failed: CUresult %d (K=%d Cout=%d box %d,%d)",
+                    (int)r, K, Cout, kc, bnc);
+  return TMX_OK;
+}
+
+int gcd_pow2(int v, int cap) {  // largest power of two dividing v, at most cap
+  int g = 1;
+  while (g < cap && (v % (g * 2)) == 0) g *= 2;
+  return g;
+}
+
+template <int BN, int KC>
+int launch_tc(tmx_handle_t h, const CUtensorMap* maps, const ConvTcParams& p, cudaStream_t st) {
+  using Cfg = TcCfg<BN, KC>;
+  auto kern = conv_tc_kernel<BN, KC>;
+  static thread_local int configured_device = -1;
+  if (configured_device != h->device) {
+    TMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured_device = h->device;
+  }
+  TMX_REQUIRE(Cfg::kSmemBytes <= h->max_smem_optin, TMX_ERR_UNSUPPORTED,
+              "tmx_conv2d_fwd[TC]: kernel needs %d B shared memory, device allows %d", Cfg::kSmemBytes,
+              h->max_smem_optin);
+  int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
+  kern<<<grid, kThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  TMX_LAUNCHED(h, "conv_tc_kernel");
+  return TMX_OK;
+}
+
+}  // namespace
+
+int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_io_t* io, int kc, cudaStream_t st) {
+  TMX_REQUIRE(io->x_hi && io->x_lo && io->w_hi && io->w_lo, TMX_ERR_ARG,
+              "tmx_conv2d_fwd[TC]: x_hi/x_lo (SPLIT_BF16_HALO) and w_hi/w_lo (prepared) are required");
+  TMX_REQUIRE(io->y_f32 || (io->y_hi && io->y_lo), TMX_ERR_ARG, "tmx_conv2d_fwd[TC]: no output");
+  TMX_REQUIRE((io->y_hi == nullptr) == (io->y_lo == nullptr), TMX_ERR_ARG,
+              "tmx_conv2d_fwd[TC]: y_hi and y_lo go together");
+  TMX_REQUIRE(!(d->flags & TMX_CONV_UP2_IN), TMX_ERR_UNSUPPORTED,
+              "tmx_conv2d_fwd[TC]: UP2_IN is not supported; use UP2_OUT on the producing layer");
+  TMX_REQUIRE(!(d->flags & TMX_CONV_UP2_OUT) || io->y_hi, TMX_ERR_ARG,
+              "tmx_conv2d_fwd[TC]: UP2_OUT applies to the split-plane output");
+  TMX_REQUIRE(!(d->flags & TMX_CONV_RESIDUAL) || io->residual, TMX_ERR_ARG,
+              "tmx_conv2d_fwd[TC]: RESIDUAL flag without residual pointer");
+  TMX_REQUIRE(kc == 64 || kc == 32, TMX_ERR_ARG, "tmx_conv2d_fwd[TC]: K chunk must be 32 or 64");
+  TMX_REQUIRE(d->Cin % kc == 0, TMX_ERR_SHAPE, "tmx_conv2d_fwd[TC]: Cin=%d must be a multiple of %d", d->Cin, kc);
+  TMX_REQUIRE(d->H >= 2 && d->W >= 2, TMX_ERR_SHAPE, "tmx_conv2d_fwd[TC]: H, W >= 2 (REFLECT)");
+  int bnc;
+  if (d->Cout % 256 == 0) bnc = 256;
+  else if (d->Cout % 128 == 0) bnc = 128;
+  else if (d->Cout % 64 == 0) bnc = 64;
+  else if (d->Cout % 32 == 0) bnc = 32;
+  else return tmx_fail(TMX_ERR_SHAPE, "tmx_conv2d_fwd[TC]: Cout=%d must be a multiple of 32", d->Cout);
+
+  ConvTcParams p;
+  p.N = d->N;
+  p.H = d->H;
+  p.W = d->W;
+  p.Cin = d->Cin;
+  p.Cout = d->Cout;
+  p.k = d->k;
+  p.taps = d->k * d->k;
+  p.pad_off = 1 - d->k / 2;
+  p.bw = gcd_pow2(d->W, 32);
+  p.bh = gcd_pow2(d->H, kTileM / p.bw);
+  p.bn = kTileM / (p.bw * p.bh);
+  p.tiles_x = d->W / p.bw;
+  p.tiles_y = d->H / p.bh;
+  p.tiles_n = (d->N + p.bn - 1) / p.bn;
+  p.tiles_c = d->Cout / bnc;
+  long long nt = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_c;
+  TMX_REQUIRE(nt < (1ll << 31), TMX_ERR_SHAPE, "tmx_conv2d_fwd[TC]: too many tiles");
+  p.num_tiles = (int)nt;
+  p.lrelu = (d->flags & TMX_CONV_LRELU) != 0;
+  p.has_res = (d->flags & TMX_CONV_RESIDUAL) != 0;
+  p.up2_out = (d->flags & TMX_CONV_UP2_OUT) != 0;
+  p.alpha = d->lrelu_alpha;
+  p.bias = io->bias;
+  p.residual = io->residual;
+  p.y_f32 = io->y_f32;
+  p.y_hi = io->y_hi;
+  p.y_lo = io->y_lo;
+
+  CUtensorMap maps[4];
+  int rc;
+  if ((rc = encode_act_map(h, &maps[0], io->x_hi, d->N, d->H + 2, d->W + 2, d->Cin, kc, p.bw, p.bh, p.bn))) return rc;
+  if ((rc = encode_act_map(h, &maps[1], io->x_lo, d->N, d->H + 2, d->W + 2, d->Cin, kc, p.bw, p.bh, p.bn))) return rc;
+  if ((rc = encode_wgt_map(h, &maps[2], io->w_hi, d->Cout, p.taps * d->Cin, kc, bnc))) return rc;
+  if ((rc = encode_wgt_map(h, &maps[3], io->w_lo, d->Cout, p.taps * d->Cin, kc, bnc))) return rc;
+
+#define TMX_TC_CASE(BN_, KC_) \
+  if (bnc == BN_ && kc == KC_) return launch_tc<BN_, KC_>(h, maps, p, st);
+  TMX_TC_CASE(256, 64)
+  TMX_TC_CASE(256, 32)
+  TMX_TC_CASE(128, 64)
+  TMX_TC_CASE(128, 32)
+  TMX_TC_CASE(64, 64)
+  TMX_TC_CASE(64, 32)
+  TMX_TC_CASE(32, 64)
+  TMX_TC_CASE(32, 32)
+#undef TMX_TC_CASE
+  return tmx_fail(TMX_ERR_UNSUPPORTED, "tmx_conv2d_fwd[TC]: no kernel for BN=%d KC=%d", bnc, kc);
+}

@@ -1,0 +1,468 @@
+// pointwise.cu — HBM-bound kernels of the TextureMixer hot path: 1x1 RGB heads,
+// 2x2 average pool, NCHW<->NHWC moves, split-bf16 halo pack/unpack, weight
+// preparation and the latent tile gather/blend (K6).  All are written for
+// coalesced 128-bit accesses; none has data reuse worth a TMA pipeline.
+#include "common.cuh"
+
+// ---------------------------------------------------------------- FromRGB
+// networks.py:226-228: act(bias + conv1x1(x)), x NCHW [N][Cin][H][W] -> y NHWC.
+// One thread = one pixel x 4 output channels; 4 (Cout=16) consecutive threads
+// write one pixel's contiguous 64 B.
+__global__ void __launch_bounds__(256) fromrgb_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, float wscale,
+                                                      float* __restrict__ y, long long npix, int HW, int Cin,
+                                                      int Cout, int lrelu, float alpha) {
+  const int groups = Cout >> 2;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = npix * groups;
+  if (t >= total) return;
+  int g = (int)(t % groups);
+  long long p = t / groups;
+  long long n = p / HW;
+  int hw = (int)(p % HW);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* xp = x + n * (long long)Cin * HW + hw;
+  for (int c = 0; c < Cin; ++c) {
+    float xv = __ldg(xp + (long long)c * HW);
+    float4 wv = __ldg(reinterpret_cast<const float4*>(w + c * Cout + g * 4));
+    acc[0] = fmaf(xv, wv.x, acc[0]);
+    acc[1] = fmaf(xv, wv.y, acc[1]);
+    acc[2] = fmaf(xv, wv.z, acc[2]);
+    acc[3] = fmaf(xv, wv.w, acc[3]);
+  }
+  float4 o;
+  float* op = &o.x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v = acc[i] * wscale + (bias ? __ldg(bias + g * 4 + i) : 0.f);
+    if (lrelu) v = fmaxf(v * alpha, v);
+    op[i] = v;
+  }
+  *reinterpret_cast<float4*>(y + p * Cout + g * 4) = o;
+}
+
+extern "C" int tmx_fromrgb_fwd(tmx_handle_t h, const float* x, const float* w, const float* bias, float wscale,
+                               float* y, int N, int Cin, int H, int W, int Cout, int lrelu, float alpha,
+                               tmx_stream_t s) {
+  TMX_REQUIRE(h && x && w && y, TMX_ERR_ARG, "tmx_fromrgb_fwd: NULL argument");
+  TMX_REQUIRE(N > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0 && Cout % 4 == 0, TMX_ERR_SHAPE,
+              "tmx_fromrgb_fwd: bad shape N=%d Cin=%d H=%d W=%d Cout=%d (Cout %% 4 == 0)", N, Cin, H, W, Cout);
+  long long npix = (long long)N * H * W;
+  long long total = npix * (Cout / 4);
+  fromrgb_kernel<<<tmx_ceil_div(total, 256), 256, 0, (cudaStream_t)s>>>(x, w, bias, wscale, y, npix, H * W, Cin, Cout,
+                                                                       lrelu, alpha);
+  TMX_LAUNCHED(h, "fromrgb_kernel");
+  return TMX_OK;
+}
+
+// ---------------------------------------------------------------- ToRGB
+// networks.py:454-457 (+ tanh :483): x NHWC [N][H][W][Cin] -> y NCHW [N][Cout<=4][H][W].
+// One thread = one pixel: reads Cin*4 contiguous bytes, writes Cout coalesced planes.
+template <int COUT>
+__global__ void __launch_bounds__(256) torgb_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                    const float* __restrict__ bias, float wscale,
+                                                    float* __restrict__ y, long long npix, int HW, int Cin,
+                                                    int apply_tanh) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+  const float4* xp = reinterpret_cast<const float4*>(x + p * Cin);
+  for (int c4 = 0; c4 < (Cin >> 2); ++c4) {
+    float4 xv = __ldg(xp + c4);
+    const float* xs = &xv.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) acc[o] = fmaf(xs[i], __ldg(w + (c4 * 4 + i) * COUT + o), acc[o]);
+    }
+  }
+  long long n = p / HW;
+  int hw = (int)(p % HW);
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) {
+    float v = acc[o] * wscale + (bias ? __ldg(bias + o) : 0.f);
+    if (apply_tanh) v = tanhf(v);
+    y[(n * COUT + o) * HW + hw] = v;
+  }
+}
+
+extern "C" int tmx_torgb_fwd(tmx_handle_t h, const float* x, const float* w, const float* bias, float wscale, float* y,
+                             int N, int H, int W, int Cin, int Cout, int apply_tanh, tmx_stream_t s) {
+  TMX_REQUIRE(h && x && w && y, TMX_ERR_ARG, "tmx_torgb_fwd: NULL argument");
+  TMX_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cin % 4 == 0 && Cout >= 1 && Cout <= 4, TMX_ERR_SHAPE,
+              "tmx_torgb_fwd: bad shape N=%d H=%d W=%d Cin=%d Cout=%d (Cin %% 4 == 0, 1 <= Cout <= 4)", N, H, W, Cin,
+              Cout);
+  long long npix = (long long)N * H * W;
+  dim3 grid(tmx_ceil_div(npix, 256));
+  cudaStream_t st = (cudaStream_t)s;
+  switch (Cout) {
+    case 1: torgb_kernel<1><<<grid, 256, 0, st>>>(x, w, bias, wscale, y, npix, H * W, Cin, apply_tanh); break;
+    case 2: torgb_kernel<2><<<grid, 256, 0, st>>>(x, w, bias, wscale, y, npix, H * W, Cin, apply_tanh); break;
+    case 3: torgb_kernel<3><<<grid, 256, 0, st>>>(x, w, bias, wscale, y, npix, H * W, Cin, apply_tanh); break;
+    default: torgb_kernel<4><<<grid, 256, 0, st>>>(x, w, bias, wscale, y, npix, H * W, Cin, apply_tanh); break;
+  }
+  TMX_LAUNCHED(h, "torgb_kernel");
+  return TMX_OK;
+}
+
+// ---------------------------------------------------------------- avg pool 2x2
+// networks.py:131-136.  NHWC; one thread = one output pixel x 4 channels.
+__global__ void __launch_bounds__(256) avgpool2_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                       long long total, int Ho, int Wo, int C4) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int c4 = (int)(t % C4);
+  long long p = t / C4;
+  int xo = (int)(p % Wo);
+  long long q = p / Wo;
+  int yo = (int)(q % Ho);
+  long long n = q / Ho;
+  int W = Wo * 2;
+  const float4* base = reinterpret_cast<const float4*>(x) + ((n * (Ho * 2) + yo * 2) * W + xo * 2) * C4 + c4;
+  float4 a = __ldg(base), b = __ldg(base + C4), c = __ldg(base + (long long)W * C4),
+         d = __ldg(base + (long long)W * C4 + C4);
+  float4 o;
+  // TF/Eigen avg-pool sums the window then divides by its size
+  o.x = (a.x + b.x + c.x + d.x) * 0.25f;
+  o.y = (a.y + b.y + c.y + d.y) * 0.25f;
+  o.z = (a.z + b.z + c.z + d.z) * 0.25f;
+  o.w = (a.w + b.w + c.w + d.w) * 0.25f;
+  reinterpret_cast<float4*>(y)[t] = o;
+}
+
+extern "C" int tmx_avgpool2_fwd(tmx_handle_t h, const float* x, float* y, int N, int H, int W, int C, tmx_stream_t s) {
+  TMX_REQUIRE(h && x && y, TMX_ERR_ARG, "tmx_avgpool2_fwd: NULL argument");
+  TMX_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 4 == 0, TMX_ERR_SHAPE,
+              "tmx_avgpool2_fwd: bad shape N=%d H=%d W=%d C=%d (even H, W; C %% 4 == 0)", N, H, W, C);
+  long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
+  avgpool2_kernel<<<tmx_ceil_div(total, 256), 256, 0, (cudaStream_t)s>>>(x, y, total, H / 2, W / 2, C / 4);
+  TMX_LAUNCHED(h, "avgpool2_kernel");
+  return TMX_OK;
+}
+
+// ---------------------------------------------------------------- NCHW <-> NHWC
+// 32x32 smem tile transpose per image between [C][HW] and [HW][C_total] (+c_off).
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C,
+                                                           int HW, int c_off, int C_total, int bcast) {
+  __shared__ float tile[32][33];
+  int n = blockIdx.z;
+  int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* xn = x + (long long)n * C * (bcast ? 1 : HW);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int c = c0 + ty + i * 8, p = p0 + tx;
+    if (c < C && p < HW) tile[ty + i * 8][tx] = bcast ? __ldg(xn + c) : __ldg(xn + (long long)c * HW + p);
+  }
+  __syncthreads();
+  float* yn = y + (long long)n * HW * C_total + c_off;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int p = p0 + ty + i * 8, c = c0 + tx;
+    if (c < C && p < HW) yn[(long long)p * C_total + c] = tile[tx][ty + i * 8];
+  }
+}
+
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int C,
+                                                           int HW, int c_off, int C_total) {
+  __shared__ float tile[32][33];
+  int n = blockIdx.z;
+  int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* xn = x + (long long)n * HW * C_total + c_off;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int p = p0 + ty + i * 8, c = c0 + tx;
+    if (c < C && p < HW) tile[ty + i * 8][tx] = __ldg(xn + (long long)p * C_total + c);
+  }
+  __syncthreads();
+  float* yn = y + (long long)n * C * HW;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int c = c0 + ty + i * 8, p = p0 + tx;
+    if (c < C && p < HW) yn[(long long)c * HW + p] = tile[tx][ty + i * 8];
+  }
+}
+
+extern "C" int tmx_nchw_to_nhwc(tmx_handle_t h, const float* x, float* y, int N, int C, int H, int W, int c_off,
+                                int C_total, int bcast_hw, tmx_stream_t s) {
+  TMX_REQUIRE(h && x && y, TMX_ERR_ARG, "tmx_nchw_to_nhwc: NULL argument");
+  TMX_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && c_off >= 0 && c_off + C <= C_total && N <= 65535, TMX_ERR_SHAPE,
+              "tmx_nchw_to_nhwc: bad shape N=%d C=%d H=%d W=%d c_off=%d C_total=%d", N, C, H, W, c_off, C_total);
+  dim3 grid(tmx_ceil_div(H * W, 32), tmx_ceil_div(C, 32), N);
+  nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, y, C, H * W, c_off, C_total, bcast_hw);
+  TMX_LAUNCHED(h, "nchw_to_nhwc_kernel");
+  return TMX_OK;
+}
+
+extern "C" int tmx_nhwc_to_nchw(tmx_handle_t h, const float* x, float* y, int N, int C, int H, int W, int c_off,
+                                int C_total, tmx_stream_t s) {
+  TMX_REQUIRE(h && x && y, TMX_ERR_ARG, "tmx_nhwc_to_nchw: NULL argument");
+  TMX_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && c_off >= 0 && c_off + C <= C_total && N <= 65535, TMX_ERR_SHAPE,
+              "tmx_nhwc_to_nchw: bad shape N=%d C=%d H=%d W=%d c_off=%d C_total=%d", N, C, H, W, c_off, C_total);
+  dim3 grid(tmx_ceil_div(H * W, 32), tmx_ceil_div(C, 32), N);
+  nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, y, C, H * W, c_off, C_total);
+  TMX_LAUNCHED(h, "nhwc_to_nchw_kernel");
+  return TMX_OK;
+}
+
+// ---------------------------------------------------------------- split-bf16 halo pack / unpack
+// One thread = one padded pixel x 8 channels (2 float4 in, 16 B hi + 16 B lo out).
+__global__ void __launch_bounds__(256) split_halo_pack_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi,
+                                                              uint16_t* __restrict__ lo, long long total, int H, int W,
+                                                              int C8) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int c8 = (int)(t % C8);
+  long long p = t / C8;
+  int Wp = W + 2, Hp = H + 2;
+  int xp = (int)(p % Wp);
+  long long q = p / Wp;
+  int yp = (int)(q % Hp);
+  long long n = q / Hp;
+  int ys = tmx_reflect(yp - 1, H), xs = tmx_reflect(xp - 1, W);
+  const float4* src = reinterpret_cast<const float4*>(x) + ((n * H + ys) * W + xs) * (C8 * 2) + c8 * 2;
+  float4 a = __ldg(src), b = __ldg(src + 1);
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t ph[4], pl[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t h0, l0, h1, l1;
+    tmx_split_bf16(v[2 * i], h0, l0);
+    tmx_split_bf16(v[2 * i + 1], h1, l1);
+    ph[i] = h0 | (h1 << 16);
+    pl[i] = l0 | (l1 << 16);
+  }
+  reinterpret_cast<uint4*>(hi)[t] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  reinterpret_cast<uint4*>(lo)[t] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+
+__global__ void __launch_bounds__(256) split_halo_unpack_kernel(const uint16_t* __restrict__ hi,
+                                                                const uint16_t* __restrict__ lo, float* __restrict__ y,
+                                                                long long total, int H, int W, int C8) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int c8 = (int)(t % C8);
+  long long p = t / C8;
+  int xo = (int)(p % W);
+  long long q = p / W;
+  int yo = (int)(q % H);
+  long long n = q / H;
+  long long src = ((n * (H + 2) + yo + 1) * (W + 2) + xo + 1) * C8 + c8;
+  uint4 a = __ldg(reinterpret_cast<const uint4*>(hi) + src);
+  uint4 b = __ldg(reinterpret_cast<const uint4*>(lo) + src);
+  const uint32_t ah[4] = {a.x, a.y, a.z, a.w}, al[4] = {b.x, b.y, b.z, b.w};
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(ah[i] << 16) + __uint_as_float(al[i] << 16);
+    v[2 * i + 1] = __uint_as_float(ah[i] & 0xffff0000u) + __uint_as_float(al[i] & 0xffff0000u);
+  }
+  float4* dst = reinterpret_cast<float4*>(y) + t * 2;
+  dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+  dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+extern "C" int tmx_split_halo_pack(tmx_handle_t h, const float* x, uint16_t* hi, uint16_t* lo, int N, int H, int W,
+                                   int C, tmx_stream_t s) {
+  TMX_REQUIRE(h && x && hi && lo, TMX_ERR_ARG, "tmx_split_halo_pack: NULL argument");
+  TMX_REQUIRE(N > 0 && H >= 2 && W >= 2 && C > 0 && C % 8 == 0, TMX_ERR_SHAPE,
+              "tmx_split_halo_pack: bad shape N=%d H=%d W=%d C=%d (H, W >= 2; C %% 8 == 0)", N, H, W, C);
+  long long total = (long long)N * (H + 2) * (W + 2) * (C / 8);
+  split_halo_pack_kernel<<<tmx_ceil_div(total, 256), 256, 0, (cudaStream_t)s>>>(x, hi, lo, total, H, W, C / 8);
+  TMX_LAUNCHED(h, "split_halo_pack_kernel");
+  return TMX_OK;
+}
+
+extern "C" int tmx_split_halo_unpack(tmx_handle_t h, const uint16_t* hi, const uint16_t* lo, float* y, int N, int H,
+                                     int W, int C, tmx_stream_t s) {
+  TMX_REQUIRE(h && y && hi && lo, TMX_ERR_ARG, "tmx_split_halo_unpack: NULL argument");
+  TMX_REQUIRE(N > 0 && H >= 2 && W >= 2 && C > 0 && C % 8 == 0, TMX_ERR_SHAPE,
+              "tmx_split_halo_unpack: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
+  long long total = (long long)N * H * W * (C / 8);
+  split_halo_unpack_kernel<<<tmx_ceil_div(total, 256), 256, 0, (cudaStream_t)s>>>(hi, lo, y, total, H, W, C / 8);
+  TMX_LAUNCHED(h, "split_halo_unpack_kernel");
+  return TMX_OK;
+}
+
+// ---------------------------------------------------------------- weight preparation (tensor-core path)
+// w HWIO [taps][Cin][Cout] fp32 -> hi/lo bf16 [Cout][taps*Cin], scaled by wscale.
+// 32x32 tile transpose: coalesced reads along Cout, coalesced writes along K.
+__global__ void __launch_bounds__(256) weights_prepare_kernel(const float* __restrict__ w, float wscale,
+                                                              uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                                              int K, int Cout) {
+  __shared__ float tile[32][33];
+  int k0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int k = k0 + ty + i * 8, o = o0 + tx;
+    if (k < K && o < Cout) tile[ty + i * 8][tx] = __ldg(w + (long long)k * Cout + o);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int o = o0 + ty + i * 8, k = k0 + tx;
+    if (k < K && o < Cout) {
+      uint32_t a, b;
+      tmx_split_bf16(tile[tx][ty + i * 8] * wscale, a, b);
+      hi[(long long)o * K + k] = (uint16_t)a;
+      lo[(long long)o * K + k] = (uint16_t)b;
+    }
+  }
+}
+
+extern "C" int tmx_conv_weights_prepare(tmx_handle_t h, const float* w, float wscale, int k, int Cin, int Cout,
+                                        uint16_t* w_hi, uint16_t* w_lo, tmx_stream_t s) {
+  TMX_REQUIRE(h && w && w_hi && w_lo, TMX_ERR_ARG, "tmx_conv_weights_prepare: NULL argument");
+  TMX_REQUIRE((k == 1 || k == 3) && Cin > 0 && Cout > 0, TMX_ERR_SHAPE,
+              "tmx_conv_weights_prepare: bad shape k=%d Cin=%d Cout=%d", k, Cin, Cout);
+  int K = k * k * Cin;
+  dim3 grid(tmx_ceil_div(K, 32), tmx_ceil_div(Cout, 32));
+  weights_prepare_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(w, wscale, w_hi, w_lo, K, Cout);
+  TMX_LAUNCHED(h, "weights_prepare_kernel");
+  return TMX_OK;
+}
+
+// ---------------------------------------------------------------- latent tile gather / blend (K6)
+// Block = (32-wide strip of canvas columns, one canvas row i, one sample n);
+// 8 warps sweep the channels, lane = column.  Values are written straight to
+// the NCHW canvas (coalesced along j) and/or staged in smem and written to the
+// NHWC trunk input (coalesced along c).
+struct BlendParams {
+  tmx_blend_desc_t d;
+  tmx_blend_io_t io;
+};
+
+template <int MODE, bool F32>
+__global__ void __launch_bounds__(256) latent_blend_kernel(const BlendParams P) {
+  extern __shared__ float tile[];  // [Cchunk][33]
+  const tmx_blend_desc_t& d = P.d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.z, i = blockIdx.y, j0 = blockIdx.x * 32, j = j0 + lane;
+  const bool jv = j < d.W;
+  const bool pin_row = (d.pin_rows >> (i / d.h)) & 1ull;
+  int sy[4], sx[4];
+  double wgt[4];
+  float wgtf[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    sy[k] = sx[k] = 0;
+    wgt[k] = 0.0;
+    wgtf[k] = 0.f;
+    if (k < d.K && jv) {
+      bool pinned = pin_row && ((d.pin_cols >> (j / d.w)) & 1ull);
+      int yy = i, xx = j;
+      if (!pinned) {
+        if (P.io.idx_h[k]) yy = __ldg(P.io.idx_h[k] + (long long)n * d.H + i);
+        if (P.io.idx_w[k]) xx = __ldg(P.io.idx_w[k] + (long long)n * d.W + j);
+      }
+      sy[k] = yy % d.h;
+      sx[k] = xx % d.w;
+      if (MODE == TMX_BLEND_MATTE) {
+        double rh = __ldg(P.io.ramp_h[k] + i), rw = __ldg(P.io.ramp_w[k] + j);
+        if (F32) wgtf[k] = __fmul_rn((float)rh, (float)rw);
+        else wgt[k] = __dmul_rn(rh, rw);
+      }
+    }
+  }
+  const int CCH = 128;
+  for (int cbase = 0; cbase < d.C; cbase += CCH) {
+    const int cn = min(CCH, d.C - cbase);
+    for (int cc = warp; cc < cn; cc += 8) {
+      const int c = cbase + cc;
+      float v = 0.f;
+      if (jv) {
+        if (MODE == TMX_BLEND_MATTE) {
+          float sv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < d.K) {
+              const int nn = ((d.src_reverse >> k) & 1u) ? d.N - 1 - n : n;
+              const float* s = P.io.src[k] + ((long long)nn * d.C + c) * (d.src_bcast ? 1 : d.h * d.w);
+              sv[k] = d.src_bcast ? __ldg(s) : __ldg(s + sy[k] * d.w + sx[k]);
+            }
+          }
+          if (F32) {
+            float acc = __fmul_rn(sv[0], wgtf[0]);
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+              if (k < d.K) acc = __fadd_rn(acc, __fmul_rn(sv[k], wgtf[k]));
+            v = acc;
+          } else {
+            double acc = __dmul_rn((double)sv[0], wgt[0]);
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+              if (k < d.K) acc = __dadd_rn(acc, __dmul_rn((double)sv[k], wgt[k]));
+            v = (float)acc;
+          }
+        } else {
+          float sv[2] = {0.f, 0.f};
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            if (k < d.K) {
+              const int nn = ((d.src_reverse >> k) & 1u) ? d.N - 1 - n : n;
+              const float* s = P.io.src[k] + ((long long)nn * d.C + c) * (d.src_bcast ? 1 : d.h * d.w);
+              sv[k] = d.src_bcast ? __ldg(s) : __ldg(s + sy[k] * d.w + sx[k]);
+            }
+          }
+          if (MODE == TMX_BLEND_LERP) {
+            float t = __ldg(P.io.t + n);
+            v = __fadd_rn(sv[0], __fmul_rn(__fsub_rn(sv[1], sv[0]), t));  // tfutil.py:41-43, unfused
+          } else {
+            v = sv[0];
+          }
+        }
+        if (P.io.out_nchw) P.io.out_nchw[(((long long)n * d.C + c) * d.H + i) * d.W + j] = v;
+      }
+      if (P.io.out_nhwc) tile[cc * 33 + lane] = v;
+    }
+    if (P.io.out_nhwc) {
+      __syncthreads();
+      const int jn = min(32, d.W - j0);
+      float* o = P.io.out_nhwc + (((long long)n * d.H + i) * d.W + j0) * d.C_total + d.c_off + cbase;
+      for (int e = threadIdx.x; e < jn * cn; e += 256) {
+        int jj = e / cn, cc = e % cn;
+        o[(long long)jj * d.C_total + cc] = tile[cc * 33 + jj];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+extern "C" int tmx_latent_blend(tmx_handle_t h, const tmx_blend_desc_t* d, const tmx_blend_io_t* io, tmx_stream_t s) {
+  TMX_REQUIRE(h && d && io, TMX_ERR_ARG, "tmx_latent_blend: NULL argument");
+  TMX_REQUIRE(d->N > 0 && d->C > 0 && d->h > 0 && d->w > 0 && d->H > 0 && d->W > 0 && d->N <= 65535 && d->H <= 65535,
+              TMX_ERR_SHAPE, "tmx_latent_blend: bad shape N=%d C=%d h=%d w=%d H=%d W=%d", d->N, d->C, d->h, d->w, d->H,
+              d->W);
+  TMX_REQUIRE(d->K >= 1 && d->K <= 4, TMX_ERR_SHAPE, "tmx_latent_blend: K=%d not in 1..4", d->K);
+  TMX_REQUIRE(d->mode == TMX_BLEND_COPY || d->mode == TMX_BLEND_MATTE || d->mode == TMX_BLEND_LERP, TMX_ERR_ARG,
+              "tmx_latent_blend: bad mode %d", d->mode);
+  TMX_REQUIRE(d->mode != TMX_BLEND_COPY || d->K == 1, TMX_ERR_SHAPE, "tmx_latent_blend: COPY needs K == 1");
+  TMX_REQUIRE(d->mode != TMX_BLEND_LERP || (d->K == 2 && io->t), TMX_ERR_SHAPE,
+              "tmx_latent_blend: LERP needs K == 2 and t");
+  TMX_REQUIRE((d->H + d->h - 1) / d->h <= 64 && (d->W + d->w - 1) / d->w <= 64, TMX_ERR_SHAPE,
+              "tmx_latent_blend: more than 64 tiles per side");
+  TMX_REQUIRE(io->out_nchw || io->out_nhwc, TMX_ERR_ARG, "tmx_latent_blend: no output");
+  TMX_REQUIRE(!io->out_nhwc || (d->c_off >= 0 && d->c_off + d->C <= d->C_total), TMX_ERR_SHAPE,
+              "tmx_latent_blend: bad NHWC slice c_off=%d C=%d C_total=%d", d->c_off, d->C, d->C_total);
+  for (int k = 0; k < d->K; ++k) {
+    TMX_REQUIRE(io->src[k] != nullptr, TMX_ERR_ARG, "tmx_latent_blend: src[%d] is NULL", k);
+    if (d->mode == TMX_BLEND_MATTE)
+      TMX_REQUIRE(io->ramp_h[k] && io->ramp_w[k], TMX_ERR_ARG, "tmx_latent_blend: ramp[%d] is NULL", k);
+  }
+  BlendParams P;
+  P.d = *d;
+  P.io = *io;
+  dim3 grid(tmx_ceil_div(d->W, 32), d->H, d->N);
+  size_t smem = io->out_nhwc ? (size_t)128 * 33 * sizeof(float) : 0;
+  cudaStream_t st = (cudaStream_t)s;
+  if (d->mode == TMX_BLEND_COPY) latent_blend_kernel<TMX_BLEND_COPY, false><<<grid, 256, smem, st>>>(P);
+  else if (d->mode == TMX_BLEND_LERP) latent_blend_kernel<TMX_BLEND_LERP, false><<<grid, 256, smem, st>>>(P);
+  else if (d->math_f32) latent_blend_kernel<TMX_BLEND_MATTE, true><<<grid, 256, smem, st>>>(P);
+  else latent_blend_kernel<TMX_BLEND_MATTE, false><<<grid, 256, smem, st>>>(P);
+  TMX_LAUNCHED(h, "latent_blend_kernel");
+  return TMX_OK;
+}

@@ -1,0 +1,456 @@
+"""`Network`: the reference's plugin boundary (tfutil.py:416-750) over device
+tensors.  Build functions are selected by dotted name (config.py:77-82 ->
+tfutil.py:212-236), called once in *template* mode to discover inputs,
+outputs and variables (tfutil.py:458-494) and then in *run* mode for every
+evaluation (tfutil.py:505-516).  Variables keep the reference's names and
+HWIO/[in,out] shapes, so `__getstate__` produces the reference's version-2
+pickle dict (tfutil.py:543-550)."""
+import contextlib
+import importlib
+import inspect
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .runtime import Runtime
+
+
+# ---------------------------------------------------------------------- name resolution (tfutil.py:212-236)
+def import_module(module_or_obj_name):
+    parts = module_or_obj_name.split('.')
+    parts[0] = {'np': 'numpy', 'tf': 'tensorflow'}.get(parts[0], parts[0])
+    for i in range(len(parts), 0, -1):
+        name = '.'.join(parts[:i])
+        for cand in (name, 'texturemixer_b200.' + name):      # 'networks.G_res' resolves to OUR networks module
+            try:
+                module = importlib.import_module(cand)
+            except ImportError:
+                continue
+            if cand == name and parts[0] in ('networks', 'loss') and not module.__name__.startswith('texturemixer_b200'):
+                continue
+            return module, '.'.join(parts[i:])
+    raise ImportError(module_or_obj_name)
+
+
+def find_obj_in_module(module, relative_obj_name):
+    obj = module
+    for part in relative_obj_name.split('.'):
+        obj = getattr(obj, part)
+    return obj
+
+
+def import_obj(obj_name):
+    module, relative = import_module(obj_name)
+    return find_obj_in_module(module, relative)
+
+
+def call_func_by_name(*args, func=None, **kwargs):
+    assert func is not None
+    return import_obj(func)(*args, **kwargs)
+
+
+# ---------------------------------------------------------------------- variables
+class Variable:
+    """A named parameter living in the owning network's flat device buffer."""
+    __slots__ = ('name', 'shape', 'trainable', 'init', 'value')
+
+    def __init__(self, name, shape, trainable, init):
+        self.name, self.shape, self.trainable, self.init = name, tuple(int(s) for s in shape), trainable, init
+        self.value = None            # torch view, set by Network._allocate
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape)) if self.shape else 1
+
+
+class T:
+    """Tensor handle seen by build functions: a static NCHW shape (None batch
+    in template mode) plus, in run mode, the device payload - either an
+    external NCHW torch tensor (`nchw`) or an internal activation (`act`)."""
+    __slots__ = ('shape', 'ctx', 'nchw', 'act', 'name')
+
+    def __init__(self, shape, ctx, nchw=None, act=None, name=None):
+        self.shape, self.ctx, self.nchw, self.act, self.name = list(shape), ctx, nchw, act, name
+
+    def set_shape(self, shape):
+        """tf.Tensor.set_shape: fixes the template shape / checks the fed one
+        (the reference's implicit shape assert, networks.py:221,325,420-421)."""
+        shape = list(shape)
+        if self.ctx.mode == 'template':
+            self.shape = shape
+        else:
+            have = self.shape
+            if len(have) != len(shape) or any(w is not None and h != w for h, w in zip(have, shape)):
+                raise ValueError('%s: input shape %s incompatible with %s' % (self.ctx.net.name, have, shape))
+
+
+class BuildContext:
+    def __init__(self, net, mode):
+        self.net, self.mode = net, mode
+        self.scopes = []
+        self.rt = net.rt if mode == 'run' else None
+
+    @contextlib.contextmanager
+    def variable_scope(self, name):
+        self.scopes.append(name)
+        try:
+            yield
+        finally:
+            self.scopes.pop()
+
+    def get_variable(self, name, shape=(), init='normal', trainable=True):
+        full = '/'.join(self.scopes + [name])
+        v = self.net.vars.get(full)
+        if v is None:
+            if self.mode != 'template':
+                raise KeyError('%s: variable %s does not exist' % (self.net.name, full))
+            v = Variable(full, shape, trainable, init)
+            self.net.vars[full] = v
+        elif tuple(shape) != v.shape:
+            raise ValueError('%s: variable %s has shape %s, requested %s' % (self.net.name, full, v.shape, tuple(shape)))
+        return v
+
+    def cond(self, pred, true_fn, false_fn):
+        """tf.cond as the reference's graph mode sees it: the template builds BOTH
+        branches (true_fn first -> same variable creation order, incl. the unused
+        lod heads); run mode evaluates only the selected branch."""
+        if self.mode == 'template':
+            t = true_fn()
+            f = false_fn()
+            return t if pred else f
+        return true_fn() if pred else false_fn()
+
+
+# ---------------------------------------------------------------------- Network
+class Network:
+    def __init__(self, name=None, func=None, reuse=False, share_vars_with=None, device=None, seed=None,
+                 **static_kwargs):
+        """name/func/reuse/**static_kwargs as tfutil.Network.__init__ (tfutil.py:417-435).
+        `reuse=True` + `share_vars_with=<Network>` gives the reference's second
+        view over the SAME scope (G_fcn over G, run.py:273)."""
+        self._init_fields()
+        self.name = name
+        self.static_kwargs = dict(static_kwargs)
+        module, self._build_func_name = import_module(func)
+        try:
+            self._build_module_src = inspect.getsource(module)
+        except (OSError, TypeError):
+            self._build_module_src = ''
+        self._build_func = find_obj_in_module(module, self._build_func_name)
+        self._device = device
+        self._init_graph(share_vars_with if reuse else None)
+        if not (reuse and share_vars_with is not None):
+            self.reset_vars(seed)
+
+    def _init_fields(self):
+        self.name = None
+        self.scope = None
+        self.static_kwargs = dict()
+        self.num_inputs = 0
+        self.num_outputs = 0
+        self.input_shapes = [[]]
+        self.output_shapes = [[]]
+        self.input_shape = []
+        self.output_shape = []
+        self.input_names = []
+        self.output_names = []
+        self.vars = OrderedDict()
+        self.trainables = OrderedDict()
+        self._build_func = None
+        self._build_func_name = None
+        self._build_module_src = None
+        self._flat = None              # one fp32 device buffer holding every variable
+        self._version = 0              # bumped whenever variable values change
+        self._prepared = {}            # per-variable tensor-core weight planes (w_hi, w_lo, version)
+        self._rt = None
+        self._device = None
+        self._staging = {}
+
+    @property
+    def rt(self):
+        if self._rt is None:
+            if self._device is not None and str(self._device) == 'cpu':
+                raise RuntimeError('%s was created with device="cpu" (variables only); evaluation needs the CUDA '
+                                   'runtime - there is no CPU path' % self.name)
+            self._rt = Runtime.get(self._device)
+        return self._rt
+
+    @property
+    def lod(self):
+        return float(self._lod_host)
+
+    def _init_graph(self, share_with=None):
+        self.input_names = []
+        for param in inspect.signature(self._build_func).parameters.values():
+            if param.kind == param.POSITIONAL_OR_KEYWORD and param.default is param.empty:
+                self.input_names.append(param.name)
+        self.num_inputs = len(self.input_names)
+        assert self.num_inputs >= 1
+        if self.name is None:
+            self.name = self._build_func_name
+        self.scope = self.name.replace('/', '_')
+        self._lod_host = 0.0
+
+        ctx = BuildContext(self, 'template')
+        templates = [T([None], ctx, name=n) for n in self.input_names]
+        out = self._build_func(*templates, is_template_graph=True, **self.static_kwargs)
+        outs = [out] if isinstance(out, T) else list(out)
+        self.output_names = [t.name for t in outs]
+        self.num_outputs = len(outs)
+        self.input_shapes = [list(t.shape) for t in templates]
+        self.output_shapes = [list(t.shape) for t in outs]
+        self.input_shape = self.input_shapes[0]
+        self.output_shape = self.output_shapes[0]
+        template_vars = self.vars
+        if share_with is not None:
+            for k, v in template_vars.items():
+                if k not in share_with.vars or share_with.vars[k].shape != v.shape:
+                    raise ValueError('reuse: variable %s missing or mis-shaped in %s' % (k, share_with.name))
+            self.vars = share_with.vars
+            self._shared_owner = share_with
+        else:
+            self._shared_owner = None
+            self._allocate()
+        self.trainables = OrderedDict((k, v) for k, v in self.vars.items() if v.trainable)
+
+    def _var_device(self):
+        # device='cpu' is allowed for variable bookkeeping only (host-logic tests,
+        # checkpoint conversion); evaluation always requires the CUDA runtime.
+        if self._device is not None and str(self._device) == 'cpu':
+            return torch.device('cpu')
+        return self.rt.device
+
+    def _allocate(self):
+        total = sum(v.size for v in self.vars.values())
+        self._flat = torch.zeros(total, dtype=torch.float32, device=self._var_device())
+        off = 0
+        for v in self.vars.values():
+            v.value = self._flat[off:off + v.size].view(v.shape)
+            off += v.size
+
+    # -------------------------------------------------------------- variables
+    def _owner(self):
+        return self._shared_owner._owner() if self._shared_owner is not None else self
+
+    def _touch(self):
+        o = self._owner()
+        o._version += 1
+
+    def reset_vars(self, seed=None):
+        """Run the initialisers (tfutil.py:497-498): weights ~N(0,1) (networks.py:31),
+        biases 0 (networks.py:62), lod 0.  TF's own Philox stream is not
+        reproducible here; numpy RandomState(seed) is used instead."""
+        rng = np.random.RandomState(seed if seed is not None else np.random.randint(1 << 31))
+        host = np.zeros(self._flat.numel(), np.float32)
+        off = 0
+        for v in self.vars.values():
+            if v.init == 'normal':
+                host[off:off + v.size] = rng.randn(v.size).astype(np.float32)
+            elif v.init != 'zeros':
+                host[off:off + v.size] = np.float32(v.init)
+            off += v.size
+        self._flat.copy_(torch.from_numpy(host))
+        self._lod_host = float(self.vars['lod'].init) if 'lod' in self.vars and self.vars['lod'].init not in ('normal', 'zeros') else 0.0
+        self._touch()
+
+    def find_var(self, var_or_localname):
+        return self.vars[var_or_localname] if isinstance(var_or_localname, str) else var_or_localname
+
+    def get_var(self, var_or_localname):
+        return self.find_var(var_or_localname).value.detach().cpu().numpy().copy()
+
+    def set_var(self, var_or_localname, new_value):
+        v = self.find_var(var_or_localname)
+        arr = np.asarray(new_value, dtype=np.float32).reshape(v.shape)
+        v.value.copy_(torch.from_numpy(np.ascontiguousarray(arr)).reshape(v.shape))
+        if v.name == 'lod':
+            self._owner()._lod_host = float(arr)
+            self._lod_host = float(arr)
+        self._touch()
+
+    def set_vars(self, name_to_value):
+        for k, val in name_to_value.items():
+            self.set_var(k, val)
+
+    def copy_vars_from(self, src_net):
+        for name in self.vars.keys():
+            self.vars[name].value.copy_(src_net.vars[name].value)
+        self._lod_host = src_net._owner()._lod_host
+        self._touch()
+
+    def copy_trainables_from(self, src_net):
+        for name in self.trainables.keys():
+            self.vars[name].value.copy_(src_net.vars[name].value)
+        self._touch()
+
+    def clone(self, name=None):
+        """tfutil.py:579-589: same build function, own copy of the variables."""
+        net = object.__new__(Network)
+        net._init_fields()
+        net.name = name if name is not None else self.name
+        net.static_kwargs = dict(self.static_kwargs)
+        net._build_module_src = self._build_module_src
+        net._build_func_name = self._build_func_name
+        net._build_func = self._build_func
+        net._device = self._device
+        net._init_graph()
+        net.copy_vars_from(self)
+        return net
+
+    def prepared_weights(self, var, wscale, k, cin, cout):
+        """Cached bf16 hi/lo planes of a conv weight for the tensor-core kernel;
+        recomputed when any variable of the owning network changed."""
+        o = self._owner()
+        key = (var.name, float(wscale))
+        ent = o._prepared.get(key)
+        if ent is None or ent[2] != o._version:
+            hi, lo = self.rt.prepare_weights(var.value, wscale, k, cin, cout)
+            ent = (hi, lo, o._version)
+            o._prepared[key] = ent
+        return ent[0], ent[1]
+
+    # -------------------------------------------------------------- evaluation
+    def get_output_for(self, *in_expr, return_as_list=False, **dynamic_kwargs):
+        """tfutil.py:505-516 on device tensors: NCHW float32 CUDA tensors in,
+        NCHW float32 CUDA tensors out (same order/names as the reference)."""
+        assert len(in_expr) == self.num_inputs
+        all_kwargs = dict(self.static_kwargs)
+        all_kwargs.update(dynamic_kwargs)
+        ctx = BuildContext(self, 'run')
+        ins = []
+        for x, name in zip(in_expr, self.input_names):
+            if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32):
+                raise TypeError('%s.get_output_for: %s must be a float32 CUDA tensor' % (self.name, name))
+            ins.append(T(list(x.shape), ctx, nchw=x.contiguous(), name=name))
+        out = self._build_func(*ins, **all_kwargs)
+        outs = [out] if isinstance(out, T) else list(out)
+        res = [t.nchw for t in outs]
+        if return_as_list:
+            return res
+        return res[0] if len(res) == 1 else tuple(res)
+
+    def run(self, *in_arrays, return_as_list=False, print_progress=False, minibatch_size=None, num_gpus=1,
+            out_mul=1.0, out_add=0.0, out_shrink=1, out_dtype=None, **dynamic_kwargs):
+        """tfutil.py:624-680: NumPy in, NumPy out, minibatched.  Host buffers are
+        staged through pinned memory; one process drives one GPU (num_gpus > 1
+        in the reference's in-process sense is expressed as one rank per GPU,
+        see texturemixer_b200.parallel)."""
+        assert len(in_arrays) == self.num_inputs
+        if num_gpus != 1:
+            raise NotImplementedError('Network.run: one process drives one GPU; shard the batch across ranks')
+        num_items = in_arrays[0].shape[0]
+        if minibatch_size is None:
+            minibatch_size = num_items
+        dev = self.rt.device
+        out_arrays = None
+        for mb_begin in range(0, num_items, minibatch_size):
+            if print_progress:
+                print('\r%d / %d' % (mb_begin, num_items), end='')
+            mb_end = min(mb_begin + minibatch_size, num_items)
+            mb_in = []
+            for i, src in enumerate(in_arrays):
+                stage = self._pinned(('in', i), (mb_end - mb_begin,) + tuple(src.shape[1:]), torch.float32)
+                stage.numpy()[...] = src[mb_begin:mb_end]             # host copy + cast into pinned memory
+                mb_in.append(stage.to(dev, non_blocking=True))
+            mb_out = self.get_output_for(*mb_in, return_as_list=True, **dynamic_kwargs)
+            mb_out = [_convert_output(x, out_mul, out_add, out_shrink, out_dtype) for x in mb_out]
+            if out_arrays is None:
+                out_arrays = [np.empty([num_items] + list(x.shape[1:]), _np_dtype(x)) for x in mb_out]
+            stages = []
+            for i, x in enumerate(mb_out):
+                stage = self._pinned(('out', i), tuple(x.shape), x.dtype)
+                stage.copy_(x, non_blocking=True)
+                stages.append(stage)
+            torch.cuda.current_stream(dev).synchronize()
+            for dst, stage in zip(out_arrays, stages):
+                dst[mb_begin:mb_end] = stage.numpy()
+        if print_progress:
+            print('\r%d / %d' % (num_items, num_items))
+        if not return_as_list:
+            out_arrays = out_arrays[0] if len(out_arrays) == 1 else tuple(out_arrays)
+        return out_arrays
+
+    def _pinned(self, key, shape, dtype):
+        """Page-locked staging buffers, kept per (slot, shape) so that repeated
+        `run` calls do not re-register host memory."""
+        k = (key, tuple(shape), dtype)
+        buf = self._staging.get(k)
+        if buf is None:
+            buf = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+            self._staging[k] = buf
+        return buf
+
+    # -------------------------------------------------------------- EMA / pickling
+    def setup_as_moving_average_of(self, src_net, beta=0.99, beta_nontrainable=0.0):
+        """tfutil.py:611-621.  Returns a callable update op: var <- lerp(src, var, beta)."""
+        def update_op():
+            for name, var in self.vars.items():
+                if name in src_net.vars:
+                    cur_beta = beta if name in self.trainables else beta_nontrainable
+                    s = src_net.vars[name].value
+                    var.value.copy_(s + (var.value - s) * cur_beta)
+            self._lod_host = src_net._owner()._lod_host
+            self._touch()
+        return update_op
+
+    def __getstate__(self):
+        return {'version': 2, 'name': self.name, 'static_kwargs': self.static_kwargs,
+                'build_module_src': self._build_module_src, 'build_func_name': self._build_func_name,
+                'variables': [(k, self.get_var(k)) for k in self.vars.keys()]}
+
+    def __setstate__(self, state):
+        """tfutil.py:553-576, except that the pickled module SOURCE is never exec'd
+        (SURVEY Appendix D): the build function is resolved by name in this package."""
+        self._init_fields()
+        assert state['version'] == 2
+        self.name = state['name']
+        self.static_kwargs = state['static_kwargs']
+        self._build_module_src = state['build_module_src']
+        self._build_func_name = state['build_func_name']
+        self._build_func = import_obj('networks.' + self._build_func_name)
+        if not torch.cuda.is_available():
+            self._device = 'cpu'     # variables only (checkpoint inspection/conversion); evaluation still needs CUDA
+        self._init_graph()
+        self.reset_vars(0)
+        self.set_vars({name: value for name, value in state['variables'] if name in self.vars})
+
+    def print_layers(self, title=None, hide_layers_with_no_params=False):
+        title = title or self.name
+        print()
+        print('%-32s%-12s%-24s' % (title, 'Params', 'WeightShape'))
+        print('%-32s%-12s%-24s' % (('---',) * 3))
+        total = 0
+        for k, v in self.trainables.items():
+            total += v.size
+            print('%-32s%-12s%-24s' % (k, v.size, list(v.shape)))
+        print('%-32s%-12s' % ('Total', total))
+        print()
+
+    def setup_weight_histograms(self, title=None):
+        pass  # TensorBoard summaries are outside the hot path
+
+
+def _np_dtype(t):
+    return {torch.float32: np.float32, torch.uint8: np.uint8, torch.int32: np.int32, torch.float16: np.float16,
+            torch.int16: np.int16, torch.int64: np.int64}[t.dtype]
+
+
+def _convert_output(x, out_mul, out_add, out_shrink, out_dtype):
+    """tfutil.py:649-659 output conversion (mul, add, avg-pool shrink, round +
+    saturate-cast).  Not part of the measured path."""
+    if out_mul != 1.0:
+        x = x * out_mul
+    if out_add != 0.0:
+        x = x + out_add
+    if out_shrink > 1:
+        x = torch.nn.functional.avg_pool2d(x, out_shrink, out_shrink)
+    if out_dtype is not None:
+        dt = np.dtype(out_dtype)
+        if np.issubdtype(dt, np.integer):
+            info = np.iinfo(dt)
+            x = torch.round(x).clamp_(info.min, info.max)
+        x = x.to({np.dtype(np.uint8): torch.uint8, np.dtype(np.int32): torch.int32, np.dtype(np.int16): torch.int16,
+                  np.dtype(np.int64): torch.int64, np.dtype(np.float32): torch.float32,
+                  np.dtype(np.float16): torch.float16}[dt])
+    return x

@@ -1,0 +1,475 @@
+"""Build functions of the TextureMixer hot path with the reference's names and
+keyword signatures (networks.py:194-211, 296-314, 388-409, 491-505), so that
+`config.*.func = 'networks.G_res'` etc. resolve here (network.import_module).
+
+They are written against `network.T` handles: in *template* mode they only
+declare variables (same names, shapes and creation order as the reference's
+`recursive` structure, tf.cond building both branches) and propagate shapes;
+in *run* mode every layer is one libtmx launch on device activations
+(`runtime.Act`).  No arithmetic happens in Python/torch.
+
+Only the reference's default layer variants are implemented on the device
+(use_wscale=True, use_pixelnorm=False, fused_scale=False, leaky ReLU,
+float32); the others raise NotImplementedError."""
+import numpy as np
+
+from .network import T
+from .runtime import Act
+
+SQRT2 = float(np.sqrt(2))
+
+
+# ---------------------------------------------------------------------- primitives
+def _wscale(shape, gain):
+    """get_weight, networks.py:26-33 (use_wscale=True): float32(gain / sqrt(fan_in))."""
+    return float(np.float32(gain / np.sqrt(np.prod(shape[:-1]))))
+
+
+def _check_variants(use_wscale, use_pixelnorm, use_leakyrelu, fused_scale, dtype):
+    if not use_wscale or use_pixelnorm or not use_leakyrelu or fused_scale or dtype != 'float32':
+        raise NotImplementedError('texturemixer_b200: only the reference defaults use_wscale=True, '
+                                  'use_pixelnorm=False, use_leakyrelu=True, fused_scale=False, dtype=float32 '
+                                  'are implemented on the device')
+
+
+def _act_of(t):
+    """Device activation of a run-mode handle (NCHW -> NHWC on first use)."""
+    if t.act is None:
+        x = t.nchw
+        n, c, h, w = x.shape
+        t.act = Act(n, h, w, c, f32=t.ctx.rt.nchw_to_nhwc(x))
+    return t.act
+
+
+def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=False, next_tc=False,
+                 next_up2=False, keep_f32=False):
+    """act(apply_bias(conv2d(x))) [+ residual] under the current variable scope:
+    networks.py:48-56 + 61-67 + 72-75 (+ :437).  `up2`: the logical input is
+    upscale2d(x) (networks.py:448).  `next_tc`/`next_up2` are layout hints: the
+    consumer is a tensor-core conv (wants split-bf16 halo planes), optionally
+    through an upscale2d."""
+    assert kernel >= 1 and kernel % 2 == 1                                # networks.py:49
+    ctx = x.ctx
+    cin = x.shape[1]
+    w = ctx.get_variable('weight', (kernel, kernel, cin, fmaps))
+    b = ctx.get_variable('bias', (fmaps,), init='zeros')
+    f = 2 if up2 else 1
+    shape = [x.shape[0], fmaps, _mul(x.shape[2], f), _mul(x.shape[3], f)]
+    if ctx.mode == 'template':
+        return T(shape, ctx)
+    if kernel not in (1, 3):
+        raise NotImplementedError('conv2d kernel=%d: only 1 and 3 occur on the path' % kernel)
+    rt = ctx.rt
+    xa = _act_of(x)
+    ws = _wscale(w.shape, gain)
+    algo = rt.choose_algo(cin, fmaps, kernel, up2)
+    prepared = None
+    if algo != 1:  # tensor-core path: cached bf16 hi/lo weight planes
+        prepared = ctx.net.prepared_weights(w, ws, kernel, cin, fmaps)
+    res = None if residual is None else rt.split_unpack(_act_of(residual)).f32
+    out = rt.conv2d(xa, w.value, b.value, ws, kernel, fmaps, lrelu=act, residual=res, up2=up2,
+                    want_f32=(not next_tc) or keep_f32, want_split=next_tc, up2_out=next_up2, algo=algo, prepared=prepared)
+    return T(shape, ctx, act=out)
+
+
+def _mul(d, f):
+    return None if d is None else d * f
+
+
+def upscale2d_pending(x):
+    """networks.py:80-88 is never materialised: the consumer conv reads through it."""
+    return x
+
+
+def downscale2d(x, factor=2):
+    """networks.py:131-136."""
+    assert isinstance(factor, int) and factor >= 1
+    if factor == 1:
+        return x
+    ctx = x.ctx
+    shape = [x.shape[0], x.shape[1], x.shape[2] // factor, x.shape[3] // factor]
+    if ctx.mode == 'template':
+        return T(shape, ctx)
+    a = _act_of(x)
+    f = factor
+    while f > 1:
+        assert f % 2 == 0
+        a = ctx.rt.avgpool2(a)
+        f //= 2
+    return T(shape, ctx, act=a)
+
+
+def _fromrgb(x, fmaps, name):
+    """act(apply_bias(conv2d(x, kernel=1))) straight from the NCHW image
+    (networks.py:226-228, 330-332, 518-520)."""
+    ctx = x.ctx
+    with ctx.variable_scope(name):
+        cin = x.shape[1]
+        w = ctx.get_variable('weight', (1, 1, cin, fmaps))
+        b = ctx.get_variable('bias', (fmaps,), init='zeros')
+        shape = [x.shape[0], fmaps, x.shape[2], x.shape[3]]
+        if ctx.mode == 'template':
+            return T(shape, ctx)
+        if x.nchw is None:
+            raise NotImplementedError('FromRGB on a downscaled image (lod > 0) is not implemented (SURVEY N1)')
+        out = ctx.rt.fromrgb(x.nchw, w.value, b.value, _wscale(w.shape, SQRT2), fmaps, lrelu=True)
+        return T(shape, ctx, act=out)
+
+
+def _slice_outputs(t, latent_channels, names):
+    """x[:, :C], x[:, C:] as NCHW outputs (networks.py:289-290, 381-382)."""
+    ctx = t.ctx
+    outs = []
+    for i, name in enumerate(names):
+        shape = [t.shape[0], latent_channels, t.shape[2], t.shape[3]]
+        if ctx.mode == 'template':
+            outs.append(T(shape, ctx, name=name))
+        else:
+            a = ctx.rt.split_unpack(_act_of(t))
+            nchw = ctx.rt.nhwc_to_nchw(a.f32, c_off=i * latent_channels, c=latent_channels)
+            outs.append(T(shape, ctx, nchw=nchw, name=name))
+    return tuple(outs)
+
+
+def _lod(ctx):
+    ctx.get_variable('lod', (), init=0.0, trainable=False)                # networks.py:223,327,424,515
+    return ctx.net.lod
+
+
+def _encoder_grow(ctx, images_in, resolution_log2, min_res_log2, block, fromrgb, lod_in):
+    """The recursive `grow` shared by E_zg / E_zl / D_patch
+    (networks.py:276-282, 368-374, 568-574), tf.cond -> ctx.cond."""
+    def lerp_lod(x, y, t):
+        if ctx.mode == 'template':
+            return x
+        raise NotImplementedError('fractional lod (progressive growing) is not implemented (SURVEY N1)')
+
+    def grow(res, lod):
+        def x_fn():
+            return fromrgb(downscale2d(images_in, 2 ** lod), res)
+        if lod > 0:
+            x = ctx.cond(lod_in < lod, lambda: grow(res + 1, lod - 1), x_fn)
+        else:
+            x = x_fn()
+        x = block(x, res)
+        if res > min_res_log2:
+            x = ctx.cond(lod_in > lod,
+                         lambda: lerp_lod(x, fromrgb(downscale2d(images_in, 2 ** (lod + 1)), res - 1), lod_in - lod),
+                         lambda: x)
+        return x
+    return grow(min_res_log2, resolution_log2 - min_res_log2)
+
+
+def _tc(ctx, cin, cout, k, up2=False):
+    """Will a conv with these dims run on the tensor-core kernel?  (layout hint)"""
+    return ctx.mode == 'run' and ctx.rt.choose_algo(cin, cout, k, up2) != 1
+
+
+# ---------------------------------------------------------------------- E_zg (networks.py:194-291)
+def E_zg(images_in, num_channels=3, resolution=128, fmap_base=8192, fmap_decay=1.0, fmap_max=512,
+         latent_channels=4, use_wscale=True, use_pixelnorm=False, pixelnorm_epsilon=1e-8, use_leakyrelu=True,
+         tanh_at_end=False, dtype='float32', fused_scale=False, structure='recursive', is_template_graph=False,
+         **kwargs):
+    resolution_log2 = int(np.log2(resolution))
+    assert resolution == 2 ** resolution_log2 and resolution >= 4         # networks.py:214
+    _check_variants(use_wscale, use_pixelnorm, use_leakyrelu, fused_scale, dtype)
+    if tanh_at_end:
+        raise NotImplementedError('E_zg tanh_at_end=True is not used by the reference config')
+
+    def nf(stage):
+        return min(int(fmap_base / (2.0 ** (stage * fmap_decay))), fmap_max)
+    if latent_channels is None:
+        latent_channels = nf(0)
+    ctx = images_in.ctx
+    images_in.set_shape([None, num_channels, resolution, resolution])
+    lod_in = _lod(ctx)
+
+    def fromrgb(x, res):
+        return _fromrgb(x, nf(res - 1), 'FromRGB_lod%d' % (resolution_log2 - res))
+
+    def block(x, res):
+        with ctx.variable_scope('%dx%d' % (2 ** res, 2 ** res)):
+            if res >= 3:
+                with ctx.variable_scope('Conv0'):
+                    x = conv2d_layer(x, nf(res - 1), 3, next_tc=_tc(ctx, nf(res - 1), nf(res - 2), 3))
+                with ctx.variable_scope('Conv1'):
+                    x = conv2d_layer(x, nf(res - 2), 3)
+                return downscale2d(x)
+            with ctx.variable_scope('Conv0'):
+                x = conv2d_layer(x, nf(res - 1), 3, next_tc=_tc(ctx, nf(res - 1), nf(res - 2), 3))
+            with ctx.variable_scope('zg_Conv1'):
+                x = conv2d_layer(x, nf(res - 2), 3)
+            x = downscale2d(x)
+            with ctx.variable_scope('zg_Conv2'):
+                x = conv2d_layer(x, nf(res - 3), 3)
+            x = downscale2d(x)
+            with ctx.variable_scope('zg_Conv3'):
+                x = conv2d_layer(x, latent_channels * 2, 1, gain=1, act=False)
+            return x
+
+    out = _encoder_grow(ctx, images_in, resolution_log2, 2, block, fromrgb, lod_in)
+    return _slice_outputs(out, latent_channels, ('zg_mu', 'zg_log_sigma'))
+
+
+# ---------------------------------------------------------------------- E_zl (networks.py:296-383)
+def E_zl(images_in, num_channels=3, resolution=128, fmap_base=8192, fmap_decay=1.0, fmap_max=512, latent_res=4,
+         latent_channels=512, use_wscale=True, use_pixelnorm=False, pixelnorm_epsilon=1e-8, use_leakyrelu=True,
+         tanh_at_end=False, dtype='float32', fused_scale=False, structure='recursive', is_template_graph=False,
+         **kwargs):
+    resolution_log2 = int(np.log2(resolution))
+    latent_res_log2 = int(np.log2(latent_res))
+    assert resolution == 2 ** resolution_log2 and latent_res == 2 ** latent_res_log2 and resolution >= latent_res
+    _check_variants(use_wscale, use_pixelnorm, use_leakyrelu, fused_scale, dtype)
+    if tanh_at_end:
+        raise NotImplementedError('E_zl tanh_at_end=True is not used by the reference config')
+
+    def nf(stage):
+        return min(int(fmap_base / (2.0 ** (stage * fmap_decay))), fmap_max)
+    if latent_channels is None:
+        latent_channels = nf(0)
+    ctx = images_in.ctx
+    images_in.set_shape([None, num_channels, resolution, resolution])
+    lod_in = _lod(ctx)
+
+    def fromrgb(x, res):
+        return _fromrgb(x, nf(res - 1), 'FromRGB_lod%d' % (resolution_log2 - res))
+
+    def block(x, res):
+        with ctx.variable_scope('%dx%d' % (2 ** res, 2 ** res)):
+            if res > latent_res_log2:
+                with ctx.variable_scope('Conv0'):
+                    x = conv2d_layer(x, nf(res - 1), 3, next_tc=_tc(ctx, nf(res - 1), nf(res - 2), 3))
+                with ctx.variable_scope('Conv1'):
+                    x = conv2d_layer(x, nf(res - 2), 3)
+                return downscale2d(x)
+            with ctx.variable_scope('Conv0'):
+                x = conv2d_layer(x, nf(res - 1), 3, next_tc=_tc(ctx, nf(res - 1), latent_channels * 2, 1))
+            with ctx.variable_scope('z_Conv1'):
+                x = conv2d_layer(x, latent_channels * 2, 1, gain=1, act=False)
+            return x
+
+    out = _encoder_grow(ctx, images_in, resolution_log2, latent_res_log2, block, fromrgb, lod_in)
+    return _slice_outputs(out, latent_channels, ('z_mu', 'z_log_sigma'))
+
+
+# ---------------------------------------------------------------------- G_res (networks.py:388-486)
+def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_base=8192, fmap_decay=1.0,
+          fmap_max=512, latent_res=4, latent_channels=512, use_wscale=True, use_pixelnorm=False,
+          pixelnorm_epsilon=1e-8, use_leakyrelu=True, tanh_at_end=False, dtype='float32', fused_scale=False,
+          structure='recursive', is_template_graph=False, scale_h=1, scale_w=1, **kwargs):
+    resolution_log2 = int(np.log2(resolution))
+    latent_res_log2 = int(np.log2(latent_res))
+    assert resolution == 2 ** resolution_log2 and latent_res == 2 ** latent_res_log2 and resolution >= latent_res
+    _check_variants(use_wscale, use_pixelnorm, use_leakyrelu, fused_scale, dtype)
+
+    def nf(stage):
+        return min(int(fmap_base / (2.0 ** (stage * fmap_decay))), fmap_max)
+    if latent_channels is None:
+        latent_channels = nf(0)
+    ctx = zg_latents_in.ctx
+    zg_latents_in.set_shape([None, latent_channels, latent_res * scale_h, latent_res * scale_w])
+    zl_latents_in.set_shape([None, latent_channels, latent_res * scale_h, latent_res * scale_w])
+    c2 = latent_channels * 2
+
+    # combo_in = concat([zg, zl], axis=1) (networks.py:423): two NCHW -> NHWC slice moves
+    combo_shape = [zg_latents_in.shape[0], c2, latent_res * scale_h, latent_res * scale_w]
+    if ctx.mode == 'template':
+        combo_in = T(combo_shape, ctx)
+    else:
+        rt = ctx.rt
+        n, _, h, w = zg_latents_in.nchw.shape
+        if tuple(zl_latents_in.nchw.shape) != (n, latent_channels, h, w):
+            raise ValueError('G_res: zg %s and zl %s disagree' % (tuple(zg_latents_in.nchw.shape),
+                                                                  tuple(zl_latents_in.nchw.shape)))
+        buf = rt.empty(n, h, w, c2)
+        rt.nchw_to_nhwc(zg_latents_in.nchw, out=buf, c_off=0, c_total=c2)
+        rt.nchw_to_nhwc(zl_latents_in.nchw, out=buf, c_off=latent_channels, c_total=c2)
+        combo_shape[0] = n
+        combo_in = T(combo_shape, ctx, act=Act(n, h, w, c2, f32=buf))
+    lod_in = _lod(ctx)
+
+    def block(x, res):
+        with ctx.variable_scope('%dx%d' % (2 ** res, 2 ** res)):
+            if res == latent_res_log2:
+                for count in range(5):                                     # networks.py:430-437
+                    x0 = x
+                    with ctx.variable_scope('Residual%d_0' % count):
+                        x = conv2d_layer(x, c2, 3, next_tc=_tc(ctx, c2, c2, 3))
+                    with ctx.variable_scope('Residual%d_1' % count):
+                        nxt = c2 if count < 4 else nf(res - 1)
+                        # the sum is also the next block's x0: keep the exact fp32 copy beside the planes
+                        x = conv2d_layer(x, c2, 3, gain=1, act=False, residual=x0, next_tc=_tc(ctx, c2, nxt, 3),
+                                         keep_f32=count < 4)
+                with ctx.variable_scope('Conv0'):
+                    x = conv2d_layer(x, nf(res - 1), 3, gain=SQRT2 / 4, next_tc=_tc(ctx, nf(res - 1), nf(res - 1), 3))
+                with ctx.variable_scope('Conv1'):
+                    up_next = res < resolution_log2
+                    ntc = up_next and _tc(ctx, nf(res - 1), nf(res), 3)
+                    x = conv2d_layer(x, nf(res - 1), 3, next_tc=ntc, next_up2=ntc)
+            else:
+                with ctx.variable_scope('Conv0'):                          # upscale2d + conv2d (networks.py:448-450)
+                    pre_up = ctx.mode == 'run' and x.act.hi is not None and x.act.hi.shape[1] == 2 * x.act.h + 2
+                    x = _conv_after_up(x, nf(res - 1), pre_up, next_tc=_tc(ctx, nf(res - 1), nf(res - 1), 3))
+                with ctx.variable_scope('Conv1'):
+                    up_next = res < resolution_log2
+                    ntc = up_next and _tc(ctx, nf(res - 1), nf(res), 3)
+                    x = conv2d_layer(x, nf(res - 1), 3, next_tc=ntc, next_up2=ntc)
+            return x
+
+    def torgb(x, res, apply_tanh=False):
+        lod = resolution_log2 - res
+        with ctx.variable_scope('ToRGB_lod%d' % lod):
+            cin = x.shape[1]
+            w = ctx.get_variable('weight', (1, 1, cin, num_channels))
+            b = ctx.get_variable('bias', (num_channels,), init='zeros')
+            shape = [x.shape[0], num_channels, x.shape[2], x.shape[3]]
+            if ctx.mode == 'template':
+                return T(shape, ctx)
+            img = ctx.rt.torgb(_act_of(x), w.value, b.value, _wscale(w.shape, 1.0), num_channels, apply_tanh)
+            return T(shape, ctx, nchw=img)
+
+    def up_img(t, factor):
+        if factor == 1:
+            return t
+        if ctx.mode == 'template':
+            return T([t.shape[0], t.shape[1], t.shape[2] * factor, t.shape[3] * factor], ctx)
+        raise NotImplementedError('G_res at lod > 0 (image upscale/fade) is not implemented (SURVEY N1)')
+
+    def lerp_lod(a, b, t):
+        if ctx.mode == 'template':
+            return a
+        raise NotImplementedError('G_res fractional lod is not implemented (SURVEY N1)')
+
+    def grow(x, res, lod):                                                 # networks.py:473-479
+        y = block(x, res)
+
+        def img_fn():
+            return up_img(torgb(y, res, apply_tanh=tanh_at_end and lod == 0), 2 ** lod)
+        img = img_fn
+        if res > latent_res_log2:
+            prev = img
+
+            def img_fade():
+                return ctx.cond(lod_in > lod,
+                                lambda: up_img(lerp_lod(torgb(y, res), up_img(torgb(x, res - 1), 2), lod_in - lod),
+                                               2 ** lod),
+                                prev)
+            img = img_fade
+        if lod > 0:
+            prev2 = img
+
+            def img_deeper():
+                return ctx.cond(lod_in < lod, lambda: grow(y, res + 1, lod - 1), prev2)
+            img = img_deeper
+        return img()
+
+    images_out = grow(combo_in, latent_res_log2, resolution_log2 - latent_res_log2)
+    if ctx.mode == 'run' and tanh_at_end and lod_in != 0:
+        raise NotImplementedError('G_res at lod != 0 is not implemented (SURVEY N1)')
+    images_out.name = 'images_out'
+    return images_out
+
+
+def _conv_after_up(x, fmaps, pre_upscaled, next_tc):
+    """conv2d(upscale2d(x)).  If the producer already wrote its split planes x2
+    upsampled (TMX_CONV_UP2_OUT) the conv is a plain tensor-core conv on them;
+    otherwise the CUDA-core kernel reads through the upsampling (TMX_CONV_UP2_IN)."""
+    ctx = x.ctx
+    if ctx.mode == 'run' and pre_upscaled:
+        a = x.act
+        up = Act(a.n, a.h * 2, a.w * 2, a.c, hi=a.hi, lo=a.lo)
+        xs = T([x.shape[0], x.shape[1], x.shape[2] * 2, x.shape[3] * 2], ctx, act=up)
+        return conv2d_layer(xs, fmaps, 3, next_tc=next_tc)
+    return conv2d_layer(x, fmaps, 3, up2=True, next_tc=next_tc)
+
+
+# ---------------------------------------------------------------------- D_patch (networks.py:491-577)
+def D_patch(images_in, num_channels=3, resolution=128, fmap_base=8192, fmap_decay=1.0, fmap_max=512,
+            latent_res=4, use_wscale=True, mbstd_group_size=4, dtype='float32', fused_scale=False,
+            structure='recursive', is_template_graph=False, **kwargs):
+    resolution_log2 = int(np.log2(resolution))
+    latent_res_log2 = 2 if latent_res == -1 else int(np.log2(latent_res))
+    _check_variants(use_wscale, False, True, fused_scale, dtype)
+
+    def nf(stage):
+        return min(int(fmap_base / (2.0 ** (stage * fmap_decay))), fmap_max)
+    ctx = images_in.ctx
+    images_in.set_shape([None, num_channels, resolution, resolution])
+    lod_in = _lod(ctx)
+
+    def fromrgb(x, res):
+        return _fromrgb(x, nf(res - 1), 'FromRGB_lod%d' % (resolution_log2 - res))
+
+    def block(x, res):
+        with ctx.variable_scope('%dx%d' % (2 ** res, 2 ** res)):
+            if res > latent_res_log2:
+                with ctx.variable_scope('Conv0'):
+                    x = conv2d_layer(x, nf(res - 1), 3, next_tc=_tc(ctx, nf(res - 1), nf(res - 2), 3))
+                with ctx.variable_scope('Conv1'):
+                    x = conv2d_layer(x, nf(res - 2), 3)
+                return downscale2d(x)
+            if mbstd_group_size > 1:
+                x = _minibatch_stddev_layer(x, mbstd_group_size)
+            with ctx.variable_scope('Conv0'):
+                x = conv2d_layer(x, nf(res - 1), 3)
+            if latent_res == -1:
+                with ctx.variable_scope('Dense1'):
+                    x = _dense_layer(x, nf(res - 2), act=True)
+                with ctx.variable_scope('Dense2'):
+                    x = _dense_layer(x, 1, gain=1, act=False)
+                if ctx.mode == 'run':
+                    x.nchw = x.nchw.view(x.nchw.shape[0], 1, 1, 1)
+                x.shape = [x.shape[0], 1, 1, 1]
+            else:
+                with ctx.variable_scope('Conv1'):
+                    x = conv2d_layer(x, nf(res - 2), 1)
+                with ctx.variable_scope('Conv2'):
+                    x = conv2d_layer(x, 1, 1, gain=1, act=False)
+            return x
+
+    scores_out = _encoder_grow(ctx, images_in, resolution_log2, latent_res_log2, block, fromrgb, lod_in)
+    if ctx.mode == 'run' and scores_out.nchw is None:
+        a = ctx.rt.split_unpack(_act_of(scores_out))
+        scores_out.nchw = ctx.rt.nhwc_to_nchw(a.f32)
+    scores_out.name = 'scores_out'
+    return scores_out
+
+
+def _minibatch_stddev_layer(x, group_size):
+    """networks.py:177-189: one extra channel holding the group-of-G stddev statistic."""
+    ctx = x.ctx
+    shape = [x.shape[0], x.shape[1] + 1, x.shape[2], x.shape[3]]
+    if ctx.mode == 'template':
+        return T(shape, ctx)
+    a = ctx.rt.split_unpack(_act_of(x))
+    return T(shape, ctx, act=ctx.rt.mbstd(a, group_size))
+
+
+def _dense_layer(x, fmaps, gain=SQRT2, act=True):
+    """act(apply_bias(dense(x))) (networks.py:38-43, 61-67): rows are the NCHW
+    flattening of x, the variable is [in, out]."""
+    ctx = x.ctx
+    fan_in = int(np.prod(x.shape[1:]))
+    w = ctx.get_variable('weight', (fan_in, fmaps))
+    b = ctx.get_variable('bias', (fmaps,), init='zeros')
+    shape = [x.shape[0], fmaps]
+    if ctx.mode == 'template':
+        return T(shape, ctx)
+    rt = ctx.rt
+    if x.nchw is None:
+        a = rt.split_unpack(_act_of(x))
+        x.nchw = rt.nhwc_to_nchw(a.f32)
+    flat = x.nchw.view(x.nchw.shape[0], -1)
+    out = rt.dense(flat, w.value, b.value, _wscale(w.shape, gain), lrelu=act)
+    return T(shape, ctx, nchw=out)
+
+
+# ---------------------------------------------------------------------- north_star aliases
+def build_encoder(images_in, kind='zl', **kwargs):
+    """`build_encoder(kind='zg'|'zl')` == E_zg / E_zl."""
+    return {'zg': E_zg, 'zl': E_zl}[kind](images_in, **kwargs)
+
+
+def build_generator(zg_latents_in, zl_latents_in, **kwargs):
+    """`build_generator` == G_res."""
+    return G_res(zg_latents_in, zl_latents_in, **kwargs)

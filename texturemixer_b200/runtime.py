@@ -1,0 +1,281 @@
+"""Device runtime: thin Python over the C ABI (include/tmx.h).  PyTorch supplies
+device memory and the current CUDA stream only; every arithmetic op on the hot
+path is a libtmx kernel.  Nothing here falls back to torch ops or the CPU."""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+LRELU_ALPHA = 0.2
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Act:
+    """A device activation in one or both internal layouts.
+    f32: torch.float32 [N,H,W,C] (NHWC) ; hi/lo: torch.bfloat16 [N,H+2,W+2,C]
+    (SPLIT_BF16_HALO: x ~= hi + lo, REFLECT halo materialised)."""
+    __slots__ = ('n', 'h', 'w', 'c', 'f32', 'hi', 'lo')
+
+    def __init__(self, n, h, w, c, f32=None, hi=None, lo=None):
+        self.n, self.h, self.w, self.c = n, h, w, c
+        self.f32, self.hi, self.lo = f32, hi, lo
+
+    @property
+    def shape_nchw(self):
+        return (self.n, self.c, self.h, self.w)
+
+
+class Runtime:
+    """One per (process, device).  Holds the tmx handle; launches on torch's
+    current stream so that CUDA-graph capture and stream semantics are torch's."""
+    _instances = {}
+
+    @classmethod
+    def get(cls, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('texturemixer_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
+        if device is None:
+            device = torch.cuda.current_device()
+        device = torch.device('cuda', device) if isinstance(device, int) else torch.device(device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if idx not in cls._instances:
+            cls._instances[idx] = cls(idx)
+        return cls._instances[idx]
+
+    def __init__(self, index):
+        self.lib = _lib.load()
+        self.index = index
+        self.device = torch.device('cuda', index)
+        h = C.c_void_p()
+        _lib.check(self.lib.tmx_create(index, C.byref(h)), 'tmx_create')
+        self.handle = h
+        sm, major, minor = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(self.lib.tmx_device_info(h, C.byref(sm), C.byref(major), C.byref(minor)))
+        self.sm_count, self.cc = sm.value, (major.value, minor.value)
+        # kernel selection override for tests/benchmarks: auto | ffma | tc | tc_k32
+        self.conv_algo = os.environ.get('TMX_CONV_ALGO', 'auto')
+        # bench.py: CUDA events around each conv launch -> [(tag, start, end)], tag = (algo, k, cin, cout)
+        self.profile_kernels = False
+        self.kernel_events = []
+
+    # ------------------------------------------------------------------ helpers
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def launch_count(self):
+        v = C.c_uint64()
+        _lib.check(self.lib.tmx_launch_count(self.handle, C.byref(v)))
+        return int(v.value)
+
+    def empty(self, *shape, dtype=torch.float32):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    # ------------------------------------------------------------------ layout
+    def nchw_to_nhwc(self, x, out=None, c_off=0, c_total=None, bcast_hw=None):
+        """x: NCHW f32 device tensor ([N,C,1,1] with bcast_hw=(H,W)) -> NHWC slice."""
+        assert x.dtype == torch.float32 and x.is_cuda and x.is_contiguous()
+        n, c = x.shape[0], x.shape[1]
+        h, w = (x.shape[2], x.shape[3]) if bcast_hw is None else bcast_hw
+        c_total = c if c_total is None else c_total
+        if out is None:
+            out = self.empty(n, h, w, c_total)
+        _lib.check(self.lib.tmx_nchw_to_nhwc(self.handle, _ptr(x), _ptr(out), n, c, h, w, c_off, c_total,
+                                             0 if bcast_hw is None else 1, self.stream()), 'tmx_nchw_to_nhwc')
+        return out
+
+    def nhwc_to_nchw(self, x, c_off=0, c=None):
+        n, h, w, c_total = x.shape
+        c = c_total - c_off if c is None else c
+        out = self.empty(n, c, h, w)
+        _lib.check(self.lib.tmx_nhwc_to_nchw(self.handle, _ptr(x), _ptr(out), n, c, h, w, c_off, c_total,
+                                             self.stream()), 'tmx_nhwc_to_nchw')
+        return out
+
+    def split_pack(self, act):
+        if act.hi is None:
+            assert act.f32 is not None
+            act.hi = self.empty(act.n, act.h + 2, act.w + 2, act.c, dtype=torch.bfloat16)
+            act.lo = self.empty(act.n, act.h + 2, act.w + 2, act.c, dtype=torch.bfloat16)
+            _lib.check(self.lib.tmx_split_halo_pack(self.handle, _ptr(act.f32), _ptr(act.hi), _ptr(act.lo), act.n,
+                                                    act.h, act.w, act.c, self.stream()), 'tmx_split_halo_pack')
+        return act
+
+    def split_unpack(self, act):
+        if act.f32 is None:
+            assert act.hi is not None
+            act.f32 = self.empty(act.n, act.h, act.w, act.c)
+            _lib.check(self.lib.tmx_split_halo_unpack(self.handle, _ptr(act.hi), _ptr(act.lo), _ptr(act.f32), act.n,
+                                                      act.h, act.w, act.c, self.stream()), 'tmx_split_halo_unpack')
+        return act
+
+    # ------------------------------------------------------------------ conv
+    def choose_algo(self, cin, cout, k, up2):
+        mode = self.conv_algo
+        tc_ok = (not up2) and cin % 32 == 0 and cout % 32 == 0
+        if mode == 'ffma' or not tc_ok:
+            return _lib.ALGO_FFMA
+        if mode == 'tc':
+            return _lib.ALGO_TC if cin % 64 == 0 else _lib.ALGO_TC_K32
+        if mode == 'tc_k32':
+            return _lib.ALGO_TC_K32
+        # auto: tensor cores once the contraction is deep enough to pay for the operand split
+        if k * k * cin >= 576:
+            return _lib.ALGO_TC if cin % 64 == 0 else _lib.ALGO_TC_K32
+        return _lib.ALGO_FFMA
+
+    def prepare_weights(self, w, wscale, k, cin, cout):
+        hi = self.empty(cout, k * k * cin, dtype=torch.bfloat16)
+        lo = self.empty(cout, k * k * cin, dtype=torch.bfloat16)
+        _lib.check(self.lib.tmx_conv_weights_prepare(self.handle, _ptr(w), float(wscale), k, cin, cout, _ptr(hi),
+                                                     _ptr(lo), self.stream()), 'tmx_conv_weights_prepare')
+        return hi, lo
+
+    def conv2d(self, x, w, bias, wscale, k, cout, lrelu=False, residual=None, up2=False, want_f32=True,
+               want_split=False, up2_out=False, algo=None, prepared=None):
+        """y = [residual +] lrelu(wscale*conv(x, w) + bias) on an Act.  `w` is the raw
+        HWIO variable; `prepared` an optional (w_hi, w_lo) pair for the TC kernel."""
+        cin = x.c
+        h, w_ = (x.h * 2, x.w * 2) if up2 else (x.h, x.w)
+        if algo is None:
+            algo = self.choose_algo(cin, cout, k, up2)
+        d = _lib.ConvDesc(N=x.n, H=h, W=w_, Cin=cin, Cout=cout, k=k, flags=0, algo=algo, wscale=float(wscale),
+                          lrelu_alpha=LRELU_ALPHA)
+        io = _lib.ConvIO()
+        flags = 0
+        if lrelu:
+            flags |= _lib.CONV_LRELU
+        if residual is not None:
+            flags |= _lib.CONV_RESIDUAL
+            io.residual = residual.data_ptr()
+        io.bias = None if bias is None else bias.data_ptr()
+        keep = []
+        if algo == _lib.ALGO_FFMA:
+            if up2:
+                flags |= _lib.CONV_UP2_IN
+            self.split_unpack(x)
+            io.x_f32 = x.f32.data_ptr()
+            io.w = w.data_ptr()
+            out = Act(x.n, h, w_, cout, f32=self.empty(x.n, h, w_, cout))
+            io.y_f32 = out.f32.data_ptr()
+        else:
+            assert not up2
+            self.split_pack(x)
+            io.x_hi, io.x_lo = x.hi.data_ptr(), x.lo.data_ptr()
+            if prepared is None:
+                prepared = self.prepare_weights(w, wscale, k, cin, cout)
+            keep.append(prepared)
+            io.w_hi, io.w_lo = prepared[0].data_ptr(), prepared[1].data_ptr()
+            out = Act(x.n, h, w_, cout)
+            if want_f32 or not want_split:
+                out.f32 = self.empty(x.n, h, w_, cout)
+                io.y_f32 = out.f32.data_ptr()
+            if want_split:
+                ho, wo = (h * 2, w_ * 2) if up2_out else (h, w_)
+                out.hi = self.empty(x.n, ho + 2, wo + 2, cout, dtype=torch.bfloat16)
+                out.lo = self.empty(x.n, ho + 2, wo + 2, cout, dtype=torch.bfloat16)
+                io.y_hi, io.y_lo = out.hi.data_ptr(), out.lo.data_ptr()
+                if up2_out:
+                    flags |= _lib.CONV_UP2_OUT
+        d.flags = flags
+        if self.profile_kernels:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        _lib.check(self.lib.tmx_conv2d_fwd(self.handle, C.byref(d), C.byref(io), self.stream()), 'tmx_conv2d_fwd')
+        if self.profile_kernels:
+            e1.record()
+            self.kernel_events.append((('ffma' if algo == _lib.ALGO_FFMA else 'tc', k, cin, cout), e0, e1))
+        if want_split and out.hi is None:
+            self.split_pack(out)
+        return out
+
+    # ------------------------------------------------------------------ pointwise
+    def fromrgb(self, x_nchw, w, bias, wscale, cout, lrelu=True):
+        n, cin, h, w_ = x_nchw.shape
+        out = Act(n, h, w_, cout, f32=self.empty(n, h, w_, cout))
+        _lib.check(self.lib.tmx_fromrgb_fwd(self.handle, _ptr(x_nchw), _ptr(w), _ptr(bias), float(wscale),
+                                            _ptr(out.f32), n, cin, h, w_, cout, int(lrelu), LRELU_ALPHA,
+                                            self.stream()), 'tmx_fromrgb_fwd')
+        return out
+
+    def torgb(self, x, w, bias, wscale, cout, apply_tanh):
+        self.split_unpack(x)
+        out = self.empty(x.n, cout, x.h, x.w)
+        _lib.check(self.lib.tmx_torgb_fwd(self.handle, _ptr(x.f32), _ptr(w), _ptr(bias), float(wscale), _ptr(out),
+                                          x.n, x.h, x.w, x.c, cout, int(apply_tanh), self.stream()), 'tmx_torgb_fwd')
+        return out
+
+    def avgpool2(self, x):
+        self.split_unpack(x)
+        out = Act(x.n, x.h // 2, x.w // 2, x.c, f32=self.empty(x.n, x.h // 2, x.w // 2, x.c))
+        _lib.check(self.lib.tmx_avgpool2_fwd(self.handle, _ptr(x.f32), _ptr(out.f32), x.n, x.h, x.w, x.c,
+                                             self.stream()), 'tmx_avgpool2_fwd')
+        return out
+
+    def mbstd(self, x, group_size):
+        raise NotImplementedError('minibatch_stddev_layer (D_patch) has no device kernel yet')
+
+    def dense(self, x, w, bias, wscale, lrelu):
+        raise NotImplementedError('dense (D_patch head) has no device kernel yet')
+
+    # ------------------------------------------------------------------ latent blend
+    def latent_blend(self, srcs, H, W, mode, idx_h=None, idx_w=None, ramps_h=None, ramps_w=None, t=None,
+                     pin_rows=0, pin_cols=0, src_reverse=0, math_f32=False, out_nchw=True, out_nhwc=None,
+                     c_off=0, c_total=None):
+        """srcs: list of NCHW f32 device tensors ([N,C,h,w] or [N,C,1,1] broadcast)."""
+        k = len(srcs)
+        n, c, h, w = srcs[0].shape
+        bcast = (h == 1 and w == 1 and (H > 1 or W > 1))
+        d = _lib.BlendDesc(N=n, C=c, h=h, w=w, H=H, W=W, K=k, mode=mode, math_f32=int(math_f32),
+                           src_bcast=int(bcast), src_reverse=src_reverse, pin_rows=pin_rows, pin_cols=pin_cols,
+                           c_off=c_off, C_total=c if c_total is None else c_total)
+        io = _lib.BlendIO()
+        for i, s in enumerate(srcs):
+            assert s.dtype == torch.float32 and s.is_contiguous() and tuple(s.shape) == (n, c, h, w)
+            io.src[i] = s.data_ptr()
+            if idx_h is not None and idx_h[i] is not None:
+                assert idx_h[i].dtype == torch.int32 and tuple(idx_h[i].shape) == (n, H)
+                io.idx_h[i] = idx_h[i].data_ptr()
+            if idx_w is not None and idx_w[i] is not None:
+                assert idx_w[i].dtype == torch.int32 and tuple(idx_w[i].shape) == (n, W)
+                io.idx_w[i] = idx_w[i].data_ptr()
+            if ramps_h is not None:
+                assert ramps_h[i].dtype == torch.float64 and ramps_h[i].numel() == H
+                assert ramps_w[i].dtype == torch.float64 and ramps_w[i].numel() == W
+                io.ramp_h[i] = ramps_h[i].data_ptr()
+                io.ramp_w[i] = ramps_w[i].data_ptr()
+        if t is not None:
+            assert t.dtype == torch.float32 and t.numel() == n
+            io.t = t.data_ptr()
+        res_nchw = None
+        if out_nchw:
+            res_nchw = self.empty(n, c, H, W)
+            io.out_nchw = res_nchw.data_ptr()
+        if out_nhwc is not None:
+            io.out_nhwc = out_nhwc.data_ptr()
+        _lib.check(self.lib.tmx_latent_blend(self.handle, C.byref(d), C.byref(io), self.stream()),
+                   'tmx_latent_blend')
+        return res_nchw
+
+
+# ---------------------------------------------------------------------- host sampler
+def perm_indices_from_uniforms(u, length, levels, count):
+    """Index vectors of the hierarchical swap permutation (run.py:107-182, 436-507)
+    from pre-drawn uniforms.  Host only.  -> (int32 [count, length], consumed)."""
+    lib = _lib.load()
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.empty((count, length), np.int32)
+    used = C.c_int64()
+    _lib.check(lib.tmx_perm_indices_from_uniforms(u.ctypes.data_as(C.POINTER(C.c_double)), u.size, length, levels,
+                                                  count, out.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(used)),
+               'tmx_perm_indices_from_uniforms')
+    return out, int(used.value)
+
+
+def uniforms_per_matrix(length, levels):
+    return sum(2 * (length >> lvl) for lvl in range(levels) if (length >> lvl) > 1)
