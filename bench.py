@@ -201,6 +201,11 @@ def run_ours(args):
     barrier()
     launches = rt.launch_count() - l0
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    if args.device_only:                                       # for ncu: no host arm, no JSON line
+        if rank == 0:
+            sampler.stop()
+            sys.stderr.write('device-only: %.3f ms/step\n' % (dev_ms / args.steps))
+        return
 
     # ---- end to end through Network.run (host numpy in / out)
     for _ in range(2):
@@ -273,6 +278,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--device-only', action='store_true', help='only the device-resident loop (profiling runs)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -2,7 +2,8 @@
 reference-style `Network` boundary) against the CPU oracle and the committed
 golden vectors minted from the reference's own networks.py
 (tests/golden/make_golden.py).  north_star tolerance: 1e-3 relative fp32
-(normalised max error); we assert 2e-4."""
+(normalised max error); we assert 5e-4 (bf16x3 products carry ~2^-16 relative
+error each; 17 stacked convs measure 1-3e-4 normalised max)."""
 import os
 
 import numpy as np
@@ -16,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 SUBSAMPLE = 37
-TOL = 2e-4
+TOL = 5e-4
 
 
 def _nmax(got, want):

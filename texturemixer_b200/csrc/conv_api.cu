@@ -14,6 +14,11 @@ extern "C" int tmx_conv2d_fwd(tmx_handle_t h, const tmx_conv_desc_t* d, const tm
               "tmx_conv2d_fwd: bad shape N=%d H=%d W=%d Cin=%d Cout=%d", d->N, d->H, d->W, d->Cin, d->Cout);
   TMX_REQUIRE(d->k == 1 || (d->H >= 2 && d->W >= 2), TMX_ERR_SHAPE,
               "tmx_conv2d_fwd: REFLECT pad needs H, W >= 2 (got %d x %d)", d->H, d->W);
+  const void* ptrs[] = {io->x_f32, io->x_hi, io->x_lo, io->w, io->w_hi, io->w_lo, io->bias, io->residual,
+                        io->y_f32, io->y_hi, io->y_lo};
+  for (const void* q : ptrs)
+    TMX_REQUIRE(((uintptr_t)q & 15) == 0, TMX_ERR_ARG,
+                "tmx_conv2d_fwd: every buffer must be 16-byte aligned (got %p) - the kernels use 128-bit accesses", q);
   cudaStream_t st = (cudaStream_t)s;
   int algo = d->algo;
   if (algo == TMX_ALGO_AUTO) algo = (io->x_hi != nullptr) ? TMX_ALGO_TC : TMX_ALGO_FFMA;

@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(256) latent_blend_kernel(const BlendParams P) 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = blockIdx.z, i = blockIdx.y, j0 = blockIdx.x * 32, j = j0 + lane;
   const bool jv = j < d.W;
-  const bool pin_row = (d.pin_rows >> (i / d.h)) & 1ull;
+  const bool pin_row = d.pin_rows != 0 && ((d.pin_rows >> (i / d.h)) & 1ull);
   int sy[4], sx[4];
   double wgt[4];
   float wgtf[4];
@@ -443,8 +443,9 @@ extern "C" int tmx_latent_blend(tmx_handle_t h, const tmx_blend_desc_t* d, const
   TMX_REQUIRE(d->mode != TMX_BLEND_COPY || d->K == 1, TMX_ERR_SHAPE, "tmx_latent_blend: COPY needs K == 1");
   TMX_REQUIRE(d->mode != TMX_BLEND_LERP || (d->K == 2 && io->t), TMX_ERR_SHAPE,
               "tmx_latent_blend: LERP needs K == 2 and t");
-  TMX_REQUIRE((d->H + d->h - 1) / d->h <= 64 && (d->W + d->w - 1) / d->w <= 64, TMX_ERR_SHAPE,
-              "tmx_latent_blend: more than 64 tiles per side");
+  TMX_REQUIRE((d->pin_rows == 0 && d->pin_cols == 0) ||
+                  ((d->H + d->h - 1) / d->h <= 64 && (d->W + d->w - 1) / d->w <= 64),
+              TMX_ERR_SHAPE, "tmx_latent_blend: re-pinned tiles need at most 64 tiles per side");
   TMX_REQUIRE(io->out_nchw || io->out_nhwc, TMX_ERR_ARG, "tmx_latent_blend: no output");
   TMX_REQUIRE(!io->out_nhwc || (d->c_off >= 0 && d->c_off + d->C <= d->C_total), TMX_ERR_SHAPE,
               "tmx_latent_blend: bad NHWC slice c_off=%d C=%d C_total=%d", d->c_off, d->C, d->C_total);

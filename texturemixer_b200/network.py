@@ -221,13 +221,19 @@ class Network:
             return torch.device('cpu')
         return self.rt.device
 
+    _ALIGN = 64   # floats: every variable starts on a 256-byte boundary (vector loads, TMA)
+
     def _allocate(self):
-        total = sum(v.size for v in self.vars.values())
-        self._flat = torch.zeros(total, dtype=torch.float32, device=self._var_device())
+        """One flat fp32 device buffer for all variables (what the fused optimizer
+        and the gradient all-reduce walk); padding between variables stays zero."""
         off = 0
+        offsets = []
         for v in self.vars.values():
-            v.value = self._flat[off:off + v.size].view(v.shape)
-            off += v.size
+            offsets.append(off)
+            off += (v.size + self._ALIGN - 1) // self._ALIGN * self._ALIGN
+        self._flat = torch.zeros(off, dtype=torch.float32, device=self._var_device())
+        for v, o in zip(self.vars.values(), offsets):
+            v.value = self._flat[o:o + v.size].view(v.shape)
 
     # -------------------------------------------------------------- variables
     def _owner(self):
@@ -242,15 +248,14 @@ class Network:
         biases 0 (networks.py:62), lod 0.  TF's own Philox stream is not
         reproducible here; numpy RandomState(seed) is used instead."""
         rng = np.random.RandomState(seed if seed is not None else np.random.randint(1 << 31))
-        host = np.zeros(self._flat.numel(), np.float32)
-        off = 0
         for v in self.vars.values():
             if v.init == 'normal':
-                host[off:off + v.size] = rng.randn(v.size).astype(np.float32)
-            elif v.init != 'zeros':
-                host[off:off + v.size] = np.float32(v.init)
-            off += v.size
-        self._flat.copy_(torch.from_numpy(host))
+                host = rng.randn(v.size).astype(np.float32)
+            elif v.init == 'zeros':
+                host = np.zeros(v.size, np.float32)
+            else:
+                host = np.full(v.size, np.float32(v.init))
+            v.value.copy_(torch.from_numpy(host).reshape(v.shape))
         self._lod_host = float(self.vars['lod'].init) if 'lod' in self.vars and self.vars['lod'].init not in ('normal', 'zeros') else 0.0
         self._touch()
 
