@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TMX_ABI_VERSION 1
+#define TMX_ABI_VERSION 2
 
 typedef struct tmx_ctx* tmx_handle_t;
 typedef void* tmx_stream_t; /* cudaStream_t */
@@ -62,13 +62,21 @@ int tmx_launch_count(tmx_handle_t h, uint64_t* count);
  * y = [residual +] lrelu( wscale * xcorr(reflect_pad(up2?(x)), w) + bias )      */
 #define TMX_CONV_LRELU 1u    /* max(alpha*x, x) after bias */
 #define TMX_CONV_RESIDUAL 2u /* y += residual (after activation; G_res :437 has none) */
-#define TMX_CONV_UP2_IN 4u   /* logical input = nearest-neighbour x2 of the stored input (FFMA only) */
-#define TMX_CONV_UP2_OUT 8u  /* split-plane output is written x2 upsampled (TC producer side of :448) */
+#define TMX_CONV_UP2_IN 4u   /* logical input = nearest-neighbour x2 of the stored input (networks.py:448).
+                              * FFMA: the gather reads through the upsampling.
+                              * TC: sub-pixel form - conv3x3(up2(x)) == four 2x2-tap convs of x, run as ONE
+                              *     3x3-tap GEMM with N = 4*Cout over the stored low-res planes, which must
+                              *     carry a REPLICATE halo (REFLECT of the upsampled image == clamp of the
+                              *     stored one) and weights prepared with up2_phase = 1. */
+#define TMX_CONV_UP2_OUT 8u  /* split-plane output is written x2 upsampled (then REFLECT halo of the big image) */
+#define TMX_CONV_HALO_REPLICATE 16u /* split-plane output gets a REPLICATE halo (consumer is a TC UP2_IN conv) */
+#define TMX_CONV_TORGB 32u   /* TC, Cout <= 32: additionally y_rgb = [tanh](rgb_wscale * (y . rgb_w) + rgb_b) as NCHW
+                              * (networks.py:454-457 torgb + :483 tanh fused behind the last conv) */
 
 #define TMX_ALGO_AUTO 0
 #define TMX_ALGO_FFMA 1 /* CUDA-core fp32 implicit GEMM, NHWC f32 in/out */
-#define TMX_ALGO_TC 2   /* tcgen05 bf16x3 implicit GEMM, SPLIT_BF16_HALO in (64-channel K chunks, 128B swizzle) */
-#define TMX_ALGO_TC_K32 3 /* same, 32-channel K chunks (64B swizzle, deeper pipeline) */
+#define TMX_ALGO_TC 2   /* tcgen05 bf16x3 implicit GEMM, SPLIT_BF16_HALO in; K chunk = 64/32/16 channels by Cin */
+#define TMX_ALGO_TC_K32 3 /* same, K chunks of at most 32 channels (64B swizzle, deeper pipeline) */
 
 typedef struct {
   int32_t N, H, W;   /* output size == logical input size (stride 1, 'same') */
@@ -78,32 +86,42 @@ typedef struct {
   int32_t algo;      /* TMX_ALGO_* */
   float wscale;      /* gain / sqrt(k*k*Cin), networks.py:28-30 (FFMA applies it; TC expects it folded by tmx_conv_weights_prepare) */
   float lrelu_alpha; /* 0.2 */
+  int32_t rgb_cout;  /* TORGB: number of image channels (<= 4) */
+  int32_t rgb_tanh;  /* TORGB: apply tanh */
+  float rgb_wscale;  /* TORGB: gain / sqrt(Cout) of the 1x1 head */
 } tmx_conv_desc_t;
 
 typedef struct {
   const float* x_f32;    /* FFMA: NHWC f32 [N][H][W][Cin] ([N][H/2][W/2][Cin] with UP2_IN) */
-  const uint16_t* x_hi;  /* TC: SPLIT_BF16_HALO planes [N][H+2][W+2][Cin] */
+  const uint16_t* x_hi;  /* TC: SPLIT_BF16_HALO planes [N][H+2][W+2][Cin] ([N][H/2+2][W/2+2][Cin] with UP2_IN) */
   const uint16_t* x_lo;
   const float* w;        /* FFMA: raw variable, HWIO [k][k][Cin][Cout] */
-  const uint16_t* w_hi;  /* TC: prepared planes [Cout][k*k*Cin] */
+  const uint16_t* w_hi;  /* TC: prepared planes [Cout][k*k*Cin] ([4*Cout][9*Cin] with UP2_IN) */
   const uint16_t* w_lo;
   const float* bias;     /* [Cout] or NULL */
   const float* residual; /* NHWC f32 [N][H][W][Cout] or NULL */
   float* y_f32;          /* NHWC f32 [N][H][W][Cout] or NULL */
   uint16_t* y_hi;        /* SPLIT_BF16_HALO out [N][H+2][W+2][Cout] ([N][2H+2][2W+2][Cout] with UP2_OUT) or NULL */
   uint16_t* y_lo;
+  const float* rgb_w;    /* TORGB: raw 1x1 head variable [Cout][rgb_cout] */
+  const float* rgb_b;    /* TORGB: [rgb_cout] or NULL */
+  float* y_rgb;          /* TORGB: NCHW f32 [N][rgb_cout][H][W] */
 } tmx_conv_io_t;
 
 int tmx_conv2d_fwd(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_io_t* io, tmx_stream_t s);
 
 /* get_weight (networks.py:26-33) for the tensor-core path: w_hwio * wscale ->
- * bf16 hi/lo planes laid out K-major [Cout][k*k*Cin], K index = (u*k+v)*Cin + c. */
+ * bf16 hi/lo planes laid out K-major [Cout][k*k*Cin], K index = (u*k+v)*Cin + c.
+ * up2_phase (k == 3 only): the sub-pixel weights of conv3x3(upscale2d(x)) as [4*Cout][9*Cin]: row
+ * (a*2+b)*Cout + o holds, for output phase (a,b) = (row parity, column parity), the 3x3 low-res taps
+ * (U,V): sum of w[u][v] over the upsampled taps that fall on low-res offset (U-1, V-1)
+ * (a=0: {0},{1,2},{} ; a=1: {},{0,1},{2}); fp32 sums, then * wscale, then split. */
 int tmx_conv_weights_prepare(tmx_handle_t h, const float* w_hwio, float wscale, int k, int Cin, int Cout,
-                             uint16_t* w_hi, uint16_t* w_lo, tmx_stream_t s);
+                             int up2_phase, uint16_t* w_hi, uint16_t* w_lo, tmx_stream_t s);
 
-/* NHWC f32 -> SPLIT_BF16_HALO (tf.pad REFLECT of networks.py:55 materialised). */
+/* NHWC f32 -> SPLIT_BF16_HALO (tf.pad REFLECT of networks.py:55 materialised; replicate != 0: edge-clamped halo). */
 int tmx_split_halo_pack(tmx_handle_t h, const float* x_nhwc, uint16_t* hi, uint16_t* lo, int N, int H, int W, int C,
-                        tmx_stream_t s);
+                        int replicate, tmx_stream_t s);
 /* SPLIT_BF16_HALO interior -> NHWC f32 (hi + lo), for tests and FFMA consumers. */
 int tmx_split_halo_unpack(tmx_handle_t h, const uint16_t* hi, const uint16_t* lo, float* y_nhwc, int N, int H, int W,
                           int C, tmx_stream_t s);

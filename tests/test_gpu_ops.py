@@ -143,6 +143,12 @@ TC_CASES = [
     (2, 64, 256, 32, 32, 1, False, False, 'tc'),
     (1, 128, 128, 96, 96, 3, True, False, 'tc'),
     (2, 128, 64, 12, 20, 3, True, True, 'tc'),
+    (2, 16, 16, 32, 32, 3, True, False, 'tc'),        # KC=16 (32B swizzle), BN=16
+    (1, 16, 32, 128, 128, 3, True, False, 'tc'),
+    (2, 32, 16, 16, 16, 3, True, True, 'tc'),
+    (3, 48, 48, 8, 8, 3, False, False, 'tc'),
+    (2, 64, 16, 8, 16, 3, True, False, 'tc'),
+    (2, 32, 32, 64, 64, 3, True, False, 'tc'),
 ]
 
 
@@ -192,6 +198,70 @@ def test_conv_tc_up2_out(rt):
     assert hp.shape == (2, 34, 34, 64)
     wantp = np.pad(_nhwc(want), ((0, 0), (1, 1), (1, 1), (0, 0)), mode='reflect')
     assert _nmax(hp, wantp) <= 1e-4
+
+
+@pytest.mark.parametrize('n,cin,cout,h,w', [(2, 64, 32, 16, 16), (2, 32, 16, 32, 32), (1, 64, 64, 8, 4),
+                                            (3, 16, 16, 6, 10), (2, 256, 64, 4, 4)])
+def test_conv_tc_upscale_subpixel_form(rt, n, cin, cout, h, w):
+    """conv3x3(upscale2d(x)) on the tensor-core kernel: low-res REPLICATE-halo planes, 4*Cout phase GEMM."""
+    from texturemixer_b200 import _lib
+    from texturemixer_b200.runtime import Act
+    rng = np.random.RandomState(n + cin + cout + h)
+    x = rng.randn(n, cin, h, w).astype(np.float32)
+    wt = rng.randn(3, 3, cin, cout).astype(np.float32)
+    b = (0.1 * rng.randn(cout)).astype(np.float32)
+    want = _oracle_conv(x, wt, b, R.SQRT2, True, None, up2=True)
+    out = _run_conv(rt, x, wt, b, R.SQRT2, True, None, True, _lib.ALGO_TC, want_split=True)
+    assert out.f32.shape == (n, 2 * h, 2 * w, cout)
+    assert _nmax(_nchw(out.f32.cpu().numpy()), want) <= 1e-4
+    hp = out.hi.float().cpu().numpy() + out.lo.float().cpu().numpy()
+    wantp = np.pad(_nhwc(want), ((0, 0), (1, 1), (1, 1), (0, 0)), mode='reflect')
+    assert _nmax(hp, wantp) <= 1e-4
+    # the exact-fp32 CUDA-core kernel reading through the upsampling agrees
+    ff = _run_conv(rt, x, wt, b, R.SQRT2, True, None, True, _lib.ALGO_FFMA)
+    assert _nmax(_nchw(ff.f32.cpu().numpy()), want) <= 1e-5
+
+
+def test_conv_tc_replicate_halo_and_split_pack(rt):
+    from texturemixer_b200 import _lib
+    from texturemixer_b200.runtime import Act
+    rng = np.random.RandomState(21)
+    x = rng.randn(2, 32, 8, 12).astype(np.float32)
+    wt = rng.randn(3, 3, 32, 32).astype(np.float32)
+    b = (0.1 * rng.randn(32)).astype(np.float32)
+    want = _oracle_conv(x, wt, b, R.SQRT2, True)
+    a = Act(2, 8, 12, 32, f32=_dev(_nhwc(x)))
+    out = rt.conv2d(a, _dev(wt), _dev(b), float(R.wscale_of(wt.shape)), 3, 32, lrelu=True, want_f32=False,
+                    want_split=True, halo_out='replicate', algo=_lib.ALGO_TC)
+    hp = out.hi.float().cpu().numpy() + out.lo.float().cpu().numpy()
+    wantp = np.pad(_nhwc(want), ((0, 0), (1, 1), (1, 1), (0, 0)), mode='edge')
+    assert out.halo == 'replicate' and _nmax(hp, wantp) <= 1e-4
+    b2 = rt.split_pack(Act(2, 8, 12, 32, f32=_dev(_nhwc(x))), 'replicate')
+    hp2 = b2.hi.float().cpu().numpy().astype(np.float64) + b2.lo.float().cpu().numpy()
+    xp = np.pad(_nhwc(x), ((0, 0), (1, 1), (1, 1), (0, 0)), mode='edge')
+    assert np.abs(hp2 - xp).max() <= 2.0 ** -16 * np.abs(xp).max()
+
+
+@pytest.mark.parametrize('cout,tanh', [(16, True), (32, False)])
+def test_conv_tc_fused_torgb(rt, cout, tanh):
+    from texturemixer_b200 import _lib
+    from texturemixer_b200.runtime import Act
+    rng = np.random.RandomState(22)
+    n, cin, h, w = 2, 16, 32, 16
+    x = rng.randn(n, cin, h, w).astype(np.float32)
+    wt = rng.randn(3, 3, cin, cout).astype(np.float32)
+    b = (0.1 * rng.randn(cout)).astype(np.float32)
+    wr = rng.randn(1, 1, cout, 3).astype(np.float32)
+    br = (0.1 * rng.randn(3)).astype(np.float32)
+    y = _oracle_conv(x, wt, b, R.SQRT2, True)
+    want = _oracle_conv(y, wr, br, 1.0, False)
+    if tanh:
+        want = np.tanh(want)
+    a = Act(n, h, w, cin, f32=_dev(_nhwc(x)))
+    out, img = rt.conv2d(a, _dev(wt), _dev(b), float(R.wscale_of(wt.shape)), 3, cout, lrelu=True, want_f32=True,
+                         algo=_lib.ALGO_TC, torgb=(_dev(wr), _dev(br), float(R.wscale_of(wr.shape, 1.0)), 3, tanh))
+    assert _nmax(_nchw(out.f32.cpu().numpy()), y) <= 1e-4
+    assert img.shape == (n, 3, h, w) and _nmax(img.cpu().numpy(), want) <= 1e-4
 
 
 # ---------------------------------------------------------------------- pointwise

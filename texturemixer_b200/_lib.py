@@ -6,10 +6,10 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'libtmx.so')
 
-TMX_ABI_VERSION = 1
+TMX_ABI_VERSION = 2
 
 # flags / enums (include/tmx.h)
-CONV_LRELU, CONV_RESIDUAL, CONV_UP2_IN, CONV_UP2_OUT = 1, 2, 4, 8
+CONV_LRELU, CONV_RESIDUAL, CONV_UP2_IN, CONV_UP2_OUT, CONV_HALO_REPLICATE, CONV_TORGB = 1, 2, 4, 8, 16, 32
 ALGO_AUTO, ALGO_FFMA, ALGO_TC, ALGO_TC_K32 = 0, 1, 2, 3
 BLEND_COPY, BLEND_MATTE, BLEND_LERP = 0, 1, 2
 
@@ -20,13 +20,15 @@ c_u16p = C.c_void_p
 class ConvDesc(C.Structure):
     _fields_ = [('N', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('Cin', C.c_int32), ('Cout', C.c_int32),
                 ('k', C.c_int32), ('flags', C.c_uint32), ('algo', C.c_int32), ('wscale', C.c_float),
-                ('lrelu_alpha', C.c_float)]
+                ('lrelu_alpha', C.c_float), ('rgb_cout', C.c_int32), ('rgb_tanh', C.c_int32),
+                ('rgb_wscale', C.c_float)]
 
 
 class ConvIO(C.Structure):
     _fields_ = [('x_f32', C.c_void_p), ('x_hi', C.c_void_p), ('x_lo', C.c_void_p), ('w', C.c_void_p),
                 ('w_hi', C.c_void_p), ('w_lo', C.c_void_p), ('bias', C.c_void_p), ('residual', C.c_void_p),
-                ('y_f32', C.c_void_p), ('y_hi', C.c_void_p), ('y_lo', C.c_void_p)]
+                ('y_f32', C.c_void_p), ('y_hi', C.c_void_p), ('y_lo', C.c_void_p), ('rgb_w', C.c_void_p),
+                ('rgb_b', C.c_void_p), ('y_rgb', C.c_void_p)]
 
 
 class BlendDesc(C.Structure):
@@ -51,8 +53,8 @@ _SIGNATURES = {
     'tmx_device_info': (C.c_int, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     'tmx_launch_count': (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     'tmx_conv2d_fwd': (C.c_int, [_P, C.POINTER(ConvDesc), C.POINTER(ConvIO), _P]),
-    'tmx_conv_weights_prepare': (C.c_int, [_P, _P, _F, _I, _I, _I, _P, _P, _P]),
-    'tmx_split_halo_pack': (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    'tmx_conv_weights_prepare': (C.c_int, [_P, _P, _F, _I, _I, _I, _I, _P, _P, _P]),
+    'tmx_split_halo_pack': (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'tmx_split_halo_unpack': (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     'tmx_fromrgb_fwd': (C.c_int, [_P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     'tmx_torgb_fwd': (C.c_int, [_P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _I, _P]),

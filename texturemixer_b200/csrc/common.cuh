@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/tmx.h"
 
@@ -48,6 +49,11 @@ int tmx_cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 static inline int tmx_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+// debugging / A-B switches read from the environment (unset or "0" = off)
+static inline bool tmx_env_flag(const char* name) {
+  const char* v = getenv(name);
+  return v != nullptr && v[0] != '\0' && v[0] != '0';
+}
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__

@@ -5,7 +5,7 @@
 #include "common.cuh"
 
 int tmx_conv2d_fwd_ffma(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_io_t* io, cudaStream_t st);
-int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_io_t* io, int kc, cudaStream_t st);
+int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_io_t* io, int kc_max, cudaStream_t st);
 
 extern "C" int tmx_conv2d_fwd(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_io_t* io, tmx_stream_t s) {
   TMX_REQUIRE(h && d && io, TMX_ERR_ARG, "tmx_conv2d_fwd: NULL argument");
@@ -15,7 +15,7 @@ extern "C" int tmx_conv2d_fwd(tmx_handle_t h, const tmx_conv_desc_t* d, const tm
   TMX_REQUIRE(d->k == 1 || (d->H >= 2 && d->W >= 2), TMX_ERR_SHAPE,
               "tmx_conv2d_fwd: REFLECT pad needs H, W >= 2 (got %d x %d)", d->H, d->W);
   const void* ptrs[] = {io->x_f32, io->x_hi, io->x_lo, io->w, io->w_hi, io->w_lo, io->bias, io->residual,
-                        io->y_f32, io->y_hi, io->y_lo};
+                        io->y_f32, io->y_hi, io->y_lo, io->y_rgb};
   for (const void* q : ptrs)
     TMX_REQUIRE(((uintptr_t)q & 15) == 0, TMX_ERR_ARG,
                 "tmx_conv2d_fwd: every buffer must be 16-byte aligned (got %p) - the kernels use 128-bit accesses", q);
@@ -24,7 +24,7 @@ extern "C" int tmx_conv2d_fwd(tmx_handle_t h, const tmx_conv_desc_t* d, const tm
   if (algo == TMX_ALGO_AUTO) algo = (io->x_hi != nullptr) ? TMX_ALGO_TC : TMX_ALGO_FFMA;
   switch (algo) {
     case TMX_ALGO_FFMA: return tmx_conv2d_fwd_ffma(h, d, io, st);
-    case TMX_ALGO_TC: return tmx_conv2d_fwd_tc(h, d, io, (d->Cin % 64 == 0) ? 64 : 32, st);
+    case TMX_ALGO_TC: return tmx_conv2d_fwd_tc(h, d, io, 64, st);
     case TMX_ALGO_TC_K32: return tmx_conv2d_fwd_tc(h, d, io, 32, st);
     default: return tmx_fail(TMX_ERR_ARG, "tmx_conv2d_fwd: unknown algo %d", d->algo);
   }

@@ -22,9 +22,17 @@
 //   warp 0 lane 0 : TMA producer     warp 1 lane 0 : MMA issuer
 //   warp 2        : TMEM allocator   warps 4-7     : epilogue (TMEM -> regs -> HBM)
 // Epilogue fusions: bias, leaky-ReLU, residual add (fp32 stream), fp32 NHWC
-// store, re-split into bf16 hi/lo planes INCLUDING the reflect halo of the next
-// layer (edge threads store their pixel to the mirrored halo slots too) and
-// optional nearest-neighbour x2 upsampling of the written planes.
+// store, re-split into bf16 hi/lo planes INCLUDING the halo of the next layer
+// (edge threads store their pixel to the mirrored / clamped halo slots too),
+// optional nearest-neighbour x2 upsampling of the written planes, and the 1x1
+// ToRGB head + tanh (networks.py:454-457, :483) written straight to NCHW.
+//
+// upscale2d + conv (networks.py:448-450) runs in sub-pixel form (UP2_IN): a 3x3
+// conv of the x2 nearest-upsampled image equals, per output parity (a,b), a conv
+// of the LOW-res image with taps summed pairwise, so the main loop is an
+// ordinary 3x3 GEMM over the low-res planes (REPLICATE halo) with N = 4*Cout
+// prepared weights and only the epilogue scatters column group (a,b) to pixel
+// (2y+a, 2x+b): a quarter of the activation traffic of the materialised form.
 #include "common.cuh"
 
 namespace {
@@ -122,25 +130,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major operand, hardware swizzle:
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major: 1) | [32,46) SBO>>4
-//   [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+//   [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B)
 // SBO = byte distance between 8-row groups = 8 * row_bytes (rows are dense).
 template <int KC>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   constexpr uint64_t row_bytes = KC * 2;
-  constexpr uint64_t layout = (KC == 64) ? 2 : 4;
+  constexpr uint64_t layout = (KC == 64) ? 2 : (KC == 32 ? 4 : 6);  // SWIZZLE_128B / 64B / 32B
   return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | (((8 * row_bytes) >> 4) << 32) | (1ull << 46) |
          (layout << 61);
 }
 // Instruction descriptor (kind::f16): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
 // A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
-template <int BN>
-__host__ __device__ constexpr uint32_t make_idesc() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 
 struct ConvTcParams {
@@ -148,13 +164,25 @@ struct ConvTcParams {
   int taps, k, pad_off;   // pad_off = 1 - k/2: halo offset of tap 0
   int bw, bh, bn;         // pixel patch of a tile: bw*bh*bn == 128
   int tiles_x, tiles_y, tiles_n, tiles_c, num_tiles;
+  // work items: the first full_items tiles are whole (BN columns); the tiles of the last, partial wave
+  // are split into `split` column slices of BN/split so that it still fills the SMs
+  int full_items, split, num_items;
   int lrelu, has_res, up2_out;
+  int phase;      // UP2_IN sub-pixel form: GEMM column = (a*2+b)*cout_log + c, output pixel (2y+a, 2x+b)
+  int cout_log;   // logical Cout of the layer (== Cout unless phase)
+  int halo_rep;   // written planes get a REPLICATE (clamp) halo instead of REFLECT
   float alpha;
   const float* bias;
   const float* residual;
   float* y_f32;
   uint16_t* y_hi;
   uint16_t* y_lo;
+  // fused ToRGB head
+  int rgb_c, rgb_tanh;
+  float rgb_wscale;
+  const float* rgb_w;
+  const float* rgb_b;
+  float* y_rgb;
 };
 
 template <int BN, int KC>
@@ -164,7 +192,7 @@ struct TcCfg {
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kSmemBudget = 200 * 1024;
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
   static constexpr int kAuxBytes = 1024;  // barriers + tmem ptr
   static constexpr int kSmemBytes = kStages * kStageBytes + kAuxBytes + 1024 /*align slack*/;
@@ -172,10 +200,24 @@ struct TcCfg {
   static_assert((kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns: power of two <= 512");
 };
 
-template <int BN, int KC>
+__device__ __forceinline__ void decode_item(const ConvTcParams& p, int item, int& tile, int& part, int& parts) {
+  if (item < p.full_items) {
+    tile = item;
+    part = 0;
+    parts = 1;
+  } else {
+    const int q = item - p.full_items;
+    tile = p.full_items + q / p.split;
+    part = q - (q / p.split) * p.split;
+    parts = p.split;
+  }
+}
+
+template <int BN, int KC, int GW>
 __global__ void __launch_bounds__(kThreads, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                   const __grid_constant__ CUtensorMap tm_bs_hi, const __grid_constant__ CUtensorMap tm_bs_lo,
                    const ConvTcParams p) {
   using Cfg = TcCfg<BN, KC>;
   constexpr int S = Cfg::kStages;
@@ -198,6 +240,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     tma_prefetch_desc(&tm_a_lo);
     tma_prefetch_desc(&tm_b_hi);
     tma_prefetch_desc(&tm_b_lo);
+    if (p.split > 1) {
+      tma_prefetch_desc(&tm_bs_hi);
+      tma_prefetch_desc(&tm_bs_lo);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
@@ -221,24 +267,30 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        int tile, part, parts;
+        decode_item(p, item, tile, part, parts);
         const int cblk = tile % p.tiles_c;
         int t = tile / p.tiles_c;
         const int x0 = (t % p.tiles_x) * p.bw;
         t /= p.tiles_x;
         const int y0 = (t % p.tiles_y) * p.bh;
         const int n0 = (t / p.tiles_y) * p.bn;
+        const CUtensorMap* mb_hi = parts > 1 ? &tm_bs_hi : &tm_b_hi;
+        const CUtensorMap* mb_lo = parts > 1 ? &tm_bs_lo : &tm_b_lo;
+        const int brow = cblk * BN + part * (BN / parts);
+        const uint32_t bytes = 2 * Cfg::kABytes + 2 * Cfg::kBBytes / parts;
         for (int ks = 0; ks < ksteps; ++ks) {
           const int tap = ks / cchunks;
           const int c0 = (ks - tap * cchunks) * KC;
           const int u = tap / p.k, v = tap - u * p.k;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          mbar_arrive_expect_tx(&full_bar[stage], bytes);
           tma_load_4d(sa, &tm_a_hi, &full_bar[stage], c0, x0 + v + p.pad_off, y0 + u + p.pad_off, n0);
           tma_load_4d(sa + Cfg::kABytes, &tm_a_lo, &full_bar[stage], c0, x0 + v + p.pad_off, y0 + u + p.pad_off, n0);
-          tma_load_2d(sa + 2 * Cfg::kABytes, &tm_b_hi, &full_bar[stage], tap * p.Cin + c0, cblk * BN);
-          tma_load_2d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &tm_b_lo, &full_bar[stage], tap * p.Cin + c0, cblk * BN);
+          tma_load_2d(sa + 2 * Cfg::kABytes, mb_hi, &full_bar[stage], tap * p.Cin + c0, brow);
+          tma_load_2d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, mb_lo, &full_bar[stage], tap * p.Cin + c0, brow);
           if (++stage == S) {
             stage = 0;
             phase ^= 1;
@@ -249,11 +301,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<BN>();
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        const uint32_t idesc = make_idesc(item < p.full_items ? BN : BN / p.split);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator
@@ -286,15 +338,23 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue =====================
+    // One thread = one tile row (pixel); columns are processed in groups of GW
+    // channels.  A group lies inside one output phase (a,b) when p.phase.
     const int quad = warp & 3;            // TMEM lane quadrant this warp may read
     const int r = quad * 32 + lane;       // row of the tile = pixel
     const int in_ = r / (p.bh * p.bw);
     const int rem = r - in_ * (p.bh * p.bw);
     const int iy = rem / p.bw, ix = rem - iy * p.bw;
-    const int Ho = p.up2_out ? 2 * p.H : p.H, Wo = p.up2_out ? 2 * p.W : p.W;
+    const int Hl = p.phase ? 2 * p.H : p.H, Wl = p.phase ? 2 * p.W : p.W;      // logical output size
+    const int Ho = p.up2_out ? 2 * Hl : Hl, Wo = p.up2_out ? 2 * Wl : Wl;      // size of the written planes
     const long long Hp = Ho + 2, Wp = Wo + 2;
+    const int CL = p.cout_log;
+    const int lo_edge = p.halo_rep ? 0 : 1;                // source row/col copied into halo slot 0
+    const int hi_off = p.halo_rep ? 1 : 2;                 // ... and (size - hi_off) into slot size+1
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      int tile, part, parts;
+      decode_item(p, item, tile, part, parts);
       const int cblk = tile % p.tiles_c;
       int t = tile / p.tiles_c;
       const int x = (t % p.tiles_x) * p.bw + ix;
@@ -305,44 +365,37 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
 
-      // target rows / cols of the split planes (interior + mirrored halo slots)
-      int rows[4], cols[4], nrows = 0, ncols = 0;
-      if (p.y_hi != nullptr) {
-        const int reps = p.up2_out ? 2 : 1;
-        for (int d = 0; d < reps; ++d) {
-          const int Y = p.up2_out ? 2 * y + d : y;
-          rows[nrows++] = Y + 1;
-          if (Y == 1) rows[nrows++] = 0;
-          if (Y == Ho - 2) rows[nrows++] = Ho + 1;
-          const int X = p.up2_out ? 2 * x + d : x;
-          cols[ncols++] = X + 1;
-          if (X == 1) cols[ncols++] = 0;
-          if (X == Wo - 2) cols[ncols++] = Wo + 1;
-        }
-      }
-
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-      const long long pix = ((long long)n * p.H + y) * p.W + x;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      const int ngroups = BN / parts / GW;
+      for (int g = 0; g < ngroups; ++g) {
         uint32_t acc[32];
-        tmem_ld32(taddr0 + ch * 32, acc);
+        if (GW == 32) tmem_ld32(taddr0 + g * GW, acc);
+        else tmem_ld16(taddr0 + g * GW, acc);
         tmem_ld_wait();
         if (valid) {
-          const int cbase = cblk * BN + ch * 32;
-          float v[32];
+          const int col0 = cblk * BN + part * (BN / parts) + g * GW;
+          int cbase = col0, oy = y, ox = x;
+          if (p.phase) {
+            const int ph = col0 / CL;
+            cbase = col0 - ph * CL;
+            oy = 2 * y + (ph >> 1);
+            ox = 2 * x + (ph & 1);
+          }
+          float v[GW];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < GW; ++j) {
             float f = __uint_as_float(acc[j]) + (p.bias ? __ldg(p.bias + cbase + j) : 0.f);
             if (p.lrelu) f = fmaxf(f * p.alpha, f);
             v[j] = f;
           }
+          const long long pix = ((long long)n * Hl + oy) * Wl + ox;
           if (p.has_res) {
-            const float4* rp = reinterpret_cast<const float4*>(p.residual + pix * p.Cout + cbase);
+            const float4* rp = reinterpret_cast<const float4*>(p.residual + pix * CL + cbase);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < GW / 4; ++j) {
               const float4 rr = __ldg(rp + j);
               v[4 * j] += rr.x;
               v[4 * j + 1] += rr.y;
@@ -351,14 +404,27 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           }
           if (p.y_f32 != nullptr) {
-            float4* op = reinterpret_cast<float4*>(p.y_f32 + pix * p.Cout + cbase);
+            float4* op = reinterpret_cast<float4*>(p.y_f32 + pix * CL + cbase);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < GW / 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
           if (p.y_hi != nullptr) {
-            uint32_t ph[16], pl[16];
+            // target rows / cols of the split planes: interior + halo slots this pixel feeds
+            int rows[4], cols[4], nrows = 0, ncols = 0;
+            const int reps = p.up2_out ? 2 : 1;
+            for (int d = 0; d < reps; ++d) {
+              const int Y = p.up2_out ? 2 * oy + d : oy;
+              rows[nrows++] = Y + 1;
+              if (Y == lo_edge) rows[nrows++] = 0;
+              if (Y == Ho - hi_off) rows[nrows++] = Ho + 1;
+              const int X = p.up2_out ? 2 * ox + d : ox;
+              cols[ncols++] = X + 1;
+              if (X == lo_edge) cols[ncols++] = 0;
+              if (X == Wo - hi_off) cols[ncols++] = Wo + 1;
+            }
+            uint32_t ph[GW / 2], pl[GW / 2];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < GW / 2; ++j) {
               uint32_t h0, l0, h1, l1;
               tmx_split_bf16(v[2 * j], h0, l0);
               tmx_split_bf16(v[2 * j + 1], h1, l1);
@@ -367,15 +433,29 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             for (int a = 0; a < nrows; ++a) {
               for (int b = 0; b < ncols; ++b) {
-                const long long o = (((long long)n * Hp + rows[a]) * Wp + cols[b]) * p.Cout + cbase;
+                const long long o = (((long long)n * Hp + rows[a]) * Wp + cols[b]) * CL + cbase;
                 uint4* oh = reinterpret_cast<uint4*>(p.y_hi + o);
                 uint4* ol = reinterpret_cast<uint4*>(p.y_lo + o);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < GW / 8; ++j) {
                   oh[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
                   ol[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
                 }
               }
+            }
+          }
+          if (p.y_rgb != nullptr) {
+            // ToRGB 1x1 head on the fp32 activations of this pixel (host guarantees CL == GW)
+            float rgb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < GW; ++j) {
+              for (int o = 0; o < p.rgb_c; ++o) rgb[o] = fmaf(v[j], __ldg(p.rgb_w + (cbase + j) * p.rgb_c + o), rgb[o]);
+            }
+            const long long hw = (long long)Hl * Wl;
+            for (int o = 0; o < p.rgb_c; ++o) {
+              float f = rgb[o] * p.rgb_wscale + (p.rgb_b ? __ldg(p.rgb_b + o) : 0.f);
+              if (p.rgb_tanh) f = tanhf(f);
+              p.y_rgb[((long long)n * p.rgb_c + o) * hw + (long long)oy * Wl + ox] = f;
             }
           }
         }
@@ -395,13 +475,17 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 // ---------------------------------------------------------------- host side
+CUtensorMapSwizzle swizzle_of(int kc) {
+  return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
 int encode_act_map(tmx_handle_t h, CUtensorMap* m, const uint16_t* base, int N, int Hp, int Wp, int C, int kc, int bw,
                    int bh, int bn) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
   cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMapSwizzle sw = swizzle_of(kc);
   CUresult r = h->encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -416,7 +500,7 @@ int encode_wgt_map(tmx_handle_t h, CUtensorMap* m, const uint16_t* base, int Cou
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
   cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)bnc};
   cuuint32_t estr[2] = {1, 1};
-  CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMapSwizzle sw = swizzle_of(kc);
   CUresult r = h->encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -432,10 +516,10 @@ int gcd_pow2(int v, int cap) {  // largest power of two dividing v, at most cap
   return g;
 }
 
-template <int BN, int KC>
+template <int BN, int KC, int GW>
 int launch_tc(tmx_handle_t h, const CUtensorMap* maps, const ConvTcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BN, KC>;
-  auto kern = conv_tc_kernel<BN, KC>;
+  auto kern = conv_tc_kernel<BN, KC, GW>;
   static thread_local int configured_device = -1;
   if (configured_device != h->device) {
     TMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -444,82 +528,139 @@ int launch_tc(tmx_handle_t h, const CUtensorMap* maps, const ConvTcParams& p, cu
   TMX_REQUIRE(Cfg::kSmemBytes <= h->max_smem_optin, TMX_ERR_UNSUPPORTED,
               "tmx_conv2d_fwd[TC]: kernel needs %d B shared memory, device allows %d", Cfg::kSmemBytes,
               h->max_smem_optin);
-  int grid = p.num_tiles < h->sm_count ? p.num_tiles : h->sm_count;
-  kern<<<grid, kThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  int grid = p.num_items < h->sm_count ? p.num_items : h->sm_count;
+  kern<<<grid, kThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   TMX_LAUNCHED(h, "conv_tc_kernel");
   return TMX_OK;
 }
 
 }  // namespace
 
-int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_io_t* io, int kc, cudaStream_t st) {
+int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_io_t* io, int kc_max, cudaStream_t st) {
+  const bool phase = (d->flags & TMX_CONV_UP2_IN) != 0;
+  const bool torgb = (d->flags & TMX_CONV_TORGB) != 0;
   TMX_REQUIRE(io->x_hi && io->x_lo && io->w_hi && io->w_lo, TMX_ERR_ARG,
               "tmx_conv2d_fwd[TC]: x_hi/x_lo (SPLIT_BF16_HALO) and w_hi/w_lo (prepared) are required");
-  TMX_REQUIRE(io->y_f32 || (io->y_hi && io->y_lo), TMX_ERR_ARG, "tmx_conv2d_fwd[TC]: no output");
+  TMX_REQUIRE(io->y_f32 || (io->y_hi && io->y_lo) || (torgb && io->y_rgb), TMX_ERR_ARG,
+              "tmx_conv2d_fwd[TC]: no output");
   TMX_REQUIRE((io->y_hi == nullptr) == (io->y_lo == nullptr), TMX_ERR_ARG,
               "tmx_conv2d_fwd[TC]: y_hi and y_lo go together");
-  TMX_REQUIRE(!(d->flags & TMX_CONV_UP2_IN), TMX_ERR_UNSUPPORTED,
-              "tmx_conv2d_fwd[TC]: UP2_IN is not supported; use UP2_OUT on the producing layer");
   TMX_REQUIRE(!(d->flags & TMX_CONV_UP2_OUT) || io->y_hi, TMX_ERR_ARG,
               "tmx_conv2d_fwd[TC]: UP2_OUT applies to the split-plane output");
+  TMX_REQUIRE(!(phase && (d->flags & TMX_CONV_UP2_OUT)), TMX_ERR_UNSUPPORTED,
+              "tmx_conv2d_fwd[TC]: UP2_IN and UP2_OUT cannot be combined");
+  TMX_REQUIRE(!((d->flags & TMX_CONV_HALO_REPLICATE) && (d->flags & TMX_CONV_UP2_OUT)), TMX_ERR_UNSUPPORTED,
+              "tmx_conv2d_fwd[TC]: HALO_REPLICATE and UP2_OUT cannot be combined");
   TMX_REQUIRE(!(d->flags & TMX_CONV_RESIDUAL) || io->residual, TMX_ERR_ARG,
               "tmx_conv2d_fwd[TC]: RESIDUAL flag without residual pointer");
-  TMX_REQUIRE(kc == 64 || kc == 32, TMX_ERR_ARG, "tmx_conv2d_fwd[TC]: K chunk must be 32 or 64");
-  TMX_REQUIRE(d->Cin % kc == 0, TMX_ERR_SHAPE, "tmx_conv2d_fwd[TC]: Cin=%d must be a multiple of %d", d->Cin, kc);
-  TMX_REQUIRE(d->H >= 2 && d->W >= 2, TMX_ERR_SHAPE, "tmx_conv2d_fwd[TC]: H, W >= 2 (REFLECT)");
+  TMX_REQUIRE(!phase || (d->k == 3 && d->H % 2 == 0 && d->W % 2 == 0), TMX_ERR_SHAPE,
+              "tmx_conv2d_fwd[TC]: UP2_IN needs k == 3 and even H, W (got k=%d, %d x %d)", d->k, d->H, d->W);
+  TMX_REQUIRE(d->Cin % 16 == 0 && d->Cout % 16 == 0, TMX_ERR_SHAPE,
+              "tmx_conv2d_fwd[TC]: Cin=%d and Cout=%d must be multiples of 16", d->Cin, d->Cout);
+  int kc = d->Cin % 64 == 0 ? 64 : (d->Cin % 32 == 0 ? 32 : 16);
+  if (kc > kc_max) kc = kc_max;
+  // stored (GEMM-side) geometry
+  const int Hs = phase ? d->H / 2 : d->H, Ws = phase ? d->W / 2 : d->W;
+  const int Ng = phase ? 4 * d->Cout : d->Cout;  // GEMM N
+  TMX_REQUIRE(Hs >= 2 && Ws >= 2, TMX_ERR_SHAPE, "tmx_conv2d_fwd[TC]: stored H, W >= 2 (halo)");
+  const int gw = d->Cout % 32 == 0 ? 32 : 16;
   int bnc;
-  if (d->Cout % 256 == 0) bnc = 256;
-  else if (d->Cout % 128 == 0) bnc = 128;
-  else if (d->Cout % 64 == 0) bnc = 64;
-  else if (d->Cout % 32 == 0) bnc = 32;
-  else return tmx_fail(TMX_ERR_SHAPE, "tmx_conv2d_fwd[TC]: Cout=%d must be a multiple of 32", d->Cout);
+  if (Ng % 256 == 0) bnc = 256;
+  else if (Ng % 128 == 0) bnc = 128;
+  else if (Ng % 64 == 0) bnc = 64;
+  else if (Ng % 32 == 0) bnc = 32;
+  else bnc = 16;
+  if (torgb) {
+    TMX_REQUIRE(io->rgb_w && io->y_rgb && d->rgb_cout >= 1 && d->rgb_cout <= 4, TMX_ERR_ARG,
+                "tmx_conv2d_fwd[TC]: TORGB needs rgb_w, y_rgb and 1 <= rgb_cout <= 4");
+    TMX_REQUIRE(d->Cout == gw, TMX_ERR_SHAPE,
+                "tmx_conv2d_fwd[TC]: TORGB needs Cout in {16, 32} (one column group per pixel), got %d", d->Cout);
+  }
 
   ConvTcParams p;
   p.N = d->N;
-  p.H = d->H;
-  p.W = d->W;
+  p.H = Hs;
+  p.W = Ws;
   p.Cin = d->Cin;
-  p.Cout = d->Cout;
+  p.Cout = Ng;
   p.k = d->k;
   p.taps = d->k * d->k;
   p.pad_off = 1 - d->k / 2;
-  p.bw = gcd_pow2(d->W, 32);
-  p.bh = gcd_pow2(d->H, kTileM / p.bw);
+  p.bw = gcd_pow2(Ws, 32);
+  p.bh = gcd_pow2(Hs, kTileM / p.bw);
   p.bn = kTileM / (p.bw * p.bh);
-  p.tiles_x = d->W / p.bw;
-  p.tiles_y = d->H / p.bh;
+  p.tiles_x = Ws / p.bw;
+  p.tiles_y = Hs / p.bh;
   p.tiles_n = (d->N + p.bn - 1) / p.bn;
-  p.tiles_c = d->Cout / bnc;
+  p.tiles_c = Ng / bnc;
   long long nt = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_c;
   TMX_REQUIRE(nt < (1ll << 31), TMX_ERR_SHAPE, "tmx_conv2d_fwd[TC]: too many tiles");
   p.num_tiles = (int)nt;
+  // last-wave split: T tiles over G SMs leave R = T mod G tiles for a final, partly empty wave; cut those
+  // into 2 or 4 column slices (>= 32 columns, whole epilogue groups) when that lets the wave fill the SMs
+  {
+    const int G = h->sm_count;
+    const int R = p.num_tiles % G;
+    p.split = 1;
+    if (R > 0 && !tmx_env_flag("TMX_NO_SPLIT")) {
+      for (int sp = 4; sp >= 2; sp /= 2) {
+        const int bs = bnc / sp;
+        if (bs >= 32 && bs % gw == 0 && (long long)R * sp <= G) {
+          p.split = sp;
+          break;
+        }
+      }
+    }
+    p.full_items = p.split > 1 ? p.num_tiles - R : p.num_tiles;
+    p.num_items = p.full_items + (p.split > 1 ? R * p.split : 0);
+  }
   p.lrelu = (d->flags & TMX_CONV_LRELU) != 0;
   p.has_res = (d->flags & TMX_CONV_RESIDUAL) != 0;
   p.up2_out = (d->flags & TMX_CONV_UP2_OUT) != 0;
+  p.phase = phase;
+  p.cout_log = d->Cout;
+  p.halo_rep = (d->flags & TMX_CONV_HALO_REPLICATE) != 0;
   p.alpha = d->lrelu_alpha;
   p.bias = io->bias;
   p.residual = io->residual;
   p.y_f32 = io->y_f32;
   p.y_hi = io->y_hi;
   p.y_lo = io->y_lo;
+  p.rgb_c = torgb ? d->rgb_cout : 0;
+  p.rgb_tanh = d->rgb_tanh;
+  p.rgb_wscale = d->rgb_wscale;
+  p.rgb_w = torgb ? io->rgb_w : nullptr;
+  p.rgb_b = torgb ? io->rgb_b : nullptr;
+  p.y_rgb = torgb ? io->y_rgb : nullptr;
 
-  CUtensorMap maps[4];
+  CUtensorMap maps[6];
   int rc;
-  if ((rc = encode_act_map(h, &maps[0], io->x_hi, d->N, d->H + 2, d->W + 2, d->Cin, kc, p.bw, p.bh, p.bn))) return rc;
-  if ((rc = encode_act_map(h, &maps[1], io->x_lo, d->N, d->H + 2, d->W + 2, d->Cin, kc, p.bw, p.bh, p.bn))) return rc;
-  if ((rc = encode_wgt_map(h, &maps[2], io->w_hi, d->Cout, p.taps * d->Cin, kc, bnc))) return rc;
-  if ((rc = encode_wgt_map(h, &maps[3], io->w_lo, d->Cout, p.taps * d->Cin, kc, bnc))) return rc;
+  if ((rc = encode_act_map(h, &maps[0], io->x_hi, d->N, Hs + 2, Ws + 2, d->Cin, kc, p.bw, p.bh, p.bn))) return rc;
+  if ((rc = encode_act_map(h, &maps[1], io->x_lo, d->N, Hs + 2, Ws + 2, d->Cin, kc, p.bw, p.bh, p.bn))) return rc;
+  if ((rc = encode_wgt_map(h, &maps[2], io->w_hi, Ng, p.taps * d->Cin, kc, bnc))) return rc;
+  if ((rc = encode_wgt_map(h, &maps[3], io->w_lo, Ng, p.taps * d->Cin, kc, bnc))) return rc;
+  if ((rc = encode_wgt_map(h, &maps[4], io->w_hi, Ng, p.taps * d->Cin, kc, bnc / p.split))) return rc;
+  if ((rc = encode_wgt_map(h, &maps[5], io->w_lo, Ng, p.taps * d->Cin, kc, bnc / p.split))) return rc;
 
-#define TMX_TC_CASE(BN_, KC_) \
-  if (bnc == BN_ && kc == KC_) return launch_tc<BN_, KC_>(h, maps, p, st);
-  TMX_TC_CASE(256, 64)
-  TMX_TC_CASE(256, 32)
-  TMX_TC_CASE(128, 64)
-  TMX_TC_CASE(128, 32)
-  TMX_TC_CASE(64, 64)
-  TMX_TC_CASE(64, 32)
-  TMX_TC_CASE(32, 64)
-  TMX_TC_CASE(32, 32)
+#define TMX_TC_CASE(BN_, KC_, GW_) \
+  if (bnc == BN_ && kc == KC_ && gw == GW_) return launch_tc<BN_, KC_, GW_>(h, maps, p, st);
+  TMX_TC_CASE(256, 64, 32)
+  TMX_TC_CASE(256, 32, 32)
+  TMX_TC_CASE(128, 64, 32)
+  TMX_TC_CASE(128, 32, 32)
+  TMX_TC_CASE(64, 64, 32)
+  TMX_TC_CASE(64, 32, 32)
+  TMX_TC_CASE(64, 16, 32)
+  TMX_TC_CASE(32, 64, 32)
+  TMX_TC_CASE(32, 32, 32)
+  TMX_TC_CASE(32, 16, 32)
+  TMX_TC_CASE(64, 64, 16)
+  TMX_TC_CASE(64, 32, 16)
+  TMX_TC_CASE(64, 16, 16)
+  TMX_TC_CASE(16, 64, 16)
+  TMX_TC_CASE(16, 32, 16)
+  TMX_TC_CASE(16, 16, 16)
 #undef TMX_TC_CASE
-  return tmx_fail(TMX_ERR_UNSUPPORTED, "tmx_conv2d_fwd[TC]: no kernel for BN=%d KC=%d", bnc, kc);
+  return tmx_fail(TMX_ERR_UNSUPPORTED, "tmx_conv2d_fwd[TC]: no kernel for BN=%d KC=%d GW=%d (Cin=%d Cout=%d)", bnc, kc,
+                  gw, d->Cin, d->Cout);
 }

@@ -212,7 +212,7 @@ extern "C" int tmx_nhwc_to_nchw(tmx_handle_t h, const float* x, float* y, int N,
 // One thread = one padded pixel x 8 channels (2 float4 in, 16 B hi + 16 B lo out).
 __global__ void __launch_bounds__(256) split_halo_pack_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi,
                                                               uint16_t* __restrict__ lo, long long total, int H, int W,
-                                                              int C8) {
+                                                              int C8, int replicate) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   int c8 = (int)(t % C8);
@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(256) split_halo_pack_kernel(const float* __res
   long long q = p / Wp;
   int yp = (int)(q % Hp);
   long long n = q / Hp;
-  int ys = tmx_reflect(yp - 1, H), xs = tmx_reflect(xp - 1, W);
+  int ys = replicate ? min(max(yp - 1, 0), H - 1) : tmx_reflect(yp - 1, H);
+  int xs = replicate ? min(max(xp - 1, 0), W - 1) : tmx_reflect(xp - 1, W);
   const float4* src = reinterpret_cast<const float4*>(x) + ((n * H + ys) * W + xs) * (C8 * 2) + c8 * 2;
   float4 a = __ldg(src), b = __ldg(src + 1);
   float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -266,12 +267,13 @@ __global__ void __launch_bounds__(256) split_halo_unpack_kernel(const uint16_t* 
 }
 
 extern "C" int tmx_split_halo_pack(tmx_handle_t h, const float* x, uint16_t* hi, uint16_t* lo, int N, int H, int W,
-                                   int C, tmx_stream_t s) {
+                                   int C, int replicate, tmx_stream_t s) {
   TMX_REQUIRE(h && x && hi && lo, TMX_ERR_ARG, "tmx_split_halo_pack: NULL argument");
   TMX_REQUIRE(N > 0 && H >= 2 && W >= 2 && C > 0 && C % 8 == 0, TMX_ERR_SHAPE,
               "tmx_split_halo_pack: bad shape N=%d H=%d W=%d C=%d (H, W >= 2; C %% 8 == 0)", N, H, W, C);
   long long total = (long long)N * (H + 2) * (W + 2) * (C / 8);
-  split_halo_pack_kernel<<<tmx_ceil_div(total, 256), 256, 0, (cudaStream_t)s>>>(x, hi, lo, total, H, W, C / 8);
+  split_halo_pack_kernel<<<tmx_ceil_div(total, 256), 256, 0, (cudaStream_t)s>>>(x, hi, lo, total, H, W, C / 8,
+                                                                                replicate);
   TMX_LAUNCHED(h, "split_halo_pack_kernel");
   return TMX_OK;
 }
@@ -314,11 +316,47 @@ __global__ void __launch_bounds__(256) weights_prepare_kernel(const float* __res
   }
 }
 
+// Sub-pixel weights of conv3x3(upscale2d(x)) (see tmx.h): out [4*Cout][9*Cin], one thread per element.
+__global__ void __launch_bounds__(256) weights_prepare_phase_kernel(const float* __restrict__ w, float wscale,
+                                                                    uint16_t* __restrict__ hi,
+                                                                    uint16_t* __restrict__ lo, int Cin, int Cout) {
+  const long long K = 9ll * Cin;
+  const long long total = 4ll * Cout * K;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int kk = (int)(t % K);
+  const int row = (int)(t / K);
+  const int c = kk % Cin, tap = kk / Cin;
+  const int U = tap / 3, V = tap % 3;
+  const int o = row % Cout, ph = row / Cout;
+  const int a = ph >> 1, b = ph & 1;
+  // upsampled taps u that land on low-res offset U-1 for output parity a: a=0: {0},{1,2},{}; a=1: {},{0,1},{2}
+  const int u0 = a == 0 ? (U == 0 ? 0 : (U == 1 ? 1 : 3)) : (U == 0 ? 3 : (U == 1 ? 0 : 2));
+  const int u1 = a == 0 ? (U == 0 ? 0 : (U == 1 ? 2 : 2)) : (U == 0 ? 2 : (U == 1 ? 1 : 2));
+  const int v0 = b == 0 ? (V == 0 ? 0 : (V == 1 ? 1 : 3)) : (V == 0 ? 3 : (V == 1 ? 0 : 2));
+  const int v1 = b == 0 ? (V == 0 ? 0 : (V == 1 ? 2 : 2)) : (V == 0 ? 2 : (V == 1 ? 1 : 2));
+  float acc = 0.f;
+  for (int u = u0; u <= u1; ++u)
+    for (int v = v0; v <= v1; ++v) acc += __ldg(w + ((long long)(u * 3 + v) * Cin + c) * Cout + o);
+  uint32_t x, y;
+  tmx_split_bf16(acc * wscale, x, y);
+  hi[t] = (uint16_t)x;
+  lo[t] = (uint16_t)y;
+}
+
 extern "C" int tmx_conv_weights_prepare(tmx_handle_t h, const float* w, float wscale, int k, int Cin, int Cout,
-                                        uint16_t* w_hi, uint16_t* w_lo, tmx_stream_t s) {
+                                        int up2_phase, uint16_t* w_hi, uint16_t* w_lo, tmx_stream_t s) {
   TMX_REQUIRE(h && w && w_hi && w_lo, TMX_ERR_ARG, "tmx_conv_weights_prepare: NULL argument");
   TMX_REQUIRE((k == 1 || k == 3) && Cin > 0 && Cout > 0, TMX_ERR_SHAPE,
               "tmx_conv_weights_prepare: bad shape k=%d Cin=%d Cout=%d", k, Cin, Cout);
+  if (up2_phase) {
+    TMX_REQUIRE(k == 3, TMX_ERR_SHAPE, "tmx_conv_weights_prepare: up2_phase needs k == 3");
+    long long total = 36ll * Cin * Cout;
+    weights_prepare_phase_kernel<<<tmx_ceil_div(total, 256), 256, 0, (cudaStream_t)s>>>(w, wscale, w_hi, w_lo, Cin,
+                                                                                       Cout);
+    TMX_LAUNCHED(h, "weights_prepare_phase_kernel");
+    return TMX_OK;
+  }
   int K = k * k * Cin;
   dim3 grid(tmx_ceil_div(K, 32), tmx_ceil_div(Cout, 32));
   weights_prepare_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(w, wscale, w_hi, w_lo, K, Cout);

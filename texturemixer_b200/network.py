@@ -68,10 +68,11 @@ class T:
     """Tensor handle seen by build functions: a static NCHW shape (None batch
     in template mode) plus, in run mode, the device payload - either an
     external NCHW torch tensor (`nchw`) or an internal activation (`act`)."""
-    __slots__ = ('shape', 'ctx', 'nchw', 'act', 'name')
+    __slots__ = ('shape', 'ctx', 'nchw', 'act', 'name', 'rgb')
 
     def __init__(self, shape, ctx, nchw=None, act=None, name=None):
         self.shape, self.ctx, self.nchw, self.act, self.name = list(shape), ctx, nchw, act, name
+        self.rgb = None      # images already produced by a fused ToRGB epilogue: (scope, tanh, NCHW tensor)
 
     def set_shape(self, shape):
         """tf.Tensor.set_shape: fixes the template shape / checks the fed one
@@ -303,14 +304,15 @@ class Network:
         net.copy_vars_from(self)
         return net
 
-    def prepared_weights(self, var, wscale, k, cin, cout):
-        """Cached bf16 hi/lo planes of a conv weight for the tensor-core kernel;
-        recomputed when any variable of the owning network changed."""
+    def prepared_weights(self, var, wscale, k, cin, cout, up2_phase=False):
+        """Cached bf16 hi/lo planes of a conv weight for the tensor-core kernel
+        (sub-pixel planes when the conv reads through upscale2d); recomputed
+        when any variable of the owning network changed."""
         o = self._owner()
-        key = (var.name, float(wscale))
+        key = (var.name, float(wscale), bool(up2_phase))
         ent = o._prepared.get(key)
         if ent is None or ent[2] != o._version:
-            hi, lo = self.rt.prepare_weights(var.value, wscale, k, cin, cout)
+            hi, lo = self.rt.prepare_weights(var.value, wscale, k, cin, cout, up2_phase=up2_phase)
             ent = (hi, lo, o._version)
             o._prepared[key] = ent
         return ent[0], ent[1]

@@ -42,12 +42,13 @@ def _act_of(t):
 
 
 def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=False, next_tc=False,
-                 next_up2=False, keep_f32=False):
+                 next_up2=False, keep_f32=False, torgb=None):
     """act(apply_bias(conv2d(x))) [+ residual] under the current variable scope:
     networks.py:48-56 + 61-67 + 72-75 (+ :437).  `up2`: the logical input is
-    upscale2d(x) (networks.py:448).  `next_tc`/`next_up2` are layout hints: the
-    consumer is a tensor-core conv (wants split-bf16 halo planes), optionally
-    through an upscale2d."""
+    upscale2d(x) (networks.py:448), never materialised.  `next_tc`/`next_up2` are
+    layout hints: the consumer is a tensor-core conv (wants split-bf16 planes),
+    reading through an upscale2d (wants a REPLICATE halo).  `torgb` =
+    (scope, num_channels, tanh): fuse that 1x1 image head into the epilogue."""
     assert kernel >= 1 and kernel % 2 == 1                                # networks.py:49
     ctx = x.ctx
     cin = x.shape[1]
@@ -62,23 +63,30 @@ def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=Fals
     rt = ctx.rt
     xa = _act_of(x)
     ws = _wscale(w.shape, gain)
-    algo = rt.choose_algo(cin, fmaps, kernel, up2)
+    algo = rt.choose_algo(cin, fmaps, kernel, up2, (xa.h, xa.w))
     prepared = None
     if algo != 1:  # tensor-core path: cached bf16 hi/lo weight planes
-        prepared = ctx.net.prepared_weights(w, ws, kernel, cin, fmaps)
+        prepared = ctx.net.prepared_weights(w, ws, kernel, cin, fmaps, up2_phase=up2)
     res = None if residual is None else rt.split_unpack(_act_of(residual)).f32
+    head = None
+    if torgb is not None and algo != 1:
+        scope, nch, tanh = torgb
+        wr, br = ctx.net.vars[scope + '/weight'], ctx.net.vars[scope + '/bias']
+        head = (wr.value, br.value, _wscale(wr.shape, 1.0), nch, tanh)
     out = rt.conv2d(xa, w.value, b.value, ws, kernel, fmaps, lrelu=act, residual=res, up2=up2,
-                    want_f32=(not next_tc) or keep_f32, want_split=next_tc, up2_out=next_up2, algo=algo, prepared=prepared)
-    return T(shape, ctx, act=out)
+                    want_f32=((not next_tc) and head is None) or keep_f32, want_split=next_tc,
+                    halo_out='replicate' if next_up2 else 'reflect', algo=algo, prepared=prepared, torgb=head)
+    t = T(shape, ctx)
+    if head is not None:
+        t.act, images = out
+        t.rgb = (torgb[0], torgb[2], images)
+    else:
+        t.act = out
+    return t
 
 
 def _mul(d, f):
     return None if d is None else d * f
-
-
-def upscale2d_pending(x):
-    """networks.py:80-88 is never materialised: the consumer conv reads through it."""
-    return x
 
 
 def downscale2d(x, factor=2):
@@ -303,18 +311,25 @@ def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_bas
                 with ctx.variable_scope('Conv0'):
                     x = conv2d_layer(x, nf(res - 1), 3, gain=SQRT2 / 4, next_tc=_tc(ctx, nf(res - 1), nf(res - 1), 3))
                 with ctx.variable_scope('Conv1'):
-                    up_next = res < resolution_log2
-                    ntc = up_next and _tc(ctx, nf(res - 1), nf(res), 3)
-                    x = conv2d_layer(x, nf(res - 1), 3, next_tc=ntc, next_up2=ntc)
+                    x = last_conv(x, res)
             else:
                 with ctx.variable_scope('Conv0'):                          # upscale2d + conv2d (networks.py:448-450)
-                    pre_up = ctx.mode == 'run' and x.act.hi is not None and x.act.hi.shape[1] == 2 * x.act.h + 2
-                    x = _conv_after_up(x, nf(res - 1), pre_up, next_tc=_tc(ctx, nf(res - 1), nf(res - 1), 3))
+                    x = conv2d_layer(x, nf(res - 1), 3, up2=True, next_tc=_tc(ctx, nf(res - 1), nf(res - 1), 3))
                 with ctx.variable_scope('Conv1'):
-                    up_next = res < resolution_log2
-                    ntc = up_next and _tc(ctx, nf(res - 1), nf(res), 3)
-                    x = conv2d_layer(x, nf(res - 1), 3, next_tc=ntc, next_up2=ntc)
+                    x = last_conv(x, res)
             return x
+
+    def last_conv(x, res):
+        """Conv1 of a block: its consumer is either the next block's upscale2d+Conv0
+        (hand over REPLICATE-halo planes) or, at the output resolution with lod == 0,
+        the ToRGB head + tanh (fused into the epilogue)."""
+        if res < resolution_log2:
+            ntc = _tc(ctx, nf(res - 1), nf(res), 3, up2=True)
+            return conv2d_layer(x, nf(res - 1), 3, next_tc=ntc, next_up2=ntc)
+        head = None
+        if ctx.mode == 'run' and lod_in == 0 and nf(res - 1) in (16, 32) and _tc(ctx, nf(res - 1), nf(res - 1), 3):
+            head = ('ToRGB_lod0', num_channels, bool(tanh_at_end))
+        return conv2d_layer(x, nf(res - 1), 3, torgb=head)
 
     def torgb(x, res, apply_tanh=False):
         lod = resolution_log2 - res
@@ -325,6 +340,8 @@ def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_bas
             shape = [x.shape[0], num_channels, x.shape[2], x.shape[3]]
             if ctx.mode == 'template':
                 return T(shape, ctx)
+            if x.rgb is not None and x.rgb[0] == 'ToRGB_lod%d' % lod and x.rgb[1] == bool(apply_tanh):
+                return T(shape, ctx, nchw=x.rgb[2])                        # produced by the conv epilogue
             img = ctx.rt.torgb(_act_of(x), w.value, b.value, _wscale(w.shape, 1.0), num_channels, apply_tanh)
             return T(shape, ctx, nchw=img)
 
@@ -368,19 +385,6 @@ def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_bas
         raise NotImplementedError('G_res at lod != 0 is not implemented (SURVEY N1)')
     images_out.name = 'images_out'
     return images_out
-
-
-def _conv_after_up(x, fmaps, pre_upscaled, next_tc):
-    """conv2d(upscale2d(x)).  If the producer already wrote its split planes x2
-    upsampled (TMX_CONV_UP2_OUT) the conv is a plain tensor-core conv on them;
-    otherwise the CUDA-core kernel reads through the upsampling (TMX_CONV_UP2_IN)."""
-    ctx = x.ctx
-    if ctx.mode == 'run' and pre_upscaled:
-        a = x.act
-        up = Act(a.n, a.h * 2, a.w * 2, a.c, hi=a.hi, lo=a.lo)
-        xs = T([x.shape[0], x.shape[1], x.shape[2] * 2, x.shape[3] * 2], ctx, act=up)
-        return conv2d_layer(xs, fmaps, 3, next_tc=next_tc)
-    return conv2d_layer(x, fmaps, 3, up2=True, next_tc=next_tc)
 
 
 # ---------------------------------------------------------------------- D_patch (networks.py:491-577)

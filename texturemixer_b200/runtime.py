@@ -19,12 +19,13 @@ def _ptr(t):
 class Act:
     """A device activation in one or both internal layouts.
     f32: torch.float32 [N,H,W,C] (NHWC) ; hi/lo: torch.bfloat16 [N,H+2,W+2,C]
-    (SPLIT_BF16_HALO: x ~= hi + lo, REFLECT halo materialised)."""
-    __slots__ = ('n', 'h', 'w', 'c', 'f32', 'hi', 'lo')
+    (SPLIT_BF16_HALO: x ~= hi + lo, halo materialised: 'reflect' for a 3x3
+    consumer, 'replicate' for a consumer that reads through upscale2d)."""
+    __slots__ = ('n', 'h', 'w', 'c', 'f32', 'hi', 'lo', 'halo')
 
-    def __init__(self, n, h, w, c, f32=None, hi=None, lo=None):
+    def __init__(self, n, h, w, c, f32=None, hi=None, lo=None, halo='reflect'):
         self.n, self.h, self.w, self.c = n, h, w, c
-        self.f32, self.hi, self.lo = f32, hi, lo
+        self.f32, self.hi, self.lo, self.halo = f32, hi, lo, halo
 
     @property
     def shape_nchw(self):
@@ -97,13 +98,17 @@ class Runtime:
                                              self.stream()), 'tmx_nhwc_to_nchw')
         return out
 
-    def split_pack(self, act):
-        if act.hi is None:
-            assert act.f32 is not None
+    def split_pack(self, act, halo='reflect'):
+        """Make sure `act` carries split planes with the requested halo kind."""
+        if act.hi is None or act.halo != halo:
+            if act.f32 is None:
+                self.split_unpack(act)
             act.hi = self.empty(act.n, act.h + 2, act.w + 2, act.c, dtype=torch.bfloat16)
             act.lo = self.empty(act.n, act.h + 2, act.w + 2, act.c, dtype=torch.bfloat16)
+            act.halo = halo
             _lib.check(self.lib.tmx_split_halo_pack(self.handle, _ptr(act.f32), _ptr(act.hi), _ptr(act.lo), act.n,
-                                                    act.h, act.w, act.c, self.stream()), 'tmx_split_halo_pack')
+                                                    act.h, act.w, act.c, int(halo == 'replicate'), self.stream()),
+                       'tmx_split_halo_pack')
         return act
 
     def split_unpack(self, act):
@@ -115,35 +120,43 @@ class Runtime:
         return act
 
     # ------------------------------------------------------------------ conv
-    def choose_algo(self, cin, cout, k, up2):
+    def choose_algo(self, cin, cout, k, up2, hw=None):
+        """Tensor cores for every conv whose channel counts fit the UMMA tile
+        (multiples of 16) and whose contraction is at least one 3x3x16 window;
+        the CUDA-core kernel keeps the rest (and is the exact-fp32 cross-check)."""
         mode = self.conv_algo
-        tc_ok = (not up2) and cin % 32 == 0 and cout % 32 == 0
+        tc_ok = cin % 16 == 0 and cout % 16 == 0 and (k == 3 or not up2)
+        if hw is not None and (hw[0] < 2 or hw[1] < 2):
+            tc_ok = False              # the halo layout needs at least 2x2 stored pixels
         if mode == 'ffma' or not tc_ok:
             return _lib.ALGO_FFMA
         if mode == 'tc':
-            return _lib.ALGO_TC if cin % 64 == 0 else _lib.ALGO_TC_K32
+            return _lib.ALGO_TC
         if mode == 'tc_k32':
             return _lib.ALGO_TC_K32
-        # auto: tensor cores once the contraction is deep enough to pay for the operand split
-        if k * k * cin >= 576:
-            return _lib.ALGO_TC if cin % 64 == 0 else _lib.ALGO_TC_K32
+        if k * k * cin >= 144 or (k == 1 and cin >= 64):
+            return _lib.ALGO_TC
         return _lib.ALGO_FFMA
 
-    def prepare_weights(self, w, wscale, k, cin, cout):
-        hi = self.empty(cout, k * k * cin, dtype=torch.bfloat16)
-        lo = self.empty(cout, k * k * cin, dtype=torch.bfloat16)
-        _lib.check(self.lib.tmx_conv_weights_prepare(self.handle, _ptr(w), float(wscale), k, cin, cout, _ptr(hi),
-                                                     _ptr(lo), self.stream()), 'tmx_conv_weights_prepare')
+    def prepare_weights(self, w, wscale, k, cin, cout, up2_phase=False):
+        rows = cout * 4 if up2_phase else cout
+        hi = self.empty(rows, k * k * cin, dtype=torch.bfloat16)
+        lo = self.empty(rows, k * k * cin, dtype=torch.bfloat16)
+        _lib.check(self.lib.tmx_conv_weights_prepare(self.handle, _ptr(w), float(wscale), k, cin, cout,
+                                                     int(up2_phase), _ptr(hi), _ptr(lo), self.stream()),
+                   'tmx_conv_weights_prepare')
         return hi, lo
 
     def conv2d(self, x, w, bias, wscale, k, cout, lrelu=False, residual=None, up2=False, want_f32=True,
-               want_split=False, up2_out=False, algo=None, prepared=None):
+               want_split=False, up2_out=False, halo_out='reflect', algo=None, prepared=None, torgb=None):
         """y = [residual +] lrelu(wscale*conv(x, w) + bias) on an Act.  `w` is the raw
-        HWIO variable; `prepared` an optional (w_hi, w_lo) pair for the TC kernel."""
+        HWIO variable; `prepared` an optional (w_hi, w_lo) pair for the TC kernel
+        (sub-pixel planes when up2).  `torgb` = (w_rgb [Cout,C], b_rgb, wscale, C, tanh)
+        fuses the 1x1 image head behind the conv (TC only) and returns (out, images)."""
         cin = x.c
         h, w_ = (x.h * 2, x.w * 2) if up2 else (x.h, x.w)
         if algo is None:
-            algo = self.choose_algo(cin, cout, k, up2)
+            algo = self.choose_algo(cin, cout, k, up2, (x.h, x.w))
         d = _lib.ConvDesc(N=x.n, H=h, W=w_, Cin=cin, Cout=cout, k=k, flags=0, algo=algo, wscale=float(wscale),
                           lrelu_alpha=LRELU_ALPHA)
         io = _lib.ConvIO()
@@ -153,35 +166,48 @@ class Runtime:
         if residual is not None:
             flags |= _lib.CONV_RESIDUAL
             io.residual = residual.data_ptr()
+        if up2:
+            flags |= _lib.CONV_UP2_IN
         io.bias = None if bias is None else bias.data_ptr()
         keep = []
+        images = None
         if algo == _lib.ALGO_FFMA:
-            if up2:
-                flags |= _lib.CONV_UP2_IN
+            if torgb is not None:
+                raise RuntimeError('conv2d: the fused ToRGB head needs the tensor-core kernel')
             self.split_unpack(x)
             io.x_f32 = x.f32.data_ptr()
             io.w = w.data_ptr()
             out = Act(x.n, h, w_, cout, f32=self.empty(x.n, h, w_, cout))
             io.y_f32 = out.f32.data_ptr()
         else:
-            assert not up2
-            self.split_pack(x)
+            self.split_pack(x, 'replicate' if up2 else 'reflect')
             io.x_hi, io.x_lo = x.hi.data_ptr(), x.lo.data_ptr()
             if prepared is None:
-                prepared = self.prepare_weights(w, wscale, k, cin, cout)
+                prepared = self.prepare_weights(w, wscale, k, cin, cout, up2_phase=up2)
             keep.append(prepared)
             io.w_hi, io.w_lo = prepared[0].data_ptr(), prepared[1].data_ptr()
             out = Act(x.n, h, w_, cout)
-            if want_f32 or not want_split:
+            if torgb is not None:
+                w_rgb, b_rgb, ws_rgb, c_rgb, tanh_rgb = torgb
+                images = self.empty(x.n, c_rgb, h, w_)
+                flags |= _lib.CONV_TORGB
+                d.rgb_cout, d.rgb_tanh, d.rgb_wscale = c_rgb, int(tanh_rgb), float(ws_rgb)
+                io.rgb_w = w_rgb.data_ptr()
+                io.rgb_b = None if b_rgb is None else b_rgb.data_ptr()
+                io.y_rgb = images.data_ptr()
+            if want_f32 or (not want_split and torgb is None):
                 out.f32 = self.empty(x.n, h, w_, cout)
                 io.y_f32 = out.f32.data_ptr()
             if want_split:
                 ho, wo = (h * 2, w_ * 2) if up2_out else (h, w_)
                 out.hi = self.empty(x.n, ho + 2, wo + 2, cout, dtype=torch.bfloat16)
                 out.lo = self.empty(x.n, ho + 2, wo + 2, cout, dtype=torch.bfloat16)
+                out.halo = halo_out
                 io.y_hi, io.y_lo = out.hi.data_ptr(), out.lo.data_ptr()
                 if up2_out:
                     flags |= _lib.CONV_UP2_OUT
+                if halo_out == 'replicate':
+                    flags |= _lib.CONV_HALO_REPLICATE
         d.flags = flags
         if self.profile_kernels:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -191,8 +217,8 @@ class Runtime:
             e1.record()
             self.kernel_events.append((('ffma' if algo == _lib.ALGO_FFMA else 'tc', k, cin, cout), e0, e1))
         if want_split and out.hi is None:
-            self.split_pack(out)
-        return out
+            self.split_pack(out, halo_out)
+        return (out, images) if torgb is not None else out
 
     # ------------------------------------------------------------------ pointwise
     def fromrgb(self, x_nchw, w, bias, wscale, cout, lrelu=True):
