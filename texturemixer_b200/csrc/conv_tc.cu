@@ -86,6 +86,67 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// --- CTA-pair (cta_group::2) variants.  Addresses of CTA-local shared memory double as shared::cluster
+// addresses of the own CTA; clearing bit 24 (the peer bit of a 2-CTA cluster) names the same offset in
+// the even (leader) CTA.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive on the leader CTA's copy
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                             int c3) {  // data into the own CTA, completion on the leader's barrier
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1),
+      "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 per CTA] * B[N rows: N/2 per CTA]^T
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs once all prior MMAs of the pair have completed
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -155,8 +216,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 // Instruction descriptor (kind::f16): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
 // A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n, int m = kTileM) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 struct ConvTcParams {
@@ -185,10 +246,10 @@ struct ConvTcParams {
   float* y_rgb;
 };
 
-template <int BN, int KC>
+template <int BN, int KC, bool PAIR = false>
 struct TcCfg {
   static constexpr int kABytes = kTileM * KC * 2;
-  static constexpr int kBBytes = BN * KC * 2;
+  static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * KC * 2;  // per CTA: a pair splits the weight tile
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kSmemBudget = 200 * 1024;
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
@@ -213,14 +274,21 @@ __device__ __forceinline__ void decode_item(const ConvTcParams& p, int item, int
   }
 }
 
-template <int BN, int KC, int GW>
+template <int BN, int KC, int GW, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const __grid_constant__ CUtensorMap tm_bs_hi, const __grid_constant__ CUtensorMap tm_bs_lo,
                    const ConvTcParams p) {
-  using Cfg = TcCfg<BN, KC>;
+  // PAIR: a cluster of two CTAs runs one 256-pixel x BN tile with cta_group::2 MMAs issued by the even
+  // (leader) CTA.  Each CTA loads its own 128 pixels of A and HALF of the weight tile, so the L2->SM
+  // weight traffic per pixel halves; accumulators live in both CTAs' TMEM (own 128 rows each).
+  using Cfg = TcCfg<BN, KC, PAIR>;
   constexpr int S = Cfg::kStages;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int cta_lin = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // index of this CTA (pair) in the grid
+  const int cta_cnt = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int kBRowsFull = PAIR ? BN / 2 : BN;                          // weight rows this CTA loads for a whole tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
@@ -252,13 +320,17 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_s);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc2<Cfg::kTmemCols>(tmem_ptr_s);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_ptr_s);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // barrier inits + TMEM allocation visible in both CTAs
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
@@ -267,30 +339,42 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      for (int item = cta_lin; item < p.num_items; item += cta_cnt) {
         int tile, part, parts;
         decode_item(p, item, tile, part, parts);
         const int cblk = tile % p.tiles_c;
         int t = tile / p.tiles_c;
+        if (PAIR) t = 2 * t + rank;   // the pair covers pixel tiles 2t (leader) and 2t+1; past-the-end tiles load zeros
         const int x0 = (t % p.tiles_x) * p.bw;
         t /= p.tiles_x;
         const int y0 = (t % p.tiles_y) * p.bh;
         const int n0 = (t / p.tiles_y) * p.bn;
         const CUtensorMap* mb_hi = parts > 1 ? &tm_bs_hi : &tm_b_hi;
         const CUtensorMap* mb_lo = parts > 1 ? &tm_bs_lo : &tm_b_lo;
-        const int brow = cblk * BN + part * (BN / parts);
-        const uint32_t bytes = 2 * Cfg::kABytes + 2 * Cfg::kBBytes / parts;
+        const int brows = kBRowsFull / parts;
+        const int brow = cblk * BN + part * (BN / parts) + rank * brows;
+        const uint32_t bytes = 2 * Cfg::kABytes + 2 * brows * KC * 2;
         for (int ks = 0; ks < ksteps; ++ks) {
           const int tap = ks / cchunks;
           const int c0 = (ks - tap * cchunks) * KC;
           const int u = tap / p.k, v = tap - u * p.k;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], bytes);
-          tma_load_4d(sa, &tm_a_hi, &full_bar[stage], c0, x0 + v + p.pad_off, y0 + u + p.pad_off, n0);
-          tma_load_4d(sa + Cfg::kABytes, &tm_a_lo, &full_bar[stage], c0, x0 + v + p.pad_off, y0 + u + p.pad_off, n0);
-          tma_load_2d(sa + 2 * Cfg::kABytes, mb_hi, &full_bar[stage], tap * p.Cin + c0, brow);
-          tma_load_2d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, mb_lo, &full_bar[stage], tap * p.Cin + c0, brow);
+          const int ax = x0 + v + p.pad_off, ay = y0 + u + p.pad_off, bk = tap * p.Cin + c0;
+          if (PAIR) {
+            // the leader's barrier collects the bytes of both CTAs
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * bytes);
+            tma2_load_4d(sa, &tm_a_hi, &full_bar[stage], c0, ax, ay, n0);
+            tma2_load_4d(sa + Cfg::kABytes, &tm_a_lo, &full_bar[stage], c0, ax, ay, n0);
+            tma2_load_2d(sa + 2 * Cfg::kABytes, mb_hi, &full_bar[stage], bk, brow);
+            tma2_load_2d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, mb_lo, &full_bar[stage], bk, brow);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], bytes);
+            tma_load_4d(sa, &tm_a_hi, &full_bar[stage], c0, ax, ay, n0);
+            tma_load_4d(sa + Cfg::kABytes, &tm_a_lo, &full_bar[stage], c0, ax, ay, n0);
+            tma_load_2d(sa + 2 * Cfg::kABytes, mb_hi, &full_bar[stage], bk, brow);
+            tma_load_2d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, mb_lo, &full_bar[stage], bk, brow);
+          }
           if (++stage == S) {
             stage = 0;
             phase ^= 1;
@@ -299,13 +383,13 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (leader CTA only in pair mode) =====================
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        const uint32_t idesc = make_idesc(item < p.full_items ? BN : BN / p.split);
+      for (int item = cta_lin; item < p.num_items; item += cta_cnt, ++it) {
+        const uint32_t idesc = make_idesc(item < p.full_items ? BN : BN / p.split, PAIR ? 2 * kTileM : kTileM);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator
@@ -323,17 +407,27 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int kk = 0; kk < KC / 16; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 2);  // +32 B along K inside the swizzle row, >>4
             // small terms first, then the dominant hi*hi product
-            umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, (ks | kk) != 0);
-            umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
-            umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, 1);
+            if (PAIR) {
+              umma2_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, (ks | kk) != 0);
+              umma2_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
+              umma2_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, 1);
+            } else {
+              umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, (ks | kk) != 0);
+              umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
+              umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, 1);
+            }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs) when these MMAs retire
+          if (PAIR) umma2_commit(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == S) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (PAIR) umma2_commit(&tfull_bar[as]);
+        else umma_commit(&tfull_bar[as]);
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -352,11 +446,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int lo_edge = p.halo_rep ? 0 : 1;                // source row/col copied into halo slot 0
     const int hi_off = p.halo_rep ? 1 : 2;                 // ... and (size - hi_off) into slot size+1
     int it = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+    for (int item = cta_lin; item < p.num_items; item += cta_cnt, ++it) {
       int tile, part, parts;
       decode_item(p, item, tile, part, parts);
       const int cblk = tile % p.tiles_c;
       int t = tile / p.tiles_c;
+      if (PAIR) t = 2 * t + rank;
       const int x = (t % p.tiles_x) * p.bw + ix;
       t /= p.tiles_x;
       const int y = (t % p.tiles_y) * p.bh + iy;
@@ -462,15 +557,20 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(&tempty_bar[as]);
+        else mbar_arrive(&tempty_bar[as]);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // nobody leaves (or frees TMEM) while the peer can still signal / be signalled
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (PAIR) tmem_dealloc2<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -516,10 +616,10 @@ int gcd_pow2(int v, int cap) {  // largest power of two dividing v, at most cap
   return g;
 }
 
-template <int BN, int KC, int GW>
+template <int BN, int KC, int GW, bool PAIR>
 int launch_tc(tmx_handle_t h, const CUtensorMap* maps, const ConvTcParams& p, cudaStream_t st) {
-  using Cfg = TcCfg<BN, KC>;
-  auto kern = conv_tc_kernel<BN, KC, GW>;
+  using Cfg = TcCfg<BN, KC, PAIR>;
+  auto kern = conv_tc_kernel<BN, KC, GW, PAIR>;
   static thread_local int configured_device = -1;
   if (configured_device != h->device) {
     TMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -528,8 +628,21 @@ int launch_tc(tmx_handle_t h, const CUtensorMap* maps, const ConvTcParams& p, cu
   TMX_REQUIRE(Cfg::kSmemBytes <= h->max_smem_optin, TMX_ERR_UNSUPPORTED,
               "tmx_conv2d_fwd[TC]: kernel needs %d B shared memory, device allows %d", Cfg::kSmemBytes,
               h->max_smem_optin);
-  int grid = p.num_items < h->sm_count ? p.num_items : h->sm_count;
-  kern<<<grid, kThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  const int units = PAIR ? h->sm_count / 2 : h->sm_count;   // CTAs, or CTA pairs
+  const int n = p.num_items < units ? p.num_items : units;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(PAIR ? 2 * n : n);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TMX_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p));
   TMX_LAUNCHED(h, "conv_tc_kernel");
   return TMX_OK;
 }
@@ -593,13 +706,17 @@ int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_i
   p.tiles_y = Hs / p.bh;
   p.tiles_n = (d->N + p.bn - 1) / p.bn;
   p.tiles_c = Ng / bnc;
-  long long nt = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.tiles_c;
+  long long tiles_m = (long long)p.tiles_x * p.tiles_y * p.tiles_n;
+  // CTA pairs (cta_group::2) for the wide layers: two pixel tiles share one weight tile split over the pair
+  const bool pair = bnc == 256 && kc == 64 && tiles_m >= 2 && !tmx_env_flag("TMX_NO_PAIR");
+  if (pair) tiles_m = (tiles_m + 1) / 2;
+  long long nt = tiles_m * p.tiles_c;
   TMX_REQUIRE(nt < (1ll << 31), TMX_ERR_SHAPE, "tmx_conv2d_fwd[TC]: too many tiles");
   p.num_tiles = (int)nt;
   // last-wave split: T tiles over G SMs leave R = T mod G tiles for a final, partly empty wave; cut those
   // into 2 or 4 column slices (>= 32 columns, whole epilogue groups) when that lets the wave fill the SMs
   {
-    const int G = h->sm_count;
+    const int G = pair ? h->sm_count / 2 : h->sm_count;
     const int R = p.num_tiles % G;
     p.split = 1;
     if (R > 0 && !tmx_env_flag("TMX_NO_SPLIT")) {
@@ -637,13 +754,15 @@ int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_i
   int rc;
   if ((rc = encode_act_map(h, &maps[0], io->x_hi, d->N, Hs + 2, Ws + 2, d->Cin, kc, p.bw, p.bh, p.bn))) return rc;
   if ((rc = encode_act_map(h, &maps[1], io->x_lo, d->N, Hs + 2, Ws + 2, d->Cin, kc, p.bw, p.bh, p.bn))) return rc;
-  if ((rc = encode_wgt_map(h, &maps[2], io->w_hi, Ng, p.taps * d->Cin, kc, bnc))) return rc;
-  if ((rc = encode_wgt_map(h, &maps[3], io->w_lo, Ng, p.taps * d->Cin, kc, bnc))) return rc;
-  if ((rc = encode_wgt_map(h, &maps[4], io->w_hi, Ng, p.taps * d->Cin, kc, bnc / p.split))) return rc;
-  if ((rc = encode_wgt_map(h, &maps[5], io->w_lo, Ng, p.taps * d->Cin, kc, bnc / p.split))) return rc;
+  const int brows = pair ? bnc / 2 : bnc;   // weight rows one CTA loads per stage
+  if ((rc = encode_wgt_map(h, &maps[2], io->w_hi, Ng, p.taps * d->Cin, kc, brows))) return rc;
+  if ((rc = encode_wgt_map(h, &maps[3], io->w_lo, Ng, p.taps * d->Cin, kc, brows))) return rc;
+  if ((rc = encode_wgt_map(h, &maps[4], io->w_hi, Ng, p.taps * d->Cin, kc, brows / p.split))) return rc;
+  if ((rc = encode_wgt_map(h, &maps[5], io->w_lo, Ng, p.taps * d->Cin, kc, brows / p.split))) return rc;
+  if (pair) return launch_tc<256, 64, 32, true>(h, maps, p, st);
 
 #define TMX_TC_CASE(BN_, KC_, GW_) \
-  if (bnc == BN_ && kc == KC_ && gw == GW_) return launch_tc<BN_, KC_, GW_>(h, maps, p, st);
+  if (bnc == BN_ && kc == KC_ && gw == GW_) return launch_tc<BN_, KC_, GW_, false>(h, maps, p, st);
   TMX_TC_CASE(256, 64, 32)
   TMX_TC_CASE(256, 32, 32)
   TMX_TC_CASE(128, 64, 32)
