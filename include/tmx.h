@@ -115,8 +115,10 @@ int tmx_conv2d_fwd(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_io_t
  * up2_phase (k == 3 only): the sub-pixel weights of conv3x3(upscale2d(x)) as [4*Cout][9*Cin]: row
  * (a*2+b)*Cout + o holds, for output phase (a,b) = (row parity, column parity), the 3x3 low-res taps
  * (U,V): sum of w[u][v] over the upsampled taps that fall on low-res offset (U-1, V-1)
- * (a=0: {0},{1,2},{} ; a=1: {},{0,1},{2}); fp32 sums, then * wscale, then split. */
-int tmx_conv_weights_prepare(tmx_handle_t h, const float* w_hwio, float wscale, int k, int Cin, int Cout,
+ * (a=0: {0},{1,2},{} ; a=1: {},{0,1},{2}); fp32 sums, then * wscale, then split.
+ * Cin_pad >= Cin: the planes are laid out for an activation whose channel count was zero-padded to
+ * Cin_pad (a multiple of 16), e.g. the 513-channel minibatch-stddev output; K index = tap*Cin_pad + c. */
+int tmx_conv_weights_prepare(tmx_handle_t h, const float* w_hwio, float wscale, int k, int Cin, int Cin_pad, int Cout,
                              int up2_phase, uint16_t* w_hi, uint16_t* w_lo, tmx_stream_t s);
 
 /* NHWC f32 -> SPLIT_BF16_HALO (tf.pad REFLECT of networks.py:55 materialised; replicate != 0: edge-clamped halo). */
@@ -146,6 +148,18 @@ int tmx_nchw_to_nhwc(tmx_handle_t h, const float* x_nchw, float* y_nhwc, int N, 
                      int C_total, int bcast_hw, tmx_stream_t s);
 int tmx_nhwc_to_nchw(tmx_handle_t h, const float* x_nhwc, float* y_nchw, int N, int C, int H, int W, int c_off,
                      int C_total, tmx_stream_t s);
+
+/* ------------------------------------------------------------------ discriminator head (D_patch)
+ * minibatch_stddev_layer (networks.py:177-189): x NHWC [N][H][W][C] -> y NHWC [N][H][W][C_total] with
+ * y[..., :C] = x, y[..., C] = group statistic (groups of min(group_size, N) samples {m, m+M, ...}),
+ * y[..., C+1:] = 0 (channel padding for the consumer conv).  stat: [N / G] floats of scratch/output. */
+int tmx_mbstd_fwd(tmx_handle_t h, const float* x_nhwc, float* y_nhwc, float* stat, int N, int H, int W, int C,
+                  int C_total, int group_size, tmx_stream_t s);
+/* dense + apply_bias + leaky_relu (networks.py:38-43, 61-67, 72-75): y[N][Cout] = act(wscale * x[N][K] . w[K][Cout] + b).
+ * Deterministic split-K through a caller-owned workspace of tmx_dense_workspace_bytes(). */
+int tmx_dense_workspace_bytes(int N, int K, int Cout, size_t* bytes);
+int tmx_dense_fwd(tmx_handle_t h, const float* x, const float* w, const float* bias, float wscale, float* y,
+                  float* workspace, int N, int K, int Cout, int lrelu, float alpha, tmx_stream_t s);
 
 /* ------------------------------------------------------------------ latent tile blend (K6)
  * loss.py:92-100 tiling_permutation + tfutil.py:41-43 lerp + the matte sums of
@@ -199,6 +213,18 @@ typedef struct {
 } tmx_blend_io_t;
 
 int tmx_latent_blend(tmx_handle_t h, const tmx_blend_desc_t* d, const tmx_blend_io_t* io, tmx_stream_t s);
+
+/* ------------------------------------------------------------------ optimizer (tfutil.py:246-399, 611-621)
+ * All over flat fp32 buffers (a network's variables are one contiguous, 256-B aligned buffer).
+ * tmx_nonfinite_check: *flag = 1 if any g[i] is inf/nan (never clears it; tfutil.py:347-355).
+ * tmx_adam_step: TF1 Adam on (w, g*grad_scale, m, v); lr_t = lr*sqrt(1-powers[1])/(1-powers[0]) with the running
+ *   beta powers on the device (initialise to {beta1, beta2}); the whole step - including the power update - is
+ *   skipped when skip_flag != NULL and *skip_flag != 0.
+ * tmx_ema_update: dst = src + (dst - src) * beta  (Network.setup_as_moving_average_of). */
+int tmx_nonfinite_check(tmx_handle_t h, const float* g, int64_t n, int* flag, tmx_stream_t s);
+int tmx_adam_step(tmx_handle_t h, float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float grad_scale, float* powers, const int* skip_flag, tmx_stream_t s);
+int tmx_ema_update(tmx_handle_t h, const float* src, float* dst, int64_t n, float beta, tmx_stream_t s);
 
 /* ------------------------------------------------------------------ permutation sampler (host)
  * run.py:107-182 (my_swap_h / my_swap_w / block_permutation) as driven by

@@ -53,7 +53,10 @@ _SIGNATURES = {
     'tmx_device_info': (C.c_int, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     'tmx_launch_count': (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     'tmx_conv2d_fwd': (C.c_int, [_P, C.POINTER(ConvDesc), C.POINTER(ConvIO), _P]),
-    'tmx_conv_weights_prepare': (C.c_int, [_P, _P, _F, _I, _I, _I, _I, _P, _P, _P]),
+    'tmx_conv_weights_prepare': (C.c_int, [_P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P]),
+    'tmx_mbstd_fwd': (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'tmx_dense_workspace_bytes': (C.c_int, [_I, _I, _I, C.POINTER(C.c_size_t)]),
+    'tmx_dense_fwd': (C.c_int, [_P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _F, _P]),
     'tmx_split_halo_pack': (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'tmx_split_halo_unpack': (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     'tmx_fromrgb_fwd': (C.c_int, [_P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
@@ -61,6 +64,9 @@ _SIGNATURES = {
     'tmx_avgpool2_fwd': (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     'tmx_nchw_to_nhwc': (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'tmx_nhwc_to_nchw': (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'tmx_nonfinite_check': (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    'tmx_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _F, _F, _F, _F, _F, _P, _P, _P]),
+    'tmx_ema_update': (C.c_int, [_P, _P, _P, C.c_int64, _F, _P]),
     'tmx_latent_blend': (C.c_int, [_P, C.POINTER(BlendDesc), C.POINTER(BlendIO), _P]),
     'tmx_perm_indices_from_uniforms': (C.c_int, [C.POINTER(C.c_double), C.c_int64, _I, _I, _I,
                                                   C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),

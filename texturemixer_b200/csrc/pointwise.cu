@@ -292,6 +292,25 @@ extern "C" int tmx_split_halo_unpack(tmx_handle_t h, const uint16_t* hi, const u
 // ---------------------------------------------------------------- weight preparation (tensor-core path)
 // w HWIO [taps][Cin][Cout] fp32 -> hi/lo bf16 [Cout][taps*Cin], scaled by wscale.
 // 32x32 tile transpose: coalesced reads along Cout, coalesced writes along K.
+// Cin_pad > Cin: every tap's channel run is zero-extended to Cin_pad (activation padded to a multiple of 16).
+__global__ void __launch_bounds__(256) weights_prepare_padded_kernel(const float* __restrict__ w, float wscale,
+                                                                     uint16_t* __restrict__ hi,
+                                                                     uint16_t* __restrict__ lo, int taps, int Cin,
+                                                                     int Cin_pad, int Cout) {
+  const long long Kp = (long long)taps * Cin_pad;
+  const long long total = (long long)Cout * Kp;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int kk = (int)(t % Kp);
+  const int o = (int)(t / Kp);
+  const int c = kk % Cin_pad, tap = kk / Cin_pad;
+  const float v = c < Cin ? __ldg(w + ((long long)tap * Cin + c) * Cout + o) * wscale : 0.f;
+  uint32_t a, b;
+  tmx_split_bf16(v, a, b);
+  hi[t] = (uint16_t)a;
+  lo[t] = (uint16_t)b;
+}
+
 __global__ void __launch_bounds__(256) weights_prepare_kernel(const float* __restrict__ w, float wscale,
                                                               uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
                                                               int K, int Cout) {
@@ -344,11 +363,19 @@ __global__ void __launch_bounds__(256) weights_prepare_phase_kernel(const float*
   lo[t] = (uint16_t)y;
 }
 
-extern "C" int tmx_conv_weights_prepare(tmx_handle_t h, const float* w, float wscale, int k, int Cin, int Cout,
-                                        int up2_phase, uint16_t* w_hi, uint16_t* w_lo, tmx_stream_t s) {
+extern "C" int tmx_conv_weights_prepare(tmx_handle_t h, const float* w, float wscale, int k, int Cin, int Cin_pad,
+                                        int Cout, int up2_phase, uint16_t* w_hi, uint16_t* w_lo, tmx_stream_t s) {
   TMX_REQUIRE(h && w && w_hi && w_lo, TMX_ERR_ARG, "tmx_conv_weights_prepare: NULL argument");
-  TMX_REQUIRE((k == 1 || k == 3) && Cin > 0 && Cout > 0, TMX_ERR_SHAPE,
-              "tmx_conv_weights_prepare: bad shape k=%d Cin=%d Cout=%d", k, Cin, Cout);
+  TMX_REQUIRE((k == 1 || k == 3) && Cin > 0 && Cout > 0 && Cin_pad >= Cin, TMX_ERR_SHAPE,
+              "tmx_conv_weights_prepare: bad shape k=%d Cin=%d Cin_pad=%d Cout=%d", k, Cin, Cin_pad, Cout);
+  if (Cin_pad > Cin) {
+    TMX_REQUIRE(!up2_phase, TMX_ERR_UNSUPPORTED, "tmx_conv_weights_prepare: Cin padding with up2_phase");
+    long long total = (long long)Cout * k * k * Cin_pad;
+    weights_prepare_padded_kernel<<<tmx_ceil_div(total, 256), 256, 0, (cudaStream_t)s>>>(w, wscale, w_hi, w_lo, k * k,
+                                                                                        Cin, Cin_pad, Cout);
+    TMX_LAUNCHED(h, "weights_prepare_padded_kernel");
+    return TMX_OK;
+  }
   if (up2_phase) {
     TMX_REQUIRE(k == 3, TMX_ERR_SHAPE, "tmx_conv_weights_prepare: up2_phase needs k == 3");
     long long total = 36ll * Cin * Cout;
@@ -503,5 +530,133 @@ extern "C" int tmx_latent_blend(tmx_handle_t h, const tmx_blend_desc_t* d, const
   else if (d->math_f32) latent_blend_kernel<TMX_BLEND_MATTE, true><<<grid, 256, smem, st>>>(P);
   else latent_blend_kernel<TMX_BLEND_MATTE, false><<<grid, 256, smem, st>>>(P);
   TMX_LAUNCHED(h, "latent_blend_kernel");
+  return TMX_OK;
+}
+
+// ---------------------------------------------------------------- minibatch stddev (D_patch)
+// networks.py:177-189.  x NHWC [N][H][W][C] -> y NHWC [N][H][W][C_total]: channels [0,C) copy x, channel C
+// holds the group statistic s[n % M] (M = N / G groups; group m = samples {m, m+M, ...}), channels
+// (C, C_total) are zero padding so that the consumer conv sees a multiple of 16 input channels.
+// One block per group m: s[m] = mean_{h,w,c} sqrt( mean_g (x - mean_g x)^2 + 1e-8 ).
+__global__ void __launch_bounds__(256) mbstd_stat_kernel(const float* __restrict__ x, float* __restrict__ stat, int G,
+                                                         int M, long long per_sample) {
+  const int m = blockIdx.x;
+  float acc = 0.f;
+  for (long long e = threadIdx.x; e < per_sample; e += blockDim.x) {
+    float mean = 0.f;
+    for (int g = 0; g < G; ++g) mean += __ldg(x + ((long long)(g * M + m)) * per_sample + e);
+    mean /= (float)G;
+    float var = 0.f;
+    for (int g = 0; g < G; ++g) {
+      const float d = __ldg(x + ((long long)(g * M + m)) * per_sample + e) - mean;
+      var += d * d;
+    }
+    acc += sqrtf(var / (float)G + 1e-8f);
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) stat[m] = red[0] / (float)per_sample;
+}
+
+__global__ void __launch_bounds__(256) mbstd_concat_kernel(const float* __restrict__ x, const float* __restrict__ stat,
+                                                           float* __restrict__ y, long long total, int C, int C_total,
+                                                           int M, long long pix_per_sample) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % C_total);
+  const long long pix = t / C_total;
+  float v = 0.f;
+  if (c < C) v = __ldg(x + pix * C + c);
+  else if (c == C) v = __ldg(stat + (int)((pix / pix_per_sample) % M));
+  y[t] = v;
+}
+
+extern "C" int tmx_mbstd_fwd(tmx_handle_t h, const float* x, float* y, float* stat, int N, int H, int W, int C,
+                             int C_total, int group_size, tmx_stream_t s) {
+  TMX_REQUIRE(h && x && y && stat, TMX_ERR_ARG, "tmx_mbstd_fwd: NULL argument");
+  TMX_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C_total > C && group_size >= 1, TMX_ERR_SHAPE,
+              "tmx_mbstd_fwd: bad shape N=%d H=%d W=%d C=%d C_total=%d group=%d", N, H, W, C, C_total, group_size);
+  const int G = group_size < N ? group_size : N;
+  TMX_REQUIRE(N % G == 0, TMX_ERR_SHAPE, "tmx_mbstd_fwd: batch %d is not a multiple of the group size %d", N, G);
+  const int M = N / G;
+  const long long per_sample = (long long)H * W * C;
+  mbstd_stat_kernel<<<M, 256, 0, (cudaStream_t)s>>>(x, stat, G, M, per_sample);
+  TMX_LAUNCHED(h, "mbstd_stat_kernel");
+  const long long total = (long long)N * H * W * C_total;
+  mbstd_concat_kernel<<<tmx_ceil_div(total, 256), 256, 0, (cudaStream_t)s>>>(x, stat, y, total, C, C_total, M,
+                                                                             (long long)H * W);
+  TMX_LAUNCHED(h, "mbstd_concat_kernel");
+  return TMX_OK;
+}
+
+// ---------------------------------------------------------------- dense (D_patch head)
+// networks.py:38-43 + 61-67 + 72-75: y[n][o] = act(wscale * sum_k x[n][k] w[k][o] + b[o]).
+// Deterministic split-K: block (o-tile of 64, k-slice) accumulates a [NT samples x 64] partial tile into the
+// workspace, a second kernel sums the slices in order and applies bias / leaky ReLU.
+constexpr int kDenseNT = 32;   // samples per block
+constexpr int kDenseKS = 256;  // k-slice length (32 x 257 floats of shared memory)
+__global__ void __launch_bounds__(256) dense_partial_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            float* __restrict__ part, int N, int K, int Cout) {
+  __shared__ float xs[kDenseNT][kDenseKS + 1];
+  const int o = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int ty = threadIdx.x >> 6;                       // 0..3 -> samples ty*8 .. ty*8+7
+  const int k0 = blockIdx.y * kDenseKS;
+  const int n0 = blockIdx.z * kDenseNT;
+  const int klen = min(kDenseKS, K - k0);
+  for (int e = threadIdx.x; e < kDenseNT * kDenseKS; e += 256) {
+    const int n = e / kDenseKS, k = e % kDenseKS;
+    xs[n][k] = (n0 + n < N && k < klen) ? __ldg(x + (long long)(n0 + n) * K + k0 + k) : 0.f;
+  }
+  __syncthreads();
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (o < Cout) {
+    for (int k = 0; k < klen; ++k) {
+      const float wv = __ldg(w + (long long)(k0 + k) * Cout + o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(xs[ty * 8 + i][k], wv, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = n0 + ty * 8 + i;
+      if (n < N) part[((long long)blockIdx.y * N + n) * Cout + o] = acc[i];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) dense_finish_kernel(const float* __restrict__ part, const float* __restrict__ bias,
+                                                           float* __restrict__ y, int N, int Cout, int slices,
+                                                           float wscale, int lrelu, float alpha) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)N * Cout) return;
+  float acc = 0.f;
+  for (int s = 0; s < slices; ++s) acc += __ldg(part + (long long)s * N * Cout + t);
+  float v = fmaf(acc, wscale, bias ? __ldg(bias + (int)(t % Cout)) : 0.f);
+  if (lrelu) v = fmaxf(v * alpha, v);
+  y[t] = v;
+}
+
+extern "C" int tmx_dense_workspace_bytes(int N, int K, int Cout, size_t* bytes) {
+  TMX_REQUIRE(bytes && N > 0 && K > 0 && Cout > 0, TMX_ERR_ARG, "tmx_dense_workspace_bytes: bad argument");
+  *bytes = (size_t)tmx_ceil_div(K, kDenseKS) * N * Cout * sizeof(float);
+  return TMX_OK;
+}
+
+extern "C" int tmx_dense_fwd(tmx_handle_t h, const float* x, const float* w, const float* bias, float wscale, float* y,
+                             float* workspace, int N, int K, int Cout, int lrelu, float alpha, tmx_stream_t s) {
+  TMX_REQUIRE(h && x && w && y && workspace, TMX_ERR_ARG, "tmx_dense_fwd: NULL argument");
+  TMX_REQUIRE(N > 0 && K > 0 && Cout > 0, TMX_ERR_SHAPE, "tmx_dense_fwd: bad shape N=%d K=%d Cout=%d", N, K, Cout);
+  const int slices = tmx_ceil_div(K, kDenseKS);
+  dim3 grid(tmx_ceil_div(Cout, 64), slices, tmx_ceil_div(N, kDenseNT));
+  TMX_REQUIRE(grid.y <= 65535 && grid.z <= 65535, TMX_ERR_SHAPE, "tmx_dense_fwd: problem too large");
+  dense_partial_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, w, workspace, N, K, Cout);
+  TMX_LAUNCHED(h, "dense_partial_kernel");
+  dense_finish_kernel<<<tmx_ceil_div((long long)N * Cout, 256), 256, 0, (cudaStream_t)s>>>(
+      workspace, bias, y, N, Cout, slices, wscale, lrelu, alpha);
+  TMX_LAUNCHED(h, "dense_finish_kernel");
   return TMX_OK;
 }

@@ -237,6 +237,17 @@ class Network:
             v.value = self._flat[o:o + v.size].view(v.shape)
 
     # -------------------------------------------------------------- variables
+    @property
+    def flat(self):
+        """The one fp32 device buffer holding every variable (256-B aligned slots, zero padding)."""
+        return self._owner()._flat
+
+    def mark_variables_changed(self):
+        """Call after writing `flat` in place (optimizer step): drops the cached tensor-core weight planes."""
+        self._touch()
+        if 'lod' in self.vars and self.flat.is_cuda is False:
+            self._lod_host = float(self.vars['lod'].value)
+
     def _owner(self):
         return self._shared_owner._owner() if self._shared_owner is not None else self
 
@@ -304,15 +315,15 @@ class Network:
         net.copy_vars_from(self)
         return net
 
-    def prepared_weights(self, var, wscale, k, cin, cout, up2_phase=False):
+    def prepared_weights(self, var, wscale, k, cin, cout, up2_phase=False, cin_pad=None):
         """Cached bf16 hi/lo planes of a conv weight for the tensor-core kernel
         (sub-pixel planes when the conv reads through upscale2d); recomputed
         when any variable of the owning network changed."""
         o = self._owner()
-        key = (var.name, float(wscale), bool(up2_phase))
+        key = (var.name, float(wscale), bool(up2_phase), cin_pad)
         ent = o._prepared.get(key)
         if ent is None or ent[2] != o._version:
-            hi, lo = self.rt.prepare_weights(var.value, wscale, k, cin, cout, up2_phase=up2_phase)
+            hi, lo = self.rt.prepare_weights(var.value, wscale, k, cin, cout, up2_phase=up2_phase, cin_pad=cin_pad)
             ent = (hi, lo, o._version)
             o._prepared[key] = ent
         return ent[0], ent[1]
@@ -391,12 +402,28 @@ class Network:
     # -------------------------------------------------------------- EMA / pickling
     def setup_as_moving_average_of(self, src_net, beta=0.99, beta_nontrainable=0.0):
         """tfutil.py:611-621.  Returns a callable update op: var <- lerp(src, var, beta)."""
+        same_layout = list(self.vars.keys()) == list(src_net.vars.keys()) and \
+            all(a.shape == b.shape for a, b in zip(self.vars.values(), src_net.vars.values()))
+
         def update_op():
-            for name, var in self.vars.items():
-                if name in src_net.vars:
-                    cur_beta = beta if name in self.trainables else beta_nontrainable
-                    s = src_net.vars[name].value
-                    var.value.copy_(s + (var.value - s) * cur_beta)
+            if same_layout and self.flat.is_cuda and beta_nontrainable == 0.0:
+                # one fused kernel over the flat buffers; non-trainables (lod) then follow beta_nontrainable
+                import ctypes as C
+                from . import _lib
+                rt = self.rt
+                _lib.check(rt.lib.tmx_ema_update(rt.handle, C.c_void_p(src_net.flat.data_ptr()),
+                                                 C.c_void_p(self.flat.data_ptr()), self.flat.numel(), float(beta),
+                                                 rt.stream()), 'tmx_ema_update')
+                for name, var in self.vars.items():
+                    if name not in self.trainables:
+                        s = src_net.vars[name].value
+                        var.value.copy_(s + (var.value - s) * beta_nontrainable)
+            else:
+                for name, var in self.vars.items():
+                    if name in src_net.vars:
+                        cur_beta = beta if name in self.trainables else beta_nontrainable
+                        s = src_net.vars[name].value
+                        var.value.copy_(s + (var.value - s) * cur_beta)
             self._lod_host = src_net._owner()._lod_host
             self._touch()
         return update_op

@@ -63,10 +63,13 @@ def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=Fals
     rt = ctx.rt
     xa = _act_of(x)
     ws = _wscale(w.shape, gain)
-    algo = rt.choose_algo(cin, fmaps, kernel, up2, (xa.h, xa.w))
+    algo = rt.choose_algo(xa.c, fmaps, kernel, up2, (xa.h, xa.w))
+    if xa.c != cin and algo == 1:
+        raise NotImplementedError('conv2d: a channel-padded activation (%d -> %d) needs the tensor-core kernel'
+                                  % (cin, xa.c))
     prepared = None
-    if algo != 1:  # tensor-core path: cached bf16 hi/lo weight planes
-        prepared = ctx.net.prepared_weights(w, ws, kernel, cin, fmaps, up2_phase=up2)
+    if algo != 1:  # tensor-core path: cached bf16 hi/lo weight planes (zero rows for padded input channels)
+        prepared = ctx.net.prepared_weights(w, ws, kernel, cin, fmaps, up2_phase=up2, cin_pad=xa.c)
     res = None if residual is None else rt.split_unpack(_act_of(residual)).f32
     head = None
     if torgb is not None and algo != 1:
@@ -445,8 +448,8 @@ def _minibatch_stddev_layer(x, group_size):
     shape = [x.shape[0], x.shape[1] + 1, x.shape[2], x.shape[3]]
     if ctx.mode == 'template':
         return T(shape, ctx)
-    a = ctx.rt.split_unpack(_act_of(x))
-    return T(shape, ctx, act=ctx.rt.mbstd(a, group_size))
+    out, _ = ctx.rt.mbstd(_act_of(x), group_size)
+    return T(shape, ctx, act=out)
 
 
 def _dense_layer(x, fmaps, gain=SQRT2, act=True):

@@ -138,11 +138,12 @@ class Runtime:
             return _lib.ALGO_TC
         return _lib.ALGO_FFMA
 
-    def prepare_weights(self, w, wscale, k, cin, cout, up2_phase=False):
+    def prepare_weights(self, w, wscale, k, cin, cout, up2_phase=False, cin_pad=None):
         rows = cout * 4 if up2_phase else cout
-        hi = self.empty(rows, k * k * cin, dtype=torch.bfloat16)
-        lo = self.empty(rows, k * k * cin, dtype=torch.bfloat16)
-        _lib.check(self.lib.tmx_conv_weights_prepare(self.handle, _ptr(w), float(wscale), k, cin, cout,
+        cin_pad = cin if cin_pad is None else cin_pad
+        hi = self.empty(rows, k * k * cin_pad, dtype=torch.bfloat16)
+        lo = self.empty(rows, k * k * cin_pad, dtype=torch.bfloat16)
+        _lib.check(self.lib.tmx_conv_weights_prepare(self.handle, _ptr(w), float(wscale), k, cin, cin_pad, cout,
                                                      int(up2_phase), _ptr(hi), _ptr(lo), self.stream()),
                    'tmx_conv_weights_prepare')
         return hi, lo
@@ -244,10 +245,28 @@ class Runtime:
         return out
 
     def mbstd(self, x, group_size):
-        raise NotImplementedError('minibatch_stddev_layer (D_patch) has no device kernel yet')
+        """minibatch_stddev_layer: Act [N,H,W,C] -> Act [N,H,W,C+1 padded to a multiple of 64]; the logical
+        channel count (C+1) is kept in `.c_logical` for the consumer's weight layout."""
+        self.split_unpack(x)
+        c_total = (x.c + 1 + 63) // 64 * 64          # 64-channel K chunks for the consumer conv
+        g = min(group_size, x.n)
+        out = Act(x.n, x.h, x.w, c_total, f32=self.empty(x.n, x.h, x.w, c_total))
+        stat = self.empty(x.n // g)
+        _lib.check(self.lib.tmx_mbstd_fwd(self.handle, _ptr(x.f32), _ptr(out.f32), _ptr(stat), x.n, x.h, x.w, x.c,
+                                          c_total, group_size, self.stream()), 'tmx_mbstd_fwd')
+        return out, stat
 
     def dense(self, x, w, bias, wscale, lrelu):
-        raise NotImplementedError('dense (D_patch head) has no device kernel yet')
+        """x [N,K] fp32 device tensor, w [K,Cout] raw variable -> [N,Cout]."""
+        n, k = x.shape
+        cout = w.shape[1]
+        nbytes = C.c_size_t()
+        _lib.check(self.lib.tmx_dense_workspace_bytes(n, k, cout, C.byref(nbytes)))
+        ws = self.empty(max(1, nbytes.value // 4))
+        out = self.empty(n, cout)
+        _lib.check(self.lib.tmx_dense_fwd(self.handle, _ptr(x), _ptr(w), _ptr(bias), float(wscale), _ptr(out), _ptr(ws),
+                                          n, k, cout, int(lrelu), LRELU_ALPHA, self.stream()), 'tmx_dense_fwd')
+        return out
 
     # ------------------------------------------------------------------ latent blend
     def latent_blend(self, srcs, H, W, mode, idx_h=None, idx_w=None, ramps_h=None, ramps_w=None, t=None,
