@@ -214,6 +214,49 @@ typedef struct {
 
 int tmx_latent_blend(tmx_handle_t h, const tmx_blend_desc_t* d, const tmx_blend_io_t* io, tmx_stream_t s);
 
+/* ------------------------------------------------------------------ backward (tf.gradients of the ops above,
+ * tfutil.py:299).  Gradients w.r.t. layer outputs travel as fp32 NHWC or as bf16 hi/lo planes on a
+ * ZERO-RINGED grid [N][H+4][W+4][C] (interior at offset 2) shared by the input and the output of the data
+ * gradient, so that a 3x3 tap is a constant row shift of that grid.
+ *
+ * tmx_conv2d_dgrad: g[n][r][c][ci] = sum_{u,v,co} dz[n][r+1-u][c+1-v][co] * w[u][v][ci][co] * wscale at EVERY grid
+ *   position (fp32 [N][H+4][W+4][Cin]); the ring 1..H+2 holds what the padding adjoint folds back, the outermost
+ *   ring is garbage.  wt_hi/wt_lo = tmx_conv_weights_transpose of the forward planes: [Cin][k*k*Cout].
+ *   For a UP2_IN (sub-pixel) layer pass the low-res H, W, Cout := 4*Cout and phase-packed dz planes. */
+int tmx_conv2d_dgrad(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, const uint16_t* dz_hi,
+                     const uint16_t* dz_lo, const uint16_t* wt_hi, const uint16_t* wt_lo, float* g_f32, tmx_stream_t s);
+/* prepared forward planes [rows][taps*K] -> data-gradient planes [K][taps*rows], taps flipped. */
+int tmx_conv_weights_transpose(tmx_handle_t h, const uint16_t* w_hi, const uint16_t* w_lo, int rows, int taps, int K,
+                               uint16_t* wt_hi, uint16_t* wt_lo, tmx_stream_t s);
+
+/* tmx_grad_prepare: gradient w.r.t. a layer OUTPUT y [N][H][W][C] -> operand of that layer's dgrad / wgrad:
+ *   v = src (+ add) ; v *= (y > 0 ? 1 : alpha) if mask ; dbias[c] += dbias_scale * sum v ; write v.
+ *   src_kind 0: g on the zero-ringed grid (a consumer's tmx_conv2d_dgrad output) folded by `fold`
+ *               (0 REFLECT adjoint of networks.py:55, 1 REPLICATE adjoint, 2 none);
+ *            1: plain NHWC fp32 [N][H][W][C];   2: NHWC fp32 at half resolution = downscale2d adjoint (x 0.25).
+ *   mask_kind 0 none, 1: y as NHWC fp32, 2: y as the hi plane of SPLIT_BF16_HALO [N][H+2][W+2][C] (sign only).
+ *   Outputs (any subset): dz_hi/dz_lo planes on the zero-ringed grid (ring written as zeros) - or, with
+ *   phase_pack, on the HALF-resolution grid [N][H/2+4][W/2+4][4C] with channel (a*2+b)*C + c for pixel
+ *   (2y+a, 2x+b) (caller zeroes that buffer's ring once); dz_f32 NHWC; dbias[C] (atomic accumulate). */
+typedef struct {
+  int32_t N, H, W, C;
+  int32_t src_kind, fold, mask_kind, phase_pack;
+  float alpha;
+  float dbias_scale;
+} tmx_grad_desc_t;
+
+typedef struct {
+  const float* g;
+  const float* add;     /* NHWC fp32 [N][H][W][C] or NULL */
+  const void* y_mask;
+  uint16_t* dz_hi;
+  uint16_t* dz_lo;
+  float* dz_f32;
+  float* dbias;
+} tmx_grad_io_t;
+
+int tmx_grad_prepare(tmx_handle_t h, const tmx_grad_desc_t* d, const tmx_grad_io_t* io, tmx_stream_t s);
+
 /* ------------------------------------------------------------------ optimizer (tfutil.py:246-399, 611-621)
  * All over flat fp32 buffers (a network's variables are one contiguous, 256-B aligned buffer).
  * tmx_nonfinite_check: *flag = 1 if any g[i] is inf/nan (never clears it; tfutil.py:347-355).

@@ -31,6 +31,17 @@ class ConvIO(C.Structure):
                 ('rgb_b', C.c_void_p), ('y_rgb', C.c_void_p)]
 
 
+class GradDesc(C.Structure):
+    _fields_ = [('N', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('C', C.c_int32), ('src_kind', C.c_int32),
+                ('fold', C.c_int32), ('mask_kind', C.c_int32), ('phase_pack', C.c_int32), ('alpha', C.c_float),
+                ('dbias_scale', C.c_float)]
+
+
+class GradIO(C.Structure):
+    _fields_ = [('g', C.c_void_p), ('add', C.c_void_p), ('y_mask', C.c_void_p), ('dz_hi', C.c_void_p),
+                ('dz_lo', C.c_void_p), ('dz_f32', C.c_void_p), ('dbias', C.c_void_p)]
+
+
 class BlendDesc(C.Structure):
     _fields_ = [('N', C.c_int32), ('C', C.c_int32), ('h', C.c_int32), ('w', C.c_int32), ('H', C.c_int32),
                 ('W', C.c_int32), ('K', C.c_int32), ('mode', C.c_int32), ('math_f32', C.c_int32),
@@ -64,6 +75,9 @@ _SIGNATURES = {
     'tmx_avgpool2_fwd': (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     'tmx_nchw_to_nhwc': (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'tmx_nhwc_to_nchw': (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'tmx_conv2d_dgrad': (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    'tmx_conv_weights_transpose': (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    'tmx_grad_prepare': (C.c_int, [_P, C.POINTER(GradDesc), C.POINTER(GradIO), _P]),
     'tmx_nonfinite_check': (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     'tmx_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _F, _F, _F, _F, _F, _P, _P, _P]),
     'tmx_ema_update': (C.c_int, [_P, _P, _P, C.c_int64, _F, _P]),

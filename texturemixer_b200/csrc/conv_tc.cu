@@ -232,6 +232,12 @@ struct ConvTcParams {
   int phase;      // UP2_IN sub-pixel form: GEMM column = (a*2+b)*cout_log + c, output pixel (2y+a, 2x+b)
   int cout_log;   // logical Cout of the layer (== Cout unless phase)
   int halo_rep;   // written planes get a REPLICATE (clamp) halo instead of REFLECT
+  // LIN mode (data gradient): pixels are the rows of ONE zero-ringed grid [N][H+4][W+4] shared by input and
+  // output; a tile is 128 consecutive grid rows, tap (U,V) is the constant row shift (U-1)*pitch + (V-1), so the
+  // A operand is a 2-D TMA box at row m0 + shift (out-of-range rows read zeros) and every grid position -
+  // including the ring the reflect/replicate adjoint folds back - is produced.  Output: fp32 rows only.
+  int lin, lin_pitch;
+  long long lin_rows;
   float alpha;
   const float* bias;
   const float* residual;
@@ -345,6 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int cblk = tile % p.tiles_c;
         int t = tile / p.tiles_c;
         if (PAIR) t = 2 * t + rank;   // the pair covers pixel tiles 2t (leader) and 2t+1; past-the-end tiles load zeros
+        const int tlin = t;
         const int x0 = (t % p.tiles_x) * p.bw;
         t /= p.tiles_x;
         const int y0 = (t % p.tiles_y) * p.bh;
@@ -361,17 +368,28 @@ __global__ void __launch_bounds__(kThreads, 1)
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
           const int ax = x0 + v + p.pad_off, ay = y0 + u + p.pad_off, bk = tap * p.Cin + c0;
+          const int arow = tlin * kTileM + (p.k == 3 ? (u - 1) * p.lin_pitch + (v - 1) : 0);   // LIN mode
           if (PAIR) {
             // the leader's barrier collects the bytes of both CTAs
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * bytes);
-            tma2_load_4d(sa, &tm_a_hi, &full_bar[stage], c0, ax, ay, n0);
-            tma2_load_4d(sa + Cfg::kABytes, &tm_a_lo, &full_bar[stage], c0, ax, ay, n0);
+            if (p.lin) {
+              tma2_load_2d(sa, &tm_a_hi, &full_bar[stage], c0, arow);
+              tma2_load_2d(sa + Cfg::kABytes, &tm_a_lo, &full_bar[stage], c0, arow);
+            } else {
+              tma2_load_4d(sa, &tm_a_hi, &full_bar[stage], c0, ax, ay, n0);
+              tma2_load_4d(sa + Cfg::kABytes, &tm_a_lo, &full_bar[stage], c0, ax, ay, n0);
+            }
             tma2_load_2d(sa + 2 * Cfg::kABytes, mb_hi, &full_bar[stage], bk, brow);
             tma2_load_2d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, mb_lo, &full_bar[stage], bk, brow);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], bytes);
-            tma_load_4d(sa, &tm_a_hi, &full_bar[stage], c0, ax, ay, n0);
-            tma_load_4d(sa + Cfg::kABytes, &tm_a_lo, &full_bar[stage], c0, ax, ay, n0);
+            if (p.lin) {
+              tma_load_2d(sa, &tm_a_hi, &full_bar[stage], c0, arow);
+              tma_load_2d(sa + Cfg::kABytes, &tm_a_lo, &full_bar[stage], c0, arow);
+            } else {
+              tma_load_4d(sa, &tm_a_hi, &full_bar[stage], c0, ax, ay, n0);
+              tma_load_4d(sa + Cfg::kABytes, &tm_a_lo, &full_bar[stage], c0, ax, ay, n0);
+            }
             tma_load_2d(sa + 2 * Cfg::kABytes, mb_hi, &full_bar[stage], bk, brow);
             tma_load_2d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, mb_lo, &full_bar[stage], bk, brow);
           }
@@ -452,11 +470,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int cblk = tile % p.tiles_c;
       int t = tile / p.tiles_c;
       if (PAIR) t = 2 * t + rank;
+      const long long mlin = (long long)t * kTileM + r;          // LIN mode: grid row of this thread
       const int x = (t % p.tiles_x) * p.bw + ix;
       t /= p.tiles_x;
       const int y = (t % p.tiles_y) * p.bh + iy;
       const int n = (t / p.tiles_y) * p.bn + in_;
-      const bool valid = n < p.N;
+      const bool valid = p.lin ? (mlin < p.lin_rows) : (n < p.N);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
 
@@ -486,7 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (p.lrelu) f = fmaxf(f * p.alpha, f);
             v[j] = f;
           }
-          const long long pix = ((long long)n * Hl + oy) * Wl + ox;
+          const long long pix = p.lin ? mlin : ((long long)n * Hl + oy) * Wl + ox;
           if (p.has_res) {
             const float4* rp = reinterpret_cast<const float4*>(p.residual + pix * CL + cbase);
 #pragma unroll
@@ -647,6 +666,80 @@ int launch_tc(tmx_handle_t h, const CUtensorMap* maps, const ConvTcParams& p, cu
   return TMX_OK;
 }
 
+// Activations as a plain 2-D matrix [rows][C] (LIN mode): box = 128 rows x kc channels.
+int encode_rows_map(tmx_handle_t h, CUtensorMap* m, const uint16_t* base, long long rows, int C, int kc) {
+  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)kTileM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return tmx_fail(TMX_ERR_DRIVER, "cuTensorMapEncodeTiled(rows) failed: CUresult %d (rows=%lld C=%d)", (int)r, rows, C);
+  return TMX_OK;
+}
+
+// Common tail of the forward and data-gradient launches: tile schedule (CTA pairs, last-wave split), weight
+// tensor maps, kernel selection.  `tiles_m` = number of 128-row tiles, Ng = GEMM N, Kc = GEMM K per tap.
+int schedule_and_launch(tmx_handle_t h, ConvTcParams& p, CUtensorMap* maps, const uint16_t* w_hi, const uint16_t* w_lo,
+                        long long tiles_m, int Ng, int Kc, int bnc, int kc, int gw, cudaStream_t st) {
+  p.tiles_c = Ng / bnc;
+  // CTA pairs (cta_group::2) for the wide layers: two pixel tiles share one weight tile split over the pair
+  const bool pair = bnc == 256 && kc == 64 && tiles_m >= 2 && !tmx_env_flag("TMX_NO_PAIR");
+  if (pair) tiles_m = (tiles_m + 1) / 2;
+  long long nt = tiles_m * p.tiles_c;
+  TMX_REQUIRE(nt < (1ll << 31), TMX_ERR_SHAPE, "conv_tc: too many tiles");
+  p.num_tiles = (int)nt;
+  // last-wave split: T tiles over G SMs leave R = T mod G tiles for a final, partly empty wave; cut those
+  // into 2 or 4 column slices (>= 32 columns, whole epilogue groups) when that lets the wave fill the SMs
+  {
+    const int G = pair ? h->sm_count / 2 : h->sm_count;
+    const int R = p.num_tiles % G;
+    p.split = 1;
+    if (R > 0 && !tmx_env_flag("TMX_NO_SPLIT")) {
+      for (int sp = 4; sp >= 2; sp /= 2) {
+        const int bs = bnc / sp;
+        if (bs >= 32 && bs % gw == 0 && (long long)R * sp <= G) {
+          p.split = sp;
+          break;
+        }
+      }
+    }
+    p.full_items = p.split > 1 ? p.num_tiles - R : p.num_tiles;
+    p.num_items = p.full_items + (p.split > 1 ? R * p.split : 0);
+  }
+  int rc;
+  const int brows = pair ? bnc / 2 : bnc;   // weight rows one CTA loads per stage
+  if ((rc = encode_wgt_map(h, &maps[2], w_hi, Ng, p.taps * Kc, kc, brows))) return rc;
+  if ((rc = encode_wgt_map(h, &maps[3], w_lo, Ng, p.taps * Kc, kc, brows))) return rc;
+  if ((rc = encode_wgt_map(h, &maps[4], w_hi, Ng, p.taps * Kc, kc, brows / p.split))) return rc;
+  if ((rc = encode_wgt_map(h, &maps[5], w_lo, Ng, p.taps * Kc, kc, brows / p.split))) return rc;
+  if (pair) return launch_tc<256, 64, 32, true>(h, maps, p, st);
+
+#define TMX_TC_CASE(BN_, KC_, GW_) \
+  if (bnc == BN_ && kc == KC_ && gw == GW_) return launch_tc<BN_, KC_, GW_, false>(h, maps, p, st);
+  TMX_TC_CASE(256, 64, 32)
+  TMX_TC_CASE(256, 32, 32)
+  TMX_TC_CASE(128, 64, 32)
+  TMX_TC_CASE(128, 32, 32)
+  TMX_TC_CASE(128, 16, 32)
+  TMX_TC_CASE(64, 64, 32)
+  TMX_TC_CASE(64, 32, 32)
+  TMX_TC_CASE(64, 16, 32)
+  TMX_TC_CASE(32, 64, 32)
+  TMX_TC_CASE(32, 32, 32)
+  TMX_TC_CASE(32, 16, 32)
+  TMX_TC_CASE(64, 64, 16)
+  TMX_TC_CASE(64, 32, 16)
+  TMX_TC_CASE(64, 16, 16)
+  TMX_TC_CASE(16, 64, 16)
+  TMX_TC_CASE(16, 32, 16)
+  TMX_TC_CASE(16, 16, 16)
+#undef TMX_TC_CASE
+  return tmx_fail(TMX_ERR_UNSUPPORTED, "conv_tc: no kernel for BN=%d KC=%d GW=%d (K=%d N=%d)", bnc, kc, gw, Kc, Ng);
+}
+
 }  // namespace
 
 int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_io_t* io, int kc_max, cudaStream_t st) {
@@ -705,32 +798,10 @@ int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_i
   p.tiles_x = Ws / p.bw;
   p.tiles_y = Hs / p.bh;
   p.tiles_n = (d->N + p.bn - 1) / p.bn;
-  p.tiles_c = Ng / bnc;
-  long long tiles_m = (long long)p.tiles_x * p.tiles_y * p.tiles_n;
-  // CTA pairs (cta_group::2) for the wide layers: two pixel tiles share one weight tile split over the pair
-  const bool pair = bnc == 256 && kc == 64 && tiles_m >= 2 && !tmx_env_flag("TMX_NO_PAIR");
-  if (pair) tiles_m = (tiles_m + 1) / 2;
-  long long nt = tiles_m * p.tiles_c;
-  TMX_REQUIRE(nt < (1ll << 31), TMX_ERR_SHAPE, "tmx_conv2d_fwd[TC]: too many tiles");
-  p.num_tiles = (int)nt;
-  // last-wave split: T tiles over G SMs leave R = T mod G tiles for a final, partly empty wave; cut those
-  // into 2 or 4 column slices (>= 32 columns, whole epilogue groups) when that lets the wave fill the SMs
-  {
-    const int G = pair ? h->sm_count / 2 : h->sm_count;
-    const int R = p.num_tiles % G;
-    p.split = 1;
-    if (R > 0 && !tmx_env_flag("TMX_NO_SPLIT")) {
-      for (int sp = 4; sp >= 2; sp /= 2) {
-        const int bs = bnc / sp;
-        if (bs >= 32 && bs % gw == 0 && (long long)R * sp <= G) {
-          p.split = sp;
-          break;
-        }
-      }
-    }
-    p.full_items = p.split > 1 ? p.num_tiles - R : p.num_tiles;
-    p.num_items = p.full_items + (p.split > 1 ? R * p.split : 0);
-  }
+  p.lin = 0;
+  p.lin_pitch = 0;
+  p.lin_rows = 0;
+  const long long tiles_m = (long long)p.tiles_x * p.tiles_y * p.tiles_n;
   p.lrelu = (d->flags & TMX_CONV_LRELU) != 0;
   p.has_res = (d->flags & TMX_CONV_RESIDUAL) != 0;
   p.up2_out = (d->flags & TMX_CONV_UP2_OUT) != 0;
@@ -754,32 +825,56 @@ int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_i
   int rc;
   if ((rc = encode_act_map(h, &maps[0], io->x_hi, d->N, Hs + 2, Ws + 2, d->Cin, kc, p.bw, p.bh, p.bn))) return rc;
   if ((rc = encode_act_map(h, &maps[1], io->x_lo, d->N, Hs + 2, Ws + 2, d->Cin, kc, p.bw, p.bh, p.bn))) return rc;
-  const int brows = pair ? bnc / 2 : bnc;   // weight rows one CTA loads per stage
-  if ((rc = encode_wgt_map(h, &maps[2], io->w_hi, Ng, p.taps * d->Cin, kc, brows))) return rc;
-  if ((rc = encode_wgt_map(h, &maps[3], io->w_lo, Ng, p.taps * d->Cin, kc, brows))) return rc;
-  if ((rc = encode_wgt_map(h, &maps[4], io->w_hi, Ng, p.taps * d->Cin, kc, brows / p.split))) return rc;
-  if ((rc = encode_wgt_map(h, &maps[5], io->w_lo, Ng, p.taps * d->Cin, kc, brows / p.split))) return rc;
-  if (pair) return launch_tc<256, 64, 32, true>(h, maps, p, st);
+  return schedule_and_launch(h, p, maps, io->w_hi, io->w_lo, tiles_m, Ng, d->Cin, bnc, kc, gw, st);
+}
 
-#define TMX_TC_CASE(BN_, KC_, GW_) \
-  if (bnc == BN_ && kc == KC_ && gw == GW_) return launch_tc<BN_, KC_, GW_, false>(h, maps, p, st);
-  TMX_TC_CASE(256, 64, 32)
-  TMX_TC_CASE(256, 32, 32)
-  TMX_TC_CASE(128, 64, 32)
-  TMX_TC_CASE(128, 32, 32)
-  TMX_TC_CASE(64, 64, 32)
-  TMX_TC_CASE(64, 32, 32)
-  TMX_TC_CASE(64, 16, 32)
-  TMX_TC_CASE(32, 64, 32)
-  TMX_TC_CASE(32, 32, 32)
-  TMX_TC_CASE(32, 16, 32)
-  TMX_TC_CASE(64, 64, 16)
-  TMX_TC_CASE(64, 32, 16)
-  TMX_TC_CASE(64, 16, 16)
-  TMX_TC_CASE(16, 64, 16)
-  TMX_TC_CASE(16, 32, 16)
-  TMX_TC_CASE(16, 16, 16)
-#undef TMX_TC_CASE
-  return tmx_fail(TMX_ERR_UNSUPPORTED, "tmx_conv2d_fwd[TC]: no kernel for BN=%d KC=%d GW=%d (Cin=%d Cout=%d)", bnc, kc,
-                  gw, d->Cin, d->Cout);
+// ---------------------------------------------------------------- data gradient (LIN mode)
+// dL/dx of y = conv3x3(pad(x)) (or conv1x1) before the padding adjoint: for EVERY position of the zero-ringed
+// grid [N][H+4][W+4] (interior at offset 2)   g[r][c][ci] = sum_{u,v,co} dz[r+1-u][c+1-v][co] * w[u][v][ci][co],
+// i.e. the forward kernel with K = Cout, N = Cin, flipped taps (tmx_conv_weights_prepare_dgrad) and a 2-D
+// row-shifted A operand.  The ring 1 <= r <= H+2 holds the values the REFLECT / REPLICATE adjoint folds onto
+// the interior (tmx_grad_prepare); the outermost ring is garbage by construction and never read.
+int tmx_conv2d_dgrad_tc(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, const uint16_t* dz_hi,
+                        const uint16_t* dz_lo, const uint16_t* wt_hi, const uint16_t* wt_lo, float* g_f32,
+                        cudaStream_t st) {
+  TMX_REQUIRE(dz_hi && dz_lo && wt_hi && wt_lo && g_f32, TMX_ERR_ARG, "tmx_conv2d_dgrad: NULL argument");
+  TMX_REQUIRE((k == 1 || k == 3) && N > 0 && H > 0 && W > 0, TMX_ERR_SHAPE, "tmx_conv2d_dgrad: bad shape");
+  TMX_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0, TMX_ERR_SHAPE,
+              "tmx_conv2d_dgrad: Cin=%d and Cout=%d must be multiples of 16", Cin, Cout);
+  const int kc = Cout % 64 == 0 ? 64 : (Cout % 32 == 0 ? 32 : 16);   // contraction runs over Cout
+  const int gw = Cin % 32 == 0 ? 32 : 16;
+  int bnc;
+  if (Cin % 256 == 0) bnc = 256;
+  else if (Cin % 128 == 0) bnc = 128;
+  else if (Cin % 64 == 0) bnc = 64;
+  else if (Cin % 32 == 0) bnc = 32;
+  else bnc = 16;
+  const long long rows = (long long)N * (H + 4) * (W + 4);
+  TMX_REQUIRE(rows < (1ll << 31) - 4096, TMX_ERR_SHAPE, "tmx_conv2d_dgrad: grid too large");
+  ConvTcParams p = {};
+  p.N = N;
+  p.H = H;
+  p.W = W;
+  p.Cin = Cout;      // GEMM K per tap
+  p.Cout = Cin;      // GEMM N
+  p.k = k;
+  p.taps = k * k;
+  p.pad_off = 0;
+  p.bw = kTileM;     // unused geometry of the 4-D mode: keep the divisions harmless
+  p.bh = 1;
+  p.bn = 1;
+  p.tiles_x = 1;
+  p.tiles_y = 1;
+  p.tiles_n = 1;
+  p.cout_log = Cin;
+  p.lin = 1;
+  p.lin_pitch = W + 4;
+  p.lin_rows = rows;
+  p.y_f32 = g_f32;
+  const long long tiles_m = (rows + kTileM - 1) / kTileM;
+  CUtensorMap maps[6];
+  int rc;
+  if ((rc = encode_rows_map(h, &maps[0], dz_hi, rows, Cout, kc))) return rc;
+  if ((rc = encode_rows_map(h, &maps[1], dz_lo, rows, Cout, kc))) return rc;
+  return schedule_and_launch(h, p, maps, wt_hi, wt_lo, tiles_m, Cin, Cout, bnc, kc, gw, st);
 }

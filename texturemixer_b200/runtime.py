@@ -221,6 +221,55 @@ class Runtime:
             self.split_pack(out, halo_out)
         return (out, images) if torgb is not None else out
 
+    # ------------------------------------------------------------------ backward
+    def transpose_weights(self, prepared, rows, taps, kdim):
+        """Forward planes [rows][taps*kdim] -> data-gradient planes [kdim][taps*rows] (taps flipped)."""
+        hi = self.empty(kdim, taps * rows, dtype=torch.bfloat16)
+        lo = self.empty(kdim, taps * rows, dtype=torch.bfloat16)
+        _lib.check(self.lib.tmx_conv_weights_transpose(self.handle, _ptr(prepared[0]), _ptr(prepared[1]), rows, taps,
+                                                       kdim, _ptr(hi), _ptr(lo), self.stream()),
+                   'tmx_conv_weights_transpose')
+        return hi, lo
+
+    def conv_dgrad(self, dz, n, h, w, cin, cout, k, wt):
+        """dz = (hi, lo) planes on the zero-ringed grid [n][h+4][w+4][cout]; wt = transposed weight planes.
+        -> fp32 g on the grid [n][h+4][w+4][cin] (ring = what the padding adjoint folds back)."""
+        g = self.empty(n, h + 4, w + 4, cin)
+        _lib.check(self.lib.tmx_conv2d_dgrad(self.handle, n, h, w, cin, cout, k, _ptr(dz[0]), _ptr(dz[1]),
+                                             _ptr(wt[0]), _ptr(wt[1]), _ptr(g), self.stream()), 'tmx_conv2d_dgrad')
+        return g
+
+    def grad_prepare(self, g, n, h, w, c, src_kind, fold=2, add=None, y_f32=None, y_hi=None, want_planes=True,
+                     want_f32=False, dbias=None, dbias_scale=1.0, phase_pack=False):
+        """See tmx_grad_prepare (include/tmx.h).  Returns (planes or None, f32 or None)."""
+        d = _lib.GradDesc(N=n, H=h, W=w, C=c, src_kind=src_kind, fold=fold, mask_kind=0, phase_pack=int(phase_pack),
+                          alpha=LRELU_ALPHA, dbias_scale=float(dbias_scale))
+        io = _lib.GradIO()
+        io.g = g.data_ptr()
+        if add is not None:
+            io.add = add.data_ptr()
+        if y_f32 is not None:
+            d.mask_kind, io.y_mask = 1, y_f32.data_ptr()
+        elif y_hi is not None:
+            d.mask_kind, io.y_mask = 2, y_hi.data_ptr()
+        planes = f32 = None
+        if want_planes:
+            if phase_pack:   # half-resolution grid; its ring is never written by the kernel: start from zeros
+                shape = (n, h // 2 + 4, w // 2 + 4, 4 * c)
+                planes = (torch.zeros(shape, dtype=torch.bfloat16, device=self.device),
+                          torch.zeros(shape, dtype=torch.bfloat16, device=self.device))
+            else:
+                planes = (self.empty(n, h + 4, w + 4, c, dtype=torch.bfloat16),
+                          self.empty(n, h + 4, w + 4, c, dtype=torch.bfloat16))
+            io.dz_hi, io.dz_lo = planes[0].data_ptr(), planes[1].data_ptr()
+        if want_f32:
+            f32 = self.empty(n, h, w, c)
+            io.dz_f32 = f32.data_ptr()
+        if dbias is not None:
+            io.dbias = dbias.data_ptr()
+        _lib.check(self.lib.tmx_grad_prepare(self.handle, C.byref(d), C.byref(io), self.stream()), 'tmx_grad_prepare')
+        return planes, f32
+
     # ------------------------------------------------------------------ pointwise
     def fromrgb(self, x_nchw, w, bias, wscale, cout, lrelu=True):
         n, cin, h, w_ = x_nchw.shape
