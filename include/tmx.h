@@ -229,6 +229,17 @@ int tmx_conv2d_dgrad(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int
 int tmx_conv_weights_transpose(tmx_handle_t h, const uint16_t* w_hi, const uint16_t* w_lo, int rows, int taps, int K,
                                uint16_t* wt_hi, uint16_t* wt_lo, tmx_stream_t s);
 
+/* tmx_conv2d_wgrad: dw[u][v][ci][co] += wscale * sum_{n,y,x} xpad[n][y+u][x+v][ci] * dz[n][y][x][co]  (ACCUMULATES
+ *   into the HWIO gradient of the raw variable).  x_hi/x_lo: the layer's forward input planes (SPLIT_BF16_HALO
+ *   [N][H+2][W+2][Cin], the halo kind the forward used); dz_hi/dz_lo: tmx_grad_prepare planes on the zero-ringed
+ *   grid [N][H+4][W+4][Cout].  Tensor cores, Cin and Cout multiples of 64; deterministic split-K through a
+ *   caller-owned workspace.  For a UP2_IN layer pass low-res H, W, Cout := 4*Cout, phase-packed dz and reduce the
+ *   phase gradient with tmx_conv_wgrad_unphase. */
+int tmx_conv2d_wgrad_workspace_bytes(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, size_t* bytes);
+int tmx_conv2d_wgrad(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, float wscale, const uint16_t* x_hi,
+                     const uint16_t* x_lo, const uint16_t* dz_hi, const uint16_t* dz_lo, float* dw, float* workspace,
+                     tmx_stream_t s);
+
 /* tmx_grad_prepare: gradient w.r.t. a layer OUTPUT y [N][H][W][C] -> operand of that layer's dgrad / wgrad:
  *   v = src (+ add) ; v *= (y > 0 ? 1 : alpha) if mask ; dbias[c] += dbias_scale * sum v ; write v.
  *   src_kind 0: g on the zero-ringed grid (a consumer's tmx_conv2d_dgrad output) folded by `fold`

@@ -119,3 +119,34 @@ def test_upscale_conv_dgrad_subpixel_form(rt, n, cin, cout, h, w):
     g = rt.conv_dgrad(dz, n, h, w, cin, 4 * cout, 3, wtp)
     _, dx = rt.grad_prepare(g, n, h, w, cin, src_kind=0, fold=1, want_planes=False, want_f32=True)
     assert _nmax(_nchw(dx.cpu().numpy()), dx_want) <= 1e-4
+
+
+WGRAD_CASES = [
+    # n, cin, cout, h, w, k
+    (2, 256, 256, 32, 32, 3),
+    (3, 64, 128, 8, 8, 3),
+    (5, 512, 512, 4, 4, 3),
+    (9, 128, 64, 2, 2, 3),
+    (2, 64, 256, 8, 8, 1),
+    (1, 256, 64, 96, 96, 3),
+    (4, 64, 64, 32, 32, 3),
+]
+
+
+@pytest.mark.parametrize('n,cin,cout,h,w,k', WGRAD_CASES)
+def test_conv_wgrad_vs_autograd(rt, n, cin, cout, h, w, k):
+    from texturemixer_b200.runtime import Act
+    rng = np.random.RandomState(n + cin + cout + h)
+    x = rng.randn(n, cin, h, w).astype(np.float32)
+    wt = rng.randn(k, k, cin, cout).astype(np.float32)
+    b = (0.1 * rng.randn(cout)).astype(np.float32)
+    dy = rng.randn(n, cout, h, w).astype(np.float32)
+    _, dw_want, _, _ = _oracle_layer_grads(x, wt, b, dy, R.SQRT2, False)
+    ws = float(R.wscale_of(wt.shape))
+    xa = rt.split_pack(Act(n, h, w, cin, f32=_dev(_nhwc(x))))
+    dz, _ = rt.grad_prepare(_dev(_nhwc(dy)), n, h, w, cout, src_kind=1, want_planes=True)
+    dw = torch.zeros(k, k, cin, cout, device='cuda')
+    rt.conv_wgrad((xa.hi, xa.lo), dz, n, h, w, cin, cout, k, ws, dw)
+    assert _nmax(dw.cpu().numpy(), dw_want) <= 1e-4
+    rt.conv_wgrad((xa.hi, xa.lo), dz, n, h, w, cin, cout, k, ws, dw)       # accumulates
+    assert _nmax(dw.cpu().numpy(), 2 * dw_want) <= 1e-4

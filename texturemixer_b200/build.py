@@ -8,7 +8,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_PATH = os.path.join(PKG_DIR, 'libtmx.so')
-SOURCES = ['context.cu', 'pointwise.cu', 'conv_ffma.cu', 'conv_tc.cu', 'conv_api.cu', 'perm_host.cu', 'optim.cu', 'backward.cu']
+SOURCES = ['context.cu', 'pointwise.cu', 'conv_ffma.cu', 'conv_tc.cu', 'conv_api.cu', 'perm_host.cu', 'optim.cu', 'backward.cu', 'conv_wgrad.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--use_fast_math=false', '-Xcompiler', '-fPIC,-O2,-fvisibility=default', '-shared']
 
@@ -21,7 +21,8 @@ def _nvcc():
 
 
 OBJ_DIR = os.path.join(PKG_DIR, 'build')
-HEADERS = [os.path.join(CSRC, 'common.cuh'), os.path.join(PKG_DIR, '..', 'include', 'tmx.h')]
+HEADERS = [os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'tc_common.cuh'),
+           os.path.join(PKG_DIR, '..', 'include', 'tmx.h')]
 
 
 def _stale(target, deps):

@@ -239,6 +239,18 @@ class Runtime:
                                              _ptr(wt[0]), _ptr(wt[1]), _ptr(g), self.stream()), 'tmx_conv2d_dgrad')
         return g
 
+    def conv_wgrad(self, x, dz, n, h, w, cin, cout, k, wscale, dw):
+        """dw (HWIO fp32 view of the gradient buffer) += wscale * x^T dz; x = (hi, lo) forward input planes
+        [n][h+2][w+2][cin], dz = (hi, lo) planes on the zero-ringed grid [n][h+4][w+4][cout]."""
+        nbytes = C.c_size_t()
+        _lib.check(self.lib.tmx_conv2d_wgrad_workspace_bytes(self.handle, n, h, w, cin, cout, k, C.byref(nbytes)),
+                   'tmx_conv2d_wgrad_workspace_bytes')
+        ws = self.empty(max(1, nbytes.value // 4))
+        _lib.check(self.lib.tmx_conv2d_wgrad(self.handle, n, h, w, cin, cout, k, float(wscale), _ptr(x[0]), _ptr(x[1]),
+                                             _ptr(dz[0]), _ptr(dz[1]), _ptr(dw), _ptr(ws), self.stream()),
+                   'tmx_conv2d_wgrad')
+        return dw
+
     def grad_prepare(self, g, n, h, w, c, src_kind, fold=2, add=None, y_f32=None, y_hi=None, want_planes=True,
                      want_f32=False, dbias=None, dbias_scale=1.0, phase_pack=False):
         """See tmx_grad_prepare (include/tmx.h).  Returns (planes or None, f32 or None)."""
