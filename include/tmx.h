@@ -240,6 +240,19 @@ int tmx_conv2d_wgrad(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int
                      const uint16_t* x_lo, const uint16_t* dz_hi, const uint16_t* dz_lo, float* dw, float* workspace,
                      tmx_stream_t s);
 
+/* dwp = gradient of the sub-pixel weights as [9][Cin][4*Cout] (what tmx_conv2d_wgrad writes for a UP2_IN layer);
+ * dw[u][v][ci][co] += sum of the phase entries tap (u,v) contributed to (adjoint of tmx_conv_weights_prepare up2_phase,
+ * without its wscale). */
+int tmx_conv_wgrad_unphase(tmx_handle_t h, const float* dwp, float* dw, int Cin, int Cout, tmx_stream_t s);
+/* ToRGB + tanh backward (networks.py:454-457, :483): dimg/img NCHW [N][Cimg][H][W], y NHWC [N][H][W][Cin] (the head's
+ * input), w raw [Cin][Cimg]; writes dy NHWC, accumulates dw (x wscale) and db. */
+int tmx_torgb_bwd(tmx_handle_t h, const float* dimg, const float* img, const float* y, const float* w, float wscale,
+                  float* dy, float* dw, float* db, int N, int H, int W, int Cin, int Cimg, int use_tanh, tmx_stream_t s);
+/* FromRGB backward (networks.py:226-228): dz = masked gradient NHWC [N][H][W][Cout]; accumulates dw [Cimg][Cout]
+ * (x wscale); dimg (NCHW, optional) = gradient w.r.t. the image. */
+int tmx_fromrgb_bwd(tmx_handle_t h, const float* img, const float* dz, const float* w, float wscale, float* dw,
+                    float* dimg, int N, int Cimg, int H, int W, int Cout, tmx_stream_t s);
+
 /* tmx_grad_prepare: gradient w.r.t. a layer OUTPUT y [N][H][W][C] -> operand of that layer's dgrad / wgrad:
  *   v = src (+ add) ; v *= (y > 0 ? 1 : alpha) if mask ; dbias[c] += dbias_scale * sum v ; write v.
  *   src_kind 0: g on the zero-ringed grid (a consumer's tmx_conv2d_dgrad output) folded by `fold`

@@ -79,6 +79,9 @@ _SIGNATURES = {
     'tmx_conv_weights_transpose': (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     'tmx_conv2d_wgrad_workspace_bytes': (C.c_int, [_P, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_size_t)]),
     'tmx_conv2d_wgrad': (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
+    'tmx_conv_wgrad_unphase': (C.c_int, [_P, _P, _P, _I, _I, _P]),
+    'tmx_torgb_bwd': (C.c_int, [_P, _P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'tmx_fromrgb_bwd': (C.c_int, [_P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _I, _P]),
     'tmx_grad_prepare': (C.c_int, [_P, C.POINTER(GradDesc), C.POINTER(GradIO), _P]),
     'tmx_nonfinite_check': (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     'tmx_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _F, _F, _F, _F, _F, _P, _P, _P]),

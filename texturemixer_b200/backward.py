@@ -1,0 +1,185 @@
+"""Reverse pass over a forward tape: the hand-written counterpart of `tf.gradients`
+(tfutil.py:299, loss.py:285,333) for the networks of networks.py.  No autograd:
+`Network.get_output_for(..., tape=[])` records one entry per layer (saved input
+planes, fp32 output, variable names); `backward()` walks it backwards and launches
+
+    tmx_grad_prepare   padding / pooling adjoints, residual add, leaky-ReLU mask, bias gradient
+    tmx_conv2d_wgrad   weight gradient (tcgen05, MN-major operands)
+    tmx_conv2d_dgrad   data gradient   (tcgen05, LIN mode)
+    tmx_torgb_bwd / tmx_fromrgb_bwd    the 1x1 RGB heads
+
+Weight/bias gradients are ACCUMULATED into `flat_grad`, a fp32 buffer laid out like
+`net.flat` (what Optimizer.register_gradients takes).  A gradient with respect to an
+activation travels in one of three forms:
+    ('f32', t)            NHWC fp32 at the activation's resolution
+    ('grid', g, fold)     a consumer's dgrad output on the zero-ringed grid, to be folded
+                          (0 REFLECT, 1 REPLICATE [consumer read through upscale2d], 2 none)
+    ('pool', t)           NHWC fp32 at half resolution (consumer was downscale2d)"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class _Grads:
+    """Pending gradient contributions per activation (keyed by object identity)."""
+
+    def __init__(self):
+        self.by_id = {}
+
+    def add(self, act, contrib):
+        self.by_id.setdefault(id(act), []).append(contrib)
+
+    def pop(self, act):
+        return self.by_id.pop(id(act), [])
+
+
+def _combine(rt, act, contribs, want_planes, want_f32, mask_y=None, dbias=None, phase_pack=False):
+    """All contributions to dL/d(act) -> (planes on the zero-ringed grid, fp32 NHWC), masked by lrelu'(mask_y)."""
+    n, h, w, c = act.n, act.h, act.w, act.c
+    main = [x for x in contribs if x[0] in ('grid', 'pool')]
+    f32s = [x[1] for x in contribs if x[0] == 'f32']
+    if len(main) > 1:
+        raise NotImplementedError('more than one grid/pool gradient contribution to one activation')
+    add = None
+    if main:
+        if len(f32s) > 1:
+            raise NotImplementedError('more than one fp32 addend next to a grid contribution')
+        add = f32s[0] if f32s else None
+        if main[0][0] == 'grid':
+            src, kind, fold = main[0][1], 0, main[0][2]
+        else:
+            src, kind, fold = main[0][1], 2, 2
+    else:
+        if not f32s:
+            return None, None
+        if len(f32s) > 2:
+            raise NotImplementedError('more than two fp32 gradient contributions to one activation')
+        src, kind, fold = f32s[0], 1, 2
+        add = f32s[1] if len(f32s) == 2 else None
+    return rt.grad_prepare(src, n, h, w, c, kind, fold=fold, add=add, y_f32=mask_y, want_planes=want_planes,
+                           want_f32=want_f32, dbias=dbias, phase_pack=phase_pack)
+
+
+def backward(net, tape, out_grads, flat_grad, want_input_grads=True):
+    """Differentiate one recorded evaluation of `net`.
+    out_grads : list matching the network outputs (NCHW fp32 device tensors, or None for unused outputs)
+    flat_grad : fp32 buffer like net.flat; variable gradients are accumulated into it
+    Returns the list of gradients w.r.t. the network inputs (NCHW fp32; None for image inputs of the
+    encoders unless the first layer's data gradient is defined, i.e. for D_patch/FromRGB: NCHW image gradient)."""
+    rt = net.rt
+    assert tape and tape[-1]['kind'] == 'outputs'
+    outs = tape[-1]['tensors']
+    assert len(out_grads) == len(outs)
+    grads = _Grads()
+    by_tensor = {id(t): g for t, g in zip(outs, out_grads) if g is not None}
+    input_grads = {}
+
+    def gview(name):
+        return net.grad_view(flat_grad, name)
+
+    for rec in reversed(tape[:-1]):
+        kind = rec['kind']
+        if kind == 'slice':
+            g = by_tensor.get(id(rec['out']))
+            if g is not None:
+                a = rec['x']
+                key = ('slicebuf', id(a))
+                buf = input_grads.get(key)
+                if buf is None:
+                    buf = torch.zeros(a.n, a.h, a.w, a.c, dtype=torch.float32, device=rt.device)
+                    input_grads[key] = buf
+                    grads.add(a, ('f32', buf))
+                rt.nchw_to_nhwc(g.contiguous(), out=buf, c_off=rec['c_off'], c_total=a.c)
+        elif kind == 'torgb':
+            g = by_tensor.get(id(rec['img']))
+            if g is None:
+                continue
+            a = rt.split_unpack(rec['x'])
+            dy = rt.empty(a.n, a.h, a.w, a.c)
+            w = net.vars[rec['w']]
+            _lib.check(rt.lib.tmx_torgb_bwd(rt.handle, _ptr(g.contiguous()), _ptr(rec['img']), _ptr(a.f32),
+                                            _ptr(w.value), float(rec['wscale']), _ptr(dy), _ptr(gview(rec['w'])),
+                                            _ptr(gview(rec['b'])), a.n, a.h, a.w, a.c, w.shape[3], int(rec['tanh']),
+                                            rt.stream()), 'tmx_torgb_bwd')
+            grads.add(a, ('f32', dy))
+        elif kind == 'view':
+            # y holds the first `pixels` pixels of x (or vice versa) in another [n,h,w] arrangement
+            contribs = grads.pop(rec['y'])
+            if not contribs:
+                continue
+            _, f32 = _combine(rt, rec['y'], contribs, want_planes=False, want_f32=True)
+            x, m = rec['x'], rec['pixels']
+            gx = torch.zeros(x.n * x.h * x.w, x.c, dtype=torch.float32, device=rt.device)
+            gx[:m].copy_(f32.view(-1, x.c)[:m])
+            grads.add(x, ('f32', gx.view(x.n, x.h, x.w, x.c)))
+        elif kind == 'pool':
+            contribs = grads.pop(rec['y'])
+            if not contribs:
+                continue
+            _, f32 = _combine(rt, rec['y'], contribs, want_planes=False, want_f32=True)
+            grads.add(rec['x'], ('pool', f32))
+        elif kind == 'conv':
+            y, x = rec['y'], rec['x']
+            contribs = grads.pop(y)
+            if not contribs:
+                continue
+            cin_g, cout, k, up2 = x.c, rec['cout'], rec['k'], rec['up2']
+            has_res = rec['residual'] is not None
+            mask = rt.split_unpack(y).f32 if rec['act'] else None
+            dz, dz_f32 = _combine(rt, y, contribs, want_planes=True, want_f32=has_res, mask_y=mask,
+                                  dbias=gview(rec['b']), phase_pack=up2)
+            if has_res:
+                grads.add(rec['residual'], ('f32', dz_f32))         # y = conv(x) + residual (networks.py:437)
+            w = net.vars[rec['w']]
+            if x.c != rec['cin']:
+                raise NotImplementedError('weight gradient of a channel-padded conv (minibatch stddev) is not built yet')
+            fwd = net.prepared_weights(w, rec['wscale'], k, rec['cin'], cout, up2_phase=up2, cin_pad=x.c)
+            if up2:
+                # sub-pixel form: low-res geometry, 4*Cout phase channels
+                hs, ws_, ng = x.h, x.w, 4 * cout
+                dwp = torch.zeros(9, cin_g, ng, dtype=torch.float32, device=rt.device)
+                rt.conv_wgrad((x.hi, x.lo), dz, x.n, hs, ws_, cin_g, ng, 3, rec['wscale'], dwp)
+                _lib.check(rt.lib.tmx_conv_wgrad_unphase(rt.handle, _ptr(dwp), _ptr(gview(rec['w'])), cin_g, cout,
+                                                         rt.stream()), 'tmx_conv_wgrad_unphase')
+                wt = rt.transpose_weights(fwd, ng, 9, cin_g)
+                g = rt.conv_dgrad(dz, x.n, hs, ws_, cin_g, ng, 3, wt)
+                grads.add(x, ('grid', g, 1))
+            else:
+                rt.conv_wgrad((x.hi, x.lo), dz, x.n, x.h, x.w, cin_g, cout, k, rec['wscale'], gview(rec['w']))
+                wt = rt.transpose_weights(fwd, cout, k * k, cin_g)
+                g = rt.conv_dgrad(dz, x.n, x.h, x.w, cin_g, cout, k, wt)
+                grads.add(x, ('grid', g, 0 if k == 3 else 2))
+        elif kind == 'fromrgb':
+            y = rec['y']
+            contribs = grads.pop(y)
+            if not contribs:
+                continue
+            _, dz = _combine(rt, y, contribs, want_planes=False, want_f32=True, mask_y=y.f32, dbias=gview(rec['b']))
+            img = rec['img']
+            n, cimg, h, w_ = img.shape
+            dimg = rt.empty(n, cimg, h, w_) if want_input_grads else None
+            wv = net.vars[rec['w']]
+            _lib.check(rt.lib.tmx_fromrgb_bwd(rt.handle, _ptr(img), _ptr(dz), _ptr(wv.value), float(rec['wscale']),
+                                              _ptr(gview(rec['w'])), _ptr(dimg), n, cimg, h, w_, rec['cout'],
+                                              rt.stream()), 'tmx_fromrgb_bwd')
+            input_grads[('img', id(img))] = dimg
+        elif kind == 'concat':
+            y = rec['y']
+            contribs = grads.pop(y)
+            if not contribs or not want_input_grads:
+                continue
+            _, f32 = _combine(rt, y, contribs, want_planes=False, want_f32=True)
+            c = rec['c']
+            input_grads['concat'] = [rt.nhwc_to_nchw(f32, c_off=i * c, c=c) for i in range(len(rec['inputs']))]
+        else:
+            raise NotImplementedError('backward of tape record %r' % kind)
+    if 'concat' in input_grads:
+        return input_grads['concat']
+    imgs = [v for k, v in input_grads.items() if isinstance(k, tuple) and k[0] == 'img']
+    return imgs if imgs else []

@@ -64,9 +64,6 @@ __global__ void __launch_bounds__(256) grad_prepare_kernel(const GradPrepParams 
           if (c == 0) cs[nc++] = 1;
           if (c == W - 1) cs[nc++] = W + 2;
         }
-        // H == 2 (or W == 2) with REFLECT: row 1 receives padded -1 AND row 0 receives padded H; both handled above
-        if (d.fold == 0 && H == 2 && nr == 1) {   // r == 0 == H-2 was caught; r == 1 caught too
-        }
         for (int a = 0; a < nr; ++a)
           for (int b = 0; b < nc; ++b) {
             float t[8];
@@ -223,6 +220,195 @@ extern "C" int tmx_conv_weights_transpose(tmx_handle_t h, const uint16_t* w_hi, 
   dim3 grid(tmx_ceil_div(K, 32), tmx_ceil_div(rows, 32), taps);
   weights_transpose_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(w_hi, w_lo, wt_hi, wt_lo, rows, taps, K);
   TMX_LAUNCHED(h, "weights_transpose_kernel");
+  return TMX_OK;
+}
+
+// ---------------------------------------------------------------- sub-pixel weight gradient -> 3x3 gradient
+// dwp: gradient of the phase weights as HWIO-like [9][Cin][4*Cout] (tap (U,V), column (a*2+b)*Cout + co).
+// Tap u of the upsampled kernel lands on low-res offset U(a,u): a=0: 0,1,1; a=1: 1,1,2 (same for columns), so
+// dw[u][v][ci][co] += sum_{a,b} dwp[U(a,u)*3 + V(b,v)][ci][(a*2+b)*Cout + co].
+__global__ void __launch_bounds__(256) wgrad_unphase_kernel(const float* __restrict__ dwp, float* __restrict__ dw,
+                                                            int Cin, int Cout) {
+  const long long total = 9ll * Cin * Cout;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int co = (int)(t % Cout);
+  const long long q = t / Cout;
+  const int ci = (int)(q % Cin);
+  const int tap = (int)(q / Cin);
+  const int u = tap / 3, v = tap % 3;
+  float acc = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int U = a == 0 ? (u == 0 ? 0 : 1) : (u == 2 ? 2 : 1);
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int V = b == 0 ? (v == 0 ? 0 : 1) : (v == 2 ? 2 : 1);
+      acc += __ldg(dwp + ((long long)(U * 3 + V) * Cin + ci) * (4 * Cout) + (a * 2 + b) * Cout + co);
+    }
+  }
+  dw[t] += acc;
+}
+
+extern "C" int tmx_conv_wgrad_unphase(tmx_handle_t h, const float* dwp, float* dw, int Cin, int Cout, tmx_stream_t s) {
+  TMX_REQUIRE(h && dwp && dw && Cin > 0 && Cout > 0, TMX_ERR_ARG, "tmx_conv_wgrad_unphase: bad argument");
+  const long long total = 9ll * Cin * Cout;
+  wgrad_unphase_kernel<<<tmx_ceil_div(total, 256), 256, 0, (cudaStream_t)s>>>(dwp, dw, Cin, Cout);
+  TMX_LAUNCHED(h, "wgrad_unphase_kernel");
+  return TMX_OK;
+}
+
+// ---------------------------------------------------------------- RGB heads (1x1 convs with 3 image channels)
+// ToRGB backward (networks.py:454-457 + tanh :483).  Forward: img[n][o][p] = f(ws * sum_c y[p][c] w[c][o] + b[o]).
+// Given dimg (NCHW) and the forward image (for tanh' = 1 - img^2):  dpre = dimg * (1 - img^2);
+//   dy[p][c] = ws * sum_o dpre[o] w[c][o];  dw[c][o] += ws * sum_p y[p][c] dpre[o];  db[o] += sum_p dpre[o].
+// One thread per pixel; block partial sums -> atomics (3*(Cin+1) values per block).
+template <int CIN>
+__global__ void __launch_bounds__(256) torgb_bwd_kernel(const float* __restrict__ dimg, const float* __restrict__ img,
+                                                        const float* __restrict__ y, const float* __restrict__ w,
+                                                        float wscale, float* __restrict__ dy, float* __restrict__ dw,
+                                                        float* __restrict__ db, long long npix, int HW, int Cimg,
+                                                        int use_tanh) {
+  __shared__ float red[4][CIN + 1][8];   // [o][c or bias][warp]
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float dpre[4] = {0.f, 0.f, 0.f, 0.f};
+  float yv[CIN];
+#pragma unroll
+  for (int c = 0; c < CIN; ++c) yv[c] = 0.f;
+  if (p < npix) {
+    const long long n = p / HW;
+    const int hw = (int)(p % HW);
+    for (int o = 0; o < Cimg; ++o) {
+      const long long idx = (n * Cimg + o) * HW + hw;
+      float g = __ldg(dimg + idx);
+      if (use_tanh) {
+        const float t = __ldg(img + idx);
+        g *= (1.f - t * t);
+      }
+      dpre[o] = g;
+    }
+    const float4* yp = reinterpret_cast<const float4*>(y + p * CIN);
+#pragma unroll
+    for (int c4 = 0; c4 < CIN / 4; ++c4) {
+      const float4 t = __ldg(yp + c4);
+      yv[4 * c4] = t.x; yv[4 * c4 + 1] = t.y; yv[4 * c4 + 2] = t.z; yv[4 * c4 + 3] = t.w;
+    }
+    float4* dyp = reinterpret_cast<float4*>(dy + p * CIN);
+#pragma unroll
+    for (int c4 = 0; c4 < CIN / 4; ++c4) {
+      float o4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float acc = 0.f;
+        for (int o = 0; o < Cimg; ++o) acc = fmaf(dpre[o], __ldg(w + (4 * c4 + i) * Cimg + o), acc);
+        o4[i] = acc * wscale;
+      }
+      dyp[c4] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    }
+  }
+  // block reduction of y[c]*dpre[o] and dpre[o]
+  for (int o = 0; o < Cimg; ++o) {
+#pragma unroll
+    for (int c = 0; c <= CIN; ++c) {
+      float vsum = (c < CIN ? yv[c < CIN ? c : 0] : 1.f) * dpre[o];
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, sft);
+      if (lane == 0) red[o][c][warp] = vsum;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < Cimg * (CIN + 1); e += blockDim.x) {
+    const int o = e / (CIN + 1), c = e % (CIN + 1);
+    float sacc = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) sacc += red[o][c][wv];
+    if (c < CIN) atomicAdd(dw + c * Cimg + o, sacc * wscale);
+    else if (db != nullptr) atomicAdd(db + o, sacc);
+  }
+}
+
+extern "C" int tmx_torgb_bwd(tmx_handle_t h, const float* dimg, const float* img, const float* y, const float* w,
+                             float wscale, float* dy, float* dw, float* db, int N, int H, int W, int Cin, int Cimg,
+                             int use_tanh, tmx_stream_t s) {
+  TMX_REQUIRE(h && dimg && y && w && dy && dw && (!use_tanh || img), TMX_ERR_ARG, "tmx_torgb_bwd: NULL argument");
+  TMX_REQUIRE(N > 0 && H > 0 && W > 0 && Cimg >= 1 && Cimg <= 4 && (Cin == 16 || Cin == 32 || Cin == 64), TMX_ERR_SHAPE,
+              "tmx_torgb_bwd: bad shape (Cin in {16,32,64}, Cimg <= 4), got Cin=%d Cimg=%d", Cin, Cimg);
+  const long long npix = (long long)N * H * W;
+  dim3 grid(tmx_ceil_div(npix, 256));
+  cudaStream_t st = (cudaStream_t)s;
+  if (Cin == 16) torgb_bwd_kernel<16><<<grid, 256, 0, st>>>(dimg, img, y, w, wscale, dy, dw, db, npix, H * W, Cimg, use_tanh);
+  else if (Cin == 32) torgb_bwd_kernel<32><<<grid, 256, 0, st>>>(dimg, img, y, w, wscale, dy, dw, db, npix, H * W, Cimg, use_tanh);
+  else torgb_bwd_kernel<64><<<grid, 256, 0, st>>>(dimg, img, y, w, wscale, dy, dw, db, npix, H * W, Cimg, use_tanh);
+  TMX_LAUNCHED(h, "torgb_bwd_kernel");
+  return TMX_OK;
+}
+
+// FromRGB backward (networks.py:226-228): forward y[p][o] = lrelu(ws * sum_c img[c][p] w[c][o] + b[o]).
+// dz (already masked, NHWC fp32 [npix][Cout]) ->  dw[c][o] += ws * sum_p img[c][p] dz[p][o];  optionally
+// dimg[n][c][p] = ws * sum_o dz[p][o] w[c][o] (needed when the image itself is a function of trained weights).
+template <int COUT>
+__global__ void __launch_bounds__(256) fromrgb_bwd_kernel(const float* __restrict__ img, const float* __restrict__ dz,
+                                                          const float* __restrict__ w, float wscale,
+                                                          float* __restrict__ dw, float* __restrict__ dimg,
+                                                          long long npix, int HW, int Cimg) {
+  __shared__ float red[4][COUT][8];
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float iv[4] = {0.f, 0.f, 0.f, 0.f};
+  float zv[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) zv[o] = 0.f;
+  if (p < npix) {
+    const long long n = p / HW;
+    const int hw = (int)(p % HW);
+    for (int c = 0; c < Cimg; ++c) iv[c] = __ldg(img + (n * Cimg + c) * HW + hw);
+    const float4* zp = reinterpret_cast<const float4*>(dz + p * COUT);
+#pragma unroll
+    for (int o4 = 0; o4 < COUT / 4; ++o4) {
+      const float4 t = __ldg(zp + o4);
+      zv[4 * o4] = t.x; zv[4 * o4 + 1] = t.y; zv[4 * o4 + 2] = t.z; zv[4 * o4 + 3] = t.w;
+    }
+    if (dimg != nullptr) {
+      for (int c = 0; c < Cimg; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc = fmaf(zv[o], __ldg(w + c * COUT + o), acc);
+        dimg[(n * Cimg + c) * HW + hw] = acc * wscale;
+      }
+    }
+  }
+  for (int c = 0; c < Cimg; ++c) {
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+      float vsum = iv[c] * zv[o];
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, sft);
+      if (lane == 0) red[c][o][warp] = vsum;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < Cimg * COUT; e += blockDim.x) {
+    const int c = e / COUT, o = e % COUT;
+    float sacc = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) sacc += red[c][o][wv];
+    atomicAdd(dw + c * COUT + o, sacc * wscale);
+  }
+}
+
+extern "C" int tmx_fromrgb_bwd(tmx_handle_t h, const float* img, const float* dz, const float* w, float wscale,
+                               float* dw, float* dimg, int N, int Cimg, int H, int W, int Cout, tmx_stream_t s) {
+  TMX_REQUIRE(h && img && dz && w && dw, TMX_ERR_ARG, "tmx_fromrgb_bwd: NULL argument");
+  TMX_REQUIRE(N > 0 && H > 0 && W > 0 && Cimg >= 1 && Cimg <= 4 && (Cout == 16 || Cout == 32 || Cout == 64),
+              TMX_ERR_SHAPE, "tmx_fromrgb_bwd: bad shape (Cout in {16,32,64}, Cimg <= 4), got Cout=%d Cimg=%d", Cout, Cimg);
+  const long long npix = (long long)N * H * W;
+  dim3 grid(tmx_ceil_div(npix, 256));
+  cudaStream_t st = (cudaStream_t)s;
+  if (Cout == 16) fromrgb_bwd_kernel<16><<<grid, 256, 0, st>>>(img, dz, w, wscale, dw, dimg, npix, H * W, Cimg);
+  else if (Cout == 32) fromrgb_bwd_kernel<32><<<grid, 256, 0, st>>>(img, dz, w, wscale, dw, dimg, npix, H * W, Cimg);
+  else fromrgb_bwd_kernel<64><<<grid, 256, 0, st>>>(img, dz, w, wscale, dw, dimg, npix, H * W, Cimg);
+  TMX_LAUNCHED(h, "fromrgb_bwd_kernel");
   return TMX_OK;
 }
 

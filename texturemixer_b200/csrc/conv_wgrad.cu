@@ -10,6 +10,9 @@
 // (SPLIT_BF16_HALO, shifted by the tap), dz from the zero-ringed gradient planes of tmx_grad_prepare.
 // bf16x3 like the forward (x_lo*dz_hi + x_hi*dz_lo + x_hi*dz_hi).
 //
+// Channel counts that are not multiples of 64 are handled by the TMA unit: boxes reach past the channel extent
+// and read zeros, so the thin layers (16/32 channels) run the same kernel with idle rows / columns.
+//
 // Work split: an output tile is (tap, 128 input channels, BN output channels); the pixel range is cut into
 // `splits` slices so that tiles x splits fills the SMs (split-K).  Each CTA accumulates its slice in TMEM and
 // writes a partial tile to the workspace; tmx_conv2d_wgrad then reduces the slices in a fixed order
@@ -30,7 +33,8 @@ struct WgradParams {
   int bw, bh, bn;                  // pixel patch of one stage: bw*bh*bn == 64
   int tiles_x, tiles_y, tiles_n;   // patches per image row / column / batch
   int chunks;                      // total pixel patches
-  int ci_tiles, co_tiles;          // Cin/128 (rounded up), Cout/BN
+  int ci_tiles, co_tiles;          // Cin/128, Cout/BN, both rounded up (channels past the end read zeros)
+  int co_pad;                      // co_tiles*BN: row length of a partial tile row
   int splits, chunks_per_split;
   float* partial;                  // [splits][taps][ci_tiles*128][Cout]
 };
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(kWThreads, 1)
     const int row = quad * 32 + lane;                 // input channel within the tile
     const int ci = ci_t * kWM + row;
     const int cin_pad = p.ci_tiles * kWM;
-    float* dst = p.partial + (((long long)split * p.taps + tap) * cin_pad + ci) * p.Cout + co_t * BN;
+    float* dst = p.partial + (((long long)split * p.taps + tap) * cin_pad + ci) * p.co_pad + co_t * BN;
     if (nchunks > 0) {
       mbar_wait(done_bar, 0);
       tc_fence_after();
@@ -215,7 +219,7 @@ __global__ void __launch_bounds__(kWThreads, 1)
 // dw[tap][ci][co] += scale * sum_s partial[s][tap][ci][co]   (fixed order -> deterministic)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                                            int splits, int taps, int Cin, int cin_pad, int Cout,
-                                                           float scale) {
+                                                           int co_pad, float scale) {
   const long long total4 = (long long)taps * Cin * Cout / 4;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total4) return;
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int s = 0; s < splits; ++s) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(
-        partial + (((long long)s * taps + tap) * cin_pad + ci) * Cout + co));
+        partial + (((long long)s * taps + tap) * cin_pad + ci) * co_pad + co));
     acc.x += v.x;
     acc.y += v.y;
     acc.z += v.z;
@@ -279,7 +283,8 @@ void wgrad_plan(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, i
   p.tiles_n = (N + p.bn - 1) / p.bn;
   p.chunks = p.tiles_x * p.tiles_y * p.tiles_n;
   p.ci_tiles = (Cin + kWM - 1) / kWM;
-  p.co_tiles = Cout / bn_cols;
+  p.co_tiles = (Cout + bn_cols - 1) / bn_cols;
+  p.co_pad = p.co_tiles * bn_cols;
   const int tiles = p.taps * p.ci_tiles * p.co_tiles;
   int splits = h->sm_count / tiles;
   if (splits < 1) splits = 1;
@@ -310,11 +315,11 @@ int launch_wgrad(tmx_handle_t h, const CUtensorMap* maps, const WgradParams& p, 
 extern "C" int tmx_conv2d_wgrad_workspace_bytes(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k,
                                                 size_t* bytes) {
   TMX_REQUIRE(h && bytes, TMX_ERR_ARG, "tmx_conv2d_wgrad_workspace_bytes: NULL argument");
-  TMX_REQUIRE((k == 1 || k == 3) && N > 0 && H > 0 && W > 0 && Cin % 64 == 0 && Cout % 64 == 0, TMX_ERR_SHAPE,
-              "tmx_conv2d_wgrad: needs k in {1,3}, Cin and Cout multiples of 64 (got k=%d Cin=%d Cout=%d)", k, Cin, Cout);
+  TMX_REQUIRE((k == 1 || k == 3) && N > 0 && H > 0 && W > 0 && Cin % 8 == 0 && Cout % 8 == 0, TMX_ERR_SHAPE,
+              "tmx_conv2d_wgrad: needs k in {1,3}, Cin and Cout multiples of 8 (got k=%d Cin=%d Cout=%d)", k, Cin, Cout);
   WgradParams p;
   wgrad_plan(h, N, H, W, Cin, Cout, k, wgrad_bn(Cout), p);
-  *bytes = (size_t)p.splits * p.taps * p.ci_tiles * kWM * Cout * sizeof(float);
+  *bytes = (size_t)p.splits * p.taps * p.ci_tiles * kWM * p.co_pad * sizeof(float);
   return TMX_OK;
 }
 
@@ -322,8 +327,8 @@ extern "C" int tmx_conv2d_wgrad(tmx_handle_t h, int N, int H, int W, int Cin, in
                                 const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* dz_hi,
                                 const uint16_t* dz_lo, float* dw, float* workspace, tmx_stream_t s) {
   TMX_REQUIRE(h && x_hi && x_lo && dz_hi && dz_lo && dw && workspace, TMX_ERR_ARG, "tmx_conv2d_wgrad: NULL argument");
-  TMX_REQUIRE((k == 1 || k == 3) && N > 0 && H >= 2 && W >= 2 && Cin % 64 == 0 && Cout % 64 == 0, TMX_ERR_SHAPE,
-              "tmx_conv2d_wgrad: needs k in {1,3}, H, W >= 2, Cin and Cout multiples of 64 (got k=%d %dx%d Cin=%d "
+  TMX_REQUIRE((k == 1 || k == 3) && N > 0 && H >= 2 && W >= 2 && Cin % 8 == 0 && Cout % 8 == 0, TMX_ERR_SHAPE,
+              "tmx_conv2d_wgrad: needs k in {1,3}, H, W >= 2, Cin and Cout multiples of 8 (got k=%d %dx%d Cin=%d "
               "Cout=%d)", k, H, W, Cin, Cout);
   const void* ptrs[] = {x_hi, x_lo, dz_hi, dz_lo, dw, workspace};
   for (const void* q : ptrs)
@@ -345,7 +350,7 @@ extern "C" int tmx_conv2d_wgrad(tmx_handle_t h, int N, int H, int W, int Cin, in
   if (rc) return rc;
   const long long total4 = (long long)p.taps * Cin * Cout / 4;
   wgrad_reduce_kernel<<<tmx_ceil_div(total4, 256), 256, 0, st>>>(workspace, dw, p.splits, p.taps, Cin,
-                                                                 p.ci_tiles * kWM, Cout, wscale);
+                                                                 p.ci_tiles * kWM, Cout, p.co_pad, wscale);
   TMX_LAUNCHED(h, "wgrad_reduce_kernel");
   return TMX_OK;
 }

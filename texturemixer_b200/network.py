@@ -87,10 +87,11 @@ class T:
 
 
 class BuildContext:
-    def __init__(self, net, mode):
+    def __init__(self, net, mode, tape=None):
         self.net, self.mode = net, mode
         self.scopes = []
         self.rt = net.rt if mode == 'run' else None
+        self.tape = tape        # list of layer records when the forward is run for training (backward.py)
 
     @contextlib.contextmanager
     def variable_scope(self, name):
@@ -248,6 +249,16 @@ class Network:
         if 'lod' in self.vars and self.flat.is_cuda is False:
             self._lod_host = float(self.vars['lod'].value)
 
+    def var_offset(self, name):
+        """Element offset of variable `name` inside `flat` (same layout for the flat gradient buffer)."""
+        v = self.vars[name].value
+        return (v.data_ptr() - self.flat.data_ptr()) // 4
+
+    def grad_view(self, flat_grad, name):
+        v = self.vars[name]
+        off = self.var_offset(name)
+        return flat_grad[off:off + v.size].view(v.shape)
+
     def _owner(self):
         return self._shared_owner._owner() if self._shared_owner is not None else self
 
@@ -329,13 +340,16 @@ class Network:
         return ent[0], ent[1]
 
     # -------------------------------------------------------------- evaluation
-    def get_output_for(self, *in_expr, return_as_list=False, **dynamic_kwargs):
+    def get_output_for(self, *in_expr, return_as_list=False, tape=None, **dynamic_kwargs):
         """tfutil.py:505-516 on device tensors: NCHW float32 CUDA tensors in,
-        NCHW float32 CUDA tensors out (same order/names as the reference)."""
+        NCHW float32 CUDA tensors out (same order/names as the reference).
+        `tape`: a list that receives one record per layer (saved activations) so that
+        texturemixer_b200.backward.backward() can differentiate this evaluation - the
+        counterpart of tf.gradients over the graph built here (tfutil.py:299)."""
         assert len(in_expr) == self.num_inputs
         all_kwargs = dict(self.static_kwargs)
         all_kwargs.update(dynamic_kwargs)
-        ctx = BuildContext(self, 'run')
+        ctx = BuildContext(self, 'run', tape=tape)
         ins = []
         for x, name in zip(in_expr, self.input_names):
             if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32):
@@ -344,6 +358,8 @@ class Network:
         out = self._build_func(*ins, **all_kwargs)
         outs = [out] if isinstance(out, T) else list(out)
         res = [t.nchw for t in outs]
+        if tape is not None:
+            tape.append(dict(kind='outputs', tensors=res))
         if return_as_list:
             return res
         return res[0] if len(res) == 1 else tuple(res)

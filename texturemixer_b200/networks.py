@@ -12,6 +12,7 @@ Only the reference's default layer variants are implemented on the device
 (use_wscale=True, use_pixelnorm=False, fused_scale=False, leaky ReLU,
 float32); the others raise NotImplementedError."""
 import numpy as np
+import torch
 
 from .network import T
 from .runtime import Act
@@ -63,6 +64,12 @@ def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=Fals
     rt = ctx.rt
     xa = _act_of(x)
     ws = _wscale(w.shape, gain)
+    strip = None
+    if kernel == 1 and (xa.h < 2 or xa.w < 2) and ctx.tape is not None:
+        # a 1x1 conv couples no pixels: run it on the pixels laid out as one 2-row strip so that the
+        # tensor-core kernels (which need a 2x2 halo layout) and their backward apply (E_zg's zg_Conv3)
+        strip = _pixel_strip(ctx, xa)
+        xa = strip
     algo = rt.choose_algo(xa.c, fmaps, kernel, up2, (xa.h, xa.w))
     if xa.c != cin and algo == 1:
         raise NotImplementedError('conv2d: a channel-padded activation (%d -> %d) needs the tensor-core kernel'
@@ -72,6 +79,14 @@ def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=Fals
         prepared = ctx.net.prepared_weights(w, ws, kernel, cin, fmaps, up2_phase=up2, cin_pad=xa.c)
     res = None if residual is None else rt.split_unpack(_act_of(residual)).f32
     head = None
+    rec = ctx.tape is not None
+    if rec:
+        # training forward: keep what the backward needs - the input planes (weight gradient), the fp32
+        # output (activation mask, pooling) and the output planes (next layer) - and no fused image head
+        if algo == 1:
+            raise NotImplementedError('backward needs the tensor-core conv (channels multiple of 16), got %d -> %d'
+                                      % (cin, fmaps))
+        torgb, keep_f32, next_tc = None, True, True
     if torgb is not None and algo != 1:
         scope, nch, tanh = torgb
         wr, br = ctx.net.vars[scope + '/weight'], ctx.net.vars[scope + '/bias']
@@ -85,7 +100,30 @@ def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=Fals
         t.rgb = (torgb[0], torgb[2], images)
     else:
         t.act = out
+    if rec:
+        ctx.tape.append(dict(kind='conv', x=xa, y=t.act, w=w.name, b=b.name, wscale=ws, k=kernel, cin=cin, cout=fmaps,
+                             act=act, up2=up2, residual=None if residual is None else _act_of(residual)))
+    if strip is not None:
+        orig = _act_of(x)
+        m = orig.n * orig.h * orig.w
+        flat = rt.split_unpack(t.act).f32.view(-1, fmaps)[:m]
+        out = Act(orig.n, orig.h, orig.w, fmaps, f32=flat.view(orig.n, orig.h, orig.w, fmaps))
+        ctx.tape.append(dict(kind='view', x=t.act, y=out, pixels=m))
+        t.act = out
     return t
+
+
+def _pixel_strip(ctx, a):
+    """[n,h,w,c] -> the same pixels as one image [1,2,ceil(m/2),c] (zero padded); records the view."""
+    rt = ctx.rt
+    rt.split_unpack(a)
+    m = a.n * a.h * a.w
+    m2 = (m + 1) // 2
+    buf = torch.zeros(2 * m2, a.c, dtype=torch.float32, device=rt.device)
+    buf[:m].copy_(a.f32.view(m, a.c))
+    strip = Act(1, 2, m2, a.c, f32=buf.view(1, 2, m2, a.c))
+    ctx.tape.append(dict(kind='view', x=a, y=strip, pixels=m))
+    return strip
 
 
 def _mul(d, f):
@@ -105,7 +143,10 @@ def downscale2d(x, factor=2):
     f = factor
     while f > 1:
         assert f % 2 == 0
-        a = ctx.rt.avgpool2(a)
+        b = ctx.rt.avgpool2(a)
+        if ctx.tape is not None:
+            ctx.tape.append(dict(kind='pool', x=a, y=b))
+        a = b
         f //= 2
     return T(shape, ctx, act=a)
 
@@ -124,6 +165,9 @@ def _fromrgb(x, fmaps, name):
         if x.nchw is None:
             raise NotImplementedError('FromRGB on a downscaled image (lod > 0) is not implemented (SURVEY N1)')
         out = ctx.rt.fromrgb(x.nchw, w.value, b.value, _wscale(w.shape, SQRT2), fmaps, lrelu=True)
+        if ctx.tape is not None:
+            ctx.tape.append(dict(kind='fromrgb', img=x.nchw, y=out, w=w.name, b=b.name, wscale=_wscale(w.shape, SQRT2),
+                                 cout=fmaps))
         return T(shape, ctx, act=out)
 
 
@@ -138,6 +182,8 @@ def _slice_outputs(t, latent_channels, names):
         else:
             a = ctx.rt.split_unpack(_act_of(t))
             nchw = ctx.rt.nhwc_to_nchw(a.f32, c_off=i * latent_channels, c=latent_channels)
+            if ctx.tape is not None:
+                ctx.tape.append(dict(kind='slice', x=a, out=nchw, c_off=i * latent_channels, c=latent_channels))
             outs.append(T(shape, ctx, nchw=nchw, name=name))
     return tuple(outs)
 
@@ -297,6 +343,9 @@ def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_bas
         rt.nchw_to_nhwc(zl_latents_in.nchw, out=buf, c_off=latent_channels, c_total=c2)
         combo_shape[0] = n
         combo_in = T(combo_shape, ctx, act=Act(n, h, w, c2, f32=buf))
+        if ctx.tape is not None:
+            ctx.tape.append(dict(kind='concat', y=combo_in.act, inputs=[zg_latents_in.nchw, zl_latents_in.nchw],
+                                 c=latent_channels))
     lod_in = _lod(ctx)
 
     def block(x, res):
@@ -346,6 +395,9 @@ def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_bas
             if x.rgb is not None and x.rgb[0] == 'ToRGB_lod%d' % lod and x.rgb[1] == bool(apply_tanh):
                 return T(shape, ctx, nchw=x.rgb[2])                        # produced by the conv epilogue
             img = ctx.rt.torgb(_act_of(x), w.value, b.value, _wscale(w.shape, 1.0), num_channels, apply_tanh)
+            if ctx.tape is not None:
+                ctx.tape.append(dict(kind='torgb', x=_act_of(x), img=img, w=w.name, b=b.name,
+                                     wscale=_wscale(w.shape, 1.0), tanh=bool(apply_tanh)))
             return T(shape, ctx, nchw=img)
 
     def up_img(t, factor):
