@@ -253,6 +253,24 @@ int tmx_torgb_bwd(tmx_handle_t h, const float* dimg, const float* img, const flo
 int tmx_fromrgb_bwd(tmx_handle_t h, const float* img, const float* dz, const float* w, float wscale, float* dw,
                     float* dimg, int N, int Cimg, int H, int W, int Cout, tmx_stream_t s);
 
+/* D_patch head, input gradients: dense (networks.py:38-43; dz = dy * lrelu'(y) when lrelu) and
+ * minibatch_stddev_layer (networks.py:177-189; x, dx NHWC [N][H][W][C], dy NHWC [N][H][W][C_total], ds: [N/G] scratch). */
+int tmx_dense_bwd_input(tmx_handle_t h, const float* dy, const float* y, const float* w, float wscale, float* dx, int N,
+                        int K, int Cout, int lrelu, float alpha, tmx_stream_t s);
+int tmx_mbstd_bwd(tmx_handle_t h, const float* x, const float* dy, float* dx, float* ds, int N, int H, int W, int C,
+                  int C_total, int group_size, tmx_stream_t s);
+/* L1 image loss of EG_wgan (loss.py:142-146): grad = scale * sign(a - b), *loss_sum += sum |a - b| (may be NULL). */
+int tmx_loss_l1_grad(tmx_handle_t h, const float* a, const float* b, float* grad, float* loss_sum, int64_t n, float scale,
+                     tmx_stream_t s);
+/* Adjoint of tmx_latent_blend COPY mode (tiling_permutation, loss.py:92-100): scatter-add of the canvas gradient
+ * NCHW [N][C][H][W] into d_src NCHW [N][C][sh][sw] (caller zero-initialises); reverse: source sample N-1-n. */
+int tmx_latent_gather_bwd(tmx_handle_t h, const float* dcanvas, float* dsrc, const int32_t* idx_h, const int32_t* idx_w,
+                          int N, int C, int sh, int sw, int H, int W, uint64_t pin_rows, uint64_t pin_cols, int reverse,
+                          tmx_stream_t s);
+/* out[row] (+)= scale * sum_i in[row][i] : adjoint of tiling a [N][C][1][1] code over a canvas (loss.py:176), loss means. */
+int tmx_row_sum(tmx_handle_t h, const float* in, float* out, int rows, int len, float scale, int accumulate,
+                tmx_stream_t s);
+
 /* tmx_grad_prepare: gradient w.r.t. a layer OUTPUT y [N][H][W][C] -> operand of that layer's dgrad / wgrad:
  *   v = src (+ add) ; v *= (y > 0 ? 1 : alpha) if mask ; dbias[c] += dbias_scale * sum v ; write v.
  *   src_kind 0: g on the zero-ringed grid (a consumer's tmx_conv2d_dgrad output) folded by `fold`

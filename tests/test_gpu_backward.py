@@ -253,3 +253,28 @@ def test_encoder_backward_vs_autograd(func, alpha, monkeypatch):
              want_input_grads=False)
     torch.cuda.synchronize()
     print('worst variable gradient (rel L2):', _check_param_grads(net, flat_grad, P, L2_TOL[alpha], MAX_TOL[alpha]))
+
+
+@pytest.mark.parametrize('alpha', [1.0, 0.2])
+def test_discriminator_input_gradient_vs_autograd(alpha, monkeypatch):
+    """D_patch as the fixed critic of the E/G loss: d sum(scores * ds) / d images (conv pyramid, pooling,
+    minibatch stddev, dense head, FromRGB), no variable gradients."""
+    from texturemixer_b200.backward import backward
+    _set_alpha(monkeypatch, alpha)
+    rng = np.random.RandomState(11)
+    params = R.init_params('D_patch', rng, **R.CONFIG['D_patch'])
+    net, cfg = _net('D_patch', params)
+    n = 8
+    x = rng.uniform(-1, 1, (n, 3, 128, 128)).astype(np.float32)
+    ds = rng.randn(n, 1, 1, 1).astype(np.float32)
+    xt = torch.from_numpy(x).requires_grad_(True)
+    P = R.to_torch(params)
+    scores = R.D_patch(xt, P, **cfg)
+    (scores * torch.from_numpy(ds)).sum().backward()
+    tape = []
+    got_scores = net.get_output_for(torch.from_numpy(x).cuda(), tape=tape)
+    assert _nmax(got_scores.cpu().numpy(), scores.detach().numpy()) <= 1e-3
+    (dimg,) = backward(net, tape, [torch.from_numpy(ds).cuda()], None, want_input_grads=True, param_grads=False)
+    torch.cuda.synchronize()
+    assert dimg.shape == (n, 3, 128, 128)
+    assert _rel_l2(dimg.cpu().numpy(), xt.grad.numpy()) <= L2_TOL[alpha]

@@ -82,6 +82,11 @@ _SIGNATURES = {
     'tmx_conv_wgrad_unphase': (C.c_int, [_P, _P, _P, _I, _I, _P]),
     'tmx_torgb_bwd': (C.c_int, [_P, _P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'tmx_fromrgb_bwd': (C.c_int, [_P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _I, _P]),
+    'tmx_dense_bwd_input': (C.c_int, [_P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _F, _P]),
+    'tmx_mbstd_bwd': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'tmx_loss_l1_grad': (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _F, _P]),
+    'tmx_latent_gather_bwd': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, C.c_uint64, C.c_uint64, _I, _P]),
+    'tmx_row_sum': (C.c_int, [_P, _P, _P, _I, _I, _F, _I, _P]),
     'tmx_grad_prepare': (C.c_int, [_P, C.POINTER(GradDesc), C.POINTER(GradIO), _P]),
     'tmx_nonfinite_check': (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     'tmx_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _F, _F, _F, _F, _F, _P, _P, _P]),

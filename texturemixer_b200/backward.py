@@ -19,7 +19,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib
+from . import _lib, runtime
 
 
 def _ptr(t):
@@ -66,10 +66,11 @@ def _combine(rt, act, contribs, want_planes, want_f32, mask_y=None, dbias=None, 
                            want_f32=want_f32, dbias=dbias, phase_pack=phase_pack)
 
 
-def backward(net, tape, out_grads, flat_grad, want_input_grads=True):
+def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads=True):
     """Differentiate one recorded evaluation of `net`.
     out_grads : list matching the network outputs (NCHW fp32 device tensors, or None for unused outputs)
     flat_grad : fp32 buffer like net.flat; variable gradients are accumulated into it
+    param_grads=False: only propagate to the inputs (a fixed critic inside the E/G loss: flat_grad may be None)
     Returns the list of gradients w.r.t. the network inputs (NCHW fp32; None for image inputs of the
     encoders unless the first layer's data gradient is defined, i.e. for D_patch/FromRGB: NCHW image gradient)."""
     rt = net.rt
@@ -80,8 +81,17 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True):
     by_tensor = {id(t): g for t, g in zip(outs, out_grads) if g is not None}
     input_grads = {}
 
+    scratch = {}
+
     def gview(name):
-        return net.grad_view(flat_grad, name)
+        if param_grads:
+            return net.grad_view(flat_grad, name)
+        v = net.vars[name]                      # throw-away target for kernels that always emit a weight gradient
+        if v.size not in scratch:
+            scratch[v.size] = torch.zeros(v.size, dtype=torch.float32, device=rt.device)
+        return scratch[v.size]
+
+    tgrads = {}        # gradients w.r.t. plain tensors (dense head), keyed by tensor identity
 
     for rec in reversed(tape[:-1]):
         kind = rec['kind']
@@ -108,6 +118,43 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True):
                                             _ptr(gview(rec['b'])), a.n, a.h, a.w, a.c, w.shape[3], int(rec['tanh']),
                                             rt.stream()), 'tmx_torgb_bwd')
             grads.add(a, ('f32', dy))
+        elif kind == 'dense':
+            g = by_tensor.get(id(rec['y']))
+            if g is None and rec.get('alias') is not None:
+                g = by_tensor.get(id(rec['alias']))
+            if g is None:
+                g = tgrads.pop(id(rec['y']), None)
+            if g is None:
+                continue
+            if param_grads:
+                raise NotImplementedError('weight gradient of the dense head is not built yet (D-phase, round 2)')
+            y, xin = rec['y'], rec['x']
+            n, cout = y.shape
+            kdim = xin.numel() // n
+            dx = rt.empty(*xin.shape)
+            wv = net.vars[rec['w']]
+            _lib.check(rt.lib.tmx_dense_bwd_input(rt.handle, _ptr(g.contiguous()), _ptr(y), _ptr(wv.value),
+                                                  float(rec['wscale']), _ptr(dx), n, kdim, cout, int(rec['act']),
+                                                  runtime.LRELU_ALPHA, rt.stream()), 'tmx_dense_bwd_input')
+            tgrads[id(xin)] = dx
+        elif kind == 'flatten':
+            g = tgrads.pop(id(rec['y']), None)
+            if g is None:
+                continue
+            a = rec['x']
+            grads.add(a, ('f32', rt.nchw_to_nhwc(g.view(a.n, a.c, a.h, a.w))))
+        elif kind == 'mbstd':
+            contribs = grads.pop(rec['y'])
+            if not contribs:
+                continue
+            y, x = rec['y'], rec['x']
+            _, dy = _combine(rt, y, contribs, want_planes=False, want_f32=True)
+            g = min(rec['group'], x.n)
+            dx = rt.empty(x.n, x.h, x.w, x.c)
+            ds = rt.empty(x.n // g)
+            _lib.check(rt.lib.tmx_mbstd_bwd(rt.handle, _ptr(rt.split_unpack(x).f32), _ptr(dy), _ptr(dx), _ptr(ds), x.n,
+                                            x.h, x.w, x.c, y.c, rec['group'], rt.stream()), 'tmx_mbstd_bwd')
+            grads.add(x, ('f32', dx))
         elif kind == 'view':
             # y holds the first `pixels` pixels of x (or vice versa) in another [n,h,w] arrangement
             contribs = grads.pop(rec['y'])
@@ -133,26 +180,28 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True):
             has_res = rec['residual'] is not None
             mask = rt.split_unpack(y).f32 if rec['act'] else None
             dz, dz_f32 = _combine(rt, y, contribs, want_planes=True, want_f32=has_res, mask_y=mask,
-                                  dbias=gview(rec['b']), phase_pack=up2)
+                                  dbias=gview(rec['b']) if param_grads else None, phase_pack=up2)
             if has_res:
                 grads.add(rec['residual'], ('f32', dz_f32))         # y = conv(x) + residual (networks.py:437)
             w = net.vars[rec['w']]
-            if x.c != rec['cin']:
+            if param_grads and x.c != rec['cin']:
                 raise NotImplementedError('weight gradient of a channel-padded conv (minibatch stddev) is not built yet')
             fwd = net.prepared_weights(w, rec['wscale'], k, rec['cin'], cout, up2_phase=up2, cin_pad=x.c)
             if up2:
                 # sub-pixel form: low-res geometry, 4*Cout phase channels
                 hs, ws_, ng = x.h, x.w, 4 * cout
-                dwp = torch.zeros(9, cin_g, ng, dtype=torch.float32, device=rt.device)
-                rt.conv_wgrad((x.hi, x.lo), dz, x.n, hs, ws_, cin_g, ng, 3, rec['wscale'], dwp)
-                _lib.check(rt.lib.tmx_conv_wgrad_unphase(rt.handle, _ptr(dwp), _ptr(gview(rec['w'])), cin_g, cout,
-                                                         rt.stream()), 'tmx_conv_wgrad_unphase')
-                wt = rt.transpose_weights(fwd, ng, 9, cin_g)
+                if param_grads:
+                    dwp = torch.zeros(9, cin_g, ng, dtype=torch.float32, device=rt.device)
+                    rt.conv_wgrad((x.hi, x.lo), dz, x.n, hs, ws_, cin_g, ng, 3, rec['wscale'], dwp)
+                    _lib.check(rt.lib.tmx_conv_wgrad_unphase(rt.handle, _ptr(dwp), _ptr(gview(rec['w'])), cin_g, cout,
+                                                             rt.stream()), 'tmx_conv_wgrad_unphase')
+                wt = net.cached(('wt', rec['w'], True), lambda: rt.transpose_weights(fwd, ng, 9, cin_g))
                 g = rt.conv_dgrad(dz, x.n, hs, ws_, cin_g, ng, 3, wt)
                 grads.add(x, ('grid', g, 1))
             else:
-                rt.conv_wgrad((x.hi, x.lo), dz, x.n, x.h, x.w, cin_g, cout, k, rec['wscale'], gview(rec['w']))
-                wt = rt.transpose_weights(fwd, cout, k * k, cin_g)
+                if param_grads:
+                    rt.conv_wgrad((x.hi, x.lo), dz, x.n, x.h, x.w, cin_g, cout, k, rec['wscale'], gview(rec['w']))
+                wt = net.cached(('wt', rec['w'], False), lambda: rt.transpose_weights(fwd, cout, k * k, cin_g))
                 g = rt.conv_dgrad(dz, x.n, x.h, x.w, cin_g, cout, k, wt)
                 grads.add(x, ('grid', g, 0 if k == 3 else 2))
         elif kind == 'fromrgb':
@@ -160,7 +209,8 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True):
             contribs = grads.pop(y)
             if not contribs:
                 continue
-            _, dz = _combine(rt, y, contribs, want_planes=False, want_f32=True, mask_y=y.f32, dbias=gview(rec['b']))
+            _, dz = _combine(rt, y, contribs, want_planes=False, want_f32=True, mask_y=y.f32,
+                             dbias=gview(rec['b']) if param_grads else None)
             img = rec['img']
             n, cimg, h, w_ = img.shape
             dimg = rt.empty(n, cimg, h, w_) if want_input_grads else None

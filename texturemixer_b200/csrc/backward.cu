@@ -412,6 +412,210 @@ extern "C" int tmx_fromrgb_bwd(tmx_handle_t h, const float* img, const float* dz
   return TMX_OK;
 }
 
+// ---------------------------------------------------------------- dense / minibatch-stddev input gradients (D head)
+// dx[n][k] = wscale * sum_o dz[n][o] * w[k][o],  dz = dy * lrelu'(y) (networks.py:38-43, 72-75).
+// One warp per input feature k: lanes stride over o (coalesced rows of w), up to 32 samples accumulated per pass.
+__global__ void __launch_bounds__(256) dense_bwd_input_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                              const float* __restrict__ w, float wscale,
+                                                              float* __restrict__ dx, int N, int K, int Cout, int lrelu,
+                                                              float alpha) {
+  const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (k >= K) return;
+  for (int n0 = 0; n0 < N; n0 += 32) {
+    const int nn = min(32, N - n0);
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int o = lane; o < Cout; o += 32) {
+      const float wv = __ldg(w + (long long)k * Cout + o);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i < nn) {
+          float g = __ldg(dy + (long long)(n0 + i) * Cout + o);
+          if (lrelu) g *= (__ldg(y + (long long)(n0 + i) * Cout + o) > 0.f) ? 1.f : alpha;
+          acc[i] = fmaf(g, wv, acc[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float v = acc[i];
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+      if (lane == 0 && i < nn) dx[(long long)(n0 + i) * K + k] = v * wscale;
+    }
+  }
+}
+
+extern "C" int tmx_dense_bwd_input(tmx_handle_t h, const float* dy, const float* y, const float* w, float wscale,
+                                   float* dx, int N, int K, int Cout, int lrelu, float alpha, tmx_stream_t s) {
+  TMX_REQUIRE(h && dy && w && dx && (!lrelu || y), TMX_ERR_ARG, "tmx_dense_bwd_input: NULL argument");
+  TMX_REQUIRE(N > 0 && K > 0 && Cout > 0, TMX_ERR_SHAPE, "tmx_dense_bwd_input: bad shape");
+  dense_bwd_input_kernel<<<tmx_ceil_div(K, 8), 256, 0, (cudaStream_t)s>>>(dy, y, w, wscale, dx, N, K, Cout, lrelu, alpha);
+  TMX_LAUNCHED(h, "dense_bwd_input_kernel");
+  return TMX_OK;
+}
+
+// minibatch_stddev_layer backward (networks.py:177-189).  y = [x, s broadcast, 0...]:
+//   dx = dy[..., :C] + ds[m] * d s[m] / dx,   ds[m] = sum over the group's samples and pixels of dy[..., C],
+//   d s[m] / dx[g,m,e] = (x[g,m,e] - mean_g) / (G * sigma[m,e] * E),  sigma = sqrt(var_g + 1e-8), E = H*W*C.
+__global__ void __launch_bounds__(256) mbstd_ds_kernel(const float* __restrict__ dy, float* __restrict__ ds, int G,
+                                                       int M, int HW, int C, int C_total) {
+  const int m = blockIdx.x;
+  float acc = 0.f;
+  for (int e = threadIdx.x; e < G * HW; e += blockDim.x) {
+    const int g = e / HW, p = e % HW;
+    acc += __ldg(dy + ((long long)(g * M + m) * HW + p) * C_total + C);
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ds[m] = red[0];
+}
+
+__global__ void __launch_bounds__(256) mbstd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                        const float* __restrict__ ds, float* __restrict__ dx, int G,
+                                                        int M, long long per_sample, int C, int C_total) {
+  // one thread per (m, e): loops over the G samples of the group
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)M * per_sample) return;
+  const int m = (int)(t / per_sample);
+  const long long e = t % per_sample;
+  const long long pix = e / C;
+  const int c = (int)(e % C);
+  float mean = 0.f;
+  for (int g = 0; g < G; ++g) mean += __ldg(x + (long long)(g * M + m) * per_sample + e);
+  mean /= (float)G;
+  float var = 0.f;
+  for (int g = 0; g < G; ++g) {
+    const float d = __ldg(x + (long long)(g * M + m) * per_sample + e) - mean;
+    var += d * d;
+  }
+  const float sigma = sqrtf(var / (float)G + 1e-8f);
+  const float coef = __ldg(ds + m) / ((float)G * sigma * (float)per_sample);
+  const long long HW = per_sample / C;
+  for (int g = 0; g < G; ++g) {
+    const long long n = g * M + m;
+    const float xv = __ldg(x + n * per_sample + e);
+    dx[n * per_sample + e] = __ldg(dy + (n * HW + pix) * C_total + c) + coef * (xv - mean);
+  }
+}
+
+extern "C" int tmx_mbstd_bwd(tmx_handle_t h, const float* x, const float* dy, float* dx, float* ds, int N, int H, int W,
+                             int C, int C_total, int group_size, tmx_stream_t s) {
+  TMX_REQUIRE(h && x && dy && dx && ds, TMX_ERR_ARG, "tmx_mbstd_bwd: NULL argument");
+  TMX_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C_total > C, TMX_ERR_SHAPE, "tmx_mbstd_bwd: bad shape");
+  const int G = group_size < N ? group_size : N;
+  TMX_REQUIRE(N % G == 0, TMX_ERR_SHAPE, "tmx_mbstd_bwd: batch %d is not a multiple of the group size %d", N, G);
+  const int M = N / G;
+  const long long per_sample = (long long)H * W * C;
+  mbstd_ds_kernel<<<M, 256, 0, (cudaStream_t)s>>>(dy, ds, G, M, H * W, C, C_total);
+  TMX_LAUNCHED(h, "mbstd_ds_kernel");
+  mbstd_bwd_kernel<<<tmx_ceil_div((long long)M * per_sample, 256), 256, 0, (cudaStream_t)s>>>(x, dy, ds, dx, G, M,
+                                                                                             per_sample, C, C_total);
+  TMX_LAUNCHED(h, "mbstd_bwd_kernel");
+  return TMX_OK;
+}
+
+// ---------------------------------------------------------------- loss gradients (loss.py:105-259)
+// L1 image term: loss_n = weight * mean_{c,h,w} |a - b| ; the optimizer takes the batch mean (run.py:321), so
+// d/da = scale * sign(a - b) with scale = weight / (C*H*W*N); *loss_sum accumulates sum |a - b| for reporting.
+__global__ void __launch_bounds__(256) l1_grad_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                      float* __restrict__ grad, float* __restrict__ loss_sum,
+                                                      long long n, float scale) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float d = __ldg(a + i) - __ldg(b + i);
+    acc += fabsf(d);
+    grad[i] = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+  }
+  if (loss_sum != nullptr) {
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+    if ((threadIdx.x & 31) == 0) atomicAdd(loss_sum, acc);
+  }
+}
+
+extern "C" int tmx_loss_l1_grad(tmx_handle_t h, const float* a, const float* b, float* grad, float* loss_sum, int64_t n,
+                                float scale, tmx_stream_t s) {
+  TMX_REQUIRE(h && a && b && grad && n > 0, TMX_ERR_ARG, "tmx_loss_l1_grad: bad argument");
+  long long blocks = (n + 255) / 256;
+  if (blocks > (long long)h->sm_count * 8) blocks = (long long)h->sm_count * 8;
+  l1_grad_kernel<<<(int)blocks, 256, 0, (cudaStream_t)s>>>(a, b, grad, loss_sum, n, scale);
+  TMX_LAUNCHED(h, "l1_grad_kernel");
+  return TMX_OK;
+}
+
+// ---------------------------------------------------------------- adjoints of the latent canvas ops
+// tiling_permutation (+ corner re-pin) is a gather; its adjoint scatters: d_src[n][c][sy][sx] += d_canvas[n][c][i][j].
+// d_src must be zero-initialised (or hold an earlier contribution).  Same index conventions as tmx_latent_blend COPY.
+__global__ void __launch_bounds__(256) blend_copy_bwd_kernel(const float* __restrict__ dcanvas, float* __restrict__ dsrc,
+                                                             const int32_t* __restrict__ idx_h,
+                                                             const int32_t* __restrict__ idx_w, int N, int C, int h,
+                                                             int w, int H, int W, unsigned long long pin_rows,
+                                                             unsigned long long pin_cols, int reverse) {
+  const long long total = (long long)N * C * H * W;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int j = (int)(t % W);
+  long long q = t / W;
+  const int i = (int)(q % H);
+  q /= H;
+  const int c = (int)(q % C);
+  const int n = (int)(q / C);
+  const bool pinned = pin_rows != 0 && ((pin_rows >> (i / h)) & 1ull) && ((pin_cols >> (j / w)) & 1ull);
+  int yy = i, xx = j;
+  if (!pinned) {
+    if (idx_h) yy = __ldg(idx_h + (long long)n * H + i);
+    if (idx_w) xx = __ldg(idx_w + (long long)n * W + j);
+  }
+  const int nn = reverse ? N - 1 - n : n;
+  atomicAdd(dsrc + (((long long)nn * C + c) * h + yy % h) * w + xx % w, __ldg(dcanvas + t));
+}
+
+extern "C" int tmx_latent_gather_bwd(tmx_handle_t h, const float* dcanvas, float* dsrc, const int32_t* idx_h,
+                                     const int32_t* idx_w, int N, int C, int sh, int sw, int H, int W, uint64_t pin_rows,
+                                     uint64_t pin_cols, int reverse, tmx_stream_t s) {
+  TMX_REQUIRE(h && dcanvas && dsrc, TMX_ERR_ARG, "tmx_latent_gather_bwd: NULL argument");
+  TMX_REQUIRE(N > 0 && C > 0 && sh > 0 && sw > 0 && H > 0 && W > 0, TMX_ERR_SHAPE, "tmx_latent_gather_bwd: bad shape");
+  const long long total = (long long)N * C * H * W;
+  blend_copy_bwd_kernel<<<tmx_ceil_div(total, 256), 256, 0, (cudaStream_t)s>>>(dcanvas, dsrc, idx_h, idx_w, N, C, sh, sw,
+                                                                                H, W, pin_rows, pin_cols, reverse);
+  TMX_LAUNCHED(h, "blend_copy_bwd_kernel");
+  return TMX_OK;
+}
+
+// tf.tile of a [N][C][1][1] code over the canvas (loss.py:176): adjoint = sum over the canvas, one block per (n, c).
+// out[row] (+)= scale * sum_i in[row][i]
+__global__ void __launch_bounds__(256) row_sum_kernel(const float* __restrict__ in, float* __restrict__ out, int len,
+                                                      float scale, int accumulate) {
+  const long long row = blockIdx.x;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) acc += __ldg(in + row * len + i);
+  __shared__ float red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[row] = (accumulate ? out[row] : 0.f) + red[0] * scale;
+}
+
+extern "C" int tmx_row_sum(tmx_handle_t h, const float* in, float* out, int rows, int len, float scale, int accumulate,
+                           tmx_stream_t s) {
+  TMX_REQUIRE(h && in && out && rows > 0 && len > 0, TMX_ERR_ARG, "tmx_row_sum: bad argument");
+  row_sum_kernel<<<rows, 256, 0, (cudaStream_t)s>>>(in, out, len, scale, accumulate);
+  TMX_LAUNCHED(h, "row_sum_kernel");
+  return TMX_OK;
+}
+
 int tmx_conv2d_dgrad_tc(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, const uint16_t* dz_hi,
                         const uint16_t* dz_lo, const uint16_t* wt_hi, const uint16_t* wt_lo, float* g_f32,
                         cudaStream_t st);

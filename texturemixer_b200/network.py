@@ -326,6 +326,15 @@ class Network:
         net.copy_vars_from(self)
         return net
 
+    def cached(self, key, make):
+        """Per-weight-version cache for derived tensors (e.g. transposed planes for the data gradient)."""
+        o = self._owner()
+        ent = o._prepared.get(key)
+        if ent is None or ent[1] != o._version:
+            ent = (make(), o._version)
+            o._prepared[key] = ent
+        return ent[0]
+
     def prepared_weights(self, var, wscale, k, cin, cout, up2_phase=False, cin_pad=None):
         """Cached bf16 hi/lo planes of a conv weight for the tensor-core kernel
         (sub-pixel planes when the conv reads through upscale2d); recomputed

@@ -478,6 +478,8 @@ def D_patch(images_in, num_channels=3, resolution=128, fmap_base=8192, fmap_deca
                     x = _dense_layer(x, 1, gain=1, act=False)
                 if ctx.mode == 'run':
                     x.nchw = x.nchw.view(x.nchw.shape[0], 1, 1, 1)
+                    if ctx.tape is not None:
+                        ctx.tape[-1]['alias'] = x.nchw
                 x.shape = [x.shape[0], 1, 1, 1]
             else:
                 with ctx.variable_scope('Conv1'):
@@ -500,7 +502,10 @@ def _minibatch_stddev_layer(x, group_size):
     shape = [x.shape[0], x.shape[1] + 1, x.shape[2], x.shape[3]]
     if ctx.mode == 'template':
         return T(shape, ctx)
-    out, _ = ctx.rt.mbstd(_act_of(x), group_size)
+    xa = _act_of(x)
+    out, _ = ctx.rt.mbstd(xa, group_size)
+    if ctx.tape is not None:
+        ctx.tape.append(dict(kind='mbstd', x=xa, y=out, group=group_size))
     return T(shape, ctx, act=out)
 
 
@@ -518,8 +523,12 @@ def _dense_layer(x, fmaps, gain=SQRT2, act=True):
     if x.nchw is None:
         a = rt.split_unpack(_act_of(x))
         x.nchw = rt.nhwc_to_nchw(a.f32)
+        if ctx.tape is not None:
+            ctx.tape.append(dict(kind='flatten', x=a, y=x.nchw))
     flat = x.nchw.view(x.nchw.shape[0], -1)
     out = rt.dense(flat, w.value, b.value, _wscale(w.shape, gain), lrelu=act)
+    if ctx.tape is not None:
+        ctx.tape.append(dict(kind='dense', x=x.nchw, y=out, w=w.name, b=b.name, wscale=_wscale(w.shape, gain), act=act))
     return T(shape, ctx, nchw=out)
 
 
