@@ -271,6 +271,9 @@ int tmx_latent_gather_bwd(tmx_handle_t h, const float* dcanvas, float* dsrc, con
 int tmx_row_sum(tmx_handle_t h, const float* in, float* out, int rows, int len, float scale, int accumulate,
                 tmx_stream_t s);
 
+/* out = a + b over n fp32 elements (two gradient contributions meeting at one tensor). */
+int tmx_add_f32(tmx_handle_t h, const float* a, const float* b, float* out, int64_t n, tmx_stream_t s);
+
 /* tmx_grad_prepare: gradient w.r.t. a layer OUTPUT y [N][H][W][C] -> operand of that layer's dgrad / wgrad:
  *   v = src (+ add) ; v *= (y > 0 ? 1 : alpha) if mask ; dbias[c] += dbias_scale * sum v ; write v.
  *   src_kind 0: g on the zero-ringed grid (a consumer's tmx_conv2d_dgrad output) folded by `fold`

@@ -1,0 +1,75 @@
+"""ORACLE (test infrastructure): torch restatement of the E/G loss of the train step,
+`loss.EG_wgan` (/root/reference/loss.py:105-259) with the reference config
+(config.py:50-68: zg 'hard', zl 'permutational', block_size 0) and
+gram_weight = 0 (VGG weights are not available) - autograd supplies the
+gradients the device backward is checked against.
+
+The random draws of the graph (crop offsets of `random_crop`, loss.py:78-90, and the
+blend `mixing_factors`, loss.py:237) are explicit arguments so that both sides see
+the same values; index vectors replace the 0/1 permutation matrices."""
+import torch
+
+from . import networks_ref as R
+
+
+def tiling_permutation(x, scale_h, scale_w, idx_h, idx_w):
+    """loss.py:92-100 in gather form (differentiable).  x [N,C,h,w]; idx_h [N,h*sh]; idx_w [N,w*sw] int."""
+    n, c, h, w = x.shape
+    t = x.repeat(1, 1, scale_h, scale_w)
+    ih = torch.as_tensor(idx_h, dtype=torch.long)
+    iw = torch.as_tensor(idx_w, dtype=torch.long)
+    t = torch.stack([t[b][:, ih[b]][:, :, iw[b]] for b in range(n)])          # P_h @ tile(X) @ P_w
+    t1 = torch.cat([x, t[:, :, :h, w:-w], x], dim=3)
+    t2 = t[:, :, h:-h, :]
+    t3 = torch.cat([x, t[:, :, -h:, w:-w], x], dim=3)
+    return torch.cat([t1, t2, t3], dim=2)
+
+
+def crop(images, yx, size):
+    """loss.py:78-90 with the drawn offset made explicit: one (y, x) for the whole batch."""
+    y, x = yx
+    return images[:, :, y:y + size[0], x:x + size[1]]
+
+
+def EG_wgan(P, reals, idx, crop_interp, crop_blend, mixing_factors, scale_h=3, scale_w=3, rec_G_weight=1.0,
+            pixel_weight=200.0, kl_weight=0.0, interp_G_weight=1.0, blend_interp_G_weight=1.0, cfg=None):
+    """P: dict of parameter dicts for 'E_zg','E_zl','G','D_rec','D_interp','D_blend'.  Returns the per-sample
+    loss vector [N] (the optimizer differentiates its mean, run.py:321) and a dict of named terms."""
+    cfg = cfg or R.CONFIG
+    zg_mu, zg_ls = R.E_zg(reals, P['E_zg'], **cfg['E_zg'])                           # loss.py:119
+    zl_mu, zl_ls = R.E_zl(reals, P['E_zl'], **cfg['E_zl'])                           # loss.py:126
+    lat = zl_mu.shape[2]
+    rec = R.G_res(zg_mu.repeat(1, 1, lat, lat), zl_mu, P['G'], **cfg['G_res'])        # loss.py:130
+    terms = {}
+    loss = 0
+    if rec_G_weight > 0:
+        terms['rec_G'] = (-R.D_patch(rec, P['D_rec'], **cfg['D_patch'])).mean(dim=(1, 2, 3)) * rec_G_weight
+        loss = loss + terms['rec_G']
+    if pixel_weight > 0:
+        terms['rec_pixel'] = (rec - reals).abs().mean(dim=(1, 2, 3)) * pixel_weight  # loss.py:143
+        loss = loss + terms['rec_pixel']
+    if kl_weight > 0:                                                                 # loss.py:163-171
+        for tag, mu, ls in (('KL_zg', zg_mu, zg_ls), ('KL_zl', zl_mu, zl_ls)):
+            terms[tag] = -0.5 * (1 + 2 * ls - mu ** 2 - torch.exp(2 * ls)).mean(dim=(1, 2, 3)) * kl_weight
+            loss = loss + terms[tag]
+    g_cfg = dict(cfg['G_res'], scale_h=scale_h, scale_w=scale_w)
+    zg_c = zg_mu.repeat(1, 1, lat * scale_h, lat * scale_w)                           # loss.py:176 'hard'
+    zl_c = tiling_permutation(zl_mu, scale_h, scale_w, idx['h_forward'], idx['w_forward'])   # loss.py:194
+    size = reals.shape[2:]
+    if interp_G_weight > 0:
+        interp = R.G_res(zg_c, zl_c, P['G'], **g_cfg)                                 # loss.py:197
+        terms['interp_G'] = (-R.D_patch(crop(interp, crop_interp, size), P['D_interp'], **cfg['D_patch'])
+                             ).mean(dim=(1, 2, 3)) * interp_G_weight
+        loss = loss + terms['interp_G']
+    if blend_interp_G_weight > 0:
+        zg_r = torch.flip(zg_mu, dims=[0]).repeat(1, 1, lat * scale_h, lat * scale_w)             # loss.py:218
+        zl_r = tiling_permutation(torch.flip(zl_mu, dims=[0]), scale_h, scale_w, idx['h_backward'],
+                                  idx['w_backward'])                                              # loss.py:236
+        t = mixing_factors
+        bzg = zg_r + (zg_c - zg_r) * t                                                            # loss.py:238
+        bzl = zl_r + (zl_c - zl_r) * t
+        blend = R.G_res(bzg, bzl, P['G'], **g_cfg)                                                # loss.py:240
+        terms['blend_G'] = (-R.D_patch(crop(blend, crop_blend, size), P['D_blend'], **cfg['D_patch'])
+                            ).mean(dim=(1, 2, 3)) * blend_interp_G_weight
+        loss = loss + terms['blend_G']
+    return loss, terms

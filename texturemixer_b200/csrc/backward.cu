@@ -616,6 +616,22 @@ extern "C" int tmx_row_sum(tmx_handle_t h, const float* in, float* out, int rows
   return TMX_OK;
 }
 
+// out = a + b (fp32): two gradient contributions meeting at one tensor (e.g. critic gradient + L1 gradient)
+__global__ void __launch_bounds__(256) add_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                  float* __restrict__ out, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __ldg(a + i) + __ldg(b + i);
+}
+
+extern "C" int tmx_add_f32(tmx_handle_t h, const float* a, const float* b, float* out, int64_t n, tmx_stream_t s) {
+  TMX_REQUIRE(h && a && b && out && n > 0, TMX_ERR_ARG, "tmx_add_f32: bad argument");
+  long long blocks = (n + 255) / 256;
+  if (blocks > (long long)h->sm_count * 8) blocks = (long long)h->sm_count * 8;
+  add_kernel<<<(int)blocks, 256, 0, (cudaStream_t)s>>>(a, b, out, n);
+  TMX_LAUNCHED(h, "add_kernel");
+  return TMX_OK;
+}
+
 int tmx_conv2d_dgrad_tc(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, const uint16_t* dz_hi,
                         const uint16_t* dz_lo, const uint16_t* wt_hi, const uint16_t* wt_lo, float* g_f32,
                         cudaStream_t st);
