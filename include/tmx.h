@@ -267,9 +267,32 @@ int tmx_loss_l1_grad(tmx_handle_t h, const float* a, const float* b, float* grad
 int tmx_latent_gather_bwd(tmx_handle_t h, const float* dcanvas, float* dsrc, const int32_t* idx_h, const int32_t* idx_w,
                           int N, int C, int sh, int sw, int H, int W, uint64_t pin_rows, uint64_t pin_cols, int reverse,
                           tmx_stream_t s);
-/* out[row] (+)= scale * sum_i in[row][i] : adjoint of tiling a [N][C][1][1] code over a canvas (loss.py:176), loss means. */
-int tmx_row_sum(tmx_handle_t h, const float* in, float* out, int rows, int len, float scale, int accumulate,
+/* out[row] (+)= scale * sum_i f(in[row][i]), f = identity or square: adjoint of tiling a [N][C][1][1] code over a
+ * canvas (loss.py:176), loss means, per-sample squared gradient norms (loss.py:334). */
+int tmx_row_sum(tmx_handle_t h, const float* in, float* out, int rows, int len, float scale, int accumulate, int square,
                 tmx_stream_t s);
+/* out = a * in + b over n fp32 elements. */
+int tmx_axpb(tmx_handle_t h, const float* in, float* out, int64_t n, float a, float b, tmx_stream_t s);
+
+/* ---- WGAN-GP double backward (loss.py:332-336).  For the piecewise-linear layers the second-order
+ * term needs no new conv kernel: d/dtheta [ v . grad_x D ] = weight gradients with the TANGENT activations
+ * (forward of the bias-free, mask-frozen network on v) against the adjoints of the first backward.  Only the
+ * minibatch-stddev layer has curvature:
+ * tmx_mbstd_tangent:  ydot = J_mbstd(x) xdot   ([xdot, sdot broadcast, 0...], NHWC [N][H][W][C_total]; sdot: [N/G])
+ * tmx_mbstd_curvature: q = d/dx ( lam[m] * sdot[m] )  with xdot fixed (NHWC [N][H][W][C]; lam: [N/G])
+ * tmx_dense_wgrad:    dw[k][o] += wscale * sum_n x[n][k] dz[n][o],  db[o] += sum_n dz[n][o],  dz = dy * lrelu'(y)
+ * tmx_scale_rows:     out[n][:] = scale[n] * in[n][:]
+ * tmx_gp_coefficients: from squared gradient norms sq[n]: penalty[n] = lambda (sqrt(sq)-target)^2 / target^2 and
+ *                     coef[n] = d mean_n(penalty) / d||g_n|| / ||g_n|| (the tangent seed is coef[n] * g_n). */
+int tmx_mbstd_tangent(tmx_handle_t h, const float* x, const float* xdot, float* ydot, float* sdot, int N, int H, int W,
+                      int C, int C_total, int group_size, tmx_stream_t s);
+int tmx_mbstd_curvature(tmx_handle_t h, const float* x, const float* xdot, const float* lam, float* q, int N, int H, int W,
+                        int C, int group_size, tmx_stream_t s);
+int tmx_dense_wgrad(tmx_handle_t h, const float* x, const float* dy, const float* y, float* dw, float* db, int N, int K,
+                    int Cout, float wscale, int lrelu, float alpha, tmx_stream_t s);
+int tmx_scale_rows(tmx_handle_t h, const float* in, const float* scale, float* out, int rows, int64_t len, tmx_stream_t s);
+int tmx_gp_coefficients(tmx_handle_t h, const float* sq_norms, float* penalty, float* coef, int N, float lambda,
+                        float target, tmx_stream_t s);
 
 /* out = a + b over n fp32 elements (two gradient contributions meeting at one tensor). */
 int tmx_add_f32(tmx_handle_t h, const float* a, const float* b, float* out, int64_t n, tmx_stream_t s);

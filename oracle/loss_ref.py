@@ -73,3 +73,22 @@ def EG_wgan(P, reals, idx, crop_interp, crop_blend, mixing_factors, scale_h=3, s
                             ).mean(dim=(1, 2, 3)) * blend_interp_G_weight
         loss = loss + terms['blend_G']
     return loss, terms
+
+
+def D_wgangp(P_D, fakes, reals, mixing_factors, wgan_lambda=10.0, wgan_epsilon=0.001, wgan_target=1.0, cfg=None):
+    """The critic loss of loss.py:303-346 (D_rec_wgangp; D_interp_/D_blend_wgangp, :351-521, differ only in how
+    the fake images are produced).  `fakes` are constants here (D's optimizer only sees D's variables,
+    run.py:322-324).  Returns the per-sample loss [N] and the named terms; the gradient penalty differentiates
+    through the gradient (create_graph), like tf.gradients of loss.py:333 inside tfutil.py:299."""
+    cfg = cfg or R.CONFIG
+    s_f = R.D_patch(fakes, P_D, **cfg['D_patch'])
+    s_r = R.D_patch(reals, P_D, **cfg['D_patch'])
+    terms = {'D_loss': (s_f - s_r).mean(dim=(1, 2, 3))}                                    # loss.py:323
+    mixed = (reals + (fakes - reals) * mixing_factors).detach().requires_grad_(True)      # loss.py:329-330
+    s_m = R.D_patch(mixed, P_D, **cfg['D_patch'])
+    (g,) = torch.autograd.grad(s_m.sum(), mixed, create_graph=True)                       # loss.py:332-333
+    norms = torch.sqrt((g * g).sum(dim=(1, 2, 3)))
+    terms['gradient_penalty'] = (norms - wgan_target) ** 2 * (wgan_lambda / wgan_target ** 2)   # loss.py:335-336
+    terms['epsilon_penalty'] = (s_r * s_r).mean(dim=(1, 2, 3)) * wgan_epsilon              # loss.py:342
+    loss = terms['D_loss'] + terms['gradient_penalty'] + terms['epsilon_penalty']
+    return loss, terms

@@ -83,3 +83,44 @@ def test_eg_loss_and_gradients_vs_autograd(alpha, sh, sw, monkeypatch):
                 worst = (k + '/' + name, err)
             assert err <= gtol, (k, name, err)
     print('alpha', alpha, 'worst variable gradient rel-L2', worst)
+
+
+@pytest.mark.parametrize('alpha', [1.0, 0.2])
+def test_critic_wgangp_double_backward_vs_autograd(alpha, monkeypatch):
+    """D_*_wgangp (loss.py:303-521): every variable gradient of the critic, including the gradient penalty's
+    second-order terms (tangent x adjoint weight gradients + minibatch-stddev curvature), vs create_graph autograd."""
+    from texturemixer_b200 import loss as dev_loss
+    from texturemixer_b200 import runtime
+    from texturemixer_b200.network import Network
+    monkeypatch.setattr(runtime, 'LRELU_ALPHA', alpha)
+    monkeypatch.setattr(R, 'leaky_relu', lambda x, a=alpha: torch.maximum(x * a, x) if a != 1.0 else x)
+    rng = np.random.RandomState(5)
+    n = 8
+    params = R.init_params('D_patch', rng, **R.CONFIG['D_patch'])
+    reals = rng.uniform(-1, 1, (n, 3, 128, 128)).astype(np.float32)
+    fakes = np.tanh(rng.randn(n, 3, 128, 128)).astype(np.float32)
+    mix = rng.uniform(0, 1, (n, 1, 1, 1)).astype(np.float32)
+    P = R.to_torch(params, dtype=torch.float64, requires_grad=True)
+    loss, terms = L.D_wgangp(P, torch.from_numpy(fakes).double(), torch.from_numpy(reals).double(),
+                             torch.from_numpy(mix).double())
+    loss.mean().backward()
+    D = Network('D_rec', func='networks.D_patch', seed=0, num_channels=3, resolution=128, **R.CONFIG['D_patch'])
+    D.set_vars(params)
+    fg = torch.zeros_like(D.flat)
+    rep = dev_loss.D_wgangp(D, torch.from_numpy(fakes).cuda(), torch.from_numpy(reals).cuda(),
+                            torch.from_numpy(mix).cuda(), fg)
+    torch.cuda.synchronize()
+    ltol = 2e-3 if alpha == 1.0 else 2e-2
+    for k in ('D_loss', 'gradient_penalty', 'epsilon_penalty'):
+        want, got = float(terms[k].mean()), float(rep[k].reshape(-1)[0])
+        assert abs(got - want) <= ltol * max(1e-3, abs(want)), (k, got, want)
+    gtol = 3e-3 if alpha == 1.0 else 5e-2
+    worst = ('', 0.0)
+    for name, t in P.items():
+        if name == 'lod' or t.grad is None or float(t.grad.abs().max()) == 0:
+            continue
+        err = _rel_l2(D.grad_view(fg, name).cpu().numpy(), t.grad.numpy())
+        if err > worst[1]:
+            worst = (name, err)
+        assert err <= gtol, (name, err)
+    print('alpha', alpha, 'critic worst variable gradient rel-L2', worst)

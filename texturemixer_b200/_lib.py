@@ -86,7 +86,13 @@ _SIGNATURES = {
     'tmx_mbstd_bwd': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'tmx_loss_l1_grad': (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _F, _P]),
     'tmx_latent_gather_bwd': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, C.c_uint64, C.c_uint64, _I, _P]),
-    'tmx_row_sum': (C.c_int, [_P, _P, _P, _I, _I, _F, _I, _P]),
+    'tmx_row_sum': (C.c_int, [_P, _P, _P, _I, _I, _F, _I, _I, _P]),
+    'tmx_axpb': (C.c_int, [_P, _P, _P, C.c_int64, _F, _F, _P]),
+    'tmx_mbstd_tangent': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'tmx_mbstd_curvature': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    'tmx_dense_wgrad': (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _F, _P]),
+    'tmx_scale_rows': (C.c_int, [_P, _P, _P, _P, _I, C.c_int64, _P]),
+    'tmx_gp_coefficients': (C.c_int, [_P, _P, _P, _P, _I, _F, _F, _P]),
     'tmx_add_f32': (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
     'tmx_grad_prepare': (C.c_int, [_P, C.POINTER(GradDesc), C.POINTER(GradIO), _P]),
     'tmx_nonfinite_check': (C.c_int, [_P, _P, C.c_int64, _P, _P]),

@@ -66,11 +66,31 @@ def _combine(rt, act, contribs, want_planes, want_f32, mask_y=None, dbias=None, 
                            want_f32=want_f32, dbias=dbias, phase_pack=phase_pack)
 
 
-def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads=True):
+def conv_wgrad_into(rt, net, rec, x_planes, dz, dw):
+    """Weight gradient of a (non-upsampling) conv record into `dw` (HWIO view of the flat gradient).  A conv whose
+    input was channel-padded (513 -> 576 after minibatch stddev) goes through a padded scratch gradient."""
+    x = rec['x']
+    if x.c == rec['cin']:
+        rt.conv_wgrad(x_planes, dz, x.n, x.h, x.w, x.c, rec['cout'], rec['k'], rec['wscale'], dw)
+        return
+    taps = rec['k'] * rec['k']
+    tmp = torch.zeros(taps, x.c, rec['cout'], dtype=torch.float32, device=rt.device)
+    rt.conv_wgrad(x_planes, dz, x.n, x.h, x.w, x.c, rec['cout'], rec['k'], rec['wscale'], tmp)
+    dwv = dw.view(taps, rec['cin'], rec['cout'])
+    for t in range(taps):      # rows of the real channels are a contiguous prefix of each tap
+        a, b = dwv[t], tmp[t, :rec['cin']]
+        _lib.check(rt.lib.tmx_add_f32(rt.handle, _ptr(a), _ptr(b), _ptr(a), a.numel(), rt.stream()), 'tmx_add_f32')
+
+
+def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads=True, adjoints=None, seeds=None):
     """Differentiate one recorded evaluation of `net`.
     out_grads : list matching the network outputs (NCHW fp32 device tensors, or None for unused outputs)
     flat_grad : fp32 buffer like net.flat; variable gradients are accumulated into it
     param_grads=False: only propagate to the inputs (a fixed critic inside the E/G loss: flat_grad may be None)
+    adjoints : optional dict filled with the adjoint that met each parametrised layer, keyed by tape position
+               (conv: dz planes on the zero-ringed grid; fromrgb: masked dz fp32; dense: (dy, y)) - the WGAN-GP
+               double backward pairs them with tangent activations (loss.gradient_penalty)
+    seeds    : optional [(activation, fp32 NHWC gradient)] injected at intermediate activations
     Returns the list of gradients w.r.t. the network inputs (NCHW fp32; None for image inputs of the
     encoders unless the first layer's data gradient is defined, i.e. for D_patch/FromRGB: NCHW image gradient)."""
     rt = net.rt
@@ -78,6 +98,8 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
     outs = tape[-1]['tensors']
     assert len(out_grads) == len(outs)
     grads = _Grads()
+    for act, g in (seeds or []):
+        grads.add(act, ('f32', g))
     by_tensor = {id(t): g for t, g in zip(outs, out_grads) if g is not None}
     input_grads = {}
 
@@ -93,7 +115,8 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
 
     tgrads = {}        # gradients w.r.t. plain tensors (dense head), keyed by tensor identity
 
-    for rec in reversed(tape[:-1]):
+    for pos in range(len(tape) - 2, -1, -1):
+        rec = tape[pos]
         kind = rec['kind']
         if kind == 'slice':
             g = by_tensor.get(id(rec['out']))
@@ -126,13 +149,19 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
                 g = tgrads.pop(id(rec['y']), None)
             if g is None:
                 continue
-            if param_grads:
-                raise NotImplementedError('weight gradient of the dense head is not built yet (D-phase, round 2)')
             y, xin = rec['y'], rec['x']
             n, cout = y.shape
             kdim = xin.numel() // n
-            dx = rt.empty(*xin.shape)
+            g = g.contiguous()
+            if adjoints is not None:
+                adjoints[pos] = (g, y)
             wv = net.vars[rec['w']]
+            if param_grads:
+                _lib.check(rt.lib.tmx_dense_wgrad(rt.handle, _ptr(xin), _ptr(g), _ptr(y), _ptr(gview(rec['w'])),
+                                                  _ptr(gview(rec['b'])), n, kdim, cout, float(rec['wscale']),
+                                                  int(rec['act']), runtime.LRELU_ALPHA, rt.stream()),
+                           'tmx_dense_wgrad')
+            dx = rt.empty(*xin.shape)
             _lib.check(rt.lib.tmx_dense_bwd_input(rt.handle, _ptr(g.contiguous()), _ptr(y), _ptr(wv.value),
                                                   float(rec['wscale']), _ptr(dx), n, kdim, cout, int(rec['act']),
                                                   runtime.LRELU_ALPHA, rt.stream()), 'tmx_dense_bwd_input')
@@ -154,6 +183,8 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
             ds = rt.empty(x.n // g)
             _lib.check(rt.lib.tmx_mbstd_bwd(rt.handle, _ptr(rt.split_unpack(x).f32), _ptr(dy), _ptr(dx), _ptr(ds), x.n,
                                             x.h, x.w, x.c, y.c, rec['group'], rt.stream()), 'tmx_mbstd_bwd')
+            if adjoints is not None:
+                adjoints[pos] = ds          # adjoint of the group statistic
             grads.add(x, ('f32', dx))
         elif kind == 'view':
             # y holds the first `pixels` pixels of x (or vice versa) in another [n,h,w] arrangement
@@ -183,9 +214,9 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
                                   dbias=gview(rec['b']) if param_grads else None, phase_pack=up2)
             if has_res:
                 grads.add(rec['residual'], ('f32', dz_f32))         # y = conv(x) + residual (networks.py:437)
+            if adjoints is not None:
+                adjoints[pos] = dz
             w = net.vars[rec['w']]
-            if param_grads and x.c != rec['cin']:
-                raise NotImplementedError('weight gradient of a channel-padded conv (minibatch stddev) is not built yet')
             fwd = net.prepared_weights(w, rec['wscale'], k, rec['cin'], cout, up2_phase=up2, cin_pad=x.c)
             if up2:
                 # sub-pixel form: low-res geometry, 4*Cout phase channels
@@ -200,7 +231,7 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
                 grads.add(x, ('grid', g, 1))
             else:
                 if param_grads:
-                    rt.conv_wgrad((x.hi, x.lo), dz, x.n, x.h, x.w, cin_g, cout, k, rec['wscale'], gview(rec['w']))
+                    conv_wgrad_into(rt, net, rec, (x.hi, x.lo), dz, gview(rec['w']))
                 wt = net.cached(('wt', rec['w'], False), lambda: rt.transpose_weights(fwd, cout, k * k, cin_g))
                 g = rt.conv_dgrad(dz, x.n, x.h, x.w, cin_g, cout, k, wt)
                 grads.add(x, ('grid', g, 0 if k == 3 else 2))
@@ -211,6 +242,8 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
                 continue
             _, dz = _combine(rt, y, contribs, want_planes=False, want_f32=True, mask_y=y.f32,
                              dbias=gview(rec['b']) if param_grads else None)
+            if adjoints is not None:
+                adjoints[pos] = dz
             img = rec['img']
             n, cimg, h, w_ = img.shape
             dimg = rt.empty(n, cimg, h, w_) if want_input_grads else None

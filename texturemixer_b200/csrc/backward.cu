@@ -594,10 +594,13 @@ extern "C" int tmx_latent_gather_bwd(tmx_handle_t h, const float* dcanvas, float
 // tf.tile of a [N][C][1][1] code over the canvas (loss.py:176): adjoint = sum over the canvas, one block per (n, c).
 // out[row] (+)= scale * sum_i in[row][i]
 __global__ void __launch_bounds__(256) row_sum_kernel(const float* __restrict__ in, float* __restrict__ out, int len,
-                                                      float scale, int accumulate) {
+                                                      float scale, int accumulate, int square) {
   const long long row = blockIdx.x;
   float acc = 0.f;
-  for (int i = threadIdx.x; i < len; i += blockDim.x) acc += __ldg(in + row * len + i);
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const float v = __ldg(in + row * len + i);
+    acc += square ? v * v : v;
+  }
   __shared__ float red[256];
   red[threadIdx.x] = acc;
   __syncthreads();
@@ -609,10 +612,201 @@ __global__ void __launch_bounds__(256) row_sum_kernel(const float* __restrict__ 
 }
 
 extern "C" int tmx_row_sum(tmx_handle_t h, const float* in, float* out, int rows, int len, float scale, int accumulate,
-                           tmx_stream_t s) {
+                           int square, tmx_stream_t s) {
   TMX_REQUIRE(h && in && out && rows > 0 && len > 0, TMX_ERR_ARG, "tmx_row_sum: bad argument");
-  row_sum_kernel<<<rows, 256, 0, (cudaStream_t)s>>>(in, out, len, scale, accumulate);
+  row_sum_kernel<<<rows, 256, 0, (cudaStream_t)s>>>(in, out, len, scale, accumulate, square);
   TMX_LAUNCHED(h, "row_sum_kernel");
+  return TMX_OK;
+}
+
+// ---------------------------------------------------------------- dense weight gradient, mbstd tangent / curvature
+// dw[k][o] += wscale * sum_n x[n][k] * dz[n][o],  db[o] += sum_n dz[n][o],  dz = dy * lrelu'(y)
+__global__ void __launch_bounds__(256) dense_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                          const float* __restrict__ y, float* __restrict__ dw,
+                                                          float* __restrict__ db, int N, int K, int Cout, float wscale,
+                                                          int lrelu, float alpha) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)K * Cout) return;
+  const int o = (int)(t % Cout);
+  const int k = (int)(t / Cout);
+  float acc = 0.f, bacc = 0.f;
+  for (int n = 0; n < N; ++n) {
+    float g = __ldg(dy + (long long)n * Cout + o);
+    if (lrelu) g *= (__ldg(y + (long long)n * Cout + o) > 0.f) ? 1.f : alpha;
+    acc = fmaf(__ldg(x + (long long)n * K + k), g, acc);
+    bacc += g;
+  }
+  dw[t] += acc * wscale;
+  if (db != nullptr && k == 0) db[o] += bacc;
+}
+
+extern "C" int tmx_dense_wgrad(tmx_handle_t h, const float* x, const float* dy, const float* y, float* dw, float* db, int N,
+                               int K, int Cout, float wscale, int lrelu, float alpha, tmx_stream_t s) {
+  TMX_REQUIRE(h && x && dy && dw && (!lrelu || y), TMX_ERR_ARG, "tmx_dense_wgrad: NULL argument");
+  TMX_REQUIRE(N > 0 && K > 0 && Cout > 0, TMX_ERR_SHAPE, "tmx_dense_wgrad: bad shape");
+  dense_wgrad_kernel<<<tmx_ceil_div((long long)K * Cout, 256), 256, 0, (cudaStream_t)s>>>(x, dy, y, dw, db, N, K, Cout,
+                                                                                         wscale, lrelu, alpha);
+  TMX_LAUNCHED(h, "dense_wgrad_kernel");
+  return TMX_OK;
+}
+
+// Forward-mode tangent and curvature of minibatch_stddev_layer (networks.py:177-189), for the WGAN-GP double
+// backward (loss.py:332-336).  Per group m and element e over the G samples of the group:
+//   sigma = sqrt(var_g(x) + 1e-8),  s[m] = mean_e sigma
+//   d sigma / dx_g = (x_g - mu) / (G sigma)
+//   tangent:   sdot[m] = (1/E) sum_e sum_g (x_g - mu) xdot_g / (G sigma)
+//   curvature: (H xdot)_g = (xdot_g - mean_g xdot) / (G sigma) - (x_g - mu) * sum_h (x_h - mu) xdot_h / (G^2 sigma^3)
+//   q[g][m][e] = lam[m] / E * (H xdot)_g      (gradient w.r.t. the PRIMAL x of  lam[m] * sdot[m])
+// mode 0: ydot = [xdot, sdot broadcast, 0...] (NHWC [N][H][W][C_total]);  mode 1: q (NHWC [N][H][W][C]).
+__global__ void __launch_bounds__(256) mbstd_sdot_kernel(const float* __restrict__ x, const float* __restrict__ xdot,
+                                                         float* __restrict__ sdot, int G, int M, long long per_sample) {
+  const int m = blockIdx.x;
+  float acc = 0.f;
+  for (long long e = threadIdx.x; e < per_sample; e += blockDim.x) {
+    float mean = 0.f;
+    for (int g = 0; g < G; ++g) mean += __ldg(x + (long long)(g * M + m) * per_sample + e);
+    mean /= (float)G;
+    float var = 0.f, dot = 0.f;
+    for (int g = 0; g < G; ++g) {
+      const float d = __ldg(x + (long long)(g * M + m) * per_sample + e) - mean;
+      var += d * d;
+      dot += d * __ldg(xdot + (long long)(g * M + m) * per_sample + e);
+    }
+    acc += dot / ((float)G * sqrtf(var / (float)G + 1e-8f));
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sdot[m] = red[0] / (float)per_sample;
+}
+
+__global__ void __launch_bounds__(256) mbstd_hess_kernel(const float* __restrict__ x, const float* __restrict__ xdot,
+                                                         const float* __restrict__ lam, float* __restrict__ q, int G,
+                                                         int M, long long per_sample) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)M * per_sample) return;
+  const int m = (int)(t / per_sample);
+  const long long e = t % per_sample;
+  float mean = 0.f, dmean = 0.f;
+  for (int g = 0; g < G; ++g) {
+    mean += __ldg(x + (long long)(g * M + m) * per_sample + e);
+    dmean += __ldg(xdot + (long long)(g * M + m) * per_sample + e);
+  }
+  mean /= (float)G;
+  dmean /= (float)G;
+  float var = 0.f, dot = 0.f;
+  for (int g = 0; g < G; ++g) {
+    const float d = __ldg(x + (long long)(g * M + m) * per_sample + e) - mean;
+    var += d * d;
+    dot += d * __ldg(xdot + (long long)(g * M + m) * per_sample + e);
+  }
+  const float sigma = sqrtf(var / (float)G + 1e-8f);
+  const float c1 = 1.f / ((float)G * sigma);
+  const float c2 = dot / ((float)G * (float)G * sigma * sigma * sigma);
+  const float scale = __ldg(lam + m) / (float)per_sample;
+  for (int g = 0; g < G; ++g) {
+    const long long i = (long long)(g * M + m) * per_sample + e;
+    q[i] = scale * ((__ldg(xdot + i) - dmean) * c1 - (__ldg(x + i) - mean) * c2);
+  }
+}
+
+__global__ void __launch_bounds__(256) mbstd_tangent_concat_kernel(const float* __restrict__ x,
+                                                                   const float* __restrict__ stat,
+                                                                   float* __restrict__ y, long long total, int C,
+                                                                   int C_total, int M, long long pix_per_sample) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % C_total);
+  const long long pix = t / C_total;
+  float v = 0.f;
+  if (c < C) v = __ldg(x + pix * C + c);
+  else if (c == C) v = __ldg(stat + (int)((pix / pix_per_sample) % M));
+  y[t] = v;
+}
+
+extern "C" int tmx_mbstd_tangent(tmx_handle_t h, const float* x, const float* xdot, float* ydot, float* sdot, int N, int H,
+                                 int W, int C, int C_total, int group_size, tmx_stream_t s) {
+  TMX_REQUIRE(h && x && xdot && ydot && sdot, TMX_ERR_ARG, "tmx_mbstd_tangent: NULL argument");
+  const int G = group_size < N ? group_size : N;
+  TMX_REQUIRE(N > 0 && N % G == 0 && C_total > C, TMX_ERR_SHAPE, "tmx_mbstd_tangent: bad shape");
+  const int M = N / G;
+  const long long per_sample = (long long)H * W * C;
+  mbstd_sdot_kernel<<<M, 256, 0, (cudaStream_t)s>>>(x, xdot, sdot, G, M, per_sample);
+  TMX_LAUNCHED(h, "mbstd_sdot_kernel");
+  const long long total = (long long)N * H * W * C_total;
+  mbstd_tangent_concat_kernel<<<tmx_ceil_div(total, 256), 256, 0, (cudaStream_t)s>>>(xdot, sdot, ydot, total, C, C_total,
+                                                                                     M, (long long)H * W);
+  TMX_LAUNCHED(h, "mbstd_tangent_concat_kernel");
+  return TMX_OK;
+}
+
+extern "C" int tmx_mbstd_curvature(tmx_handle_t h, const float* x, const float* xdot, const float* lam, float* q, int N,
+                                   int H, int W, int C, int group_size, tmx_stream_t s) {
+  TMX_REQUIRE(h && x && xdot && lam && q, TMX_ERR_ARG, "tmx_mbstd_curvature: NULL argument");
+  const int G = group_size < N ? group_size : N;
+  TMX_REQUIRE(N > 0 && N % G == 0, TMX_ERR_SHAPE, "tmx_mbstd_curvature: bad shape");
+  const int M = N / G;
+  const long long per_sample = (long long)H * W * C;
+  mbstd_hess_kernel<<<tmx_ceil_div((long long)M * per_sample, 256), 256, 0, (cudaStream_t)s>>>(x, xdot, lam, q, G, M,
+                                                                                              per_sample);
+  TMX_LAUNCHED(h, "mbstd_hess_kernel");
+  return TMX_OK;
+}
+
+// out[n][i] = scale[n] * in[n][i]   (per-sample coefficient of the gradient-penalty tangent seed)
+__global__ void __launch_bounds__(256) scale_rows_kernel(const float* __restrict__ in, const float* __restrict__ scale,
+                                                         float* __restrict__ out, long long len, long long total) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+    out[i] = __ldg(in + i) * __ldg(scale + i / len);
+}
+
+// WGAN-GP per-sample terms from the squared gradient norms (loss.py:334-336): pen[n] = lambda (||g_n|| - target)^2 / target^2,
+// coef[n] = d mean(pen) / d g_n direction scale = (1/N) 2 lambda (||g_n|| - target) / (target^2 ||g_n||)
+__global__ void gp_coef_kernel(const float* __restrict__ sq, float* __restrict__ pen, float* __restrict__ coef, int N,
+                               float lambda, float target) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float norm = sqrtf(__ldg(sq + n));
+  const float d = norm - target;
+  pen[n] = lambda * d * d / (target * target);
+  coef[n] = (2.f * lambda * d / (target * target * norm)) / (float)N;
+}
+
+extern "C" int tmx_scale_rows(tmx_handle_t h, const float* in, const float* scale, float* out, int rows, int64_t len,
+                              tmx_stream_t s) {
+  TMX_REQUIRE(h && in && scale && out && rows > 0 && len > 0, TMX_ERR_ARG, "tmx_scale_rows: bad argument");
+  const long long total = (long long)rows * len;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)h->sm_count * 8) blocks = (long long)h->sm_count * 8;
+  scale_rows_kernel<<<(int)blocks, 256, 0, (cudaStream_t)s>>>(in, scale, out, len, total);
+  TMX_LAUNCHED(h, "scale_rows_kernel");
+  return TMX_OK;
+}
+
+extern "C" int tmx_gp_coefficients(tmx_handle_t h, const float* sq_norms, float* penalty, float* coef, int N, float lambda,
+                                   float target, tmx_stream_t s) {
+  TMX_REQUIRE(h && sq_norms && penalty && coef && N > 0, TMX_ERR_ARG, "tmx_gp_coefficients: bad argument");
+  gp_coef_kernel<<<tmx_ceil_div(N, 128), 128, 0, (cudaStream_t)s>>>(sq_norms, penalty, coef, N, lambda, target);
+  TMX_LAUNCHED(h, "gp_coef_kernel");
+  return TMX_OK;
+}
+
+// out = a * in + b  (seeds of the critic losses: d loss / d score)
+__global__ void __launch_bounds__(256) axpb_kernel(const float* __restrict__ in, float* __restrict__ out, long long n,
+                                                   float a, float b) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fmaf(__ldg(in + i), a, b);
+}
+
+extern "C" int tmx_axpb(tmx_handle_t h, const float* in, float* out, int64_t n, float a, float b, tmx_stream_t s) {
+  TMX_REQUIRE(h && in && out && n > 0, TMX_ERR_ARG, "tmx_axpb: bad argument");
+  axpb_kernel<<<tmx_ceil_div(n, 256), 256, 0, (cudaStream_t)s>>>(in, out, n, a, b);
+  TMX_LAUNCHED(h, "axpb_kernel");
   return TMX_OK;
 }
 

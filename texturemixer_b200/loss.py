@@ -17,7 +17,9 @@ import numpy as np
 import torch
 
 from . import _lib, interp
-from .backward import backward
+from . import runtime
+from .backward import backward, conv_wgrad_into
+from .runtime import Act
 from .runtime import Runtime
 
 
@@ -30,11 +32,11 @@ def _tile_code(rt, z, H, W):
     return rt.latent_blend([z.contiguous()], H, W, _lib.BLEND_COPY)
 
 
-def _row_sum(rt, x, rows, length, out=None, scale=1.0, accumulate=False):
+def _row_sum(rt, x, rows, length, out=None, scale=1.0, accumulate=False, square=False):
     if out is None:
         out = rt.empty(rows)
     _lib.check(rt.lib.tmx_row_sum(rt.handle, _ptr(x), _ptr(out), rows, length, float(scale), int(accumulate),
-                                  rt.stream()), 'tmx_row_sum')
+                                  int(square), rt.stream()), 'tmx_row_sum')
     return out
 
 
@@ -160,3 +162,138 @@ def _add(rt, a, b):
     _lib.check(rt.lib.tmx_add_f32(rt.handle, _ptr(a.contiguous()), _ptr(b.contiguous()), _ptr(out), a.numel(),
                                   rt.stream()), 'tmx_add_f32')
     return out
+
+
+# ====================================================================== critic phase (WGAN-GP)
+def _mask(rt, t, y, n, h, w, c):
+    """t * lrelu'(y): the activation of the mask-frozen (linearised) network."""
+    _, out = rt.grad_prepare(t, n, h, w, c, src_kind=1, y_f32=y, want_planes=False, want_f32=True)
+    return out
+
+
+def tangent_forward(D, tape, v):
+    """Forward of the linearised critic (no biases, leaky-ReLU branches frozen at the recorded evaluation) on the
+    tangent image v [N,3,R,R]: J_D(x) v.  Returns {tape position: tangent INPUT of that parametrised layer} and the
+    (primal, tangent) pair at the minibatch-stddev layer."""
+    rt = D.rt
+    tang, tin, mb = {}, {}, None
+    for pos, rec in enumerate(tape[:-1]):
+        kind = rec['kind']
+        if kind == 'fromrgb':
+            y = rec['y']
+            t = rt.fromrgb(v, D.vars[rec['w']].value, None, rec['wscale'], rec['cout'], lrelu=False)
+            t.f32 = _mask(rt, t.f32, y.f32, y.n, y.h, y.w, y.c)
+            tin[pos] = v
+            tang[id(y)] = t
+        elif kind == 'conv':
+            xin, y = tang[id(rec['x'])], rec['y']
+            wv = D.vars[rec['w']]
+            prepared = D.prepared_weights(wv, rec['wscale'], rec['k'], rec['cin'], rec['cout'], cin_pad=xin.c)
+            out = rt.conv2d(xin, wv.value, None, rec['wscale'], rec['k'], rec['cout'], lrelu=False, want_f32=True,
+                            want_split=False, algo=_lib.ALGO_TC, prepared=prepared)
+            if rec['act']:
+                out.f32 = _mask(rt, out.f32, rt.split_unpack(y).f32, y.n, y.h, y.w, y.c)
+            tin[pos] = xin                      # carries the REFLECT planes the conv just packed
+            tang[id(y)] = out
+        elif kind == 'pool':
+            tang[id(rec['y'])] = rt.avgpool2(tang[id(rec['x'])])
+        elif kind == 'mbstd':
+            x, y, xd = rec['x'], rec['y'], rt.split_unpack(tang[id(rec['x'])])
+            g = min(rec['group'], x.n)
+            yd = Act(y.n, y.h, y.w, y.c, f32=rt.empty(y.n, y.h, y.w, y.c))
+            sdot = rt.empty(x.n // g)
+            _lib.check(rt.lib.tmx_mbstd_tangent(rt.handle, _ptr(rt.split_unpack(x).f32), _ptr(xd.f32), _ptr(yd.f32),
+                                                _ptr(sdot), x.n, x.h, x.w, x.c, y.c, rec['group'], rt.stream()),
+                       'tmx_mbstd_tangent')
+            tang[id(y)] = yd
+            mb = (pos, x, xd)
+        elif kind == 'flatten':
+            a = rt.split_unpack(tang[id(rec['x'])])
+            tang[id(rec['y'])] = rt.nhwc_to_nchw(a.f32)
+        elif kind == 'dense':
+            xin, y = tang[id(rec['x'])], rec['y']
+            n = y.shape[0]
+            out = rt.dense(xin.view(n, -1), D.vars[rec['w']].value, None, rec['wscale'], lrelu=False)
+            if rec['act']:
+                out = _mask(rt, out, y, n, 1, 1, y.shape[1])
+            tin[pos] = xin
+            tang[id(y)] = out
+        else:
+            raise NotImplementedError('tangent of tape record %r' % kind)
+    return tin, mb
+
+
+def gradient_penalty(D, mixed, flat_grad, wgan_lambda=10.0, wgan_target=1.0):
+    """mean_n lambda (||grad_x D(x_n)|| - target)^2 / target^2 (loss.py:327-337) and its gradient w.r.t. D's
+    variables, accumulated into flat_grad.  Double backward without autograd:
+      1. forward at `mixed` (tape) and first backward of sum(scores) w.r.t. the images, keeping every layer's adjoint
+      2. per-sample coefficient c_n = d mean(penalty) / d||g_n|| / ||g_n||; tangent seed v_n = c_n g_n
+      3. tangent forward of the mask-frozen network on v
+      4. weight gradients = adjoint (step 1) x tangent input (step 3) for every conv / dense / FromRGB layer
+      5. curvature of the minibatch-stddev statistic -> an extra fp32 gradient at its input, pushed through an
+         ordinary backward of the layers below it."""
+    rt = D.rt
+    n = mixed.shape[0]
+    tape, adj = [], {}
+    s = D.get_output_for(mixed, tape=tape)
+    (g,) = backward(D, tape, [torch.ones_like(s)], None, param_grads=False, adjoints=adj)
+    per = g[0].numel()
+    sq = _row_sum(rt, g, n, per, square=True)
+    pen, coef = rt.empty(n), rt.empty(n)
+    _lib.check(rt.lib.tmx_gp_coefficients(rt.handle, _ptr(sq), _ptr(pen), _ptr(coef), n, float(wgan_lambda),
+                                          float(wgan_target), rt.stream()), 'tmx_gp_coefficients')
+    v = rt.empty(*g.shape)
+    _lib.check(rt.lib.tmx_scale_rows(rt.handle, _ptr(g), _ptr(coef), _ptr(v), n, per, rt.stream()), 'tmx_scale_rows')
+    tin, mb = tangent_forward(D, tape, v)
+    for pos, rec in enumerate(tape[:-1]):
+        if pos not in adj or pos not in tin:
+            continue
+        kind = rec['kind']
+        if kind == 'conv':
+            x = tin[pos]
+            conv_wgrad_into(rt, D, dict(rec, x=x), (x.hi, x.lo), adj[pos], D.grad_view(flat_grad, rec['w']))
+        elif kind == 'fromrgb':
+            img = tin[pos]
+            nn, cimg, h, w = img.shape
+            _lib.check(rt.lib.tmx_fromrgb_bwd(rt.handle, _ptr(img), _ptr(adj[pos]), _ptr(D.vars[rec['w']].value),
+                                              float(rec['wscale']), _ptr(D.grad_view(flat_grad, rec['w'])), None, nn,
+                                              cimg, h, w, rec['cout'], rt.stream()), 'tmx_fromrgb_bwd')
+        elif kind == 'dense':
+            dy, y = adj[pos]
+            xin = tin[pos]
+            _lib.check(rt.lib.tmx_dense_wgrad(rt.handle, _ptr(xin), _ptr(dy), _ptr(y),
+                                              _ptr(D.grad_view(flat_grad, rec['w'])), None, y.shape[0],
+                                              xin.numel() // y.shape[0], y.shape[1], float(rec['wscale']),
+                                              int(rec['act']), runtime.LRELU_ALPHA, rt.stream()), 'tmx_dense_wgrad')
+    if mb is not None:
+        pos, x, xd = mb
+        q = rt.empty(x.n, x.h, x.w, x.c)
+        _lib.check(rt.lib.tmx_mbstd_curvature(rt.handle, _ptr(x.f32), _ptr(xd.f32), _ptr(adj[pos]), _ptr(q), x.n, x.h,
+                                              x.w, x.c, tape[pos]['group'], rt.stream()), 'tmx_mbstd_curvature')
+        backward(D, tape, [None], flat_grad, want_input_grads=False, param_grads=True, seeds=[(x, q)])
+    return _row_sum(rt, pen, 1, n, scale=1.0 / n)
+
+
+def D_wgangp(D, fakes, reals, mixing_factors, flat_grad, wgan_lambda=10.0, wgan_epsilon=0.001, wgan_target=1.0):
+    """The critic loss shared by D_rec_wgangp / D_interp_wgangp / D_blend_wgangp (loss.py:303-521); they differ
+    only in how `fakes` is produced (reconstruction, interpolation crop, blend crop):
+        mean(D(fake) - D(real)) + lambda (||grad D(mixed)|| - 1)^2 + eps D(real)^2,  mixed = lerp(real, fake, t).
+    Differentiates mean over the batch w.r.t. D's variables into flat_grad; returns the term means."""
+    rt = D.rt
+    n = reals.shape[0]
+    rep = {}
+    t_f, t_r = [], []
+    s_f = D.get_output_for(fakes.contiguous(), tape=t_f)
+    backward(D, t_f, [torch.full_like(s_f, 1.0 / n)], flat_grad, want_input_grads=False)
+    s_r = D.get_output_for(reals.contiguous(), tape=t_r)
+    seed = rt.empty(*s_r.shape)                       # d/ds_real [ -s/N + eps s^2 / N ]
+    _lib.check(rt.lib.tmx_axpb(rt.handle, _ptr(s_r), _ptr(seed), n, 2.0 * wgan_epsilon / n, -1.0 / n, rt.stream()),
+               'tmx_axpb')
+    backward(D, t_r, [seed], flat_grad, want_input_grads=False)
+    rep['D_loss'] = _add(rt, _row_sum(rt, s_f, 1, n, scale=1.0 / n), _row_sum(rt, s_r, 1, n, scale=-1.0 / n))
+    rep['epsilon_penalty'] = _row_sum(rt, s_r, 1, n, scale=wgan_epsilon / n, square=True)
+    per = reals[0].numel()
+    mixed = rt.latent_blend([reals.contiguous().view(n, 1, 1, per), fakes.contiguous().view(n, 1, 1, per)], 1, per,
+                            _lib.BLEND_LERP, t=mixing_factors.reshape(-1).contiguous()).view(*reals.shape)
+    rep['gradient_penalty'] = gradient_penalty(D, mixed, flat_grad, wgan_lambda, wgan_target)
+    return rep
