@@ -45,7 +45,8 @@ class Optimizer:
         assert flat_grad.shape == net.flat.shape and flat_grad.dtype == torch.float32
         for ent in self._nets:
             if ent[0] is net:
-                ent[1].add_(flat_grad) if ent[1] is not flat_grad else None
+                if ent[1] is not flat_grad:
+                    raise ValueError('one flat gradient buffer per network: accumulate further losses into it')
                 ent[4] += 1
                 return
         m = torch.zeros_like(net.flat)
@@ -83,6 +84,4 @@ class Optimizer:
                                             self.beta1, self.beta2, self.epsilon, scale, _ptr(p), _ptr(self._flag),
                                             st), 'tmx_adam_step')
             net.mark_variables_changed()
-        for ent in self._nets:
-            ent[4] = 0
         return self._flag        # device int32: 1 = the step was skipped (overflow_frequency, tfutil.py:365)

@@ -1,0 +1,145 @@
+"""One TextureMixer train step on the device: the inner loop of
+`run.train_TextureMixer` (run.py:426-514) at lod 0 - permutation sampling, the three
+critic updates, the encoder/generator update, the EMA of the inference copies.
+
+    for repeat in range(minibatch_repeats):                      # run.py:510
+        run([D_rec_train_op, D_interp_train_op, D_blend_train_op])    # critics, pre-step E/G   (run.py:511)
+        run([EG_train_op])                                            # E_zg, E_zl, G, post-step critics (:512)
+        run([Es_zg_update_op, Es_zl_update_op, Gs_update_op])          # EMA beta = 0.999         (:513, :233)
+
+Data parallel like the reference: every rank holds all nine networks, takes its contiguous share of
+the global batch, and `Optimizer.apply_updates` sums each network's flat gradient across ranks with one NCCL
+all-reduce, scales by 1/world and steps Adam(beta1 0, beta2 0.99, eps 1e-8; config.py:84-87).
+
+gram_weight is 0 (VGG-19 weights not redistributable - stated deviation); lod > 0 (progressive
+growing) is not implemented."""
+import numpy as np
+import torch
+
+from . import _lib, interp, loss, parallel
+from .network import Network
+from .optim import Optimizer
+from .runtime import Runtime
+
+NET_FUNCS = dict(E_zg='networks.E_zg', E_zl='networks.E_zl', G='networks.G_res', D_rec='networks.D_patch',
+                 D_interp='networks.D_patch', D_blend='networks.D_patch')
+
+
+def default_config(train_size=128, fmap_base=1024, fmap_max=512, latent_channels=128, scale_h=3, scale_w=3):
+    """The values of config.py:39-87 that the hot path reads."""
+    latent_res = train_size // 4
+    enc = dict(fmap_base=fmap_base, fmap_max=fmap_max, latent_channels=latent_channels, use_pixelnorm=False,
+               tanh_at_end=False)
+    return dict(
+        resolution=train_size, latent_res=latent_res, scale_h=scale_h, scale_w=scale_w,
+        E_zg=dict(enc), E_zl=dict(enc, latent_res=latent_res),
+        G=dict(fmap_base=fmap_base, fmap_max=fmap_max, latent_res=latent_res, latent_channels=latent_channels,
+               use_pixelnorm=False, tanh_at_end=True),
+        D_rec=dict(fmap_base=fmap_base, fmap_max=fmap_max, latent_res=-1),
+        D_interp=dict(fmap_base=fmap_base, fmap_max=fmap_max, latent_res=-1),
+        D_blend=dict(fmap_base=fmap_base, fmap_max=fmap_max, latent_res=-1),
+        opt=dict(beta1=0.0, beta2=0.99, epsilon=1e-8), lrate=0.0015, ema_beta=0.999,
+        loss=dict(rec_G_weight=1.0, pixel_weight=200.0, interp_G_weight=1.0, blend_interp_G_weight=1.0),
+        levels=int(np.log2(latent_res)))
+
+
+class Trainer:
+    """Owns the nine networks, the four optimizers and the per-network flat gradient buffers of one rank."""
+
+    def __init__(self, config=None, seed=1000, device=None):
+        self.cfg = config or default_config()
+        c = self.cfg
+        self.rt = Runtime.get(device)
+        res = c['resolution']
+        self.nets = {}
+        for i, (name, func) in enumerate(NET_FUNCS.items()):                       # run.py:264-269
+            self.nets[name] = Network(name, func=func, seed=seed + i, num_channels=3, resolution=res,
+                                      device=self.rt.device, **c[name])
+        self.G_fcn = Network('G', func=NET_FUNCS['G'], reuse=True, share_vars_with=self.nets['G'], num_channels=3,
+                             resolution=res, scale_h=c['scale_h'], scale_w=c['scale_w'], device=self.rt.device,
+                             **c['G'])                                              # run.py:273
+        parallel.broadcast_([n.flat for n in self.nets.values()])                  # identical replicas
+        self.ema = {}
+        for src, dst in (('E_zg', 'Es_zg'), ('E_zl', 'Es_zl'), ('G', 'Gs')):       # run.py:270-272
+            self.nets[dst] = self.nets[src].clone(dst)
+            self.ema[dst] = self.nets[dst].setup_as_moving_average_of(self.nets[src], beta=c['ema_beta'])
+        self.grads = {k: torch.zeros_like(self.nets[k].flat) for k in NET_FUNCS}
+        self.opts = {}
+        for name, members in (('EG', ('E_zg', 'E_zl', 'G')), ('D_rec', ('D_rec',)), ('D_interp', ('D_interp',)),
+                              ('D_blend', ('D_blend',))):                           # run.py:297-300
+            opt = Optimizer(name='Train' + name, learning_rate=c['lrate'], **c['opt'])
+            for m in members:
+                opt.register_gradients(self.nets[m], self.grads[m])
+            self.opts[name] = opt
+
+    # ------------------------------------------------------------------ host-side random draws of one step
+    def sample_draws(self, minibatch, rng, uniform=None):
+        """Permutation index vectors (run.py:436-507, same np.random stream as the reference when `uniform` is None)
+        plus the graph's own random ops made explicit: one crop offset per loss that crops (loss.py:78-90) and the
+        per-sample mixing factors (loss.py:237,329,405,489,505)."""
+        c = self.cfg
+        idx = interp.sample_schedule_indices(minibatch, c['latent_res'], c['scale_h'], c['scale_w'], c['levels'], uniform)
+        res = c['resolution']
+        hi_y, hi_x = res * c['scale_h'] - res, res * c['scale_w'] - res
+
+        def crop():
+            return (int(rng.randint(0, hi_y)) if hi_y > 0 else 0, int(rng.randint(0, hi_x)) if hi_x > 0 else 0)
+
+        def mix():
+            return torch.from_numpy(rng.uniform(0.0, 1.0, (minibatch, 1, 1, 1)).astype(np.float32)).to(self.rt.device)
+        return dict(idx=idx, eg_crop_interp=crop(), eg_crop_blend=crop(), eg_mix=mix(), d_rec_gp=mix(),
+                    d_interp_crop=crop(), d_interp_gp=mix(), d_blend_mix=mix(), d_blend_crop=crop(), d_blend_gp=mix())
+
+    # ------------------------------------------------------------------ fake images for the critics (no tape)
+    def _fakes(self, reals, d):
+        c, rt = self.cfg, self.rt
+        n, res = reals.shape[0], self.cfg['resolution']
+        zg_mu, _ = self.nets['E_zg'].get_output_for(reals)
+        zl_mu, _ = self.nets['E_zl'].get_output_for(reals)
+        lat = c['latent_res']
+        H, W = lat * c['scale_h'], lat * c['scale_w']
+        pins = interp._corner_pins(c['scale_h'], c['scale_w'])
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(rt.device)  # noqa: E731
+        idx = d['idx']
+        rec = self.nets['G'].get_output_for(rt.latent_blend([zg_mu.contiguous()], lat, lat, _lib.BLEND_COPY), zl_mu)
+        zg_c = rt.latent_blend([zg_mu.contiguous()], H, W, _lib.BLEND_COPY)
+        zl_c = rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[dev(idx['h_forward'])],
+                               idx_w=[dev(idx['w_forward'])], pin_rows=pins[0], pin_cols=pins[1])
+        y0, x0 = d['d_interp_crop']
+        interp_img = self.G_fcn.get_output_for(zg_c, zl_c)[:, :, y0:y0 + res, x0:x0 + res].contiguous()
+        zg_r = rt.latent_blend([zg_mu.contiguous()], H, W, _lib.BLEND_COPY, src_reverse=1)
+        zl_r = rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[dev(idx['h_backward'])],
+                               idx_w=[dev(idx['w_backward'])], pin_rows=pins[0], pin_cols=pins[1], src_reverse=1)
+        t = d['d_blend_mix'].reshape(-1).contiguous()
+        bzg = rt.latent_blend([zg_r, zg_c], H, W, _lib.BLEND_LERP, t=t)
+        bzl = rt.latent_blend([zl_r, zl_c], H, W, _lib.BLEND_LERP, t=t)
+        y0, x0 = d['d_blend_crop']
+        blend_img = self.G_fcn.get_output_for(bzg, bzl)[:, :, y0:y0 + res, x0:x0 + res].contiguous()
+        return rec, interp_img, blend_img
+
+    # ------------------------------------------------------------------ one step
+    def step(self, reals, draws, lrate=None, phases=('D', 'EG', 'EMA')):
+        """reals: this rank's share [n,3,R,R] fp32 in [-1,1] on the device.  Returns the loss-term report."""
+        report = {}
+        if 'D' in phases:
+            rec, interp_img, blend_img = self._fakes(reals, draws)
+            for name, fake, gp in (('D_rec', rec, 'd_rec_gp'), ('D_interp', interp_img, 'd_interp_gp'),
+                                   ('D_blend', blend_img, 'd_blend_gp')):
+                self.grads[name].zero_()
+                rep = loss.D_wgangp(self.nets[name], fake, reals, draws[gp], self.grads[name])
+                report.update({name + '/' + k: v for k, v in rep.items()})
+            for name in ('D_rec', 'D_interp', 'D_blend'):                           # one session.run (run.py:511)
+                report[name + '/skipped'] = self.opts[name].apply_updates(lrate)
+        if 'EG' in phases:
+            for k in ('E_zg', 'E_zl', 'G'):
+                self.grads[k].zero_()
+            rep = loss.EG_wgan(self.nets['E_zg'], self.nets['E_zl'], self.nets['G'], self.nets['D_rec'], self.G_fcn,
+                               self.nets['D_interp'], self.nets['D_blend'], reals, draws['idx'], draws['eg_crop_interp'],
+                               draws['eg_crop_blend'], draws['eg_mix'], self.grads, scale_h=self.cfg['scale_h'],
+                               scale_w=self.cfg['scale_w'], **self.cfg['loss'])
+            report.update({'EG/' + k: v for k, v in rep.items()})
+            report['EG/skipped'] = self.opts['EG'].apply_updates(lrate)
+        if 'EMA' in phases:
+            for upd in self.ema.values():
+                upd()
+        return report
