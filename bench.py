@@ -272,6 +272,107 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------ train step (BASELINE configs[2] / [4])
+TRAIN_BATCH = 32
+TRAIN_GFLOP_PER_SAMPLE = 908.9     # SURVEY Appendix C (gram off, shared forwards); as executed here the E/G forwards
+#                                    of the critic phase are recomputed, so the device does ~1 044 GFLOP per sample
+
+
+def run_train(args):
+    import torch
+    import torch.distributed as dist
+    from texturemixer_b200 import parallel
+    from texturemixer_b200.train import Trainer
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a B200; there is no CPU path')
+    torch.cuda.set_device(local)
+    parallel.init_from_env()
+    tr = Trainer(seed=1000, device=local)
+    rt, dev = tr.rt, tr.rt.device
+    rng = np.random.RandomState(1000 + rank)
+    np.random.seed(1000 + rank)
+    reals_h = torch.from_numpy(rng.uniform(-1, 1, (TRAIN_BATCH, 3, 128, 128)).astype(np.float32)).pin_memory()
+    reals_d = reals_h.to(dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        tr.step(reals_d, tr.sample_draws(TRAIN_BATCH, rng))
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # device-resident: reals already in HBM; the host permutation sampler runs inside the step (it is part of it)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0 = rt.launch_count()
+    ev0.record()
+    for _ in range(args.steps):
+        tr.step(reals_d, tr.sample_draws(TRAIN_BATCH, rng))
+    ev1.record()
+    barrier()
+    launches = rt.launch_count() - l0
+    dev_ms = ev0.elapsed_time(ev1)
+    # end to end: reals from pinned host memory every step, loss report read back
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        x = reals_h.to(dev, non_blocking=True)
+        rep = tr.step(x, tr.sample_draws(TRAIN_BATCH, rng))
+        host_rep = {k: float(v.reshape(-1)[0].item()) for k, v in rep.items()}
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    # replicas must stay identical: compare a checksum of G's weights across ranks
+    chk = tr.nets['G'].flat.double().sum().reshape(1)
+    lo, hi = chk.clone(), chk.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = float(t[0]), float(t[1])
+    if rank == 0:
+        pk = peaks()
+        samples = TRAIN_BATCH * world * args.steps
+        value = samples / (dev_ms * 1e-3)
+        tf = value * TRAIN_GFLOP_PER_SAMPLE / 1e3 / world
+        line = {
+            'metric': '128x128 texture images/sec (full train step: 3 critics + E/G + EMA)', 'value': value,
+            'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 (bf16x3 tensor-core products, fp32 accumulate)', 'data': 'synthetic',
+            'config': {'workload': 'cfg3/5: full train step, batch 32 per GPU, lod 0, gram_weight 0, 3x3 canvases',
+                       'batch_per_gpu': TRAIN_BATCH, 'global_batch': TRAIN_BATCH * world,
+                       'l2': 'working set per step (>20 GB) far exceeds the 126 MB L2',
+                       'parallelism': 'dp%d: one flat-bucket NCCL all-reduce per network per optimizer' % world,
+                       'gflop_per_sample': TRAIN_GFLOP_PER_SAMPLE},
+            'e2e': {'value': samples / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': int(reals_h.numel() * 4),
+                    'd2h_bytes_per_step': 4 * len(host_rep), 'api': 'Trainer.step(reals) with host reals + loss report'},
+            'gpu_launches': int(launches),
+            'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': pk['bf16_sustained'] or pk['bf16'], 'unit': 'TFLOP/s',
+                         'frac': tf / (pk['bf16_sustained'] or pk['bf16']), 'traffic': None,
+                         'kernel': 'whole step per GPU (algorithmic fp32-conv FLOPs; tensor pipe executes 3x)',
+                         'peak_source': pk['source'] + ', bf16 sustained'},
+            'cpu_baseline': None,
+            'replicas_identical': bool(float(hi - lo) == 0.0),
+            'clocks': clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -279,9 +380,14 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--device-only', action='store_true', help='only the device-resident loop (profiling runs)')
+    ap.add_argument('--workload', default='gen_fwd', choices=['gen_fwd', 'train_step'],
+                    help='gen_fwd = BASELINE configs[1] (headline); train_step = configs[2]/[4]: full train step, '
+                         'batch 32 per GPU, NCCL gradient all-reduce')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'train_step':
+        run_train(args)
     else:
         run_ours(args)
 
