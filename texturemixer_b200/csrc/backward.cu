@@ -414,36 +414,45 @@ extern "C" int tmx_fromrgb_bwd(tmx_handle_t h, const float* img, const float* dz
 
 // ---------------------------------------------------------------- dense / minibatch-stddev input gradients (D head)
 // dx[n][k] = wscale * sum_o dz[n][o] * w[k][o],  dz = dy * lrelu'(y) (networks.py:38-43, 72-75).
-// One warp per input feature k: lanes stride over o (coalesced rows of w), up to 32 samples accumulated per pass.
+// Block = 64 input features x 32 samples; the contraction over o runs in chunks of 32 staged in shared memory
+// (w rows read coalesced along o).  Thread (kk, ng) owns feature kk and samples ng*8 .. ng*8+7.
 __global__ void __launch_bounds__(256) dense_bwd_input_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                                               const float* __restrict__ w, float wscale,
                                                               float* __restrict__ dx, int N, int K, int Cout, int lrelu,
                                                               float alpha) {
-  const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (k >= K) return;
-  for (int n0 = 0; n0 < N; n0 += 32) {
-    const int nn = min(32, N - n0);
-    float acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    for (int o = lane; o < Cout; o += 32) {
-      const float wv = __ldg(w + (long long)k * Cout + o);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i < nn) {
-          float g = __ldg(dy + (long long)(n0 + i) * Cout + o);
-          if (lrelu) g *= (__ldg(y + (long long)(n0 + i) * Cout + o) > 0.f) ? 1.f : alpha;
-          acc[i] = fmaf(g, wv, acc[i]);
-        }
-      }
+  __shared__ float ws[64][33];
+  __shared__ float zs[32][33];
+  const int k0 = blockIdx.x * 64, n0 = blockIdx.y * 32;
+  const int kk = threadIdx.x & 63, ng = threadIdx.x >> 6;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int o0 = 0; o0 < Cout; o0 += 32) {
+    for (int e = threadIdx.x; e < 64 * 32; e += 256) {
+      const int r = e >> 5, c = e & 31;
+      ws[r][c] = (k0 + r < K && o0 + c < Cout) ? __ldg(w + (long long)(k0 + r) * Cout + o0 + c) : 0.f;
     }
+    for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+      const int r = e >> 5, c = e & 31;
+      float g = 0.f;
+      if (n0 + r < N && o0 + c < Cout) {
+        g = __ldg(dy + (long long)(n0 + r) * Cout + o0 + c);
+        if (lrelu) g *= (__ldg(y + (long long)(n0 + r) * Cout + o0 + c) > 0.f) ? 1.f : alpha;
+      }
+      zs[r][c] = g;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < 32; ++c) {
+      const float wv = ws[kk][c];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float v = acc[i];
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(zs[ng * 8 + i][c], wv, acc[i]);
+    }
+    __syncthreads();
+  }
+  if (k0 + kk < K) {
 #pragma unroll
-      for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
-      if (lane == 0 && i < nn) dx[(long long)(n0 + i) * K + k] = v * wscale;
+    for (int i = 0; i < 8; ++i) {
+      const int n = n0 + ng * 8 + i;
+      if (n < N) dx[(long long)n * K + k0 + kk] = acc[i] * wscale;
     }
   }
 }
@@ -452,7 +461,8 @@ extern "C" int tmx_dense_bwd_input(tmx_handle_t h, const float* dy, const float*
                                    float* dx, int N, int K, int Cout, int lrelu, float alpha, tmx_stream_t s) {
   TMX_REQUIRE(h && dy && w && dx && (!lrelu || y), TMX_ERR_ARG, "tmx_dense_bwd_input: NULL argument");
   TMX_REQUIRE(N > 0 && K > 0 && Cout > 0, TMX_ERR_SHAPE, "tmx_dense_bwd_input: bad shape");
-  dense_bwd_input_kernel<<<tmx_ceil_div(K, 8), 256, 0, (cudaStream_t)s>>>(dy, y, w, wscale, dx, N, K, Cout, lrelu, alpha);
+  dim3 grid(tmx_ceil_div(K, 64), tmx_ceil_div(N, 32));
+  dense_bwd_input_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(dy, y, w, wscale, dx, N, K, Cout, lrelu, alpha);
   TMX_LAUNCHED(h, "dense_bwd_input_kernel");
   return TMX_OK;
 }

@@ -321,9 +321,24 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-#pragma unroll 1
       const int ngroups = BN / parts / GW;
+      // residual stream (networks.py:437; never combined with the sub-pixel form): the loads of group g+1 are
+      // issued before the TMEM read of group g so that their latency hides behind it
+      const bool res_on = p.has_res && valid;
+      const long long res_pix = p.lin ? mlin : ((long long)n * Hl + y) * Wl + x;
+      const float4* res_base =
+          reinterpret_cast<const float4*>(p.residual + res_pix * CL + cblk * BN + part * (BN / parts));
+      float4 rcur[GW / 4], rnext[GW / 4];
+      if (res_on) {
+#pragma unroll
+        for (int j = 0; j < GW / 4; ++j) rcur[j] = __ldg(res_base + j);
+      }
+#pragma unroll 1
       for (int g = 0; g < ngroups; ++g) {
+        if (res_on && g + 1 < ngroups) {
+#pragma unroll
+          for (int j = 0; j < GW / 4; ++j) rnext[j] = __ldg(res_base + (g + 1) * (GW / 4) + j);
+        }
         uint32_t acc[32];
         if (GW == 32) tmem_ld32(taddr0 + g * GW, acc);
         else tmem_ld16(taddr0 + g * GW, acc);
@@ -346,14 +361,13 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           const long long pix = p.lin ? mlin : ((long long)n * Hl + oy) * Wl + ox;
           if (p.has_res) {
-            const float4* rp = reinterpret_cast<const float4*>(p.residual + pix * CL + cbase);
 #pragma unroll
             for (int j = 0; j < GW / 4; ++j) {
-              const float4 rr = __ldg(rp + j);
-              v[4 * j] += rr.x;
-              v[4 * j + 1] += rr.y;
-              v[4 * j + 2] += rr.z;
-              v[4 * j + 3] += rr.w;
+              v[4 * j] += rcur[j].x;
+              v[4 * j + 1] += rcur[j].y;
+              v[4 * j + 2] += rcur[j].z;
+              v[4 * j + 3] += rcur[j].w;
+              rcur[j] = rnext[j];
             }
           }
           if (p.y_f32 != nullptr) {
@@ -598,6 +612,8 @@ int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_i
               "tmx_conv2d_fwd[TC]: HALO_REPLICATE and UP2_OUT cannot be combined");
   TMX_REQUIRE(!(d->flags & TMX_CONV_RESIDUAL) || io->residual, TMX_ERR_ARG,
               "tmx_conv2d_fwd[TC]: RESIDUAL flag without residual pointer");
+  TMX_REQUIRE(!(phase && (d->flags & TMX_CONV_RESIDUAL)), TMX_ERR_UNSUPPORTED,
+              "tmx_conv2d_fwd[TC]: RESIDUAL and UP2_IN cannot be combined");
   TMX_REQUIRE(!phase || (d->k == 3 && d->H % 2 == 0 && d->W % 2 == 0), TMX_ERR_SHAPE,
               "tmx_conv2d_fwd[TC]: UP2_IN needs k == 3 and even H, W (got k=%d, %d x %d)", d->k, d->H, d->W);
   TMX_REQUIRE(d->Cin % 16 == 0 && d->Cout % 16 == 0, TMX_ERR_SHAPE,
