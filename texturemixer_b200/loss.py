@@ -60,83 +60,91 @@ def _crop_adjoint(dcrop, full_hw, yx):
     return full
 
 
-def EG_wgan(E_zg, E_zl, G, D_rec, G_fcn, D_interp, D_blend, reals, idx, crop_interp, crop_blend, mixing_factors,
-            grads, scale_h=3, scale_w=3, rec_G_weight=1.0, pixel_weight=200.0, interp_G_weight=1.0,
-            blend_interp_G_weight=1.0):
-    """One evaluation + differentiation of mean(EG_loss) (run.py:321).
-    reals: [N,3,R,R] fp32 device tensor in [-1,1]; idx: dict of int32 index vectors (interp.sample_schedule_indices);
-    crop_*: (y, x); mixing_factors: [N,1,1,1] fp32 device tensor; grads: {'E_zg','E_zl','G'} -> flat gradient
-    buffers (accumulated into).  Returns a dict of per-term batch means (device scalars)."""
-    rt = Runtime.get(reals.device)
-    n, _, res, _ = reals.shape
+class EGForward:
+    """The E/G side of `EG_wgan` run once with tapes: encoders, reconstruction, interpolated and blended canvases.
+    Its images depend only on the E/G variables, which do not change between the critic update and the E/G update of
+    one step (run.py:511-512), so the critic phase can reuse `rec` and `interp` as its fakes."""
+
+    def __init__(self, E_zg, E_zl, G, G_fcn, reals, idx, mixing_factors, scale_h=3, scale_w=3, need_interp=True,
+                 need_blend=True):
+        rt = self.rt = Runtime.get(reals.device)
+        self.nets = (E_zg, E_zl, G, G_fcn)
+        self.reals, self.scale = reals, (scale_h, scale_w)
+        self.n = n = reals.shape[0]
+        self.t_zg, self.t_zl, self.t_rec, self.t_int, self.t_bl = [], [], [], [], []
+        self.zg_mu, _ = E_zg.get_output_for(reals, tape=self.t_zg)
+        self.zl_mu, _ = E_zl.get_output_for(reals, tape=self.t_zl)
+        zg_mu, zl_mu = self.zg_mu, self.zl_mu
+        self.c, self.lat = c, lat = zl_mu.shape[1], zl_mu.shape[2]
+        self.H, self.W = H, W = lat * scale_h, lat * scale_w
+        self.pins = pins = interp._corner_pins(scale_h, scale_w)
+        self.rec = G.get_output_for(_tile_code(rt, zg_mu, lat, lat), zl_mu, tape=self.t_rec)
+        self.interp = self.blend = None
+        if need_interp or need_blend:
+            self.ih_f, self.iw_f = _dev_idx(rt, idx['h_forward']), _dev_idx(rt, idx['w_forward'])
+            zg_c = _tile_code(rt, zg_mu, H, W)
+            zl_c = rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[self.ih_f], idx_w=[self.iw_f],
+                                   pin_rows=pins[0], pin_cols=pins[1])
+        if need_interp:
+            self.interp = G_fcn.get_output_for(zg_c, zl_c, tape=self.t_int)
+        if need_blend:
+            self.ih_b, self.iw_b = _dev_idx(rt, idx['h_backward']), _dev_idx(rt, idx['w_backward'])
+            # tf.reverse(axis=[0]) of the sources is folded into the gather (src_reverse)
+            zg_r = rt.latent_blend([zg_mu.contiguous()], H, W, _lib.BLEND_COPY, src_reverse=1)
+            zl_r = rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[self.ih_b], idx_w=[self.iw_b],
+                                   pin_rows=pins[0], pin_cols=pins[1], src_reverse=1)
+            self.t = t = mixing_factors.reshape(-1).contiguous()
+            bzg = rt.latent_blend([zg_r, zg_c], H, W, _lib.BLEND_LERP, t=t)      # lerp(reverse, forward, t), loss.py:238
+            bzl = rt.latent_blend([zl_r, zl_c], H, W, _lib.BLEND_LERP, t=t)
+            self.blend = G_fcn.get_output_for(bzg, bzl, tape=self.t_bl)
+
+    def crop(self, which, yx):
+        img = self.interp if which == 'interp' else self.blend
+        res = self.reals.shape[2]
+        return img[:, :, yx[0]:yx[0] + res, yx[1]:yx[1] + res].contiguous()
+
+
+def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, rec_G_weight=1.0, pixel_weight=200.0,
+                interp_G_weight=1.0, blend_interp_G_weight=1.0):
+    """Loss terms of `EG_wgan` on the images of `fwd` and the whole reverse pass into `grads`."""
+    rt = fwd.rt
+    E_zg, E_zl, G, G_fcn = fwd.nets
+    reals, n, c, lat, H, W, pins = fwd.reals, fwd.n, fwd.c, fwd.lat, fwd.H, fwd.W, fwd.pins
     inv_n = 1.0 / n
     report = {}
-
-    # ---------------- forward
-    t_zg, t_zl = [], []
-    zg_mu, _ = E_zg.get_output_for(reals, tape=t_zg)
-    zl_mu, _ = E_zl.get_output_for(reals, tape=t_zl)
-    c, lat = zl_mu.shape[1], zl_mu.shape[2]
-    H, W = lat * scale_h, lat * scale_w
-    pins = interp._corner_pins(scale_h, scale_w)
-
-    t_rec, t_drec = [], []
-    rec = G.get_output_for(_tile_code(rt, zg_mu, lat, lat), zl_mu, tape=t_rec)
+    rec = fwd.rec
     d_rec_img = None
     if rec_G_weight > 0:
-        s = D_rec.get_output_for(rec, tape=t_drec)
+        t_d = []
+        s = D_rec.get_output_for(rec, tape=t_d)
         report['rec_G'] = _row_sum(rt, s, 1, n, scale=-rec_G_weight * inv_n)
-        (d_rec_img,) = backward(D_rec, t_drec, [torch.full_like(s, -rec_G_weight * inv_n)], None, param_grads=False)
+        (d_rec_img,) = backward(D_rec, t_d, [torch.full_like(s, -rec_G_weight * inv_n)], None, param_grads=False)
     if pixel_weight > 0:
         l1 = rt.empty(*rec.shape)
         lsum = torch.zeros(1, dtype=torch.float32, device=rt.device)
         per = rec[0].numel()
         _lib.check(rt.lib.tmx_loss_l1_grad(rt.handle, _ptr(rec), _ptr(reals.contiguous()), _ptr(l1), _ptr(lsum),
                                            rec.numel(), pixel_weight * inv_n / per, rt.stream()), 'tmx_loss_l1_grad')
-        report['rec_pixel'] = lsum * (pixel_weight * inv_n / per)
-        if d_rec_img is None:
-            d_rec_img = l1
-        else:
-            d_rec_img = _add(rt, d_rec_img, l1)
-    dzg_tiled, dzl = backward(G, t_rec, [d_rec_img], grads['G'])
+        report['rec_pixel'] = _row_sum(rt, lsum, 1, 1, scale=pixel_weight * inv_n / per)
+        d_rec_img = l1 if d_rec_img is None else _add(rt, d_rec_img, l1)
+    dzg_tiled, dzl = backward(G, fwd.t_rec, [d_rec_img], grads['G'])
     dzg = _row_sum(rt, dzg_tiled, n * c, lat * lat)                      # adjoint of the 32x32 tile of zg
     dzl = dzl.contiguous()
-
-    if interp_G_weight > 0 or blend_interp_G_weight > 0:
-        ih_f, iw_f = _dev_idx(rt, idx['h_forward']), _dev_idx(rt, idx['w_forward'])
-        zg_c = _tile_code(rt, zg_mu, H, W)
-        zl_c = rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[ih_f], idx_w=[iw_f],
-                               pin_rows=pins[0], pin_cols=pins[1])
     if interp_G_weight > 0:
-        t_g, t_d = [], []
-        img = G_fcn.get_output_for(zg_c, zl_c, tape=t_g)
-        y0, x0 = crop_interp
-        cr = img[:, :, y0:y0 + res, x0:x0 + res].contiguous()
-        s = D_interp.get_output_for(cr, tape=t_d)
+        t_d = []
+        s = D_interp.get_output_for(fwd.crop('interp', crop_interp), tape=t_d)
         report['interp_G'] = _row_sum(rt, s, 1, n, scale=-interp_G_weight * inv_n)
         (dcr,) = backward(D_interp, t_d, [torch.full_like(s, -interp_G_weight * inv_n)], None, param_grads=False)
-        dzg_c, dzl_c = backward(G_fcn, t_g, [_crop_adjoint(dcr, img.shape[2:], crop_interp)], grads['G'])
+        dzg_c, dzl_c = backward(G_fcn, fwd.t_int, [_crop_adjoint(dcr, fwd.interp.shape[2:], crop_interp)], grads['G'])
         _row_sum(rt, dzg_c, n * c, H * W, out=dzg, accumulate=True)
-        _gather_bwd(rt, dzl_c, dzl, ih_f, iw_f, pins)
-        del t_g, t_d, img
+        _gather_bwd(rt, dzl_c, dzl, fwd.ih_f, fwd.iw_f, pins)
     if blend_interp_G_weight > 0:
-        ih_b, iw_b = _dev_idx(rt, idx['h_backward']), _dev_idx(rt, idx['w_backward'])
-        zero1 = torch.zeros_like(zg_mu)
-        # tf.reverse(axis=[0]) of the sources is folded into the gather (src_reverse)
-        zg_r = rt.latent_blend([zg_mu.contiguous()], H, W, _lib.BLEND_COPY, src_reverse=1)
-        zl_r = rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[ih_b], idx_w=[iw_b],
-                               pin_rows=pins[0], pin_cols=pins[1], src_reverse=1)
-        t = mixing_factors.reshape(-1).contiguous()
-        bzg = rt.latent_blend([zg_r, zg_c], H, W, _lib.BLEND_LERP, t=t)          # lerp(reverse, forward, t), loss.py:238
-        bzl = rt.latent_blend([zl_r, zl_c], H, W, _lib.BLEND_LERP, t=t)
-        t_g, t_d = [], []
-        img = G_fcn.get_output_for(bzg, bzl, tape=t_g)
-        y0, x0 = crop_blend
-        cr = img[:, :, y0:y0 + res, x0:x0 + res].contiguous()
-        s = D_blend.get_output_for(cr, tape=t_d)
+        t_d = []
+        t = fwd.t
+        s = D_blend.get_output_for(fwd.crop('blend', crop_blend), tape=t_d)
         report['blend_G'] = _row_sum(rt, s, 1, n, scale=-blend_interp_G_weight * inv_n)
         (dcr,) = backward(D_blend, t_d, [torch.full_like(s, -blend_interp_G_weight * inv_n)], None, param_grads=False)
-        dbzg, dbzl = backward(G_fcn, t_g, [_crop_adjoint(dcr, img.shape[2:], crop_blend)], grads['G'])
+        dbzg, dbzl = backward(G_fcn, fwd.t_bl, [_crop_adjoint(dcr, fwd.blend.shape[2:], crop_blend)], grads['G'])
         zero_c = torch.zeros_like(dbzg)
         # adjoint of lerp: d forward = t * d, d reverse = d - t * d   (same fp32 ops as autograd of a + (b - a) * t)
         for d, dsrc_kind in ((dbzg, 'zg'), (dbzl, 'zl')):
@@ -147,14 +155,24 @@ def EG_wgan(E_zg, E_zl, G, D_rec, G_fcn, D_interp, D_blend, reals, idx, crop_int
                 tmp = _row_sum(rt, d_rev, n * c, H * W).view(n, c, 1, 1)
                 _gather_bwd(rt, tmp, dzg.view(n, c, 1, 1), None, None, (0, 0), reverse=True)
             else:
-                _gather_bwd(rt, d_fwd, dzl, ih_f, iw_f, pins)
-                _gather_bwd(rt, d_rev, dzl, ih_b, iw_b, pins, reverse=True)
-        del t_g, t_d, img, zero1
-
-    # ---------------- encoders
-    backward(E_zl, t_zl, [dzl, None], grads['E_zl'], want_input_grads=False)
-    backward(E_zg, t_zg, [dzg.view(n, c, 1, 1), None], grads['E_zg'], want_input_grads=False)
+                _gather_bwd(rt, d_fwd, dzl, fwd.ih_f, fwd.iw_f, pins)
+                _gather_bwd(rt, d_rev, dzl, fwd.ih_b, fwd.iw_b, pins, reverse=True)
+    backward(E_zl, fwd.t_zl, [dzl, None], grads['E_zl'], want_input_grads=False)
+    backward(E_zg, fwd.t_zg, [dzg.view(n, c, 1, 1), None], grads['E_zg'], want_input_grads=False)
     return report
+
+
+def EG_wgan(E_zg, E_zl, G, D_rec, G_fcn, D_interp, D_blend, reals, idx, crop_interp, crop_blend, mixing_factors,
+            grads, scale_h=3, scale_w=3, rec_G_weight=1.0, pixel_weight=200.0, interp_G_weight=1.0,
+            blend_interp_G_weight=1.0):
+    """One evaluation + differentiation of mean(EG_loss) (loss.py:105-259, run.py:321).
+    reals: [N,3,R,R] fp32 device tensor in [-1,1]; idx: dict of int32 index vectors (interp.sample_schedule_indices);
+    crop_*: (y, x); mixing_factors: [N,1,1,1] fp32 device tensor; grads: {'E_zg','E_zl','G'} -> flat gradient
+    buffers (accumulated into).  Returns a dict of per-term batch means (device scalars)."""
+    fwd = EGForward(E_zg, E_zl, G, G_fcn, reals, idx, mixing_factors, scale_h, scale_w,
+                    need_interp=interp_G_weight > 0, need_blend=blend_interp_G_weight > 0)
+    return EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, rec_G_weight, pixel_weight,
+                       interp_G_weight, blend_interp_G_weight)
 
 
 def _add(rt, a, b):

@@ -90,41 +90,39 @@ class Trainer:
         return dict(idx=idx, eg_crop_interp=crop(), eg_crop_blend=crop(), eg_mix=mix(), d_rec_gp=mix(),
                     d_interp_crop=crop(), d_interp_gp=mix(), d_blend_mix=mix(), d_blend_crop=crop(), d_blend_gp=mix())
 
-    # ------------------------------------------------------------------ fake images for the critics (no tape)
-    def _fakes(self, reals, d):
+    # ------------------------------------------------------------------ fake image of the blend critic (no tape)
+    def _blend_fake(self, fwd, d):
+        """D_blend_wgangp draws its own mixing factors (loss.py:489), so its fake needs its own G_fcn forward; the
+        reconstruction and interpolation fakes are the images of the shared E/G forward."""
         c, rt = self.cfg, self.rt
-        n, res = reals.shape[0], self.cfg['resolution']
-        zg_mu, _ = self.nets['E_zg'].get_output_for(reals)
-        zl_mu, _ = self.nets['E_zl'].get_output_for(reals)
-        lat = c['latent_res']
-        H, W = lat * c['scale_h'], lat * c['scale_w']
-        pins = interp._corner_pins(c['scale_h'], c['scale_w'])
-        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(rt.device)  # noqa: E731
-        idx = d['idx']
-        rec = self.nets['G'].get_output_for(rt.latent_blend([zg_mu.contiguous()], lat, lat, _lib.BLEND_COPY), zl_mu)
+        res = c['resolution']
+        H, W, pins = fwd.H, fwd.W, fwd.pins
+        zg_mu, zl_mu = fwd.zg_mu, fwd.zl_mu
         zg_c = rt.latent_blend([zg_mu.contiguous()], H, W, _lib.BLEND_COPY)
-        zl_c = rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[dev(idx['h_forward'])],
-                               idx_w=[dev(idx['w_forward'])], pin_rows=pins[0], pin_cols=pins[1])
-        y0, x0 = d['d_interp_crop']
-        interp_img = self.G_fcn.get_output_for(zg_c, zl_c)[:, :, y0:y0 + res, x0:x0 + res].contiguous()
+        zl_c = rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[fwd.ih_f], idx_w=[fwd.iw_f],
+                               pin_rows=pins[0], pin_cols=pins[1])
         zg_r = rt.latent_blend([zg_mu.contiguous()], H, W, _lib.BLEND_COPY, src_reverse=1)
-        zl_r = rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[dev(idx['h_backward'])],
-                               idx_w=[dev(idx['w_backward'])], pin_rows=pins[0], pin_cols=pins[1], src_reverse=1)
+        zl_r = rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[fwd.ih_b], idx_w=[fwd.iw_b],
+                               pin_rows=pins[0], pin_cols=pins[1], src_reverse=1)
         t = d['d_blend_mix'].reshape(-1).contiguous()
         bzg = rt.latent_blend([zg_r, zg_c], H, W, _lib.BLEND_LERP, t=t)
         bzl = rt.latent_blend([zl_r, zl_c], H, W, _lib.BLEND_LERP, t=t)
         y0, x0 = d['d_blend_crop']
-        blend_img = self.G_fcn.get_output_for(bzg, bzl)[:, :, y0:y0 + res, x0:x0 + res].contiguous()
-        return rec, interp_img, blend_img
+        return self.G_fcn.get_output_for(bzg, bzl)[:, :, y0:y0 + res, x0:x0 + res].contiguous()
 
     # ------------------------------------------------------------------ one step
     def step(self, reals, draws, lrate=None, phases=('D', 'EG', 'EMA')):
-        """reals: this rank's share [n,3,R,R] fp32 in [-1,1] on the device.  Returns the loss-term report."""
+        """reals: this rank's share [n,3,R,R] fp32 in [-1,1] on the device.  Returns the loss-term report.
+        Order of run.py:511-513: critics see the pre-step E/G; E/G see the post-step critics; then EMA.  The E/G
+        forward is evaluated ONCE (its variables do not change in between) and serves both phases."""
         report = {}
+        c = self.cfg
+        fwd = loss.EGForward(self.nets['E_zg'], self.nets['E_zl'], self.nets['G'], self.G_fcn, reals, draws['idx'],
+                             draws['eg_mix'], c['scale_h'], c['scale_w'])
         if 'D' in phases:
-            rec, interp_img, blend_img = self._fakes(reals, draws)
-            for name, fake, gp in (('D_rec', rec, 'd_rec_gp'), ('D_interp', interp_img, 'd_interp_gp'),
-                                   ('D_blend', blend_img, 'd_blend_gp')):
+            fakes = (('D_rec', fwd.rec, 'd_rec_gp'), ('D_interp', fwd.crop('interp', draws['d_interp_crop']), 'd_interp_gp'),
+                     ('D_blend', self._blend_fake(fwd, draws), 'd_blend_gp'))
+            for name, fake, gp in fakes:
                 self.grads[name].zero_()
                 rep = loss.D_wgangp(self.nets[name], fake, reals, draws[gp], self.grads[name])
                 report.update({name + '/' + k: v for k, v in rep.items()})
@@ -133,12 +131,11 @@ class Trainer:
         if 'EG' in phases:
             for k in ('E_zg', 'E_zl', 'G'):
                 self.grads[k].zero_()
-            rep = loss.EG_wgan(self.nets['E_zg'], self.nets['E_zl'], self.nets['G'], self.nets['D_rec'], self.G_fcn,
-                               self.nets['D_interp'], self.nets['D_blend'], reals, draws['idx'], draws['eg_crop_interp'],
-                               draws['eg_crop_blend'], draws['eg_mix'], self.grads, scale_h=self.cfg['scale_h'],
-                               scale_w=self.cfg['scale_w'], **self.cfg['loss'])
+            rep = loss.EG_backward(fwd, self.nets['D_rec'], self.nets['D_interp'], self.nets['D_blend'],
+                                   draws['eg_crop_interp'], draws['eg_crop_blend'], self.grads, **c['loss'])
             report.update({'EG/' + k: v for k, v in rep.items()})
             report['EG/skipped'] = self.opts['EG'].apply_updates(lrate)
+        del fwd
         if 'EMA' in phases:
             for upd in self.ema.values():
                 upd()
