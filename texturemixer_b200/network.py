@@ -6,6 +6,8 @@ evaluation (tfutil.py:505-516).  Variables keep the reference's names and
 HWIO/[in,out] shapes, so `__getstate__` produces the reference's version-2
 pickle dict (tfutil.py:543-550)."""
 import contextlib
+import gc
+import os
 import importlib
 import inspect
 from collections import OrderedDict
@@ -168,6 +170,8 @@ class Network:
         self._rt = None
         self._device = None
         self._staging = {}
+        self._copy_stream = None
+        self._graphs = {}
 
     @property
     def rt(self):
@@ -387,32 +391,103 @@ class Network:
             minibatch_size = num_items
         dev = self.rt.device
         out_arrays = None
-        for mb_begin in range(0, num_items, minibatch_size):
+        # Software pipeline over minibatches: (1) threaded host copy of minibatch k+1 into pinned staging,
+        # (2) its H2D on a copy stream, (3) compute of minibatch k on the current stream, (4) D2H of its result
+        # into pinned staging, (5) host copy of minibatch k-1's result - all overlapped; two staging slots.
+        main = torch.cuda.current_stream(dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        copy_stream = self._copy_stream
+        bounds = [(b, min(b + minibatch_size, num_items)) for b in range(0, num_items, minibatch_size)]
+        slot_free = [None, None]          # event: the H2D that last read input slot s has finished
+
+        out_pinned = None                 # results land directly in page-locked arrays that are handed to the caller
+
+        use_graph = not os.environ.get('TMX_NO_GRAPH')
+        conv = (out_mul, out_add, out_shrink, out_dtype)
+        slot_done = [None, None]          # event: the compute that last read graph slot s has finished
+        for k, (mb_begin, mb_end) in enumerate(bounds):
             if print_progress:
                 print('\r%d / %d' % (mb_begin, num_items), end='')
-            mb_end = min(mb_begin + minibatch_size, num_items)
+            slot = k & 1
+            if slot_free[slot] is not None:
+                slot_free[slot].synchronize()
+            shapes = [(mb_end - mb_begin,) + tuple(src.shape[1:]) for src in in_arrays]
+            graph = self._forward_graph(slot, shapes, conv, dynamic_kwargs) if use_graph else None
             mb_in = []
-            for i, src in enumerate(in_arrays):
-                stage = self._pinned(('in', i), (mb_end - mb_begin,) + tuple(src.shape[1:]), torch.float32)
-                stage.numpy()[...] = src[mb_begin:mb_end]             # host copy + cast into pinned memory
-                mb_in.append(stage.to(dev, non_blocking=True))
-            mb_out = self.get_output_for(*mb_in, return_as_list=True, **dynamic_kwargs)
-            mb_out = [_convert_output(x, out_mul, out_add, out_shrink, out_dtype) for x in mb_out]
-            if out_arrays is None:
-                out_arrays = [np.empty([num_items] + list(x.shape[1:]), _np_dtype(x)) for x in mb_out]
-            stages = []
-            for i, x in enumerate(mb_out):
-                stage = self._pinned(('out', i), tuple(x.shape), x.dtype)
-                stage.copy_(x, non_blocking=True)
-                stages.append(stage)
-            torch.cuda.current_stream(dev).synchronize()
-            for dst, stage in zip(out_arrays, stages):
-                dst[mb_begin:mb_end] = stage.numpy()
+            with torch.cuda.stream(copy_stream):
+                if graph is not None and slot_done[slot] is not None:
+                    copy_stream.wait_event(slot_done[slot])       # the graph's static inputs are free again
+                for i, src in enumerate(in_arrays):
+                    stage = self._pinned(('in', i, slot), shapes[i], torch.float32)
+                    _parallel_copy(stage.numpy(), src[mb_begin:mb_end])       # host copy + cast into pinned memory
+                    if graph is not None:
+                        graph[1][i].copy_(stage, non_blocking=True)           # H2D straight into the static input
+                    else:
+                        mb_in.append(stage.to(dev, non_blocking=True))
+                ev_in = torch.cuda.Event()
+                ev_in.record(copy_stream)
+            slot_free[slot] = ev_in
+            main.wait_event(ev_in)
+            if graph is not None:
+                graph[0].replay()                                             # one launch for the whole forward
+                mb_out = graph[2]
+                slot_done[slot] = torch.cuda.Event()
+                slot_done[slot].record(main)
+            else:
+                for t in mb_in:
+                    t.record_stream(main)
+                mb_out = self.get_output_for(*mb_in, return_as_list=True, **dynamic_kwargs)
+                mb_out = [_convert_output(x, *conv) for x in mb_out]
+            if out_pinned is None:
+                out_pinned = [torch.empty([num_items] + list(x.shape[1:]), dtype=x.dtype, pin_memory=True)
+                              for x in mb_out]
+            for dst, x in zip(out_pinned, mb_out):
+                dst[mb_begin:mb_end].copy_(x, non_blocking=True)
+        main.synchronize()
+        out_arrays = [t.numpy() for t in out_pinned]
         if print_progress:
             print('\r%d / %d' % (num_items, num_items))
         if not return_as_list:
             out_arrays = out_arrays[0] if len(out_arrays) == 1 else tuple(out_arrays)
         return out_arrays
+
+    def _forward_graph(self, slot, shapes, conv, dynamic_kwargs):
+        """CUDA graph of get_output_for (+ output conversion) for fixed input shapes and the current weight version:
+        (graph, static inputs, static outputs).  ~20 kernel launches and as many allocations become one replay, which
+        is what lets `run` pipeline small minibatches without being bound by host launch overhead."""
+        o = self._owner()
+        key = (slot, tuple(shapes), conv, tuple(sorted(dynamic_kwargs.items())))
+        ent = self._graphs.get(key)
+        if ent is not None and ent[3] == o._version:
+            return ent
+        dev = self.rt.device
+        static_in = [torch.zeros(sh, dtype=torch.float32, device=dev) for sh in shapes]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):       # warm-up outside the capture: weight planes, kernel attributes
+            outs = self.get_output_for(*static_in, return_as_list=True, **dynamic_kwargs)
+            [_convert_output(x, *conv) for x in outs]
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        # no cyclic garbage collection inside the capture: finalising unrelated CUDA objects (older graphs, events)
+        # from another test or caller while the stream is capturing invalidates it
+        gc.collect()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(g):
+                outs = self.get_output_for(*static_in, return_as_list=True, **dynamic_kwargs)
+                static_out = [_convert_output(x, *conv) for x in outs]
+        finally:
+            if gc_was_on:
+                gc.enable()
+        if len(self._graphs) > 8:
+            self._graphs.clear()
+        ent = (g, static_in, static_out, o._version)
+        self._graphs[key] = ent
+        return ent
 
     def _pinned(self, key, shape, dtype):
         """Page-locked staging buffers, kept per (slot, shape) so that repeated
@@ -488,6 +563,28 @@ class Network:
 
     def setup_weight_histograms(self, title=None):
         pass  # TensorBoard summaries are outside the hot path
+
+
+_COPY_POOL = None
+
+
+def _parallel_copy(dst, src, min_bytes=4 << 20, workers=8):
+    """dst[...] = src for large host arrays, split over a few threads (numpy releases the GIL while copying):
+    a single-threaded memcpy of the 64 MB latent batch would cost more than the whole GPU step."""
+    global _COPY_POOL
+    n = dst.shape[0]
+    if dst.nbytes < min_bytes or n < 2:
+        dst[...] = src
+        return
+    if _COPY_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _COPY_POOL = ThreadPoolExecutor(max_workers=workers)
+    parts = min(workers, n)
+    edges = [n * i // parts for i in range(parts + 1)]
+
+    def one(i):
+        dst[edges[i]:edges[i + 1]] = src[edges[i]:edges[i + 1]]
+    list(_COPY_POOL.map(one, range(parts)))
 
 
 def _np_dtype(t):
