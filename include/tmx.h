@@ -73,6 +73,10 @@ int tmx_launch_count(tmx_handle_t h, uint64_t* count);
 #define TMX_CONV_TORGB 32u   /* TC, Cout <= 32: additionally y_rgb = [tanh](rgb_wscale * (y . rgb_w) + rgb_b) as NCHW
                               * (networks.py:454-457 torgb + :483 tanh fused behind the last conv) */
 
+#define TMX_CONV_XMERGE 64u  /* TC, Cin == 16, k == 3: operand rows carry the 3 horizontal taps (4 pixels = 128 B) of
+                              * an overlapping-stride view; weights from tmx_conv_weights_prepare with xmerge = 1.
+                              * The x planes must be allocated (and zero-filled) 64 elements past their end. */
+
 #define TMX_ALGO_AUTO 0
 #define TMX_ALGO_FFMA 1 /* CUDA-core fp32 implicit GEMM, NHWC f32 in/out */
 #define TMX_ALGO_TC 2   /* tcgen05 bf16x3 implicit GEMM, SPLIT_BF16_HALO in; K chunk = 64/32/16 channels by Cin */
@@ -120,6 +124,9 @@ int tmx_conv2d_fwd(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_io_t
  * Cin_pad (a multiple of 16), e.g. the 513-channel minibatch-stddev output; K index = tap*Cin_pad + c. */
 int tmx_conv_weights_prepare(tmx_handle_t h, const float* w_hwio, float wscale, int k, int Cin, int Cin_pad, int Cout,
                              int up2_phase, uint16_t* w_hi, uint16_t* w_lo, tmx_stream_t s);
+/* XMERGE layout for 16-channel 3x3 layers: [Cout][3 (u)][64], K index u*64 + v*16 + c for v < 3, zeros for v == 3. */
+int tmx_conv_weights_prepare_xmerge(tmx_handle_t h, const float* w_hwio, float wscale, int Cout, uint16_t* w_hi,
+                                    uint16_t* w_lo, tmx_stream_t s);
 
 /* NHWC f32 -> SPLIT_BF16_HALO (tf.pad REFLECT of networks.py:55 materialised; replicate != 0: edge-clamped halo). */
 int tmx_split_halo_pack(tmx_handle_t h, const float* x_nhwc, uint16_t* hi, uint16_t* lo, int N, int H, int W, int C,

@@ -142,10 +142,19 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* tfull_bar = empty_bar + S;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* rgb_smem = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes + 256);   // [GW+1][4]: ToRGB weights + bias
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int cchunks = p.Cin / KC;
+  if (p.y_rgb != nullptr && threadIdx.x >= 128) {
+    for (int e = threadIdx.x - 128; e < (GW + 1) * 4; e += 128) {   // visible after the setup barrier below
+      const int c = e >> 2, o = e & 3;
+      float val = 0.f;
+      if (o < p.rgb_c) val = c < GW ? __ldg(p.rgb_w + c * p.rgb_c + o) : (p.rgb_b ? __ldg(p.rgb_b + o) : 0.f);
+      rgb_smem[e] = val;
+    }
+  }
   const int ksteps = p.taps * cchunks;
 
   if (warp == 0 && lane == 0) {
@@ -302,6 +311,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int CL = p.cout_log;
     const int lo_edge = p.halo_rep ? 0 : 1;                // source row/col copied into halo slot 0
     const int hi_off = p.halo_rep ? 1 : 2;                 // ... and (size - hi_off) into slot size+1
+    const bool has_bias = p.bias != nullptr;
+    const float slope = p.lrelu ? p.alpha : 1.f;
+    const float4* rgb_s = reinterpret_cast<const float4*>(rgb_smem);
     int it = 0;
     for (int item = cta_lin; item < p.num_items; item += cta_cnt, ++it) {
       int tile, part, parts;
@@ -352,13 +364,24 @@ __global__ void __launch_bounds__(kThreads, 1)
             oy = 2 * y + (ph >> 1);
             ox = 2 * x + (ph & 1);
           }
+          // bias as 128-bit loads, leaky-ReLU branch-free (slope 1 == identity: max(f, f))
           float v[GW];
+          if (has_bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + cbase);
 #pragma unroll
-          for (int j = 0; j < GW; ++j) {
-            float f = __uint_as_float(acc[j]) + (p.bias ? __ldg(p.bias + cbase + j) : 0.f);
-            if (p.lrelu) f = fmaxf(f * p.alpha, f);
-            v[j] = f;
+            for (int j = 0; j < GW / 4; ++j) {
+              const float4 b4 = __ldg(bp + j);
+              v[4 * j] = __uint_as_float(acc[4 * j]) + b4.x;
+              v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b4.y;
+              v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b4.z;
+              v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < GW; ++j) v[j] = __uint_as_float(acc[j]);
           }
+#pragma unroll
+          for (int j = 0; j < GW; ++j) v[j] = fmaxf(v[j] * slope, v[j]);
           const long long pix = p.lin ? mlin : ((long long)n * Hl + oy) * Wl + ox;
           if (p.has_res) {
 #pragma unroll
@@ -376,19 +399,6 @@ __global__ void __launch_bounds__(kThreads, 1)
             for (int j = 0; j < GW / 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
           if (p.y_hi != nullptr) {
-            // target rows / cols of the split planes: interior + halo slots this pixel feeds
-            int rows[4], cols[4], nrows = 0, ncols = 0;
-            const int reps = p.up2_out ? 2 : 1;
-            for (int d = 0; d < reps; ++d) {
-              const int Y = p.up2_out ? 2 * oy + d : oy;
-              rows[nrows++] = Y + 1;
-              if (Y == lo_edge) rows[nrows++] = 0;
-              if (Y == Ho - hi_off) rows[nrows++] = Ho + 1;
-              const int X = p.up2_out ? 2 * ox + d : ox;
-              cols[ncols++] = X + 1;
-              if (X == lo_edge) cols[ncols++] = 0;
-              if (X == Wo - hi_off) cols[ncols++] = Wo + 1;
-            }
             uint32_t ph[GW / 2], pl[GW / 2];
 #pragma unroll
             for (int j = 0; j < GW / 2; ++j) {
@@ -398,31 +408,65 @@ __global__ void __launch_bounds__(kThreads, 1)
               ph[j] = h0 | (h1 << 16);
               pl[j] = l0 | (l1 << 16);
             }
-            for (int a = 0; a < nrows; ++a) {
-              for (int b = 0; b < ncols; ++b) {
-                const long long o = (((long long)n * Hp + rows[a]) * Wp + cols[b]) * CL + cbase;
-                uint4* oh = reinterpret_cast<uint4*>(p.y_hi + o);
-                uint4* ol = reinterpret_cast<uint4*>(p.y_lo + o);
+            auto store_px = [&](int prow, int pcol) {
+              const long long o = (((long long)n * Hp + prow) * Wp + pcol) * CL + cbase;
+              uint4* oh = reinterpret_cast<uint4*>(p.y_hi + o);
+              uint4* ol = reinterpret_cast<uint4*>(p.y_lo + o);
 #pragma unroll
-                for (int j = 0; j < GW / 8; ++j) {
-                  oh[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-                  ol[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+              for (int j = 0; j < GW / 8; ++j) {
+                oh[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+                ol[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+              }
+            };
+            if (!p.up2_out) {
+              // interior slot plus at most one halo row and one halo column this pixel feeds (H, W >= 2)
+              const int r0 = oy + 1, c0 = ox + 1;
+              const int r1 = oy == lo_edge ? 0 : (oy == Ho - hi_off ? Ho + 1 : -1);
+              const int c1 = ox == lo_edge ? 0 : (ox == Wo - hi_off ? Wo + 1 : -1);
+              store_px(r0, c0);
+              if (r1 >= 0) store_px(r1, c0);
+              if (c1 >= 0) {
+                store_px(r0, c1);
+                if (r1 >= 0) store_px(r1, c1);
+              }
+            } else {
+              // x2 nearest upsampling of the written planes: 2x2 copies, each with its own halo slots
+              for (int d = 0; d < 2; ++d) {
+                const int Y = 2 * oy + d;
+                const int r1 = Y == lo_edge ? 0 : (Y == Ho - hi_off ? Ho + 1 : -1);
+                for (int e = 0; e < 2; ++e) {
+                  const int X = 2 * ox + e;
+                  const int c1 = X == lo_edge ? 0 : (X == Wo - hi_off ? Wo + 1 : -1);
+                  store_px(Y + 1, X + 1);
+                  if (r1 >= 0) store_px(r1, X + 1);
+                  if (c1 >= 0) {
+                    store_px(Y + 1, c1);
+                    if (r1 >= 0) store_px(r1, c1);
+                  }
                 }
               }
             }
           }
           if (p.y_rgb != nullptr) {
-            // ToRGB 1x1 head on the fp32 activations of this pixel (host guarantees CL == GW)
-            float rgb[4] = {0.f, 0.f, 0.f, 0.f};
+            // ToRGB 1x1 head on the fp32 activations of this pixel (host guarantees CL == GW, rgb_c <= 4);
+            // the head's weights were staged in shared memory as [c][4] at kernel start
+            float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
 #pragma unroll
             for (int j = 0; j < GW; ++j) {
-              for (int o = 0; o < p.rgb_c; ++o) rgb[o] = fmaf(v[j], __ldg(p.rgb_w + (cbase + j) * p.rgb_c + o), rgb[o]);
+              const float4 w4 = rgb_s[j];
+              r0 = fmaf(v[j], w4.x, r0);
+              r1 = fmaf(v[j], w4.y, r1);
+              r2 = fmaf(v[j], w4.z, r2);
+              r3 = fmaf(v[j], w4.w, r3);
             }
+            const float4 b4 = rgb_s[GW];
+            const float rr[4] = {fmaf(r0, p.rgb_wscale, b4.x), fmaf(r1, p.rgb_wscale, b4.y),
+                                 fmaf(r2, p.rgb_wscale, b4.z), fmaf(r3, p.rgb_wscale, b4.w)};
             const long long hw = (long long)Hl * Wl;
-            for (int o = 0; o < p.rgb_c; ++o) {
-              float f = rgb[o] * p.rgb_wscale + (p.rgb_b ? __ldg(p.rgb_b + o) : 0.f);
-              if (p.rgb_tanh) f = tanhf(f);
-              p.y_rgb[((long long)n * p.rgb_c + o) * hw + (long long)oy * Wl + ox] = f;
+            float* dst = p.y_rgb + (long long)n * p.rgb_c * hw + (long long)oy * Wl + ox;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              if (o < p.rgb_c) dst[o * hw] = p.rgb_tanh ? tanhf(rr[o]) : rr[o];
             }
           }
         }
@@ -451,9 +495,12 @@ CUtensorMapSwizzle swizzle_of(int kc) {
   return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+// xwin > 1: X-MERGED view for thin layers - the innermost dimension spans `xwin` consecutive pixels (xwin*C
+// channels), while the pixel stride stays C: overlapping rows, so that ONE box row of 128 B carries the three
+// horizontal taps of a 16-channel layer (plus one zero-weighted neighbour) instead of three 32-B rows.
 int encode_act_map(tmx_handle_t h, CUtensorMap* m, const uint16_t* base, int N, int Hp, int Wp, int C, int kc, int bw,
-                   int bh, int bn) {
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
+                   int bh, int bn, int xwin = 1) {
+  cuuint64_t dims[4] = {(cuuint64_t)C * xwin, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
   cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -620,6 +667,13 @@ int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_i
               "tmx_conv2d_fwd[TC]: Cin=%d and Cout=%d must be multiples of 16", d->Cin, d->Cout);
   int kc = d->Cin % 64 == 0 ? 64 : (d->Cin % 32 == 0 ? 32 : 16);
   if (kc > kc_max) kc = kc_max;
+  // thin layers: three horizontal taps of a 16-channel input in one 128-B operand row (weights prepared with
+  // tmx_conv_weights_prepare xmerge layout [Cout][3][64]); the caller opts in because the plane buffers must be
+  // readable (and finite) 3 pixels past their end
+  const bool xmerge = (d->flags & TMX_CONV_XMERGE) != 0;
+  TMX_REQUIRE(!xmerge || (d->Cin == 16 && d->k == 3 && !phase), TMX_ERR_SHAPE,
+              "tmx_conv2d_fwd[TC]: XMERGE needs Cin == 16, k == 3, no UP2_IN");
+  if (xmerge) kc = 64;
   // stored (GEMM-side) geometry
   const int Hs = phase ? d->H / 2 : d->H, Ws = phase ? d->W / 2 : d->W;
   const int Ng = phase ? 4 * d->Cout : d->Cout;  // GEMM N
@@ -642,11 +696,11 @@ int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_i
   p.N = d->N;
   p.H = Hs;
   p.W = Ws;
-  p.Cin = d->Cin;
+  p.Cin = xmerge ? 64 : d->Cin;          // contraction length per (merged) tap
   p.Cout = Ng;
-  p.k = d->k;
-  p.taps = d->k * d->k;
-  p.pad_off = 1 - d->k / 2;
+  p.k = xmerge ? 1 : d->k;               // merged: tap index == vertical tap u, no horizontal shift
+  p.taps = xmerge ? 3 : d->k * d->k;
+  p.pad_off = xmerge ? 0 : 1 - d->k / 2;
   p.bw = gcd_pow2(Ws, 32);
   p.bh = gcd_pow2(Hs, kTileM / p.bw);
   p.bn = kTileM / (p.bw * p.bh);
@@ -678,9 +732,10 @@ int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_i
 
   CUtensorMap maps[6];
   int rc;
-  if ((rc = encode_act_map(h, &maps[0], io->x_hi, d->N, Hs + 2, Ws + 2, d->Cin, kc, p.bw, p.bh, p.bn))) return rc;
-  if ((rc = encode_act_map(h, &maps[1], io->x_lo, d->N, Hs + 2, Ws + 2, d->Cin, kc, p.bw, p.bh, p.bn))) return rc;
-  return schedule_and_launch(h, p, maps, io->w_hi, io->w_lo, tiles_m, Ng, d->Cin, bnc, kc, gw, st);
+  const int xw = xmerge ? 4 : 1;
+  if ((rc = encode_act_map(h, &maps[0], io->x_hi, d->N, Hs + 2, Ws + 2, d->Cin, kc, p.bw, p.bh, p.bn, xw))) return rc;
+  if ((rc = encode_act_map(h, &maps[1], io->x_lo, d->N, Hs + 2, Ws + 2, d->Cin, kc, p.bw, p.bh, p.bn, xw))) return rc;
+  return schedule_and_launch(h, p, maps, io->w_hi, io->w_lo, tiles_m, Ng, p.Cin, bnc, kc, gw, st);
 }
 
 // ---------------------------------------------------------------- data gradient (LIN mode)

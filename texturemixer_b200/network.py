@@ -339,15 +339,18 @@ class Network:
             o._prepared[key] = ent
         return ent[0]
 
-    def prepared_weights(self, var, wscale, k, cin, cout, up2_phase=False, cin_pad=None):
+    def prepared_weights(self, var, wscale, k, cin, cout, up2_phase=False, cin_pad=None, xmerge=False):
         """Cached bf16 hi/lo planes of a conv weight for the tensor-core kernel
         (sub-pixel planes when the conv reads through upscale2d); recomputed
         when any variable of the owning network changed."""
         o = self._owner()
-        key = (var.name, float(wscale), bool(up2_phase), cin_pad)
+        key = (var.name, float(wscale), bool(up2_phase), cin_pad, bool(xmerge))
         ent = o._prepared.get(key)
         if ent is None or ent[2] != o._version:
-            hi, lo = self.rt.prepare_weights(var.value, wscale, k, cin, cout, up2_phase=up2_phase, cin_pad=cin_pad)
+            if xmerge:
+                hi, lo = self.rt.prepare_weights_xmerge(var.value, wscale, cout)
+            else:
+                hi, lo = self.rt.prepare_weights(var.value, wscale, k, cin, cout, up2_phase=up2_phase, cin_pad=cin_pad)
             ent = (hi, lo, o._version)
             o._prepared[key] = ent
         return ent[0], ent[1]

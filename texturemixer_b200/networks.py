@@ -76,7 +76,8 @@ def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=Fals
                                   % (cin, xa.c))
     prepared = None
     if algo != 1:  # tensor-core path: cached bf16 hi/lo weight planes (zero rows for padded input channels)
-        prepared = ctx.net.prepared_weights(w, ws, kernel, cin, fmaps, up2_phase=up2, cin_pad=xa.c)
+        prepared = ctx.net.prepared_weights(w, ws, kernel, cin, fmaps, up2_phase=up2, cin_pad=xa.c,
+                                            xmerge=rt.use_xmerge(xa.c, kernel, up2))
     res = None if residual is None else rt.split_unpack(_act_of(residual)).f32
     head = None
     rec = ctx.tape is not None

@@ -98,13 +98,21 @@ class Runtime:
                                              self.stream()), 'tmx_nhwc_to_nchw')
         return out
 
+    def planes(self, n, hp, wp, c):
+        """One bf16 plane [n,hp,wp,c] with 64 zeroed elements of slack behind it: the X-MERGED operand view of the
+        16-channel layers (TMX_CONV_XMERGE) reads up to 3 pixels past the last one (times a zero weight)."""
+        numel = n * hp * wp * c
+        buf = torch.empty(numel + 64, dtype=torch.bfloat16, device=self.device)
+        buf[numel:].zero_()
+        return buf[:numel].view(n, hp, wp, c)
+
     def split_pack(self, act, halo='reflect'):
         """Make sure `act` carries split planes with the requested halo kind."""
         if act.hi is None or act.halo != halo:
             if act.f32 is None:
                 self.split_unpack(act)
-            act.hi = self.empty(act.n, act.h + 2, act.w + 2, act.c, dtype=torch.bfloat16)
-            act.lo = self.empty(act.n, act.h + 2, act.w + 2, act.c, dtype=torch.bfloat16)
+            act.hi = self.planes(act.n, act.h + 2, act.w + 2, act.c)
+            act.lo = self.planes(act.n, act.h + 2, act.w + 2, act.c)
             act.halo = halo
             _lib.check(self.lib.tmx_split_halo_pack(self.handle, _ptr(act.f32), _ptr(act.hi), _ptr(act.lo), act.n,
                                                     act.h, act.w, act.c, int(halo == 'replicate'), self.stream()),
@@ -137,6 +145,16 @@ class Runtime:
         if k * k * cin >= 144 or (k == 1 and cin >= 64):
             return _lib.ALGO_TC
         return _lib.ALGO_FFMA
+
+    def use_xmerge(self, cin, k, up2):
+        return cin == 16 and k == 3 and not up2 and not os.environ.get('TMX_NO_XMERGE')
+
+    def prepare_weights_xmerge(self, w, wscale, cout):
+        hi = self.empty(cout, 192, dtype=torch.bfloat16)
+        lo = self.empty(cout, 192, dtype=torch.bfloat16)
+        _lib.check(self.lib.tmx_conv_weights_prepare_xmerge(self.handle, _ptr(w), float(wscale), cout, _ptr(hi),
+                                                            _ptr(lo), self.stream()), 'tmx_conv_weights_prepare_xmerge')
+        return hi, lo
 
     def prepare_weights(self, w, wscale, k, cin, cout, up2_phase=False, cin_pad=None):
         rows = cout * 4 if up2_phase else cout
@@ -183,6 +201,13 @@ class Runtime:
         else:
             self.split_pack(x, 'replicate' if up2 else 'reflect')
             io.x_hi, io.x_lo = x.hi.data_ptr(), x.lo.data_ptr()
+            xmerge = self.use_xmerge(cin, k, up2) and x.hi.untyped_storage().nbytes() >= (x.hi.numel() + 64) * 2
+            if xmerge:
+                flags |= _lib.CONV_XMERGE
+                if prepared is None or prepared[0].shape[1] != 192:
+                    prepared = self.prepare_weights_xmerge(w, wscale, cout)
+            elif prepared is not None and prepared[0].shape[1] == 192 and k * k * cin != 192:
+                prepared = None          # X-MERGED planes handed in, but this call cannot use them
             if prepared is None:
                 prepared = self.prepare_weights(w, wscale, k, cin, cout, up2_phase=up2)
             keep.append(prepared)
@@ -201,8 +226,8 @@ class Runtime:
                 io.y_f32 = out.f32.data_ptr()
             if want_split:
                 ho, wo = (h * 2, w_ * 2) if up2_out else (h, w_)
-                out.hi = self.empty(x.n, ho + 2, wo + 2, cout, dtype=torch.bfloat16)
-                out.lo = self.empty(x.n, ho + 2, wo + 2, cout, dtype=torch.bfloat16)
+                out.hi = self.planes(x.n, ho + 2, wo + 2, cout)
+                out.lo = self.planes(x.n, ho + 2, wo + 2, cout)
                 out.halo = halo_out
                 io.y_hi, io.y_lo = out.hi.data_ptr(), out.lo.data_ptr()
                 if up2_out:
