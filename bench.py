@@ -276,8 +276,12 @@ def run_ours(args):
 
 # ------------------------------------------------------------------ train step (BASELINE configs[2] / [4])
 TRAIN_BATCH = 32
-TRAIN_GFLOP_PER_SAMPLE = 908.9     # SURVEY Appendix C (gram off, shared forwards); as executed here the E/G forwards
-#                                    of the critic phase are recomputed, so the device does ~1 044 GFLOP per sample
+# Algorithmic GFLOP per sample of one train step (gram off, E/G forwards shared between phases):
+#   whole canvases : E 5.6 + G 38.7 + three D 51.2 + G_fcn 7 evaluation units x 116.2                  = 908.9
+#   crop-aware     : G_fcn decodes the 64x64 latent window each random_crop depends on instead of the 96x96 canvas
+#                    (identical results, SURVEY Appendix C note): 8 units (the critics' interpolation fake no longer
+#                    shares the E/G image) x 116.2 x (64/96)^2 = 413.2, + 95.5                             = 508.7
+TRAIN_GFLOP = {True: 508.7, False: 908.9}
 
 
 def run_train(args):
@@ -293,7 +297,11 @@ def run_train(args):
         raise RuntimeError('bench.py needs a B200; there is no CPU path')
     torch.cuda.set_device(local)
     parallel.init_from_env()
-    tr = Trainer(seed=1000, device=local)
+    from texturemixer_b200.train import default_config
+    cfg = default_config()
+    cfg['crop_aware'] = not args.whole_canvas
+    TRAIN_GFLOP_PER_SAMPLE = TRAIN_GFLOP[cfg['crop_aware']]
+    tr = Trainer(cfg, seed=1000, device=local)
     rt, dev = tr.rt, tr.rt.device
     rng = np.random.RandomState(1000 + rank)
     np.random.seed(1000 + rank)
@@ -358,6 +366,8 @@ def run_train(args):
                        'batch_per_gpu': TRAIN_BATCH, 'global_batch': TRAIN_BATCH * world,
                        'l2': 'working set per step (>20 GB) far exceeds the 126 MB L2',
                        'parallelism': 'dp%d: one flat-bucket NCCL all-reduce per network per optimizer' % world,
+                       'g_fcn': 'crop-aware: decodes the 64x64 latent window of each random_crop (identical results)'
+                       if cfg['crop_aware'] else 'whole 96x96 canvases decoded',
                        'gflop_per_sample': TRAIN_GFLOP_PER_SAMPLE},
             'e2e': {'value': samples / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': int(reals_h.numel() * 4),
                     'd2h_bytes_per_step': 4 * len(host_rep), 'api': 'Trainer.step(reals) with host reals + loss report'},
@@ -382,6 +392,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--device-only', action='store_true', help='only the device-resident loop (profiling runs)')
+    ap.add_argument('--whole-canvas', action='store_true',
+                    help='train_step: decode the whole 3x3 canvases in G_fcn instead of the crop windows')
     ap.add_argument('--workload', default='gen_fwd', choices=['gen_fwd', 'train_step'],
                     help='gen_fwd = BASELINE configs[1] (headline); train_step = configs[2]/[4]: full train step, '
                          'batch 32 per GPU, NCCL gradient all-reduce')

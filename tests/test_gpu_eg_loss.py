@@ -124,3 +124,48 @@ def test_critic_wgangp_double_backward_vs_autograd(alpha, monkeypatch):
             worst = (name, err)
         assert err <= gtol, (name, err)
     print('alpha', alpha, 'critic worst variable gradient rel-L2', worst)
+
+
+@pytest.mark.parametrize('crops', [((0, 0), (255, 255)), ((57, 131), (200, 56)), ((130, 3), (128, 129))])
+def test_crop_aware_g_fcn_equals_whole_canvas(crops):
+    """Decoding only the latent window each random_crop depends on (loss.crop_window; SURVEY Appendix C note) against
+    decoding the whole 3x3 canvas, both on the device: same crops, same loss terms, same variable gradients up to the
+    summation order of the weight-gradient split-K (the per-pixel arithmetic is identical)."""
+    from texturemixer_b200 import loss as dev_loss
+    from texturemixer_b200.network import Network
+    rng = np.random.RandomState(11)
+    n, sh, sw = 4, 3, 3
+    names = ['E_zg', 'E_zl', 'G', 'D_rec', 'D_interp', 'D_blend']
+    funcs = dict(E_zg='E_zg', E_zl='E_zl', G='G_res', D_rec='D_patch', D_interp='D_patch', D_blend='D_patch')
+    nets = {k: Network(k, func='networks.' + funcs[k], seed=20 + i, num_channels=3, resolution=128,
+                       **R.CONFIG[funcs[k]]) for i, k in enumerate(names)}
+    for net in nets.values():
+        for vn, v in net.trainables.items():
+            if vn.endswith('/bias'):
+                net.set_var(vn, 0.1 * rng.randn(*v.shape).astype(np.float32))
+    G_fcn = Network('G', func='networks.G_res', reuse=True, share_vars_with=nets['G'], num_channels=3, resolution=128,
+                    scale_h=sh, scale_w=sw, **R.CONFIG['G_res'])
+    reals = torch.from_numpy(rng.uniform(-1, 1, (n, 3, 128, 128)).astype(np.float32)).cuda()
+    np.random.seed(5)
+    idx = I.sample_schedule_indices(n, latent_res=32, scale_h=sh, scale_w=sw)
+    mix = torch.from_numpy(rng.uniform(0, 1, (n, 1, 1, 1)).astype(np.float32)).cuda()
+    out = {}
+    for aware in (False, True):
+        fwd = dev_loss.EGForward(nets['E_zg'], nets['E_zl'], nets['G'], G_fcn, reals, idx, mix, sh, sw,
+                                 crop_interp=crops[0] if aware else None, crop_blend=crops[1] if aware else None)
+        assert (fwd.win['interp'] is not None) == aware and (tuple(fwd.interp.shape[2:]) == (256, 256)) == aware
+        imgs = (fwd.crop('interp', crops[0]).clone(), fwd.crop('blend', crops[1]).clone())
+        grads = {k: torch.zeros_like(nets[k].flat) for k in ('E_zg', 'E_zl', 'G')}
+        rep = dev_loss.EG_backward(fwd, nets['D_rec'], nets['D_interp'], nets['D_blend'], crops[0], crops[1], grads)
+        torch.cuda.synchronize()
+        out[aware] = (imgs, grads, {k: float(v.reshape(-1)[0]) for k, v in rep.items()})
+    for a, b in zip(out[False][0], out[True][0]):
+        assert float((a - b).abs().max()) <= 1e-6              # same per-pixel arithmetic (expected: bit-identical)
+        print('crop pixels bit-identical:', bool(torch.equal(a, b)))
+    for k, v in out[False][2].items():
+        assert abs(out[True][2][k] - v) <= 1e-5 * max(1.0, abs(v)), k
+    for k in ('E_zg', 'E_zl', 'G'):
+        a, b = out[False][1][k].double(), out[True][1][k].double()
+        assert float((a - b).norm() / a.norm()) <= 1e-5, k
+    with pytest.raises(ValueError):
+        fwd.crop('interp', (crops[0][0] + 1, crops[0][1]))      # a window serves exactly the crop it was planned for

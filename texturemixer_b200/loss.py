@@ -52,6 +52,76 @@ def _dev_idx(rt, a):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(rt.device)
 
 
+G_CONTEXT = 14   # latent pixels of context one output pixel of G_res sees on each side: 12 convs at the latent
+#                  resolution (networks.py:427-446) + 2 at 2x + 2 at 4x (:447-457) = 12 + 1 + 0.5, rounded up
+
+
+def crop_window(yx, res, lat, H, W):
+    """Latent window (oy, ox, wh, ww) of the H x W canvas outside of which nothing reaches the res x res image crop
+    at pixel offset yx (SURVEY Appendix C note).  D only ever sees `random_crop(G_fcn(canvas))` (loss.py:198,241), the
+    offset is drawn before decoding and every layer of G_res is local, so decoding just the window gives the same crop
+    pixels and - gradients being zero outside the crop's cone of dependence - the same gradients; where the window
+    ends inside the canvas its REFLECT padding differs from the true neighbours, which perturbs only pixels within
+    G_CONTEXT of that edge, and those are outside the cone by construction.  None = whole canvas."""
+    up = res // lat
+    if up != 4 or res % lat:
+        return None
+    need = lat + 1 + 2 * G_CONTEXT                # an unaligned crop touches lat + 1 latent pixels
+
+    def axis(c0, L):
+        win = -(-need // lat) * lat               # a whole number of tiles: G_fcn at a smaller (scale_h, scale_w)
+        if win >= L:
+            return 0, L
+        return min(max(c0 // up - G_CONTEXT, 0), L - win), win
+    oy, wh = axis(yx[0], H)
+    ox, ww = axis(yx[1], W)
+    if wh == H and ww == W:
+        return None
+    return oy, ox, wh, ww
+
+
+def _win(x, win):
+    if win is None:
+        return x
+    oy, ox, wh, ww = win
+    return x[:, :, oy:oy + wh, ox:ox + ww].contiguous()
+
+
+def _embed(d, win, H, W):
+    """Adjoint of `_win`: the window gradient inside a zero canvas."""
+    if win is None:
+        return d
+    oy, ox, wh, ww = win
+    full = torch.zeros(d.shape[0], d.shape[1], H, W, dtype=torch.float32, device=d.device)
+    full[:, :, oy:oy + wh, ox:ox + ww].copy_(d)
+    return full
+
+
+def fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, ih_f, iw_f, win, blend=None):
+    """The latent canvases G_fcn decodes (loss.py:176-186 interpolation; :218-239 blend when `blend` =
+    (ih_b, iw_b, t)), restricted to `win`."""
+    wh, ww = (H, W) if win is None else win[2:]
+    zg_c = _tile_code(rt, zg_mu, wh, ww)
+    zl_c = _win(rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[ih_f], idx_w=[iw_f],
+                                pin_rows=pins[0], pin_cols=pins[1]), win)
+    if blend is None:
+        return zg_c, zl_c
+    ih_b, iw_b, t = blend
+    # tf.reverse(axis=[0]) of the sources is folded into the gather (src_reverse)
+    zg_r = rt.latent_blend([zg_mu.contiguous()], wh, ww, _lib.BLEND_COPY, src_reverse=1)
+    zl_r = _win(rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[ih_b], idx_w=[iw_b],
+                                pin_rows=pins[0], pin_cols=pins[1], src_reverse=1), win)
+    bzg = rt.latent_blend([zg_r, zg_c], wh, ww, _lib.BLEND_LERP, t=t)      # lerp(reverse, forward, t), loss.py:238
+    bzl = rt.latent_blend([zl_r, zl_c], wh, ww, _lib.BLEND_LERP, t=t)
+    return bzg, bzl
+
+
+def fcn_scale(canvas, lat):
+    """G_fcn's (scale_h, scale_w) for a canvas or a window of one: the same variables decode any whole number of
+    tiles (the reference builds one G_fcn per scale over the shared scope, run.py:273, util_scripts.py:380-384)."""
+    return dict(scale_h=canvas.shape[2] // lat, scale_w=canvas.shape[3] // lat)
+
+
 def _crop_adjoint(dcrop, full_hw, yx):
     """Adjoint of random_crop (loss.py:78-90): zeros outside the window (pure data movement)."""
     n, c, h, w = dcrop.shape
@@ -66,11 +136,15 @@ class EGForward:
     one step (run.py:511-512), so the critic phase can reuse `rec` and `interp` as its fakes."""
 
     def __init__(self, E_zg, E_zl, G, G_fcn, reals, idx, mixing_factors, scale_h=3, scale_w=3, need_interp=True,
-                 need_blend=True):
+                 need_blend=True, crop_interp=None, crop_blend=None):
+        """crop_interp / crop_blend: the (y, x) offsets the E/G loss will crop at; when given, G_fcn decodes only the
+        latent window those crops depend on (`crop_window`) - same crop pixels, same gradients, 44 % of the work at
+        the reference's 3x3 canvases.  None decodes the whole canvas."""
         rt = self.rt = Runtime.get(reals.device)
         self.nets = (E_zg, E_zl, G, G_fcn)
         self.reals, self.scale = reals, (scale_h, scale_w)
         self.n = n = reals.shape[0]
+        res = reals.shape[2]
         self.t_zg, self.t_zl, self.t_rec, self.t_int, self.t_bl = [], [], [], [], []
         self.zg_mu, _ = E_zg.get_output_for(reals, tape=self.t_zg)
         self.zl_mu, _ = E_zl.get_output_for(reals, tape=self.t_zl)
@@ -80,28 +154,37 @@ class EGForward:
         self.pins = pins = interp._corner_pins(scale_h, scale_w)
         self.rec = G.get_output_for(_tile_code(rt, zg_mu, lat, lat), zl_mu, tape=self.t_rec)
         self.interp = self.blend = None
+        self.win = {'interp': None if crop_interp is None else crop_window(crop_interp, res, lat, H, W),
+                    'blend': None if crop_blend is None else crop_window(crop_blend, res, lat, H, W)}
+        self.planned = {'interp': crop_interp, 'blend': crop_blend}
         if need_interp or need_blend:
             self.ih_f, self.iw_f = _dev_idx(rt, idx['h_forward']), _dev_idx(rt, idx['w_forward'])
-            zg_c = _tile_code(rt, zg_mu, H, W)
-            zl_c = rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[self.ih_f], idx_w=[self.iw_f],
-                                   pin_rows=pins[0], pin_cols=pins[1])
         if need_interp:
-            self.interp = G_fcn.get_output_for(zg_c, zl_c, tape=self.t_int)
+            zg_c, zl_c = fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, self.ih_f, self.iw_f, self.win['interp'])
+            self.interp = G_fcn.get_output_for(zg_c, zl_c, tape=self.t_int, **fcn_scale(zl_c, lat))
         if need_blend:
             self.ih_b, self.iw_b = _dev_idx(rt, idx['h_backward']), _dev_idx(rt, idx['w_backward'])
-            # tf.reverse(axis=[0]) of the sources is folded into the gather (src_reverse)
-            zg_r = rt.latent_blend([zg_mu.contiguous()], H, W, _lib.BLEND_COPY, src_reverse=1)
-            zl_r = rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[self.ih_b], idx_w=[self.iw_b],
-                                   pin_rows=pins[0], pin_cols=pins[1], src_reverse=1)
             self.t = t = mixing_factors.reshape(-1).contiguous()
-            bzg = rt.latent_blend([zg_r, zg_c], H, W, _lib.BLEND_LERP, t=t)      # lerp(reverse, forward, t), loss.py:238
-            bzl = rt.latent_blend([zl_r, zl_c], H, W, _lib.BLEND_LERP, t=t)
-            self.blend = G_fcn.get_output_for(bzg, bzl, tape=self.t_bl)
+            bzg, bzl = fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, self.ih_f, self.iw_f, self.win['blend'],
+                                    blend=(self.ih_b, self.iw_b, t))
+            self.blend = G_fcn.get_output_for(bzg, bzl, tape=self.t_bl, **fcn_scale(bzl, lat))
+
+    def window_offset(self, which, yx):
+        """Pixel offset of crop `yx` inside the decoded image of `which` (== yx when the whole canvas was decoded)."""
+        win = self.win[which]
+        if win is None:
+            return yx
+        if tuple(yx) != tuple(self.planned[which]):
+            raise ValueError('%s was decoded for the crop at %r only (crop-aware G_fcn); asked for %r'
+                             % (which, self.planned[which], yx))
+        up = self.reals.shape[2] // self.lat
+        return yx[0] - up * win[0], yx[1] - up * win[1]
 
     def crop(self, which, yx):
         img = self.interp if which == 'interp' else self.blend
         res = self.reals.shape[2]
-        return img[:, :, yx[0]:yx[0] + res, yx[1]:yx[1] + res].contiguous()
+        y0, x0 = self.window_offset(which, yx)
+        return img[:, :, y0:y0 + res, x0:x0 + res].contiguous()
 
 
 def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, rec_G_weight=1.0, pixel_weight=200.0,
@@ -135,28 +218,32 @@ def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, r
         s = D_interp.get_output_for(fwd.crop('interp', crop_interp), tape=t_d)
         report['interp_G'] = _row_sum(rt, s, 1, n, scale=-interp_G_weight * inv_n)
         (dcr,) = backward(D_interp, t_d, [torch.full_like(s, -interp_G_weight * inv_n)], None, param_grads=False)
-        dzg_c, dzl_c = backward(G_fcn, fwd.t_int, [_crop_adjoint(dcr, fwd.interp.shape[2:], crop_interp)], grads['G'])
-        _row_sum(rt, dzg_c, n * c, H * W, out=dzg, accumulate=True)
-        _gather_bwd(rt, dzl_c, dzl, fwd.ih_f, fwd.iw_f, pins)
+        dzg_c, dzl_c = backward(G_fcn, fwd.t_int, [_crop_adjoint(dcr, fwd.interp.shape[2:],
+                                                                 fwd.window_offset('interp', crop_interp))], grads['G'])
+        _row_sum(rt, dzg_c, n * c, dzg_c.shape[2] * dzg_c.shape[3], out=dzg, accumulate=True)
+        _gather_bwd(rt, _embed(dzl_c, fwd.win['interp'], H, W), dzl, fwd.ih_f, fwd.iw_f, pins)
     if blend_interp_G_weight > 0:
         t_d = []
         t = fwd.t
         s = D_blend.get_output_for(fwd.crop('blend', crop_blend), tape=t_d)
         report['blend_G'] = _row_sum(rt, s, 1, n, scale=-blend_interp_G_weight * inv_n)
         (dcr,) = backward(D_blend, t_d, [torch.full_like(s, -blend_interp_G_weight * inv_n)], None, param_grads=False)
-        dbzg, dbzl = backward(G_fcn, fwd.t_bl, [_crop_adjoint(dcr, fwd.blend.shape[2:], crop_blend)], grads['G'])
+        dbzg, dbzl = backward(G_fcn, fwd.t_bl, [_crop_adjoint(dcr, fwd.blend.shape[2:],
+                                                              fwd.window_offset('blend', crop_blend))], grads['G'])
         zero_c = torch.zeros_like(dbzg)
+        win = fwd.win['blend']
+        wh, ww = dbzg.shape[2:]
         # adjoint of lerp: d forward = t * d, d reverse = d - t * d   (same fp32 ops as autograd of a + (b - a) * t)
         for d, dsrc_kind in ((dbzg, 'zg'), (dbzl, 'zl')):
-            d_fwd = rt.latent_blend([zero_c, d.contiguous()], H, W, _lib.BLEND_LERP, t=t)
-            d_rev = rt.latent_blend([d.contiguous(), zero_c], H, W, _lib.BLEND_LERP, t=t)
+            d_fwd = rt.latent_blend([zero_c, d.contiguous()], wh, ww, _lib.BLEND_LERP, t=t)
+            d_rev = rt.latent_blend([d.contiguous(), zero_c], wh, ww, _lib.BLEND_LERP, t=t)
             if dsrc_kind == 'zg':
-                _row_sum(rt, d_fwd, n * c, H * W, out=dzg, accumulate=True)
-                tmp = _row_sum(rt, d_rev, n * c, H * W).view(n, c, 1, 1)
+                _row_sum(rt, d_fwd, n * c, wh * ww, out=dzg, accumulate=True)
+                tmp = _row_sum(rt, d_rev, n * c, wh * ww).view(n, c, 1, 1)
                 _gather_bwd(rt, tmp, dzg.view(n, c, 1, 1), None, None, (0, 0), reverse=True)
             else:
-                _gather_bwd(rt, d_fwd, dzl, fwd.ih_f, fwd.iw_f, pins)
-                _gather_bwd(rt, d_rev, dzl, fwd.ih_b, fwd.iw_b, pins, reverse=True)
+                _gather_bwd(rt, _embed(d_fwd, win, H, W), dzl, fwd.ih_f, fwd.iw_f, pins)
+                _gather_bwd(rt, _embed(d_rev, win, H, W), dzl, fwd.ih_b, fwd.iw_b, pins, reverse=True)
     backward(E_zl, fwd.t_zl, [dzl, None], grads['E_zl'], want_input_grads=False)
     backward(E_zg, fwd.t_zg, [dzg.view(n, c, 1, 1), None], grads['E_zg'], want_input_grads=False)
     return report
@@ -164,13 +251,14 @@ def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, r
 
 def EG_wgan(E_zg, E_zl, G, D_rec, G_fcn, D_interp, D_blend, reals, idx, crop_interp, crop_blend, mixing_factors,
             grads, scale_h=3, scale_w=3, rec_G_weight=1.0, pixel_weight=200.0, interp_G_weight=1.0,
-            blend_interp_G_weight=1.0):
+            blend_interp_G_weight=1.0, crop_aware=True):
     """One evaluation + differentiation of mean(EG_loss) (loss.py:105-259, run.py:321).
     reals: [N,3,R,R] fp32 device tensor in [-1,1]; idx: dict of int32 index vectors (interp.sample_schedule_indices);
     crop_*: (y, x); mixing_factors: [N,1,1,1] fp32 device tensor; grads: {'E_zg','E_zl','G'} -> flat gradient
     buffers (accumulated into).  Returns a dict of per-term batch means (device scalars)."""
     fwd = EGForward(E_zg, E_zl, G, G_fcn, reals, idx, mixing_factors, scale_h, scale_w,
-                    need_interp=interp_G_weight > 0, need_blend=blend_interp_G_weight > 0)
+                    need_interp=interp_G_weight > 0, need_blend=blend_interp_G_weight > 0,
+                    crop_interp=crop_interp if crop_aware else None, crop_blend=crop_blend if crop_aware else None)
     return EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, rec_G_weight, pixel_weight,
                        interp_G_weight, blend_interp_G_weight)
 

@@ -39,6 +39,7 @@ def default_config(train_size=128, fmap_base=1024, fmap_max=512, latent_channels
         D_interp=dict(fmap_base=fmap_base, fmap_max=fmap_max, latent_res=-1),
         D_blend=dict(fmap_base=fmap_base, fmap_max=fmap_max, latent_res=-1),
         opt=dict(beta1=0.0, beta2=0.99, epsilon=1e-8), lrate=0.0015, ema_beta=0.999,
+        crop_aware=True,      # G_fcn decodes only the latent window each random_crop depends on (loss.crop_window)
         loss=dict(rec_G_weight=1.0, pixel_weight=200.0, interp_G_weight=1.0, blend_interp_G_weight=1.0),
         levels=int(np.log2(latent_res)))
 
@@ -90,25 +91,21 @@ class Trainer:
         return dict(idx=idx, eg_crop_interp=crop(), eg_crop_blend=crop(), eg_mix=mix(), d_rec_gp=mix(),
                     d_interp_crop=crop(), d_interp_gp=mix(), d_blend_mix=mix(), d_blend_crop=crop(), d_blend_gp=mix())
 
-    # ------------------------------------------------------------------ fake image of the blend critic (no tape)
-    def _blend_fake(self, fwd, d):
-        """D_blend_wgangp draws its own mixing factors (loss.py:489), so its fake needs its own G_fcn forward; the
-        reconstruction and interpolation fakes are the images of the shared E/G forward."""
+    # ------------------------------------------------------------------ fake images of the canvas critics (no tape)
+    def _fcn_fake(self, fwd, which, yx, mix=None):
+        """Crop at `yx` of G_fcn's image of the interpolated (`which` = 'interp') or blended canvas, decoding only
+        the latent window the crop depends on (loss.crop_window).  D_blend_wgangp draws its own mixing factors
+        (loss.py:489), D_interp_wgangp its own crop offset (loss.py:398-400): neither can reuse the E/G images once
+        those are decoded crop-aware."""
         c, rt = self.cfg, self.rt
         res = c['resolution']
-        H, W, pins = fwd.H, fwd.W, fwd.pins
-        zg_mu, zl_mu = fwd.zg_mu, fwd.zl_mu
-        zg_c = rt.latent_blend([zg_mu.contiguous()], H, W, _lib.BLEND_COPY)
-        zl_c = rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[fwd.ih_f], idx_w=[fwd.iw_f],
-                               pin_rows=pins[0], pin_cols=pins[1])
-        zg_r = rt.latent_blend([zg_mu.contiguous()], H, W, _lib.BLEND_COPY, src_reverse=1)
-        zl_r = rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[fwd.ih_b], idx_w=[fwd.iw_b],
-                               pin_rows=pins[0], pin_cols=pins[1], src_reverse=1)
-        t = d['d_blend_mix'].reshape(-1).contiguous()
-        bzg = rt.latent_blend([zg_r, zg_c], H, W, _lib.BLEND_LERP, t=t)
-        bzl = rt.latent_blend([zl_r, zl_c], H, W, _lib.BLEND_LERP, t=t)
-        y0, x0 = d['d_blend_crop']
-        return self.G_fcn.get_output_for(bzg, bzl)[:, :, y0:y0 + res, x0:x0 + res].contiguous()
+        win = loss.crop_window(yx, res, fwd.lat, fwd.H, fwd.W) if c.get('crop_aware', True) else None
+        blend = None if which == 'interp' else (fwd.ih_b, fwd.iw_b, mix.reshape(-1).contiguous())
+        zg_c, zl_c = loss.fcn_canvases(rt, fwd.zg_mu, fwd.zl_mu, fwd.H, fwd.W, fwd.pins, fwd.ih_f, fwd.iw_f, win, blend)
+        up = res // fwd.lat
+        y0, x0 = yx if win is None else (yx[0] - up * win[0], yx[1] - up * win[1])
+        img = self.G_fcn.get_output_for(zg_c, zl_c, **loss.fcn_scale(zl_c, fwd.lat))
+        return img[:, :, y0:y0 + res, x0:x0 + res].contiguous()
 
     # ------------------------------------------------------------------ one step
     def step(self, reals, draws, lrate=None, phases=('D', 'EG', 'EMA')):
@@ -117,11 +114,18 @@ class Trainer:
         forward is evaluated ONCE (its variables do not change in between) and serves both phases."""
         report = {}
         c = self.cfg
+        ca = c.get('crop_aware', True)
         fwd = loss.EGForward(self.nets['E_zg'], self.nets['E_zl'], self.nets['G'], self.G_fcn, reals, draws['idx'],
-                             draws['eg_mix'], c['scale_h'], c['scale_w'])
+                             draws['eg_mix'], c['scale_h'], c['scale_w'],
+                             crop_interp=draws['eg_crop_interp'] if ca else None,
+                             crop_blend=draws['eg_crop_blend'] if ca else None)
         if 'D' in phases:
-            fakes = (('D_rec', fwd.rec, 'd_rec_gp'), ('D_interp', fwd.crop('interp', draws['d_interp_crop']), 'd_interp_gp'),
-                     ('D_blend', self._blend_fake(fwd, draws), 'd_blend_gp'))
+            if fwd.win['interp'] is None:           # whole canvas decoded: the interpolation image serves both phases
+                fake_interp = fwd.crop('interp', draws['d_interp_crop'])
+            else:
+                fake_interp = self._fcn_fake(fwd, 'interp', draws['d_interp_crop'])
+            fakes = (('D_rec', fwd.rec, 'd_rec_gp'), ('D_interp', fake_interp, 'd_interp_gp'),
+                     ('D_blend', self._fcn_fake(fwd, 'blend', draws['d_blend_crop'], draws['d_blend_mix']), 'd_blend_gp'))
             for name, fake, gp in fakes:
                 self.grads[name].zero_()
                 rep = loss.D_wgangp(self.nets[name], fake, reals, draws[gp], self.grads[name])
