@@ -317,20 +317,29 @@ def run_train(args):
     for _ in range(max(args.warmup, 3)):
         tr.step(reals_d, tr.sample_draws(TRAIN_BATCH, rng))
     barrier()
+    if args.device_only:      # for `ncu --profile-from-start off`: exactly one step between cudaProfilerStart/Stop
+        torch.cuda.profiler.start()
+        tr.step(reals_d, tr.sample_draws(TRAIN_BATCH, rng))
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     # device-resident: reals already in HBM; the host permutation sampler runs inside the step (it is part of it)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
     l0 = rt.launch_count()
-    ev0.record()
-    for _ in range(args.steps):
+    t_host = time.perf_counter()
+    for i in range(args.steps):
+        evs[i].record()
         tr.step(reals_d, tr.sample_draws(TRAIN_BATCH, rng))
-    ev1.record()
+    evs[-1].record()
+    host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps        # host time to ENQUEUE one step (no sync inside)
     barrier()
     launches = rt.launch_count() - l0
-    dev_ms = ev0.elapsed_time(ev1)
+    dev_ms = evs[0].elapsed_time(evs[-1])
+    step_ms = [round(evs[i].elapsed_time(evs[i + 1]), 2) for i in range(args.steps)]
     # end to end: reals from pinned host memory every step, loss report read back
     barrier()
     t0 = time.perf_counter()
@@ -371,13 +380,157 @@ def run_train(args):
                        'gflop_per_sample': TRAIN_GFLOP_PER_SAMPLE},
             'e2e': {'value': samples / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': int(reals_h.numel() * 4),
                     'd2h_bytes_per_step': 4 * len(host_rep), 'api': 'Trainer.step(reals) with host reals + loss report'},
-            'gpu_launches': int(launches),
+            'gpu_launches': int(launches), 'host_enqueue_ms_per_step': host_ms, 'step_ms': step_ms,
             'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': pk['bf16_sustained'] or pk['bf16'], 'unit': 'TFLOP/s',
                          'frac': tf / (pk['bf16_sustained'] or pk['bf16']), 'traffic': None,
                          'kernel': 'whole step per GPU (algorithmic fp32-conv FLOPs; tensor pipe executes 3x)',
                          'peak_source': pk['source'] + ', bf16 sustained'},
             'cpu_baseline': None,
             'replicas_identical': bool(float(hi - lo) == 0.0),
+            'clocks': clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ latent-tile interpolation (BASELINE configs[3])
+INTERP_BATCH = 16
+INTERP_SCALE = 4
+INTERP_GFLOP_PER_CANVAS = 206.586 + 4 * (0.5636 + 1.3042)      # G_res at 4x4 + E_zl/E_zg of the 4 sources
+INTERP_CANVAS_BYTES = 2 * 128 * 128 * 128 * 4                   # zg + zl canvases written per output (16.8 MB)
+
+
+def run_interp(args):
+    """cfg 4 (util_scripts.py:722-787 pattern): per canvas 4 source crops -> E_zg/E_zl -> zl tiled 4x4, gathered by
+    per-source index vectors (levels 1,2,4,8,16), corners re-pinned, 4-corner matte blend (zg likewise) ->
+    G_res(scale 4x4) -> [16,3,512,512]."""
+    import torch
+    import torch.distributed as dist
+    from texturemixer_b200 import interp, parallel
+    from texturemixer_b200.network import Network
+    from texturemixer_b200.runtime import Runtime
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a B200; there is no CPU path')
+    torch.cuda.set_device(local)
+    parallel.init_from_env()
+    rt = Runtime.get(local)
+    dev = rt.device
+    enc = dict(fmap_base=1024, fmap_max=512, latent_channels=128, use_pixelnorm=False, tanh_at_end=False)
+    E_zg = Network('E_zg', func='networks.E_zg', seed=1000, num_channels=3, resolution=128, **enc)
+    E_zl = Network('E_zl', func='networks.E_zl', seed=1001, num_channels=3, resolution=128, latent_res=32, **enc)
+    G = Network('G', func='networks.G_res', seed=1002, num_channels=3, resolution=128, scale_h=INTERP_SCALE,
+                scale_w=INTERP_SCALE, **G_CFG)
+    rng = np.random.RandomState(1000 + rank)
+    np.random.seed(1000 + rank)
+    n, S, L = INTERP_BATCH, INTERP_SCALE, 32 * INTERP_SCALE
+    src_h = torch.from_numpy(rng.uniform(-1, 1, (4 * n, 3, 128, 128)).astype(np.float32)).pin_memory()
+    src_d = src_h.to(dev)
+    out_h = torch.empty((n, 3, 128 * S, 128 * S), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(x):
+        # host: 8 index vectors per canvas (4 sources x h, w), same sampler / RNG stream as the reference's loops
+        idx_h = [interp.sample_permutation_indices(n, L, 5) for _ in range(4)]
+        idx_w = [interp.sample_permutation_indices(n, L, 5) for _ in range(4)]
+        zg_mu, _ = E_zg.get_output_for(x)
+        zl_mu, _ = E_zl.get_output_for(x)
+        zg, zl = interp.interpolate([zg_mu[k * n:(k + 1) * n] for k in range(4)],
+                                    [zl_mu[k * n:(k + 1) * n] for k in range(4)], S, S, idx_h=idx_h, idx_w=idx_w)
+        return G.get_output_for(zg, zl)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(src_d)
+    barrier()
+    if args.device_only:
+        torch.cuda.profiler.start()
+        step(src_d)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = rt.launch_count()
+    for a, b in evs:
+        flush.fill_(1)
+        a.record()
+        step(src_d)
+        b.record()
+    barrier()
+    launches = rt.launch_count() - l0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_h.copy_(step(src_h.to(dev, non_blocking=True)), non_blocking=True)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    # dominant kernel (trunk conv at 128x128 latent pixels, batch 16), timed live around each launch
+    rt.profile_kernels, rt.kernel_events = True, []
+    for _ in range(2):
+        flush.fill_(1)
+        step(src_d)
+    torch.cuda.synchronize()
+    trunk = [a.elapsed_time(b) for tag, a, b in rt.kernel_events if tag == ('tc', 3, 256, 256)]
+    rt.profile_kernels = False
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = float(t[0]), float(t[1])
+    if rank == 0:
+        pk = peaks()
+        canvases = n * world * args.steps
+        value = canvases / (dev_ms * 1e-3)
+        trunk_ms = float(np.mean(trunk)) if trunk else None
+        roof = None
+        if trunk_ms:
+            tf = TRUNK_GFLOP_PER_IMAGE * S * S * n / trunk_ms
+            roof = {'bound': 'tensor', 'achieved': tf, 'peak': pk['bf16_sustained'] or pk['bf16'], 'unit': 'TFLOP/s',
+                    'frac': tf / (pk['bf16_sustained'] or pk['bf16']), 'traffic': None,
+                    'kernel': 'conv_tc_kernel (3x3 256->256 @128x128 latent pixels, batch 16)', 'kernel_ms': trunk_ms,
+                    'launches_timed': len(trunk), 'peak_source': pk['source'] + ', bf16 sustained',
+                    'note': 'algorithmic fp32-conv FLOPs; bf16x3 executes 3x: %.1f TFLOP/s' % (3 * tf)}
+        import torch as _t
+        from oracle import networks_ref as R
+        cores = os.cpu_count() or 1
+        _t.set_num_threads(cores)
+        P = R.to_torch(R.init_params('G_res', np.random.RandomState(0), **G_CFG))
+        z = _t.randn(1, 128, L, L)
+        t0 = time.perf_counter()
+        with _t.no_grad():
+            R.G_res(z, z, P, **dict(G_CFG, scale_h=S, scale_w=S))
+        cpu_s = time.perf_counter() - t0
+        line = {
+            'metric': '512x512 interpolated textures/sec (4 sources -> 4x4 latent tile grid -> G_res)', 'value': value,
+            'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 (bf16x3 tensor-core products, fp32 accumulate; index grid int32)', 'data': 'synthetic',
+            'config': {'workload': 'cfg4: latent-tile interpolation, 4x4 tile grid blended to 512x512, batch 16 per GPU',
+                       'batch_per_gpu': n, 'l2': 'flushed between timed steps (256 MiB write)',
+                       'gflop_per_canvas': INTERP_GFLOP_PER_CANVAS, 'canvas_bytes': INTERP_CANVAS_BYTES,
+                       'tiles_128_per_s': value * S * S, 'parallelism': 'canvases sharded over ranks, no collective'},
+            'tflops_algorithmic': value * INTERP_GFLOP_PER_CANVAS / 1e3 / world,
+            'e2e': {'value': canvases / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': int(src_h.numel() * 4),
+                    'd2h_bytes_per_step': int(out_h.numel() * 4),
+                    'api': 'E_zg/E_zl.get_output_for -> interp.interpolate -> G.get_output_for; pinned host crops in, '
+                           'pinned host images out'},
+            'gpu_launches': int(launches), 'roofline': roof,
+            'cpu_baseline': {'value': 1.0 / cpu_s, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                             'sample': 'G_res(scale 4x4) of ONE canvas, torch-CPU fp32 restatement (oracle/)'},
             'clocks': clocks,
         }
         print(json.dumps(line))
@@ -394,7 +547,7 @@ def main():
     ap.add_argument('--device-only', action='store_true', help='only the device-resident loop (profiling runs)')
     ap.add_argument('--whole-canvas', action='store_true',
                     help='train_step: decode the whole 3x3 canvases in G_fcn instead of the crop windows')
-    ap.add_argument('--workload', default='gen_fwd', choices=['gen_fwd', 'train_step'],
+    ap.add_argument('--workload', default='gen_fwd', choices=['gen_fwd', 'train_step', 'interp'],
                     help='gen_fwd = BASELINE configs[1] (headline); train_step = configs[2]/[4]: full train step, '
                          'batch 32 per GPU, NCCL gradient all-reduce')
     args = ap.parse_args()
@@ -402,6 +555,8 @@ def main():
         run_reference(args)
     elif args.workload == 'train_step':
         run_train(args)
+    elif args.workload == 'interp':
+        run_interp(args)
     else:
         run_ours(args)
 

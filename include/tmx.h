@@ -301,6 +301,16 @@ int tmx_scale_rows(tmx_handle_t h, const float* in, const float* scale, float* o
 int tmx_gp_coefficients(tmx_handle_t h, const float* sq_norms, float* penalty, float* coef, int N, float lambda,
                         float target, tmx_stream_t s);
 
+/* Network.run output conversion (tfutil.py:649-659): y = saturate_cast(round(avg_pool_shrink(x * mul + add))) over
+ * `planes` = N*C image planes [H][W] fp32.  out_kind 0: fp32, no rounding; 1: uint8 (round half to even, clamp to
+ * [0,255], NaN -> 0); 2: fp32 holding rounded values (the caller narrows to the other integer types). */
+int tmx_convert_output(tmx_handle_t h, const float* x, void* y, int64_t planes, int H, int W, float mul, float add,
+                       int shrink, int out_kind, tmx_stream_t s);
+/* out = tanh(in) over n fp32 elements: the generator's image head when lod != 0 (networks.py:482-483). */
+int tmx_tanh_f32(tmx_handle_t h, const float* in, float* out, int64_t n, tmx_stream_t s);
+/* pixel_norm (networks.py:170-172) on NHWC fp32 [npix][C]: y = x * rsqrt(mean_c x^2 + eps). */
+int tmx_pixel_norm(tmx_handle_t h, const float* x, float* y, int64_t npix, int C, float eps, tmx_stream_t s);
+
 /* out = a + b over n fp32 elements (two gradient contributions meeting at one tensor). */
 int tmx_add_f32(tmx_handle_t h, const float* a, const float* b, float* out, int64_t n, tmx_stream_t s);
 

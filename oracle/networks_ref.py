@@ -254,12 +254,16 @@ def to_torch(params, dtype=torch.float32, requires_grad=False):
 # dict, receives every named intermediate (pre-activation too) for per-layer
 # parity checks.
 
-def _layer(P, scope, x, gain=SQRT2, act=True, taps=None):
+def _layer(P, scope, x, gain=SQRT2, act=True, taps=None, pn=None):
+    """[PN](act(apply_bias(conv2d(x)))): `pn` = pixel_norm epsilon of the blocks' activated convs when
+    use_pixelnorm (networks.py:216,320,415), None otherwise."""
     x = apply_bias(conv2d(x, P[scope + '/weight'], gain), P[scope + '/bias'])
     if taps is not None:
         taps[scope + ':pre'] = x
     if act:
         x = leaky_relu(x)
+        if pn is not None:
+            x = pixel_norm(x, pn)
     return x
 
 
@@ -281,8 +285,9 @@ def _encoder_trunk(images_in, P, resolution, min_res_log2, block, fromrgb, lod_i
 
 
 def E_zg(images_in, P, num_channels=3, resolution=128, fmap_base=1024, fmap_decay=1.0, fmap_max=512,
-         latent_channels=128, tanh_at_end=False, taps=None, **_):
+         latent_channels=128, tanh_at_end=False, taps=None, use_pixelnorm=False, pixelnorm_epsilon=1e-8, **_):
     """networks.py:194-291 -> (zg_mu, zg_log_sigma), each [N,latent_channels,1,1]."""
+    pn = pixelnorm_epsilon if use_pixelnorm else None
     rl2 = int(np.log2(resolution))
     assert resolution == 2 ** rl2 and resolution >= 4
     assert tuple(images_in.shape[1:]) == (num_channels, resolution, resolution)
@@ -294,13 +299,13 @@ def E_zg(images_in, P, num_channels=3, resolution=128, fmap_base=1024, fmap_deca
     def block(x, res):
         s = '%dx%d' % (2 ** res, 2 ** res)
         if res >= 3:
-            x = _layer(P, s + '/Conv0', x, taps=taps)
-            x = _layer(P, s + '/Conv1', x, taps=taps)
+            x = _layer(P, s + '/Conv0', x, taps=taps, pn=pn)
+            x = _layer(P, s + '/Conv1', x, taps=taps, pn=pn)
             return downscale2d(x)
-        x = _layer(P, s + '/Conv0', x, taps=taps)
-        x = downscale2d(_layer(P, s + '/zg_Conv1', x, taps=taps))
-        x = downscale2d(_layer(P, s + '/zg_Conv2', x, taps=taps))
-        return _layer(P, s + '/zg_Conv3', x, gain=1.0, act=False, taps=taps)
+        x = _layer(P, s + '/Conv0', x, taps=taps, pn=pn)
+        x = downscale2d(_layer(P, s + '/zg_Conv1', x, taps=taps, pn=pn))
+        x = downscale2d(_layer(P, s + '/zg_Conv2', x, taps=taps, pn=pn))
+        return _layer(P, s + '/zg_Conv3', x, gain=1.0, act=False, taps=taps, pn=pn)
 
     out = _encoder_trunk(images_in, P, resolution, 2, block, fromrgb, lod_in)
     if tanh_at_end:
@@ -309,8 +314,10 @@ def E_zg(images_in, P, num_channels=3, resolution=128, fmap_base=1024, fmap_deca
 
 
 def E_zl(images_in, P, num_channels=3, resolution=128, fmap_base=1024, fmap_decay=1.0, fmap_max=512,
-         latent_res=32, latent_channels=128, tanh_at_end=False, taps=None, **_):
+         latent_res=32, latent_channels=128, tanh_at_end=False, taps=None, use_pixelnorm=False,
+         pixelnorm_epsilon=1e-8, **_):
     """networks.py:296-383 -> (z_mu, z_log_sigma), each [N,latent_channels,latent_res,latent_res]."""
+    pn = pixelnorm_epsilon if use_pixelnorm else None
     rl2 = int(np.log2(resolution))
     ll2 = int(np.log2(latent_res))
     assert resolution == 2 ** rl2 and latent_res == 2 ** ll2 and resolution >= latent_res
@@ -323,11 +330,11 @@ def E_zl(images_in, P, num_channels=3, resolution=128, fmap_base=1024, fmap_deca
     def block(x, res):
         s = '%dx%d' % (2 ** res, 2 ** res)
         if res > ll2:
-            x = _layer(P, s + '/Conv0', x, taps=taps)
-            x = _layer(P, s + '/Conv1', x, taps=taps)
+            x = _layer(P, s + '/Conv0', x, taps=taps, pn=pn)
+            x = _layer(P, s + '/Conv1', x, taps=taps, pn=pn)
             return downscale2d(x)
-        x = _layer(P, s + '/Conv0', x, taps=taps)
-        return _layer(P, s + '/z_Conv1', x, gain=1.0, act=False, taps=taps)
+        x = _layer(P, s + '/Conv0', x, taps=taps, pn=pn)
+        return _layer(P, s + '/z_Conv1', x, gain=1.0, act=False, taps=taps, pn=pn)
 
     out = _encoder_trunk(images_in, P, resolution, ll2, block, fromrgb, lod_in)
     if tanh_at_end:
@@ -337,8 +344,9 @@ def E_zl(images_in, P, num_channels=3, resolution=128, fmap_base=1024, fmap_deca
 
 def G_res(zg_latents_in, zl_latents_in, P, num_channels=3, resolution=128, fmap_base=1024,
           fmap_decay=1.0, fmap_max=512, latent_res=32, latent_channels=128, tanh_at_end=True,
-          scale_h=1, scale_w=1, taps=None, **_):
+          scale_h=1, scale_w=1, taps=None, use_pixelnorm=False, pixelnorm_epsilon=1e-8, **_):
     """networks.py:388-486 -> images [N,num_channels,resolution*scale_h,resolution*scale_w]."""
+    pn = pixelnorm_epsilon if use_pixelnorm else None
     rl2 = int(np.log2(resolution))
     ll2 = int(np.log2(latent_res))
     assert resolution == 2 ** rl2 and latent_res == 2 ** ll2 and resolution >= latent_res
@@ -352,17 +360,17 @@ def G_res(zg_latents_in, zl_latents_in, P, num_channels=3, resolution=128, fmap_
         if res == ll2:
             for count in range(5):                                     # networks.py:431-437
                 x0 = x
-                x = _layer(P, s + '/Residual%d_0' % count, x, taps=taps)
-                x = _layer(P, s + '/Residual%d_1' % count, x, gain=1.0, act=False, taps=taps)
+                x = _layer(P, s + '/Residual%d_0' % count, x, taps=taps, pn=pn)
+                x = _layer(P, s + '/Residual%d_1' % count, x, gain=1.0, act=False, taps=taps, pn=pn)
                 x = x0 + x
                 if taps is not None:
                     taps[s + '/Residual%d:sum' % count] = x
-            x = _layer(P, s + '/Conv0', x, gain=SQRT2 / 4, taps=taps)  # networks.py:440
-            x = _layer(P, s + '/Conv1', x, taps=taps)
+            x = _layer(P, s + '/Conv0', x, gain=SQRT2 / 4, taps=taps, pn=pn)  # networks.py:440
+            x = _layer(P, s + '/Conv1', x, taps=taps, pn=pn)
         else:
             x = upscale2d(x)
-            x = _layer(P, s + '/Conv0', x, taps=taps)
-            x = _layer(P, s + '/Conv1', x, taps=taps)
+            x = _layer(P, s + '/Conv0', x, taps=taps, pn=pn)
+            x = _layer(P, s + '/Conv1', x, taps=taps, pn=pn)
         return x
 
     def torgb(x, res):

@@ -103,8 +103,52 @@ def gen_networks():
     print('networks.npz', {k: v.shape for k, v in out.items() if 'out' in k and 'shape' not in k})
 
 
+# (tag, func, lod, use_pixelnorm): progressive-growing levels of detail (integer and fractional: every tf.cond
+# branch of networks.py:276-282, 368-374, 473-479, 568-574) and the pixel-norm variant (networks.py:170-172)
+VARIANTS = [('E_zg', 1.0, False), ('E_zg', 0.5, False), ('E_zg', 3.25, False), ('E_zg', 5.0, False),
+            ('E_zl', 1.0, False), ('E_zl', 1.5, False), ('E_zl', 2.0, False),
+            ('G_res', 1.0, False), ('G_res', 0.25, False), ('G_res', 1.75, False), ('G_res', 2.0, False),
+            ('D_patch', 1.0, False), ('D_patch', 2.5, False), ('D_patch', 5.0, False),
+            ('E_zg', 0.0, True), ('E_zl', 0.0, True), ('G_res', 0.0, True), ('G_res', 1.5, True)]
+
+
+def variant_tag(func, lod, pn):
+    return '%s_lod%s%s' % (func, ('%g' % lod).replace('.', 'p'), '_pn' if pn else '')
+
+
+def gen_network_variants():
+    net, tf = refload.reference_networks()
+    out = {}
+    for func, lod, pn in VARIANTS:
+        n = 4 if func == 'D_patch' else 2
+        rng = np.random.RandomState(1000)
+        cfg = dict(R.CONFIG[func])
+        if pn:
+            cfg['use_pixelnorm'] = True
+        params = R.init_params(func, rng, **cfg)
+        params['lod'] = np.float32(lod)
+        ins = network_inputs(func, rng, n)
+        tf.reset_default_graph(values={func + '/' + k: v for k, v in params.items()})
+        with tf.variable_scope(func):
+            res = getattr(net, func)(*[tf.convert_to_tensor(a) for a in ins], num_channels=3, resolution=128, **cfg)
+        res = res if isinstance(res, tuple) else (res,)
+        tag = variant_tag(func, lod, pn)
+        for i, r in enumerate(res):
+            a = r.numpy()
+            flat = a.reshape(-1)
+            out['%s_out%d_shape' % (tag, i)] = np.array(a.shape, np.int64)
+            out['%s_out%d' % (tag, i)] = (flat[::SUBSAMPLE] if flat.size > 4096 else flat).astype(np.float32)
+            out['%s_out%d_absmax' % (tag, i)] = np.array([np.abs(a).max()], np.float32)
+    np.savez_compressed(os.path.join(HERE, 'networks_variants.npz'), **out)
+    print('networks_variants.npz', sorted(k for k in out if k.endswith('_out0')))
+
+
 if __name__ == '__main__':
     assert refload.reference_available(), 'needs /root/reference'
+    if 'variants' in sys.argv[1:]:
+        gen_network_variants()
+        sys.exit(0)
     gen_perm()
     gen_mattes()
     gen_networks()
+    gen_network_variants()

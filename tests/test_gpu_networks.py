@@ -196,3 +196,73 @@ def test_network_run_output_conversion():
     u = net.run(zg, zl, out_mul=127.5, out_add=127.5, out_dtype=np.uint8, minibatch_size=1)
     want = np.clip(np.rint(f * np.float32(127.5) + np.float32(127.5)), 0, 255).astype(np.uint8)
     assert u.dtype == np.uint8 and np.abs(u.astype(np.int32) - want.astype(np.int32)).max() <= 1
+
+
+def _variant_table():
+    src = open(os.path.join(GOLDEN, 'make_golden.py')).read()
+    ns = {}
+    exec(src[src.index('VARIANTS = ['):src.index('def gen_network_variants')], ns)
+    return ns['VARIANTS'], ns['variant_tag']
+
+
+VARIANTS, variant_tag = _variant_table()
+
+
+@pytest.mark.parametrize('func,lod,pn', VARIANTS)
+def test_lod_and_pixelnorm_variants_match_reference_golden(func, lod, pn):
+    """every branch of the progressive-growing tf.cond trees (integer and fractional lod:
+    FromRGB / ToRGB heads of the lower resolutions, image down/up-scaling, fades) and use_pixelnorm, against the
+    outputs of the reference's own networks.py (tests/golden/networks_variants.npz) and the oracle."""
+    g = np.load(os.path.join(GOLDEN, 'networks_variants.npz'))
+    n = 4 if func == 'D_patch' else 2
+    rng = np.random.RandomState(1000)
+    cfg = dict(R.CONFIG[func])
+    extra = {'use_pixelnorm': True} if pn else {}
+    cfg.update(extra)
+    params = R.init_params(func, rng, **cfg)
+    params['lod'] = np.float32(lod)
+    ins = _inputs(func, rng, n)
+    net = _make(func, params, **extra)
+    assert net.lod == float(np.float32(lod))
+    outs = net.run(*ins, return_as_list=True)
+    tag = variant_tag(func, lod, pn)
+    with torch.no_grad():
+        want = R.NETWORKS[func](*[torch.from_numpy(a) for a in ins], R.to_torch(params), **cfg)
+    want = want if isinstance(want, tuple) else (want,)
+    for i, a in enumerate(outs):
+        assert list(a.shape) == g['%s_out%d_shape' % (tag, i)].tolist()
+        flat = a.reshape(-1)
+        got = flat[::SUBSAMPLE] if flat.size > 4096 else flat
+        scale = float(g['%s_out%d_absmax' % (tag, i)][0])
+        assert np.abs(got - g['%s_out%d' % (tag, i)]).max() <= TOL * scale
+        assert _nmax(a, want[i].numpy()) <= TOL
+
+
+def test_training_tape_at_lod_is_refused():
+    rng = np.random.RandomState(2)
+    params = R.init_params('E_zl', rng, **R.CONFIG['E_zl'])
+    params['lod'] = np.float32(1.0)
+    net = _make('E_zl', params)
+    with pytest.raises(NotImplementedError):
+        net.get_output_for(torch.from_numpy(_inputs('E_zl', rng, 1)[0]).cuda(), tape=[])
+
+
+def test_output_conversion_kernel_bit_exact():
+    """tfutil.py:649-659 on the device (tmx_convert_output): x * mul + add, avg-pool shrink, round half to even,
+    saturate - bit-exact against numpy for uint8, and the shrink path against an fp32 mean."""
+    from texturemixer_b200.network import _convert_output
+    rng = np.random.RandomState(4)
+    x = (rng.randn(3, 3, 16, 24) * 1.2).astype(np.float32)
+    x[0, 0, 0, :4] = [1.0, -1.0, 0.00392157, np.nan]            # 255, 0, a .5 tie region, NaN -> 0
+    xd = torch.from_numpy(x).cuda()
+    u = _convert_output(xd, 127.5, 127.5, 1, np.uint8).cpu().numpy()
+    v = x * np.float32(127.5) + np.float32(127.5)
+    want = np.where(np.isnan(v), 0, np.clip(np.rint(v), 0, 255)).astype(np.uint8)
+    assert u.dtype == np.uint8 and np.array_equal(u, want)
+    ties = torch.tensor([[[[0.5, 1.5, 2.5, 3.5, 254.5, 255.5, -0.5, 300.0]]]], dtype=torch.float32).cuda()
+    assert _convert_output(ties, 1.0, 0.0, 1, np.uint8).cpu().numpy().reshape(-1).tolist() == [0, 2, 2, 4, 254, 255, 0, 255]
+    s = _convert_output(xd[1:], 2.0, 0.25, 4, None).cpu().numpy()
+    ref = (x[1:] * np.float32(2.0) + np.float32(0.25)).reshape(2, 3, 4, 4, 6, 4).mean(axis=(3, 5))
+    assert s.shape == (2, 3, 4, 6) and np.abs(s - ref).max() <= 1e-5
+    i16 = _convert_output(xd[1:], 30000.0, 0.0, 1, np.int16).cpu().numpy()
+    assert i16.dtype == np.int16 and np.array_equal(i16, np.clip(np.rint(x[1:] * np.float32(30000.0)), -32768, 32767).astype(np.int16))

@@ -683,3 +683,98 @@ extern "C" int tmx_dense_fwd(tmx_handle_t h, const float* x, const float* w, con
   TMX_LAUNCHED(h, "dense_finish_kernel");
   return TMX_OK;
 }
+
+// ---------------------------------------------------------------- Network.run output conversion (tfutil.py:649-659)
+// y = saturate_cast(round(avg_pool_s(x * mul + add))) per image plane; the ops keep the reference's order and
+// rounding: separate multiply and add (no fma contraction), window sum / count, tf.round = round-half-to-even,
+// saturate_cast clamps to the integer range (NaN -> 0).  One thread per OUTPUT element; rows = N * C planes.
+template <int OUT_U8>
+__global__ void __launch_bounds__(256) convert_output_kernel(const float* __restrict__ x, void* __restrict__ y,
+                                                             long long total, int H, int W, int shrink, float mul,
+                                                             float add, int do_round) {
+  const int Ho = H / shrink, Wo = W / shrink;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int xo = (int)(i % Wo);
+    const int yo = (int)((i / Wo) % Ho);
+    const long long plane = i / ((long long)Wo * Ho);
+    const float* p = x + (plane * H + (long long)yo * shrink) * W + (long long)xo * shrink;
+    float v;
+    if (shrink == 1) {
+      v = __fadd_rn(__fmul_rn(__ldg(p), mul), add);
+    } else {
+      float acc = 0.f;
+      for (int a = 0; a < shrink; ++a)
+        for (int b = 0; b < shrink; ++b) acc = __fadd_rn(acc, __fadd_rn(__fmul_rn(__ldg(p + (long long)a * W + b), mul), add));
+      v = __fdiv_rn(acc, (float)(shrink * shrink));
+    }
+    if (OUT_U8) {
+      v = rintf(v);
+      v = v != v ? 0.f : fminf(fmaxf(v, 0.f), 255.f);
+      ((uint8_t*)y)[i] = (uint8_t)v;
+    } else {
+      ((float*)y)[i] = do_round ? rintf(v) : v;
+    }
+  }
+}
+
+extern "C" int tmx_convert_output(tmx_handle_t h, const float* x, void* y, int64_t planes, int H, int W, float mul,
+                                  float add, int shrink, int out_kind, tmx_stream_t s) {
+  TMX_REQUIRE(h && x && y, TMX_ERR_ARG, "tmx_convert_output: NULL argument");
+  TMX_REQUIRE(planes > 0 && H > 0 && W > 0 && shrink >= 1 && H % shrink == 0 && W % shrink == 0, TMX_ERR_SHAPE,
+              "tmx_convert_output: bad shape planes=%lld H=%d W=%d shrink=%d", (long long)planes, H, W, shrink);
+  TMX_REQUIRE(out_kind >= 0 && out_kind <= 2, TMX_ERR_ARG, "tmx_convert_output: out_kind %d", out_kind);
+  const long long total = planes * (H / shrink) * (W / shrink);
+  const int grid = (int)(total / 256 + 1 < 148LL * 16 ? total / 256 + 1 : 148LL * 16);
+  if (out_kind == 1)
+    convert_output_kernel<1><<<grid, 256, 0, (cudaStream_t)s>>>(x, y, total, H, W, shrink, mul, add, 1);
+  else
+    convert_output_kernel<0><<<grid, 256, 0, (cudaStream_t)s>>>(x, y, total, H, W, shrink, mul, add, out_kind == 2);
+  TMX_LAUNCHED(h, "convert_output_kernel");
+  return TMX_OK;
+}
+
+// ---------------------------------------------------------------- tanh over a flat fp32 tensor (networks.py:482-483)
+// the image head's tanh when it cannot ride in the ToRGB epilogue (lod != 0: tanh follows the fade / upscale)
+__global__ void __launch_bounds__(256) tanh_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = tanhf(__ldg(in + i));
+}
+
+extern "C" int tmx_tanh_f32(tmx_handle_t h, const float* in, float* out, int64_t n, tmx_stream_t s) {
+  TMX_REQUIRE(h && in && out && n > 0, TMX_ERR_ARG, "tmx_tanh_f32: bad argument");
+  const int grid = (int)(n / 256 + 1 < 148LL * 16 ? n / 256 + 1 : 148LL * 16);
+  tanh_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(in, out, n);
+  TMX_LAUNCHED(h, "tanh_kernel");
+  return TMX_OK;
+}
+
+// ---------------------------------------------------------------- pixel_norm (networks.py:170-172)
+// y[p][c] = x[p][c] * rsqrt(mean_c x[p][c]^2 + eps) on NHWC fp32; one warp per pixel, channels strided over lanes.
+__global__ void __launch_bounds__(256) pixel_norm_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                         long long npix, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long p = warp; p < npix; p += nwarp) {
+    const float* xp = x + p * C;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float v = __ldg(xp + c);
+      acc = fmaf(v, v, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const float r = rsqrtf(acc / (float)C + eps);
+    for (int c = lane; c < C; c += 32) y[p * C + c] = __ldg(xp + c) * r;
+  }
+}
+
+extern "C" int tmx_pixel_norm(tmx_handle_t h, const float* x, float* y, int64_t npix, int C, float eps, tmx_stream_t s) {
+  TMX_REQUIRE(h && x && y && npix > 0 && C > 0, TMX_ERR_ARG, "tmx_pixel_norm: bad argument");
+  const long long blocks = (npix + 7) / 8;
+  const int grid = (int)(blocks < 148LL * 16 ? blocks : 148LL * 16);
+  pixel_norm_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, y, npix, C, eps);
+  TMX_LAUNCHED(h, "pixel_norm_kernel");
+  return TMX_OK;
+}

@@ -49,6 +49,8 @@ def _gather_bwd(rt, dcanvas, dsrc, idx_h, idx_w, pins=(0, 0), reverse=False):
 
 
 def _dev_idx(rt, a):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=rt.device, dtype=torch.int32).contiguous()
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(rt.device)
 
 

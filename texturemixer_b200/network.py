@@ -94,6 +94,7 @@ class BuildContext:
         self.scopes = []
         self.rt = net.rt if mode == 'run' else None
         self.tape = tape        # list of layer records when the forward is run for training (backward.py)
+        self.pixelnorm = None   # epsilon of pixel_norm after every activated conv (set by the build function)
 
     @contextlib.contextmanager
     def variable_scope(self, name):
@@ -596,20 +597,27 @@ def _np_dtype(t):
 
 
 def _convert_output(x, out_mul, out_add, out_shrink, out_dtype):
-    """tfutil.py:649-659 output conversion (mul, add, avg-pool shrink, round +
-    saturate-cast).  Not part of the measured path."""
-    if out_mul != 1.0:
-        x = x * out_mul
-    if out_add != 0.0:
-        x = x + out_add
-    if out_shrink > 1:
-        x = torch.nn.functional.avg_pool2d(x, out_shrink, out_shrink)
-    if out_dtype is not None:
-        dt = np.dtype(out_dtype)
-        if np.issubdtype(dt, np.integer):
-            info = np.iinfo(dt)
-            x = torch.round(x).clamp_(info.min, info.max)
-        x = x.to({np.dtype(np.uint8): torch.uint8, np.dtype(np.int32): torch.int32, np.dtype(np.int16): torch.int16,
-                  np.dtype(np.int64): torch.int64, np.dtype(np.float32): torch.float32,
-                  np.dtype(np.float16): torch.float16}[dt])
-    return x
+    """tfutil.py:649-659 output conversion on the device (tmx_convert_output): x * mul + add, avg-pool shrink,
+    tf.round (half to even) + saturate_cast for integer dtypes - one kernel, uint8 written directly."""
+    dt = None if out_dtype is None else np.dtype(out_dtype)
+    if out_mul == 1.0 and out_add == 0.0 and out_shrink == 1 and (dt is None or dt == np.dtype(np.float32)):
+        return x
+    import ctypes as C
+    from . import _lib
+    rt = Runtime.get(x.device)
+    x = x.contiguous()
+    lead, (h, w) = x.shape[:-2], x.shape[-2:]
+    is_int = dt is not None and np.issubdtype(dt, np.integer)
+    kind = 1 if dt == np.dtype(np.uint8) else (2 if is_int else 0)
+    out = torch.empty(tuple(lead) + (h // out_shrink, w // out_shrink),
+                      dtype=torch.uint8 if kind == 1 else torch.float32, device=x.device)
+    _lib.check(rt.lib.tmx_convert_output(rt.handle, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()),
+                                         int(np.prod(lead)), h, w, float(out_mul), float(out_add), int(out_shrink),
+                                         kind, rt.stream()), 'tmx_convert_output')
+    if dt is None or kind == 1 or dt == np.dtype(np.float32):
+        return out
+    if is_int:                       # other integer types: rounded on the device, narrowed with saturation here
+        info = np.iinfo(dt)
+        out = out.clamp_(float(info.min), float(info.max))
+    return out.to({np.dtype(np.int32): torch.int32, np.dtype(np.int16): torch.int16, np.dtype(np.int64): torch.int64,
+                   np.dtype(np.float16): torch.float16, np.dtype(np.float64): torch.float64}[dt])

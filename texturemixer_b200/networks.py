@@ -8,9 +8,12 @@ declare variables (same names, shapes and creation order as the reference's
 in *run* mode every layer is one libtmx launch on device activations
 (`runtime.Act`).  No arithmetic happens in Python/torch.
 
-Only the reference's default layer variants are implemented on the device
-(use_wscale=True, use_pixelnorm=False, fused_scale=False, leaky ReLU,
-float32); the others raise NotImplementedError."""
+Layer variants on the device: the reference defaults (use_wscale=True,
+fused_scale=False, leaky ReLU, float32) plus `use_pixelnorm` in the generator;
+the others raise NotImplementedError.  Progressive growing
+(`lod` > 0, integer or fractional: the tf.cond trees of networks.py:276-282,
+368-374, 473-479, 568-574) is evaluated for inference; a training tape at
+lod != 0 raises."""
 import numpy as np
 import torch
 
@@ -26,11 +29,11 @@ def _wscale(shape, gain):
     return float(np.float32(gain / np.sqrt(np.prod(shape[:-1]))))
 
 
-def _check_variants(use_wscale, use_pixelnorm, use_leakyrelu, fused_scale, dtype):
-    if not use_wscale or use_pixelnorm or not use_leakyrelu or fused_scale or dtype != 'float32':
-        raise NotImplementedError('texturemixer_b200: only the reference defaults use_wscale=True, '
-                                  'use_pixelnorm=False, use_leakyrelu=True, fused_scale=False, dtype=float32 '
-                                  'are implemented on the device')
+def _check_variants(use_wscale, use_leakyrelu, fused_scale, dtype):
+    if not use_wscale or not use_leakyrelu or fused_scale or dtype != 'float32':
+        raise NotImplementedError('texturemixer_b200: only use_wscale=True, use_leakyrelu=True, fused_scale=False, '
+                                  'dtype=float32 (the reference defaults; use_pixelnorm is free) are implemented on '
+                                  'the device')
 
 
 def _act_of(t):
@@ -80,6 +83,9 @@ def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=Fals
                                             xmerge=rt.use_xmerge(xa.c, kernel, up2))
     res = None if residual is None else rt.split_unpack(_act_of(residual)).f32
     head = None
+    pn = getattr(ctx, 'pixelnorm', None) if act else None      # PN(act(...)) of networks.py:216,320,415
+    if pn is not None:
+        torgb, next_tc, keep_f32 = None, False, True           # the normalised map is what every consumer reads
     rec = ctx.tape is not None
     if rec:
         # training forward: keep what the backward needs - the input planes (weight gradient), the fp32
@@ -104,6 +110,8 @@ def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=Fals
     if rec:
         ctx.tape.append(dict(kind='conv', x=xa, y=t.act, w=w.name, b=b.name, wscale=ws, k=kernel, cin=cin, cout=fmaps,
                              act=act, up2=up2, residual=None if residual is None else _act_of(residual)))
+    if pn is not None:
+        t = _pixel_norm(ctx, t, pn)
     if strip is not None:
         orig = _act_of(x)
         m = orig.n * orig.h * orig.w
@@ -140,6 +148,11 @@ def downscale2d(x, factor=2):
     shape = [x.shape[0], x.shape[1], x.shape[2] // factor, x.shape[3] // factor]
     if ctx.mode == 'template':
         return T(shape, ctx)
+    if x.act is None and x.nchw is not None:
+        # the network's input image pooled for a lower level of detail (networks.py:278,281): one VALID average
+        # pool of the whole factor on the NCHW planes (3 channels: not an NHWC/tensor-core layout)
+        _no_tape_at_lod(ctx)
+        return T(shape, ctx, nchw=_pool_image(ctx.rt, x.nchw, factor))
     a = _act_of(x)
     f = factor
     while f > 1:
@@ -150,6 +163,67 @@ def downscale2d(x, factor=2):
         a = b
         f //= 2
     return T(shape, ctx, act=a)
+
+
+def _no_tape_at_lod(ctx):
+    if ctx.tape is not None:
+        raise NotImplementedError('training (a backward tape) at lod != 0 is not implemented (SURVEY N1); '
+                                  'inference at any lod is')
+
+
+def _pool_image(rt, img, factor):
+    import ctypes as C
+    from . import _lib
+    n, c, h, w = img.shape
+    out = rt.empty(n, c, h // factor, w // factor)
+    _lib.check(rt.lib.tmx_convert_output(rt.handle, C.c_void_p(img.data_ptr()), C.c_void_p(out.data_ptr()), n * c, h, w,
+                                         1.0, 0.0, int(factor), 0, rt.stream()), 'tmx_convert_output')
+    return out
+
+
+def _lerp_lod(rt, a, b, t):
+    """tfutil.lerp(a, b, t) = a + (b - a) * t (tfutil.py:41-43) on two equally shaped fp32 device tensors with the
+    scalar t = lod_in - lod, in float32 like the graph."""
+    from . import _lib
+    n = a.shape[0]
+    per = a[0].numel()
+    tt = torch.full((n,), float(np.float32(t)), dtype=torch.float32, device=a.device)
+    out = rt.latent_blend([a.contiguous().view(n, 1, 1, per), b.contiguous().view(n, 1, 1, per)], 1, per,
+                          _lib.BLEND_LERP, t=tt)
+    return out.view(a.shape)
+
+
+def _upscale_image(rt, img, factor):
+    """upscale2d (networks.py:80-88) of an NCHW image: nearest-neighbour gather y[i][j] = x[i // f][j // f]."""
+    from . import _lib
+    n, c, h, w = img.shape
+    ih = torch.arange(h * factor, dtype=torch.int32, device=img.device).div_(factor, rounding_mode='floor')
+    iw = torch.arange(w * factor, dtype=torch.int32, device=img.device).div_(factor, rounding_mode='floor')
+    return rt.latent_blend([img.contiguous()], h * factor, w * factor, _lib.BLEND_COPY,
+                           idx_h=[ih.repeat(n, 1).contiguous()], idx_w=[iw.repeat(n, 1).contiguous()])
+
+
+def _tanh(rt, x):
+    import ctypes as C
+    from . import _lib
+    out = rt.empty(*x.shape)
+    _lib.check(rt.lib.tmx_tanh_f32(rt.handle, C.c_void_p(x.contiguous().data_ptr()), C.c_void_p(out.data_ptr()),
+                                   x.numel(), rt.stream()), 'tmx_tanh_f32')
+    return out
+
+
+def _pixel_norm(ctx, t, epsilon):
+    """pixel_norm (networks.py:170-172) of a run-mode handle: x * rsqrt(mean_c x^2 + eps) on the NHWC fp32 map."""
+    import ctypes as C
+    from . import _lib
+    if ctx.tape is not None:
+        raise NotImplementedError('training with use_pixelnorm=True is not implemented (SURVEY N4); inference is')
+    rt = ctx.rt
+    a = rt.split_unpack(_act_of(t))
+    out = rt.empty(a.n, a.h, a.w, a.c)
+    _lib.check(rt.lib.tmx_pixel_norm(rt.handle, C.c_void_p(a.f32.data_ptr()), C.c_void_p(out.data_ptr()),
+                                     a.n * a.h * a.w, a.c, float(epsilon), rt.stream()), 'tmx_pixel_norm')
+    return T(t.shape, ctx, act=Act(a.n, a.h, a.w, a.c, f32=out))
 
 
 def _fromrgb(x, fmaps, name):
@@ -164,7 +238,8 @@ def _fromrgb(x, fmaps, name):
         if ctx.mode == 'template':
             return T(shape, ctx)
         if x.nchw is None:
-            raise NotImplementedError('FromRGB on a downscaled image (lod > 0) is not implemented (SURVEY N1)')
+            a = ctx.rt.split_unpack(_act_of(x))
+            x.nchw = ctx.rt.nhwc_to_nchw(a.f32)
         out = ctx.rt.fromrgb(x.nchw, w.value, b.value, _wscale(w.shape, SQRT2), fmaps, lrelu=True)
         if ctx.tape is not None:
             ctx.tape.append(dict(kind='fromrgb', img=x.nchw, y=out, w=w.name, b=b.name, wscale=_wscale(w.shape, SQRT2),
@@ -200,7 +275,10 @@ def _encoder_grow(ctx, images_in, resolution_log2, min_res_log2, block, fromrgb,
     def lerp_lod(x, y, t):
         if ctx.mode == 'template':
             return x
-        raise NotImplementedError('fractional lod (progressive growing) is not implemented (SURVEY N1)')
+        _no_tape_at_lod(ctx)
+        rt = ctx.rt
+        a, b = rt.split_unpack(_act_of(x)), rt.split_unpack(_act_of(y))
+        return T(x.shape, ctx, act=Act(a.n, a.h, a.w, a.c, f32=_lerp_lod(rt, a.f32, b.f32, t)))
 
     def grow(res, lod):
         def x_fn():
@@ -230,7 +308,7 @@ def E_zg(images_in, num_channels=3, resolution=128, fmap_base=8192, fmap_decay=1
          **kwargs):
     resolution_log2 = int(np.log2(resolution))
     assert resolution == 2 ** resolution_log2 and resolution >= 4         # networks.py:214
-    _check_variants(use_wscale, use_pixelnorm, use_leakyrelu, fused_scale, dtype)
+    _check_variants(use_wscale, use_leakyrelu, fused_scale, dtype)
     if tanh_at_end:
         raise NotImplementedError('E_zg tanh_at_end=True is not used by the reference config')
 
@@ -239,6 +317,7 @@ def E_zg(images_in, num_channels=3, resolution=128, fmap_base=8192, fmap_decay=1
     if latent_channels is None:
         latent_channels = nf(0)
     ctx = images_in.ctx
+    ctx.pixelnorm = pixelnorm_epsilon if use_pixelnorm else None
     images_in.set_shape([None, num_channels, resolution, resolution])
     lod_in = _lod(ctx)
 
@@ -277,7 +356,7 @@ def E_zl(images_in, num_channels=3, resolution=128, fmap_base=8192, fmap_decay=1
     resolution_log2 = int(np.log2(resolution))
     latent_res_log2 = int(np.log2(latent_res))
     assert resolution == 2 ** resolution_log2 and latent_res == 2 ** latent_res_log2 and resolution >= latent_res
-    _check_variants(use_wscale, use_pixelnorm, use_leakyrelu, fused_scale, dtype)
+    _check_variants(use_wscale, use_leakyrelu, fused_scale, dtype)
     if tanh_at_end:
         raise NotImplementedError('E_zl tanh_at_end=True is not used by the reference config')
 
@@ -286,6 +365,7 @@ def E_zl(images_in, num_channels=3, resolution=128, fmap_base=8192, fmap_decay=1
     if latent_channels is None:
         latent_channels = nf(0)
     ctx = images_in.ctx
+    ctx.pixelnorm = pixelnorm_epsilon if use_pixelnorm else None
     images_in.set_shape([None, num_channels, resolution, resolution])
     lod_in = _lod(ctx)
 
@@ -318,13 +398,14 @@ def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_bas
     resolution_log2 = int(np.log2(resolution))
     latent_res_log2 = int(np.log2(latent_res))
     assert resolution == 2 ** resolution_log2 and latent_res == 2 ** latent_res_log2 and resolution >= latent_res
-    _check_variants(use_wscale, use_pixelnorm, use_leakyrelu, fused_scale, dtype)
+    _check_variants(use_wscale, use_leakyrelu, fused_scale, dtype)
 
     def nf(stage):
         return min(int(fmap_base / (2.0 ** (stage * fmap_decay))), fmap_max)
     if latent_channels is None:
         latent_channels = nf(0)
     ctx = zg_latents_in.ctx
+    ctx.pixelnorm = pixelnorm_epsilon if use_pixelnorm else None
     zg_latents_in.set_shape([None, latent_channels, latent_res * scale_h, latent_res * scale_w])
     zl_latents_in.set_shape([None, latent_channels, latent_res * scale_h, latent_res * scale_w])
     c2 = latent_channels * 2
@@ -380,7 +461,8 @@ def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_bas
             ntc = _tc(ctx, nf(res - 1), nf(res), 3, up2=True)
             return conv2d_layer(x, nf(res - 1), 3, next_tc=ntc, next_up2=ntc)
         head = None
-        if ctx.mode == 'run' and lod_in == 0 and nf(res - 1) in (16, 32) and _tc(ctx, nf(res - 1), nf(res - 1), 3):
+        if ctx.mode == 'run' and lod_in == 0 and not use_pixelnorm and nf(res - 1) in (16, 32) and \
+                _tc(ctx, nf(res - 1), nf(res - 1), 3):
             head = ('ToRGB_lod0', num_channels, bool(tanh_at_end))
         return conv2d_layer(x, nf(res - 1), 3, torgb=head)
 
@@ -394,24 +476,30 @@ def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_bas
             if ctx.mode == 'template':
                 return T(shape, ctx)
             if x.rgb is not None and x.rgb[0] == 'ToRGB_lod%d' % lod and x.rgb[1] == bool(apply_tanh):
-                return T(shape, ctx, nchw=x.rgb[2])                        # produced by the conv epilogue
-            img = ctx.rt.torgb(_act_of(x), w.value, b.value, _wscale(w.shape, 1.0), num_channels, apply_tanh)
-            if ctx.tape is not None:
-                ctx.tape.append(dict(kind='torgb', x=_act_of(x), img=img, w=w.name, b=b.name,
-                                     wscale=_wscale(w.shape, 1.0), tanh=bool(apply_tanh)))
-            return T(shape, ctx, nchw=img)
+                out = T(shape, ctx, nchw=x.rgb[2])                         # produced by the conv epilogue
+            else:
+                img = ctx.rt.torgb(_act_of(x), w.value, b.value, _wscale(w.shape, 1.0), num_channels, apply_tanh)
+                if ctx.tape is not None:
+                    ctx.tape.append(dict(kind='torgb', x=_act_of(x), img=img, w=w.name, b=b.name,
+                                         wscale=_wscale(w.shape, 1.0), tanh=bool(apply_tanh)))
+                out = T(shape, ctx, nchw=img)
+            out.tanh_done = bool(apply_tanh)
+            return out
 
     def up_img(t, factor):
         if factor == 1:
             return t
+        shape = [t.shape[0], t.shape[1], _mul(t.shape[2], factor), _mul(t.shape[3], factor)]
         if ctx.mode == 'template':
-            return T([t.shape[0], t.shape[1], t.shape[2] * factor, t.shape[3] * factor], ctx)
-        raise NotImplementedError('G_res at lod > 0 (image upscale/fade) is not implemented (SURVEY N1)')
+            return T(shape, ctx)
+        _no_tape_at_lod(ctx)
+        return T(shape, ctx, nchw=_upscale_image(ctx.rt, t.nchw, factor))
 
     def lerp_lod(a, b, t):
         if ctx.mode == 'template':
             return a
-        raise NotImplementedError('G_res fractional lod is not implemented (SURVEY N1)')
+        _no_tape_at_lod(ctx)
+        return T(a.shape, ctx, nchw=_lerp_lod(ctx.rt, a.nchw, b.nchw, t))
 
     def grow(x, res, lod):                                                 # networks.py:473-479
         y = block(x, res)
@@ -437,8 +525,9 @@ def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_bas
         return img()
 
     images_out = grow(combo_in, latent_res_log2, resolution_log2 - latent_res_log2)
-    if ctx.mode == 'run' and tanh_at_end and lod_in != 0:
-        raise NotImplementedError('G_res at lod != 0 is not implemented (SURVEY N1)')
+    if ctx.mode == 'run' and tanh_at_end and not getattr(images_out, 'tanh_done', False):
+        # lod != 0: tf.nn.tanh follows the fade / upscale of the lower-resolution heads (networks.py:482-483)
+        images_out = T(images_out.shape, ctx, nchw=_tanh(ctx.rt, images_out.nchw))
     images_out.name = 'images_out'
     return images_out
 
@@ -449,7 +538,7 @@ def D_patch(images_in, num_channels=3, resolution=128, fmap_base=8192, fmap_deca
             structure='recursive', is_template_graph=False, **kwargs):
     resolution_log2 = int(np.log2(resolution))
     latent_res_log2 = 2 if latent_res == -1 else int(np.log2(latent_res))
-    _check_variants(use_wscale, False, True, fused_scale, dtype)
+    _check_variants(use_wscale, True, fused_scale, dtype)
 
     def nf(stage):
         return min(int(fmap_base / (2.0 ** (stage * fmap_decay))), fmap_max)

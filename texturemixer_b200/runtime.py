@@ -103,7 +103,8 @@ class Runtime:
         16-channel layers (TMX_CONV_XMERGE) reads up to 3 pixels past the last one (times a zero weight)."""
         numel = n * hp * wp * c
         buf = torch.empty(numel + 64, dtype=torch.bfloat16, device=self.device)
-        buf[numel:].zero_()
+        if c == 16:                 # only the 16-channel layers are ever read X-MERGED (use_xmerge)
+            buf[numel:].zero_()
         return buf[:numel].view(n, hp, wp, c)
 
     def split_pack(self, act, halo='reflect'):

@@ -86,10 +86,23 @@ class Trainer:
         def crop():
             return (int(rng.randint(0, hi_y)) if hi_y > 0 else 0, int(rng.randint(0, hi_x)) if hi_x > 0 else 0)
 
-        def mix():
-            return torch.from_numpy(rng.uniform(0.0, 1.0, (minibatch, 1, 1, 1)).astype(np.float32)).to(self.rt.device)
-        return dict(idx=idx, eg_crop_interp=crop(), eg_crop_blend=crop(), eg_mix=mix(), d_rec_gp=mix(),
-                    d_interp_crop=crop(), d_interp_gp=mix(), d_blend_mix=mix(), d_blend_crop=crop(), d_blend_gp=mix())
+        # every random draw of the step crosses to the device in two page-locked, non-blocking copies: a pageable
+        # `.to(device)` per tensor would stall the host behind all queued kernels nine times per step
+        mix_names = ('eg_mix', 'd_rec_gp', 'd_interp_gp', 'd_blend_mix', 'd_blend_gp')
+        mixes = torch.from_numpy(rng.uniform(0.0, 1.0, (len(mix_names), minibatch, 1, 1, 1)).astype(np.float32))
+        idx_names = ('h_forward', 'w_forward', 'h_backward', 'w_backward')
+        packed = torch.from_numpy(np.concatenate([idx[k].reshape(-1) for k in idx_names]).astype(np.int32))
+        if self.rt.device.type == 'cuda':
+            mixes = mixes.pin_memory().to(self.rt.device, non_blocking=True)
+            packed = packed.pin_memory().to(self.rt.device, non_blocking=True)
+        idx_dev, off = {}, 0
+        for k in idx_names:
+            idx_dev[k] = packed[off:off + idx[k].size].view(idx[k].shape)
+            off += idx[k].size
+        out = dict(idx=idx, idx_dev=idx_dev, eg_crop_interp=crop(), eg_crop_blend=crop(), d_interp_crop=crop(),
+                   d_blend_crop=crop())
+        out.update({k: mixes[i] for i, k in enumerate(mix_names)})
+        return out
 
     # ------------------------------------------------------------------ fake images of the canvas critics (no tape)
     def _fcn_fake(self, fwd, which, yx, mix=None):
@@ -115,7 +128,7 @@ class Trainer:
         report = {}
         c = self.cfg
         ca = c.get('crop_aware', True)
-        fwd = loss.EGForward(self.nets['E_zg'], self.nets['E_zl'], self.nets['G'], self.G_fcn, reals, draws['idx'],
+        fwd = loss.EGForward(self.nets['E_zg'], self.nets['E_zl'], self.nets['G'], self.G_fcn, reals, draws.get('idx_dev', draws['idx']),
                              draws['eg_mix'], c['scale_h'], c['scale_w'],
                              crop_interp=draws['eg_crop_interp'] if ca else None,
                              crop_blend=draws['eg_crop_blend'] if ca else None)
