@@ -329,7 +329,7 @@ def run_train(args):
     # device-resident: reals already in HBM; the host permutation sampler runs inside the step (it is part of it)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
-    l0 = rt.launch_count()
+    l0, g0 = rt.launch_count(), tr.graph_launches
     t_host = time.perf_counter()
     for i in range(args.steps):
         evs[i].record()
@@ -337,7 +337,7 @@ def run_train(args):
     evs[-1].record()
     host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps        # host time to ENQUEUE one step (no sync inside)
     barrier()
-    launches = rt.launch_count() - l0
+    launches = rt.launch_count() - l0 + tr.graph_launches - g0
     dev_ms = evs[0].elapsed_time(evs[-1])
     step_ms = [round(evs[i].elapsed_time(evs[i + 1]), 2) for i in range(args.steps)]
     # end to end: reals from pinned host memory every step, loss report read back

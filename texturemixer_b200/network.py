@@ -55,26 +55,26 @@ def call_func_by_name(*args, func=None, **kwargs):
 # ---------------------------------------------------------------------- variables
 class Variable:
     """A named parameter living in the owning network's flat device buffer."""
-    __slots__ = ('name', 'shape', 'trainable', 'init', 'value')
+    __slots__ = ('name', 'shape', 'trainable', 'init', 'value', 'size')
 
     def __init__(self, name, shape, trainable, init):
         self.name, self.shape, self.trainable, self.init = name, tuple(int(s) for s in shape), trainable, init
         self.value = None            # torch view, set by Network._allocate
-
-    @property
-    def size(self):
-        return int(np.prod(self.shape)) if self.shape else 1
+        self.size = int(np.prod(self.shape)) if self.shape else 1
 
 
 class T:
     """Tensor handle seen by build functions: a static NCHW shape (None batch
     in template mode) plus, in run mode, the device payload - either an
     external NCHW torch tensor (`nchw`) or an internal activation (`act`)."""
-    __slots__ = ('shape', 'ctx', 'nchw', 'act', 'name', 'rgb')
+    __slots__ = ('shape', 'ctx', 'nchw', 'act', 'name', 'rgb', 'tanh_done')
 
     def __init__(self, shape, ctx, nchw=None, act=None, name=None):
         self.shape, self.ctx, self.nchw, self.act, self.name = list(shape), ctx, nchw, act, name
+        if ctx is not None and ctx.mode == 'run':
+            ctx.handles.append(self)
         self.rgb = None      # images already produced by a fused ToRGB epilogue: (scope, tanh, NCHW tensor)
+        self.tanh_done = False   # image head: tanh already applied by the ToRGB kernel (lod == 0)
 
     def set_shape(self, shape):
         """tf.Tensor.set_shape: fixes the template shape / checks the fed one
@@ -95,6 +95,17 @@ class BuildContext:
         self.rt = net.rt if mode == 'run' else None
         self.tape = tape        # list of layer records when the forward is run for training (backward.py)
         self.pixelnorm = None   # epsilon of pixel_norm after every activated conv (set by the build function)
+        self.handles = []       # every run-mode T, so that release() can drop their device payloads
+
+    def release(self):
+        """The recursive closures of the build functions (grow -> grow) are reference CYCLES that capture this
+        context and their T handles; left alone they keep every activation and the whole tape of the evaluation
+        alive until the cyclic garbage collector happens to run (measured: 16 GB per train step).  Dropping the
+        payload references here returns device memory by reference counting as soon as the caller lets go."""
+        for t in self.handles:
+            t.nchw = t.act = t.rgb = None
+        self.handles = []
+        self.tape = None
 
     @contextlib.contextmanager
     def variable_scope(self, name):
@@ -168,6 +179,7 @@ class Network:
         self._flat = None              # one fp32 device buffer holding every variable
         self._version = 0              # bumped whenever variable values change
         self._prepared = {}            # per-variable tensor-core weight planes (w_hi, w_lo, version)
+        self._grad_slots = {}          # name -> (offset, size, shape) inside flat / flat gradient buffers
         self._rt = None
         self._device = None
         self._staging = {}
@@ -260,9 +272,14 @@ class Network:
         return (v.data_ptr() - self.flat.data_ptr()) // 4
 
     def grad_view(self, flat_grad, name):
-        v = self.vars[name]
-        off = self.var_offset(name)
-        return flat_grad[off:off + v.size].view(v.shape)
+        """The slot of variable `name` inside a flat gradient buffer laid out like `flat`."""
+        o = self._owner()
+        ent = o._grad_slots.get(name)
+        if ent is None:
+            v = self.vars[name]
+            ent = o._grad_slots[name] = (self.var_offset(name), v.size, v.shape)
+        off, size, shape = ent
+        return flat_grad[off:off + size].view(shape)
 
     def _owner(self):
         return self._shared_owner._owner() if self._shared_owner is not None else self
@@ -375,6 +392,7 @@ class Network:
         out = self._build_func(*ins, **all_kwargs)
         outs = [out] if isinstance(out, T) else list(out)
         res = [t.nchw for t in outs]
+        ctx.release()
         if tape is not None:
             tape.append(dict(kind='outputs', tensors=res))
         if return_as_list:

@@ -14,6 +14,8 @@ the others raise NotImplementedError.  Progressive growing
 (`lod` > 0, integer or fractional: the tf.cond trees of networks.py:276-282,
 368-374, 473-479, 568-574) is evaluated for inference; a training tape at
 lod != 0 raises."""
+import functools
+
 import numpy as np
 import torch
 
@@ -26,6 +28,11 @@ SQRT2 = float(np.sqrt(2))
 # ---------------------------------------------------------------------- primitives
 def _wscale(shape, gain):
     """get_weight, networks.py:26-33 (use_wscale=True): float32(gain / sqrt(fan_in))."""
+    return _wscale_cached(tuple(shape), float(gain))
+
+
+@functools.lru_cache(maxsize=None)
+def _wscale_cached(shape, gain):
     return float(np.float32(gain / np.sqrt(np.prod(shape[:-1]))))
 
 

@@ -32,6 +32,13 @@ class Act:
         return (self.n, self.c, self.h, self.w)
 
 
+try:
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:                                     # pragma: no cover - older/newer torch without the accessor
+    def _raw_stream(index):
+        return torch.cuda.current_stream(index).cuda_stream
+
+
 class Runtime:
     """One per (process, device).  Holds the tmx handle; launches on torch's
     current stream so that CUDA-graph capture and stream semantics are torch's."""
@@ -67,7 +74,9 @@ class Runtime:
 
     # ------------------------------------------------------------------ helpers
     def stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        # torch's CURRENT stream of this device as a raw cudaStream_t (the private accessor is ~20x cheaper than
+        # building a torch.cuda.Stream object; it is called once per launch, ~1 800 times per train step)
+        return C.c_void_p(_raw_stream(self.index))
 
     def launch_count(self):
         v = C.c_uint64()
