@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TMX_ABI_VERSION 2
+#define TMX_ABI_VERSION 3
 
 typedef struct tmx_ctx* tmx_handle_t;
 typedef void* tmx_stream_t; /* cudaStream_t */
@@ -241,11 +241,16 @@ int tmx_conv_weights_transpose(tmx_handle_t h, const uint16_t* w_hi, const uint1
  *   [N][H+2][W+2][Cin], the halo kind the forward used); dz_hi/dz_lo: tmx_grad_prepare planes on the zero-ringed
  *   grid [N][H+4][W+4][Cout].  Tensor cores, Cin and Cout multiples of 64; deterministic split-K through a
  *   caller-owned workspace.  For a UP2_IN layer pass low-res H, W, Cout := 4*Cout, phase-packed dz and reduce the
- *   phase gradient with tmx_conv_wgrad_unphase. */
-int tmx_conv2d_wgrad_workspace_bytes(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, size_t* bytes);
+ *   phase gradient with tmx_conv_wgrad_unphase.
+ *   flags: TMX_WGRAD_X_SLACK = at least 128 readable bytes follow each x plane; lets the 16/32-channel 3x3 layers
+ *   read their horizontal taps through overlapping tensor-map rows (PACKED-M mode, conv_wgrad.cu).  Pass the same
+ *   flags to the workspace query. */
+#define TMX_WGRAD_X_SLACK 1
+int tmx_conv2d_wgrad_workspace_bytes(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, int flags,
+                                     size_t* bytes);
 int tmx_conv2d_wgrad(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, float wscale, const uint16_t* x_hi,
                      const uint16_t* x_lo, const uint16_t* dz_hi, const uint16_t* dz_lo, float* dw, float* workspace,
-                     tmx_stream_t s);
+                     int flags, tmx_stream_t s);
 
 /* dwp = gradient of the sub-pixel weights as [9][Cin][4*Cout] (what tmx_conv2d_wgrad writes for a UP2_IN layer);
  * dw[u][v][ci][co] += sum of the phase entries tap (u,v) contributed to (adjoint of tmx_conv_weights_prepare up2_phase,

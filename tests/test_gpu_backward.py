@@ -130,6 +130,15 @@ WGRAD_CASES = [
     (2, 64, 256, 8, 8, 1),
     (1, 256, 64, 96, 96, 3),
     (4, 64, 64, 32, 32, 3),
+    # thin layers: PACKED-M mode (two vertical taps x 64/Cin horizontal taps per MMA, overlapping tensor-map rows)
+    (2, 16, 16, 32, 32, 3),
+    (3, 32, 32, 16, 16, 3),
+    (2, 16, 32, 64, 64, 3),
+    (2, 32, 64, 8, 8, 3),
+    (1, 64, 32, 16, 16, 3),
+    (2, 32, 16, 6, 10, 3),
+    (3, 16, 64, 2, 2, 3),
+    (2, 64, 128, 12, 20, 3),
 ]
 
 
@@ -150,6 +159,11 @@ def test_conv_wgrad_vs_autograd(rt, n, cin, cout, h, w, k):
     assert _nmax(dw.cpu().numpy(), dw_want) <= 1e-4
     rt.conv_wgrad((xa.hi, xa.lo), dz, n, h, w, cin, cout, k, ws, dw)       # accumulates
     assert _nmax(dw.cpu().numpy(), 2 * dw_want) <= 1e-4
+    if cin in (16, 32):
+        # planes without readable slack behind them must take the plain (one tap per MMA) path - same result
+        dw2 = torch.zeros(k, k, cin, cout, device='cuda')
+        rt.conv_wgrad((xa.hi.clone(), xa.lo.clone()), dz, n, h, w, cin, cout, k, ws, dw2)
+        assert _nmax(dw2.cpu().numpy(), dw_want) <= 1e-4
 
 
 def _rel_l2(got, want):

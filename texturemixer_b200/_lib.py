@@ -6,12 +6,13 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'libtmx.so')
 
-TMX_ABI_VERSION = 2
+TMX_ABI_VERSION = 3
 
 # flags / enums (include/tmx.h)
 CONV_LRELU, CONV_RESIDUAL, CONV_UP2_IN, CONV_UP2_OUT, CONV_HALO_REPLICATE, CONV_TORGB, CONV_XMERGE = 1, 2, 4, 8, 16, 32, 64
 ALGO_AUTO, ALGO_FFMA, ALGO_TC, ALGO_TC_K32 = 0, 1, 2, 3
 BLEND_COPY, BLEND_MATTE, BLEND_LERP = 0, 1, 2
+WGRAD_X_SLACK = 1
 
 c_f32p = C.c_void_p
 c_u16p = C.c_void_p
@@ -78,8 +79,8 @@ _SIGNATURES = {
     'tmx_nhwc_to_nchw': (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'tmx_conv2d_dgrad': (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     'tmx_conv_weights_transpose': (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
-    'tmx_conv2d_wgrad_workspace_bytes': (C.c_int, [_P, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_size_t)]),
-    'tmx_conv2d_wgrad': (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
+    'tmx_conv2d_wgrad_workspace_bytes': (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_size_t)]),
+    'tmx_conv2d_wgrad': (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _I, _P]),
     'tmx_conv_wgrad_unphase': (C.c_int, [_P, _P, _P, _I, _I, _P]),
     'tmx_torgb_bwd': (C.c_int, [_P, _P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'tmx_fromrgb_bwd': (C.c_int, [_P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _I, _P]),

@@ -13,6 +13,16 @@
 // Channel counts that are not multiples of 64 are handled by the TMA unit: boxes reach past the channel extent
 // and read zeros, so the thin layers (16/32 channels) run the same kernel with idle rows / columns.
 //
+// PACKED-M mode (3x3, Cin <= 64): a thin layer would leave most of the 128 UMMA rows (and of every 128-B TMA row)
+// empty and pay the TMA row rate nine times per pixel - measured: the 16/32/64-channel layers at 128^2..256^2 took
+// as long as the 256-channel trunk.  Instead the 128 rows of one MMA carry TWO 64-row blocks, each block = one
+// vertical tap u and xwin = 64/Cin consecutive horizontal taps: block row m = dx*Cin + ci reads x[pix + dx] through
+// an OVERLAPPING tensor map (innermost extent xwin*Cin elements, pixel stride Cin: one full 128-B row per pixel
+// carries the horizontal neighbours too).  3*ceil(3/xwin) blocks -> 2 / 3 / 5 "tap groups" for Cin = 16 / 32 / 64
+// instead of 9 taps: 4.5x / 3x / 1.8x fewer TMA rows and MMAs.  Rows whose horizontal tap would be >= 3 are junk
+// (they read the next pixels / up to 96 B behind the plane - the caller vouches for that slack) and are dropped by
+// the reduction.
+//
 // Work split: an output tile is (tap, 128 input channels, BN output channels); the pixel range is cut into
 // `splits` slices so that tiles x splits fills the SMs (split-K).  Each CTA accumulates its slice in TMEM and
 // writes a partial tile to the workspace; tmx_conv2d_wgrad then reduces the slices in a fixed order
@@ -37,6 +47,7 @@ struct WgradParams {
   int co_pad;                      // co_tiles*BN: row length of a partial tile row
   int splits, chunks_per_split;
   float* partial;                  // [splits][taps][ci_tiles*128][Cout]
+  int packed, xwin, bpu, nblocks;  // PACKED-M mode: taps == tap groups; blocks per vertical tap, total blocks
 };
 
 // MN-major SWIZZLE_128B operand: 8 K-rows of 128 B per atom (SBO = 1024 B), 64-channel blocks LBO apart.
@@ -130,10 +141,15 @@ __global__ void __launch_bounds__(kWThreads, 1)
         // A: x planes, halo layout [N][H+2][W+2][Cin], shifted by the tap; channels beyond Cin read zeros
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
-          const int c0 = ci_t * kWM + b * 64;
-          tma_load_4d(sa + b * kBlk, &tm_x_hi, &full_bar[stage], c0, x0 + v + pad_off, y0 + u + pad_off, n0);
-          tma_load_4d(sa + Cfg::kABytes + b * kBlk, &tm_x_lo, &full_bar[stage], c0, x0 + v + pad_off, y0 + u + pad_off,
-                      n0);
+          int c0 = ci_t * kWM + b * 64, xs = x0 + v + pad_off, ys = y0 + u + pad_off;
+          if (p.packed) {       // block bi = (vertical tap, first horizontal tap) through the overlapping-row map
+            const int bi = min(2 * tap + b, p.nblocks - 1);
+            c0 = 0;
+            xs = x0 + (bi % p.bpu) * p.xwin;
+            ys = y0 + bi / p.bpu;
+          }
+          tma_load_4d(sa + b * kBlk, &tm_x_hi, &full_bar[stage], c0, xs, ys, n0);
+          tma_load_4d(sa + Cfg::kABytes + b * kBlk, &tm_x_lo, &full_bar[stage], c0, xs, ys, n0);
         }
         // B: dz planes on the zero-ringed grid [N][H+4][W+4][Cout], interior at offset 2
 #pragma unroll
@@ -246,9 +262,44 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   *o = cur;
 }
 
+// PACKED-M reduction: dw[u][v][ci][co] += scale * sum_s partial[s][group][row][co] with
+// block bi = u*bpu + v/xwin, group = bi/2, row = (bi&1)*64 + (v%xwin)*Cin + ci
+__global__ void __launch_bounds__(256) wgrad_reduce_packed_kernel(const float* __restrict__ partial,
+                                                                  float* __restrict__ dw, int splits, int groups, int Cin,
+                                                                  int Cout, int co_pad, int xwin, int bpu, float scale) {
+  const long long total4 = 9LL * Cin * Cout / 4;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total4) return;
+  const long long e = t * 4;
+  const int co = (int)(e % Cout);
+  const long long q = e / Cout;
+  const int ci = (int)(q % Cin);
+  const int tap = (int)(q / Cin);
+  const int u = tap / 3, v = tap - u * 3;
+  const int bi = u * bpu + v / xwin;
+  const int row = (bi & 1) * 64 + (v % xwin) * Cin + ci;
+  const int group = bi >> 1;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(
+        partial + (((long long)s * groups + group) * kWM + row) * co_pad + co));
+    acc.x += x.x;
+    acc.y += x.y;
+    acc.z += x.z;
+    acc.w += x.w;
+  }
+  float4* o = reinterpret_cast<float4*>(dw + e);
+  float4 cur = *o;
+  cur.x = fmaf(acc.x, scale, cur.x);
+  cur.y = fmaf(acc.y, scale, cur.y);
+  cur.z = fmaf(acc.z, scale, cur.z);
+  cur.w = fmaf(acc.w, scale, cur.w);
+  *o = cur;
+}
+
 int encode_map4(tmx_handle_t h, CUtensorMap* m, const uint16_t* base, int N, int Hp, int Wp, int C, int bw, int bh,
-                int bn) {
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
+                int bn, int xwin = 1) {
+  cuuint64_t dims[4] = {(cuuint64_t)C * xwin, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
   cuuint32_t box[4] = {64u, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -267,7 +318,13 @@ int pow2_div(int v, int cap) {
   return g;
 }
 
-void wgrad_plan(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, int bn_cols, WgradParams& p) {
+bool wgrad_packed(int Cin, int k, int flags) {
+  if (tmx_env_flag("TMX_NO_WGRAD_PACK") || k != 3) return false;
+  if (Cin == 64) return true;                                    // plain map: no slack needed
+  return (Cin == 16 || Cin == 32) && (flags & TMX_WGRAD_X_SLACK) != 0;
+}
+
+void wgrad_plan(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, int bn_cols, int flags, WgradParams& p) {
   p.N = N;
   p.H = H;
   p.W = W;
@@ -285,6 +342,14 @@ void wgrad_plan(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, i
   p.ci_tiles = (Cin + kWM - 1) / kWM;
   p.co_tiles = (Cout + bn_cols - 1) / bn_cols;
   p.co_pad = p.co_tiles * bn_cols;
+  p.packed = wgrad_packed(Cin, k, flags) ? 1 : 0;
+  p.xwin = p.bpu = p.nblocks = 1;
+  if (p.packed) {
+    p.xwin = 64 / Cin;
+    p.bpu = (3 + p.xwin - 1) / p.xwin;
+    p.nblocks = 3 * p.bpu;
+    p.taps = (p.nblocks + 1) / 2;          // tap groups of two 64-row blocks
+  }
   const int tiles = p.taps * p.ci_tiles * p.co_tiles;
   int splits = h->sm_count / tiles;
   if (splits < 1) splits = 1;
@@ -312,20 +377,20 @@ int launch_wgrad(tmx_handle_t h, const CUtensorMap* maps, const WgradParams& p, 
 
 }  // namespace
 
-extern "C" int tmx_conv2d_wgrad_workspace_bytes(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k,
+extern "C" int tmx_conv2d_wgrad_workspace_bytes(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, int flags,
                                                 size_t* bytes) {
   TMX_REQUIRE(h && bytes, TMX_ERR_ARG, "tmx_conv2d_wgrad_workspace_bytes: NULL argument");
   TMX_REQUIRE((k == 1 || k == 3) && N > 0 && H > 0 && W > 0 && Cin % 8 == 0 && Cout % 8 == 0, TMX_ERR_SHAPE,
               "tmx_conv2d_wgrad: needs k in {1,3}, Cin and Cout multiples of 8 (got k=%d Cin=%d Cout=%d)", k, Cin, Cout);
   WgradParams p;
-  wgrad_plan(h, N, H, W, Cin, Cout, k, wgrad_bn(Cout), p);
+  wgrad_plan(h, N, H, W, Cin, Cout, k, wgrad_bn(Cout), flags, p);
   *bytes = (size_t)p.splits * p.taps * p.ci_tiles * kWM * p.co_pad * sizeof(float);
   return TMX_OK;
 }
 
 extern "C" int tmx_conv2d_wgrad(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, float wscale,
                                 const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* dz_hi,
-                                const uint16_t* dz_lo, float* dw, float* workspace, tmx_stream_t s) {
+                                const uint16_t* dz_lo, float* dw, float* workspace, int flags, tmx_stream_t s) {
   TMX_REQUIRE(h && x_hi && x_lo && dz_hi && dz_lo && dw && workspace, TMX_ERR_ARG, "tmx_conv2d_wgrad: NULL argument");
   TMX_REQUIRE((k == 1 || k == 3) && N > 0 && H >= 2 && W >= 2 && Cin % 8 == 0 && Cout % 8 == 0, TMX_ERR_SHAPE,
               "tmx_conv2d_wgrad: needs k in {1,3}, H, W >= 2, Cin and Cout multiples of 8 (got k=%d %dx%d Cin=%d "
@@ -335,12 +400,12 @@ extern "C" int tmx_conv2d_wgrad(tmx_handle_t h, int N, int H, int W, int Cin, in
     TMX_REQUIRE(((uintptr_t)q & 15) == 0, TMX_ERR_ARG, "tmx_conv2d_wgrad: buffers must be 16-byte aligned (%p)", q);
   const int bn_cols = wgrad_bn(Cout);
   WgradParams p;
-  wgrad_plan(h, N, H, W, Cin, Cout, k, bn_cols, p);
+  wgrad_plan(h, N, H, W, Cin, Cout, k, bn_cols, flags, p);
   p.partial = workspace;
   CUtensorMap maps[4];
   int rc;
-  if ((rc = encode_map4(h, &maps[0], x_hi, N, H + 2, W + 2, Cin, p.bw, p.bh, p.bn))) return rc;
-  if ((rc = encode_map4(h, &maps[1], x_lo, N, H + 2, W + 2, Cin, p.bw, p.bh, p.bn))) return rc;
+  if ((rc = encode_map4(h, &maps[0], x_hi, N, H + 2, W + 2, Cin, p.bw, p.bh, p.bn, p.xwin))) return rc;
+  if ((rc = encode_map4(h, &maps[1], x_lo, N, H + 2, W + 2, Cin, p.bw, p.bh, p.bn, p.xwin))) return rc;
   if ((rc = encode_map4(h, &maps[2], dz_hi, N, H + 4, W + 4, Cout, p.bw, p.bh, p.bn))) return rc;
   if ((rc = encode_map4(h, &maps[3], dz_lo, N, H + 4, W + 4, Cout, p.bw, p.bh, p.bn))) return rc;
   cudaStream_t st = (cudaStream_t)s;
@@ -348,9 +413,13 @@ extern "C" int tmx_conv2d_wgrad(tmx_handle_t h, int N, int H, int W, int Cin, in
   else if (bn_cols == 128) rc = launch_wgrad<128>(h, maps, p, st);
   else rc = launch_wgrad<64>(h, maps, p, st);
   if (rc) return rc;
-  const long long total4 = (long long)p.taps * Cin * Cout / 4;
-  wgrad_reduce_kernel<<<tmx_ceil_div(total4, 256), 256, 0, st>>>(workspace, dw, p.splits, p.taps, Cin,
-                                                                 p.ci_tiles * kWM, Cout, p.co_pad, wscale);
+  const long long total4 = (long long)k * k * Cin * Cout / 4;
+  if (p.packed)
+    wgrad_reduce_packed_kernel<<<tmx_ceil_div(total4, 256), 256, 0, st>>>(workspace, dw, p.splits, p.taps, Cin, Cout,
+                                                                          p.co_pad, p.xwin, p.bpu, wscale);
+  else
+    wgrad_reduce_kernel<<<tmx_ceil_div(total4, 256), 256, 0, st>>>(workspace, dw, p.splits, p.taps, Cin,
+                                                                   p.ci_tiles * kWM, Cout, p.co_pad, wscale);
   TMX_LAUNCHED(h, "wgrad_reduce_kernel");
   return TMX_OK;
 }

@@ -277,12 +277,17 @@ class Runtime:
     def conv_wgrad(self, x, dz, n, h, w, cin, cout, k, wscale, dw):
         """dw (HWIO fp32 view of the gradient buffer) += wscale * x^T dz; x = (hi, lo) forward input planes
         [n][h+2][w+2][cin], dz = (hi, lo) planes on the zero-ringed grid [n][h+4][w+4][cout]."""
+        # planes from Runtime.planes() carry 64 elements of slack: the thin layers may read their taps PACKED
+        flags = 0
+        if k == 3 and cin in (16, 32) and all(t.untyped_storage().nbytes() - t.storage_offset() * 2 >=
+                                              (t.numel() + 64) * 2 for t in x):
+            flags = _lib.WGRAD_X_SLACK
         nbytes = C.c_size_t()
-        _lib.check(self.lib.tmx_conv2d_wgrad_workspace_bytes(self.handle, n, h, w, cin, cout, k, C.byref(nbytes)),
+        _lib.check(self.lib.tmx_conv2d_wgrad_workspace_bytes(self.handle, n, h, w, cin, cout, k, flags, C.byref(nbytes)),
                    'tmx_conv2d_wgrad_workspace_bytes')
         ws = self.empty(max(1, nbytes.value // 4))
         _lib.check(self.lib.tmx_conv2d_wgrad(self.handle, n, h, w, cin, cout, k, float(wscale), _ptr(x[0]), _ptr(x[1]),
-                                             _ptr(dz[0]), _ptr(dz[1]), _ptr(dw), _ptr(ws), self.stream()),
+                                             _ptr(dz[0]), _ptr(dz[1]), _ptr(dw), _ptr(ws), flags, self.stream()),
                    'tmx_conv2d_wgrad')
         return dw
 
