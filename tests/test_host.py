@@ -177,3 +177,67 @@ def test_product_does_not_import_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), f
+
+
+def test_reference_checkpoint_round_trip(tmp_path):
+    """misc.load_pkl / save_pkl (misc.py:27-33): a 9-tuple pickled the way the reference does it - instances of
+    `tfutil.Network` whose state is the version-2 dict of tfutil.py:543-550 - loads into this package's Network by
+    variable name, without executing the stored module source; saving writes the same class reference back."""
+    import pickle
+    import pickletools
+    import sys
+    import types
+    from oracle import networks_ref as R
+    from texturemixer_b200 import misc
+    from texturemixer_b200.network import Network
+
+    funcs = dict(E_zg='E_zg', E_zl='E_zl', G='G_res', D_rec='D_patch', D_interp='D_patch', D_blend='D_patch',
+                 Es_zg='E_zg', Es_zl='E_zl', Gs='G_res')
+    rng = np.random.RandomState(5)
+    params = {k: R.init_params(f, rng, **R.CONFIG[f]) for k, f in funcs.items()}
+    params['Gs']['lod'] = np.float32(1.5)
+
+    mod = types.ModuleType('tfutil')
+
+    class RefNetwork:                                   # stand-in for the reference class: only its pickled form
+        def __init__(self, name, func, variables, kwargs):
+            self.state = {'version': 2, 'name': name, 'static_kwargs': dict(kwargs, num_channels=3, resolution=128),
+                          'build_module_src': 'raise SystemExit("module source must never be executed")',
+                          'build_func_name': func, 'variables': list(variables.items())}
+
+        def __getstate__(self):
+            return self.state
+    RefNetwork.__module__, RefNetwork.__qualname__, RefNetwork.__name__ = 'tfutil', 'Network', 'Network'
+    mod.Network = RefNetwork
+    sys.modules['tfutil'] = mod
+    try:
+        path = str(tmp_path / 'network-snapshot-000000.pkl')
+        with open(path, 'wb') as f:
+            pickle.dump(tuple(RefNetwork(k, f_, params[k], R.CONFIG[f_]) for k, f_ in funcs.items()), f,
+                        protocol=pickle.HIGHEST_PROTOCOL)
+    finally:
+        del sys.modules['tfutil']
+    nets = misc.load_pkl(path)
+    assert len(nets) == 9 and all(isinstance(n, Network) for n in nets)
+    for net, (k, f_) in zip(nets, funcs.items()):
+        assert net.name == k and net._build_func_name == f_
+        assert list(net.vars.keys()) == list(params[k].keys())
+        for vn, want in params[k].items():
+            assert np.array_equal(net.get_var(vn), np.asarray(want, np.float32)), (k, vn)
+    assert nets[8].lod == 1.5 and nets[2].lod == 0.0
+    # save: same class reference, same state keys, the file's own module source carried through
+    out = str(tmp_path / 'network-final.pkl')
+    misc.save_pkl(nets, out)
+    assert 'tfutil' not in sys.modules
+    ops = [(op.name, arg) for op, arg, _ in pickletools.genops(open(out, 'rb').read())]
+    globals_named = {arg for name, arg in ops if name in ('GLOBAL', 'STACK_GLOBAL', 'SHORT_BINUNICODE', 'BINUNICODE')
+                     and isinstance(arg, str)}
+    assert 'tfutil' in globals_named and 'Network' in globals_named
+    assert not any('texturemixer_b200' in a for a in globals_named)
+    again = misc.load_pkl(out)
+    for a, b in zip(again, nets):
+        st_a, st_b = a.__getstate__(), b.__getstate__()
+        assert set(st_a) == {'version', 'name', 'static_kwargs', 'build_module_src', 'build_func_name', 'variables'}
+        assert st_a['build_module_src'].startswith('raise SystemExit') and st_a['name'] == st_b['name']
+        for (na, va), (nb, vb) in zip(st_a['variables'], st_b['variables']):
+            assert na == nb and np.array_equal(va, vb)

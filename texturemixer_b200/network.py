@@ -421,6 +421,9 @@ class Network:
             self._copy_stream = torch.cuda.Stream(device=dev)
         copy_stream = self._copy_stream
         bounds = [(b, min(b + minibatch_size, num_items)) for b in range(0, num_items, minibatch_size)]
+        # inputs that already live in page-locked memory (e.g. torch.empty(..., pin_memory=True).numpy()) are copied
+        # to the device straight from the caller's array; pageable ones go through the pinned staging slots
+        pinned_src = [_as_pinned(a) for a in in_arrays]
         slot_free = [None, None]          # event: the H2D that last read input slot s has finished
 
         out_pinned = None                 # results land directly in page-locked arrays that are handed to the caller
@@ -441,8 +444,11 @@ class Network:
                 if graph is not None and slot_done[slot] is not None:
                     copy_stream.wait_event(slot_done[slot])       # the graph's static inputs are free again
                 for i, src in enumerate(in_arrays):
-                    stage = self._pinned(('in', i, slot), shapes[i], torch.float32)
-                    _parallel_copy(stage.numpy(), src[mb_begin:mb_end])       # host copy + cast into pinned memory
+                    if pinned_src[i] is not None:
+                        stage = pinned_src[i][mb_begin:mb_end]                # caller's page-locked array: DMA from it
+                    else:
+                        stage = self._pinned(('in', i, slot), shapes[i], torch.float32)
+                        _parallel_copy(stage.numpy(), src[mb_begin:mb_end])   # host copy + cast into pinned memory
                     if graph is not None:
                         graph[1][i].copy_(stage, non_blocking=True)           # H2D straight into the static input
                     else:
@@ -585,6 +591,20 @@ class Network:
 
     def setup_weight_histograms(self, title=None):
         pass  # TensorBoard summaries are outside the hot path
+
+
+def _as_pinned(a):
+    """torch view of a float32 C-contiguous numpy array if it sits in page-locked memory, else None."""
+    if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags['C_CONTIGUOUS'] and a.flags['ALIGNED']):
+        return None
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')       # read-only arrays: we only read
+            t = torch.from_numpy(a)
+        return t if t.is_pinned() else None
+    except (TypeError, ValueError, RuntimeError):
+        return None
 
 
 _COPY_POOL = None
