@@ -313,6 +313,8 @@ int tmx_convert_output(tmx_handle_t h, const float* x, void* y, int64_t planes, 
                        int shrink, int out_kind, tmx_stream_t s);
 /* out = tanh(in) over n fp32 elements: the generator's image head when lod != 0 (networks.py:482-483). */
 int tmx_tanh_f32(tmx_handle_t h, const float* in, float* out, int64_t n, tmx_stream_t s);
+/* its adjoint: dx = dy * (1 - y^2) with y = tanh(x). */
+int tmx_tanh_bwd(tmx_handle_t h, const float* dy, const float* y, float* dx, int64_t n, tmx_stream_t s);
 /* pixel_norm (networks.py:170-172) on NHWC fp32 [npix][C]: y = x * rsqrt(mean_c x^2 + eps). */
 int tmx_pixel_norm(tmx_handle_t h, const float* x, float* y, int64_t npix, int C, float eps, tmx_stream_t s);
 

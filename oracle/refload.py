@@ -24,14 +24,15 @@ def reference_available():
     return os.path.isfile(os.path.join(REFERENCE_ROOT, 'networks.py'))
 
 
-def reference_functions(filename, names):
+def reference_functions(filename, names, extra_globals=None):
     import numpy as np
     src = open(os.path.join(REFERENCE_ROOT, filename)).read()
     tree = ast.parse(src)
-    wanted = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    wanted = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names]
     missing = set(names) - {n.name for n in wanted}
     assert not missing, 'not found in %s: %s' % (filename, missing)
     ns = {'np': np, '__name__': 'reference_' + filename}
+    ns.update(extra_globals or {})
     exec(compile(ast.Module(body=wanted, type_ignores=[]), os.path.join(REFERENCE_ROOT, filename), 'exec'), ns)
     return {n: ns[n] for n in names}
 

@@ -143,12 +143,44 @@ def gen_network_variants():
     print('networks_variants.npz', sorted(k for k in out if k.endswith('_out0')))
 
 
+# (num_gpus, schedule kwargs): the reference's own config (config.py:96 + run.py:649-658 presets) and the defaults
+SCHEDULES = [
+    (1, dict(lod_initial_resolution=32, lod_training_kimg=1000, lod_transition_kimg=3000, minibatch_base=4,
+             lrate_dict={128: 0.0015, 256: 0.002, 512: 0.003, 1024: 0.003})),
+    (8, dict(lod_initial_resolution=32, lod_training_kimg=1000, lod_transition_kimg=3000, minibatch_base=32,
+             lrate_dict={128: 0.0015, 256: 0.002, 512: 0.003, 1024: 0.003}, max_minibatch_per_gpu={128: 3})),
+    (2, dict()),
+]
+SCHEDULE_NIMG = [0, 1, 999999, 1000000, 1000001, 2500000, 3999999, 4000000, 4700000, 7999000, 8000000, 8000001,
+                 12000000, 500000000]
+
+
+def gen_schedule():
+    """run.py:187-226 TrainingSchedule executed from the reference file -> (lod, resolution, minibatch, lrate, tick)."""
+    import types
+    out = {}
+    for i, (gpus, kw) in enumerate(SCHEDULES):
+        cfg = types.SimpleNamespace(num_gpus=gpus)
+        cls = refload.reference_functions('run.py', ['TrainingSchedule'], extra_globals={'config': cfg})['TrainingSchedule']
+        rows = []
+        for nimg in SCHEDULE_NIMG:
+            s = cls(nimg, types.SimpleNamespace(resolution_log2=7), **kw)
+            rows.append([s.lod, s.resolution, s.minibatch, s.lrate, s.tick_kimg])
+        out['sched%d' % i] = np.array(rows, np.float64)
+    np.savez_compressed(os.path.join(HERE, 'schedule.npz'), **out)
+    print('schedule.npz', {k: v.shape for k, v in out.items()})
+
+
 if __name__ == '__main__':
     assert refload.reference_available(), 'needs /root/reference'
     if 'variants' in sys.argv[1:]:
         gen_network_variants()
         sys.exit(0)
+    if 'schedule' in sys.argv[1:]:
+        gen_schedule()
+        sys.exit(0)
     gen_perm()
     gen_mattes()
     gen_networks()
     gen_network_variants()
+    gen_schedule()

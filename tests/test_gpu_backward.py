@@ -292,3 +292,81 @@ def test_discriminator_input_gradient_vs_autograd(alpha, monkeypatch):
     torch.cuda.synchronize()
     assert dimg.shape == (n, 3, 128, 128)
     assert _rel_l2(dimg.cpu().numpy(), xt.grad.numpy()) <= L2_TOL[alpha]
+
+
+# ---------------------------------------------------------------- progressive growing: gradients at lod > 0
+@pytest.mark.parametrize('lod', [1.0, 1.5, 0.25, 2.0])
+def test_generator_backward_at_lod(lod, monkeypatch):
+    """G_res at an integer / fractional level of detail: lower-resolution ToRGB heads, image upscaling, fade and the
+    trailing tanh on the tape (alpha = 1: exact chain)."""
+    from texturemixer_b200.backward import backward
+    _set_alpha(monkeypatch, 1.0)
+    rng = np.random.RandomState(21)
+    params = R.init_params('G_res', rng, **R.CONFIG['G_res'])
+    params['lod'] = np.float32(lod)
+    net, cfg = _net('G_res', params)
+    n = 2
+    zg = rng.randn(n, 128, 32, 32).astype(np.float32)
+    zl = rng.randn(n, 128, 32, 32).astype(np.float32)
+    dimg = rng.randn(n, 3, 128, 128).astype(np.float32)
+    P = R.to_torch(params, requires_grad=True)
+    zg_t, zl_t = torch.from_numpy(zg).requires_grad_(True), torch.from_numpy(zl).requires_grad_(True)
+    out = R.G_res(zg_t, zl_t, P, **cfg)
+    (out * torch.from_numpy(dimg)).sum().backward()
+    tape = []
+    img = net.get_output_for(torch.from_numpy(zg).cuda(), torch.from_numpy(zl).cuda(), tape=tape)
+    assert _nmax(img.cpu().numpy(), out.detach().numpy()) <= 1e-2
+    flat_grad = torch.zeros_like(net.flat)
+    dzg, dzl = backward(net, tape, [torch.from_numpy(dimg).cuda()], flat_grad)
+    torch.cuda.synchronize()
+    assert _rel_l2(dzg.cpu().numpy(), zg_t.grad.numpy()) <= 1e-3
+    assert _rel_l2(dzl.cpu().numpy(), zl_t.grad.numpy()) <= 1e-3
+    print('worst variable gradient (rel L2):', _check_param_grads(net, flat_grad, P, 1e-3, 1e-2))
+
+
+@pytest.mark.parametrize('func,lod', [('E_zl', 1.0), ('E_zl', 1.5), ('E_zg', 0.5), ('E_zg', 3.0), ('E_zg', 4.75)])
+def test_encoder_backward_at_lod(func, lod, monkeypatch):
+    from texturemixer_b200.backward import backward
+    _set_alpha(monkeypatch, 1.0)
+    rng = np.random.RandomState(23)
+    params = R.init_params(func, rng, **R.CONFIG[func])
+    params['lod'] = np.float32(lod)
+    net, cfg = _net(func, params)
+    n = 3
+    x = rng.uniform(-1, 1, (n, 3, 128, 128)).astype(np.float32)
+    P = R.to_torch(params, requires_grad=True)
+    mu, ls = R.NETWORKS[func](torch.from_numpy(x), P, **cfg)
+    dmu, dls = rng.randn(*mu.shape).astype(np.float32), rng.randn(*ls.shape).astype(np.float32)
+    ((mu * torch.from_numpy(dmu)).sum() + (ls * torch.from_numpy(dls)).sum()).backward()
+    tape = []
+    net.get_output_for(torch.from_numpy(x).cuda(), tape=tape)
+    flat_grad = torch.zeros_like(net.flat)
+    backward(net, tape, [torch.from_numpy(dmu).cuda(), torch.from_numpy(dls).cuda()], flat_grad, want_input_grads=False)
+    torch.cuda.synchronize()
+    print('worst variable gradient (rel L2):', _check_param_grads(net, flat_grad, P, 1e-3, 1e-2))
+
+
+@pytest.mark.parametrize('lod', [1.0, 0.5, 2.5])
+def test_discriminator_gradients_at_lod(lod, monkeypatch):
+    """D_patch at lod > 0: image gradient (through the pooled copies of the input) and variable gradients."""
+    from texturemixer_b200.backward import backward
+    _set_alpha(monkeypatch, 1.0)
+    rng = np.random.RandomState(29)
+    params = R.init_params('D_patch', rng, **R.CONFIG['D_patch'])
+    params['lod'] = np.float32(lod)
+    net, cfg = _net('D_patch', params)
+    n = 8
+    x = rng.uniform(-1, 1, (n, 3, 128, 128)).astype(np.float32)
+    ds = rng.randn(n, 1, 1, 1).astype(np.float32)
+    xt = torch.from_numpy(x).requires_grad_(True)
+    P = R.to_torch(params, requires_grad=True)
+    scores = R.D_patch(xt, P, **cfg)
+    (scores * torch.from_numpy(ds)).sum().backward()
+    tape = []
+    got = net.get_output_for(torch.from_numpy(x).cuda(), tape=tape)
+    assert _nmax(got.cpu().numpy(), scores.detach().numpy()) <= 1e-3
+    flat_grad = torch.zeros_like(net.flat)
+    (dimg,) = backward(net, tape, [torch.from_numpy(ds).cuda()], flat_grad, want_input_grads=True)
+    torch.cuda.synchronize()
+    assert _rel_l2(dimg.cpu().numpy(), xt.grad.numpy()) <= 1e-3
+    print('worst variable gradient (rel L2):', _check_param_grads(net, flat_grad, P, 1e-3, 1e-2))

@@ -238,15 +238,6 @@ def test_lod_and_pixelnorm_variants_match_reference_golden(func, lod, pn):
         assert _nmax(a, want[i].numpy()) <= TOL
 
 
-def test_training_tape_at_lod_is_refused():
-    rng = np.random.RandomState(2)
-    params = R.init_params('E_zl', rng, **R.CONFIG['E_zl'])
-    params['lod'] = np.float32(1.0)
-    net = _make('E_zl', params)
-    with pytest.raises(NotImplementedError):
-        net.get_output_for(torch.from_numpy(_inputs('E_zl', rng, 1)[0]).cuda(), tape=[])
-
-
 def test_output_conversion_kernel_bit_exact():
     """tfutil.py:649-659 on the device (tmx_convert_output): x * mul + add, avg-pool shrink, round half to even,
     saturate - bit-exact against numpy for uint8, and the shrink path against an fp32 mean."""

@@ -103,3 +103,31 @@ def test_adam_nonfinite_ema_vs_oracle(rt):
     assert applied == [True, True, False, True, True]
     # the cached tensor-core weight planes were invalidated by the step
     assert E._owner()._version > 0
+
+
+@pytest.mark.parametrize('lod,mirror', [(0.0, False), (1.0, False), (1.25, True), (2.0, False), (0.5, True)])
+def test_process_reals_vs_numpy(rt, lod, mirror):
+    """run.py:68-102: dynamic range, mirror augmentation, FadeLOD, UpscaleLOD restated in numpy."""
+    from texturemixer_b200.train import process_reals
+    rng = np.random.RandomState(int(lod * 100) + 3)
+    r = 128 // 2 ** int(np.floor(lod))
+    x = rng.randint(0, 256, (5, 3, r, r)).astype(np.uint8)
+    fade, orig = process_reals(torch.from_numpy(x).cuda(), lod, lr_mirror_augment=mirror, ud_mirror_augment=mirror,
+                               rng=np.random.RandomState(9))
+    scale = np.float32(2.0) / np.float32(255.0)
+    y = x.astype(np.float32) * scale + (np.float32(-1.0) - np.float32(0.0) * scale)
+    if mirror:
+        draw = np.random.RandomState(9)
+        f = draw.uniform(0.0, 1.0, 5) >= 0.5
+        y = np.where(f[:, None, None, None], y[:, :, :, ::-1], y)
+        f = draw.uniform(0.0, 1.0, 5) >= 0.5
+        y = np.where(f[:, None, None, None], y[:, :, ::-1, :], y)
+    box = y.reshape(5, 3, r // 2, 2, r // 2, 2).mean(axis=(3, 5), keepdims=True)
+    box = np.tile(box, (1, 1, 1, 2, 1, 2)).reshape(5, 3, r, r)
+    t = np.float32(lod) - np.floor(np.float32(lod))
+    yf = y + (box - y) * t
+    k = 2 ** int(np.floor(lod))
+    up = lambda a: np.repeat(np.repeat(a, k, axis=2), k, axis=3)
+    assert orig.shape == (5, 3, 128, 128) and fade.shape == (5, 3, 128, 128)
+    assert np.array_equal(orig.cpu().numpy(), up(y))
+    assert np.abs(fade.cpu().numpy() - up(yf)).max() <= 1e-6

@@ -32,7 +32,10 @@ def _grads(P):
                            for k, t in P.items() if k != 'lod'])
 
 
-def test_train_step_vs_oracle():
+@pytest.mark.parametrize('lod', [0.0, 1.5])
+def test_train_step_vs_oracle(lod):
+    """lod = 1.5: the same step in the middle of a progressive-growing fade (run.py:310: every network at lod 1.5 -
+    64x64 heads blended with the 32x32 ones; critics evaluated without CUDA graphs since the fade is baked in)."""
     from texturemixer_b200.train import Trainer, default_config, NET_FUNCS
     cfg = default_config(scale_h=2, scale_w=2)
     tr = Trainer(cfg, seed=1000)
@@ -52,6 +55,7 @@ def test_train_step_vs_oracle():
                 net.set_var(vn, 0.1 * rng.randn(*v.shape).astype(np.float32))
         params[k] = type(R.init_params(ofunc[k], np.random.RandomState(0), **R.CONFIG[ofunc[k]]))(
             (vn, net.get_var(vn)) for vn in net.vars)
+        params[k]['lod'] = np.float32(lod)
     for src, dst in (('E_zg', 'Es_zg'), ('E_zl', 'Es_zl'), ('G', 'Gs')):
         tr.nets[dst].copy_vars_from(tr.nets[src])
     w0 = {k: _flat(params[k]) for k in names}
@@ -99,7 +103,7 @@ def test_train_step_vs_oracle():
         off += w0[k].size
 
     # ---------------- device step
-    rep = tr.step(torch.from_numpy(reals).cuda(), draws)
+    rep = tr.step(torch.from_numpy(reals).cuda(), draws, lod=lod)
     torch.cuda.synchronize()
     assert all(int(rep[k + '/skipped'].item()) == 0 for k in ('D_rec', 'D_interp', 'D_blend', 'EG'))
     step = 0.0015 * np.sqrt(1 - 0.99)      # first Adam step moves every weight by ~ lr_t * 10 * sign(g) = 1.5e-3
@@ -110,7 +114,8 @@ def test_train_step_vs_oracle():
         # the first Adam step is +-1.5e-3 * sign(g): only gradients within the (leaky-ReLU-flip limited) device
         # error of zero may land on the other side
         assert bad.mean() <= 0.02, (k, float(bad.mean()))
-        assert moved.mean() > 0.9 and np.abs(got - w0[k]).max() <= 1.05 * step * 10 + 1e-6
+        # (at lod 1.5 the 128x128 blocks and lod-0 heads take no part: their gradients are zero on both sides)
+        assert moved.mean() > (0.9 if lod == 0 else 0.75) and np.abs(got - w0[k]).max() <= 1.05 * step * 10 + 1e-6
     # EMA: Gs = lerp(G, Gs, 0.999) with Gs initialised to the pre-step G
     g_new = np.concatenate([tr.nets['G'].get_var(vn).reshape(-1) for vn in tr.nets['G'].vars if vn != 'lod'])
     gs = np.concatenate([tr.nets['Gs'].get_var(vn).reshape(-1) for vn in tr.nets['Gs'].vars if vn != 'lod'])

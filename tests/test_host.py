@@ -241,3 +241,19 @@ def test_reference_checkpoint_round_trip(tmp_path):
         assert st_a['build_module_src'].startswith('raise SystemExit') and st_a['name'] == st_b['name']
         for (na, va), (nb, vb) in zip(st_a['variables'], st_b['variables']):
             assert na == nb and np.array_equal(va, vb)
+
+
+def test_training_schedule_matches_reference_class():
+    """train.TrainingSchedule vs the reference's own class (run.py:187-226) executed from the reference file by
+    tests/golden/make_golden.py -> schedule.npz: lod, resolution, minibatch, lrate, tick at phase boundaries."""
+    import types
+    from texturemixer_b200.train import TrainingSchedule
+    src = open(os.path.join(GOLDEN, 'make_golden.py')).read()
+    ns = {}
+    exec(src[src.index('SCHEDULES = ['):src.index('def gen_schedule')], ns)
+    g = np.load(os.path.join(GOLDEN, 'schedule.npz'))
+    for i, (gpus, kw) in enumerate(ns['SCHEDULES']):
+        for nimg, want in zip(ns['SCHEDULE_NIMG'], g['sched%d' % i]):
+            s = TrainingSchedule(nimg, 7, num_gpus=gpus, **kw)
+            got = [s.lod, s.resolution, s.minibatch, s.lrate, s.tick_kimg]
+            assert np.array_equal(np.array(got, np.float64), want), (i, nimg, got, want)

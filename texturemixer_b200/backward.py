@@ -66,6 +66,47 @@ def _combine(rt, act, contribs, want_planes, want_f32, mask_y=None, dbias=None, 
                            want_f32=want_f32, dbias=dbias, phase_pack=phase_pack)
 
 
+def _scaled(rt, x, a):
+    """a * x (fp32, any shape)."""
+    x = x.contiguous()
+    out = rt.empty(*x.shape)
+    _lib.check(rt.lib.tmx_axpb(rt.handle, _ptr(x), _ptr(out), x.numel(), float(a), 0.0, rt.stream()), 'tmx_axpb')
+    return out
+
+
+def _accumulate(rt, table, key, g):
+    """table[key] += g for gradients that reach one tensor along several paths."""
+    cur = table.get(key)
+    if cur is None:
+        table[key] = g
+    else:
+        out = rt.empty(*g.shape)
+        _lib.check(rt.lib.tmx_add_f32(rt.handle, _ptr(cur.contiguous()), _ptr(g.contiguous()), _ptr(out), g.numel(),
+                                      rt.stream()), 'tmx_add_f32')
+        table[key] = out
+
+
+def _block_sum(rt, g, factor):
+    """Adjoint of upscale2d of an NCHW image (networks.py:80-88): sum over each factor x factor block."""
+    n, c, h, w = g.shape
+    out = rt.empty(n, c, h // factor, w // factor)
+    _lib.check(rt.lib.tmx_convert_output(rt.handle, _ptr(g.contiguous()), _ptr(out), n * c, h, w,
+                                         float(factor * factor), 0.0, int(factor), 0, rt.stream()),
+               'tmx_convert_output')     # mean of (x * f^2) over the block == the block sum (f^2 is a power of two)
+    return out
+
+
+def _spread(rt, g, factor):
+    """Adjoint of the VALID average pool of an NCHW image (networks.py:131-136): g / f^2 copied to the block."""
+    n, c, h, w = g.shape
+    dev = g.device
+    ih = torch.arange(h * factor, dtype=torch.int32, device=dev).div_(factor, rounding_mode='floor')
+    iw = torch.arange(w * factor, dtype=torch.int32, device=dev).div_(factor, rounding_mode='floor')
+    up = rt.latent_blend([g.contiguous()], h * factor, w * factor, _lib.BLEND_COPY,
+                         idx_h=[ih.repeat(n, 1).contiguous()], idx_w=[iw.repeat(n, 1).contiguous()])
+    return _scaled(rt, up, 1.0 / (factor * factor))
+
+
 def conv_wgrad_into(rt, net, rec, x_planes, dz, dw):
     """Weight gradient of a (non-upsampling) conv record into `dw` (HWIO view of the flat gradient).  A conv whose
     input was channel-padded (513 -> 576 after minibatch stddev) goes through a padded scratch gradient."""
@@ -118,7 +159,33 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
     for pos in range(len(tape) - 2, -1, -1):
         rec = tape[pos]
         kind = rec['kind']
-        if kind == 'slice':
+        if kind == 'tanh':                 # trailing tanh of G_res at lod != 0 (networks.py:482-483)
+            g = by_tensor.pop(id(rec['y']), None)
+            if g is not None:
+                dx = rt.empty(*g.shape)
+                _lib.check(rt.lib.tmx_tanh_bwd(rt.handle, _ptr(g.contiguous()), _ptr(rec['y']), _ptr(dx), g.numel(),
+                                               rt.stream()), 'tmx_tanh_bwd')
+                _accumulate(rt, by_tensor, id(rec['x']), dx)
+        elif kind == 'imgup':              # upscale2d of an image head (networks.py:476-477)
+            g = by_tensor.pop(id(rec['y']), None)
+            if g is not None:
+                _accumulate(rt, by_tensor, id(rec['x']), _block_sum(rt, g, rec['factor']))
+        elif kind == 'imglerp':            # fade between two image heads: a + (b - a) t
+            g = by_tensor.pop(id(rec['y']), None)
+            if g is not None:
+                _accumulate(rt, by_tensor, id(rec['a']), _scaled(rt, g, 1.0 - rec['t']))
+                _accumulate(rt, by_tensor, id(rec['b']), _scaled(rt, g, rec['t']))
+        elif kind == 'lerp':               # fade between two feature maps (networks.py:281,373,573)
+            contribs = grads.pop(rec['y'])
+            if contribs:
+                _, g = _combine(rt, rec['y'], contribs, want_planes=False, want_f32=True)
+                grads.add(rec['a'], ('f32', _scaled(rt, g, 1.0 - rec['t'])))
+                grads.add(rec['b'], ('f32', _scaled(rt, g, rec['t'])))
+        elif kind == 'imgpool':            # the input image pooled for a lower level of detail (networks.py:278,281)
+            g = input_grads.pop(('img', id(rec['y'])), None)
+            if g is not None:
+                _accumulate(rt, input_grads, ('img', id(rec['x'])), _spread(rt, g, rec['factor']))
+        elif kind == 'slice':
             g = by_tensor.get(id(rec['out']))
             if g is not None:
                 a = rec['x']
@@ -251,7 +318,8 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
             _lib.check(rt.lib.tmx_fromrgb_bwd(rt.handle, _ptr(img), _ptr(dz), _ptr(wv.value), float(rec['wscale']),
                                               _ptr(gview(rec['w'])), _ptr(dimg), n, cimg, h, w_, rec['cout'],
                                               rt.stream()), 'tmx_fromrgb_bwd')
-            input_grads[('img', id(img))] = dimg
+            if dimg is not None:
+                _accumulate(rt, input_grads, ('img', id(img)), dimg)
         elif kind == 'concat':
             y = rec['y']
             contribs = grads.pop(y)
@@ -264,5 +332,5 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
             raise NotImplementedError('backward of tape record %r' % kind)
     if 'concat' in input_grads:
         return input_grads['concat']
-    imgs = [v for k, v in input_grads.items() if isinstance(k, tuple) and k[0] == 'img']
+    imgs = [v for k, v in input_grads.items() if isinstance(k, tuple) and k[0] == 'img' and v is not None]
     return imgs if imgs else []

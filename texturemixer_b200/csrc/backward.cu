@@ -351,7 +351,9 @@ template <int COUT>
 __global__ void __launch_bounds__(256) fromrgb_bwd_kernel(const float* __restrict__ img, const float* __restrict__ dz,
                                                           const float* __restrict__ w, float wscale,
                                                           float* __restrict__ dw, float* __restrict__ dimg,
-                                                          long long npix, int HW, int Cimg) {
+                                                          long long npix, int HW, int Cimg, int Ctot, int c0) {
+  // COUT channels [c0, c0 + COUT) of a head with Ctot output channels (Ctot > 64: one launch per 64-channel chunk,
+  // the chunks after the first ADD their share to dimg - same stream, so the launches are ordered)
   __shared__ float red[4][COUT][8];
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -363,7 +365,7 @@ __global__ void __launch_bounds__(256) fromrgb_bwd_kernel(const float* __restric
     const long long n = p / HW;
     const int hw = (int)(p % HW);
     for (int c = 0; c < Cimg; ++c) iv[c] = __ldg(img + (n * Cimg + c) * HW + hw);
-    const float4* zp = reinterpret_cast<const float4*>(dz + p * COUT);
+    const float4* zp = reinterpret_cast<const float4*>(dz + p * Ctot + c0);
 #pragma unroll
     for (int o4 = 0; o4 < COUT / 4; ++o4) {
       const float4 t = __ldg(zp + o4);
@@ -373,8 +375,9 @@ __global__ void __launch_bounds__(256) fromrgb_bwd_kernel(const float* __restric
       for (int c = 0; c < Cimg; ++c) {
         float acc = 0.f;
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) acc = fmaf(zv[o], __ldg(w + c * COUT + o), acc);
-        dimg[(n * Cimg + c) * HW + hw] = acc * wscale;
+        for (int o = 0; o < COUT; ++o) acc = fmaf(zv[o], __ldg(w + c * Ctot + c0 + o), acc);
+        float* dst = dimg + (n * Cimg + c) * HW + hw;
+        *dst = c0 == 0 ? acc * wscale : fmaf(acc, wscale, *dst);
       }
     }
   }
@@ -393,22 +396,31 @@ __global__ void __launch_bounds__(256) fromrgb_bwd_kernel(const float* __restric
     float sacc = 0.f;
 #pragma unroll
     for (int wv = 0; wv < 8; ++wv) sacc += red[c][o][wv];
-    atomicAdd(dw + c * COUT + o, sacc * wscale);
+    atomicAdd(dw + c * Ctot + c0 + o, sacc * wscale);
   }
 }
 
 extern "C" int tmx_fromrgb_bwd(tmx_handle_t h, const float* img, const float* dz, const float* w, float wscale,
                                float* dw, float* dimg, int N, int Cimg, int H, int W, int Cout, tmx_stream_t s) {
   TMX_REQUIRE(h && img && dz && w && dw, TMX_ERR_ARG, "tmx_fromrgb_bwd: NULL argument");
-  TMX_REQUIRE(N > 0 && H > 0 && W > 0 && Cimg >= 1 && Cimg <= 4 && (Cout == 16 || Cout == 32 || Cout == 64),
-              TMX_ERR_SHAPE, "tmx_fromrgb_bwd: bad shape (Cout in {16,32,64}, Cimg <= 4), got Cout=%d Cimg=%d", Cout, Cimg);
+  TMX_REQUIRE(N > 0 && H > 0 && W > 0 && Cimg >= 1 && Cimg <= 4 && (Cout == 16 || Cout == 32 || Cout % 64 == 0),
+              TMX_ERR_SHAPE, "tmx_fromrgb_bwd: bad shape (Cout 16, 32 or a multiple of 64, Cimg <= 4), got Cout=%d Cimg=%d",
+              Cout, Cimg);
   const long long npix = (long long)N * H * W;
   dim3 grid(tmx_ceil_div(npix, 256));
   cudaStream_t st = (cudaStream_t)s;
-  if (Cout == 16) fromrgb_bwd_kernel<16><<<grid, 256, 0, st>>>(img, dz, w, wscale, dw, dimg, npix, H * W, Cimg);
-  else if (Cout == 32) fromrgb_bwd_kernel<32><<<grid, 256, 0, st>>>(img, dz, w, wscale, dw, dimg, npix, H * W, Cimg);
-  else fromrgb_bwd_kernel<64><<<grid, 256, 0, st>>>(img, dz, w, wscale, dw, dimg, npix, H * W, Cimg);
-  TMX_LAUNCHED(h, "fromrgb_bwd_kernel");
+  if (Cout == 16) {
+    fromrgb_bwd_kernel<16><<<grid, 256, 0, st>>>(img, dz, w, wscale, dw, dimg, npix, H * W, Cimg, 16, 0);
+    TMX_LAUNCHED(h, "fromrgb_bwd_kernel");
+  } else if (Cout == 32) {
+    fromrgb_bwd_kernel<32><<<grid, 256, 0, st>>>(img, dz, w, wscale, dw, dimg, npix, H * W, Cimg, 32, 0);
+    TMX_LAUNCHED(h, "fromrgb_bwd_kernel");
+  } else {
+    for (int c0 = 0; c0 < Cout; c0 += 64) {   // the lower-resolution heads of progressive growing: 3 -> 128..512
+      fromrgb_bwd_kernel<64><<<grid, 256, 0, st>>>(img, dz, w, wscale, dw, dimg, npix, H * W, Cimg, Cout, c0);
+      TMX_LAUNCHED(h, "fromrgb_bwd_kernel");
+    }
+  }
   return TMX_OK;
 }
 

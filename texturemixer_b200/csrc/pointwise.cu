@@ -749,6 +749,24 @@ extern "C" int tmx_tanh_f32(tmx_handle_t h, const float* in, float* out, int64_t
   return TMX_OK;
 }
 
+// adjoint of the trailing tanh: dx = dy * (1 - y^2), y = tanh(x)
+__global__ void __launch_bounds__(256) tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                       float* __restrict__ dx, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float t = __ldg(y + i);
+    dx[i] = __ldg(dy + i) * (1.f - t * t);
+  }
+}
+
+extern "C" int tmx_tanh_bwd(tmx_handle_t h, const float* dy, const float* y, float* dx, int64_t n, tmx_stream_t s) {
+  TMX_REQUIRE(h && dy && y && dx && n > 0, TMX_ERR_ARG, "tmx_tanh_bwd: bad argument");
+  const int grid = (int)(n / 256 + 1 < 148LL * 16 ? n / 256 + 1 : 148LL * 16);
+  tanh_bwd_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(dy, y, dx, n);
+  TMX_LAUNCHED(h, "tanh_bwd_kernel");
+  return TMX_OK;
+}
+
 // ---------------------------------------------------------------- pixel_norm (networks.py:170-172)
 // y[p][c] = x[p][c] * rsqrt(mean_c x[p][c]^2 + eps) on NHWC fp32; one warp per pixel, channels strided over lanes.
 __global__ void __launch_bounds__(256) pixel_norm_kernel(const float* __restrict__ x, float* __restrict__ y,

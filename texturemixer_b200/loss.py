@@ -190,11 +190,14 @@ class EGForward:
 
 
 def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, rec_G_weight=1.0, pixel_weight=200.0,
-                interp_G_weight=1.0, blend_interp_G_weight=1.0):
-    """Loss terms of `EG_wgan` on the images of `fwd` and the whole reverse pass into `grads`."""
+                interp_G_weight=1.0, blend_interp_G_weight=1.0, reals_fade=None):
+    """Loss terms of `EG_wgan` on the images of `fwd` and the whole reverse pass into `grads`.  `reals_fade`: the
+    target of the pixel loss (loss.py:143) when it differs from what the encoders saw (fractional lod)."""
     rt = fwd.rt
     E_zg, E_zl, G, G_fcn = fwd.nets
     reals, n, c, lat, H, W, pins = fwd.reals, fwd.n, fwd.c, fwd.lat, fwd.H, fwd.W, fwd.pins
+    if reals_fade is not None:
+        reals = reals_fade
     inv_n = 1.0 / n
     report = {}
     rec = fwd.rec
@@ -285,13 +288,23 @@ def tangent_forward(D, tape, v):
     (primal, tangent) pair at the minibatch-stddev layer."""
     rt = D.rt
     tang, tin, mb = {}, {}, None
+    timg = {}          # tangents of the pooled copies of the input image (progressive growing, lod > 0)
     for pos, rec in enumerate(tape[:-1]):
         kind = rec['kind']
-        if kind == 'fromrgb':
+        if kind == 'imgpool':
+            from .networks import _pool_image
+            timg[id(rec['y'])] = _pool_image(rt, timg.get(id(rec['x']), v), rec['factor'])
+        elif kind == 'lerp':
+            from .networks import _lerp_lod
+            ta, tb = rt.split_unpack(tang[id(rec['a'])]), rt.split_unpack(tang[id(rec['b'])])
             y = rec['y']
-            t = rt.fromrgb(v, D.vars[rec['w']].value, None, rec['wscale'], rec['cout'], lrelu=False)
+            tang[id(y)] = Act(y.n, y.h, y.w, y.c, f32=_lerp_lod(rt, ta.f32, tb.f32, rec['t']))
+        elif kind == 'fromrgb':
+            y = rec['y']
+            vin = timg.get(id(rec['img']), v)
+            t = rt.fromrgb(vin, D.vars[rec['w']].value, None, rec['wscale'], rec['cout'], lrelu=False)
             t.f32 = _mask(rt, t.f32, y.f32, y.n, y.h, y.w, y.c)
-            tin[pos] = v
+            tin[pos] = vin
             tang[id(y)] = t
         elif kind == 'conv':
             xin, y = tang[id(rec['x'])], rec['y']

@@ -180,6 +180,8 @@ class Network:
         self._version = 0              # bumped whenever variable values change
         self._prepared = {}            # per-variable tensor-core weight planes (w_hi, w_lo, version)
         self._grad_slots = {}          # name -> (offset, size, shape) inside flat / flat gradient buffers
+        self._shared_owner = None      # the network whose variables this view shares (reuse=True), if any
+        self._lod_host = 0.0
         self._rt = None
         self._device = None
         self._staging = {}
@@ -197,7 +199,7 @@ class Network:
 
     @property
     def lod(self):
-        return float(self._lod_host)
+        return float(self._owner()._lod_host)
 
     def _init_graph(self, share_with=None):
         self.input_names = []
@@ -318,6 +320,16 @@ class Network:
             self._owner()._lod_host = float(arr)
             self._lod_host = float(arr)
         self._touch()
+
+    def set_lod(self, value):
+        """The `tf.assign(net.find_var('lod'), lod_in)` of run.py:310: level of detail of the next evaluations."""
+        value = float(np.float32(value))
+        o = self._owner()
+        if 'lod' in self.vars and (o._lod_host != value or self._lod_host != value):
+            self.vars['lod'].value.fill_(value)
+            o._lod_host = value
+            self._lod_host = value
+            self._touch()
 
     def set_vars(self, name_to_value):
         for k, val in name_to_value.items():

@@ -12,8 +12,8 @@ Layer variants on the device: the reference defaults (use_wscale=True,
 fused_scale=False, leaky ReLU, float32) plus `use_pixelnorm` in the generator;
 the others raise NotImplementedError.  Progressive growing
 (`lod` > 0, integer or fractional: the tf.cond trees of networks.py:276-282,
-368-374, 473-479, 568-574) is evaluated for inference; a training tape at
-lod != 0 raises."""
+368-374, 473-479, 568-574) is evaluated and recorded on the tape like every
+other layer."""
 import functools
 
 import numpy as np
@@ -158,8 +158,10 @@ def downscale2d(x, factor=2):
     if x.act is None and x.nchw is not None:
         # the network's input image pooled for a lower level of detail (networks.py:278,281): one VALID average
         # pool of the whole factor on the NCHW planes (3 channels: not an NHWC/tensor-core layout)
-        _no_tape_at_lod(ctx)
-        return T(shape, ctx, nchw=_pool_image(ctx.rt, x.nchw, factor))
+        pooled = _pool_image(ctx.rt, x.nchw, factor)
+        if ctx.tape is not None:
+            ctx.tape.append(dict(kind='imgpool', x=x.nchw, y=pooled, factor=factor))
+        return T(shape, ctx, nchw=pooled)
     a = _act_of(x)
     f = factor
     while f > 1:
@@ -170,12 +172,6 @@ def downscale2d(x, factor=2):
         a = b
         f //= 2
     return T(shape, ctx, act=a)
-
-
-def _no_tape_at_lod(ctx):
-    if ctx.tape is not None:
-        raise NotImplementedError('training (a backward tape) at lod != 0 is not implemented (SURVEY N1); '
-                                  'inference at any lod is')
 
 
 def _pool_image(rt, img, factor):
@@ -282,10 +278,12 @@ def _encoder_grow(ctx, images_in, resolution_log2, min_res_log2, block, fromrgb,
     def lerp_lod(x, y, t):
         if ctx.mode == 'template':
             return x
-        _no_tape_at_lod(ctx)
         rt = ctx.rt
         a, b = rt.split_unpack(_act_of(x)), rt.split_unpack(_act_of(y))
-        return T(x.shape, ctx, act=Act(a.n, a.h, a.w, a.c, f32=_lerp_lod(rt, a.f32, b.f32, t)))
+        out = Act(a.n, a.h, a.w, a.c, f32=_lerp_lod(rt, a.f32, b.f32, t))
+        if ctx.tape is not None:
+            ctx.tape.append(dict(kind='lerp', a=a, b=b, y=out, t=float(np.float32(t))))
+        return T(x.shape, ctx, act=out)
 
     def grow(res, lod):
         def x_fn():
@@ -499,14 +497,18 @@ def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_bas
         shape = [t.shape[0], t.shape[1], _mul(t.shape[2], factor), _mul(t.shape[3], factor)]
         if ctx.mode == 'template':
             return T(shape, ctx)
-        _no_tape_at_lod(ctx)
-        return T(shape, ctx, nchw=_upscale_image(ctx.rt, t.nchw, factor))
+        up = _upscale_image(ctx.rt, t.nchw, factor)
+        if ctx.tape is not None:
+            ctx.tape.append(dict(kind='imgup', x=t.nchw, y=up, factor=factor))
+        return T(shape, ctx, nchw=up)
 
     def lerp_lod(a, b, t):
         if ctx.mode == 'template':
             return a
-        _no_tape_at_lod(ctx)
-        return T(a.shape, ctx, nchw=_lerp_lod(ctx.rt, a.nchw, b.nchw, t))
+        out = _lerp_lod(ctx.rt, a.nchw, b.nchw, t)
+        if ctx.tape is not None:
+            ctx.tape.append(dict(kind='imglerp', a=a.nchw, b=b.nchw, y=out, t=float(np.float32(t))))
+        return T(a.shape, ctx, nchw=out)
 
     def grow(x, res, lod):                                                 # networks.py:473-479
         y = block(x, res)
@@ -534,7 +536,10 @@ def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_bas
     images_out = grow(combo_in, latent_res_log2, resolution_log2 - latent_res_log2)
     if ctx.mode == 'run' and tanh_at_end and not getattr(images_out, 'tanh_done', False):
         # lod != 0: tf.nn.tanh follows the fade / upscale of the lower-resolution heads (networks.py:482-483)
-        images_out = T(images_out.shape, ctx, nchw=_tanh(ctx.rt, images_out.nchw))
+        pre = images_out.nchw
+        images_out = T(images_out.shape, ctx, nchw=_tanh(ctx.rt, pre))
+        if ctx.tape is not None:
+            ctx.tape.append(dict(kind='tanh', x=pre, y=images_out.nchw))
     images_out.name = 'images_out'
     return images_out
 

@@ -11,8 +11,10 @@ Data parallel like the reference: every rank holds all nine networ
 the global batch, and `Optimizer.apply_updates` sums each network's flat gradient across ranks with one NCCL
 all-reduce, scales by 1/world and steps Adam(beta1 0, beta2 0.99, eps 1e-8; config.py:84-87).
 
-gram_weight is 0 (VGG-19 weights not redistributable - stated deviation); lod > 0 (progressive
-growing) is not implemented."""
+gram_weight is 0 (VGG-19 weights not redistributable - stated deviation).  Progressive growing
+(SURVEY N1): `TrainingSchedule` (run.py:187-226) gives the level of detail per step, `process_reals`
+(run.py:68-102) fades / upscales the reals, and `Trainer.step(..., lod=...)` assigns it to every network
+(run.py:310) before the losses are evaluated."""
 import gc
 import os
 
@@ -46,6 +48,75 @@ def default_config(train_size=128, fmap_base=1024, fmap_max=512, latent_channels
         crop_aware=True,      # G_fcn decodes only the latent window each random_crop depends on (loss.crop_window)
         loss=dict(rec_G_weight=1.0, pixel_weight=200.0, interp_G_weight=1.0, blend_interp_G_weight=1.0),
         levels=int(np.log2(latent_res)))
+
+
+class TrainingSchedule:
+    """run.py:187-226: level of detail, resolution, minibatch and learning rate as functions of the images shown."""
+
+    def __init__(self, cur_nimg, resolution_log2, num_gpus=1, lod_initial_resolution=4, lod_training_kimg=1500,
+                 lod_transition_kimg=1500, minibatch_base=16, minibatch_dict=None, max_minibatch_per_gpu=None,
+                 lrate_base=0.001, lrate_dict=None, tick_kimg_base=1, tick_kimg_dict=None):
+        minibatch_dict, max_minibatch_per_gpu = minibatch_dict or {}, max_minibatch_per_gpu or {}
+        lrate_dict, tick_kimg_dict = lrate_dict or {}, tick_kimg_dict or {}
+        self.kimg = cur_nimg / 1000.0
+        phase_dur = lod_training_kimg + lod_transition_kimg
+        phase_idx = int(np.floor(self.kimg / phase_dur)) if phase_dur > 0 else 0
+        phase_kimg = self.kimg - phase_idx * phase_dur
+        self.lod = resolution_log2
+        self.lod -= np.floor(np.log2(lod_initial_resolution))
+        self.lod -= phase_idx
+        if lod_transition_kimg > 0:
+            self.lod -= max(phase_kimg - lod_training_kimg, 0.0) / lod_transition_kimg
+        self.lod = max(self.lod, 0.0)
+        self.resolution = 2 ** (resolution_log2 - int(np.floor(self.lod)))
+        self.minibatch = minibatch_dict.get(self.resolution, minibatch_base)
+        self.minibatch -= self.minibatch % num_gpus
+        if self.resolution in max_minibatch_per_gpu:
+            self.minibatch = min(self.minibatch, max_minibatch_per_gpu[self.resolution] * num_gpus)
+        self.lrate = lrate_dict.get(self.resolution, lrate_base)
+        self.tick_kimg = tick_kimg_dict.get(self.resolution, tick_kimg_base)
+
+
+def process_reals(x, lod, lr_mirror_augment=False, ud_mirror_augment=False, drange_data=(0, 255), drange_net=(-1, 1),
+                  rng=None):
+    """run.py:68-102 on the device.  x: [n,C,r,r] uint8 or float device tensor at the dataset's CURRENT resolution
+    r = R / 2^floor(lod) (dataset.configure, run.py:430).  -> (reals_fade, reals_orig), fp32 [n,C,R,R]:
+    dynamic range (misc.py:38-43: x * scale + bias), optional mirror augmentation (one uniform per sample,
+    flipped when >= 0.5), FadeLOD (lerp towards the 2x2 box-filtered image by lod - floor(lod)), UpscaleLOD
+    (nearest-neighbour by 2^floor(lod))."""
+    import ctypes as C
+    from .networks import _lerp_lod, _pool_image, _upscale_image
+    rt = Runtime.get(x.device)
+    x = x.to(torch.float32).contiguous()
+    n, c, h, w = x.shape
+    scale = (np.float32(drange_net[1]) - np.float32(drange_net[0])) / (np.float32(drange_data[1]) - np.float32(drange_data[0]))
+    bias = np.float32(drange_net[0]) - np.float32(drange_data[0]) * scale
+    if tuple(drange_data) != tuple(drange_net):
+        y = rt.empty(n, c, h, w)
+        _lib.check(rt.lib.tmx_convert_output(rt.handle, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), n * c, h, w,
+                                             float(scale), float(bias), 1, 0, rt.stream()), 'tmx_convert_output')
+        x = y
+    for on, axis in ((lr_mirror_augment, 3), (ud_mirror_augment, 2)):
+        if on:
+            rng = rng or np.random
+            flip = rng.uniform(0.0, 1.0, n) >= 0.5                       # tf.where(mask < 0.5, x, reverse(x))
+            length = x.shape[axis]
+            idx = np.where(flip[:, None], np.arange(length - 1, -1, -1)[None], np.arange(length)[None]).astype(np.int32)
+            idx = torch.from_numpy(np.ascontiguousarray(idx)).to(rt.device)
+            kw = dict(idx_w=[idx]) if axis == 3 else dict(idx_h=[idx])
+            x = rt.latent_blend([x], h, w, _lib.BLEND_COPY, **kw)
+    frac = float(np.float32(lod) - np.floor(np.float32(lod)))
+    x_fade = x
+    if frac != 0.0:
+        y = _upscale_image(rt, _pool_image(rt, x, 2), 2)
+        x_fade = _lerp_lod(rt, x, y, frac)
+    factor = int(2 ** int(np.floor(lod)))
+    if factor > 1:
+        x_orig = _upscale_image(rt, x, factor)
+        x_fade = _upscale_image(rt, x_fade, factor) if x_fade is not x else x_orig
+    else:
+        x_orig = x
+    return x_fade, x_orig
 
 
 class GraphedCritic:
@@ -180,7 +251,7 @@ class Trainer:
         return img[:, :, y0:y0 + res, x0:x0 + res].contiguous()
 
     def _critic(self, name, n):
-        key = (name, n)
+        key = (name, n, self.nets[name].lod)
         g = self._critic_graphs.get(key)
         if g is None:
             if self.graph_pool is None:
@@ -190,13 +261,22 @@ class Trainer:
         return g
 
     # ------------------------------------------------------------------ one step
-    def step(self, reals, draws, lrate=None, phases=('D', 'EG', 'EMA')):
-        """reals: this rank's share [n,3,R,R] fp32 in [-1,1] on the device.  Returns the loss-term report.
+    def step(self, reals, draws, lrate=None, phases=('D', 'EG', 'EMA'), lod=None, reals_orig=None):
+        """reals: this rank's share [n,3,R,R] fp32 in [-1,1] on the device (`reals_fade` of run.py:311; `reals_orig`
+        - what the encoders see, loss.py:119,126 - defaults to the same tensor, which is exact at integer lod).
+        lod: level of detail assigned to all networks before the losses run (run.py:310); None keeps theirs.
+        Returns the loss-term report.
         Order of run.py:511-513: critics see the pre-step E/G; E/G see the post-step critics; then EMA.  The E/G
         forward is evaluated ONCE (its variables do not change in between) and serves both phases."""
         report = {}
         c = self.cfg
-        ca = c.get('crop_aware', True)
+        if lod is not None:
+            for name in NET_FUNCS:
+                self.nets[name].set_lod(lod)
+        lod_now = self.nets['G'].lod
+        ca = c.get('crop_aware', True) and lod_now <= 2.0      # windows stay aligned to the upscaled low-res pixels
+        reals_fade = reals
+        reals = reals if reals_orig is None else reals_orig
         fwd = loss.EGForward(self.nets['E_zg'], self.nets['E_zl'], self.nets['G'], self.G_fcn, reals, draws.get('idx_dev', draws['idx']),
                              draws['eg_mix'], c['scale_h'], c['scale_w'],
                              crop_interp=draws['eg_crop_interp'] if ca else None,
@@ -208,13 +288,14 @@ class Trainer:
                 fake_interp = self._fcn_fake(fwd, 'interp', draws['d_interp_crop'])
             fakes = (('D_rec', fwd.rec, 'd_rec_gp'), ('D_interp', fake_interp, 'd_interp_gp'),
                      ('D_blend', self._fcn_fake(fwd, 'blend', draws['d_blend_crop'], draws['d_blend_mix']), 'd_blend_gp'))
-            graphs = c.get('cuda_graphs', True) and not os.environ.get('TMX_NO_GRAPH')
+            # a fractional lod changes every step and is baked into the launches: graphs only at integer lod
+            graphs = c.get('cuda_graphs', True) and not os.environ.get('TMX_NO_GRAPH') and lod_now == int(lod_now)
             for name, fake, gp in fakes:
                 if graphs:
-                    rep = self._critic(name, reals.shape[0])(fake, reals, draws[gp])
+                    rep = self._critic(name, reals.shape[0])(fake, reals_fade, draws[gp])
                 else:
                     self.grads[name].zero_()
-                    rep = loss.D_wgangp(self.nets[name], fake, reals, draws[gp], self.grads[name])
+                    rep = loss.D_wgangp(self.nets[name], fake, reals_fade, draws[gp], self.grads[name])
                 report.update({name + '/' + k: v for k, v in rep.items()})
             for name in ('D_rec', 'D_interp', 'D_blend'):                           # one session.run (run.py:511)
                 report[name + '/skipped'] = self.opts[name].apply_updates(lrate)
@@ -222,7 +303,8 @@ class Trainer:
             for k in ('E_zg', 'E_zl', 'G'):
                 self.grads[k].zero_()
             rep = loss.EG_backward(fwd, self.nets['D_rec'], self.nets['D_interp'], self.nets['D_blend'],
-                                   draws['eg_crop_interp'], draws['eg_crop_blend'], self.grads, **c['loss'])
+                                   draws['eg_crop_interp'], draws['eg_crop_blend'], self.grads, reals_fade=reals_fade,
+                                   **c['loss'])
             report.update({'EG/' + k: v for k, v in rep.items()})
             report['EG/skipped'] = self.opts['EG'].apply_updates(lrate)
         del fwd
