@@ -217,7 +217,7 @@ def run_ours(args):
         return
 
     # ---- end to end through Network.run (host numpy in / out)
-    E2E_MB = 32      # Network.run(minibatch_size=...) (tfutil.py:624-680): minibatches are pipelined H2D / compute / D2H
+    E2E_MB = int(os.environ.get('TMX_E2E_MB', '32'))      # Network.run(minibatch_size=...) (tfutil.py:624-680): minibatches are pipelined H2D / compute / D2H
     # the step's inputs wait in page-locked host memory (bench contract); Network.run DMAs straight from them
     zg_p = torch.empty(zg_h.shape, dtype=torch.float32, pin_memory=True).numpy()
     zl_p = torch.empty(zl_h.shape, dtype=torch.float32, pin_memory=True).numpy()
@@ -277,7 +277,7 @@ def run_ours(args):
             'tflops_algorithmic': value * GFLOP_PER_IMAGE / 1e3,
             'e2e': {'value': e2e, 'unit': 'images/s', 'h2d_bytes_per_step': int(zg_h.nbytes + zl_h.nbytes),
                     'd2h_bytes_per_step': int(out_h.nbytes),
-                    'api': 'Network.run(zg, zl, minibatch_size=32): numpy in (page-locked arrays), numpy out'},
+                    'api': 'Network.run(zg, zl, minibatch_size=%d): numpy in (page-locked arrays), numpy out' % E2E_MB},
             'gpu_launches': int(launches),
             'roofline': roof,
             'cpu_baseline': {'value': cpu_ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',

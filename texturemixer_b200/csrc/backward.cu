@@ -169,9 +169,13 @@ extern "C" int tmx_grad_prepare(tmx_handle_t h, const tmx_grad_desc_t* d, const 
   P.io = *io;
   P.C8 = d->C / 8;
   P.ppb = 256 / P.C8 > 0 ? 256 / P.C8 : 1;
-  P.iters = 16;
   const int threads = P.ppb * P.C8;
   const long long total = (long long)d->N * (d->H + 4) * (d->W + 4);
+  // positions per thread: 16 amortise the bias-gradient atomics on the big maps, but on the small ones (most of the
+  // ~390 calls of a train step) they are 16 DEPENDENT round trips on a handful of CTAs - keep >= 4 CTAs per SM
+  P.iters = 16;
+  while (P.iters > 1 && (total + (long long)P.ppb * P.iters - 1) / ((long long)P.ppb * P.iters) < 4LL * h->sm_count)
+    P.iters >>= 1;
   const long long per_block = (long long)P.ppb * P.iters;
   const size_t smem = io->dbias ? (size_t)threads * 8 * sizeof(float) : 0;
   TMX_REQUIRE(threads <= 256 && smem <= 48 * 1024, TMX_ERR_SHAPE, "tmx_grad_prepare: C=%d not supported", d->C);

@@ -151,7 +151,7 @@ class GraphedCritic:
         gc_was_on = gc.isenabled()
         gc.disable()                           # finalising unrelated CUDA objects mid-capture would invalidate it
         try:
-            with torch.cuda.graph(self.graph, pool=trainer.graph_pool):
+            with torch.cuda.graph(self.graph):
                 self.grad.zero_()
                 self.report = loss.D_wgangp(self.D, self.fake, self.real, self.mix, self.grad)
         finally:
@@ -201,6 +201,7 @@ class Trainer:
         # CUDA graphs of the three critic evaluations (cfg['cuda_graphs'], TMX_NO_GRAPH=1 turns them off)
         self.graph_pool = None
         self._critic_graphs = {}
+        self._critic_streams = [torch.cuda.Stream(device=self.rt.device) for _ in range(3)]
         self.graph_launches = 0       # kernels replayed from graphs (libtmx counts launches at capture time only)
 
     # ------------------------------------------------------------------ host-side random draws of one step
@@ -254,9 +255,7 @@ class Trainer:
         key = (name, n, self.nets[name].lod)
         g = self._critic_graphs.get(key)
         if g is None:
-            if self.graph_pool is None:
-                self.graph_pool = torch.cuda.graph_pool_handle()     # the three graphs never overlap: one pool
-            g = self._critic_graphs[key] = GraphedCritic(self, name, n)
+            g = self._critic_graphs[key] = GraphedCritic(self, name, n)     # own memory pool: the graphs run concurrently
         self.graph_launches += g.launches
         return g
 
@@ -290,13 +289,30 @@ class Trainer:
                      ('D_blend', self._fcn_fake(fwd, 'blend', draws['d_blend_crop'], draws['d_blend_mix']), 'd_blend_gp'))
             # a fractional lod changes every step and is baked into the launches: graphs only at integer lod
             graphs = c.get('cuda_graphs', True) and not os.environ.get('TMX_NO_GRAPH') and lod_now == int(lod_now)
-            for name, fake, gp in fakes:
-                if graphs:
-                    rep = self._critic(name, reals.shape[0])(fake, reals_fade, draws[gp])
-                else:
+            if graphs:
+                # the three critic graphs are independent: replay them on three streams so that their many small,
+                # latency-bound kernels (8x8 / 4x4 maps, dense head) overlap instead of queueing behind each other
+                main = torch.cuda.current_stream(self.rt.device)
+                fork = torch.cuda.Event()
+                fork.record(main)
+                joins = []
+                for i, (name, fake, gp) in enumerate(fakes):
+                    critic = self._critic(name, reals.shape[0])          # captured on the main stream the first time
+                    side = self._critic_streams[i]
+                    side.wait_event(fork)
+                    with torch.cuda.stream(side):
+                        rep = critic(fake, reals_fade, draws[gp])
+                    done = torch.cuda.Event()
+                    done.record(side)
+                    joins.append(done)
+                    report.update({name + '/' + k: v for k, v in rep.items()})
+                for done in joins:
+                    main.wait_event(done)       # fakes / reals are only released by the caller after this join
+            else:
+                for name, fake, gp in fakes:
                     self.grads[name].zero_()
                     rep = loss.D_wgangp(self.nets[name], fake, reals_fade, draws[gp], self.grads[name])
-                report.update({name + '/' + k: v for k, v in rep.items()})
+                    report.update({name + '/' + k: v for k, v in rep.items()})
             for name in ('D_rec', 'D_interp', 'D_blend'):                           # one session.run (run.py:511)
                 report[name + '/skipped'] = self.opts[name].apply_updates(lrate)
         if 'EG' in phases:
