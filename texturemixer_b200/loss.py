@@ -189,10 +189,24 @@ class EGForward:
         return img[:, :, y0:y0 + res, x0:x0 + res].contiguous()
 
 
+def critic_input_gradient(D, images, weight):
+    """One adversarial term of `EG_wgan` (loss.py:135-136, 194-199, 241-246): the critic as a FIXED function.
+    -> (mean over the batch of -weight * D(images) [device scalar], its gradient w.r.t. images [N,3,R,R])."""
+    rt = D.rt
+    n = images.shape[0]
+    tape = []
+    s = D.get_output_for(images, tape=tape)
+    term = _row_sum(rt, s, 1, n, scale=-weight / n)
+    (d,) = backward(D, tape, [torch.full_like(s, -weight / n)], None, param_grads=False)
+    return term, d
+
+
 def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, rec_G_weight=1.0, pixel_weight=200.0,
-                interp_G_weight=1.0, blend_interp_G_weight=1.0, reals_fade=None):
+                interp_G_weight=1.0, blend_interp_G_weight=1.0, reals_fade=None, critic_grads=None):
     """Loss terms of `EG_wgan` on the images of `fwd` and the whole reverse pass into `grads`.  `reals_fade`: the
-    target of the pixel loss (loss.py:143) when it differs from what the encoders saw (fractional lod)."""
+    target of the pixel loss (loss.py:143) when it differs from what the encoders saw (fractional lod).
+    `critic_grads`: optional {'rec' | 'interp' | 'blend': critic_input_gradient(...)} evaluated by the caller (the
+    trainer replays them as CUDA graphs on parallel streams)."""
     rt = fwd.rt
     E_zg, E_zl, G, G_fcn = fwd.nets
     reals, n, c, lat, H, W, pins = fwd.reals, fwd.n, fwd.c, fwd.lat, fwd.H, fwd.W, fwd.pins
@@ -202,11 +216,9 @@ def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, r
     report = {}
     rec = fwd.rec
     d_rec_img = None
+    cg = critic_grads or {}
     if rec_G_weight > 0:
-        t_d = []
-        s = D_rec.get_output_for(rec, tape=t_d)
-        report['rec_G'] = _row_sum(rt, s, 1, n, scale=-rec_G_weight * inv_n)
-        (d_rec_img,) = backward(D_rec, t_d, [torch.full_like(s, -rec_G_weight * inv_n)], None, param_grads=False)
+        report['rec_G'], d_rec_img = cg['rec'] if 'rec' in cg else critic_input_gradient(D_rec, rec, rec_G_weight)
     if pixel_weight > 0:
         l1 = rt.empty(*rec.shape)
         lsum = torch.zeros(1, dtype=torch.float32, device=rt.device)
@@ -219,20 +231,16 @@ def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, r
     dzg = _row_sum(rt, dzg_tiled, n * c, lat * lat)                      # adjoint of the 32x32 tile of zg
     dzl = dzl.contiguous()
     if interp_G_weight > 0:
-        t_d = []
-        s = D_interp.get_output_for(fwd.crop('interp', crop_interp), tape=t_d)
-        report['interp_G'] = _row_sum(rt, s, 1, n, scale=-interp_G_weight * inv_n)
-        (dcr,) = backward(D_interp, t_d, [torch.full_like(s, -interp_G_weight * inv_n)], None, param_grads=False)
+        report['interp_G'], dcr = cg['interp'] if 'interp' in cg else \
+            critic_input_gradient(D_interp, fwd.crop('interp', crop_interp), interp_G_weight)
         dzg_c, dzl_c = backward(G_fcn, fwd.t_int, [_crop_adjoint(dcr, fwd.interp.shape[2:],
                                                                  fwd.window_offset('interp', crop_interp))], grads['G'])
         _row_sum(rt, dzg_c, n * c, dzg_c.shape[2] * dzg_c.shape[3], out=dzg, accumulate=True)
         _gather_bwd(rt, _embed(dzl_c, fwd.win['interp'], H, W), dzl, fwd.ih_f, fwd.iw_f, pins)
     if blend_interp_G_weight > 0:
-        t_d = []
         t = fwd.t
-        s = D_blend.get_output_for(fwd.crop('blend', crop_blend), tape=t_d)
-        report['blend_G'] = _row_sum(rt, s, 1, n, scale=-blend_interp_G_weight * inv_n)
-        (dcr,) = backward(D_blend, t_d, [torch.full_like(s, -blend_interp_G_weight * inv_n)], None, param_grads=False)
+        report['blend_G'], dcr = cg['blend'] if 'blend' in cg else \
+            critic_input_gradient(D_blend, fwd.crop('blend', crop_blend), blend_interp_G_weight)
         dbzg, dbzl = backward(G_fcn, fwd.t_bl, [_crop_adjoint(dcr, fwd.blend.shape[2:],
                                                               fwd.window_offset('blend', crop_blend))], grads['G'])
         zero_c = torch.zeros_like(dbzg)

@@ -141,7 +141,7 @@ class GraphedCritic:
         with torch.cuda.stream(side):          # warm-up outside the capture: kernel attributes, allocator pools
             self.fake.uniform_(-1, 1)
             self.real.uniform_(-1, 1)
-            loss.D_wgangp(self.D, self.fake, self.real, self.mix, torch.zeros_like(self.grad))
+            self._evaluate(torch.zeros_like(self.grad))
         main.wait_stream(side)
         torch.cuda.synchronize(dev)
         self.D._owner()._prepared.clear()      # capture the weight-plane kernels too
@@ -152,13 +152,16 @@ class GraphedCritic:
         gc.disable()                           # finalising unrelated CUDA objects mid-capture would invalidate it
         try:
             with torch.cuda.graph(self.graph):
-                self.grad.zero_()
-                self.report = loss.D_wgangp(self.D, self.fake, self.real, self.mix, self.grad)
+                self.report = self._evaluate(self.grad)
         finally:
             if gc_was_on:
                 gc.enable()
         self.launches = rt.launch_count() - l0
         self.D._owner()._prepared.clear()      # those planes live in the graph's pool; nobody else may keep them
+
+    def _evaluate(self, grad):
+        grad.zero_()
+        return loss.D_wgangp(self.D, self.fake, self.real, self.mix, grad)
 
     def __call__(self, fake, real, mix):
         """Refresh the static inputs and replay.  The returned report tensors are the graph's static outputs: read
@@ -166,6 +169,23 @@ class GraphedCritic:
         self.fake.copy_(fake)
         self.real.copy_(real)
         self.mix.copy_(mix.reshape(self.mix.shape))
+        self.graph.replay()
+        return self.report
+
+
+class GraphedCriticGradient(GraphedCritic):
+    """The critic as a fixed function inside the E/G loss (`loss.critic_input_gradient`: forward + data gradients,
+    ~150 launches), captured and replayed the same way."""
+
+    def __init__(self, trainer, name, n, weight):
+        self.weight = weight
+        super().__init__(trainer, name, n)
+
+    def _evaluate(self, grad):
+        return loss.critic_input_gradient(self.D, self.fake, self.weight)
+
+    def __call__(self, images):
+        self.fake.copy_(images)
         self.graph.replay()
         return self.report
 
@@ -259,6 +279,39 @@ class Trainer:
         self.graph_launches += g.launches
         return g
 
+    def _eg_critic_gradients(self, fwd, draws):
+        """The three adversarial terms of the E/G loss (post-step critics as fixed functions): graphs on three
+        streams, joined before the generator's backward consumes their image gradients."""
+        w = self.cfg['loss']
+        jobs = (('rec', 'D_rec', w['rec_G_weight'], lambda: fwd.rec),
+                ('interp', 'D_interp', w['interp_G_weight'], lambda: fwd.crop('interp', draws['eg_crop_interp'])),
+                ('blend', 'D_blend', w['blend_interp_G_weight'], lambda: fwd.crop('blend', draws['eg_crop_blend'])))
+        jobs = [(key, name, wt, img()) for key, name, wt, img in jobs if wt > 0]
+        main = torch.cuda.current_stream(self.rt.device)
+        graphs = []
+        for key, name, wt, img in jobs:
+            gkey = (name, 'input', img.shape[0], self.nets[name].lod, float(wt))
+            g = self._critic_graphs.get(gkey)
+            if g is None:
+                g = self._critic_graphs[gkey] = GraphedCriticGradient(self, name, img.shape[0], float(wt))
+            self.graph_launches += g.launches
+            graphs.append(g)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        out, joins = {}, []
+        for i, ((key, name, wt, img), g) in enumerate(zip(jobs, graphs)):
+            side = self._critic_streams[i]
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                out[key] = g(img)
+            done = torch.cuda.Event()
+            done.record(side)
+            joins.append(done)
+        for done in joins:
+            main.wait_event(done)
+        self._eg_inputs = [j[3] for j in jobs]      # keep the crops alive until the next step (read on side streams)
+        return out
+
     # ------------------------------------------------------------------ one step
     def step(self, reals, draws, lrate=None, phases=('D', 'EG', 'EMA'), lod=None, reals_orig=None):
         """reals: this rank's share [n,3,R,R] fp32 in [-1,1] on the device (`reals_fade` of run.py:311; `reals_orig`
@@ -318,9 +371,12 @@ class Trainer:
         if 'EG' in phases:
             for k in ('E_zg', 'E_zl', 'G'):
                 self.grads[k].zero_()
+            critic_grads = None
+            if c.get('cuda_graphs', True) and not os.environ.get('TMX_NO_GRAPH') and lod_now == int(lod_now):
+                critic_grads = self._eg_critic_gradients(fwd, draws)
             rep = loss.EG_backward(fwd, self.nets['D_rec'], self.nets['D_interp'], self.nets['D_blend'],
                                    draws['eg_crop_interp'], draws['eg_crop_blend'], self.grads, reals_fade=reals_fade,
-                                   **c['loss'])
+                                   critic_grads=critic_grads, **c['loss'])
             report.update({'EG/' + k: v for k, v in rep.items()})
             report['EG/skipped'] = self.opts['EG'].apply_updates(lrate)
         del fwd
