@@ -311,6 +311,12 @@ int tmx_gp_coefficients(tmx_handle_t h, const float* sq_norms, float* penalty, f
  * [0,255], NaN -> 0); 2: fp32 holding rounded values (the caller narrows to the other integer types). */
 int tmx_convert_output(tmx_handle_t h, const float* x, void* y, int64_t planes, int H, int W, float mul, float add,
                        int shrink, int out_kind, tmx_stream_t s);
+/* App-level matte compositing (util_scripts.py:1262,1268 `np.sum(latents * weights, axis=0)`, :1337,1342
+ * `left * matt + right * (1 - matt)`): out[n][c][p] = sum_k srcs[k][n][c][p] * weights[k][p] over K NCHW sources
+ * (device array of K device pointers; bcast[k] != 0: source k is [N][C][1][1]).  float64 products and sums rounded
+ * once to float32 (numpy promotion), or float32 throughout (math_f32). */
+int tmx_weighted_sum(tmx_handle_t h, const float* const* srcs, const int* bcast, const double* weights, float* out, int K,
+                     int N, int C, int H, int W, int math_f32, tmx_stream_t s);
 /* out = tanh(in) over n fp32 elements: the generator's image head when lod != 0 (networks.py:482-483). */
 int tmx_tanh_f32(tmx_handle_t h, const float* in, float* out, int64_t n, tmx_stream_t s);
 /* its adjoint: dx = dy * (1 - y^2) with y = tanh(x). */

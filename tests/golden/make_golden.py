@@ -72,6 +72,28 @@ def gen_mattes():
     print('mattes.npz', {k: (v.shape, v.dtype) for k, v in out.items()})
 
 
+APP_MATTE_CASES = dict(
+    gkern_for_weight_arbitrary_shape=[(24, 40, 7, 5, 6.0), (32, 32, 31.5, 0, 12.0), (20, 48, -3, 25, 3.0)],
+    gkern_for_weight_arbitrary_shape_hybridization=[(24, 40, 7, 5, 6.0), (16, 16, 8, 8, 2.5)],
+    gkern_for_weight_grid_shape_hybridization=[(24, 40, 3.25, 4.5, 8.0, 6.0), (32, 24, -2.0, 20.0, 8.0, 4.0),
+                                               (16, 16, 0.0, 0.0, 32.0, 8.0)],
+    linkern_for_weight_square=[(24, 4), (40, 8)],
+    gkern_for_scale_horizontal=[([2, 3, 4, 40], 8)],
+)
+
+
+def gen_app_mattes():
+    """util_scripts.py:53-62, 104-182: the brush / hybridization weight kernels, executed from the reference file."""
+    f = refload.reference_functions('util_scripts.py', list(APP_MATTE_CASES) + ['l2', 'dist2square'])
+    out = {}
+    for name, cases in APP_MATTE_CASES.items():
+        for i, args in enumerate(cases):
+            r = f[name](*args)
+            out['%s_%d' % (name, i)] = np.stack(r) if isinstance(r, tuple) else np.asarray(r)
+    np.savez_compressed(os.path.join(HERE, 'mattes_apps.npz'), **out)
+    print('mattes_apps.npz', {k: (v.shape, v.dtype) for k, v in out.items()})
+
+
 def network_inputs(func, rng, n):
     if func == 'G_res':
         return [rng.randn(n, 128, 32, 32).astype(np.float32), rng.randn(n, 128, 32, 32).astype(np.float32)]
@@ -179,8 +201,12 @@ if __name__ == '__main__':
     if 'schedule' in sys.argv[1:]:
         gen_schedule()
         sys.exit(0)
+    if 'apps' in sys.argv[1:]:
+        gen_app_mattes()
+        sys.exit(0)
     gen_perm()
     gen_mattes()
     gen_networks()
     gen_network_variants()
     gen_schedule()
+    gen_app_mattes()

@@ -370,3 +370,29 @@ def test_errors_are_loud(rt):
     n0 = rt.launch_count()
     rt.avgpool2(Act(1, 4, 4, 8, f32=torch.zeros(1, 4, 4, 8, device='cuda')))
     assert rt.launch_count() == n0 + 1
+
+
+def test_weighted_sum_bit_exact(rt):
+    """interp.weighted_sum == numpy's `np.sum(latents * weights, axis=0)` (util_scripts.py:1262,1268: float32 latents
+    promoted to the float64 RBF weights, rounded once) and the float32 horizontal matte of :1337,1342."""
+    from texturemixer_b200 import interp
+    rng = np.random.RandomState(8)
+    k, n, c, h, w = 5, 2, 6, 24, 40
+    zl = [rng.randn(n, c, h, w).astype(np.float32) for _ in range(k)]
+    zg = [rng.randn(n, c, 1, 1).astype(np.float32) for _ in range(k)]
+    wts = np.stack([interp.gkern_for_weight_grid_shape_hybridization(h, w, 3.0 * i, 2.0 * i, 8.0, 6.0) for i in range(k)])
+    wts = wts / wts.sum(axis=0, keepdims=True)
+    got = interp.weighted_sum([torch.from_numpy(a).cuda() for a in zl], wts).cpu().numpy()
+    want = np.zeros((n, c, h, w))
+    for a, m in zip(zl, wts):
+        want = want + a * m[None, None]
+    assert np.array_equal(got, want.astype(np.float32))
+    got_g = interp.weighted_sum([torch.from_numpy(a).cuda() for a in zg], wts).cpu().numpy()
+    want_g = np.zeros((n, c, h, w))
+    for a, m in zip(zg, wts):
+        want_g = want_g + np.tile(a, (1, 1, h, w)) * m[None, None]
+    assert np.array_equal(got_g, want_g.astype(np.float32))
+    matt = interp.linkern_for_weight_horizontal([n, c, h, w], 8)                 # float32 matte: float32 arithmetic
+    got_h = interp.weighted_sum([torch.from_numpy(zl[0]).cuda(), torch.from_numpy(zl[1]).cuda()],
+                                np.stack([matt[0, 0], (np.float32(1.0) - matt)[0, 0]]), math_f32=True).cpu().numpy()
+    assert np.array_equal(got_h, zl[0] * matt + zl[1] * (np.float32(1.0) - matt))

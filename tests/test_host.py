@@ -257,3 +257,24 @@ def test_training_schedule_matches_reference_class():
             s = TrainingSchedule(nimg, 7, num_gpus=gpus, **kw)
             got = [s.lod, s.resolution, s.minibatch, s.lrate, s.tick_kimg]
             assert np.array_equal(np.array(got, np.float64), want), (i, nimg, got, want)
+
+
+def test_app_mattes_match_reference_functions():
+    """interp.gkern_* / linkern_for_weight_square / gkern_for_scale_horizontal vs the reference's own functions
+    (util_scripts.py:53-62, 104-182) executed by make_golden.py -> mattes_apps.npz.  The hybridization RBF kernel is
+    a Python double loop of scalar math in the reference and array math here: equal to the last ulp of exp()."""
+    from texturemixer_b200 import interp
+    src = open(os.path.join(GOLDEN, 'make_golden.py')).read()
+    ns = {}
+    exec(src[src.index('APP_MATTE_CASES = dict('):src.index('def gen_app_mattes')], ns)
+    g = np.load(os.path.join(GOLDEN, 'mattes_apps.npz'))
+    for name, cases in ns['APP_MATTE_CASES'].items():
+        for i, args in enumerate(cases):
+            got = getattr(interp, name)(*args)
+            got = np.stack(got) if isinstance(got, tuple) else np.asarray(got)
+            want = g['%s_%d' % (name, i)]
+            assert got.shape == want.shape and got.dtype == want.dtype, (name, i)
+            if 'gkern_for_weight' in name:
+                assert np.allclose(got, want, rtol=1e-14, atol=1e-300), (name, i)
+            else:
+                assert np.array_equal(got, want), (name, i)

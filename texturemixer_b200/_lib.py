@@ -97,6 +97,7 @@ _SIGNATURES = {
     'tmx_gp_coefficients': (C.c_int, [_P, _P, _P, _P, _I, _F, _F, _P]),
     'tmx_add_f32': (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
     'tmx_convert_output': (C.c_int, [_P, _P, _P, C.c_int64, _I, _I, _F, _F, _I, _I, _P]),
+    'tmx_weighted_sum': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'tmx_tanh_f32': (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     'tmx_tanh_bwd': (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
     'tmx_pixel_norm': (C.c_int, [_P, _P, _P, C.c_int64, _I, _F, _P]),

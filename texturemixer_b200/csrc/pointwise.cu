@@ -796,3 +796,48 @@ extern "C" int tmx_pixel_norm(tmx_handle_t h, const float* x, float* y, int64_t 
   TMX_LAUNCHED(h, "pixel_norm_kernel");
   return TMX_OK;
 }
+
+// ---------------------------------------------------------------- app-level matte compositing
+// out[n][c][p] = sum_k src_k[n][c][p or 0] * w[k][p]  (util_scripts.py:1262,1268: np.sum(latents * weights, axis=0);
+// :1337,1342: left * matt + right * (1 - matt)).  float64 products and sums rounded once (numpy promotes the float32
+// latents to the float64 weights), or float32 throughout when the matte itself is float32 (math_f32).
+__global__ void __launch_bounds__(256) weighted_sum_kernel(const float* const* __restrict__ srcs,
+                                                           const int* __restrict__ bcast,
+                                                           const double* __restrict__ w, float* __restrict__ out, int K,
+                                                           long long planes, int HW, int math_f32) {
+  const long long total = planes * HW;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int p = (int)(i % HW);
+    const long long plane = i / HW;
+    if (math_f32) {
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k) {
+        const float v = __ldg(srcs[k] + (bcast[k] ? plane : i));
+        const float t = __fmul_rn(v, (float)__ldg(w + (long long)k * HW + p));
+        acc = k == 0 ? t : __fadd_rn(acc, t);
+      }
+      out[i] = acc;
+    } else {
+      double acc = 0.0;
+      for (int k = 0; k < K; ++k) {
+        const double v = (double)__ldg(srcs[k] + (bcast[k] ? plane : i));
+        const double t = __dmul_rn(v, __ldg(w + (long long)k * HW + p));
+        acc = k == 0 ? t : __dadd_rn(acc, t);
+      }
+      out[i] = (float)acc;
+    }
+  }
+}
+
+extern "C" int tmx_weighted_sum(tmx_handle_t h, const float* const* srcs, const int* bcast, const double* weights,
+                                float* out, int K, int N, int C, int H, int W, int math_f32, tmx_stream_t s) {
+  TMX_REQUIRE(h && srcs && bcast && weights && out, TMX_ERR_ARG, "tmx_weighted_sum: NULL argument");
+  TMX_REQUIRE(K >= 1 && N > 0 && C > 0 && H > 0 && W > 0, TMX_ERR_SHAPE, "tmx_weighted_sum: bad shape K=%d N=%d C=%d %dx%d",
+              K, N, C, H, W);
+  const long long total = (long long)N * C * H * W;
+  const int grid = (int)(total / 256 + 1 < 148LL * 16 ? total / 256 + 1 : 148LL * 16);
+  weighted_sum_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(srcs, bcast, weights, out, K, (long long)N * C, H * W, math_f32);
+  TMX_LAUNCHED(h, "weighted_sum_kernel");
+  return TMX_OK;
+}

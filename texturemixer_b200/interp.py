@@ -79,6 +79,92 @@ def linkern_for_weight_arbitrary_shape(out_h, out_w, latent_res):
     return tuple(a[:, None] * b[None, :] for a, b in zip(rh, rw))
 
 
+# ---------------------------------------------------------------------- app-level mattes (host, float64 like numpy)
+def gkern_for_weight_arbitrary_shape(out_h, out_w, x, y, sig_div):
+    """util_scripts.py:104-114 (texture brush strokes, :844-868): a horizontally stretched Gaussian around (x, y),
+    sigma = out_w / sig_div, min-max normalised to [0, 1].  float64 [out_h, out_w]."""
+    cx, cy = float(x), float(y)
+    sig = float(out_w) / sig_div
+    xx, yy = np.meshgrid(np.arange(0.0, float(out_w)), np.arange(0.0, float(out_h)))
+    kernel = np.exp(-(np.maximum(np.absolute(xx - cx) - sig, 0.0) ** 2 + (yy - cy) ** 2) / (2. * sig ** 2))
+    return (kernel - np.amin(kernel)) / (np.amax(kernel) - np.amin(kernel))
+
+
+def gkern_for_weight_arbitrary_shape_hybridization(out_h, out_w, x, y, sig_div):
+    """util_scripts.py:116-125: plain Gaussian around (x, y), not normalised."""
+    cx, cy = float(x), float(y)
+    sig = float(out_w) / sig_div
+    xx, yy = np.meshgrid(np.arange(0.0, float(out_w)), np.arange(0.0, float(out_h)))
+    return np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2. * sig ** 2))
+
+
+def gkern_for_weight_grid_shape_hybridization(out_h, out_w, cx, cy, size, sig_div):
+    """util_scripts.py:127-168 (hybridization RBF weights, :1145): exp(-d^2 / 2 sigma^2) with d the distance of
+    latent pixel (j, i) to the square [cx, cx+size] x [cy, cy+size], sigma = min(out_h, out_w) / sig_div.
+    The reference fills it with a Python double loop over `dist2square`; this is the same arithmetic on arrays."""
+    cx, cy = float(cx), float(cy)
+    sig = min([float(out_h), float(out_w)]) / sig_div
+    x = np.arange(out_w, dtype=np.float64)[None, :]
+    y = np.arange(out_h, dtype=np.float64)[:, None]
+    x_max, y_max = cx + size, cy + size
+    dx = np.where(x < cx, x - cx, np.where(x <= x_max, 0.0, x - x_max))
+    dy = np.where(y < cy, y - cy, np.where(y <= y_max, 0.0, y - y_max))
+    return np.exp(-(dx ** 2 + dy ** 2) / (2. * sig ** 2))
+
+
+def linkern_for_weight_square(out_length, latent_res):
+    """util_scripts.py:53-62 -> (weight_ul, weight_ur, weight_bl, weight_br) float64 [L, L]."""
+    step = 1.0 / (out_length - 2.0 * latent_res - 1.0)
+    ax = np.arange(start=0.0, stop=1.0 + step, step=step)
+    ax = np.concatenate((np.zeros(latent_res), ax, np.ones(latent_res)))
+    X, Y = np.meshgrid(ax, ax)
+    weight_br = X * Y
+    weight_ur = np.rot90(weight_br)
+    weight_ul = np.rot90(weight_ur)
+    weight_bl = np.rot90(weight_ul)
+    return weight_ul, weight_ur, weight_bl, weight_br
+
+
+def gkern_for_scale_horizontal(out_shape, latent_res):
+    """util_scripts.py:170-182: float32 [N,C,H,W], 0 over the first latent_res columns, 1 elsewhere."""
+    kernel = np.concatenate((np.zeros((1, 1, 1, latent_res)), np.ones((1, 1, 1, out_shape[3] - latent_res))), axis=3)
+    return kernel.astype(np.float32)
+
+
+def weighted_sum(sources, weights, math_f32=False):
+    """sum_k sources[k] * weights[k] on the device: the matte compositing of the apps (util_scripts.py:1262,1268
+    hybridization `np.sum(latents * weights, axis=0)`; :1337,1342 horizontal mattes; :844-868 brush strokes).
+      sources: K device tensors [N,C,H,W] (or [N,C,1,1] = a global code tiled over the canvas)
+      weights: [K,H,W] array (float64 like the reference's numpy products, rounded once to float32 at the end;
+               math_f32=True multiplies and adds in float32 like a float32 matte does)
+    -> [N,C,H,W] float32."""
+    import ctypes as C
+    rt = Runtime.get(sources[0].device)
+    k = len(sources)
+    weights = np.ascontiguousarray(weights, dtype=np.float64)
+    assert weights.ndim == 3 and weights.shape[0] == k
+    H, W = weights.shape[1:]
+    n, c = sources[0].shape[:2]
+    bcast = []
+    srcs = []
+    for s in sources:
+        assert s.dtype == torch.float32 and s.is_cuda and s.shape[:2] == (n, c)
+        if tuple(s.shape[2:]) == (1, 1) and (H, W) != (1, 1):
+            bcast.append(1)
+        else:
+            assert tuple(s.shape[2:]) == (H, W)
+            bcast.append(0)
+        srcs.append(s.contiguous())
+    ptrs = torch.tensor([s.data_ptr() for s in srcs], dtype=torch.int64).to(rt.device)
+    flags = torch.tensor(bcast, dtype=torch.int32).to(rt.device)
+    wd = torch.from_numpy(weights).to(rt.device)
+    out = rt.empty(n, c, H, W)
+    _lib.check(rt.lib.tmx_weighted_sum(rt.handle, C.c_void_p(ptrs.data_ptr()), C.c_void_p(flags.data_ptr()),
+                                       C.c_void_p(wd.data_ptr()), C.c_void_p(out.data_ptr()), k, n, c, H, W,
+                                       int(math_f32), rt.stream()), 'tmx_weighted_sum')
+    return out
+
+
 # ---------------------------------------------------------------------- device ops
 def _dev_idx(rt, idx, n, length):
     if idx is None:
