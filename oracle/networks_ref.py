@@ -91,6 +91,26 @@ def downscale2d(x, factor=2):
     return F.avg_pool2d(x, factor, factor)
 
 
+def _fuse4(w):
+    """networks.py:97-98,145-146: zero-pad the 3x3 kernel to 5x5 and add its four one-pixel shifts -> 4x4."""
+    w = F.pad(w, (0, 0, 0, 0, 1, 1, 1, 1))
+    return w[1:, 1:] + w[:-1, 1:] + w[1:, :-1] + w[:-1, :-1]
+
+
+def upscale2d_conv2d(x, w, gain=SQRT2):
+    """networks.py:94-101 (fused_scale=True): conv2d_transpose, stride 2, SAME, with the fused 4x4 kernel.
+    Variable [k, k, fmaps, Cin]; wscale from fan_in = k*k*Cin."""
+    k, _, fmaps, cin = w.shape
+    w = _fuse4(w * wscale_of(w.shape, gain, fan_in=k * k * cin))
+    return F.conv_transpose2d(x, w.permute(3, 2, 0, 1), stride=2, padding=1)
+
+
+def conv2d_downscale2d(x, w, gain=SQRT2):
+    """networks.py:142-148 (fused_scale=True): conv2d, stride 2, SAME, with the fused 4x4 kernel * 0.25."""
+    w = _fuse4(w * wscale_of(w.shape, gain)) * 0.25
+    return F.conv2d(F.pad(x, (1, 1, 1, 1)), w.permute(3, 2, 0, 1), stride=2)
+
+
 def pixel_norm(x, epsilon=1e-8):
     """networks.py:170-172 (off in config.py:77-79; kept for completeness)."""
     return x * torch.rsqrt(torch.mean(x * x, dim=1, keepdim=True) + epsilon)
@@ -132,8 +152,9 @@ def _add_dense(spec, scope, cin, cout, gain):
 
 
 def spec_E_zg(num_channels=3, resolution=128, fmap_base=1024, fmap_decay=1.0, fmap_max=512,
-              latent_channels=128, **_):
+              latent_channels=128, fused_scale=False, **_):
     """Variable table of E_zg (networks.py:194-291)."""
+    c1 = 'Conv1_down' if fused_scale else 'Conv1'
     nf = nf_fn(fmap_base, fmap_decay, fmap_max)
     rl2 = int(np.log2(resolution))
     spec = OrderedDict(lod=dict(shape=()))
@@ -143,10 +164,14 @@ def spec_E_zg(num_channels=3, resolution=128, fmap_base=1024, fmap_decay=1.0, fm
             pass
         s = '%dx%d' % (2 ** res, 2 ** res)
         _add_conv(spec, s + '/Conv0', 3, nf(res - 1), nf(res - 1), SQRT2)
-        _add_conv(spec, s + '/Conv1', 3, nf(res - 1), nf(res - 2), SQRT2)
+        _add_conv(spec, s + '/' + c1, 3, nf(res - 1), nf(res - 2), SQRT2)
     # the deepest recursion level creates FromRGB for res=2 last-but-structure:
     _add_conv(spec, 'FromRGB_lod%d' % (rl2 - 2), 1, num_channels, nf(1), SQRT2)
     _add_conv(spec, '4x4/Conv0', 3, nf(1), nf(1), SQRT2)
+    if fused_scale:                                             # networks.py:245-249
+        _add_conv(spec, '4x4/zg_Conv1_down', 3, nf(1), nf(0), SQRT2)
+        _add_conv(spec, '4x4/zg_Conv2_down', 3, nf(0), latent_channels * 2, 1.0)
+        return spec
     _add_conv(spec, '4x4/zg_Conv1', 3, nf(1), nf(0), SQRT2)
     _add_conv(spec, '4x4/zg_Conv2', 3, nf(0), nf(-1), SQRT2)
     _add_conv(spec, '4x4/zg_Conv3', 1, nf(-1), latent_channels * 2, 1.0)
@@ -154,8 +179,9 @@ def spec_E_zg(num_channels=3, resolution=128, fmap_base=1024, fmap_decay=1.0, fm
 
 
 def spec_E_zl(num_channels=3, resolution=128, fmap_base=1024, fmap_decay=1.0, fmap_max=512,
-              latent_res=32, latent_channels=128, **_):
+              latent_res=32, latent_channels=128, fused_scale=False, **_):
     """Variable table of E_zl (networks.py:296-383)."""
+    c1 = 'Conv1_down' if fused_scale else 'Conv1'
     nf = nf_fn(fmap_base, fmap_decay, fmap_max)
     rl2 = int(np.log2(resolution))
     ll2 = int(np.log2(latent_res))
@@ -164,7 +190,7 @@ def spec_E_zl(num_channels=3, resolution=128, fmap_base=1024, fmap_decay=1.0, fm
         _add_conv(spec, 'FromRGB_lod%d' % (rl2 - res), 1, num_channels, nf(res - 1), SQRT2)
         s = '%dx%d' % (2 ** res, 2 ** res)
         _add_conv(spec, s + '/Conv0', 3, nf(res - 1), nf(res - 1), SQRT2)
-        _add_conv(spec, s + '/Conv1', 3, nf(res - 1), nf(res - 2), SQRT2)
+        _add_conv(spec, s + '/' + c1, 3, nf(res - 1), nf(res - 2), SQRT2)
     _add_conv(spec, 'FromRGB_lod%d' % (rl2 - ll2), 1, num_channels, nf(ll2 - 1), SQRT2)
     s = '%dx%d' % (2 ** ll2, 2 ** ll2)
     _add_conv(spec, s + '/Conv0', 3, nf(ll2 - 1), nf(ll2 - 1), SQRT2)
@@ -173,7 +199,7 @@ def spec_E_zl(num_channels=3, resolution=128, fmap_base=1024, fmap_decay=1.0, fm
 
 
 def spec_G_res(num_channels=3, resolution=128, fmap_base=1024, fmap_decay=1.0, fmap_max=512,
-               latent_res=32, latent_channels=128, **_):
+               latent_res=32, latent_channels=128, fused_scale=False, **_):
     """Variable table of G_res (networks.py:388-486)."""
     nf = nf_fn(fmap_base, fmap_decay, fmap_max)
     rl2 = int(np.log2(resolution))
@@ -188,7 +214,11 @@ def spec_G_res(num_channels=3, resolution=128, fmap_base=1024, fmap_decay=1.0, f
     _add_conv(spec, s + '/Conv1', 3, nf(ll2 - 1), nf(ll2 - 1), SQRT2)
     for res in range(ll2 + 1, rl2 + 1):
         s = '%dx%d' % (2 ** res, 2 ** res)
-        _add_conv(spec, s + '/Conv0', 3, nf(res - 2), nf(res - 1), SQRT2)
+        if fused_scale:                  # networks.py:95: the transposed-conv variable is [k, k, fmaps, Cin]
+            spec[s + '/Conv0_up/weight'] = dict(shape=(3, 3, nf(res - 1), nf(res - 2)), gain=SQRT2)
+            spec[s + '/Conv0_up/bias'] = dict(shape=(nf(res - 1),))
+        else:
+            _add_conv(spec, s + '/Conv0', 3, nf(res - 2), nf(res - 1), SQRT2)
         _add_conv(spec, s + '/Conv1', 3, nf(res - 1), nf(res - 1), SQRT2)
     # ToRGB heads are created on the way back out of the recursion: lod0 first.
     for res in range(rl2, ll2 - 1, -1):
@@ -197,8 +227,9 @@ def spec_G_res(num_channels=3, resolution=128, fmap_base=1024, fmap_decay=1.0, f
 
 
 def spec_D_patch(num_channels=3, resolution=128, fmap_base=1024, fmap_decay=1.0, fmap_max=512,
-                 latent_res=-1, mbstd_group_size=4, **_):
+                 latent_res=-1, mbstd_group_size=4, fused_scale=False, **_):
     """Variable table of D_patch (networks.py:491-577)."""
+    c1 = 'Conv1_down' if fused_scale else 'Conv1'
     nf = nf_fn(fmap_base, fmap_decay, fmap_max)
     rl2 = int(np.log2(resolution))
     ll2 = 2 if latent_res == -1 else int(np.log2(latent_res))
@@ -207,7 +238,7 @@ def spec_D_patch(num_channels=3, resolution=128, fmap_base=1024, fmap_decay=1.0,
         _add_conv(spec, 'FromRGB_lod%d' % (rl2 - res), 1, num_channels, nf(res - 1), SQRT2)
         s = '%dx%d' % (2 ** res, 2 ** res)
         _add_conv(spec, s + '/Conv0', 3, nf(res - 1), nf(res - 1), SQRT2)
-        _add_conv(spec, s + '/Conv1', 3, nf(res - 1), nf(res - 2), SQRT2)
+        _add_conv(spec, s + '/' + c1, 3, nf(res - 1), nf(res - 2), SQRT2)
     _add_conv(spec, 'FromRGB_lod%d' % (rl2 - ll2), 1, num_channels, nf(ll2 - 1), SQRT2)
     s = '%dx%d' % (2 ** ll2, 2 ** ll2)
     cin = nf(ll2 - 1) + (1 if mbstd_group_size > 1 else 0)
@@ -254,10 +285,10 @@ def to_torch(params, dtype=torch.float32, requires_grad=False):
 # dict, receives every named intermediate (pre-activation too) for per-layer
 # parity checks.
 
-def _layer(P, scope, x, gain=SQRT2, act=True, taps=None, pn=None):
+def _layer(P, scope, x, gain=SQRT2, act=True, taps=None, pn=None, op=None):
     """[PN](act(apply_bias(conv2d(x)))): `pn` = pixel_norm epsilon of the blocks' activated convs when
-    use_pixelnorm (networks.py:216,320,415), None otherwise."""
-    x = apply_bias(conv2d(x, P[scope + '/weight'], gain), P[scope + '/bias'])
+    use_pixelnorm (networks.py:216,320,415), None otherwise; `op` = the fused up/down-scaling conv instead."""
+    x = apply_bias((op or conv2d)(x, P[scope + '/weight'], gain), P[scope + '/bias'])
     if taps is not None:
         taps[scope + ':pre'] = x
     if act:
@@ -285,7 +316,8 @@ def _encoder_trunk(images_in, P, resolution, min_res_log2, block, fromrgb, lod_i
 
 
 def E_zg(images_in, P, num_channels=3, resolution=128, fmap_base=1024, fmap_decay=1.0, fmap_max=512,
-         latent_channels=128, tanh_at_end=False, taps=None, use_pixelnorm=False, pixelnorm_epsilon=1e-8, **_):
+         latent_channels=128, tanh_at_end=False, taps=None, use_pixelnorm=False, pixelnorm_epsilon=1e-8,
+         fused_scale=False, **_):
     """networks.py:194-291 -> (zg_mu, zg_log_sigma), each [N,latent_channels,1,1]."""
     pn = pixelnorm_epsilon if use_pixelnorm else None
     rl2 = int(np.log2(resolution))
@@ -300,9 +332,14 @@ def E_zg(images_in, P, num_channels=3, resolution=128, fmap_base=1024, fmap_deca
         s = '%dx%d' % (2 ** res, 2 ** res)
         if res >= 3:
             x = _layer(P, s + '/Conv0', x, taps=taps, pn=pn)
+            if fused_scale:
+                return _layer(P, s + '/Conv1_down', x, taps=taps, pn=pn, op=conv2d_downscale2d)
             x = _layer(P, s + '/Conv1', x, taps=taps, pn=pn)
             return downscale2d(x)
         x = _layer(P, s + '/Conv0', x, taps=taps, pn=pn)
+        if fused_scale:                                                 # networks.py:245-249
+            x = _layer(P, s + '/zg_Conv1_down', x, taps=taps, pn=pn, op=conv2d_downscale2d)
+            return _layer(P, s + '/zg_Conv2_down', x, gain=1.0, act=False, taps=taps, op=conv2d_downscale2d)
         x = downscale2d(_layer(P, s + '/zg_Conv1', x, taps=taps, pn=pn))
         x = downscale2d(_layer(P, s + '/zg_Conv2', x, taps=taps, pn=pn))
         return _layer(P, s + '/zg_Conv3', x, gain=1.0, act=False, taps=taps, pn=pn)
@@ -315,7 +352,7 @@ def E_zg(images_in, P, num_channels=3, resolution=128, fmap_base=1024, fmap_deca
 
 def E_zl(images_in, P, num_channels=3, resolution=128, fmap_base=1024, fmap_decay=1.0, fmap_max=512,
          latent_res=32, latent_channels=128, tanh_at_end=False, taps=None, use_pixelnorm=False,
-         pixelnorm_epsilon=1e-8, **_):
+         pixelnorm_epsilon=1e-8, fused_scale=False, **_):
     """networks.py:296-383 -> (z_mu, z_log_sigma), each [N,latent_channels,latent_res,latent_res]."""
     pn = pixelnorm_epsilon if use_pixelnorm else None
     rl2 = int(np.log2(resolution))
@@ -331,6 +368,8 @@ def E_zl(images_in, P, num_channels=3, resolution=128, fmap_base=1024, fmap_deca
         s = '%dx%d' % (2 ** res, 2 ** res)
         if res > ll2:
             x = _layer(P, s + '/Conv0', x, taps=taps, pn=pn)
+            if fused_scale:
+                return _layer(P, s + '/Conv1_down', x, taps=taps, pn=pn, op=conv2d_downscale2d)
             x = _layer(P, s + '/Conv1', x, taps=taps, pn=pn)
             return downscale2d(x)
         x = _layer(P, s + '/Conv0', x, taps=taps, pn=pn)
@@ -344,7 +383,7 @@ def E_zl(images_in, P, num_channels=3, resolution=128, fmap_base=1024, fmap_deca
 
 def G_res(zg_latents_in, zl_latents_in, P, num_channels=3, resolution=128, fmap_base=1024,
           fmap_decay=1.0, fmap_max=512, latent_res=32, latent_channels=128, tanh_at_end=True,
-          scale_h=1, scale_w=1, taps=None, use_pixelnorm=False, pixelnorm_epsilon=1e-8, **_):
+          scale_h=1, scale_w=1, taps=None, use_pixelnorm=False, pixelnorm_epsilon=1e-8, fused_scale=False, **_):
     """networks.py:388-486 -> images [N,num_channels,resolution*scale_h,resolution*scale_w]."""
     pn = pixelnorm_epsilon if use_pixelnorm else None
     rl2 = int(np.log2(resolution))
@@ -368,8 +407,11 @@ def G_res(zg_latents_in, zl_latents_in, P, num_channels=3, resolution=128, fmap_
             x = _layer(P, s + '/Conv0', x, gain=SQRT2 / 4, taps=taps, pn=pn)  # networks.py:440
             x = _layer(P, s + '/Conv1', x, taps=taps, pn=pn)
         else:
-            x = upscale2d(x)
-            x = _layer(P, s + '/Conv0', x, taps=taps, pn=pn)
+            if fused_scale:
+                x = _layer(P, s + '/Conv0_up', x, taps=taps, pn=pn, op=upscale2d_conv2d)
+            else:
+                x = upscale2d(x)
+                x = _layer(P, s + '/Conv0', x, taps=taps, pn=pn)
             x = _layer(P, s + '/Conv1', x, taps=taps, pn=pn)
         return x
 
@@ -393,7 +435,7 @@ def G_res(zg_latents_in, zl_latents_in, P, num_channels=3, resolution=128, fmap_
 
 
 def D_patch(images_in, P, num_channels=3, resolution=128, fmap_base=1024, fmap_decay=1.0, fmap_max=512,
-            latent_res=-1, mbstd_group_size=4, taps=None, **_):
+            latent_res=-1, mbstd_group_size=4, taps=None, fused_scale=False, **_):
     """networks.py:491-577 -> scores [N,1,1,1] (latent_res=-1: FC head)."""
     rl2 = int(np.log2(resolution))
     ll2 = 2 if latent_res == -1 else int(np.log2(latent_res))
@@ -407,6 +449,8 @@ def D_patch(images_in, P, num_channels=3, resolution=128, fmap_base=1024, fmap_d
         s = '%dx%d' % (2 ** res, 2 ** res)
         if res > ll2:
             x = _layer(P, s + '/Conv0', x, taps=taps)
+            if fused_scale:
+                return _layer(P, s + '/Conv1_down', x, taps=taps, op=conv2d_downscale2d)
             x = _layer(P, s + '/Conv1', x, taps=taps)
             return downscale2d(x)
         if mbstd_group_size > 1:

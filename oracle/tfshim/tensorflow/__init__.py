@@ -464,10 +464,20 @@ class nn:
     @staticmethod
     def conv2d(x, w=None, strides=(1, 1, 1, 1), padding='VALID', data_format='NHWC', filter=None, name=None):  # noqa: A002
         w = w if w is not None else filter
-        assert data_format == 'NCHW' and padding == 'VALID', 'shim: only the NCHW/VALID form the hot path uses'
+        assert data_format == 'NCHW' and padding in ('VALID', 'SAME'), 'shim: NCHW only'
         s = _ilist(strides)
+        xr, wr = _raw(x), _raw(w)
+        if padding == 'SAME':
+            # TF SAME: out = ceil(in / stride), pad_total = max((out - 1) * stride + k - in, 0), the odd pixel goes
+            # AFTER (networks.py:148 conv2d_downscale2d: k = 4, stride 2 -> one zero pixel on every side)
+            pads = []
+            for dim, k, st in ((3, wr.shape[1], s[3]), (2, wr.shape[0], s[2])):
+                n_in = xr.shape[dim]
+                total = max((-(-n_in // st) - 1) * st + k - n_in, 0)
+                pads += [total // 2, total - total // 2]
+            xr = F.pad(xr, pads)
         # TF conv2d = cross-correlation with HWIO filters; torch conv2d = cross-correlation with OIHW.
-        return Tensor(F.conv2d(_raw(x), _raw(w).permute(3, 2, 0, 1), stride=(s[2], s[3])))
+        return Tensor(F.conv2d(xr, wr.permute(3, 2, 0, 1), stride=(s[2], s[3])))
 
     @staticmethod
     def avg_pool(x, ksize, strides, padding='VALID', data_format='NHWC'):
@@ -484,8 +494,19 @@ class nn:
         return Tensor(torch.tanh(_raw(x)), name)
 
     @staticmethod
-    def conv2d_transpose(*a, **k):
-        raise NotImplementedError('shim: fused_scale path (networks.py:94-101) is off by default')
+    def conv2d_transpose(x, w, output_shape, strides=(1, 1, 1, 1), padding='SAME', data_format='NHWC'):
+        """Gradient of nn.conv2d(SAME) w.r.t. its input (networks.py:101 upscale2d_conv2d): filter [h, w, out, in].
+        For stride 2 and the even 4x4 kernel SAME pads one pixel on every side of the forward conv's input, so the
+        transpose crops one pixel per side: torch padding = 1."""
+        assert data_format == 'NCHW' and padding == 'SAME'
+        s = _ilist(strides)
+        xr, wr = _raw(x), _raw(w)
+        k = wr.shape[0]
+        assert s[2] == s[3] == 2 and k == wr.shape[1] and (k - 2) % 2 == 0, 'shim: stride-2 SAME with an even kernel'
+        out = F.conv_transpose2d(xr, wr.permute(3, 2, 0, 1), stride=2, padding=(k - 2) // 2)
+        want = _ilist(output_shape)
+        assert list(out.shape[1:]) == [int(v) for v in want[1:]], (tuple(out.shape), want)
+        return Tensor(out)
 
 
 def trainable_variables():

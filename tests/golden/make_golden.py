@@ -138,6 +138,38 @@ def variant_tag(func, lod, pn):
     return '%s_lod%s%s' % (func, ('%g' % lod).replace('.', 'p'), '_pn' if pn else '')
 
 
+# fused_scale=True (networks.py:94-101 upscale2d_conv2d, :142-148 conv2d_downscale2d): other variables, other ops
+FUSED_VARIANTS = [('E_zg', 0.0), ('E_zl', 0.0), ('G_res', 0.0), ('D_patch', 0.0), ('G_res', 1.5), ('E_zl', 0.5)]
+
+
+def gen_network_fused():
+    net, tf = refload.reference_networks()
+    out = {}
+    for func, lod in FUSED_VARIANTS:
+        n = 4 if func == 'D_patch' else 2
+        rng = np.random.RandomState(1000)
+        cfg = dict(R.CONFIG[func], fused_scale=True)
+        params = R.init_params(func, rng, **cfg)
+        params['lod'] = np.float32(lod)
+        ins = network_inputs(func, rng, n)
+        tf.reset_default_graph(values={func + '/' + k: v for k, v in params.items()})
+        with tf.variable_scope(func):
+            res = getattr(net, func)(*[tf.convert_to_tensor(a) for a in ins], num_channels=3, resolution=128, **cfg)
+        res = res if isinstance(res, tuple) else (res,)
+        names = [k[len(func) + 1:] for k in tf.STORE.vars]
+        assert names == list(params.keys()), (names, list(params.keys()))
+        tag = variant_tag(func, lod, False) + '_fused'
+        out[tag + '_varnames'] = np.array(names)
+        for i, r in enumerate(res):
+            a = r.numpy()
+            flat = a.reshape(-1)
+            out['%s_out%d_shape' % (tag, i)] = np.array(a.shape, np.int64)
+            out['%s_out%d' % (tag, i)] = (flat[::SUBSAMPLE] if flat.size > 4096 else flat).astype(np.float32)
+            out['%s_out%d_absmax' % (tag, i)] = np.array([np.abs(a).max()], np.float32)
+    np.savez_compressed(os.path.join(HERE, 'networks_fused.npz'), **out)
+    print('networks_fused.npz', sorted(k for k in out if k.endswith('_out0')))
+
+
 def gen_network_variants():
     net, tf = refload.reference_networks()
     out = {}
@@ -204,9 +236,13 @@ if __name__ == '__main__':
     if 'apps' in sys.argv[1:]:
         gen_app_mattes()
         sys.exit(0)
+    if 'fused' in sys.argv[1:]:
+        gen_network_fused()
+        sys.exit(0)
     gen_perm()
     gen_mattes()
     gen_networks()
     gen_network_variants()
     gen_schedule()
     gen_app_mattes()
+    gen_network_fused()
