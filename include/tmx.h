@@ -321,6 +321,10 @@ int tmx_weighted_sum(tmx_handle_t h, const float* const* srcs, const int* bcast,
 int tmx_tanh_f32(tmx_handle_t h, const float* in, float* out, int64_t n, tmx_stream_t s);
 /* its adjoint: dx = dy * (1 - y^2) with y = tanh(x). */
 int tmx_tanh_bwd(tmx_handle_t h, const float* dy, const float* y, float* dx, int64_t n, tmx_stream_t s);
+/* y = [lrelu](x + bias[c]) on NHWC fp32 [npix][C]: apply_bias + leaky_relu behind the fused conv2d_downscale2d
+ * (networks.py:142-148), whose bias and activation follow the 2x2 average. */
+int tmx_bias_act(tmx_handle_t h, const float* x, const float* bias, float* y, int64_t npix, int C, int lrelu,
+                 float alpha, tmx_stream_t s);
 /* pixel_norm (networks.py:170-172) on NHWC fp32 [npix][C]: y = x * rsqrt(mean_c x^2 + eps). */
 int tmx_pixel_norm(tmx_handle_t h, const float* x, float* y, int64_t npix, int C, float eps, tmx_stream_t s);
 

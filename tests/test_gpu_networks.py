@@ -257,3 +257,38 @@ def test_output_conversion_kernel_bit_exact():
     assert s.shape == (2, 3, 4, 6) and np.abs(s - ref).max() <= 1e-5
     i16 = _convert_output(xd[1:], 30000.0, 0.0, 1, np.int16).cpu().numpy()
     assert i16.dtype == np.int16 and np.array_equal(i16, np.clip(np.rint(x[1:] * np.float32(30000.0)), -32768, 32767).astype(np.int16))
+
+
+def _fused_table():
+    src = open(os.path.join(GOLDEN, 'make_golden.py')).read()
+    ns = {}
+    exec(src[src.index('FUSED_VARIANTS = ['):src.index('def gen_network_fused')], ns)
+    return ns['FUSED_VARIANTS']
+
+
+@pytest.mark.parametrize('func,lod', _fused_table())
+def test_fused_scale_variants_match_reference_golden(func, lod):
+    """fused_scale=True - `upscale2d_conv2d` (conv2d_transpose, networks.py:94-101) as the sub-pixel
+    upsample+conv kernel over ZERO-halo planes with the flipped / channel-swapped kernel, `conv2d_downscale2d`
+    (:142-148) as zero-padded conv + 2x2 average + bias/activation - against the reference's own networks.py."""
+    g = np.load(os.path.join(GOLDEN, 'networks_fused.npz'))
+    n = 4 if func == 'D_patch' else 2
+    rng = np.random.RandomState(1000)
+    cfg = dict(R.CONFIG[func], fused_scale=True)
+    params = R.init_params(func, rng, **cfg)
+    params['lod'] = np.float32(lod)
+    ins = _inputs(func, rng, n)
+    net = _make(func, params, fused_scale=True)
+    tag = variant_tag(func, lod, False) + '_fused'
+    assert list(net.vars.keys()) == [str(s) for s in g[tag + '_varnames']]
+    outs = net.run(*ins, return_as_list=True)
+    with torch.no_grad():
+        want = R.NETWORKS[func](*[torch.from_numpy(a) for a in ins], R.to_torch(params), **cfg)
+    want = want if isinstance(want, tuple) else (want,)
+    for i, a in enumerate(outs):
+        assert list(a.shape) == g['%s_out%d_shape' % (tag, i)].tolist()
+        flat = a.reshape(-1)
+        got = flat[::SUBSAMPLE] if flat.size > 4096 else flat
+        scale = float(g['%s_out%d_absmax' % (tag, i)][0])
+        assert np.abs(got - g['%s_out%d' % (tag, i)]).max() <= TOL * scale
+        assert _nmax(a, want[i].numpy()) <= TOL

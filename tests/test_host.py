@@ -140,9 +140,12 @@ def test_network_boundary_bookkeeping():
     assert np.array_equal(G2.get_var('ToRGB_lod0/weight'), G.get_var('ToRGB_lod0/weight'))
     with pytest.raises(AssertionError):
         Network('bad', func='networks.G_res', device='cpu', num_channels=3, resolution=100, **CFG['G_res'])
-    with pytest.raises(NotImplementedError):
-        Network('bad', func='networks.G_res', device='cpu', num_channels=3, resolution=128, fused_scale=True,
+    with pytest.raises(NotImplementedError):                     # variants the device path does not implement are loud
+        Network('bad', func='networks.G_res', device='cpu', num_channels=3, resolution=128, use_wscale=False,
                 **CFG['G_res'])
+    fused = Network('G', func='networks.G_res', device='cpu', num_channels=3, resolution=128, fused_scale=True,
+                    **CFG['G_res'])                              # fused_scale: the transposed-conv variable layout
+    assert fused.vars['64x64/Conv0_up/weight'].shape == (3, 3, 32, 64) and '64x64/Conv0/weight' not in fused.vars
 
 
 def test_aliases_resolve():

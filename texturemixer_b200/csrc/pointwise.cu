@@ -212,7 +212,9 @@ extern "C" int tmx_nhwc_to_nchw(tmx_handle_t h, const float* x, float* y, int N,
 // One thread = one padded pixel x 8 channels (2 float4 in, 16 B hi + 16 B lo out).
 __global__ void __launch_bounds__(256) split_halo_pack_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi,
                                                               uint16_t* __restrict__ lo, long long total, int H, int W,
-                                                              int C8, int replicate) {
+                                                              int C8, int halo_kind) {
+  // halo_kind 0: REFLECT (networks.py:55), 1: REPLICATE (REFLECT seen through upscale2d), 2: ZERO (the SAME
+  // padding of the fused_scale convs, networks.py:101,148)
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   int c8 = (int)(t % C8);
@@ -222,11 +224,16 @@ __global__ void __launch_bounds__(256) split_halo_pack_kernel(const float* __res
   long long q = p / Wp;
   int yp = (int)(q % Hp);
   long long n = q / Hp;
+  const bool replicate = halo_kind == 1;
   int ys = replicate ? min(max(yp - 1, 0), H - 1) : tmx_reflect(yp - 1, H);
   int xs = replicate ? min(max(xp - 1, 0), W - 1) : tmx_reflect(xp - 1, W);
   const float4* src = reinterpret_cast<const float4*>(x) + ((n * H + ys) * W + xs) * (C8 * 2) + c8 * 2;
   float4 a = __ldg(src), b = __ldg(src + 1);
   float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  if (halo_kind == 2 && (yp == 0 || yp == Hp - 1 || xp == 0 || xp == Wp - 1)) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  }
   uint32_t ph[4], pl[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -269,6 +276,7 @@ __global__ void __launch_bounds__(256) split_halo_unpack_kernel(const uint16_t* 
 extern "C" int tmx_split_halo_pack(tmx_handle_t h, const float* x, uint16_t* hi, uint16_t* lo, int N, int H, int W,
                                    int C, int replicate, tmx_stream_t s) {
   TMX_REQUIRE(h && x && hi && lo, TMX_ERR_ARG, "tmx_split_halo_pack: NULL argument");
+  TMX_REQUIRE(replicate >= 0 && replicate <= 2, TMX_ERR_ARG, "tmx_split_halo_pack: halo kind %d not in 0..2", replicate);
   TMX_REQUIRE(N > 0 && H >= 2 && W >= 2 && C > 0 && C % 8 == 0, TMX_ERR_SHAPE,
               "tmx_split_halo_pack: bad shape N=%d H=%d W=%d C=%d (H, W >= 2; C %% 8 == 0)", N, H, W, C);
   long long total = (long long)N * (H + 2) * (W + 2) * (C / 8);
@@ -839,5 +847,28 @@ extern "C" int tmx_weighted_sum(tmx_handle_t h, const float* const* srcs, const 
   const int grid = (int)(total / 256 + 1 < 148LL * 16 ? total / 256 + 1 : 148LL * 16);
   weighted_sum_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(srcs, bcast, weights, out, K, (long long)N * C, H * W, math_f32);
   TMX_LAUNCHED(h, "weighted_sum_kernel");
+  return TMX_OK;
+}
+
+// ---------------------------------------------------------------- bias + leaky ReLU on an NHWC fp32 map
+// act(apply_bias(.)) behind conv2d_downscale2d (networks.py:61-75, 142-148): with fused_scale the bias and the
+// activation follow the (linear) conv + 2x2 average instead of preceding the pool.
+__global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__ x, const float* __restrict__ bias,
+                                                       float* __restrict__ y, long long total, int C, int lrelu,
+                                                       float alpha) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    float v = __ldg(x + i) + (bias ? __ldg(bias + (int)(i % C)) : 0.f);
+    y[i] = lrelu ? fmaxf(v * alpha, v) : v;
+  }
+}
+
+extern "C" int tmx_bias_act(tmx_handle_t h, const float* x, const float* bias, float* y, int64_t npix, int C, int lrelu,
+                            float alpha, tmx_stream_t s) {
+  TMX_REQUIRE(h && x && y && npix > 0 && C > 0, TMX_ERR_ARG, "tmx_bias_act: bad argument");
+  const long long total = npix * C;
+  const int grid = (int)(total / 256 + 1 < 148LL * 16 ? total / 256 + 1 : 148LL * 16);
+  bias_act_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, bias, y, total, C, lrelu, alpha);
+  TMX_LAUNCHED(h, "bias_act_kernel");
   return TMX_OK;
 }

@@ -37,10 +37,10 @@ def _wscale_cached(shape, gain):
 
 
 def _check_variants(use_wscale, use_leakyrelu, fused_scale, dtype):
-    if not use_wscale or not use_leakyrelu or fused_scale or dtype != 'float32':
-        raise NotImplementedError('texturemixer_b200: only use_wscale=True, use_leakyrelu=True, fused_scale=False, '
-                                  'dtype=float32 (the reference defaults; use_pixelnorm is free) are implemented on '
-                                  'the device')
+    if not use_wscale or not use_leakyrelu or dtype != 'float32':
+        raise NotImplementedError('texturemixer_b200: only use_wscale=True, use_leakyrelu=True, dtype=float32 (the '
+                                  'reference defaults; use_pixelnorm and fused_scale are free) are implemented on the '
+                                  'device')
 
 
 def _act_of(t):
@@ -127,6 +127,62 @@ def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=Fals
         ctx.tape.append(dict(kind='view', x=t.act, y=out, pixels=m))
         t.act = out
     return t
+
+
+def _fused_conv_prologue(x, wshape, fmaps, out_hw_factor):
+    """Variables and template shape shared by the two fused_scale layers (inference only)."""
+    ctx = x.ctx
+    w = ctx.get_variable('weight', wshape)
+    b = ctx.get_variable('bias', (fmaps,), init='zeros')
+    num, den = out_hw_factor
+    shape = [x.shape[0], fmaps, None if x.shape[2] is None else x.shape[2] * num // den,
+             None if x.shape[3] is None else x.shape[3] * num // den]
+    if ctx.mode == 'run' and ctx.tape is not None:
+        raise NotImplementedError('training with fused_scale=True is not implemented (SURVEY N4); inference is')
+    return ctx, w, b, shape
+
+
+def upscale2d_conv2d_layer(x, fmaps, gain=SQRT2):
+    """act(apply_bias(upscale2d_conv2d(x))) (networks.py:94-101, 444-446): conv2d_transpose, stride 2, SAME, with the
+    3x3 variable [k,k,fmaps,Cin] fused to 4x4.  Identical to the 3x3 convolution of the nearest-neighbour upscaled
+    input under ZERO padding with the kernel flipped and its channel axes swapped (checked against the reference
+    code in tests/golden/networks_fused.npz), i.e. the sub-pixel upsample+conv kernel over zero-halo planes."""
+    cin = x.shape[1]
+    ctx, w, b, shape = _fused_conv_prologue(x, (3, 3, fmaps, cin), fmaps, (2, 1))
+    if ctx.mode == 'template':
+        return T(shape, ctx)
+    rt = ctx.rt
+    xa = _act_of(x)
+    ws = float(np.float32(gain / np.sqrt(9 * cin)))                       # fan_in = k*k*Cin (networks.py:96)
+    w_eq, planes = ctx.net.cached(('fused_up', w.name), lambda: _fused_up_weights(rt, w.value, ws, cin, fmaps))
+    out = rt.conv2d(xa, w_eq, b.value, ws, 3, fmaps, lrelu=True, up2=True, want_f32=True, want_split=False, algo=2,
+                    prepared=planes, halo_in='zero')
+    t = T(shape, ctx, act=out)
+    return _pixel_norm(ctx, t, ctx.pixelnorm) if ctx.pixelnorm is not None else t
+
+
+def _fused_up_weights(rt, w_var, ws, cin, fmaps):
+    w_eq = w_var.flip(0, 1).permute(0, 1, 3, 2).contiguous()              # [3,3,Cin,fmaps], taps flipped (layout move)
+    return w_eq, rt.prepare_weights(w_eq, ws, 3, cin, fmaps, up2_phase=True)
+
+
+def conv2d_downscale2d_layer(x, fmaps, gain=SQRT2, act=True):
+    """[act](apply_bias(conv2d_downscale2d(x))) (networks.py:142-148): stride-2 SAME conv with the 3x3 variable fused
+    to 4x4 and scaled by 1/4 == the 2x2 average of the ZERO-padded 3x3 convolution; bias and activation follow the
+    average (they precede it in the unfused form)."""
+    cin = x.shape[1]
+    ctx, w, b, shape = _fused_conv_prologue(x, (3, 3, cin, fmaps), fmaps, (1, 2))
+    if ctx.mode == 'template':
+        return T(shape, ctx)
+    rt = ctx.rt
+    xa = _act_of(x)
+    ws = _wscale(w.shape, gain)
+    planes = ctx.net.prepared_weights(w, ws, 3, cin, fmaps, cin_pad=xa.c)
+    lin = rt.conv2d(xa, w.value, None, ws, 3, fmaps, lrelu=False, want_f32=True, want_split=False, algo=2,
+                    prepared=planes, halo_in='zero')
+    out = rt.bias_act(rt.avgpool2(lin), b.value, act)
+    t = T(shape, ctx, act=out)
+    return _pixel_norm(ctx, t, ctx.pixelnorm) if (ctx.pixelnorm is not None and act) else t
 
 
 def _pixel_strip(ctx, a):
@@ -334,11 +390,19 @@ def E_zg(images_in, num_channels=3, resolution=128, fmap_base=8192, fmap_decay=1
             if res >= 3:
                 with ctx.variable_scope('Conv0'):
                     x = conv2d_layer(x, nf(res - 1), 3, next_tc=_tc(ctx, nf(res - 1), nf(res - 2), 3))
+                if fused_scale:
+                    with ctx.variable_scope('Conv1_down'):
+                        return conv2d_downscale2d_layer(x, nf(res - 2))
                 with ctx.variable_scope('Conv1'):
                     x = conv2d_layer(x, nf(res - 2), 3)
                 return downscale2d(x)
             with ctx.variable_scope('Conv0'):
                 x = conv2d_layer(x, nf(res - 1), 3, next_tc=_tc(ctx, nf(res - 1), nf(res - 2), 3))
+            if fused_scale:                                                # networks.py:245-249
+                with ctx.variable_scope('zg_Conv1_down'):
+                    x = conv2d_downscale2d_layer(x, nf(res - 2))
+                with ctx.variable_scope('zg_Conv2_down'):
+                    return conv2d_downscale2d_layer(x, latent_channels * 2, gain=1, act=False)
             with ctx.variable_scope('zg_Conv1'):
                 x = conv2d_layer(x, nf(res - 2), 3)
             x = downscale2d(x)
@@ -382,6 +446,9 @@ def E_zl(images_in, num_channels=3, resolution=128, fmap_base=8192, fmap_decay=1
             if res > latent_res_log2:
                 with ctx.variable_scope('Conv0'):
                     x = conv2d_layer(x, nf(res - 1), 3, next_tc=_tc(ctx, nf(res - 1), nf(res - 2), 3))
+                if fused_scale:
+                    with ctx.variable_scope('Conv1_down'):
+                        return conv2d_downscale2d_layer(x, nf(res - 2))
                 with ctx.variable_scope('Conv1'):
                     x = conv2d_layer(x, nf(res - 2), 3)
                 return downscale2d(x)
@@ -449,6 +516,11 @@ def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_bas
                                          keep_f32=count < 4)
                 with ctx.variable_scope('Conv0'):
                     x = conv2d_layer(x, nf(res - 1), 3, gain=SQRT2 / 4, next_tc=_tc(ctx, nf(res - 1), nf(res - 1), 3))
+                with ctx.variable_scope('Conv1'):
+                    x = last_conv(x, res)
+            elif fused_scale:
+                with ctx.variable_scope('Conv0_up'):                       # networks.py:444-446
+                    x = upscale2d_conv2d_layer(x, nf(res - 1))
                 with ctx.variable_scope('Conv1'):
                     x = last_conv(x, res)
             else:
@@ -566,6 +638,9 @@ def D_patch(images_in, num_channels=3, resolution=128, fmap_base=8192, fmap_deca
             if res > latent_res_log2:
                 with ctx.variable_scope('Conv0'):
                     x = conv2d_layer(x, nf(res - 1), 3, next_tc=_tc(ctx, nf(res - 1), nf(res - 2), 3))
+                if fused_scale:
+                    with ctx.variable_scope('Conv1_down'):
+                        return conv2d_downscale2d_layer(x, nf(res - 2))
                 with ctx.variable_scope('Conv1'):
                     x = conv2d_layer(x, nf(res - 2), 3)
                 return downscale2d(x)

@@ -39,6 +39,9 @@ except AttributeError:                                     # pragma: no cover - 
         return torch.cuda.current_stream(index).cuda_stream
 
 
+HALO_KINDS = {'reflect': 0, 'replicate': 1, 'zero': 2}     # tmx_split_halo_pack
+
+
 class Runtime:
     """One per (process, device).  Holds the tmx handle; launches on torch's
     current stream so that CUDA-graph capture and stream semantics are torch's."""
@@ -125,7 +128,7 @@ class Runtime:
             act.lo = self.planes(act.n, act.h + 2, act.w + 2, act.c)
             act.halo = halo
             _lib.check(self.lib.tmx_split_halo_pack(self.handle, _ptr(act.f32), _ptr(act.hi), _ptr(act.lo), act.n,
-                                                    act.h, act.w, act.c, int(halo == 'replicate'), self.stream()),
+                                                    act.h, act.w, act.c, HALO_KINDS[halo], self.stream()),
                        'tmx_split_halo_pack')
         return act
 
@@ -177,7 +180,8 @@ class Runtime:
         return hi, lo
 
     def conv2d(self, x, w, bias, wscale, k, cout, lrelu=False, residual=None, up2=False, want_f32=True,
-               want_split=False, up2_out=False, halo_out='reflect', algo=None, prepared=None, torgb=None):
+               want_split=False, up2_out=False, halo_out='reflect', algo=None, prepared=None, torgb=None,
+               halo_in=None):
         """y = [residual +] lrelu(wscale*conv(x, w) + bias) on an Act.  `w` is the raw
         HWIO variable; `prepared` an optional (w_hi, w_lo) pair for the TC kernel
         (sub-pixel planes when up2).  `torgb` = (w_rgb [Cout,C], b_rgb, wscale, C, tanh)
@@ -203,13 +207,16 @@ class Runtime:
         if algo == _lib.ALGO_FFMA:
             if torgb is not None:
                 raise RuntimeError('conv2d: the fused ToRGB head needs the tensor-core kernel')
+            if halo_in not in (None, 'reflect'):
+                raise RuntimeError('conv2d: the CUDA-core kernel pads by REFLECT only (halo_in=%r)' % halo_in)
             self.split_unpack(x)
             io.x_f32 = x.f32.data_ptr()
             io.w = w.data_ptr()
             out = Act(x.n, h, w_, cout, f32=self.empty(x.n, h, w_, cout))
             io.y_f32 = out.f32.data_ptr()
         else:
-            self.split_pack(x, 'replicate' if up2 else 'reflect')
+            # halo_in='zero': the SAME (zero) padding of the fused_scale convs instead of the REFLECT default
+            self.split_pack(x, halo_in or ('replicate' if up2 else 'reflect'))
             io.x_hi, io.x_lo = x.hi.data_ptr(), x.lo.data_ptr()
             xmerge = self.use_xmerge(cin, k, up2) and x.hi.untyped_storage().nbytes() >= (x.hi.numel() + 64) * 2
             if xmerge:
@@ -367,6 +374,14 @@ class Runtime:
         out = self.empty(n, cout)
         _lib.check(self.lib.tmx_dense_fwd(self.handle, _ptr(x), _ptr(w), _ptr(bias), float(wscale), _ptr(out), _ptr(ws),
                                           n, k, cout, int(lrelu), LRELU_ALPHA, self.stream()), 'tmx_dense_fwd')
+        return out
+
+    def bias_act(self, x, bias, lrelu):
+        """[lrelu](x + bias) on an Act's fp32 map (tmx_bias_act)."""
+        self.split_unpack(x)
+        out = Act(x.n, x.h, x.w, x.c, f32=self.empty(x.n, x.h, x.w, x.c))
+        _lib.check(self.lib.tmx_bias_act(self.handle, _ptr(x.f32), _ptr(bias), _ptr(out.f32), x.n * x.h * x.w, x.c,
+                                         int(lrelu), LRELU_ALPHA, self.stream()), 'tmx_bias_act')
         return out
 
     # ------------------------------------------------------------------ latent blend
