@@ -299,6 +299,63 @@ TRAIN_BATCH = 32
 TRAIN_GFLOP = {True: 508.7, False: 908.9}
 
 
+def time_oracle_train_step(sample=2):
+    """One train step of the CPU restatement (oracle/: autograd losses incl. the create_graph gradient penalty, TF1
+    Adam restatement) on `sample` images, all host cores.  -> (samples/s, seconds, cores)."""
+    import torch
+    from oracle import interp_ref as I
+    from oracle import loss_ref as L
+    from oracle import networks_ref as R
+    from oracle import optim_ref as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rng = np.random.RandomState(1000)
+    np.random.seed(1000)
+    funcs = dict(E_zg='E_zg', E_zl='E_zl', G='G_res', D_rec='D_patch', D_interp='D_patch', D_blend='D_patch')
+    params = {k: R.init_params(f, rng, **R.CONFIG[f]) for k, f in funcs.items()}
+    x = torch.from_numpy(rng.uniform(-1, 1, (sample, 3, 128, 128)).astype(np.float32))
+    idx = I.sample_schedule_indices(sample, latent_res=32, scale_h=3, scale_w=3)
+    mix = lambda: torch.from_numpy(rng.uniform(0, 1, (sample, 1, 1, 1)).astype(np.float32))   # noqa: E731
+    crop = lambda: (int(rng.randint(0, 256)), int(rng.randint(0, 256)))                        # noqa: E731
+
+    def flat_grads(P):
+        return np.concatenate([(t.grad.numpy() if t.grad is not None else np.zeros(tuple(t.shape), np.float32)).reshape(-1)
+                               for k, t in P.items() if k != 'lod'])
+
+    def flat(P):
+        return np.concatenate([np.asarray(v, np.float32).reshape(-1) for k, v in P.items() if k != 'lod'])
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        P0 = {k: R.to_torch(params[k]) for k in ('E_zg', 'E_zl', 'G')}
+        zg, _ = R.E_zg(x, P0['E_zg'], **R.CONFIG['E_zg'])
+        zl, _ = R.E_zl(x, P0['E_zl'], **R.CONFIG['E_zl'])
+        rec = R.G_res(zg.repeat(1, 1, 32, 32), zl, P0['G'], **R.CONFIG['G_res'])
+        gcfg = dict(R.CONFIG['G_res'], scale_h=3, scale_w=3)
+        zg_c = zg.repeat(1, 1, 96, 96)
+        zl_c = L.tiling_permutation(zl, 3, 3, idx['h_forward'], idx['w_forward'])
+        y0, x0 = crop()
+        fake_i = R.G_res(zg_c, zl_c, P0['G'], **gcfg)[:, :, y0:y0 + 128, x0:x0 + 128]
+        zg_r = torch.flip(zg, dims=[0]).repeat(1, 1, 96, 96)
+        zl_r = L.tiling_permutation(torch.flip(zl, dims=[0]), 3, 3, idx['h_backward'], idx['w_backward'])
+        t = mix()
+        y0, x0 = crop()
+        fake_b = R.G_res(zg_r + (zg_c - zg_r) * t, zl_r + (zl_c - zl_r) * t, P0['G'], **gcfg)[:, :, y0:y0 + 128, x0:x0 + 128]
+    for k, fake in (('D_rec', rec), ('D_interp', fake_i), ('D_blend', fake_b)):
+        P = R.to_torch(params[k], requires_grad=True)
+        loss, _ = L.D_wgangp(P, fake, x, mix())
+        loss.mean().backward()
+        w = flat(params[k])
+        O.optimizer_step(w, [flat_grads(P)], O.AdamState(w.size, 0.0, 0.99), 0.0015)
+    P = {k: R.to_torch(params[k], requires_grad=k in ('E_zg', 'E_zl', 'G')) for k in funcs}
+    loss, _ = L.EG_wgan(P, x, idx, crop(), crop(), mix())
+    loss.mean().backward()
+    for k in ('E_zg', 'E_zl', 'G'):
+        w = flat(params[k])
+        O.optimizer_step(w, [flat_grads(P[k])], O.AdamState(w.size, 0.0, 0.99), 0.0015)
+    dt = time.perf_counter() - t0
+    return sample / dt, dt, cores
+
+
 def run_train(args):
     import torch
     import torch.distributed as dist
@@ -381,6 +438,12 @@ def run_train(args):
         samples = TRAIN_BATCH * world * args.steps
         value = samples / (dev_ms * 1e-3)
         tf = value * TRAIN_GFLOP_PER_SAMPLE / 1e3 / world
+        cpu_line = None
+        if world == 1:
+            cpu_v, cpu_s, cores = time_oracle_train_step(2)
+            cpu_line = {'value': cpu_v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                        'sample': 'ONE train step on 2 images (whole 3x3 canvases, autograd incl. the gradient penalty), '
+                                  'torch-CPU fp32 restatement (oracle/), %.1f s' % cpu_s}
         line = {
             'metric': '128x128 texture images/sec (full train step: 3 critics + E/G + EMA)', 'value': value,
             'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
@@ -400,7 +463,7 @@ def run_train(args):
                          'frac': tf / (pk['bf16_sustained'] or pk['bf16']), 'traffic': None,
                          'kernel': 'whole step per GPU (algorithmic fp32-conv FLOPs; tensor pipe executes 3x)',
                          'peak_source': pk['source'] + ', bf16 sustained'},
-            'cpu_baseline': None,
+            'cpu_baseline': cpu_line,
             'replicas_identical': bool(float(hi - lo) == 0.0),
             'clocks': clocks,
         }
@@ -553,6 +616,102 @@ def run_interp(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------ single-crop reconstruction (BASELINE configs[0])
+def run_recon(args):
+    """cfg 1 (run.py:371-375 `recs`): ONE 128x128 crop -> E_zg, E_zl -> G_res(tile(zg_mu, 32x32), z_mu), batch 1:
+    a latency number.  value: device-resident chain; e2e: the reference's own call sequence Es_zg.run / Es_zl.run /
+    np.tile / Gs.run with a host image in and a host image out; cpu_baseline: the same chain on the oracle."""
+    import torch
+    from texturemixer_b200 import interp
+    from texturemixer_b200.network import Network
+    from texturemixer_b200.runtime import Runtime
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a B200; there is no CPU path')
+    torch.cuda.set_device(local)
+    rt = Runtime.get(local)
+    dev = rt.device
+    enc = dict(fmap_base=1024, fmap_max=512, latent_channels=128, use_pixelnorm=False, tanh_at_end=False)
+    E_zg = Network('E_zg', func='networks.E_zg', seed=1000, num_channels=3, resolution=128, **enc)
+    E_zl = Network('E_zl', func='networks.E_zl', seed=1001, num_channels=3, resolution=128, latent_res=32, **enc)
+    G = Network('G', func='networks.G_res', seed=1002, num_channels=3, resolution=128, **G_CFG)
+    rng = np.random.RandomState(1000)
+    img_h = rng.uniform(-1, 1, (1, 3, 128, 128)).astype(np.float32)
+    img_d = torch.from_numpy(img_h).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def chain(x):
+        zg_mu, _ = E_zg.get_output_for(x)
+        zl_mu, _ = E_zl.get_output_for(x)
+        return G.get_output_for(interp.tiling_permutation(zg_mu, 32, 32, None, None, pin_corners=False), zl_mu)
+
+    def chain_host(x):
+        zg_mu, _ = E_zg.run(x)
+        zl_mu, _ = E_zl.run(x)
+        return G.run(np.tile(zg_mu, [1, 1, 32, 32]), zl_mu)
+
+    steps, warm = max(args.steps, 20), max(args.warmup, 3)
+    for _ in range(warm):
+        chain(img_d)
+        chain_host(img_h)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    l0 = rt.launch_count()
+    for a, b in evs:
+        flush.fill_(1)
+        a.record()
+        chain(img_d)
+        b.record()
+    torch.cuda.synchronize()
+    launches = rt.launch_count() - l0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out_h = chain_host(img_h)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    clocks = sampler.stop()
+    # CPU restatement of the same chain
+    from oracle import networks_ref as R
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = {f: R.to_torch(R.init_params(f, np.random.RandomState(i), **R.CONFIG[f])) for i, f in enumerate(('E_zg', 'E_zl', 'G_res'))}
+    x = torch.from_numpy(img_h)
+
+    def cpu_chain():
+        with torch.no_grad():
+            zg, _ = R.E_zg(x, P['E_zg'], **R.CONFIG['E_zg'])
+            zl, _ = R.E_zl(x, P['E_zl'], **R.CONFIG['E_zl'])
+            return R.G_res(zg.repeat(1, 1, 32, 32), zl, P['G_res'], **R.CONFIG['G_res'])
+    cpu_chain()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        cpu_chain()
+    cpu_ms = (time.perf_counter() - t0) * 1e3 / 5
+    line = {
+        'metric': '128x128 texture images/sec (single-crop reconstruction latency: E_zg + E_zl -> G_res, batch 1)',
+        'value': 1e3 / dev_ms, 'unit': 'images/s', 'n_gpus': 1, 'steps': steps, 'warmup': warm, 'ms_per_step': dev_ms,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32 (bf16x3 tensor-core products, fp32 accumulate)', 'data': 'synthetic',
+        'config': {'workload': 'cfg1: single 128x128x3 crop, encoder -> latent -> generator forward, batch 1',
+                   'l2': 'flushed between timed steps (256 MiB write)', 'gflop_per_image': 14.78},
+        'e2e': {'value': 1e3 / e2e_ms, 'unit': 'images/s', 'ms': e2e_ms, 'h2d_bytes_per_step': int(img_h.nbytes) * 2 + 2 * 128 * 1024 * 4,
+                'd2h_bytes_per_step': int(out_h.nbytes) + 2 * (128 + 128 * 1024) * 4,
+                'api': 'Es_zg.run(img), Es_zl.run(img), Gs.run(np.tile(zg_mu, 32x32), zl_mu) - the call sequence of run.py:371-375'},
+        'gpu_launches': int(launches),
+        'roofline': {'bound': 'tensor', 'achieved': 14.78 / dev_ms, 'peak': peaks()['bf16'], 'unit': 'TFLOP/s',
+                     'frac': 14.78 / dev_ms / peaks()['bf16'], 'traffic': None,
+                     'kernel': 'whole chain (batch 1 is launch- and latency-bound: ~60 launches on <= 8 of 148 SMs)'},
+        'cpu_baseline': {'value': 1e3 / cpu_ms, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'ms': cpu_ms,
+                         'sample': 'the same chain, 5 repetitions, torch-CPU fp32 restatement (oracle/)'},
+        'clocks': clocks,
+    }
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -562,7 +721,7 @@ def main():
     ap.add_argument('--device-only', action='store_true', help='only the device-resident loop (profiling runs)')
     ap.add_argument('--whole-canvas', action='store_true',
                     help='train_step: decode the whole 3x3 canvases in G_fcn instead of the crop windows')
-    ap.add_argument('--workload', default='gen_fwd', choices=['gen_fwd', 'train_step', 'interp'],
+    ap.add_argument('--workload', default='gen_fwd', choices=['gen_fwd', 'train_step', 'interp', 'recon'],
                     help='gen_fwd = BASELINE configs[1] (headline); train_step = configs[2]/[4]: full train step, '
                          'batch 32 per GPU, NCCL gradient all-reduce')
     args = ap.parse_args()
@@ -572,6 +731,8 @@ def main():
         run_train(args)
     elif args.workload == 'interp':
         run_interp(args)
+    elif args.workload == 'recon':
+        run_recon(args)
     else:
         run_ours(args)
 

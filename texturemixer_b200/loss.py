@@ -138,7 +138,7 @@ class EGForward:
     one step (run.py:511-512), so the critic phase can reuse `rec` and `interp` as its fakes."""
 
     def __init__(self, E_zg, E_zl, G, G_fcn, reals, idx, mixing_factors, scale_h=3, scale_w=3, need_interp=True,
-                 need_blend=True, crop_interp=None, crop_blend=None):
+                 need_blend=True, crop_interp=None, crop_blend=None, defer_canvases=False):
         """crop_interp / crop_blend: the (y, x) offsets the E/G loss will crop at; when given, G_fcn decodes only the
         latent window those crops depend on (`crop_window`) - same crop pixels, same gradients, 44 % of the work at
         the reference's 3x3 canvases.  None decodes the whole canvas."""
@@ -159,16 +159,28 @@ class EGForward:
         self.win = {'interp': None if crop_interp is None else crop_window(crop_interp, res, lat, H, W),
                     'blend': None if crop_blend is None else crop_window(crop_blend, res, lat, H, W)}
         self.planned = {'interp': crop_interp, 'blend': crop_blend}
+        self._need = (need_interp, need_blend)
         if need_interp or need_blend:
             self.ih_f, self.iw_f = _dev_idx(rt, idx['h_forward']), _dev_idx(rt, idx['w_forward'])
-        if need_interp:
-            zg_c, zl_c = fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, self.ih_f, self.iw_f, self.win['interp'])
-            self.interp = G_fcn.get_output_for(zg_c, zl_c, tape=self.t_int, **fcn_scale(zl_c, lat))
         if need_blend:
             self.ih_b, self.iw_b = _dev_idx(rt, idx['h_backward']), _dev_idx(rt, idx['w_backward'])
-            self.t = t = mixing_factors.reshape(-1).contiguous()
+            self.t = mixing_factors.reshape(-1).contiguous()
+        if not defer_canvases:
+            self.decode_canvases()
+
+    def decode_canvases(self):
+        """The two taped G_fcn evaluations (interpolated and blended canvases, loss.py:176-246).  Separate from the
+        constructor so that the trainer can start the critic phase - which only needs the encoders' codes and the
+        reconstruction - before them and let the two overlap."""
+        rt, (E_zg, E_zl, G, G_fcn) = self.rt, self.nets
+        zg_mu, zl_mu, H, W, pins, lat = self.zg_mu, self.zl_mu, self.H, self.W, self.pins, self.lat
+        need_interp, need_blend = self._need
+        if need_interp and self.interp is None:
+            zg_c, zl_c = fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, self.ih_f, self.iw_f, self.win['interp'])
+            self.interp = G_fcn.get_output_for(zg_c, zl_c, tape=self.t_int, **fcn_scale(zl_c, lat))
+        if need_blend and self.blend is None:
             bzg, bzl = fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, self.ih_f, self.iw_f, self.win['blend'],
-                                    blend=(self.ih_b, self.iw_b, t))
+                                    blend=(self.ih_b, self.iw_b, self.t))
             self.blend = G_fcn.get_output_for(bzg, bzl, tape=self.t_bl, **fcn_scale(bzl, lat))
 
     def window_offset(self, which, yx):

@@ -332,7 +332,11 @@ class Trainer:
         fwd = loss.EGForward(self.nets['E_zg'], self.nets['E_zl'], self.nets['G'], self.G_fcn, reals, draws.get('idx_dev', draws['idx']),
                              draws['eg_mix'], c['scale_h'], c['scale_w'],
                              crop_interp=draws['eg_crop_interp'] if ca else None,
-                             crop_blend=draws['eg_crop_blend'] if ca else None)
+                             crop_blend=draws['eg_crop_blend'] if ca else None, defer_canvases=True)
+        graphs = c.get('cuda_graphs', True) and not os.environ.get('TMX_NO_GRAPH') and lod_now == int(lod_now)
+        overlap = graphs and 'D' in phases and fwd.win['interp'] is not None
+        if not overlap:
+            fwd.decode_canvases()
         if 'D' in phases:
             if fwd.win['interp'] is None:           # whole canvas decoded: the interpolation image serves both phases
                 fake_interp = fwd.crop('interp', draws['d_interp_crop'])
@@ -340,8 +344,7 @@ class Trainer:
                 fake_interp = self._fcn_fake(fwd, 'interp', draws['d_interp_crop'])
             fakes = (('D_rec', fwd.rec, 'd_rec_gp'), ('D_interp', fake_interp, 'd_interp_gp'),
                      ('D_blend', self._fcn_fake(fwd, 'blend', draws['d_blend_crop'], draws['d_blend_mix']), 'd_blend_gp'))
-            # a fractional lod changes every step and is baked into the launches: graphs only at integer lod
-            graphs = c.get('cuda_graphs', True) and not os.environ.get('TMX_NO_GRAPH') and lod_now == int(lod_now)
+            # (a fractional lod changes every step and is baked into the launches: graphs only at integer lod)
             if graphs:
                 # the three critic graphs are independent: replay them on three streams so that their many small,
                 # latency-bound kernels (8x8 / 4x4 maps, dense head) overlap instead of queueing behind each other
@@ -359,6 +362,10 @@ class Trainer:
                     done.record(side)
                     joins.append(done)
                     report.update({name + '/' + k: v for k, v in rep.items()})
+                if overlap:
+                    # the taped G_fcn evaluations of the E/G phase do not depend on the critics: decode them on the
+                    # main stream WHILE the critic graphs (many thin, low-occupancy kernels) run on the side streams
+                    fwd.decode_canvases()
                 for done in joins:
                     main.wait_event(done)       # fakes / reals are only released by the caller after this join
             else:
