@@ -142,7 +142,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec_per_step * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'cfg2: G_res forward, batch 64 random latents, 128x128x3 out', 'batch_per_gpu': BATCH,
+        'config': {'workload': 'cfg2: G_res forward, batch 64 random latents per GPU, 128x128x3 out', 'batch_per_gpu': BATCH,
                    'note': 'CPU restatement of the TF1 graph (oracle/); TensorFlow 1.12 is not installable here'},
         'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': desc},
         'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -284,7 +284,7 @@ def run_ours(args):
                              'sample': '2 steps of G_res forward on 8 latents, torch-CPU fp32 restatement (oracle/)'},
             'clocks': clocks,
         }
-        print(json.dumps(line))
+        RESULT.append(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -467,7 +467,7 @@ def run_train(args):
             'replicas_identical': bool(float(hi - lo) == 0.0),
             'clocks': clocks,
         }
-        print(json.dumps(line))
+        RESULT.append(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -611,7 +611,7 @@ def run_interp(args):
                              'sample': 'G_res(scale 4x4) of ONE canvas, torch-CPU fp32 restatement (oracle/)'},
             'clocks': clocks,
         }
-        print(json.dumps(line))
+        RESULT.append(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -709,7 +709,20 @@ def run_recon(args):
                          'sample': 'the same chain, 5 repetitions, torch-CPU fp32 restatement (oracle/)'},
         'clocks': clocks,
     }
-    print(json.dumps(line))
+    RESULT.append(line)
+
+
+RESULT = []          # the JSON line of the GPU arm (rank 0), printed by main()
+BAD_CLOCK_REASONS = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown')
+
+
+def throttled(line):
+    c = (line or {}).get('clocks') or {}
+    if any(r in BAD_CLOCK_REASONS for r in c.get('reasons', [])):
+        return True
+    sm, mx = c.get('sm_mhz'), c.get('sm_max_mhz')
+    # clocks stuck well below max with no reason = a leftover clock lock (sw_power_cap is normal under tensor load)
+    return bool(sm and mx and sm < 0.7 * mx and not c.get('reasons'))
 
 
 def main():
@@ -727,14 +740,15 @@ def main():
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
-    elif args.workload == 'train_step':
-        run_train(args)
-    elif args.workload == 'interp':
-        run_interp(args)
-    elif args.workload == 'recon':
-        run_recon(args)
-    else:
-        run_ours(args)
+        return
+    fn = {'train_step': run_train, 'interp': run_interp, 'recon': run_recon}.get(args.workload, run_ours)
+    fn(args)
+    if RESULT and throttled(RESULT[-1]) and int(os.environ.get('WORLD_SIZE', '1')) == 1 and not args.device_only:
+        first = RESULT[-1]                       # thermal / hardware slowdown seen: the number is rejected, measure once more
+        fn(args)
+        RESULT[-1]['remeasured_after'] = first.get('clocks')
+    if RESULT:
+        print(json.dumps(RESULT[-1]))
 
 
 if __name__ == '__main__':
