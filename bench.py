@@ -296,7 +296,9 @@ TRAIN_BATCH = 32
 #   crop-aware     : G_fcn decodes the 64x64 latent window each random_crop depends on instead of the 96x96 canvas
 #                    (identical results, SURVEY Appendix C note): 8 units (the critics' interpolation fake no longer
 #                    shares the E/G image) x 116.2 x (64/96)^2 = 413.2, + 95.5                             = 508.7
-TRAIN_GFLOP = {True: 508.7, False: 908.9}
+#                    ... and its up-sampling blocks + ToRGB only the 40x40 latent pixels around the crop
+#                    (loss.tail_window): per unit 12.457 x 4 + 0.4546 x (40/32)^2 = 50.54 -> 8 x 50.54 + 95.5 = 499.8
+TRAIN_GFLOP = {True: 499.8, False: 908.9}
 
 
 def time_oracle_train_step(sample=2):
@@ -453,7 +455,8 @@ def run_train(args):
                        'batch_per_gpu': TRAIN_BATCH, 'global_batch': TRAIN_BATCH * world,
                        'l2': 'working set per step (>20 GB) far exceeds the 126 MB L2',
                        'parallelism': 'dp%d: one flat-bucket NCCL all-reduce per network per optimizer' % world,
-                       'g_fcn': 'crop-aware: decodes the 64x64 latent window of each random_crop (identical results)'
+                       'g_fcn': 'crop-aware: decodes the 64x64 latent window of each random_crop, up-sampling blocks on 40x40 of it '
+                                '(identical results)'
                        if cfg['crop_aware'] else 'whole 96x96 canvases decoded',
                        'gflop_per_sample': TRAIN_GFLOP_PER_SAMPLE},
             'e2e': {'value': samples / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': int(reals_h.numel() * 4),

@@ -383,7 +383,8 @@ def E_zl(images_in, P, num_channels=3, resolution=128, fmap_base=1024, fmap_deca
 
 def G_res(zg_latents_in, zl_latents_in, P, num_channels=3, resolution=128, fmap_base=1024,
           fmap_decay=1.0, fmap_max=512, latent_res=32, latent_channels=128, tanh_at_end=True,
-          scale_h=1, scale_w=1, taps=None, use_pixelnorm=False, pixelnorm_epsilon=1e-8, fused_scale=False, **_):
+          scale_h=1, scale_w=1, taps=None, use_pixelnorm=False, pixelnorm_epsilon=1e-8, fused_scale=False,
+          tail_window=None, **_):
     """networks.py:388-486 -> images [N,num_channels,resolution*scale_h,resolution*scale_w]."""
     pn = pixelnorm_epsilon if use_pixelnorm else None
     rl2 = int(np.log2(resolution))
@@ -420,6 +421,9 @@ def G_res(zg_latents_in, zl_latents_in, P, num_channels=3, resolution=128, fmap_
 
     def grow(x, res, lod):                                             # networks.py:473-479
         y = block(x, res)
+        if res == ll2 and tail_window is not None:       # not in the reference: test hook for the crop-aware windows
+            oy, ox, th, tw = tail_window
+            y = y[:, :, oy:oy + th, ox:ox + tw]
         if lod > 0 and lod_in < lod:
             return grow(y, res + 1, lod - 1)
         if res > ll2 and lod_in > lod:

@@ -7,7 +7,8 @@ import pytest
 import torch
 
 from oracle import networks_ref as R
-from texturemixer_b200.loss import G_CONTEXT, crop_window
+from texturemixer_b200 import loss as dev_loss
+from texturemixer_b200.loss import G_CONTEXT, crop_window, image_offset, tail_window
 
 CFG = dict(num_channels=3, resolution=128, fmap_base=64, fmap_max=8, latent_res=32, latent_channels=2,
            use_pixelnorm=False, tanh_at_end=True)
@@ -57,3 +58,43 @@ def test_windowed_decode_equals_full_decode(yx):
             continue
         scale = float(a.abs().max()) + 1e-12
         assert float((a - b).abs().max()) <= 1e-4 * scale, name
+
+
+@pytest.mark.parametrize('yx', [(0, 0), (255, 255), (57, 131), (128, 3), (56, 200), (199, 60), (1, 254), (130, 129),
+                                (7, 249), (64, 191)])
+def test_tail_window_equals_full_decode(yx, monkeypatch):
+    """Second level (loss.tail_window): the up-sampling blocks only see the crop's footprint + TAIL_CONTEXT latent
+    pixels.  Crop pixels and gradients must still equal the whole-canvas decode; with one pixel less context they
+    must not (the test would be blind otherwise)."""
+    rng = np.random.RandomState(9)
+    P = R.to_torch(R.init_params('G_res', rng, **CFG), requires_grad=True)
+    H = W = LAT * S
+    zg = torch.from_numpy(rng.randn(1, 2, 1, 1).astype(np.float32)).repeat(1, 1, H, W)
+    zl = torch.from_numpy(rng.randn(1, 2, H, W).astype(np.float32)).requires_grad_(True)
+    seed = torch.from_numpy(rng.randn(1, 3, RES, RES).astype(np.float32))
+    full = R.G_res(zg, zl, P, **dict(CFG, scale_h=S, scale_w=S))[:, :, yx[0]:yx[0] + RES, yx[1]:yx[1] + RES]
+    names = [k for k in P if k != 'lod']
+    g_full = torch.autograd.grad((full * seed).sum(), [zl] + [P[k] for k in names], allow_unused=True)
+
+    def windowed():
+        win = crop_window(yx, RES, LAT, H, W)
+        tail = tail_window(yx, RES, LAT, win, H, W)
+        assert tail is not None and tail[2] == tail[3] == dev_loss.TAIL_SIZE
+        oy, ox, wh, ww = win
+        img = R.G_res(zg[:, :, :wh, :ww], zl[:, :, oy:oy + wh, ox:ox + ww], P,
+                      **dict(CFG, scale_h=wh // LAT, scale_w=ww // LAT, tail_window=tail))
+        assert tuple(img.shape[2:]) == (4 * tail[2], 4 * tail[3])
+        y0, x0 = image_offset(yx, 4, win, tail)
+        return img[:, :, y0:y0 + RES, x0:x0 + RES]
+    part = windowed()
+    assert part.shape == full.shape and float((part - full).detach().abs().max()) <= 1e-5
+    g_part = torch.autograd.grad((part * seed).sum(), [zl] + [P[k] for k in names], allow_unused=True)
+    for name, a, b in zip(['zl'] + names, g_full, g_part):
+        if a is None and b is None:
+            continue
+        assert float((a - b).abs().max()) <= 1e-4 * (float(a.abs().max()) + 1e-12), name
+    if 8 <= yx[0] <= 240 and 8 <= yx[1] <= 240 and (yx[0] % 4 or yx[1] % 4):   # an interior, unaligned crop
+        monkeypatch.setattr(dev_loss, 'TAIL_CONTEXT', 1)
+        monkeypatch.setattr(dev_loss, 'TAIL_SIZE', 36)
+        bad = windowed()
+        assert float((bad - full).detach().abs().max()) > 1e-4

@@ -82,6 +82,32 @@ def crop_window(yx, res, lat, H, W):
     return oy, ox, wh, ww
 
 
+TAIL_CONTEXT = 2   # latent pixels of context the blocks ABOVE the latent resolution add: 2 convs at 2x + 2 at 4x = 1.5
+TAIL_SIZE = 40     # >= (crop footprint 33) + 2 * TAIL_CONTEXT, a multiple of 8 (whole MMA tile rows at 2x and 4x)
+
+
+def tail_window(yx, res, lat, win, H, W):
+    """Second level of the crop-aware evaluation: (oy, ox, h, w) in latent pixels RELATIVE to the trunk window `win`
+    (or to the canvas when win is None) that the up-sampling blocks of G_res need for the crop at pixel offset yx -
+    the crop's footprint plus TAIL_CONTEXT.  Same argument as `crop_window`: an edge of this window that is not an
+    edge of the canvas lies >= TAIL_CONTEXT latent pixels from the footprint, and where it coincides with an interior
+    edge of the trunk window the footprint is >= G_CONTEXT away from it by construction.  None = keep everything."""
+    up = res // lat
+    if up != 4:
+        return None
+    oy0, ox0, wh, ww = (0, 0, H, W) if win is None else win
+    if wh <= TAIL_SIZE and ww <= TAIL_SIZE:
+        return None
+
+    def axis(c0, o0, L):
+        if L <= TAIL_SIZE:
+            return 0, L
+        return min(max(c0 // up - o0 - TAIL_CONTEXT, 0), L - TAIL_SIZE), TAIL_SIZE
+    oy, h = axis(yx[0], oy0, wh)
+    ox, w = axis(yx[1], ox0, ww)
+    return oy, ox, h, w
+
+
 def _win(x, win):
     if win is None:
         return x
@@ -116,6 +142,14 @@ def fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, ih_f, iw_f, win, blend=None):
     bzg = rt.latent_blend([zg_r, zg_c], wh, ww, _lib.BLEND_LERP, t=t)      # lerp(reverse, forward, t), loss.py:238
     bzl = rt.latent_blend([zl_r, zl_c], wh, ww, _lib.BLEND_LERP, t=t)
     return bzg, bzl
+
+
+def image_offset(yx, up, win, tail):
+    """Pixel offset of the crop at canvas offset yx inside the image decoded from trunk window `win` and tail
+    window `tail` (either may be None)."""
+    oy = (0 if win is None else win[0]) + (0 if tail is None else tail[0])
+    ox = (0 if win is None else win[1]) + (0 if tail is None else tail[1])
+    return yx[0] - up * oy, yx[1] - up * ox
 
 
 def fcn_scale(canvas, lat):
@@ -159,6 +193,8 @@ class EGForward:
         self.win = {'interp': None if crop_interp is None else crop_window(crop_interp, res, lat, H, W),
                     'blend': None if crop_blend is None else crop_window(crop_blend, res, lat, H, W)}
         self.planned = {'interp': crop_interp, 'blend': crop_blend}
+        self.tail = {k: None if c is None else tail_window(c, res, lat, self.win[k], H, W)
+                     for k, c in (('interp', crop_interp), ('blend', crop_blend))}
         self._need = (need_interp, need_blend)
         if need_interp or need_blend:
             self.ih_f, self.iw_f = _dev_idx(rt, idx['h_forward']), _dev_idx(rt, idx['w_forward'])
@@ -177,22 +213,23 @@ class EGForward:
         need_interp, need_blend = self._need
         if need_interp and self.interp is None:
             zg_c, zl_c = fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, self.ih_f, self.iw_f, self.win['interp'])
-            self.interp = G_fcn.get_output_for(zg_c, zl_c, tape=self.t_int, **fcn_scale(zl_c, lat))
+            self.interp = G_fcn.get_output_for(zg_c, zl_c, tape=self.t_int, tail_window=self.tail['interp'],
+                                               **fcn_scale(zl_c, lat))
         if need_blend and self.blend is None:
             bzg, bzl = fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, self.ih_f, self.iw_f, self.win['blend'],
                                     blend=(self.ih_b, self.iw_b, self.t))
-            self.blend = G_fcn.get_output_for(bzg, bzl, tape=self.t_bl, **fcn_scale(bzl, lat))
+            self.blend = G_fcn.get_output_for(bzg, bzl, tape=self.t_bl, tail_window=self.tail['blend'],
+                                              **fcn_scale(bzl, lat))
 
     def window_offset(self, which, yx):
         """Pixel offset of crop `yx` inside the decoded image of `which` (== yx when the whole canvas was decoded)."""
-        win = self.win[which]
-        if win is None:
+        win, tail = self.win[which], self.tail[which]
+        if win is None and tail is None:
             return yx
         if tuple(yx) != tuple(self.planned[which]):
             raise ValueError('%s was decoded for the crop at %r only (crop-aware G_fcn); asked for %r'
                              % (which, self.planned[which], yx))
-        up = self.reals.shape[2] // self.lat
-        return yx[0] - up * win[0], yx[1] - up * win[1]
+        return image_offset(yx, self.reals.shape[2] // self.lat, win, tail)
 
     def crop(self, which, yx):
         img = self.interp if which == 'interp' else self.blend

@@ -262,6 +262,19 @@ def _upscale_image(rt, img, factor):
                            idx_h=[ih.repeat(n, 1).contiguous()], idx_w=[iw.repeat(n, 1).contiguous()])
 
 
+def _window(t, win):
+    """[n, oy:oy+h, ox:ox+w, :] of a run-mode handle's feature map as a new activation (recorded on the tape)."""
+    ctx = t.ctx
+    oy, ox, h, w = win
+    a = ctx.rt.split_unpack(_act_of(t))
+    if oy < 0 or ox < 0 or oy + h > a.h or ox + w > a.w:
+        raise ValueError('tail_window %r outside the %dx%d feature map' % (win, a.h, a.w))
+    out = Act(a.n, h, w, a.c, f32=a.f32[:, oy:oy + h, ox:ox + w, :].contiguous())
+    if ctx.tape is not None:
+        ctx.tape.append(dict(kind='window', x=a, y=out, win=(oy, ox, h, w)))
+    return T([t.shape[0], t.shape[1], h, w], ctx, act=out)
+
+
 def _tanh(rt, x):
     import ctypes as C
     from . import _lib
@@ -466,7 +479,11 @@ def E_zl(images_in, num_channels=3, resolution=128, fmap_base=8192, fmap_decay=1
 def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_base=8192, fmap_decay=1.0,
           fmap_max=512, latent_res=4, latent_channels=512, use_wscale=True, use_pixelnorm=False,
           pixelnorm_epsilon=1e-8, use_leakyrelu=True, tanh_at_end=False, dtype='float32', fused_scale=False,
-          structure='recursive', is_template_graph=False, scale_h=1, scale_w=1, **kwargs):
+          structure='recursive', is_template_graph=False, scale_h=1, scale_w=1, tail_window=None, **kwargs):
+    """`tail_window` = (oy, ox, h, w) in latent pixels (not a reference argument): after the latent-resolution block
+    only that window of the feature map goes on through the up-sampling blocks and the image heads - the output is
+    the corresponding [4h, 4w] part of the image.  Used by the crop-aware train step (loss.tail_window): the layers
+    above the trunk see 2 latent pixels of context around the crop instead of the trunk's 14."""
     resolution_log2 = int(np.log2(resolution))
     latent_res_log2 = int(np.log2(latent_res))
     assert resolution == 2 ** resolution_log2 and latent_res == 2 ** latent_res_log2 and resolution >= latent_res
@@ -584,6 +601,8 @@ def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_bas
 
     def grow(x, res, lod):                                                 # networks.py:473-479
         y = block(x, res)
+        if res == latent_res_log2 and tail_window is not None and ctx.mode == 'run':
+            y = _window(y, tail_window)         # crop-aware evaluation: the blocks above only see what the crop needs
 
         def img_fn():
             return up_img(torgb(y, res, apply_tanh=tanh_at_end and lod == 0), 2 ** lod)
