@@ -297,8 +297,9 @@ TRAIN_BATCH = 32
 #                    (identical results, SURVEY Appendix C note): 8 units (the critics' interpolation fake no longer
 #                    shares the E/G image) x 116.2 x (64/96)^2 = 413.2, + 95.5                             = 508.7
 #                    ... and its up-sampling blocks + ToRGB only the 40x40 latent pixels around the crop
-#                    (loss.tail_window): per unit 12.457 x 4 + 0.4546 x (40/32)^2 = 50.54 -> 8 x 50.54 + 95.5 = 499.8
-TRAIN_GFLOP = {True: 499.8, False: 908.9}
+#                    (loss.tail_window), and the last 4 latent-resolution convs 48x48 (loss.mid_window): per unit
+#                    8 x 1.208 x 4 + 2.7935 x (48/32)^2 + 0.4546 x (40/32)^2 = 45.65 -> 8 x 45.65 + 95.5    = 460.7
+TRAIN_GFLOP = {True: 460.7, False: 908.9}
 
 
 def time_oracle_train_step(sample=2):
@@ -455,7 +456,8 @@ def run_train(args):
                        'batch_per_gpu': TRAIN_BATCH, 'global_batch': TRAIN_BATCH * world,
                        'l2': 'working set per step (>20 GB) far exceeds the 126 MB L2',
                        'parallelism': 'dp%d: one flat-bucket NCCL all-reduce per network per optimizer' % world,
-                       'g_fcn': 'crop-aware: decodes the 64x64 latent window of each random_crop, up-sampling blocks on 40x40 of it '
+                       'g_fcn': 'crop-aware: decodes the 64x64 latent window of each random_crop, the last 4 latent convs on 48x48, the '
+                                'up-sampling blocks on 40x40 of it '
                                 '(identical results)'
                        if cfg['crop_aware'] else 'whole 96x96 canvases decoded',
                        'gflop_per_sample': TRAIN_GFLOP_PER_SAMPLE},

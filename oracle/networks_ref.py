@@ -384,7 +384,7 @@ def E_zl(images_in, P, num_channels=3, resolution=128, fmap_base=1024, fmap_deca
 def G_res(zg_latents_in, zl_latents_in, P, num_channels=3, resolution=128, fmap_base=1024,
           fmap_decay=1.0, fmap_max=512, latent_res=32, latent_channels=128, tanh_at_end=True,
           scale_h=1, scale_w=1, taps=None, use_pixelnorm=False, pixelnorm_epsilon=1e-8, fused_scale=False,
-          tail_window=None, **_):
+          tail_window=None, mid_window=None, **_):
     """networks.py:388-486 -> images [N,num_channels,resolution*scale_h,resolution*scale_w]."""
     pn = pixelnorm_epsilon if use_pixelnorm else None
     rl2 = int(np.log2(resolution))
@@ -405,6 +405,9 @@ def G_res(zg_latents_in, zl_latents_in, P, num_channels=3, resolution=128, fmap_
                 x = x0 + x
                 if taps is not None:
                     taps[s + '/Residual%d:sum' % count] = x
+                if count == 3 and mid_window is not None:   # not in the reference: test hook (crop-aware windows)
+                    oy, ox, th, tw = mid_window
+                    x = x[:, :, oy:oy + th, ox:ox + tw]
             x = _layer(P, s + '/Conv0', x, gain=SQRT2 / 4, taps=taps, pn=pn)  # networks.py:440
             x = _layer(P, s + '/Conv1', x, taps=taps, pn=pn)
         else:

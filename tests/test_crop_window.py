@@ -8,7 +8,7 @@ import torch
 
 from oracle import networks_ref as R
 from texturemixer_b200 import loss as dev_loss
-from texturemixer_b200.loss import G_CONTEXT, crop_window, image_offset, tail_window
+from texturemixer_b200.loss import G_CONTEXT, compose_window, crop_window, image_offset, mid_window, tail_window
 
 CFG = dict(num_channels=3, resolution=128, fmap_base=64, fmap_max=8, latent_res=32, latent_channels=2,
            use_pixelnorm=False, tanh_at_end=True)
@@ -78,13 +78,15 @@ def test_tail_window_equals_full_decode(yx, monkeypatch):
 
     def windowed():
         win = crop_window(yx, RES, LAT, H, W)
-        tail = tail_window(yx, RES, LAT, win, H, W)
-        assert tail is not None and tail[2] == tail[3] == dev_loss.TAIL_SIZE
+        mid = mid_window(yx, RES, LAT, win, H, W)
+        win_abs = compose_window(win, mid, H, W)
+        tail = tail_window(yx, RES, LAT, win_abs, H, W)
+        assert mid[2] == mid[3] == dev_loss.MID_SIZE and tail[2] == tail[3] == dev_loss.TAIL_SIZE
         oy, ox, wh, ww = win
         img = R.G_res(zg[:, :, :wh, :ww], zl[:, :, oy:oy + wh, ox:ox + ww], P,
-                      **dict(CFG, scale_h=wh // LAT, scale_w=ww // LAT, tail_window=tail))
+                      **dict(CFG, scale_h=wh // LAT, scale_w=ww // LAT, mid_window=mid, tail_window=tail))
         assert tuple(img.shape[2:]) == (4 * tail[2], 4 * tail[3])
-        y0, x0 = image_offset(yx, 4, win, tail)
+        y0, x0 = image_offset(yx, 4, win_abs, tail)
         return img[:, :, y0:y0 + RES, x0:x0 + RES]
     part = windowed()
     assert part.shape == full.shape and float((part - full).detach().abs().max()) <= 1e-5
@@ -96,5 +98,11 @@ def test_tail_window_equals_full_decode(yx, monkeypatch):
     if 8 <= yx[0] <= 240 and 8 <= yx[1] <= 240 and (yx[0] % 4 or yx[1] % 4):   # an interior, unaligned crop
         monkeypatch.setattr(dev_loss, 'TAIL_CONTEXT', 1)
         monkeypatch.setattr(dev_loss, 'TAIL_SIZE', 36)
+        bad = windowed()
+        assert float((bad - full).detach().abs().max()) > 1e-4
+        monkeypatch.setattr(dev_loss, 'TAIL_CONTEXT', 2)
+        monkeypatch.setattr(dev_loss, 'TAIL_SIZE', 40)
+        monkeypatch.setattr(dev_loss, 'MID_CONTEXT', 4)          # the middle level alone with too little context
+        monkeypatch.setattr(dev_loss, 'MID_SIZE', 43)
         bad = windowed()
         assert float((bad - full).detach().abs().max()) > 1e-4

@@ -86,6 +86,37 @@ TAIL_CONTEXT = 2   # latent pixels of context the blocks ABOVE the latent resolu
 TAIL_SIZE = 40     # >= (crop footprint 33) + 2 * TAIL_CONTEXT, a multiple of 8 (whole MMA tile rows at 2x and 4x)
 
 
+MID_CONTEXT = 6    # after the 4th residual block: 2 residual convs + Conv0 + Conv1 at the latent resolution + the tail's 2
+MID_SIZE = 48      # >= 33 + 2 * MID_CONTEXT, a multiple of 16
+
+
+def mid_window(yx, res, lat, win, H, W):
+    """Intermediate level of the crop-aware evaluation, applied after G_res's fourth residual block (8 of the 12
+    latent-resolution convs done): (oy, ox, h, w) relative to the trunk window `win`.  None = keep everything."""
+    up = res // lat
+    if up != 4:
+        return None
+    oy0, ox0, wh, ww = (0, 0, H, W) if win is None else win
+    if wh <= MID_SIZE and ww <= MID_SIZE:
+        return None
+
+    def axis(c0, o0, L):
+        if L <= MID_SIZE:
+            return 0, L
+        return min(max(c0 // up - o0 - MID_CONTEXT - 1, 0), L - MID_SIZE), MID_SIZE
+    oy, h = axis(yx[0], oy0, wh)
+    ox, w = axis(yx[1], ox0, ww)
+    return oy, ox, h, w
+
+
+def compose_window(outer, inner, H, W):
+    """Absolute (oy, ox, h, w) of window `inner` given relative to `outer` (either may be None)."""
+    if inner is None:
+        return outer
+    oy0, ox0 = (0, 0) if outer is None else outer[:2]
+    return oy0 + inner[0], ox0 + inner[1], inner[2], inner[3]
+
+
 def tail_window(yx, res, lat, win, H, W):
     """Second level of the crop-aware evaluation: (oy, ox, h, w) in latent pixels RELATIVE to the trunk window `win`
     (or to the canvas when win is None) that the up-sampling blocks of G_res need for the crop at pixel offset yx -
@@ -193,7 +224,10 @@ class EGForward:
         self.win = {'interp': None if crop_interp is None else crop_window(crop_interp, res, lat, H, W),
                     'blend': None if crop_blend is None else crop_window(crop_blend, res, lat, H, W)}
         self.planned = {'interp': crop_interp, 'blend': crop_blend}
-        self.tail = {k: None if c is None else tail_window(c, res, lat, self.win[k], H, W)
+        self.mid = {k: None if c is None else mid_window(c, res, lat, self.win[k], H, W)
+                    for k, c in (('interp', crop_interp), ('blend', crop_blend))}
+        self.tail = {k: None if c is None else
+                     tail_window(c, res, lat, compose_window(self.win[k], self.mid[k], H, W), H, W)
                      for k, c in (('interp', crop_interp), ('blend', crop_blend))}
         self._need = (need_interp, need_blend)
         if need_interp or need_blend:
@@ -213,17 +247,17 @@ class EGForward:
         need_interp, need_blend = self._need
         if need_interp and self.interp is None:
             zg_c, zl_c = fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, self.ih_f, self.iw_f, self.win['interp'])
-            self.interp = G_fcn.get_output_for(zg_c, zl_c, tape=self.t_int, tail_window=self.tail['interp'],
-                                               **fcn_scale(zl_c, lat))
+            self.interp = G_fcn.get_output_for(zg_c, zl_c, tape=self.t_int, mid_window=self.mid['interp'],
+                                               tail_window=self.tail['interp'], **fcn_scale(zl_c, lat))
         if need_blend and self.blend is None:
             bzg, bzl = fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, self.ih_f, self.iw_f, self.win['blend'],
                                     blend=(self.ih_b, self.iw_b, self.t))
-            self.blend = G_fcn.get_output_for(bzg, bzl, tape=self.t_bl, tail_window=self.tail['blend'],
-                                              **fcn_scale(bzl, lat))
+            self.blend = G_fcn.get_output_for(bzg, bzl, tape=self.t_bl, mid_window=self.mid['blend'],
+                                              tail_window=self.tail['blend'], **fcn_scale(bzl, lat))
 
     def window_offset(self, which, yx):
         """Pixel offset of crop `yx` inside the decoded image of `which` (== yx when the whole canvas was decoded)."""
-        win, tail = self.win[which], self.tail[which]
+        win, tail = compose_window(self.win[which], self.mid[which], self.H, self.W), self.tail[which]
         if win is None and tail is None:
             return yx
         if tuple(yx) != tuple(self.planned[which]):

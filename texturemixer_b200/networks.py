@@ -479,11 +479,13 @@ def E_zl(images_in, num_channels=3, resolution=128, fmap_base=8192, fmap_decay=1
 def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_base=8192, fmap_decay=1.0,
           fmap_max=512, latent_res=4, latent_channels=512, use_wscale=True, use_pixelnorm=False,
           pixelnorm_epsilon=1e-8, use_leakyrelu=True, tanh_at_end=False, dtype='float32', fused_scale=False,
-          structure='recursive', is_template_graph=False, scale_h=1, scale_w=1, tail_window=None, **kwargs):
+          structure='recursive', is_template_graph=False, scale_h=1, scale_w=1, tail_window=None, mid_window=None,
+          **kwargs):
     """`tail_window` = (oy, ox, h, w) in latent pixels (not a reference argument): after the latent-resolution block
     only that window of the feature map goes on through the up-sampling blocks and the image heads - the output is
     the corresponding [4h, 4w] part of the image.  Used by the crop-aware train step (loss.tail_window): the layers
-    above the trunk see 2 latent pixels of context around the crop instead of the trunk's 14."""
+    above the trunk see 2 latent pixels of context around the crop instead of the trunk's 14.  `mid_window` does
+    the same after the fourth residual block (loss.mid_window; `tail_window` is then relative to it)."""
     resolution_log2 = int(np.log2(resolution))
     latent_res_log2 = int(np.log2(latent_res))
     assert resolution == 2 ** resolution_log2 and latent_res == 2 ** latent_res_log2 and resolution >= latent_res
@@ -531,6 +533,8 @@ def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_bas
                         # the sum is also the next block's x0: keep the exact fp32 copy beside the planes
                         x = conv2d_layer(x, c2, 3, gain=1, act=False, residual=x0, next_tc=_tc(ctx, c2, nxt, 3),
                                          keep_f32=count < 4)
+                    if count == 3 and mid_window is not None and ctx.mode == 'run':
+                        x = _window(x, mid_window)      # crop-aware: 4 + 2 convs of context left -> a smaller window
                 with ctx.variable_scope('Conv0'):
                     x = conv2d_layer(x, nf(res - 1), 3, gain=SQRT2 / 4, next_tc=_tc(ctx, nf(res - 1), nf(res - 1), 3))
                 with ctx.variable_scope('Conv1'):

@@ -266,10 +266,15 @@ class Trainer:
         win = loss.crop_window(yx, res, fwd.lat, fwd.H, fwd.W) if c.get('crop_aware', True) else None
         blend = None if which == 'interp' else (fwd.ih_b, fwd.iw_b, mix.reshape(-1).contiguous())
         zg_c, zl_c = loss.fcn_canvases(rt, fwd.zg_mu, fwd.zl_mu, fwd.H, fwd.W, fwd.pins, fwd.ih_f, fwd.iw_f, win, blend)
-        tail = loss.tail_window(yx, res, fwd.lat, win, fwd.H, fwd.W) if c.get('crop_aware', True) and \
-            self.nets['G'].lod <= 2.0 else None
-        y0, x0 = loss.image_offset(yx, res // fwd.lat, win, tail)
-        img = self.G_fcn.get_output_for(zg_c, zl_c, tail_window=tail, **loss.fcn_scale(zl_c, fwd.lat))
+        mid = tail = None
+        if c.get('crop_aware', True) and self.nets['G'].lod <= 2.0:
+            mid = loss.mid_window(yx, res, fwd.lat, win, fwd.H, fwd.W)
+            win_abs = loss.compose_window(win, mid, fwd.H, fwd.W)
+            tail = loss.tail_window(yx, res, fwd.lat, win_abs, fwd.H, fwd.W)
+        else:
+            win_abs = win
+        y0, x0 = loss.image_offset(yx, res // fwd.lat, win_abs, tail)
+        img = self.G_fcn.get_output_for(zg_c, zl_c, mid_window=mid, tail_window=tail, **loss.fcn_scale(zl_c, fwd.lat))
         return img[:, :, y0:y0 + res, x0:x0 + res].contiguous()
 
     def _critic(self, name, n):
@@ -335,7 +340,7 @@ class Trainer:
                              crop_interp=draws['eg_crop_interp'] if ca else None,
                              crop_blend=draws['eg_crop_blend'] if ca else None, defer_canvases=True)
         graphs = c.get('cuda_graphs', True) and not os.environ.get('TMX_NO_GRAPH') and lod_now == int(lod_now)
-        shared = fwd.win['interp'] is None and fwd.tail['interp'] is None     # whole canvas decoded: one image, both phases
+        shared = fwd.win['interp'] is None and fwd.tail['interp'] is None and fwd.mid['interp'] is None   # whole canvas
         overlap = graphs and 'D' in phases and not shared
         if not overlap:
             fwd.decode_canvases()
