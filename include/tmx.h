@@ -327,6 +327,9 @@ int tmx_bias_act(tmx_handle_t h, const float* x, const float* bias, float* y, in
                  float alpha, tmx_stream_t s);
 /* pixel_norm (networks.py:170-172) on NHWC fp32 [npix][C]: y = x * rsqrt(mean_c x^2 + eps). */
 int tmx_pixel_norm(tmx_handle_t h, const float* x, float* y, int64_t npix, int C, float eps, tmx_stream_t s);
+/* its adjoint: dx = r * dy - r^3 / C * x * sum_c(dy * x), r = rsqrt(mean_c x^2 + eps). */
+int tmx_pixel_norm_bwd(tmx_handle_t h, const float* x, const float* dy, float* dx, int64_t npix, int C, float eps,
+                       tmx_stream_t s);
 
 /* out = a + b over n fp32 elements (two gradient contributions meeting at one tensor). */
 int tmx_add_f32(tmx_handle_t h, const float* a, const float* b, float* out, int64_t n, tmx_stream_t s);

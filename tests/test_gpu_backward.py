@@ -370,3 +370,40 @@ def test_discriminator_gradients_at_lod(lod, monkeypatch):
     torch.cuda.synchronize()
     assert _rel_l2(dimg.cpu().numpy(), xt.grad.numpy()) <= 1e-3
     print('worst variable gradient (rel L2):', _check_param_grads(net, flat_grad, P, 1e-3, 1e-2))
+
+
+# ---------------------------------------------------------------- N4 variants on the tape
+@pytest.mark.parametrize('func,extra', [('G_res', dict(use_pixelnorm=True)), ('G_res', dict(fused_scale=True)),
+                                        ('E_zl', dict(fused_scale=True)), ('E_zg', dict(use_pixelnorm=True)),
+                                        ('E_zg', dict(fused_scale=True)), ('G_res', dict(fused_scale=True, use_pixelnorm=True))])
+def test_variant_backward_vs_autograd(func, extra, monkeypatch):
+    """use_pixelnorm (pixel_norm adjoint) and fused_scale (conv2d_transpose / strided conv as zero-padded convs with
+    their own weight-gradient mapping) in training: every variable gradient vs the oracle's autograd (alpha = 1)."""
+    from texturemixer_b200.backward import backward
+    _set_alpha(monkeypatch, 1.0)
+    rng = np.random.RandomState(31)
+    cfg0 = dict(R.CONFIG[func], **extra)
+    params = R.init_params(func, rng, **cfg0)
+    net, cfg = _net(func, params, **extra)
+    n = 2
+    P = R.to_torch(params, requires_grad=True)
+    if func == 'G_res':
+        ins = [rng.randn(n, 128, 32, 32).astype(np.float32), rng.randn(n, 128, 32, 32).astype(np.float32)]
+    else:
+        ins = [rng.uniform(-1, 1, (n, 3, 128, 128)).astype(np.float32)]
+    tin = [torch.from_numpy(a).requires_grad_(func == 'G_res') for a in ins]
+    outs = R.NETWORKS[func](*tin, P, **cfg)
+    outs = outs if isinstance(outs, tuple) else (outs,)
+    seeds = [rng.randn(*o.shape).astype(np.float32) for o in outs]
+    sum((o * torch.from_numpy(sd)).sum() for o, sd in zip(outs, seeds)).backward()
+    tape = []
+    got = net.get_output_for(*[torch.from_numpy(a).cuda() for a in ins], tape=tape, return_as_list=True)
+    for g, o in zip(got, outs):
+        assert _nmax(g.cpu().numpy(), o.detach().numpy()) <= 1e-2
+    flat_grad = torch.zeros_like(net.flat)
+    din = backward(net, tape, [torch.from_numpy(sd).cuda() for sd in seeds], flat_grad, want_input_grads=func == 'G_res')
+    torch.cuda.synchronize()
+    if func == 'G_res':
+        for d, t in zip(din, tin):
+            assert _rel_l2(d.cpu().numpy(), t.grad.numpy()) <= 1e-3
+    print('worst variable gradient (rel L2):', _check_param_grads(net, flat_grad, P, 1e-3, 1e-2))

@@ -101,6 +101,7 @@ _SIGNATURES = {
     'tmx_tanh_f32': (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     'tmx_tanh_bwd': (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
     'tmx_pixel_norm': (C.c_int, [_P, _P, _P, C.c_int64, _I, _F, _P]),
+    'tmx_pixel_norm_bwd': (C.c_int, [_P, _P, _P, _P, C.c_int64, _I, _F, _P]),
     'tmx_bias_act': (C.c_int, [_P, _P, _P, _P, C.c_int64, _I, _I, _F, _P]),
     'tmx_grad_prepare': (C.c_int, [_P, C.POINTER(GradDesc), C.POINTER(GradIO), _P]),
     'tmx_nonfinite_check': (C.c_int, [_P, _P, C.c_int64, _P, _P]),

@@ -181,6 +181,22 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
                 _, g = _combine(rt, rec['y'], contribs, want_planes=False, want_f32=True)
                 grads.add(rec['a'], ('f32', _scaled(rt, g, 1.0 - rec['t'])))
                 grads.add(rec['b'], ('f32', _scaled(rt, g, rec['t'])))
+        elif kind == 'pixelnorm':          # pixel_norm (networks.py:170-172)
+            contribs = grads.pop(rec['y'])
+            if contribs:
+                _, g = _combine(rt, rec['y'], contribs, want_planes=False, want_f32=True)
+                x = rec['x']
+                dx = rt.empty(x.n, x.h, x.w, x.c)
+                _lib.check(rt.lib.tmx_pixel_norm_bwd(rt.handle, _ptr(x.f32), _ptr(g), _ptr(dx), x.n * x.h * x.w, x.c,
+                                                     float(rec['eps']), rt.stream()), 'tmx_pixel_norm_bwd')
+                grads.add(x, ('f32', dx))
+        elif kind == 'bias_act':           # [lrelu](x + b) behind the fused conv2d_downscale2d (networks.py:142-148)
+            contribs = grads.pop(rec['y'])
+            if contribs:
+                y = rec['y']
+                _, g = _combine(rt, y, contribs, want_planes=False, want_f32=True, mask_y=y.f32 if rec['act'] else None,
+                                dbias=gview(rec['b']) if param_grads else None)
+                grads.add(rec['x'], ('f32', g))
         elif kind == 'window':             # G_res(tail_window=...): slice of a feature map -> zeros outside
             contribs = grads.pop(rec['y'])
             if contribs:
@@ -286,31 +302,44 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
             cin_g, cout, k, up2 = x.c, rec['cout'], rec['k'], rec['up2']
             has_res = rec['residual'] is not None
             mask = rt.split_unpack(y).f32 if rec['act'] else None
+            zero_pad = rec.get('halo') == 'zero'        # fused_scale layers: SAME (zero) padding, nothing to fold
             dz, dz_f32 = _combine(rt, y, contribs, want_planes=True, want_f32=has_res, mask_y=mask,
-                                  dbias=gview(rec['b']) if param_grads else None, phase_pack=up2)
+                                  dbias=gview(rec['b']) if (param_grads and rec['b'] is not None) else None,
+                                  phase_pack=up2)
             if has_res:
                 grads.add(rec['residual'], ('f32', dz_f32))         # y = conv(x) + residual (networks.py:437)
             if adjoints is not None:
                 adjoints[pos] = dz
             w = net.vars[rec['w']]
-            fwd = net.prepared_weights(w, rec['wscale'], k, rec['cin'], cout, up2_phase=up2, cin_pad=x.c)
+            fwd = rec.get('w_planes') or net.prepared_weights(w, rec['wscale'], k, rec['cin'], cout, up2_phase=up2,
+                                                              cin_pad=x.c)
             if up2:
                 # sub-pixel form: low-res geometry, 4*Cout phase channels
                 hs, ws_, ng = x.h, x.w, 4 * cout
                 if param_grads:
                     dwp = torch.zeros(9, cin_g, ng, dtype=torch.float32, device=rt.device)
                     rt.conv_wgrad((x.hi, x.lo), dz, x.n, hs, ws_, cin_g, ng, 3, rec['wscale'], dwp)
-                    _lib.check(rt.lib.tmx_conv_wgrad_unphase(rt.handle, _ptr(dwp), _ptr(gview(rec['w'])), cin_g, cout,
-                                                             rt.stream()), 'tmx_conv_wgrad_unphase')
+                    if rec.get('transposed_var'):
+                        # upscale2d_conv2d: the kernel above differentiates w_eq[u,v,ci,co] = var[2-u,2-v,co,ci]
+                        dw_eq = torch.zeros(3, 3, cin_g, cout, dtype=torch.float32, device=rt.device)
+                        _lib.check(rt.lib.tmx_conv_wgrad_unphase(rt.handle, _ptr(dwp), _ptr(dw_eq), cin_g, cout,
+                                                                 rt.stream()), 'tmx_conv_wgrad_unphase')
+                        dvar = dw_eq.flip(0, 1).permute(0, 1, 3, 2).contiguous()         # layout move only
+                        gv = gview(rec['w'])
+                        _lib.check(rt.lib.tmx_add_f32(rt.handle, _ptr(gv), _ptr(dvar), _ptr(gv), gv.numel(),
+                                                      rt.stream()), 'tmx_add_f32')
+                    else:
+                        _lib.check(rt.lib.tmx_conv_wgrad_unphase(rt.handle, _ptr(dwp), _ptr(gview(rec['w'])), cin_g,
+                                                                 cout, rt.stream()), 'tmx_conv_wgrad_unphase')
                 wt = net.cached(('wt', rec['w'], True), lambda: rt.transpose_weights(fwd, ng, 9, cin_g))
                 g = rt.conv_dgrad(dz, x.n, hs, ws_, cin_g, ng, 3, wt)
-                grads.add(x, ('grid', g, 1))
+                grads.add(x, ('grid', g, 2 if zero_pad else 1))
             else:
                 if param_grads:
                     conv_wgrad_into(rt, net, rec, (x.hi, x.lo), dz, gview(rec['w']))
                 wt = net.cached(('wt', rec['w'], False), lambda: rt.transpose_weights(fwd, cout, k * k, cin_g))
                 g = rt.conv_dgrad(dz, x.n, x.h, x.w, cin_g, cout, k, wt)
-                grads.add(x, ('grid', g, 0 if k == 3 else 2))
+                grads.add(x, ('grid', g, 0 if (k == 3 and not zero_pad) else 2))
         elif kind == 'fromrgb':
             y = rec['y']
             contribs = grads.pop(y)

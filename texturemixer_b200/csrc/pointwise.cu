@@ -796,6 +796,42 @@ __global__ void __launch_bounds__(256) pixel_norm_kernel(const float* __restrict
   }
 }
 
+// adjoint: r = rsqrt(mean_c x^2 + eps), dx_c = r * dy_c - r^3 / C * x_c * sum_c' dy_c' x_c'
+__global__ void __launch_bounds__(256) pixel_norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                             float* __restrict__ dx, long long npix, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long p = warp; p < npix; p += nwarp) {
+    const float* xp = x + p * C;
+    const float* gp = dy + p * C;
+    float sq = 0.f, dot = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float v = __ldg(xp + c);
+      sq = fmaf(v, v, sq);
+      dot = fmaf(v, __ldg(gp + c), dot);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    }
+    const float r = rsqrtf(sq / (float)C + eps);
+    const float k = r * r * r * dot / (float)C;
+    for (int c = lane; c < C; c += 32) dx[p * C + c] = r * __ldg(gp + c) - k * __ldg(xp + c);
+  }
+}
+
+extern "C" int tmx_pixel_norm_bwd(tmx_handle_t h, const float* x, const float* dy, float* dx, int64_t npix, int C,
+                                  float eps, tmx_stream_t s) {
+  TMX_REQUIRE(h && x && dy && dx && npix > 0 && C > 0, TMX_ERR_ARG, "tmx_pixel_norm_bwd: bad argument");
+  const long long blocks = (npix + 7) / 8;
+  const int grid = (int)(blocks < 148LL * 16 ? blocks : 148LL * 16);
+  pixel_norm_bwd_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, dy, dx, npix, C, eps);
+  TMX_LAUNCHED(h, "pixel_norm_bwd_kernel");
+  return TMX_OK;
+}
+
 extern "C" int tmx_pixel_norm(tmx_handle_t h, const float* x, float* y, int64_t npix, int C, float eps, tmx_stream_t s) {
   TMX_REQUIRE(h && x && y && npix > 0 && C > 0, TMX_ERR_ARG, "tmx_pixel_norm: bad argument");
   const long long blocks = (npix + 7) / 8;

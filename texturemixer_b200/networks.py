@@ -130,15 +130,13 @@ def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=Fals
 
 
 def _fused_conv_prologue(x, wshape, fmaps, out_hw_factor):
-    """Variables and template shape shared by the two fused_scale layers (inference only)."""
+    """Variables and template shape shared by the two fused_scale layers."""
     ctx = x.ctx
     w = ctx.get_variable('weight', wshape)
     b = ctx.get_variable('bias', (fmaps,), init='zeros')
     num, den = out_hw_factor
     shape = [x.shape[0], fmaps, None if x.shape[2] is None else x.shape[2] * num // den,
              None if x.shape[3] is None else x.shape[3] * num // den]
-    if ctx.mode == 'run' and ctx.tape is not None:
-        raise NotImplementedError('training with fused_scale=True is not implemented (SURVEY N4); inference is')
     return ctx, w, b, shape
 
 
@@ -157,6 +155,11 @@ def upscale2d_conv2d_layer(x, fmaps, gain=SQRT2):
     w_eq, planes = ctx.net.cached(('fused_up', w.name), lambda: _fused_up_weights(rt, w.value, ws, cin, fmaps))
     out = rt.conv2d(xa, w_eq, b.value, ws, 3, fmaps, lrelu=True, up2=True, want_f32=True, want_split=False, algo=2,
                     prepared=planes, halo_in='zero')
+    if ctx.tape is not None:
+        # the backward differentiates the equivalent sub-pixel conv: weight gradient w.r.t. w_eq, mapped back to
+        # the [k,k,fmaps,Cin] variable by the adjoint of the flip / channel swap; ZERO padding has no fold
+        ctx.tape.append(dict(kind='conv', x=xa, y=out, w=w.name, b=b.name, wscale=ws, k=3, cin=cin, cout=fmaps,
+                             act=True, up2=True, residual=None, halo='zero', w_planes=planes, transposed_var=True))
     t = T(shape, ctx, act=out)
     return _pixel_norm(ctx, t, ctx.pixelnorm) if ctx.pixelnorm is not None else t
 
@@ -180,7 +183,13 @@ def conv2d_downscale2d_layer(x, fmaps, gain=SQRT2, act=True):
     planes = ctx.net.prepared_weights(w, ws, 3, cin, fmaps, cin_pad=xa.c)
     lin = rt.conv2d(xa, w.value, None, ws, 3, fmaps, lrelu=False, want_f32=True, want_split=False, algo=2,
                     prepared=planes, halo_in='zero')
-    out = rt.bias_act(rt.avgpool2(lin), b.value, act)
+    pooled = rt.avgpool2(lin)
+    out = rt.bias_act(pooled, b.value, act)
+    if ctx.tape is not None:
+        ctx.tape.append(dict(kind='conv', x=xa, y=lin, w=w.name, b=None, wscale=ws, k=3, cin=cin, cout=fmaps,
+                             act=False, up2=False, residual=None, halo='zero'))
+        ctx.tape.append(dict(kind='pool', x=lin, y=pooled))
+        ctx.tape.append(dict(kind='bias_act', x=pooled, y=out, b=b.name, act=act))
     t = T(shape, ctx, act=out)
     return _pixel_norm(ctx, t, ctx.pixelnorm) if (ctx.pixelnorm is not None and act) else t
 
@@ -190,7 +199,7 @@ def _pixel_strip(ctx, a):
     rt = ctx.rt
     rt.split_unpack(a)
     m = a.n * a.h * a.w
-    m2 = (m + 1) // 2
+    m2 = max((m + 1) // 2, 2)          # at least 2x2 stored pixels (halo layout), also for batches of 1-2
     buf = torch.zeros(2 * m2, a.c, dtype=torch.float32, device=rt.device)
     buf[:m].copy_(a.f32.view(m, a.c))
     strip = Act(1, 2, m2, a.c, f32=buf.view(1, 2, m2, a.c))
@@ -288,14 +297,15 @@ def _pixel_norm(ctx, t, epsilon):
     """pixel_norm (networks.py:170-172) of a run-mode handle: x * rsqrt(mean_c x^2 + eps) on the NHWC fp32 map."""
     import ctypes as C
     from . import _lib
-    if ctx.tape is not None:
-        raise NotImplementedError('training with use_pixelnorm=True is not implemented (SURVEY N4); inference is')
     rt = ctx.rt
     a = rt.split_unpack(_act_of(t))
     out = rt.empty(a.n, a.h, a.w, a.c)
     _lib.check(rt.lib.tmx_pixel_norm(rt.handle, C.c_void_p(a.f32.data_ptr()), C.c_void_p(out.data_ptr()),
                                      a.n * a.h * a.w, a.c, float(epsilon), rt.stream()), 'tmx_pixel_norm')
-    return T(t.shape, ctx, act=Act(a.n, a.h, a.w, a.c, f32=out))
+    y = Act(a.n, a.h, a.w, a.c, f32=out)
+    if ctx.tape is not None:
+        ctx.tape.append(dict(kind='pixelnorm', x=a, y=y, eps=float(epsilon)))
+    return T(t.shape, ctx, act=y)
 
 
 def _fromrgb(x, fmaps, name):
