@@ -401,12 +401,19 @@ def tangent_forward(D, tape, v):
             xin, y = tang[id(rec['x'])], rec['y']
             wv = D.vars[rec['w']]
             prepared = D.prepared_weights(wv, rec['wscale'], rec['k'], rec['cin'], rec['cout'], cin_pad=xin.c)
+            if rec['up2']:
+                raise NotImplementedError('tangent of an upsampling conv (not part of D_patch)')
             out = rt.conv2d(xin, wv.value, None, rec['wscale'], rec['k'], rec['cout'], lrelu=False, want_f32=True,
-                            want_split=False, algo=_lib.ALGO_TC, prepared=prepared)
+                            want_split=False, algo=_lib.ALGO_TC, prepared=prepared,
+                            halo_in='zero' if rec.get('halo') == 'zero' else None)
             if rec['act']:
                 out.f32 = _mask(rt, out.f32, rt.split_unpack(y).f32, y.n, y.h, y.w, y.c)
-            tin[pos] = xin                      # carries the REFLECT planes the conv just packed
+            tin[pos] = xin                      # carries the padded planes (REFLECT / ZERO) the conv just packed
             tang[id(y)] = out
+        elif kind == 'bias_act':                # fused conv2d_downscale2d: the bias drops out, the mask stays
+            t, y = rt.split_unpack(tang[id(rec['x'])]), rec['y']
+            f = _mask(rt, t.f32, y.f32, y.n, y.h, y.w, y.c) if rec['act'] else t.f32
+            tang[id(y)] = Act(y.n, y.h, y.w, y.c, f32=f)
         elif kind == 'pool':
             tang[id(rec['y'])] = rt.avgpool2(tang[id(rec['x'])])
         elif kind == 'mbstd':
