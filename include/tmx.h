@@ -331,6 +331,12 @@ int tmx_pixel_norm(tmx_handle_t h, const float* x, float* y, int64_t npix, int C
 int tmx_pixel_norm_bwd(tmx_handle_t h, const float* x, const float* dy, float* dx, int64_t npix, int C, float eps,
                        tmx_stream_t s);
 
+/* KL regulariser of EG_wgan (loss.py:163-171) on one encoder's (mu, log_sigma) pair, n elements in all:
+ * val = 1 + 2 ls - mu^2 - exp(2 ls) (reduce with tmx_row_sum, scale -0.5 * kl_weight / n), and the gradient of the
+ * batch mean, dmu = gscale * mu, dls = gscale * (exp(2 ls) - 1) with gscale = kl_weight / n. */
+int tmx_kl_terms(tmx_handle_t h, const float* mu, const float* log_sigma, float* dmu, float* dls, float* val, int64_t n,
+                 float gscale, tmx_stream_t s);
+
 /* out = a + b over n fp32 elements (two gradient contributions meeting at one tensor). */
 int tmx_add_f32(tmx_handle_t h, const float* a, const float* b, float* out, int64_t n, tmx_stream_t s);
 

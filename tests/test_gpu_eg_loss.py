@@ -19,8 +19,8 @@ def _rel_l2(got, want):
     return float(np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-30))
 
 
-@pytest.mark.parametrize('alpha,sh,sw', [(1.0, 2, 2), (0.2, 3, 3)])
-def test_eg_loss_and_gradients_vs_autograd(alpha, sh, sw, monkeypatch):
+@pytest.mark.parametrize('alpha,sh,sw,kl', [(1.0, 2, 2, 0.0), (0.2, 3, 3, 0.0), (1.0, 2, 2, 1.0)])
+def test_eg_loss_and_gradients_vs_autograd(alpha, sh, sw, kl, monkeypatch):
     from texturemixer_b200 import loss as dev_loss
     from texturemixer_b200 import runtime
     from texturemixer_b200.network import Network
@@ -48,7 +48,7 @@ def test_eg_loss_and_gradients_vs_autograd(alpha, sh, sw, monkeypatch):
     P = {k: R.to_torch(params[k], requires_grad=k in ('E_zg', 'E_zl', 'G')) for k in names}
     cfg = dict(R.CONFIG)
     loss, terms = L.EG_wgan(P, torch.from_numpy(reals), idx, crop_i, crop_b, torch.from_numpy(mix), scale_h=sh,
-                            scale_w=sw, cfg=cfg)
+                            scale_w=sw, cfg=cfg, kl_weight=kl)
     loss.mean().backward()
 
     # ---- device
@@ -61,10 +61,13 @@ def test_eg_loss_and_gradients_vs_autograd(alpha, sh, sw, monkeypatch):
     grads = {k: torch.zeros_like(nets[k].flat) for k in ('E_zg', 'E_zl', 'G')}
     rep = dev_loss.EG_wgan(nets['E_zg'], nets['E_zl'], nets['G'], nets['D_rec'], G_fcn, nets['D_interp'],
                            nets['D_blend'], torch.from_numpy(reals).cuda(), idx, crop_i, crop_b,
-                           torch.from_numpy(mix).cuda(), grads, scale_h=sh, scale_w=sw)
+                           torch.from_numpy(mix).cuda(), grads, scale_h=sh, scale_w=sw, kl_weight=kl)
     torch.cuda.synchronize()
     ltol = 2e-3 if alpha == 1.0 else 1e-2
-    for k, key in (('rec_G', 'rec_G'), ('rec_pixel', 'rec_pixel'), ('interp_G', 'interp_G'), ('blend_G', 'blend_G')):
+    keys = [('rec_G', 'rec_G'), ('rec_pixel', 'rec_pixel'), ('interp_G', 'interp_G'), ('blend_G', 'blend_G')]
+    if kl > 0:                                                   # KL regulariser on both encoders (loss.py:163-171)
+        keys += [('KL_zg', 'KL_zg'), ('KL_zl', 'KL_zl')]
+    for k, key in keys:
         want = float(terms[key].mean())
         got = float(rep[k].reshape(-1)[0])
         assert abs(got - want) <= ltol * max(1.0, abs(want)), (k, got, want)

@@ -96,6 +96,7 @@ _SIGNATURES = {
     'tmx_scale_rows': (C.c_int, [_P, _P, _P, _P, _I, C.c_int64, _P]),
     'tmx_gp_coefficients': (C.c_int, [_P, _P, _P, _P, _I, _F, _F, _P]),
     'tmx_add_f32': (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
+    'tmx_kl_terms': (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, _F, _P]),
     'tmx_convert_output': (C.c_int, [_P, _P, _P, C.c_int64, _I, _I, _F, _F, _I, _I, _P]),
     'tmx_weighted_sum': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'tmx_tanh_f32': (C.c_int, [_P, _P, _P, C.c_int64, _P]),

@@ -865,3 +865,29 @@ extern "C" int tmx_conv2d_dgrad(tmx_handle_t h, int N, int H, int W, int Cin, in
     TMX_REQUIRE(((uintptr_t)q & 15) == 0, TMX_ERR_ARG, "tmx_conv2d_dgrad: buffers must be 16-byte aligned (%p)", q);
   return tmx_conv2d_dgrad_tc(h, N, H, W, Cin, Cout, k, dz_hi, dz_lo, wt_hi, wt_lo, g_f32, (cudaStream_t)s);
 }
+
+// ---------------------------------------------------------------- KL regulariser of EG_wgan (loss.py:163-171)
+// KL = -0.5 * kl_weight * mean(1 + 2 ls - mu^2 - exp(2 ls)) per sample; with gscale = kl_weight / (elements per
+// sample * batch) the gradient of the batch mean is dmu = gscale * mu, dls = gscale * (exp(2 ls) - 1);
+// val = 1 + 2 ls - mu^2 - exp(2 ls) per element (the caller reduces it with tmx_row_sum).
+__global__ void __launch_bounds__(256) kl_terms_kernel(const float* __restrict__ mu, const float* __restrict__ ls,
+                                                       float* __restrict__ dmu, float* __restrict__ dls,
+                                                       float* __restrict__ val, long long n, float gscale) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float m = __ldg(mu + i), l = __ldg(ls + i);
+    const float e = expf(2.f * l);
+    val[i] = 1.f + 2.f * l - m * m - e;
+    dmu[i] = gscale * m;
+    dls[i] = gscale * (e - 1.f);
+  }
+}
+
+extern "C" int tmx_kl_terms(tmx_handle_t h, const float* mu, const float* log_sigma, float* dmu, float* dls, float* val,
+                            int64_t n, float gscale, tmx_stream_t s) {
+  TMX_REQUIRE(h && mu && log_sigma && dmu && dls && val && n > 0, TMX_ERR_ARG, "tmx_kl_terms: bad argument");
+  const int grid = (int)(n / 256 + 1 < 148LL * 16 ? n / 256 + 1 : 148LL * 16);
+  kl_terms_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(mu, log_sigma, dmu, dls, val, n, gscale);
+  TMX_LAUNCHED(h, "kl_terms_kernel");
+  return TMX_OK;
+}

@@ -1,6 +1,6 @@
 """E/G phase of the train step: `loss.EG_wgan` (loss.py:105-259) evaluated and
 differentiated on the device.  Reference config (config.py:50-68): zg 'hard', zl
-'permutational', kl_weight = 0; gram_weight is forced to 0 (VGG-19 weights are not
+'permutational'; the KL term (kl_weight, 0 in the reference config) is supported; gram_weight is forced to 0 (VGG-19 weights are not
 redistributable, SURVEY §2 - stated deviation).
 
 The forward builds exactly the reference graph (encoders once, G at scale 1, G_fcn
@@ -213,8 +213,8 @@ class EGForward:
         self.n = n = reals.shape[0]
         res = reals.shape[2]
         self.t_zg, self.t_zl, self.t_rec, self.t_int, self.t_bl = [], [], [], [], []
-        self.zg_mu, _ = E_zg.get_output_for(reals, tape=self.t_zg)
-        self.zl_mu, _ = E_zl.get_output_for(reals, tape=self.t_zl)
+        self.zg_mu, self.zg_ls = E_zg.get_output_for(reals, tape=self.t_zg)
+        self.zl_mu, self.zl_ls = E_zl.get_output_for(reals, tape=self.t_zl)
         zg_mu, zl_mu = self.zg_mu, self.zl_mu
         self.c, self.lat = c, lat = zl_mu.shape[1], zl_mu.shape[2]
         self.H, self.W = H, W = lat * scale_h, lat * scale_w
@@ -285,7 +285,7 @@ def critic_input_gradient(D, images, weight):
 
 
 def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, rec_G_weight=1.0, pixel_weight=200.0,
-                interp_G_weight=1.0, blend_interp_G_weight=1.0, reals_fade=None, critic_grads=None):
+                interp_G_weight=1.0, blend_interp_G_weight=1.0, reals_fade=None, critic_grads=None, kl_weight=0.0):
     """Loss terms of `EG_wgan` on the images of `fwd` and the whole reverse pass into `grads`.  `reals_fade`: the
     target of the pixel loss (loss.py:143) when it differs from what the encoders saw (fractional lod).
     `critic_grads`: optional {'rec' | 'interp' | 'blend': critic_input_gradient(...)} evaluated by the caller (the
@@ -340,14 +340,30 @@ def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, r
             else:
                 _gather_bwd(rt, _embed(d_fwd, win, H, W), dzl, fwd.ih_f, fwd.iw_f, pins)
                 _gather_bwd(rt, _embed(d_rev, win, H, W), dzl, fwd.ih_b, fwd.iw_b, pins, reverse=True)
-    backward(E_zl, fwd.t_zl, [dzl, None], grads['E_zl'], want_input_grads=False)
-    backward(E_zg, fwd.t_zg, [dzg.view(n, c, 1, 1), None], grads['E_zg'], want_input_grads=False)
+    dzl_ls = dzg_ls = None
+    dzg = dzg.view(n, c, 1, 1)
+    if kl_weight > 0:                                                     # loss.py:163-171
+        (report['KL_zg'], dzg, dzg_ls) = _kl(rt, fwd.zg_mu, fwd.zg_ls, dzg, kl_weight, 'KL_zg')
+        (report['KL_zl'], dzl, dzl_ls) = _kl(rt, fwd.zl_mu, fwd.zl_ls, dzl, kl_weight, 'KL_zl')
+    backward(E_zl, fwd.t_zl, [dzl, dzl_ls], grads['E_zl'], want_input_grads=False)
+    backward(E_zg, fwd.t_zg, [dzg, dzg_ls], grads['E_zg'], want_input_grads=False)
     return report
+
+
+def _kl(rt, mu, ls, dmu_in, kl_weight, name):
+    """KL term of one encoder: (batch mean of the term, dL/dmu incl. the incoming gradient, dL/dlog_sigma)."""
+    mu, ls = mu.contiguous(), ls.contiguous()
+    total = mu.numel()
+    dmu, dls, val = rt.empty(*mu.shape), rt.empty(*mu.shape), rt.empty(total)
+    _lib.check(rt.lib.tmx_kl_terms(rt.handle, _ptr(mu), _ptr(ls), _ptr(dmu), _ptr(dls), _ptr(val), total,
+                                   float(kl_weight) / total, rt.stream()), 'tmx_kl_terms')
+    term = _row_sum(rt, val, 1, total, scale=-0.5 * float(kl_weight) / total)
+    return term, _add(rt, dmu_in.contiguous().view(*mu.shape), dmu), dls
 
 
 def EG_wgan(E_zg, E_zl, G, D_rec, G_fcn, D_interp, D_blend, reals, idx, crop_interp, crop_blend, mixing_factors,
             grads, scale_h=3, scale_w=3, rec_G_weight=1.0, pixel_weight=200.0, interp_G_weight=1.0,
-            blend_interp_G_weight=1.0, crop_aware=True):
+            blend_interp_G_weight=1.0, crop_aware=True, kl_weight=0.0):
     """One evaluation + differentiation of mean(EG_loss) (loss.py:105-259, run.py:321).
     reals: [N,3,R,R] fp32 device tensor in [-1,1]; idx: dict of int32 index vectors (interp.sample_schedule_indices);
     crop_*: (y, x); mixing_factors: [N,1,1,1] fp32 device tensor; grads: {'E_zg','E_zl','G'} -> flat gradient
@@ -356,7 +372,7 @@ def EG_wgan(E_zg, E_zl, G, D_rec, G_fcn, D_interp, D_blend, reals, idx, crop_int
                     need_interp=interp_G_weight > 0, need_blend=blend_interp_G_weight > 0,
                     crop_interp=crop_interp if crop_aware else None, crop_blend=crop_blend if crop_aware else None)
     return EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, rec_G_weight, pixel_weight,
-                       interp_G_weight, blend_interp_G_weight)
+                       interp_G_weight, blend_interp_G_weight, kl_weight=kl_weight)
 
 
 def _add(rt, a, b):
