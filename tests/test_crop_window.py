@@ -106,3 +106,26 @@ def test_tail_window_equals_full_decode(yx, monkeypatch):
         monkeypatch.setattr(dev_loss, 'MID_SIZE', 43)
         bad = windowed()
         assert float((bad - full).detach().abs().max()) > 1e-4
+
+
+def test_nested_window_geometry_all_offsets():
+    """Every crop offset of the 3x3 canvas: the three nested windows contain what their remaining layers need, and
+    an edge that is not an edge of the canvas keeps the required context (G_CONTEXT / MID_CONTEXT / TAIL_CONTEXT)."""
+    H = W = LAT * S
+    for y in range(0, RES * S - RES):
+        win = crop_window((y, 77), RES, LAT, H, W)
+        mid = mid_window((y, 77), RES, LAT, win, H, W)
+        win_abs = compose_window(win, mid, H, W)
+        tail = tail_window((y, 77), RES, LAT, win_abs, H, W)
+        k0, k1 = y // 4, (y + RES - 1) // 4                         # latent rows of the crop's footprint
+        lo = {}
+        for name, (o, size), ctx in (('trunk', (win[0], win[2]), G_CONTEXT),
+                                     ('mid', (win_abs[0], win_abs[2]), dev_loss.MID_CONTEXT),
+                                     ('tail', (win_abs[0] + tail[0], tail[2]), dev_loss.TAIL_CONTEXT)):
+            assert 0 <= o and o + size <= H, (name, y)
+            assert o == 0 or k0 - o >= ctx, (name, y, o)
+            assert o + size == H or (o + size - 1) - k1 >= ctx, (name, y, o, size)
+            lo[name] = (o, o + size)
+        assert lo['trunk'][0] <= lo['mid'][0] <= lo['tail'][0] and lo['tail'][1] <= lo['mid'][1] <= lo['trunk'][1]
+        y_img, _ = image_offset((y, 77), 4, win_abs, tail)
+        assert 0 <= y_img and y_img + RES <= 4 * tail[2]            # the crop lies inside the decoded image
