@@ -77,6 +77,10 @@ struct ConvTcParams {
   // including the ring the reflect/replicate adjoint folds back - is produced.  Output: fp32 rows only.
   int lin, lin_pitch;
   long long lin_rows;
+  // PATCH mode (X-MERGED 3-tap layers, opt-in with TMX_XMERGE_PATCH=1; NOT yet validated on a GPU): one stage = one
+  // tile; the A operand of all three vertical taps is ONE haloed patch [(bh+2) rows][bw px][128 B] per plane, tap u
+  // reads it from row offset u*bw (a whole number of 8-row swizzle atoms), the three weight boxes follow it.
+  int patch, patch_bytes, patch_stage_bytes, patch_stages;
   float alpha;
   const float* bias;
   const float* residual;
@@ -209,6 +213,24 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int brows = kBRowsFull / parts;
         const int brow = cblk * BN + part * (BN / parts) + rank * brows;
         const uint32_t bytes = 2 * Cfg::kABytes + 2 * brows * KC * 2;
+        if (!PAIR && p.patch) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = stage_base + (size_t)stage * p.patch_stage_bytes;
+          uint8_t* sb = sa + 2 * p.patch_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], 2 * p.patch_bytes + 6 * brows * KC * 2);
+          tma_load_4d(sa, &tm_a_hi, &full_bar[stage], 0, x0, y0, n0);            // halo rows y0 .. y0 + bh + 1
+          tma_load_4d(sa + p.patch_bytes, &tm_a_lo, &full_bar[stage], 0, x0, y0, n0);
+#pragma unroll
+          for (int u = 0; u < 3; ++u) {
+            tma_load_2d(sb + u * brows * KC * 2, mb_hi, &full_bar[stage], u * p.Cin, brow);
+            tma_load_2d(sb + (3 + u) * brows * KC * 2, mb_lo, &full_bar[stage], u * p.Cin, brow);
+          }
+          if (++stage == p.patch_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
+        }
         for (int ks = 0; ks < ksteps; ++ks) {
           const int tap = ks / cchunks;
           const int c0 = (ks - tap * cchunks) * KC;
@@ -261,6 +283,35 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        if (!PAIR && p.patch) {
+          const int brows_i = item < p.full_items ? BN : BN / p.split;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + (size_t)stage * p.patch_stage_bytes);
+          const uint32_t sb = sa + 2 * p.patch_bytes;
+#pragma unroll
+          for (int u = 0; u < 3; ++u) {
+            const uint32_t aoff = (uint32_t)(u * p.bw * KC * 2);           // u patch rows down: whole swizzle atoms
+            const uint64_t a_hi = make_smem_desc<KC>(sa + aoff);
+            const uint64_t a_lo = make_smem_desc<KC>(sa + p.patch_bytes + aoff);
+            const uint64_t b_hi = make_smem_desc<KC>(sb + u * brows_i * KC * 2);
+            const uint64_t b_lo = make_smem_desc<KC>(sb + (3 + u) * brows_i * KC * 2);
+#pragma unroll
+            for (int kk = 0; kk < KC / 16; ++kk) {
+              const uint64_t adv = (uint64_t)(kk * 2);
+              umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, (u | kk) != 0);
+              umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
+              umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, 1);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.patch_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          umma_commit(&tfull_bar[as]);
+          continue;
+        }
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -733,8 +784,27 @@ int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_i
   CUtensorMap maps[6];
   int rc;
   const int xw = xmerge ? 4 : 1;
-  if ((rc = encode_act_map(h, &maps[0], io->x_hi, d->N, Hs + 2, Ws + 2, d->Cin, kc, p.bw, p.bh, p.bn, xw))) return rc;
-  if ((rc = encode_act_map(h, &maps[1], io->x_lo, d->N, Hs + 2, Ws + 2, d->Cin, kc, p.bw, p.bh, p.bn, xw))) return rc;
+  // PATCH mode (experimental, off unless TMX_XMERGE_PATCH=1): see ConvTcParams::patch
+  p.patch = p.patch_bytes = p.patch_stage_bytes = p.patch_stages = 0;
+  int box_h = p.bh;
+  if (xmerge && tmx_env_flag("TMX_XMERGE_PATCH") && p.bn == 1 && p.bw % 8 == 0 && bnc <= 64) {
+    const int k_a = kTileM * 64 * 2, k_b = bnc * 64 * 2;                  // TcCfg<bnc, 64>: bytes per plane
+    const int stage = 2 * k_a + 2 * k_b;
+    int stages = (200 * 1024) / stage;
+    if (stages > 12) stages = 12;
+    const int patch_bytes = (p.bh + 2) * p.bw * 64 * 2;
+    const int patch_stage = 2 * patch_bytes + 6 * k_b;
+    const int patch_stages = (stages * stage) / patch_stage;
+    if (patch_stages >= 2) {
+      p.patch = 1;
+      p.patch_bytes = patch_bytes;
+      p.patch_stage_bytes = patch_stage;
+      p.patch_stages = patch_stages > 12 ? 12 : patch_stages;
+      box_h = p.bh + 2;
+    }
+  }
+  if ((rc = encode_act_map(h, &maps[0], io->x_hi, d->N, Hs + 2, Ws + 2, d->Cin, kc, p.bw, box_h, p.bn, xw))) return rc;
+  if ((rc = encode_act_map(h, &maps[1], io->x_lo, d->N, Hs + 2, Ws + 2, d->Cin, kc, p.bw, box_h, p.bn, xw))) return rc;
   return schedule_and_launch(h, p, maps, io->w_hi, io->w_lo, tiles_m, Ng, p.Cin, bnc, kc, gw, st);
 }
 
