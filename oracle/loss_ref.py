@@ -92,3 +92,53 @@ def D_wgangp(P_D, fakes, reals, mixing_factors, wgan_lambda=10.0, wgan_epsilon=0
     terms['epsilon_penalty'] = (s_r * s_r).mean(dim=(1, 2, 3)) * wgan_epsilon              # loss.py:342
     loss = terms['D_loss'] + terms['gradient_penalty'] + terms['epsilon_penalty']
     return loss, terms
+
+
+# ---------------------------------------------------------------------- the three critic losses, fakes included
+def _fakes(P, reals, cfg):
+    """Encoders + reconstruction shared by the three critic losses (loss.py:308-320, 360-369, 435-444)."""
+    zg_mu, _ = R.E_zg(reals, P['E_zg'], **cfg['E_zg'])
+    zl_mu, _ = R.E_zl(reals, P['E_zl'], **cfg['E_zl'])
+    return zg_mu, zl_mu
+
+
+def D_rec_wgangp(P, reals, mixing_factors, cfg=None, **kw):
+    """loss.py:303-346.  P: parameter dicts of 'E_zg','E_zl','G','D_rec'.  The fakes are constants for the critic's
+    optimizer (run.py:322), so they are evaluated without autograd."""
+    cfg = cfg or R.CONFIG
+    with torch.no_grad():
+        zg_mu, zl_mu = _fakes(P, reals, cfg)
+        lat = zl_mu.shape[2]
+        rec = R.G_res(zg_mu.repeat(1, 1, lat, lat), zl_mu, P['G'], **cfg['G_res'])        # loss.py:320
+    return D_wgangp(P['D_rec'], rec, reals, mixing_factors, cfg=cfg, **kw)
+
+
+def D_interp_wgangp(P, reals, idx, crop_yx, mixing_factors, scale_h=3, scale_w=3, cfg=None, **kw):
+    """loss.py:351-421 ('hard' zg, 'permutational' zl)."""
+    cfg = cfg or R.CONFIG
+    with torch.no_grad():
+        zg_mu, zl_mu = _fakes(P, reals, cfg)
+        lat = zl_mu.shape[2]
+        zg_c = zg_mu.repeat(1, 1, lat * scale_h, lat * scale_w)                           # loss.py:373
+        zl_c = tiling_permutation(zl_mu, scale_h, scale_w, idx['h_forward'], idx['w_forward'])   # loss.py:391
+        img = R.G_res(zg_c, zl_c, P['G'], **dict(cfg['G_res'], scale_h=scale_h, scale_w=scale_w))  # loss.py:394
+        fake = crop(img, crop_yx, reals.shape[2:])                                        # loss.py:395
+    return D_wgangp(P['D_interp'], fake, reals, mixing_factors, cfg=cfg, **kw)
+
+
+def D_blend_wgangp(P, reals, idx, crop_yx, blend_mixing_factors, mixing_factors, scale_h=3, scale_w=3, cfg=None, **kw):
+    """loss.py:426-521: the blend draws its own mixing factors (loss.py:489), then the penalty's (loss.py:505)."""
+    cfg = cfg or R.CONFIG
+    with torch.no_grad():
+        zg_mu, zl_mu = _fakes(P, reals, cfg)
+        lat = zl_mu.shape[2]
+        zg_c = zg_mu.repeat(1, 1, lat * scale_h, lat * scale_w)
+        zl_c = tiling_permutation(zl_mu, scale_h, scale_w, idx['h_forward'], idx['w_forward'])
+        zg_r = torch.flip(zg_mu, dims=[0]).repeat(1, 1, lat * scale_h, lat * scale_w)      # loss.py:470
+        zl_r = tiling_permutation(torch.flip(zl_mu, dims=[0]), scale_h, scale_w, idx['h_backward'],
+                                  idx['w_backward'])                                       # loss.py:488
+        t = blend_mixing_factors
+        img = R.G_res(zg_r + (zg_c - zg_r) * t, zl_r + (zl_c - zl_r) * t, P['G'],
+                      **dict(cfg['G_res'], scale_h=scale_h, scale_w=scale_w))              # loss.py:490-494
+        fake = crop(img, crop_yx, reals.shape[2:])
+    return D_wgangp(P['D_blend'], fake, reals, mixing_factors, cfg=cfg, **kw)

@@ -54,3 +54,40 @@ def reference_networks():
     """-> (reference `networks` module, shim `tensorflow` module)."""
     net = _import_reference('networks')
     return net, sys.modules['tensorflow']
+
+
+def reference_loss():
+    """-> (reference `loss` module, reference `networks` module, shim `tensorflow` module).  loss.py imports
+    `tfutil` (shim: lerp + autosummary), `config` (the reference's own, pure Python) and `networks`."""
+    net = _import_reference('networks')
+    los = _import_reference('loss')
+    return los, net, sys.modules['tensorflow']
+
+
+class ReferenceNetwork:
+    """The slice of tfutil.Network that loss.py uses (tfutil.py:416-516): `get_output_for` re-runs the reference's
+    build function under the network's variable scope (variables are shared by name through the shim's store, like
+    tfutil.py:471-474 does for G_fcn over G), plus the static shape attributes."""
+
+    def __init__(self, net_module, tf, scope, func, input_shapes, output_shapes, **static_kwargs):
+        self.net_module, self.tf, self.scope, self.func = net_module, tf, scope, func
+        self.static_kwargs = dict(static_kwargs)
+        self.input_shapes, self.output_shapes = [list(s) for s in input_shapes], [list(s) for s in output_shapes]
+        self.input_shape, self.output_shape = self.input_shapes[0], self.output_shapes[0]
+
+    def get_output_for(self, *ins):
+        with self.tf.variable_scope(self.scope):
+            return getattr(self.net_module, self.func)(*ins, **self.static_kwargs)
+
+
+class ReferenceOptimizerStub:
+    """tfutil.Optimizer.apply_loss_scaling / undo_loss_scaling with use_loss_scaling=False (tfutil.py:378-391):
+    both return their argument."""
+
+    @staticmethod
+    def apply_loss_scaling(value):
+        return value
+
+    @staticmethod
+    def undo_loss_scaling(value):
+        return value

@@ -230,13 +230,15 @@ class _Store:
         self.values = dict(values or {})   # injected values by full name
         self.scope = []
         self.rng = rng or np.random.RandomState(0)
+        self.requires_grad = False         # goldens of loss gradients: trainable variables become autograd leaves
 
 
 STORE = _Store()
 
 
-def reset_default_graph(values=None, rng=None):
+def reset_default_graph(values=None, rng=None, requires_grad=False):
     STORE.reset(values, rng)
+    STORE.requires_grad = bool(requires_grad)
 
 
 @contextlib.contextmanager
@@ -299,6 +301,8 @@ def get_variable(name, shape=None, initializer=None, trainable=True, dtype=None)
     else:
         val = np.asarray(initializer, dtype=np.float32)
     t = torch.as_tensor(val).to(COMPUTE['float32']).clone()
+    if STORE.requires_grad and trainable:
+        t.requires_grad_(True)
     v = Variable(t, full, trainable)
     STORE.vars[full] = v
     return v

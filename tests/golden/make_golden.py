@@ -225,8 +225,119 @@ def gen_schedule():
     print('schedule.npz', {k: v.shape for k, v in out.items()})
 
 
+# ---------------------------------------------------------------- losses (loss.py executed unmodified)
+sys.path.insert(0, os.path.dirname(HERE))
+from loss_case import LOSS_N, LOSS_GRAD_STRIDE, LOSS_NETS, loss_case_inputs  # noqa: E402  (tests/loss_case.py)
+
+
+def gen_losses():
+    """loss.py:105-259 (EG_wgan) and :303-521 (D_rec/D_interp/D_blend_wgangp) executed UNMODIFIED on oracle/tfshim
+    with the reference's own config.py values (config.py:50-68, 89-92) except gram_weight = 0 (VGG weights are not
+    in the tree).  The networks are the reference's networks.py behind `refload.ReferenceNetwork`; the graph's random
+    ops (random_crop offsets, mixing factors) are pinned through the shim's RANDOM hooks and stored.
+    Stored: per-sample loss vectors, every autosummary'd term, and d mean(loss) / d variable (tfutil.py:299 over the
+    optimizer's own variables, run.py:321-324) - strided subsample + L2 norm per variable."""
+    from oracle import interp_ref as I
+    lossmod, net, tf = refload.reference_loss()
+    import config as refcfg                                             # the reference's config.py (pure Python)
+    import tfutil as shim_tfutil
+    assert refcfg.__file__.startswith(refload.REFERENCE_ROOT) and lossmod.__file__.startswith(refload.REFERENCE_ROOT)
+    n, sh, sw = LOSS_N, refcfg.scale_h, refcfg.scale_w
+    params, reals, idx, crops, mixes = loss_case_inputs(n, sh, sw)
+    values = {}
+    scope_of = dict(E_zg='E_zg', E_zl='E_zl', G='G', D_rec='D_rec', D_interp='D_interp', D_blend='D_blend')
+    for k in LOSS_NETS:
+        values.update({scope_of[k] + '/' + vn: v for vn, v in params[k].items()})
+    lat, res = refcfg.latent_res_EG, refcfg.train_size
+    C = refcfg.latent_channels
+
+    def kw(d):
+        d = dict(d)
+        d.pop('func')
+        return d
+    nets = dict(
+        E_zg=refload.ReferenceNetwork(net, tf, 'E_zg', 'E_zg', [[None, 3, res, res]], [[None, C, 1, 1]] * 2,
+                                      num_channels=3, resolution=res, **kw(refcfg.E_zg)),
+        E_zl=refload.ReferenceNetwork(net, tf, 'E_zl', 'E_zl', [[None, 3, res, res]], [[None, C, lat, lat]] * 2,
+                                      num_channels=3, resolution=res, **kw(refcfg.E_zl)),
+        G=refload.ReferenceNetwork(net, tf, 'G', 'G_res', [[None, C, lat, lat]] * 2, [[None, 3, res, res]],
+                                   num_channels=3, resolution=res, **kw(refcfg.G)),
+        G_fcn=refload.ReferenceNetwork(net, tf, 'G', 'G_res', [[None, C, lat * sh, lat * sw]] * 2,
+                                       [[None, 3, res * sh, res * sw]], num_channels=3, resolution=res, scale_h=sh,
+                                       scale_w=sw, **kw(refcfg.G)),                     # run.py:273
+    )
+    for k in ('D_rec', 'D_interp', 'D_blend'):
+        nets[k] = refload.ReferenceNetwork(net, tf, k, 'D_patch', [[None, 3, res, res]], [[None, 1, 1, 1]],
+                                           num_channels=3, resolution=res, **kw(getattr(refcfg, k)))
+    ph = np.stack([I.index_to_matrix_h(r) for r in idx['h_forward']])[:, None].astype(np.float32)
+    pw = np.stack([I.index_to_matrix_w(c) for c in idx['w_forward']])[:, None].astype(np.float32)
+    phb = np.stack([I.index_to_matrix_h(r) for r in idx['h_backward']])[:, None].astype(np.float32)
+    pwb = np.stack([I.index_to_matrix_w(c) for c in idx['w_backward']])[:, None].astype(np.float32)
+    opt = refload.ReferenceOptimizerStub()
+    eg_kw = kw(refcfg.EG_loss)
+    eg_kw['gram_weight'] = 0.0
+    out = {'meta_n_sh_sw_stride': np.array([n, sh, sw, LOSS_GRAD_STRIDE], np.int64)}
+    for k, v in crops.items():
+        out['draw_' + k] = np.array(v, np.int64)
+    for k, v in mixes.items():
+        out['draw_' + k] = v
+
+    def run(tag, fn, trainable_scopes, int_draws, float_draws):
+        tf.reset_default_graph(values=values, requires_grad=True)
+        terms = {}
+
+        def record(name, value):
+            terms[name] = value
+            return value
+        shim_tfutil.autosummary = record
+        ints, floats = list(int_draws), list(float_draws)
+        tf.RANDOM['uniform_int'] = lambda shp, lo, hi: np.full(shp, ints.pop(0), np.int64)
+        tf.RANDOM['uniform'] = lambda shp, lo, hi: floats.pop(0).reshape(shp)
+        x = tf.convert_to_tensor(reals)
+        loss = fn(x)
+        assert not ints and not floats, (tag, 'unused random draws', ints, floats)
+        tf.RANDOM['uniform_int'] = tf.RANDOM['uniform'] = None
+        loss.t.mean().backward()                                        # tf.reduce_mean(loss), run.py:321-324
+        out[tag + '_loss'] = loss.numpy().astype(np.float32)
+        for name, val in terms.items():
+            out[tag + '_term_' + name.replace('/', '_')] = val.numpy().astype(np.float32)
+        for full, var in tf.STORE.vars.items():
+            scope, vn = full.split('/', 1)
+            if scope not in trainable_scopes or not var.trainable:
+                continue
+            g = var.t.grad
+            g = np.zeros(tuple(var.t.shape), np.float32) if g is None else g.numpy()   # tfutil.py:298
+            flat = g.reshape(-1)
+            key = '%s_grad_%s_%s' % (tag, scope, vn.replace('/', '.'))
+            out[key] = (flat if flat.size <= 4096 else flat[::LOSS_GRAD_STRIDE]).astype(np.float32)
+            out[key + '_norm'] = np.array([np.linalg.norm(flat.astype(np.float64))])
+        print(tag, 'loss', out[tag + '_loss'], {k: float(np.mean(v.numpy())) for k, v in terms.items()})
+
+    ci, cb = crops['eg_crop_interp'], crops['eg_crop_blend']
+    run('EG', lambda x: lossmod.EG_wgan(
+        nets['E_zg'], nets['E_zl'], nets['G'], nets['D_rec'], nets['G_fcn'], nets['D_interp'], nets['D_blend'], n, x, x,
+        None, tf.convert_to_tensor(ph), tf.convert_to_tensor(pw), tf.convert_to_tensor(phb), tf.convert_to_tensor(pwb),
+        **eg_kw), ('E_zg', 'E_zl', 'G'), [ci[0], ci[1], cb[0], cb[1]], [mixes['eg_mix']])
+    run('D_rec', lambda x: lossmod.D_rec_wgangp(nets['E_zg'], nets['E_zl'], nets['G'], nets['D_rec'], opt, n, x, x,
+                                                **kw(refcfg.D_rec_loss)), ('D_rec',), [], [mixes['d_rec_gp']])
+    c = crops['d_interp_crop']
+    run('D_interp', lambda x: lossmod.D_interp_wgangp(
+        nets['E_zg'], nets['E_zl'], nets['G_fcn'], nets['D_interp'], opt, n, x, x, tf.convert_to_tensor(ph),
+        tf.convert_to_tensor(pw), **kw(refcfg.D_interp_loss)), ('D_interp',), [c[0], c[1]], [mixes['d_interp_gp']])
+    c = crops['d_blend_crop']
+    run('D_blend', lambda x: lossmod.D_blend_wgangp(
+        nets['E_zg'], nets['E_zl'], nets['G_fcn'], nets['D_blend'], opt, n, x, x, tf.convert_to_tensor(ph),
+        tf.convert_to_tensor(pw), tf.convert_to_tensor(phb), tf.convert_to_tensor(pwb), **kw(refcfg.D_blend_loss)),
+        ('D_blend',), [c[0], c[1]], [mixes['d_blend_mix'], mixes['d_blend_gp']])
+    np.savez_compressed(os.path.join(HERE, 'losses.npz'), **out)
+    print('losses.npz: %d arrays, %.1f MB' % (len(out), os.path.getsize(os.path.join(HERE, 'losses.npz')) / 1e6))
+
+
 if __name__ == '__main__':
     assert refload.reference_available(), 'needs /root/reference'
+    if 'losses' in sys.argv[1:]:
+        gen_losses()
+        sys.exit(0)
     if 'variants' in sys.argv[1:]:
         gen_network_variants()
         sys.exit(0)
@@ -246,3 +357,4 @@ if __name__ == '__main__':
     gen_schedule()
     gen_app_mattes()
     gen_network_fused()
+    gen_losses()

@@ -1,0 +1,40 @@
+"""Seeded inputs of the loss goldens (tests/golden/losses.npz): ONE recipe shared by the generator
+(tests/golden/make_golden.py gen_losses, which runs the reference's loss.py) and by the CPU / GPU tests that
+compare the oracle restatement and the device path against the fixture."""
+import os
+
+import numpy as np
+
+from oracle import interp_ref as I
+from oracle import networks_ref as R
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'losses.npz')
+LOSS_N = 4                 # per-tower minibatch: one full minibatch-stddev group, two reverse pairs for the blend
+LOSS_GRAD_STRIDE = 97      # subsample of every variable gradient kept in the fixture (whole variable if <= 4096)
+LOSS_NETS = ('E_zg', 'E_zl', 'G', 'D_rec', 'D_interp', 'D_blend')
+LOSS_FUNCS = dict(E_zg='E_zg', E_zl='E_zl', G='G_res', D_rec='D_patch', D_interp='D_patch', D_blend='D_patch')
+CROP_KEYS = ('eg_crop_interp', 'eg_crop_blend', 'd_interp_crop', 'd_blend_crop')
+MIX_KEYS = ('eg_mix', 'd_rec_gp', 'd_interp_gp', 'd_blend_mix', 'd_blend_gp')
+
+
+def loss_case_inputs(n=LOSS_N, scale_h=3, scale_w=3):
+    rng = np.random.RandomState(1000)                                   # config.py:75
+    params = {k: R.init_params(LOSS_FUNCS[k], rng, **R.CONFIG[LOSS_FUNCS[k]]) for k in LOSS_NETS}
+    reals = rng.uniform(-1, 1, (n, 3, 128, 128)).astype(np.float32)
+    np.random.seed(1000)
+    idx = I.sample_schedule_indices(n, latent_res=32, scale_h=scale_h, scale_w=scale_w)
+    hy, hx = 128 * scale_h - 128, 128 * scale_w - 128
+    crops = {k: (int(rng.randint(0, hy)), int(rng.randint(0, hx))) for k in CROP_KEYS}
+    mixes = {k: rng.uniform(0, 1, (n, 1, 1, 1)).astype(np.float32) for k in MIX_KEYS}
+    return params, reals, idx, crops, mixes
+
+
+def golden_gradient(g, tag, scope, name):
+    """(subsample or whole gradient, its L2 norm over the WHOLE variable) as stored by gen_losses."""
+    key = '%s_grad_%s_%s' % (tag, scope, name.replace('/', '.'))
+    return g[key], float(g[key + '_norm'][0])
+
+
+def subsample(flat):
+    flat = np.asarray(flat).reshape(-1)
+    return flat if flat.size <= 4096 else flat[::LOSS_GRAD_STRIDE]

@@ -16,6 +16,7 @@ activation travels in one of three forms:
                           (0 REFLECT, 1 REPLICATE [consumer read through upscale2d], 2 none)
     ('pool', t)           NHWC fp32 at half resolution (consumer was downscale2d)"""
 import ctypes as C
+import os
 
 import torch
 
@@ -39,8 +40,19 @@ class _Grads:
         return self.by_id.pop(id(act), [])
 
 
+def _mask_of(rt, y):
+    """What the leaky-ReLU mask of activation `y` is read from: the bf16 `hi` plane of its split form when the forward
+    kept one at the activation's own resolution (sign(hi) == sign(y): bf16 shares fp32's exponent range; half the
+    bytes, and the training forward need not write the fp32 map at all), else the fp32 map."""
+    if y.hi is not None and tuple(y.hi.shape) == (y.n, y.h + 2, y.w + 2, y.c) and not os.environ.get('TMX_MASK_F32'):
+        return dict(y_hi=y.hi)
+    return dict(y_f32=rt.split_unpack(y).f32)
+
+
 def _combine(rt, act, contribs, want_planes, want_f32, mask_y=None, dbias=None, phase_pack=False):
-    """All contributions to dL/d(act) -> (planes on the zero-ringed grid, fp32 NHWC), masked by lrelu'(mask_y)."""
+    """All contributions to dL/d(act) -> (planes on the zero-ringed grid, fp32 NHWC), masked by lrelu'(mask_y);
+    `mask_y` is an fp32 map or the dict returned by `_mask_of`."""
+    mask_kw = mask_y if isinstance(mask_y, dict) else dict(y_f32=mask_y)
     n, h, w, c = act.n, act.h, act.w, act.c
     main = [x for x in contribs if x[0] in ('grid', 'pool')]
     f32s = [x[1] for x in contribs if x[0] == 'f32']
@@ -62,8 +74,8 @@ def _combine(rt, act, contribs, want_planes, want_f32, mask_y=None, dbias=None, 
             raise NotImplementedError('more than two fp32 gradient contributions to one activation')
         src, kind, fold = f32s[0], 1, 2
         add = f32s[1] if len(f32s) == 2 else None
-    return rt.grad_prepare(src, n, h, w, c, kind, fold=fold, add=add, y_f32=mask_y, want_planes=want_planes,
-                           want_f32=want_f32, dbias=dbias, phase_pack=phase_pack)
+    return rt.grad_prepare(src, n, h, w, c, kind, fold=fold, add=add, want_planes=want_planes,
+                           want_f32=want_f32, dbias=dbias, phase_pack=phase_pack, **mask_kw)
 
 
 def _scaled(rt, x, a):
@@ -301,7 +313,7 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
                 continue
             cin_g, cout, k, up2 = x.c, rec['cout'], rec['k'], rec['up2']
             has_res = rec['residual'] is not None
-            mask = rt.split_unpack(y).f32 if rec['act'] else None
+            mask = _mask_of(rt, y) if rec['act'] else None
             zero_pad = rec.get('halo') == 'zero'        # fused_scale layers: SAME (zero) padding, nothing to fold
             dz, dz_f32 = _combine(rt, y, contribs, want_planes=True, want_f32=has_res, mask_y=mask,
                                   dbias=gview(rec['b']) if (param_grads and rec['b'] is not None) else None,

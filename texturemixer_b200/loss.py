@@ -54,6 +54,17 @@ def _dev_idx(rt, a):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(rt.device)
 
 
+# Test hook: when set to a list, every forward tape recorded by this module is appended as (label, network, tape) in
+# evaluation order - the parity tests read the leaky-ReLU branch masks of the device evaluation from it and hand them
+# to the oracle, so that both sides differentiate the SAME piecewise-linear function (tests/test_gpu_loss_golden.py).
+TAPE_SINK = None
+
+
+def _sink(label, net, tape):
+    if TAPE_SINK is not None:
+        TAPE_SINK.append((label, net, tape))
+
+
 G_CONTEXT = 14   # latent pixels of context one output pixel of G_res sees on each side: 12 convs at the latent
 #                  resolution (networks.py:427-446) + 2 at 2x + 2 at 4x (:447-457) = 12 + 1 + 0.5, rounded up
 
@@ -215,11 +226,14 @@ class EGForward:
         self.t_zg, self.t_zl, self.t_rec, self.t_int, self.t_bl = [], [], [], [], []
         self.zg_mu, self.zg_ls = E_zg.get_output_for(reals, tape=self.t_zg)
         self.zl_mu, self.zl_ls = E_zl.get_output_for(reals, tape=self.t_zl)
+        _sink('E_zg', E_zg, self.t_zg)
+        _sink('E_zl', E_zl, self.t_zl)
         zg_mu, zl_mu = self.zg_mu, self.zl_mu
         self.c, self.lat = c, lat = zl_mu.shape[1], zl_mu.shape[2]
         self.H, self.W = H, W = lat * scale_h, lat * scale_w
         self.pins = pins = interp._corner_pins(scale_h, scale_w)
         self.rec = G.get_output_for(_tile_code(rt, zg_mu, lat, lat), zl_mu, tape=self.t_rec)
+        _sink('G_rec', G, self.t_rec)
         self.interp = self.blend = None
         self.win = {'interp': None if crop_interp is None else crop_window(crop_interp, res, lat, H, W),
                     'blend': None if crop_blend is None else crop_window(crop_blend, res, lat, H, W)}
@@ -249,11 +263,13 @@ class EGForward:
             zg_c, zl_c = fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, self.ih_f, self.iw_f, self.win['interp'])
             self.interp = G_fcn.get_output_for(zg_c, zl_c, tape=self.t_int, mid_window=self.mid['interp'],
                                                tail_window=self.tail['interp'], **fcn_scale(zl_c, lat))
+            _sink('G_interp', G_fcn, self.t_int)
         if need_blend and self.blend is None:
             bzg, bzl = fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, self.ih_f, self.iw_f, self.win['blend'],
                                     blend=(self.ih_b, self.iw_b, self.t))
             self.blend = G_fcn.get_output_for(bzg, bzl, tape=self.t_bl, mid_window=self.mid['blend'],
                                               tail_window=self.tail['blend'], **fcn_scale(bzl, lat))
+            _sink('G_blend', G_fcn, self.t_bl)
 
     def window_offset(self, which, yx):
         """Pixel offset of crop `yx` inside the decoded image of `which` (== yx when the whole canvas was decoded)."""
@@ -272,6 +288,29 @@ class EGForward:
         return img[:, :, y0:y0 + res, x0:x0 + res].contiguous()
 
 
+def fcn_fake(G_fcn, fwd, which, yx, mix=None, crop_aware=True):
+    """Fake images of the canvas critics (no tape): the crop at `yx` of G_fcn's image of the interpolated (`which` =
+    'interp', loss.py:391-395) or blended ('blend', loss.py:466-495) canvas built from the codes of `fwd`, decoding
+    only the latent window the crop depends on (`crop_window`).  D_blend_wgangp draws its own mixing factors
+    (loss.py:489), D_interp_wgangp its own crop offset (loss.py:395): neither can reuse the E/G images once those
+    are decoded crop-aware."""
+    rt = fwd.rt
+    res = fwd.reals.shape[2]
+    win = crop_window(yx, res, fwd.lat, fwd.H, fwd.W) if crop_aware else None
+    blend = None if which == 'interp' else (fwd.ih_b, fwd.iw_b, mix.reshape(-1).contiguous())
+    zg_c, zl_c = fcn_canvases(rt, fwd.zg_mu, fwd.zl_mu, fwd.H, fwd.W, fwd.pins, fwd.ih_f, fwd.iw_f, win, blend)
+    mid = tail = None
+    if crop_aware and G_fcn.lod <= 2.0:
+        mid = mid_window(yx, res, fwd.lat, win, fwd.H, fwd.W)
+        win_abs = compose_window(win, mid, fwd.H, fwd.W)
+        tail = tail_window(yx, res, fwd.lat, win_abs, fwd.H, fwd.W)
+    else:
+        win_abs = win
+    y0, x0 = image_offset(yx, res // fwd.lat, win_abs, tail)
+    img = G_fcn.get_output_for(zg_c, zl_c, mid_window=mid, tail_window=tail, **fcn_scale(zl_c, fwd.lat))
+    return img[:, :, y0:y0 + res, x0:x0 + res].contiguous()
+
+
 def critic_input_gradient(D, images, weight):
     """One adversarial term of `EG_wgan` (loss.py:135-136, 194-199, 241-246): the critic as a FIXED function.
     -> (mean over the batch of -weight * D(images) [device scalar], its gradient w.r.t. images [N,3,R,R])."""
@@ -279,6 +318,7 @@ def critic_input_gradient(D, images, weight):
     n = images.shape[0]
     tape = []
     s = D.get_output_for(images, tape=tape)
+    _sink('critic_fixed', D, tape)
     term = _row_sum(rt, s, 1, n, scale=-weight / n)
     (d,) = backward(D, tape, [torch.full_like(s, -weight / n)], None, param_grads=False)
     return term, d
@@ -384,8 +424,10 @@ def _add(rt, a, b):
 
 # ====================================================================== critic phase (WGAN-GP)
 def _mask(rt, t, y, n, h, w, c):
-    """t * lrelu'(y): the activation of the mask-frozen (linearised) network."""
-    _, out = rt.grad_prepare(t, n, h, w, c, src_kind=1, y_f32=y, want_planes=False, want_f32=True)
+    """t * lrelu'(y): the activation of the mask-frozen (linearised) network.  y: fp32 map or an Act."""
+    from .backward import _mask_of
+    kw = _mask_of(rt, y) if isinstance(y, Act) else dict(y_f32=y)
+    _, out = rt.grad_prepare(t, n, h, w, c, src_kind=1, want_planes=False, want_f32=True, **kw)
     return out
 
 
@@ -423,7 +465,7 @@ def tangent_forward(D, tape, v):
                             want_split=False, algo=_lib.ALGO_TC, prepared=prepared,
                             halo_in='zero' if rec.get('halo') == 'zero' else None)
             if rec['act']:
-                out.f32 = _mask(rt, out.f32, rt.split_unpack(y).f32, y.n, y.h, y.w, y.c)
+                out.f32 = _mask(rt, out.f32, y, y.n, y.h, y.w, y.c)
             tin[pos] = xin                      # carries the padded planes (REFLECT / ZERO) the conv just packed
             tang[id(y)] = out
         elif kind == 'bias_act':                # fused conv2d_downscale2d: the bias drops out, the mask stays
@@ -471,6 +513,7 @@ def gradient_penalty(D, mixed, flat_grad, wgan_lambda=10.0, wgan_target=1.0):
     n = mixed.shape[0]
     tape, adj = [], {}
     s = D.get_output_for(mixed, tape=tape)
+    _sink('critic_mixed', D, tape)
     (g,) = backward(D, tape, [torch.ones_like(s)], None, param_grads=False, adjoints=adj)
     per = g[0].numel()
     sq = _row_sum(rt, g, n, per, square=True)
@@ -519,8 +562,10 @@ def D_wgangp(D, fakes, reals, mixing_factors, flat_grad, wgan_lambda=10.0, wgan_
     rep = {}
     t_f, t_r = [], []
     s_f = D.get_output_for(fakes.contiguous(), tape=t_f)
+    _sink('critic_fake', D, t_f)
     backward(D, t_f, [torch.full_like(s_f, 1.0 / n)], flat_grad, want_input_grads=False)
     s_r = D.get_output_for(reals.contiguous(), tape=t_r)
+    _sink('critic_real', D, t_r)
     seed = rt.empty(*s_r.shape)                       # d/ds_real [ -s/N + eps s^2 / N ]
     _lib.check(rt.lib.tmx_axpb(rt.handle, _ptr(s_r), _ptr(seed), n, 2.0 * wgan_epsilon / n, -1.0 / n, rt.stream()),
                'tmx_axpb')

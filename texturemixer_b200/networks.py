@@ -15,6 +15,7 @@ the others raise NotImplementedError.  Progressive growing
 368-374, 473-479, 568-574) is evaluated and recorded on the tape like every
 other layer."""
 import functools
+import os
 
 import numpy as np
 import torch
@@ -100,7 +101,9 @@ def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=Fals
         if algo == 1:
             raise NotImplementedError('backward needs the tensor-core conv (channels multiple of 16), got %d -> %d'
                                       % (cin, fmaps))
-        torgb, keep_f32, next_tc = None, True, True
+        # (the fp32 map only where a consumer reads it: pooling, the residual stream, image heads; the leaky-ReLU mask
+        # of the backward comes from the bf16 hi plane, backward._mask_of)
+        torgb, keep_f32, next_tc = None, keep_f32 or not next_tc or bool(os.environ.get('TMX_KEEP_F32')), True
     if torgb is not None and algo != 1:
         scope, nch, tanh = torgb
         wr, br = ctx.net.vars[scope + '/weight'], ctx.net.vars[scope + '/bias']

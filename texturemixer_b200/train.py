@@ -257,25 +257,7 @@ class Trainer:
 
     # ------------------------------------------------------------------ fake images of the canvas critics (no tape)
     def _fcn_fake(self, fwd, which, yx, mix=None):
-        """Crop at `yx` of G_fcn's image of the interpolated (`which` = 'interp') or blended canvas, decoding only
-        the latent window the crop depends on (loss.crop_window).  D_blend_wgangp draws its own mixing factors
-        (loss.py:489), D_interp_wgangp its own crop offset (loss.py:398-400): neither can reuse the E/G images once
-        those are decoded crop-aware."""
-        c, rt = self.cfg, self.rt
-        res = c['resolution']
-        win = loss.crop_window(yx, res, fwd.lat, fwd.H, fwd.W) if c.get('crop_aware', True) else None
-        blend = None if which == 'interp' else (fwd.ih_b, fwd.iw_b, mix.reshape(-1).contiguous())
-        zg_c, zl_c = loss.fcn_canvases(rt, fwd.zg_mu, fwd.zl_mu, fwd.H, fwd.W, fwd.pins, fwd.ih_f, fwd.iw_f, win, blend)
-        mid = tail = None
-        if c.get('crop_aware', True) and self.nets['G'].lod <= 2.0:
-            mid = loss.mid_window(yx, res, fwd.lat, win, fwd.H, fwd.W)
-            win_abs = loss.compose_window(win, mid, fwd.H, fwd.W)
-            tail = loss.tail_window(yx, res, fwd.lat, win_abs, fwd.H, fwd.W)
-        else:
-            win_abs = win
-        y0, x0 = loss.image_offset(yx, res // fwd.lat, win_abs, tail)
-        img = self.G_fcn.get_output_for(zg_c, zl_c, mid_window=mid, tail_window=tail, **loss.fcn_scale(zl_c, fwd.lat))
-        return img[:, :, y0:y0 + res, x0:x0 + res].contiguous()
+        return loss.fcn_fake(self.G_fcn, fwd, which, yx, mix, crop_aware=self.cfg.get('crop_aware', True))
 
     def _critic(self, name, n):
         key = (name, n, self.nets[name].lod)
