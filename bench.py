@@ -1,11 +1,15 @@
 #!/usr/bin/env python
 """bench.py - headline benchmark of the TextureMixer hot path on B200.
 
-Workload (BASELINE.json configs[1]): generator `G_res` forward, batch 64 random
-latents per GPU (zg tiled to 32x32, zl ~ N(0,1)), fp32 in/out, 128x128x3 out.
-Metric: 128x128 texture images/sec (whole job, all ranks).
+Default workload: the FULL TRAIN STEP (BASELINE.json configs[2] at one GPU, configs[4] at N > 1: batch 32 per GPU,
+weak scaling, one NCCL all-reduce per optimizer phase) - the path north_star says to scale.  Metric: 128x128
+texture images/sec (whole job, all ranks; one step consumes one minibatch per rank like run.py:510-514 counts it).
+`--workload gen_fwd` = configs[1] (G_res forward, batch 64), `interp` = configs[3], `recon` = configs[0].
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload ...]
+
+The gen_fwd workload: generator `G_res` forward, batch 64 random
+latents per GPU (zg tiled to 32x32, zl ~ N(0,1)), fp32 in/out, 128x128x3 out.
 
 * `value`   : inputs resident in HBM, CUDA-event time of the K steps (L2 flushed
               between steps, max over ranks).
@@ -41,6 +45,7 @@ TRUNK_GFLOP_PER_IMAGE = 1.2080       # one 3x3 256->256 conv @32x32 (2*9*256*256
 TRUNK_DRAM_BYTES = 0.5 * (105.8e6 + 239.3e6)
 TRUNK_DRAM_SOURCE = 'profiles/r01_ncu_trunk_conv_tc_v2.csv (mean of the Residual_0 and Residual_1 launches)'
 METRIC = '128x128 texture images/sec (G_res forward, fp32 parity path)'
+GEN_WORKLOAD = 'cfg2: G_res forward, batch 64 random latents per GPU, 128x128x3 out'
 G_CFG = dict(fmap_base=1024, fmap_max=512, latent_res=32, latent_channels=128, use_pixelnorm=False, tanh_at_end=True)
 
 
@@ -135,6 +140,8 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    if args.workload == 'train_step':
+        return run_reference_train(args)
     sample = 16
     ips, sec_per_step, cores = time_oracle(args.steps, args.warmup, sample)
     desc = 'G_res forward on %d of the %d-latent batch per step, torch-CPU fp32' % (sample, BATCH)
@@ -142,9 +149,29 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec_per_step * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'cfg2: G_res forward, batch 64 random latents per GPU, 128x128x3 out', 'batch_per_gpu': BATCH,
+        'config': {'workload': GEN_WORKLOAD, 'batch_per_gpu': BATCH,
                    'note': 'CPU restatement of the TF1 graph (oracle/); TensorFlow 1.12 is not installable here'},
         'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': desc},
+        'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def run_reference_train(args):
+    """The reference arm of the default workload: the CPU restatement of the TF1 train step (oracle/: the reference's
+    loss composition - pinned to /root/reference/loss.py by tests/golden/losses.npz - with autograd incl. the
+    create_graph gradient penalty, TF1 Adam restatement) on all host cores.  One step = ONE whole train step on a
+    bounded sample of CPU_TRAIN_SAMPLE images of the 32-image minibatch (whole 3x3 canvases: the reference decodes
+    them whole), so that K steps end within minutes."""
+    ips, sec, cores = time_oracle_train_step(CPU_TRAIN_SAMPLE, steps=args.steps, warmup=args.warmup, budget_s=240.0)
+    line = {
+        'impl': 'reference', 'metric': TRAIN_METRIC, 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'steps_timed': time_oracle_train_step.steps_done, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': TRAIN_WORKLOAD, 'batch_per_gpu': TRAIN_BATCH,
+                   'note': 'CPU restatement of the TF1 graph (oracle/); TensorFlow 1.12 is not installable here'},
+        'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': CPU_TRAIN_DESC},
         'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -242,7 +269,7 @@ def run_ours(args):
         flush.fill_(1)
         step()
     torch.cuda.synchronize()
-    trunk = [a.elapsed_time(b) for tag, a, b in rt.kernel_events if tag == ('tc', 3, 256, 256)]
+    trunk = [a.elapsed_time(b) for tag, a, b in rt.kernel_events if tag[:4] == ('tc', 3, 256, 256)]
     rt.profile_kernels = False
     trunk_ms = float(np.mean(trunk)) if trunk else None
 
@@ -271,7 +298,7 @@ def run_ours(args):
             'warmup': max(args.warmup, 3), 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (bf16x3 tensor-core products, fp32 accumulate)',
             'data': 'synthetic',
-            'config': {'workload': 'cfg2: G_res forward, batch 64 random latents per GPU, 128x128x3 out',
+            'config': {'workload': GEN_WORKLOAD,
                        'batch_per_gpu': BATCH, 'l2': 'flushed between timed steps (256 MiB write)',
                        'gflop_per_image': GFLOP_PER_IMAGE, 'parallelism': 'images sharded over ranks, no collective'},
             'tflops_algorithmic': value * GFLOP_PER_IMAGE / 1e3,
@@ -291,20 +318,33 @@ def run_ours(args):
 
 # ------------------------------------------------------------------ train step (BASELINE configs[2] / [4])
 TRAIN_BATCH = 32
-# Algorithmic GFLOP per sample of one train step (gram off, E/G forwards shared between phases):
-#   whole canvases : E 5.6 + G 38.7 + three D 51.2 + G_fcn 7 evaluation units x 116.2                  = 908.9
+TRAIN_METRIC = '128x128 texture images/sec (full train step: 3 critics + E/G + EMA)'
+TRAIN_WORKLOAD = ('cfg3/5: full train step (run.py:510-514), batch 32 per GPU, lod 0, gram_weight 0, 3x3 canvases, '
+                  'a fresh minibatch for the critic phase and for the E/G phase like the reference')
+# Algorithmic GFLOP per sample of one train step (gram off).  The critic phase and the E/G phase each
+# consume their own minibatch like the reference (run.py:286,511-512), so the encoders and the reconstruction run
+# forward once more for the critics' fakes: E 4 F-units 7.47 + G (scale 1) 4 units 51.6 + three D 51.2 = 110.3, plus
+# G_fcn: 8 evaluation units (D_interp fwd, D_blend fwd, E/G interp fwd + bwd 3, E/G blend 3)
+#   whole canvases : 8 x 116.2                                                                        = 1 039.9
 #   crop-aware     : G_fcn decodes the 64x64 latent window each random_crop depends on instead of the 96x96 canvas
-#                    (identical results, SURVEY Appendix C note): 8 units (the critics' interpolation fake no longer
-#                    shares the E/G image) x 116.2 x (64/96)^2 = 413.2, + 95.5                             = 508.7
-#                    ... and its up-sampling blocks + ToRGB only the 40x40 latent pixels around the crop
-#                    (loss.tail_window), and the last 4 latent-resolution convs 48x48 (loss.mid_window): per unit
-#                    8 x 1.208 x 4 + 2.7935 x (48/32)^2 + 0.4546 x (40/32)^2 = 45.65 -> 8 x 45.65 + 95.5    = 460.7
-TRAIN_GFLOP = {True: 460.7, False: 908.9}
+#                    (identical results, SURVEY Appendix C note), the last 4 latent-resolution convs on 48x48
+#                    (loss.mid_window) and the up-sampling blocks + ToRGB on 40x40 (loss.tail_window): per unit
+#                    8 x 1.208 x 4 + 2.7935 x (48/32)^2 + 0.4546 x (40/32)^2 = 45.65 -> 8 x 45.65 + 110.3 = 475.5
+TRAIN_GFLOP = {True: 475.5, False: 1039.9}
+# dominant kernel of the step: conv_tc_kernel<256,64,32,PAIR> on the 64x64 trunk windows (3x3, 256 -> 256, batch 32)
+TRUNK64_GFLOP = 2 * 9 * 256 * 256 * 64 * 64 * TRAIN_BATCH / 1e9          # 154.6 GFLOP per launch
+# dram__bytes_read.sum + dram__bytes_write.sum of one such launch from the committed `ncu --set full` capture
+TRUNK64_DRAM_BYTES = None
+TRUNK64_DRAM_SOURCE = None
+CPU_TRAIN_SAMPLE = 2
+CPU_TRAIN_DESC = ('one whole train step per step on %d images (whole 3x3 canvases, autograd incl. the gradient penalty), '
+                  'torch-CPU fp32 restatement (oracle/)' % CPU_TRAIN_SAMPLE)
 
 
-def time_oracle_train_step(sample=2):
-    """One train step of the CPU restatement (oracle/: autograd losses incl. the create_graph gradient penalty, TF1
-    Adam restatement) on `sample` images, all host cores.  -> (samples/s, seconds, cores)."""
+def time_oracle_train_step(sample=2, steps=1, warmup=0, budget_s=None):
+    """`steps` train steps of the CPU restatement (oracle/: autograd losses incl. the create_graph gradient penalty,
+    TF1 Adam restatement) on `sample` images each, all host cores, after `warmup` untimed ones.
+    -> (samples/s, seconds per step, cores)."""
     import torch
     from oracle import interp_ref as I
     from oracle import loss_ref as L
@@ -316,8 +356,6 @@ def time_oracle_train_step(sample=2):
     np.random.seed(1000)
     funcs = dict(E_zg='E_zg', E_zl='E_zl', G='G_res', D_rec='D_patch', D_interp='D_patch', D_blend='D_patch')
     params = {k: R.init_params(f, rng, **R.CONFIG[f]) for k, f in funcs.items()}
-    x = torch.from_numpy(rng.uniform(-1, 1, (sample, 3, 128, 128)).astype(np.float32))
-    idx = I.sample_schedule_indices(sample, latent_res=32, scale_h=3, scale_w=3)
     mix = lambda: torch.from_numpy(rng.uniform(0, 1, (sample, 1, 1, 1)).astype(np.float32))   # noqa: E731
     crop = lambda: (int(rng.randint(0, 256)), int(rng.randint(0, 256)))                        # noqa: E731
 
@@ -327,35 +365,49 @@ def time_oracle_train_step(sample=2):
 
     def flat(P):
         return np.concatenate([np.asarray(v, np.float32).reshape(-1) for k, v in P.items() if k != 'lod'])
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        P0 = {k: R.to_torch(params[k]) for k in ('E_zg', 'E_zl', 'G')}
-        zg, _ = R.E_zg(x, P0['E_zg'], **R.CONFIG['E_zg'])
-        zl, _ = R.E_zl(x, P0['E_zl'], **R.CONFIG['E_zl'])
-        rec = R.G_res(zg.repeat(1, 1, 32, 32), zl, P0['G'], **R.CONFIG['G_res'])
-        gcfg = dict(R.CONFIG['G_res'], scale_h=3, scale_w=3)
-        zg_c = zg.repeat(1, 1, 96, 96)
-        zl_c = L.tiling_permutation(zl, 3, 3, idx['h_forward'], idx['w_forward'])
-        y0, x0 = crop()
-        fake_i = R.G_res(zg_c, zl_c, P0['G'], **gcfg)[:, :, y0:y0 + 128, x0:x0 + 128]
-        zg_r = torch.flip(zg, dims=[0]).repeat(1, 1, 96, 96)
-        zl_r = L.tiling_permutation(torch.flip(zl, dims=[0]), 3, 3, idx['h_backward'], idx['w_backward'])
-        t = mix()
-        y0, x0 = crop()
-        fake_b = R.G_res(zg_r + (zg_c - zg_r) * t, zl_r + (zl_c - zl_r) * t, P0['G'], **gcfg)[:, :, y0:y0 + 128, x0:x0 + 128]
-    for k, fake in (('D_rec', rec), ('D_interp', fake_i), ('D_blend', fake_b)):
-        P = R.to_torch(params[k], requires_grad=True)
-        loss, _ = L.D_wgangp(P, fake, x, mix())
+    states = {k: None for k in funcs}
+
+    def adam(k, P):
+        w = flat(params[k])
+        if states[k] is None:
+            states[k] = O.AdamState(w.size, 0.0, 0.99)
+        O.optimizer_step(w, [flat_grads(P)], states[k], 0.0015)       # (weights are not written back: timing only)
+
+    def one_step():
+        x_d = torch.from_numpy(rng.uniform(-1, 1, (sample, 3, 128, 128)).astype(np.float32))
+        x = torch.from_numpy(rng.uniform(-1, 1, (sample, 3, 128, 128)).astype(np.float32))
+        idx = I.sample_schedule_indices(sample, latent_res=32, scale_h=3, scale_w=3)
+        P0 = {k: R.to_torch(params[k]) for k in funcs}
+        for k in ('D_rec', 'D_interp', 'D_blend'):                     # run.py:511: the three critics, own minibatch
+            P = dict(P0)
+            P[k] = R.to_torch(params[k], requires_grad=True)
+            if k == 'D_rec':
+                loss, _ = L.D_rec_wgangp(P, x_d, mix())
+            elif k == 'D_interp':
+                loss, _ = L.D_interp_wgangp(P, x_d, idx, crop(), mix())
+            else:
+                loss, _ = L.D_blend_wgangp(P, x_d, idx, crop(), mix(), mix())
+            loss.mean().backward()
+            adam(k, P[k])
+        P = {k: R.to_torch(params[k], requires_grad=k in ('E_zg', 'E_zl', 'G')) for k in funcs}
+        loss, _ = L.EG_wgan(P, x, idx, crop(), crop(), mix())          # run.py:512
         loss.mean().backward()
-        w = flat(params[k])
-        O.optimizer_step(w, [flat_grads(P)], O.AdamState(w.size, 0.0, 0.99), 0.0015)
-    P = {k: R.to_torch(params[k], requires_grad=k in ('E_zg', 'E_zl', 'G')) for k in funcs}
-    loss, _ = L.EG_wgan(P, x, idx, crop(), crop(), mix())
-    loss.mean().backward()
-    for k in ('E_zg', 'E_zl', 'G'):
-        w = flat(params[k])
-        O.optimizer_step(w, [flat_grads(P[k])], O.AdamState(w.size, 0.0, 0.99), 0.0015)
-    dt = time.perf_counter() - t0
+        for k in ('E_zg', 'E_zl', 'G'):
+            adam(k, P[k])
+    t_begin = time.perf_counter()
+    for i in range(warmup):
+        one_step()
+        if budget_s and i >= 0 and time.perf_counter() - t_begin > 0.25 * budget_s:
+            break                                  # bounded run: the warm-up may not eat the budget
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        one_step()
+        done += 1
+        if budget_s and time.perf_counter() - t_begin > budget_s:
+            break                                  # bounded run (a few minutes): report what was timed
+    dt = (time.perf_counter() - t0) / done
+    time_oracle_train_step.steps_done = done
     return sample / dt, dt, cores
 
 
@@ -375,13 +427,17 @@ def run_train(args):
     from texturemixer_b200.train import default_config
     cfg = default_config()
     cfg['crop_aware'] = not args.whole_canvas
+    if args.graphs is not None:
+        cfg['cuda_graphs'] = {'step': 'step', 'critics': 'critics', 'off': False}[args.graphs]
     TRAIN_GFLOP_PER_SAMPLE = TRAIN_GFLOP[cfg['crop_aware']]
     tr = Trainer(cfg, seed=1000, device=local)
     rt, dev = tr.rt, tr.rt.device
     rng = np.random.RandomState(1000 + rank)
     np.random.seed(1000 + rank)
-    reals_h = torch.from_numpy(rng.uniform(-1, 1, (TRAIN_BATCH, 3, 128, 128)).astype(np.float32)).pin_memory()
+    # two minibatches per step like the reference: one for the critic phase, one for the E/G phase (run.py:511-512)
+    reals_h = torch.from_numpy(rng.uniform(-1, 1, (2, TRAIN_BATCH, 3, 128, 128)).astype(np.float32)).pin_memory()
     reals_d = reals_h.to(dev)
+    shared = args.shared_minibatch
 
     def barrier():
         torch.cuda.synchronize()
@@ -389,12 +445,15 @@ def run_train(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def one_step(x):
+        return tr.step(x[1], tr.sample_draws(TRAIN_BATCH, rng), reals_d=None if shared else x[0])
+
     for _ in range(max(args.warmup, 3)):
-        tr.step(reals_d, tr.sample_draws(TRAIN_BATCH, rng))
+        one_step(reals_d)
     barrier()
     if args.device_only:      # for `ncu --profile-from-start off`: exactly one step between cudaProfilerStart/Stop
         torch.cuda.profiler.start()
-        tr.step(reals_d, tr.sample_draws(TRAIN_BATCH, rng))
+        one_step(reals_d)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
@@ -405,22 +464,26 @@ def run_train(args):
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
     l0, g0 = rt.launch_count(), tr.graph_launches
+    tr.time_collectives, tr.allreduce_events = True, []
     t_host = time.perf_counter()
     for i in range(args.steps):
         evs[i].record()
-        tr.step(reals_d, tr.sample_draws(TRAIN_BATCH, rng))
+        one_step(reals_d)
     evs[-1].record()
     host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps        # host time to ENQUEUE one step (no sync inside)
     barrier()
     launches = rt.launch_count() - l0 + tr.graph_launches - g0
     dev_ms = evs[0].elapsed_time(evs[-1])
     step_ms = [round(evs[i].elapsed_time(evs[i + 1]), 2) for i in range(args.steps)]
-    # end to end: reals from pinned host memory every step, loss report read back
+    coll_ms = sum(a.elapsed_time(b) for _, a, b in tr.allreduce_events) / args.steps
+    coll_n = len(tr.allreduce_events) / args.steps
+    tr.time_collectives, tr.allreduce_events = False, []
+    # end to end: both minibatches from pinned host memory every step, loss report read back
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         x = reals_h.to(dev, non_blocking=True)
-        rep = tr.step(x, tr.sample_draws(TRAIN_BATCH, rng))
+        rep = one_step(x)
         host_rep = {k: float(v.reshape(-1)[0].item()) for k, v in rep.items()}
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -432,42 +495,75 @@ def run_train(args):
     if world > 1:
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    # dominant kernel, timed live (CUDA events around each of its launches) in a separate pass issued launch by launch
+    # on ONE stream - inside the replayed graphs no event can be placed, and on parallel streams other kernels would
+    # share the SMs with it
+    trunk_ms = trunk_n = None
+    if True:      # every rank: the pass contains the collective all-reduces
+        os.environ['TMX_GRAPH_MODE'], os.environ['TMX_NO_FORK'] = 'off', '1'
+        rt.profile_kernels, rt.kernel_events = True, []
+        for _ in range(2):
+            one_step(reals_d)
+        torch.cuda.synchronize()
+        sel = [a.elapsed_time(b) for tag, a, b in rt.kernel_events if tag[:4] == ('tc', 3, 256, 256) and tag[4:] == (64, 64)]
+        rt.profile_kernels, rt.kernel_events = False, []
+        del os.environ['TMX_GRAPH_MODE'], os.environ['TMX_NO_FORK']
+        if sel:
+            trunk_ms, trunk_n = float(np.mean(sel)), len(sel)
+    t = torch.tensor([dev_ms, e2e_s, coll_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s = float(t[0]), float(t[1])
+    dev_ms, e2e_s, coll_ms = float(t[0]), float(t[1]), float(t[2])
     if rank == 0:
         pk = peaks()
         samples = TRAIN_BATCH * world * args.steps
         value = samples / (dev_ms * 1e-3)
-        tf = value * TRAIN_GFLOP_PER_SAMPLE / 1e3 / world
+        tf_step = value * TRAIN_GFLOP_PER_SAMPLE / 1e3 / world
         cpu_line = None
         if world == 1:
-            cpu_v, cpu_s, cores = time_oracle_train_step(2)
+            cpu_v, cpu_s, cores = time_oracle_train_step(CPU_TRAIN_SAMPLE, steps=2, warmup=1)
             cpu_line = {'value': cpu_v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                        'sample': 'ONE train step on 2 images (whole 3x3 canvases, autograd incl. the gradient penalty), '
-                                  'torch-CPU fp32 restatement (oracle/), %.1f s' % cpu_s}
+                        'sample': CPU_TRAIN_DESC + '; 2 timed steps after 1 warm-up, %.1f s per step' % cpu_s}
+        roof = None
+        if trunk_ms:
+            tfk = TRUNK64_GFLOP / trunk_ms                           # GFLOP / ms == TFLOP/s
+            peak = pk['bf16_sustained'] or pk['bf16']
+            roof = {'bound': 'tensor', 'achieved': tfk, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tfk / peak,
+                    'traffic': TRUNK64_DRAM_BYTES, 'traffic_source': TRUNK64_DRAM_SOURCE,
+                    'kernel': 'conv_tc_kernel<256,64,32,PAIR> forward, 3x3 256->256 on the 64x64 latent windows, batch 32 '
+                              '(the dominant kernel: 40 of its launches per step + its data-gradient twin)',
+                    'kernel_ms': trunk_ms, 'launches_timed': trunk_n,
+                    'peak_source': pk['source'] + ', bf16 sustained (kernel timed inside a long step)',
+                    'note': 'achieved = algorithmic fp32-conv FLOPs; the kernel executes 3 bf16 MMAs per product (bf16x3 '
+                            'split for 1e-3 fp32 parity): executed %.1f TFLOP/s = %.3f of peak; timed in a separate '
+                            'launch-by-launch pass on one stream' % (3 * tfk, 3 * tfk / peak),
+                    'whole_step': {'achieved': tf_step, 'frac': tf_step / peak,
+                                   'note': 'algorithmic GFLOP of the whole step per GPU / step time'}}
         line = {
-            'metric': '128x128 texture images/sec (full train step: 3 critics + E/G + EMA)', 'value': value,
+            'metric': TRAIN_METRIC, 'value': value,
             'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32 (bf16x3 tensor-core products, fp32 accumulate)', 'data': 'synthetic',
-            'config': {'workload': 'cfg3/5: full train step, batch 32 per GPU, lod 0, gram_weight 0, 3x3 canvases',
+            'config': {'workload': TRAIN_WORKLOAD if not shared else TRAIN_WORKLOAD.replace(
+                           'a fresh minibatch for the critic phase and for the E/G phase like the reference',
+                           'ONE minibatch shared by the critic and E/G phases (deviation)'),
                        'batch_per_gpu': TRAIN_BATCH, 'global_batch': TRAIN_BATCH * world,
                        'l2': 'working set per step (>20 GB) far exceeds the 126 MB L2',
-                       'parallelism': 'dp%d: one flat-bucket NCCL all-reduce per network per optimizer' % world,
+                       'parallelism': 'dp%d: ONE flat-bucket NCCL all-reduce per optimizer phase (2 per step), non-finite '
+                                      'marks in the bucket tail' % world,
+                       'cuda_graphs': str(cfg['cuda_graphs']),
                        'g_fcn': 'crop-aware: decodes the 64x64 latent window of each random_crop, the last 4 latent convs on 48x48, the '
                                 'up-sampling blocks on 40x40 of it '
                                 '(identical results)'
                        if cfg['crop_aware'] else 'whole 96x96 canvases decoded',
                        'gflop_per_sample': TRAIN_GFLOP_PER_SAMPLE},
             'e2e': {'value': samples / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': int(reals_h.numel() * 4),
-                    'd2h_bytes_per_step': 4 * len(host_rep), 'api': 'Trainer.step(reals) with host reals + loss report'},
+                    'd2h_bytes_per_step': 4 * len(host_rep), 'api': 'Trainer.step(reals, draws, reals_d=...) with both '
+                    'minibatches in page-locked host memory + the loss report read back'},
             'gpu_launches': int(launches), 'host_enqueue_ms_per_step': host_ms, 'step_ms': step_ms,
-            'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': pk['bf16_sustained'] or pk['bf16'], 'unit': 'TFLOP/s',
-                         'frac': tf / (pk['bf16_sustained'] or pk['bf16']), 'traffic': None,
-                         'kernel': 'whole step per GPU (algorithmic fp32-conv FLOPs; tensor pipe executes 3x)',
-                         'peak_source': pk['source'] + ', bf16 sustained'},
+            'collective_ms_per_step': coll_ms, 'collectives_per_step': coll_n,
+            'collective_bytes_per_step': int(sum(b.flat.numel() for b in tr.buckets.values()) * 4) if world > 1 else 0,
+            'roofline': roof,
             'cpu_baseline': cpu_line,
             'replicas_identical': bool(float(hi - lo) == 0.0),
             'clocks': clocks,
@@ -568,7 +664,7 @@ def run_interp(args):
         flush.fill_(1)
         step(src_d)
     torch.cuda.synchronize()
-    trunk = [a.elapsed_time(b) for tag, a, b in rt.kernel_events if tag == ('tc', 3, 256, 256)]
+    trunk = [a.elapsed_time(b) for tag, a, b in rt.kernel_events if tag[:4] == ('tc', 3, 256, 256)]
     rt.profile_kernels = False
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -739,9 +835,14 @@ def main():
     ap.add_argument('--device-only', action='store_true', help='only the device-resident loop (profiling runs)')
     ap.add_argument('--whole-canvas', action='store_true',
                     help='train_step: decode the whole 3x3 canvases in G_fcn instead of the crop windows')
-    ap.add_argument('--workload', default='gen_fwd', choices=['gen_fwd', 'train_step', 'interp', 'recon'],
-                    help='gen_fwd = BASELINE configs[1] (headline); train_step = configs[2]/[4]: full train step, '
-                         'batch 32 per GPU, NCCL gradient all-reduce')
+    ap.add_argument('--workload', default='train_step', choices=['gen_fwd', 'train_step', 'interp', 'recon'],
+                    help='train_step (default) = BASELINE configs[2] / [4]: full train step, batch 32 per GPU, NCCL '
+                         'gradient all-reduce; gen_fwd = configs[1]: G_res forward, batch 64')
+    ap.add_argument('--graphs', default=None, choices=['step', 'critics', 'off'],
+                    help='train_step: how the step is issued (default: whole step as CUDA graphs)')
+    ap.add_argument('--shared-minibatch', action='store_true',
+                    help='train_step: critic and E/G phases see the SAME minibatch (one E/G forward serves both; '
+                         'deviation from run.py:511-512)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TMX_ABI_VERSION 3
+#define TMX_ABI_VERSION 4
 
 typedef struct tmx_ctx* tmx_handle_t;
 typedef void* tmx_stream_t; /* cudaStream_t */
@@ -337,6 +337,15 @@ int tmx_pixel_norm_bwd(tmx_handle_t h, const float* x, const float* dy, float* d
 int tmx_kl_terms(tmx_handle_t h, const float* mu, const float* log_sigma, float* dmu, float* dls, float* val, int64_t n,
                  float gscale, tmx_stream_t s);
 
+/* Window of a [A][H][W][B] fp32 tensor (NCHW: A = N*C, B = 1; NHWC: A = N, B = C) at an offset that may live in
+ * DEVICE memory (off_dev = {oy, ox} int32, overrides oy / ox when not NULL), so that the launch is identical from
+ * one train step to the next and the step can be replayed as a CUDA graph: random_crop (loss.py:78-90) and the
+ * crop-aware latent windows derived from it.
+ *   embed = 0: dst[A][wh][ww][B] = src[A][oy+y][ox+x][B];   embed = 1: the adjoint - dst[A][H][W][B] = the window
+ *   src[A][wh][ww][B] placed at (oy, ox), zeros elsewhere (every element of dst is written). */
+int tmx_window_copy(tmx_handle_t h, const float* src, float* dst, int64_t A, int H, int W, int B, int wh, int ww,
+                    int oy, int ox, const int32_t* off_dev, int embed, tmx_stream_t s);
+
 /* out = a + b over n fp32 elements (two gradient contributions meeting at one tensor). */
 int tmx_add_f32(tmx_handle_t h, const float* a, const float* b, float* out, int64_t n, tmx_stream_t s);
 
@@ -379,6 +388,19 @@ int tmx_nonfinite_check(tmx_handle_t h, const float* g, int64_t n, int* flag, tm
 int tmx_adam_step(tmx_handle_t h, float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, float grad_scale, float* powers, const int* skip_flag, tmx_stream_t s);
 int tmx_ema_update(tmx_handle_t h, const float* src, float* dst, int64_t n, float beta, tmx_stream_t s);
+/* Data-parallel form (replaces the per-variable nccl.all_sum + per-tower finite check of
+ * tfutil.py:326-355): every rank marks its LOCAL non-finite gradients in a float slot that travels in the tail of
+ * the gradient bucket (tmx_nonfinite_mark: *mark = 1 if any g[i] is inf/nan, never clears it); after the SUM
+ * all-reduce the slot is > 0 on every rank iff any rank overflowed.
+ * tmx_adam_update: the Adam step of tmx_adam_step WITHOUT the beta-power update, skipped when *skip_flag != 0 or
+ *   *skip_mark != 0 (either may be NULL) - several networks of one optimizer step with the same powers;
+ * tmx_adam_advance: the beta-power update, once per optimizer, under the same skip condition. */
+int tmx_nonfinite_mark(tmx_handle_t h, const float* g, int64_t n, float* mark, tmx_stream_t s);
+int tmx_adam_update(tmx_handle_t h, float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float grad_scale, const float* powers, const int* skip_flag,
+                    const float* skip_mark, tmx_stream_t s);
+int tmx_adam_advance(tmx_handle_t h, float* powers, float beta1, float beta2, const int* skip_flag,
+                     const float* skip_mark, tmx_stream_t s);
 
 /* ------------------------------------------------------------------ permutation sampler (host)
  * run.py:107-182 (my_swap_h / my_swap_w / block_permutation) as driven by

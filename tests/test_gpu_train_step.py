@@ -81,12 +81,14 @@ def test_train_step_vs_oracle(lod):
         y0, x0 = draws['d_blend_crop']
         fake_b = R.G_res(zg_r + (zg_c - zg_r) * t, zl_r + (zl_c - zl_r) * t, P0['G'], **gcfg)[:, :, y0:y0 + res, x0:x0 + res]
     new = {}
+    d_grads = {}
     for k, fake, gp in (('D_rec', rec, 'd_rec_gp'), ('D_interp', fake_i, 'd_interp_gp'), ('D_blend', fake_b, 'd_blend_gp')):
         P = R.to_torch(params[k], requires_grad=True)
         loss, _ = L.D_wgangp(P, fake, x, mixes[gp])
         loss.mean().backward()
         w = w0[k].copy()
-        assert O.optimizer_step(w, [_grads(P)], O.AdamState(w.size, 0.0, 0.99), 0.0015)
+        d_grads[k] = _grads(P)
+        assert O.optimizer_step(w, [d_grads[k]], O.AdamState(w.size, 0.0, 0.99), 0.0015)
         new[k] = w
     P = {k: R.to_torch(params[k], requires_grad=True) for k in ('E_zg', 'E_zl', 'G')}
     for k in ('D_rec', 'D_interp', 'D_blend'):
@@ -102,21 +104,108 @@ def test_train_step_vs_oracle(lod):
         new[k] = w_all[off:off + w0[k].size]
         off += w0[k].size
 
-    # ---------------- device step
+    # ---------------- device step (the first step of a shape runs eagerly; later ones replay as CUDA graphs)
+    grads_ref = {}
+    off = 0
+    for k in ('E_zg', 'E_zl', 'G'):
+        grads_ref[k] = g_all[off:off + w0[k].size]
+        off += w0[k].size
+    for k in ('D_rec', 'D_interp', 'D_blend'):
+        grads_ref[k] = d_grads[k]
     rep = tr.step(torch.from_numpy(reals).cuda(), draws, lod=lod)
     torch.cuda.synchronize()
-    assert all(int(rep[k + '/skipped'].item()) == 0 for k in ('D_rec', 'D_interp', 'D_blend', 'EG'))
-    step = 0.0015 * np.sqrt(1 - 0.99)      # first Adam step moves every weight by ~ lr_t * 10 * sign(g) = 1.5e-3
+    assert all(float(rep[k + '/skipped'].item()) == 0 for k in ('D_rec', 'D_interp', 'D_blend', 'EG'))
+
+    def dev_flat(store, k):
+        return np.concatenate([tr.nets[k].grad_view(store[k], vn).cpu().numpy().reshape(-1) if store is not None else
+                               tr.nets[k].get_var(vn).reshape(-1) for vn in tr.nets[k].vars if vn != 'lod'])
+
+    def rel(a, b):
+        return float(np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64)))
+    # (1) the gradient every optimizer received, against the oracle's autograd - per network, directly.  Bound: the
+    # leaky-ReLU-flip limited one (tests/test_gpu_loss_golden.py shows <= 1e-3 per variable once the branch masks are
+    # shared; the post-step critics of the E/G phase additionally differ by their own first Adam step's sign flips)
+    g_dev = {k: dev_flat(tr.grads, k) for k in names}
     for k in names:
-        got = np.concatenate([tr.nets[k].get_var(vn).reshape(-1) for vn in tr.nets[k].vars if vn != 'lod'])
-        moved = np.abs(new[k] - w0[k]) > 1e-6
-        bad = np.abs(got - new[k]) > 1e-4
-        # the first Adam step is +-1.5e-3 * sign(g): only gradients within the (leaky-ReLU-flip limited) device
-        # error of zero may land on the other side
-        assert bad.mean() <= 0.02, (k, float(bad.mean()))
-        # (at lod 1.5 the 128x128 blocks and lod-0 heads take no part: their gradients are zero on both sides)
-        assert moved.mean() > (0.9 if lod == 0 else 0.75) and np.abs(got - w0[k]).max() <= 1.05 * step * 10 + 1e-6
+        err = rel(g_dev[k], grads_ref[k])
+        print('lod', lod, k, 'gradient rel-L2 vs oracle', err)
+        assert err <= (1e-2 if k.startswith('D_') else 5e-2), (k, err)
+    # (2) the optimizer itself, exactly: TF1 Adam (oracle restatement) applied to the DEVICE gradients must land on
+    # the device weights - no leaky-ReLU sensitivity in this check
+    states = {}
+    w_dev = {}
+    for k in names:
+        states[k] = O.AdamState(w0[k].size, 0.0, 0.99)
+        w = w0[k].copy()
+        assert O.optimizer_step(w, [g_dev[k]], states[k], 0.0015)
+        w_dev[k] = dev_flat(None, k)
+        assert np.abs(w_dev[k] - w).max() <= 2e-6, (k, float(np.abs(w_dev[k] - w).max()))
     # EMA: Gs = lerp(G, Gs, 0.999) with Gs initialised to the pre-step G
-    g_new = np.concatenate([tr.nets['G'].get_var(vn).reshape(-1) for vn in tr.nets['G'].vars if vn != 'lod'])
     gs = np.concatenate([tr.nets['Gs'].get_var(vn).reshape(-1) for vn in tr.nets['Gs'].vars if vn != 'lod'])
-    assert np.abs(gs - (g_new + (w0['G'] - g_new) * np.float32(0.999))).max() <= 1e-6
+    assert np.abs(gs - (w_dev['G'] + (w0['G'] - w_dev['G']) * np.float32(0.999))).max() <= 1e-6
+    # (3) two more steps on fresh draws (at integer lod: captured as CUDA graphs, then replayed): beta powers, Adam
+    # slots and the EMA keep following the restatement
+    # (E_zg / E_zl / G share ONE optimizer: same powers; separate state objects advance identically)
+    for it in range(2):
+        draws2 = tr.sample_draws(n, rng)
+        reals2 = rng.uniform(-1, 1, (n, 3, 128, 128)).astype(np.float32)
+        rep2 = tr.step(torch.from_numpy(reals2).cuda(), draws2, lod=lod)
+        torch.cuda.synchronize()
+        assert all(float(rep2[k + '/skipped'].item()) == 0 for k in ('D_rec', 'D_interp', 'D_blend', 'EG'))
+        for k in names:
+            g2 = dev_flat(tr.grads, k)
+            assert np.isfinite(g2).all() and np.abs(g2).max() > 0
+            w = w_dev[k].copy()
+            assert O.optimizer_step(w, [g2], states[k], 0.0015)
+            w_dev[k] = dev_flat(None, k)
+            assert np.abs(w_dev[k] - w).max() <= 2e-6, (it, k, float(np.abs(w_dev[k] - w).max()))
+        gs_new = np.concatenate([tr.nets['Gs'].get_var(vn).reshape(-1) for vn in tr.nets['Gs'].vars if vn != 'lod'])
+        assert np.abs(gs_new - (w_dev['G'] + (gs - w_dev['G']) * np.float32(0.999))).max() <= 1e-6
+        gs = gs_new
+    if lod == int(lod):
+        assert len(tr._step_graphs) == 1 and tr.graph_launches > 0          # steps 2 and 3 were graph replays
+
+
+def test_graphed_step_equals_eager_step():
+    """The captured step (device-side window offsets, multi-stream capture) against the same steps issued launch by
+    launch from Python: same draws, same reals, two trainers with identical initial weights -> same gradients (up to
+    the order of the bias-gradient atomics) and same loss report, on the reference's 3x3 canvases with a separate
+    critic minibatch (run.py:511-512)."""
+    from texturemixer_b200.train import Trainer, default_config
+    n = 4
+    out = {}
+    for mode in (False, 'step'):
+        cfg = default_config()
+        cfg['cuda_graphs'] = mode
+        tr = Trainer(cfg, seed=1000)
+        rng = np.random.RandomState(7)
+        np.random.seed(7)
+        for net in tr.nets.values():
+            for vn, v in net.trainables.items():
+                if vn.endswith('/bias'):
+                    net.set_var(vn, 0.1 * rng.randn(*v.shape).astype(np.float32))
+        for src, dst in (('E_zg', 'Es_zg'), ('E_zl', 'Es_zl'), ('G', 'Gs')):
+            tr.nets[dst].copy_vars_from(tr.nets[src])
+        reps = []
+        for it in range(4):
+            draws = tr.sample_draws(n, rng)
+            x = torch.from_numpy(rng.uniform(-1, 1, (n, 3, 128, 128)).astype(np.float32)).cuda()
+            xd = torch.from_numpy(rng.uniform(-1, 1, (n, 3, 128, 128)).astype(np.float32)).cuda()
+            rep = tr.step(x, draws, reals_d=xd)
+            torch.cuda.synchronize()
+            reps.append({k: float(v.reshape(-1)[0]) for k, v in rep.items()})
+        if mode == 'step':
+            assert len(tr._step_graphs) == 1
+        out[mode] = (reps, {k: tr.grads[k].clone() for k in tr.grads}, {k: tr.nets[k].flat.clone() for k in tr.nets})
+        del tr
+    for it in range(4):
+        for k, v in out[False][0][it].items():
+            got = out['step'][0][it][k]
+            # steps diverge slowly through Adam's sign-like first steps on near-zero gradients: loose on later steps
+            assert abs(got - v) <= (1e-5 if it == 0 else 5e-2) * max(1.0, abs(v)), (it, k, got, v)
+    # step 1 is eager in both trainers; what matters is that the replayed steps track the eager ones
+    for k in out[False][1]:
+        a, b = out[False][1][k].double(), out['step'][1][k].double()
+        err = float((a - b).norm() / a.norm())
+        print('graphed vs eager, step 4 gradient of', k, err)
+        assert err <= 5e-2, (k, err)

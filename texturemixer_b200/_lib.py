@@ -6,7 +6,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'libtmx.so')
 
-TMX_ABI_VERSION = 3
+TMX_ABI_VERSION = 4
 
 # flags / enums (include/tmx.h)
 CONV_LRELU, CONV_RESIDUAL, CONV_UP2_IN, CONV_UP2_OUT, CONV_HALO_REPLICATE, CONV_TORGB, CONV_XMERGE = 1, 2, 4, 8, 16, 32, 64
@@ -108,6 +108,10 @@ _SIGNATURES = {
     'tmx_nonfinite_check': (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     'tmx_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _F, _F, _F, _F, _F, _P, _P, _P]),
     'tmx_ema_update': (C.c_int, [_P, _P, _P, C.c_int64, _F, _P]),
+    'tmx_nonfinite_mark': (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    'tmx_adam_update': (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _F, _F, _F, _F, _F, _P, _P, _P, _P]),
+    'tmx_adam_advance': (C.c_int, [_P, _P, _F, _F, _P, _P, _P]),
+    'tmx_window_copy': (C.c_int, [_P, _P, _P, C.c_int64, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
     'tmx_latent_blend': (C.c_int, [_P, C.POINTER(BlendDesc), C.POINTER(BlendIO), _P]),
     'tmx_perm_indices_from_uniforms': (C.c_int, [C.POINTER(C.c_double), C.c_int64, _I, _I, _I,
                                                   C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),

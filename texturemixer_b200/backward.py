@@ -214,10 +214,7 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
             if contribs:
                 _, g = _combine(rt, rec['y'], contribs, want_planes=False, want_f32=True)
                 x = rec['x']
-                oy, ox, h, w = rec['win']
-                full = torch.zeros(x.n, x.h, x.w, x.c, dtype=torch.float32, device=rt.device)
-                full[:, oy:oy + h, ox:ox + w, :].copy_(g)
-                grads.add(x, ('f32', full))
+                grads.add(x, ('f32', rt.window_embed(g, rec['win'], x.h, x.w, nhwc=True)))
         elif kind == 'imgpool':            # the input image pooled for a lower level of detail (networks.py:278,281)
             g = input_grads.pop(('img', id(rec['y'])), None)
             if g is not None:

@@ -908,3 +908,61 @@ extern "C" int tmx_bias_act(tmx_handle_t h, const float* x, const float* bias, f
   TMX_LAUNCHED(h, "bias_act_kernel");
   return TMX_OK;
 }
+
+
+// ---------------------------------------------------------------- window copy / embed with device-side offsets
+// The crop-aware train step (loss.crop_window / mid_window / tail_window, loss.py:78-90 random_crop) slices fixed-SIZE
+// windows at offsets that change every step.  Reading the offsets from device memory keeps every launch of the step
+// identical from one step to the next, so the whole step can be replayed as CUDA graphs (train.GraphedStep).
+// Tensors are [A][H][W][B] fp32: NCHW -> A = N*C, B = 1; NHWC -> A = N, B = C.
+//   embed == 0: dst[A][wh][ww][B] = src[A][oy + y][ox + x][B]
+//   embed == 1: dst[A][H][W][B]   = src[A][y - oy][x - ox][B] inside the window, 0 elsewhere (adjoint of the slice)
+__global__ void __launch_bounds__(256) window_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int A,
+                                                          int H, int W, int B, int wh, int ww, int oy_h, int ox_h,
+                                                          const int32_t* __restrict__ off_dev, int embed, int vec) {
+  const int oy = off_dev ? __ldg(off_dev) : oy_h, ox = off_dev ? __ldg(off_dev + 1) : ox_h;
+  // one block row = one (a, y) row of the DESTINATION; threads run along x*B (in float4 units when vec)
+  const int rows_h = embed ? H : wh;
+  const int row = blockIdx.x;
+  const int a = row / rows_h, y = row - a * rows_h;
+  const int dw = embed ? W : ww;                          // destination row width in pixels
+  const int unit = vec ? 4 : 1;
+  const int per_row = dw * B / unit;
+  if (!embed) {
+    const float* s = src + (((long long)a * H + oy + y) * W + ox) * B;
+    float* d = dst + ((long long)a * wh + y) * ww * B;
+    for (int i = threadIdx.x; i < per_row; i += blockDim.x) {
+      if (vec) reinterpret_cast<float4*>(d)[i] = __ldg(reinterpret_cast<const float4*>(s) + i);
+      else d[i] = __ldg(s + i);
+    }
+  } else {
+    float* d = dst + ((long long)a * H + y) * W * B;
+    const bool row_in = y >= oy && y < oy + wh;
+    const float* s = src + (((long long)a * wh + (y - oy)) * ww - ox) * B;   // s[x*B + b] valid for x in [ox, ox+ww)
+    const int lo = ox * B / unit, hi = (ox + ww) * B / unit;
+    for (int i = threadIdx.x; i < per_row; i += blockDim.x) {
+      const bool in = row_in && i >= lo && i < hi;
+      if (vec) reinterpret_cast<float4*>(d)[i] = in ? __ldg(reinterpret_cast<const float4*>(s) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      else d[i] = in ? __ldg(s + i) : 0.f;
+    }
+  }
+}
+
+extern "C" int tmx_window_copy(tmx_handle_t h, const float* src, float* dst, int64_t A, int H, int W, int B, int wh,
+                               int ww, int oy, int ox, const int32_t* off_dev, int embed, tmx_stream_t s) {
+  TMX_REQUIRE(h && src && dst, TMX_ERR_ARG, "tmx_window_copy: NULL argument");
+  TMX_REQUIRE(A > 0 && H > 0 && W > 0 && B > 0 && wh > 0 && ww > 0 && wh <= H && ww <= W, TMX_ERR_SHAPE,
+              "tmx_window_copy: bad shape A=%lld H=%d W=%d B=%d window %dx%d", (long long)A, H, W, B, wh, ww);
+  TMX_REQUIRE(off_dev != nullptr || (oy >= 0 && ox >= 0 && oy + wh <= H && ox + ww <= W), TMX_ERR_SHAPE,
+              "tmx_window_copy: window (%d,%d)+%dx%d outside %dx%d", oy, ox, wh, ww, H, W);
+  const long long rows = A * (embed ? H : wh);
+  TMX_REQUIRE(rows < (1ll << 31), TMX_ERR_SHAPE, "tmx_window_copy: too many rows");
+  const int vec = (B % 4 == 0) ? 1 : 0;          // NHWC rows are 16-B aligned at any pixel offset; NCHW are not
+  const int per_row = (embed ? W : ww) * B / (vec ? 4 : 1);
+  int threads = 32;
+  while (threads < 256 && threads < per_row) threads <<= 1;
+  window_copy_kernel<<<(unsigned)rows, threads, 0, (cudaStream_t)s>>>(src, dst, (int)A, H, W, B, wh, ww, oy, ox, off_dev,
+                                                                      embed, vec);
+  TMX_LAUNCHED(h, "window_copy_kernel");
+  return TMX_OK;
+}

@@ -150,21 +150,63 @@ def tail_window(yx, res, lat, win, H, W):
     return oy, ox, h, w
 
 
-def _win(x, win):
-    if win is None:
-        return x
-    oy, ox, wh, ww = win
-    return x[:, :, oy:oy + wh, ox:ox + ww].contiguous()
+class Window(tuple):
+    """(oy, ox, h, w) of a crop-aware window.  `dev` = optional int32 device view {oy, ox}: when set, the kernels
+    read the offset from there instead of baking the host integers into the launch, so that the train step is the
+    same sequence of launches whatever the random_crop offsets are and can replay as CUDA graphs (train.GraphedStep).
+    The SIZE is always static."""
+
+    def __new__(cls, oy, ox, h, w, dev=None):
+        self = super().__new__(cls, (int(oy), int(ox), int(h), int(w)))
+        self.dev = dev
+        return self
 
 
-def _embed(d, win, H, W):
+def plan_crop(yx, res, lat, H, W, crop_aware=True, lod=0.0):
+    """Everything one random_crop of a G_fcn image needs, as host integers: {'win': trunk window of the latent
+    canvas, 'mid': window after the fourth residual block (relative to win), 'tail': window of the up-sampling
+    blocks (relative to win + mid), 'img': (y0, x0, res, res) of the crop inside the decoded image}; windows are
+    None where the whole extent is kept."""
+    win = crop_window(yx, res, lat, H, W) if crop_aware else None
+    mid = tail = None
+    win_abs = win
+    if crop_aware and lod <= 2.0:                  # windows stay aligned to the upscaled low-res pixels
+        mid = mid_window(yx, res, lat, win, H, W)
+        win_abs = compose_window(win, mid, H, W)
+        tail = tail_window(yx, res, lat, win_abs, H, W)
+    y0, x0 = image_offset(yx, res // lat, win_abs, tail)
+    return dict(yx=(int(yx[0]), int(yx[1])), win=win, mid=mid, tail=tail, img=(y0, x0, res, res))
+
+
+PLAN_KEYS = ('win', 'mid', 'tail', 'img')
+
+
+def plan_offsets(plan):
+    """The 8 int32 offsets of a plan in PLAN_KEYS order (0, 0 for an absent window)."""
+    out = []
+    for k in PLAN_KEYS:
+        w = plan[k]
+        out += [0, 0] if w is None else [int(w[0]), int(w[1])]
+    return out
+
+
+def plan_on_device(plan, dev_offsets):
+    """The same plan with `Window`s whose offsets are read from `dev_offsets` (int32 device tensor of 8 values laid
+    out by `plan_offsets`)."""
+    out = dict(yx=plan['yx'])
+    for i, k in enumerate(PLAN_KEYS):
+        w = plan[k]
+        out[k] = None if w is None else Window(w[0], w[1], w[2], w[3], dev=dev_offsets[2 * i:2 * i + 2])
+    return out
+
+
+def _win(rt, x, win):
+    return x if win is None else rt.window(x, win)
+
+
+def _embed(rt, d, win, H, W):
     """Adjoint of `_win`: the window gradient inside a zero canvas."""
-    if win is None:
-        return d
-    oy, ox, wh, ww = win
-    full = torch.zeros(d.shape[0], d.shape[1], H, W, dtype=torch.float32, device=d.device)
-    full[:, :, oy:oy + wh, ox:ox + ww].copy_(d)
-    return full
+    return d if win is None else rt.window_embed(d, win, H, W)
 
 
 def fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, ih_f, iw_f, win, blend=None):
@@ -172,15 +214,15 @@ def fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, ih_f, iw_f, win, blend=None):
     (ih_b, iw_b, t)), restricted to `win`."""
     wh, ww = (H, W) if win is None else win[2:]
     zg_c = _tile_code(rt, zg_mu, wh, ww)
-    zl_c = _win(rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[ih_f], idx_w=[iw_f],
-                                pin_rows=pins[0], pin_cols=pins[1]), win)
+    zl_c = _win(rt, rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[ih_f], idx_w=[iw_f],
+                                    pin_rows=pins[0], pin_cols=pins[1]), win)
     if blend is None:
         return zg_c, zl_c
     ih_b, iw_b, t = blend
     # tf.reverse(axis=[0]) of the sources is folded into the gather (src_reverse)
     zg_r = rt.latent_blend([zg_mu.contiguous()], wh, ww, _lib.BLEND_COPY, src_reverse=1)
-    zl_r = _win(rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[ih_b], idx_w=[iw_b],
-                                pin_rows=pins[0], pin_cols=pins[1], src_reverse=1), win)
+    zl_r = _win(rt, rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[ih_b], idx_w=[iw_b],
+                                    pin_rows=pins[0], pin_cols=pins[1], src_reverse=1), win)
     bzg = rt.latent_blend([zg_r, zg_c], wh, ww, _lib.BLEND_LERP, t=t)      # lerp(reverse, forward, t), loss.py:238
     bzl = rt.latent_blend([zl_r, zl_c], wh, ww, _lib.BLEND_LERP, t=t)
     return bzg, bzl
@@ -200,54 +242,59 @@ def fcn_scale(canvas, lat):
     return dict(scale_h=canvas.shape[2] // lat, scale_w=canvas.shape[3] // lat)
 
 
-def _crop_adjoint(dcrop, full_hw, yx):
+def _crop_adjoint(rt, dcrop, full_hw, img_win):
     """Adjoint of random_crop (loss.py:78-90): zeros outside the window (pure data movement)."""
-    n, c, h, w = dcrop.shape
-    full = torch.zeros(n, c, full_hw[0], full_hw[1], dtype=torch.float32, device=dcrop.device)
-    full[:, :, yx[0]:yx[0] + h, yx[1]:yx[1] + w].copy_(dcrop)
-    return full
+    return rt.window_embed(dcrop, img_win, full_hw[0], full_hw[1])
 
 
 class EGForward:
     """The E/G side of `EG_wgan` run once with tapes: encoders, reconstruction, interpolated and blended canvases.
     Its images depend only on the E/G variables, which do not change between the critic update and the E/G update of
-    one step (run.py:511-512), so the critic phase can reuse `rec` and `interp` as its fakes."""
+    one step (run.py:511-512), so a critic phase on the SAME reals can reuse `rec` as its fake.
+    With `record=False` nothing is taped (the critics' fakes, loss.py:308-320, when their minibatch is not the E/G
+    phase's)."""
 
     def __init__(self, E_zg, E_zl, G, G_fcn, reals, idx, mixing_factors, scale_h=3, scale_w=3, need_interp=True,
-                 need_blend=True, crop_interp=None, crop_blend=None, defer_canvases=False):
+                 need_blend=True, crop_interp=None, crop_blend=None, defer_canvases=False, plans=None, record=True):
         """crop_interp / crop_blend: the (y, x) offsets the E/G loss will crop at; when given, G_fcn decodes only the
         latent window those crops depend on (`crop_window`) - same crop pixels, same gradients, 44 % of the work at
-        the reference's 3x3 canvases.  None decodes the whole canvas."""
+        the reference's 3x3 canvases.  None decodes the whole canvas.  `plans` = {'interp' | 'blend': plan_crop(...)}
+        supplies the windows ready-made (the trainer's: their offsets live in device memory)."""
         rt = self.rt = Runtime.get(reals.device)
         self.nets = (E_zg, E_zl, G, G_fcn)
         self.reals, self.scale = reals, (scale_h, scale_w)
-        self.n = n = reals.shape[0]
+        self.n = reals.shape[0]
         res = reals.shape[2]
-        self.t_zg, self.t_zl, self.t_rec, self.t_int, self.t_bl = [], [], [], [], []
+        tape = (lambda: []) if record else (lambda: None)
+        self.t_zg, self.t_zl, self.t_rec, self.t_int, self.t_bl = tape(), tape(), tape(), tape(), tape()
         self.zg_mu, self.zg_ls = E_zg.get_output_for(reals, tape=self.t_zg)
         self.zl_mu, self.zl_ls = E_zl.get_output_for(reals, tape=self.t_zl)
         _sink('E_zg', E_zg, self.t_zg)
         _sink('E_zl', E_zl, self.t_zl)
         zg_mu, zl_mu = self.zg_mu, self.zl_mu
-        self.c, self.lat = c, lat = zl_mu.shape[1], zl_mu.shape[2]
+        self.c, self.lat = zl_mu.shape[1], zl_mu.shape[2]
+        lat = self.lat
         self.H, self.W = H, W = lat * scale_h, lat * scale_w
-        self.pins = pins = interp._corner_pins(scale_h, scale_w)
+        self.pins = interp._corner_pins(scale_h, scale_w)
         self.rec = G.get_output_for(_tile_code(rt, zg_mu, lat, lat), zl_mu, tape=self.t_rec)
         _sink('G_rec', G, self.t_rec)
         self.interp = self.blend = None
-        self.win = {'interp': None if crop_interp is None else crop_window(crop_interp, res, lat, H, W),
-                    'blend': None if crop_blend is None else crop_window(crop_blend, res, lat, H, W)}
-        self.planned = {'interp': crop_interp, 'blend': crop_blend}
-        self.mid = {k: None if c is None else mid_window(c, res, lat, self.win[k], H, W)
-                    for k, c in (('interp', crop_interp), ('blend', crop_blend))}
-        self.tail = {k: None if c is None else
-                     tail_window(c, res, lat, compose_window(self.win[k], self.mid[k], H, W), H, W)
-                     for k, c in (('interp', crop_interp), ('blend', crop_blend))}
+        plans = dict(plans or {})
+        for k, yx in (('interp', crop_interp), ('blend', crop_blend)):
+            if k not in plans:
+                plans[k] = plan_crop((0, 0) if yx is None else yx, res, lat, H, W, crop_aware=yx is not None,
+                                     lod=G_fcn.lod)
+                if yx is None:
+                    plans[k]['yx'] = None        # whole canvas decoded: any crop may be taken from it
+        self.plans = plans
+        self.win = {k: plans[k]['win'] for k in plans}
+        self.mid = {k: plans[k]['mid'] for k in plans}
+        self.tail = {k: plans[k]['tail'] for k in plans}
         self._need = (need_interp, need_blend)
         if need_interp or need_blend:
             self.ih_f, self.iw_f = _dev_idx(rt, idx['h_forward']), _dev_idx(rt, idx['w_forward'])
-        if need_blend:
             self.ih_b, self.iw_b = _dev_idx(rt, idx['h_backward']), _dev_idx(rt, idx['w_backward'])
+        if need_blend:
             self.t = mixing_factors.reshape(-1).contiguous()
         if not defer_canvases:
             self.decode_canvases()
@@ -271,44 +318,42 @@ class EGForward:
                                               tail_window=self.tail['blend'], **fcn_scale(bzl, lat))
             _sink('G_blend', G_fcn, self.t_bl)
 
-    def window_offset(self, which, yx):
-        """Pixel offset of crop `yx` inside the decoded image of `which` (== yx when the whole canvas was decoded)."""
-        win, tail = compose_window(self.win[which], self.mid[which], self.H, self.W), self.tail[which]
-        if win is None and tail is None:
-            return yx
-        if tuple(yx) != tuple(self.planned[which]):
+    def image_window(self, which, yx):
+        """(y0, x0, res, res) of crop `yx` inside the decoded image of `which` (== yx when the whole canvas was
+        decoded); carries the device offset when the plan does."""
+        plan = self.plans[which]
+        res = self.reals.shape[2]
+        if plan['yx'] is None:
+            return Window(yx[0], yx[1], res, res)
+        if tuple(yx) != tuple(plan['yx']):
             raise ValueError('%s was decoded for the crop at %r only (crop-aware G_fcn); asked for %r'
-                             % (which, self.planned[which], yx))
-        return image_offset(yx, self.reals.shape[2] // self.lat, win, tail)
+                             % (which, plan['yx'], yx))
+        return plan['img']
+
+    def window_offset(self, which, yx):
+        """Pixel offset (host integers) of crop `yx` inside the decoded image of `which`."""
+        return tuple(self.image_window(which, yx)[:2])
 
     def crop(self, which, yx):
         img = self.interp if which == 'interp' else self.blend
-        res = self.reals.shape[2]
-        y0, x0 = self.window_offset(which, yx)
-        return img[:, :, y0:y0 + res, x0:x0 + res].contiguous()
+        return self.rt.window(img, self.image_window(which, yx))
 
 
-def fcn_fake(G_fcn, fwd, which, yx, mix=None, crop_aware=True):
+def fcn_fake(G_fcn, fwd, which, yx, mix=None, crop_aware=True, plan=None):
     """Fake images of the canvas critics (no tape): the crop at `yx` of G_fcn's image of the interpolated (`which` =
     'interp', loss.py:391-395) or blended ('blend', loss.py:466-495) canvas built from the codes of `fwd`, decoding
     only the latent window the crop depends on (`crop_window`).  D_blend_wgangp draws its own mixing factors
     (loss.py:489), D_interp_wgangp its own crop offset (loss.py:395): neither can reuse the E/G images once those
-    are decoded crop-aware."""
+    are decoded crop-aware.  `plan` = plan_crop(yx, ...) ready-made (device-resident offsets)."""
     rt = fwd.rt
     res = fwd.reals.shape[2]
-    win = crop_window(yx, res, fwd.lat, fwd.H, fwd.W) if crop_aware else None
+    if plan is None:
+        plan = plan_crop(yx, res, fwd.lat, fwd.H, fwd.W, crop_aware=crop_aware, lod=G_fcn.lod)
     blend = None if which == 'interp' else (fwd.ih_b, fwd.iw_b, mix.reshape(-1).contiguous())
-    zg_c, zl_c = fcn_canvases(rt, fwd.zg_mu, fwd.zl_mu, fwd.H, fwd.W, fwd.pins, fwd.ih_f, fwd.iw_f, win, blend)
-    mid = tail = None
-    if crop_aware and G_fcn.lod <= 2.0:
-        mid = mid_window(yx, res, fwd.lat, win, fwd.H, fwd.W)
-        win_abs = compose_window(win, mid, fwd.H, fwd.W)
-        tail = tail_window(yx, res, fwd.lat, win_abs, fwd.H, fwd.W)
-    else:
-        win_abs = win
-    y0, x0 = image_offset(yx, res // fwd.lat, win_abs, tail)
-    img = G_fcn.get_output_for(zg_c, zl_c, mid_window=mid, tail_window=tail, **fcn_scale(zl_c, fwd.lat))
-    return img[:, :, y0:y0 + res, x0:x0 + res].contiguous()
+    zg_c, zl_c = fcn_canvases(rt, fwd.zg_mu, fwd.zl_mu, fwd.H, fwd.W, fwd.pins, fwd.ih_f, fwd.iw_f, plan['win'], blend)
+    img = G_fcn.get_output_for(zg_c, zl_c, mid_window=plan['mid'], tail_window=plan['tail'],
+                               **fcn_scale(zl_c, fwd.lat))
+    return rt.window(img, plan['img'])
 
 
 def critic_input_gradient(D, images, weight):
@@ -356,16 +401,16 @@ def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, r
     if interp_G_weight > 0:
         report['interp_G'], dcr = cg['interp'] if 'interp' in cg else \
             critic_input_gradient(D_interp, fwd.crop('interp', crop_interp), interp_G_weight)
-        dzg_c, dzl_c = backward(G_fcn, fwd.t_int, [_crop_adjoint(dcr, fwd.interp.shape[2:],
-                                                                 fwd.window_offset('interp', crop_interp))], grads['G'])
+        dzg_c, dzl_c = backward(G_fcn, fwd.t_int, [_crop_adjoint(rt, dcr, fwd.interp.shape[2:],
+                                                                 fwd.image_window('interp', crop_interp))], grads['G'])
         _row_sum(rt, dzg_c, n * c, dzg_c.shape[2] * dzg_c.shape[3], out=dzg, accumulate=True)
-        _gather_bwd(rt, _embed(dzl_c, fwd.win['interp'], H, W), dzl, fwd.ih_f, fwd.iw_f, pins)
+        _gather_bwd(rt, _embed(rt, dzl_c, fwd.win['interp'], H, W), dzl, fwd.ih_f, fwd.iw_f, pins)
     if blend_interp_G_weight > 0:
         t = fwd.t
         report['blend_G'], dcr = cg['blend'] if 'blend' in cg else \
             critic_input_gradient(D_blend, fwd.crop('blend', crop_blend), blend_interp_G_weight)
-        dbzg, dbzl = backward(G_fcn, fwd.t_bl, [_crop_adjoint(dcr, fwd.blend.shape[2:],
-                                                              fwd.window_offset('blend', crop_blend))], grads['G'])
+        dbzg, dbzl = backward(G_fcn, fwd.t_bl, [_crop_adjoint(rt, dcr, fwd.blend.shape[2:],
+                                                              fwd.image_window('blend', crop_blend))], grads['G'])
         zero_c = torch.zeros_like(dbzg)
         win = fwd.win['blend']
         wh, ww = dbzg.shape[2:]
@@ -378,8 +423,8 @@ def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, r
                 tmp = _row_sum(rt, d_rev, n * c, wh * ww).view(n, c, 1, 1)
                 _gather_bwd(rt, tmp, dzg.view(n, c, 1, 1), None, None, (0, 0), reverse=True)
             else:
-                _gather_bwd(rt, _embed(d_fwd, win, H, W), dzl, fwd.ih_f, fwd.iw_f, pins)
-                _gather_bwd(rt, _embed(d_rev, win, H, W), dzl, fwd.ih_b, fwd.iw_b, pins, reverse=True)
+                _gather_bwd(rt, _embed(rt, d_fwd, win, H, W), dzl, fwd.ih_f, fwd.iw_f, pins)
+                _gather_bwd(rt, _embed(rt, d_rev, win, H, W), dzl, fwd.ih_b, fwd.iw_b, pins, reverse=True)
     dzl_ls = dzg_ls = None
     dzg = dzg.view(n, c, 1, 1)
     if kl_weight > 0:                                                     # loss.py:163-171

@@ -275,15 +275,16 @@ def _upscale_image(rt, img, factor):
 
 
 def _window(t, win):
-    """[n, oy:oy+h, ox:ox+w, :] of a run-mode handle's feature map as a new activation (recorded on the tape)."""
+    """[n, oy:oy+h, ox:ox+w, :] of a run-mode handle's feature map as a new activation (recorded on the tape).  The
+    offset may live in device memory (loss.Window.dev) so that the launch does not change from step to step."""
     ctx = t.ctx
     oy, ox, h, w = win
     a = ctx.rt.split_unpack(_act_of(t))
-    if oy < 0 or ox < 0 or oy + h > a.h or ox + w > a.w:
-        raise ValueError('tail_window %r outside the %dx%d feature map' % (win, a.h, a.w))
-    out = Act(a.n, h, w, a.c, f32=a.f32[:, oy:oy + h, ox:ox + w, :].contiguous())
+    if getattr(win, 'dev', None) is None and (oy < 0 or ox < 0 or oy + h > a.h or ox + w > a.w):
+        raise ValueError('tail_window %r outside the %dx%d feature map' % (tuple(win), a.h, a.w))
+    out = Act(a.n, h, w, a.c, f32=ctx.rt.window(a.f32, win, nhwc=True))
     if ctx.tape is not None:
-        ctx.tape.append(dict(kind='window', x=a, y=out, win=(oy, ox, h, w)))
+        ctx.tape.append(dict(kind='window', x=a, y=out, win=win))
     return T([t.shape[0], t.shape[1], h, w], ctx, act=out)
 
 
@@ -570,7 +571,10 @@ def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_bas
         the ToRGB head + tanh (fused into the epilogue)."""
         if res < resolution_log2:
             ntc = _tc(ctx, nf(res - 1), nf(res), 3, up2=True)
-            return conv2d_layer(x, nf(res - 1), 3, next_tc=ntc, next_up2=ntc)
+            # a windowed output (crop-aware step) is cut from the exact fp32 map: re-splitting hi + lo is not
+            # idempotent at rounding ties, and window / whole-canvas evaluations must stay bit-identical
+            return conv2d_layer(x, nf(res - 1), 3, next_tc=ntc, next_up2=ntc,
+                                keep_f32=res == latent_res_log2 and tail_window is not None)
         head = None
         if ctx.mode == 'run' and lod_in == 0 and not use_pixelnorm and nf(res - 1) in (16, 32) and \
                 _tc(ctx, nf(res - 1), nf(res - 1), 3):

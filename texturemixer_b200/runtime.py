@@ -71,7 +71,7 @@ class Runtime:
         self.sm_count, self.cc = sm.value, (major.value, minor.value)
         # kernel selection override for tests/benchmarks: auto | ffma | tc | tc_k32
         self.conv_algo = os.environ.get('TMX_CONV_ALGO', 'auto')
-        # bench.py: CUDA events around each conv launch -> [(tag, start, end)], tag = (algo, k, cin, cout)
+        # bench.py: CUDA events around each conv launch -> [(tag, start, end)], tag = (algo, k, cin, cout, h, w)
         self.profile_kernels = False
         self.kernel_events = []
 
@@ -258,7 +258,7 @@ class Runtime:
         _lib.check(self.lib.tmx_conv2d_fwd(self.handle, C.byref(d), C.byref(io), self.stream()), 'tmx_conv2d_fwd')
         if self.profile_kernels:
             e1.record()
-            self.kernel_events.append((('ffma' if algo == _lib.ALGO_FFMA else 'tc', k, cin, cout), e0, e1))
+            self.kernel_events.append((('ffma' if algo == _lib.ALGO_FFMA else 'tc', k, cin, cout, x.h, x.w), e0, e1))
         if want_split and out.hi is None:
             self.split_pack(out, halo_out)
         return (out, images) if torgb is not None else out
@@ -382,6 +382,38 @@ class Runtime:
         out = Act(x.n, x.h, x.w, x.c, f32=self.empty(x.n, x.h, x.w, x.c))
         _lib.check(self.lib.tmx_bias_act(self.handle, _ptr(x.f32), _ptr(bias), _ptr(out.f32), x.n * x.h * x.w, x.c,
                                          int(lrelu), LRELU_ALPHA, self.stream()), 'tmx_bias_act')
+        return out
+
+    # ------------------------------------------------------------------ windows (crop-aware train step)
+    def window(self, x, win, nhwc=False):
+        """x[..., oy:oy+h, ox:ox+w] (NCHW) or x[:, oy:oy+h, ox:ox+w, :] (NHWC) as a new contiguous tensor.  `win` =
+        (oy, ox, h, w); when it carries a `.dev` int32 device view {oy, ox} the kernel reads the offset from there
+        (identical launch every step -> CUDA-graph replay, see loss.Window)."""
+        oy, ox, h, w = win
+        if nhwc:
+            n, H, W, c = x.shape
+            A, B, out = n, c, self.empty(n, h, w, c)
+        else:
+            n, c, H, W = x.shape
+            A, B, out = n * c, 1, self.empty(n, c, h, w)
+        dev = getattr(win, 'dev', None)
+        _lib.check(self.lib.tmx_window_copy(self.handle, _ptr(x.contiguous()), _ptr(out), A, H, W, B, h, w, int(oy),
+                                            int(ox), _ptr(dev), 0, self.stream()), 'tmx_window_copy')
+        return out
+
+    def window_embed(self, d, win, H, W, nhwc=False):
+        """Adjoint of `window`: `d` placed at the window's offset inside a zero [.., H, W] tensor."""
+        oy, ox, h, w = win
+        if nhwc:
+            n, dh, dw, c = d.shape
+            A, B, out = n, c, self.empty(n, H, W, c)
+        else:
+            n, c, dh, dw = d.shape
+            A, B, out = n * c, 1, self.empty(n, c, H, W)
+        assert (dh, dw) == (h, w), ((dh, dw), tuple(win))
+        dev = getattr(win, 'dev', None)
+        _lib.check(self.lib.tmx_window_copy(self.handle, _ptr(d.contiguous()), _ptr(out), A, H, W, B, h, w, int(oy),
+                                            int(ox), _ptr(dev), 1, self.stream()), 'tmx_window_copy')
         return out
 
     # ------------------------------------------------------------------ latent blend

@@ -23,7 +23,7 @@ import torch
 
 from . import _lib, interp, loss, parallel
 from .network import Network
-from .optim import Optimizer
+from .optim import GradientBucket, Optimizer
 from .runtime import Runtime
 
 NET_FUNCS = dict(E_zg='networks.E_zg', E_zl='networks.E_zl', G='networks.G_res', D_rec='networks.D_patch',
@@ -44,7 +44,8 @@ def default_config(train_size=128, fmap_base=1024, fmap_max=512, latent_channels
         D_interp=dict(fmap_base=fmap_base, fmap_max=fmap_max, latent_res=-1),
         D_blend=dict(fmap_base=fmap_base, fmap_max=fmap_max, latent_res=-1),
         opt=dict(beta1=0.0, beta2=0.99, epsilon=1e-8), lrate=0.0015, ema_beta=0.999,
-        cuda_graphs=True,     # the three critic evaluations replay as CUDA graphs (GraphedCritic)
+        cuda_graphs='step',   # 'step': the whole step replays as CUDA graphs (Trainer._capture_step); 'critics': only
+        #                       the critic evaluations (GraphedCritic); False: every launch from Python
         crop_aware=True,      # G_fcn decodes only the latent window each random_crop depends on (loss.crop_window)
         loss=dict(rec_G_weight=1.0, pixel_weight=200.0, interp_G_weight=1.0, blend_interp_G_weight=1.0),
         levels=int(np.log2(latent_res)))
@@ -190,8 +191,27 @@ class GraphedCriticGradient(GraphedCritic):
         return self.report
 
 
+CROP_KEYS = ('eg_crop_interp', 'eg_crop_blend', 'd_interp_crop', 'd_blend_crop')
+MIX_KEYS = ('eg_mix', 'd_rec_gp', 'd_interp_gp', 'd_blend_mix', 'd_blend_gp')
+IDX_KEYS = ('h_forward', 'w_forward', 'h_backward', 'w_backward')
+
+
+class _StepGraph:
+    """One captured train step: static input buffers, the replay program (CUDA graphs separated by the gradient
+    all-reduces when the job has more than one rank) and the static report tensors."""
+    __slots__ = ('reals', 'packed', 'mixes', 'draws', 'program', 'report', 'launches', 'pool', 'keep')
+
+
 class Trainer:
-    """Owns the nine networks, the four optimizers and the per-network flat gradient buffers of one rank."""
+    """Owns the nine networks, the four optimizers and the two gradient buckets (critic phase, E/G phase) of one
+    rank.
+
+    Host side of a step (`cuda_graphs='step'`, the default): the FIRST step of a given shape runs eagerly (it also
+    loads every kernel), the second one is captured - the whole of run.py:511-513 as one CUDA graph, or three when
+    the job has several ranks (cut at the two gradient all-reduces, which stay ordinary NCCL calls) - and every
+    later step is: sample the permutations on the host, five small copies into the graph's static buffers, replay.
+    What makes the step capturable although `random_crop` moves every step: window SIZES are static, window OFFSETS
+    are read by the kernels from device memory (loss.Window, tmx_window_copy)."""
 
     def __init__(self, config=None, seed=1000, device=None):
         self.cfg = config or default_config()
@@ -210,28 +230,38 @@ class Trainer:
         for src, dst in (('E_zg', 'Es_zg'), ('E_zl', 'Es_zl'), ('G', 'Gs')):       # run.py:270-272
             self.nets[dst] = self.nets[src].clone(dst)
             self.ema[dst] = self.nets[dst].setup_as_moving_average_of(self.nets[src], beta=c['ema_beta'])
-        self.grads = {k: torch.zeros_like(self.nets[k].flat) for k in NET_FUNCS}
+        # one flat gradient bucket per optimizer phase = ONE all-reduce per session.run of run.py:511-512
+        self.buckets = {'D': GradientBucket({k: self.nets[k] for k in ('D_rec', 'D_interp', 'D_blend')}),
+                        'EG': GradientBucket({k: self.nets[k] for k in ('E_zg', 'E_zl', 'G')})}
+        self.grads = dict(self.buckets['D'].views)
+        self.grads.update(self.buckets['EG'].views)
         self.opts = {}
-        for name, members in (('EG', ('E_zg', 'E_zl', 'G')), ('D_rec', ('D_rec',)), ('D_interp', ('D_interp',)),
-                              ('D_blend', ('D_blend',))):                           # run.py:297-300
+        for name, members, bucket in (('EG', ('E_zg', 'E_zl', 'G'), 'EG'), ('D_rec', ('D_rec',), 'D'),
+                                      ('D_interp', ('D_interp',), 'D'), ('D_blend', ('D_blend',), 'D')):   # run.py:297-300
             opt = Optimizer(name='Train' + name, learning_rate=c['lrate'], **c['opt'])
             for m in members:
                 opt.register_gradients(self.nets[m], self.grads[m])
+            opt.use_bucket(self.buckets[bucket])
             self.opts[name] = opt
-        # CUDA graphs of the three critic evaluations (cfg['cuda_graphs'], TMX_NO_GRAPH=1 turns them off)
         self.graph_pool = None
         self._critic_graphs = {}
         self._critic_streams = [torch.cuda.Stream(device=self.rt.device) for _ in range(3)]
         self.graph_launches = 0       # kernels replayed from graphs (libtmx counts launches at capture time only)
+        self._step_graphs = {}
+        self._warm = set()
+        self.allreduce_events = []    # (start, end) CUDA events around the phase all-reduces when `time_collectives`
+        self.time_collectives = False
 
     # ------------------------------------------------------------------ host-side random draws of one step
     def sample_draws(self, minibatch, rng, uniform=None):
         """Permutation index vectors (run.py:436-507, same np.random stream as the reference when `uniform` is None)
         plus the graph's own random ops made explicit: one crop offset per loss that crops (loss.py:78-90) and the
-        per-sample mixing factors (loss.py:237,329,405,489,505)."""
+        per-sample mixing factors (loss.py:237,329,405,489,505); and, derived from the crop offsets, the crop-aware
+        window plans (loss.plan_crop) whose offsets travel to the device with the index vectors."""
         c = self.cfg
         idx = interp.sample_schedule_indices(minibatch, c['latent_res'], c['scale_h'], c['scale_w'], c['levels'], uniform)
-        res = c['resolution']
+        res, lat = c['resolution'], c['latent_res']
+        H, W = lat * c['scale_h'], lat * c['scale_w']
         hi_y, hi_x = res * c['scale_h'] - res, res * c['scale_w'] - res
 
         def crop():
@@ -239,25 +269,39 @@ class Trainer:
 
         # every random draw of the step crosses to the device in two page-locked, non-blocking copies: a pageable
         # `.to(device)` per tensor would stall the host behind all queued kernels nine times per step
-        mix_names = ('eg_mix', 'd_rec_gp', 'd_interp_gp', 'd_blend_mix', 'd_blend_gp')
-        mixes = torch.from_numpy(rng.uniform(0.0, 1.0, (len(mix_names), minibatch, 1, 1, 1)).astype(np.float32))
-        idx_names = ('h_forward', 'w_forward', 'h_backward', 'w_backward')
-        packed = torch.from_numpy(np.concatenate([idx[k].reshape(-1) for k in idx_names]).astype(np.int32))
+        mixes = torch.from_numpy(rng.uniform(0.0, 1.0, (len(MIX_KEYS), minibatch, 1, 1, 1)).astype(np.float32))
+        crops = {k: crop() for k in CROP_KEYS}
+        lod = self.nets['G'].lod
+        plans = {k: loss.plan_crop(crops[k], res, lat, H, W, crop_aware=c.get('crop_aware', True), lod=lod)
+                 for k in CROP_KEYS}
+        offsets = np.array([v for k in CROP_KEYS for v in loss.plan_offsets(plans[k])], np.int32)
+        packed = torch.from_numpy(np.concatenate([idx[k].reshape(-1).astype(np.int32) for k in IDX_KEYS] + [offsets]))
         if self.rt.device.type == 'cuda':
             mixes = mixes.pin_memory().to(self.rt.device, non_blocking=True)
             packed = packed.pin_memory().to(self.rt.device, non_blocking=True)
+        out = dict(idx=idx, crops=crops, host_plans=plans, _packed=packed, _mixes=mixes)
+        out.update(crops)
+        out.update(self._draw_views(idx, plans, packed, mixes))
+        return out
+
+    @staticmethod
+    def _draw_views(idx, plans, packed, mixes):
+        """Device views of one step's draws inside the `packed` int32 / `mixes` fp32 buffers."""
         idx_dev, off = {}, 0
-        for k in idx_names:
+        for k in IDX_KEYS:
             idx_dev[k] = packed[off:off + idx[k].size].view(idx[k].shape)
             off += idx[k].size
-        out = dict(idx=idx, idx_dev=idx_dev, eg_crop_interp=crop(), eg_crop_blend=crop(), d_interp_crop=crop(),
-                   d_blend_crop=crop())
-        out.update({k: mixes[i] for i, k in enumerate(mix_names)})
+        dev_plans = {}
+        for k in CROP_KEYS:
+            dev_plans[k] = loss.plan_on_device(plans[k], packed[off:off + 8])
+            off += 8
+        out = dict(idx_dev=idx_dev, plans=dev_plans)
+        out.update({k: mixes[i] for i, k in enumerate(MIX_KEYS)})
         return out
 
     # ------------------------------------------------------------------ fake images of the canvas critics (no tape)
-    def _fcn_fake(self, fwd, which, yx, mix=None):
-        return loss.fcn_fake(self.G_fcn, fwd, which, yx, mix, crop_aware=self.cfg.get('crop_aware', True))
+    def _fcn_fake(self, fwd, which, yx, mix=None, plan=None):
+        return loss.fcn_fake(self.G_fcn, fwd, which, yx, mix, crop_aware=self.cfg.get('crop_aware', True), plan=plan)
 
     def _critic(self, name, n):
         key = (name, n, self.nets[name].lod)
@@ -267,116 +311,274 @@ class Trainer:
         self.graph_launches += g.launches
         return g
 
-    def _eg_critic_gradients(self, fwd, draws):
-        """The three adversarial terms of the E/G loss (post-step critics as fixed functions): graphs on three
-        streams, joined before the generator's backward consumes their image gradients."""
+    def _fork_join(self, jobs):
+        """Run the callables of `jobs` on the three side streams, forked from and joined to the current stream.
+        The critics are independent of each other: their many small, latency-bound kernels (8x8 / 4x4 maps, dense
+        head) overlap instead of queueing behind each other.  Works eagerly and under stream capture."""
+        main = torch.cuda.current_stream(self.rt.device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        results, joins = [], []
+        for i, job in enumerate(jobs):
+            side = self._critic_streams[i % len(self._critic_streams)]
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                results.append(job())
+            done = torch.cuda.Event()
+            done.record(side)
+            joins.append(done)
+
+        def join():
+            for done in joins:
+                main.wait_event(done)
+        return results, join
+
+    def _eg_critic_gradients(self, fwd, draws, use_graphs):
+        """The three adversarial terms of the E/G loss (post-step critics as fixed functions) on three streams,
+        joined before the generator's backward consumes their image gradients."""
         w = self.cfg['loss']
         jobs = (('rec', 'D_rec', w['rec_G_weight'], lambda: fwd.rec),
                 ('interp', 'D_interp', w['interp_G_weight'], lambda: fwd.crop('interp', draws['eg_crop_interp'])),
                 ('blend', 'D_blend', w['blend_interp_G_weight'], lambda: fwd.crop('blend', draws['eg_crop_blend'])))
         jobs = [(key, name, wt, img()) for key, name, wt, img in jobs if wt > 0]
-        main = torch.cuda.current_stream(self.rt.device)
-        graphs = []
-        for key, name, wt, img in jobs:
-            gkey = (name, 'input', img.shape[0], self.nets[name].lod, float(wt))
-            g = self._critic_graphs.get(gkey)
-            if g is None:
-                g = self._critic_graphs[gkey] = GraphedCriticGradient(self, name, img.shape[0], float(wt))
-            self.graph_launches += g.launches
-            graphs.append(g)
-        fork = torch.cuda.Event()
-        fork.record(main)
-        out, joins = {}, []
-        for i, ((key, name, wt, img), g) in enumerate(zip(jobs, graphs)):
-            side = self._critic_streams[i]
-            side.wait_event(fork)
-            with torch.cuda.stream(side):
-                out[key] = g(img)
-            done = torch.cuda.Event()
-            done.record(side)
-            joins.append(done)
-        for done in joins:
-            main.wait_event(done)
+
+        def make(key, name, wt, img):
+            if use_graphs:
+                gkey = (name, 'input', img.shape[0], self.nets[name].lod, float(wt))
+                g = self._critic_graphs.get(gkey)
+                if g is None:
+                    g = self._critic_graphs[gkey] = GraphedCriticGradient(self, name, img.shape[0], float(wt))
+                self.graph_launches += g.launches
+                return lambda: g(img)
+            return lambda: loss.critic_input_gradient(self.nets[name], img, float(wt))
+        results, join = self._fork_join([make(*j) for j in jobs])
+        join()
         self._eg_inputs = [j[3] for j in jobs]      # keep the crops alive until the next step (read on side streams)
-        return out
+        return {j[0]: r for j, r in zip(jobs, results)}
 
     # ------------------------------------------------------------------ one step
-    def step(self, reals, draws, lrate=None, phases=('D', 'EG', 'EMA'), lod=None, reals_orig=None):
+    def step(self, reals, draws, lrate=None, phases=('D', 'EG', 'EMA'), lod=None, reals_orig=None, reals_d=None,
+             reals_d_orig=None):
         """reals: this rank's share [n,3,R,R] fp32 in [-1,1] on the device (`reals_fade` of run.py:311; `reals_orig`
         - what the encoders see, loss.py:119,126 - defaults to the same tensor, which is exact at integer lod).
+        reals_d: the minibatch of the CRITIC phase.  In the reference `reals` is the dataset iterator's get_next()
+        inside the graph (run.py:286), so the critic session.run (run.py:511) and the E/G session.run (:512) each
+        consume a fresh minibatch: pass both to train like the reference.  None = the critics see the E/G phase's
+        minibatch (then one E/G forward serves both phases - 3 % fewer FLOPs, other training dynamics).
         lod: level of detail assigned to all networks before the losses run (run.py:310); None keeps theirs.
-        Returns the loss-term report.
-        Order of run.py:511-513: critics see the pre-step E/G; E/G see the post-step critics; then EMA.  The E/G
-        forward is evaluated ONCE (its variables do not change in between) and serves both phases."""
-        report = {}
+        Returns the loss-term report (device scalars; with CUDA graphs they are the graph's static outputs: read
+        them before the next step).
+        Order of run.py:511-513: critics see the pre-step E/G; E/G see the post-step critics; then EMA."""
         c = self.cfg
         if lod is not None:
             for name in NET_FUNCS:
                 self.nets[name].set_lod(lod)
         lod_now = self.nets['G'].lod
-        ca = c.get('crop_aware', True) and lod_now <= 2.0      # windows stay aligned to the upscaled low-res pixels
+        lrate = float(self.opts['EG'].learning_rate if lrate is None else lrate)
         reals_fade = reals
-        reals = reals if reals_orig is None else reals_orig
-        fwd = loss.EGForward(self.nets['E_zg'], self.nets['E_zl'], self.nets['G'], self.G_fcn, reals, draws.get('idx_dev', draws['idx']),
-                             draws['eg_mix'], c['scale_h'], c['scale_w'],
-                             crop_interp=draws['eg_crop_interp'] if ca else None,
-                             crop_blend=draws['eg_crop_blend'] if ca else None, defer_canvases=True)
-        graphs = c.get('cuda_graphs', True) and not os.environ.get('TMX_NO_GRAPH') and lod_now == int(lod_now)
-        shared = fwd.win['interp'] is None and fwd.tail['interp'] is None and fwd.mid['interp'] is None   # whole canvas
-        overlap = graphs and 'D' in phases and not shared
-        if not overlap:
-            fwd.decode_canvases()
+        reals_orig = reals if reals_orig is None else reals_orig
+        if reals_d is None:
+            d_fade, d_orig = reals_fade, reals_orig
+        else:
+            d_fade, d_orig = reals_d, (reals_d if reals_d_orig is None else reals_d_orig)
+        mode = c.get('cuda_graphs', True)
+        mode = 'step' if mode is True else mode
+        if os.environ.get('TMX_NO_GRAPH') or lod_now != int(lod_now):
+            mode = None      # (a fractional lod changes every step and is baked into the launches)
+        if os.environ.get('TMX_GRAPH_MODE'):
+            mode = os.environ['TMX_GRAPH_MODE']
+        if mode == 'step' and 'plans' in draws:
+            return self._step_graphed(reals_fade, reals_orig, d_fade, d_orig, draws, lrate, tuple(phases), lod_now)
+        return self._step_body(reals_fade, reals_orig, d_fade, d_orig, draws, lrate, phases,
+                               critic_graphs=(mode == 'critics'))
+
+    def _allreduce(self, name):
+        b = self.buckets[name]
+        if self.time_collectives and parallel.world_size() > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            b.allreduce()
+            e1.record()
+            self.allreduce_events.append((name, e0, e1))
+        else:
+            b.allreduce()
+
+    def _step_body(self, reals_fade, reals_orig, d_fade, d_orig, draws, lrate, phases, critic_graphs=False,
+                   boundary=None):
+        """The launches of one step.  `boundary(name)`: where the all-reduce of gradient bucket `name` goes (default:
+        issue it; the graph capture cuts the step there)."""
+        boundary = boundary or self._allreduce
+        report = {}
+        c = self.cfg
+        nets = self.nets
+        n = reals_orig.shape[0]
+        idx = draws.get('idx_dev', draws['idx'])
+        plans = draws.get('plans')
+        if plans is None:        # draws made by hand: host plans
+            res, lat = c['resolution'], c['latent_res']
+            plans = {k: loss.plan_crop(draws[k], res, lat, lat * c['scale_h'], lat * c['scale_w'],
+                                       crop_aware=c.get('crop_aware', True), lod=nets['G'].lod) for k in CROP_KEYS}
+        shared = d_orig is reals_orig and d_fade is reals_fade
+
+        def eg_forward():
+            return loss.EGForward(nets['E_zg'], nets['E_zl'], nets['G'], self.G_fcn, reals_orig, idx, draws['eg_mix'],
+                                  c['scale_h'], c['scale_w'], defer_canvases=True,
+                                  plans={'interp': plans['eg_crop_interp'], 'blend': plans['eg_crop_blend']})
+        fwd = None
         if 'D' in phases:
             if shared:
-                fake_interp = fwd.crop('interp', draws['d_interp_crop'])
+                fwd = fwd_d = eg_forward()
+            else:        # the critics' own minibatch: encoders + reconstruction without tapes (loss.py:308-320)
+                fwd_d = loss.EGForward(nets['E_zg'], nets['E_zl'], nets['G'], self.G_fcn, d_orig, idx, draws['eg_mix'],
+                                       c['scale_h'], c['scale_w'], defer_canvases=True, record=False,
+                                       plans={'interp': plans['d_interp_crop'], 'blend': plans['d_blend_crop']})
+            fakes = (('D_rec', fwd_d.rec, 'd_rec_gp'),
+                     ('D_interp', self._fcn_fake(fwd_d, 'interp', draws['d_interp_crop'], plan=plans['d_interp_crop']),
+                      'd_interp_gp'),
+                     ('D_blend', self._fcn_fake(fwd_d, 'blend', draws['d_blend_crop'], draws['d_blend_mix'],
+                                                plan=plans['d_blend_crop']), 'd_blend_gp'))
+            if critic_graphs:
+                self.buckets['D'].marks.zero_()      # (each critic graph zeroes its own gradient view)
             else:
-                fake_interp = self._fcn_fake(fwd, 'interp', draws['d_interp_crop'])
-            fakes = (('D_rec', fwd.rec, 'd_rec_gp'), ('D_interp', fake_interp, 'd_interp_gp'),
-                     ('D_blend', self._fcn_fake(fwd, 'blend', draws['d_blend_crop'], draws['d_blend_mix']), 'd_blend_gp'))
-            # (a fractional lod changes every step and is baked into the launches: graphs only at integer lod)
-            if graphs:
-                # the three critic graphs are independent: replay them on three streams so that their many small,
-                # latency-bound kernels (8x8 / 4x4 maps, dense head) overlap instead of queueing behind each other
-                main = torch.cuda.current_stream(self.rt.device)
-                fork = torch.cuda.Event()
-                fork.record(main)
-                joins = []
-                for i, (name, fake, gp) in enumerate(fakes):
-                    critic = self._critic(name, reals.shape[0])          # captured on the main stream the first time
-                    side = self._critic_streams[i]
-                    side.wait_event(fork)
-                    with torch.cuda.stream(side):
-                        rep = critic(fake, reals_fade, draws[gp])
-                    done = torch.cuda.Event()
-                    done.record(side)
-                    joins.append(done)
-                    report.update({name + '/' + k: v for k, v in rep.items()})
-                if overlap:
-                    # the taped G_fcn evaluations of the E/G phase do not depend on the critics: decode them on the
-                    # main stream WHILE the critic graphs (many thin, low-occupancy kernels) run on the side streams
-                    fwd.decode_canvases()
-                for done in joins:
-                    main.wait_event(done)       # fakes / reals are only released by the caller after this join
+                self.buckets['D'].zero_()
+
+            def critic_job(name, fake, gp):
+                if critic_graphs:
+                    g = self._critic(name, n)            # captured on the current stream the first time
+                    return lambda: g(fake, d_fade, draws[gp])
+                return lambda: loss.D_wgangp(nets[name], fake, d_fade, draws[gp], self.grads[name])
+            jobs = [critic_job(*f) for f in fakes]
+            if os.environ.get('TMX_NO_FORK'):
+                results, join = [j() for j in jobs], (lambda: None)
             else:
-                for name, fake, gp in fakes:
-                    self.grads[name].zero_()
-                    rep = loss.D_wgangp(self.nets[name], fake, reals_fade, draws[gp], self.grads[name])
-                    report.update({name + '/' + k: v for k, v in rep.items()})
+                results, join = self._fork_join(jobs)
+            # the taped evaluations of the E/G phase do not depend on the critics: run them on the main stream WHILE
+            # the critics (many thin, low-occupancy kernels) run on the side streams
+            if 'EG' in phases:
+                if fwd is None:
+                    fwd = eg_forward()
+                fwd.decode_canvases()
+            join()                   # fakes / reals are only released after this join
+            for (name, _, _), rep in zip(fakes, results):
+                report.update({name + '/' + k: v for k, v in rep.items()})
             for name in ('D_rec', 'D_interp', 'D_blend'):                           # one session.run (run.py:511)
-                report[name + '/skipped'] = self.opts[name].apply_updates(lrate)
+                self.opts[name].mark()
+            boundary('D')
+            for name in ('D_rec', 'D_interp', 'D_blend'):
+                report[name + '/skipped'] = self.opts[name].update(lrate)
+            self._d_keep = fakes
         if 'EG' in phases:
-            for k in ('E_zg', 'E_zl', 'G'):
-                self.grads[k].zero_()
+            if fwd is None:
+                fwd = eg_forward()
+            fwd.decode_canvases()
+            self.buckets['EG'].zero_()
             critic_grads = None
-            if c.get('cuda_graphs', True) and not os.environ.get('TMX_NO_GRAPH') and lod_now == int(lod_now):
-                critic_grads = self._eg_critic_gradients(fwd, draws)
-            rep = loss.EG_backward(fwd, self.nets['D_rec'], self.nets['D_interp'], self.nets['D_blend'],
+            if not os.environ.get('TMX_NO_FORK'):
+                critic_grads = self._eg_critic_gradients(fwd, draws, critic_graphs)
+            rep = loss.EG_backward(fwd, nets['D_rec'], nets['D_interp'], nets['D_blend'],
                                    draws['eg_crop_interp'], draws['eg_crop_blend'], self.grads, reals_fade=reals_fade,
                                    critic_grads=critic_grads, **c['loss'])
             report.update({'EG/' + k: v for k, v in rep.items()})
-            report['EG/skipped'] = self.opts['EG'].apply_updates(lrate)
+            self.opts['EG'].mark()
+            boundary('EG')
+            report['EG/skipped'] = self.opts['EG'].update(lrate)
         del fwd
         if 'EMA' in phases:
             for upd in self.ema.values():
                 upd()
         return report
+
+    # ------------------------------------------------------------------ the step as CUDA graphs
+    def _step_graphed(self, reals_fade, reals_orig, d_fade, d_orig, draws, lrate, phases, lod_now):
+        shared = d_orig is reals_orig and d_fade is reals_fade
+        distinct = []        # the distinct input tensors, in a fixed role order
+        roles = []
+        for t in (reals_fade, reals_orig, d_fade, d_orig):
+            for i, u in enumerate(distinct):
+                if u is t:
+                    roles.append(i)
+                    break
+            else:
+                roles.append(len(distinct))
+                distinct.append(t)
+        sig = tuple(None if draws['host_plans'][k][w] is None else tuple(draws['host_plans'][k][w][2:])
+                    for k in CROP_KEYS for w in loss.PLAN_KEYS)
+        key = (tuple(reals_fade.shape), tuple(roles), lod_now, lrate, phases, sig, parallel.world_size())
+        ent = self._step_graphs.get(key)
+        if ent is None:
+            if key not in self._warm:
+                # first step of this shape: eager (loads the kernels, sizes the allocator pools, creates the
+                # optimizers' device state) - and it is a real step
+                self._warm.add(key)
+                return self._step_body(reals_fade, reals_orig, d_fade, d_orig, draws, lrate, phases)
+            ent = self._step_graphs[key] = self._capture_step(distinct, roles, draws, lrate, phases)
+        for dst, src in zip(ent.reals, distinct):
+            dst.copy_(src, non_blocking=True)
+        ent.packed.copy_(draws['_packed'], non_blocking=True)
+        ent.mixes.copy_(draws['_mixes'], non_blocking=True)
+        for kind, obj in ent.program:
+            if kind == 'graph':
+                obj.replay()
+            else:
+                self._allreduce(obj)
+        self.graph_launches += ent.launches
+        for net in self.nets.values():      # the graph re-derives its weight planes itself; eager users must too
+            net._touch()
+        return ent.report
+
+    def _capture_step(self, distinct, roles, draws, lrate, phases):
+        rt = self.rt
+        dev = rt.device
+        ent = _StepGraph()
+        ent.reals = [torch.empty_like(t) for t in distinct]
+        ent.packed = torch.empty_like(draws['_packed'])
+        ent.mixes = torch.empty_like(draws['_mixes'])
+        for dst, src in zip(ent.reals, distinct):
+            dst.copy_(src)
+        ent.packed.copy_(draws['_packed'])
+        ent.mixes.copy_(draws['_mixes'])
+        sdraws = dict(draws)
+        sdraws.update(self._draw_views(draws['idx'], draws['host_plans'], ent.packed, ent.mixes))
+        ent.draws = sdraws
+        x = [ent.reals[i] for i in roles]
+        torch.cuda.synchronize(dev)
+        for net in list(self.nets.values()) + [self.G_fcn]:
+            net._owner()._prepared.clear()       # capture the weight-plane kernels too
+        ent.pool = torch.cuda.graph_pool_handle()
+        cap_stream = torch.cuda.Stream(device=dev)
+        program, state = [], {}
+
+        def begin():
+            g = torch.cuda.CUDAGraph()
+            ctx = torch.cuda.graph(g, pool=ent.pool, stream=cap_stream)
+            ctx.__enter__()
+            state['g'], state['ctx'] = g, ctx
+
+        def end():
+            state['ctx'].__exit__(None, None, None)
+            program.append(('graph', state['g']))
+
+        def boundary(name):
+            if parallel.world_size() > 1:        # the all-reduce stays an ordinary NCCL call between two graphs
+                end()
+                program.append(('allreduce', name))
+                begin()
+        l0 = rt.launch_count()
+        gc.collect()
+        gc_was_on = gc.isenabled()
+        gc.disable()                           # finalising unrelated CUDA objects mid-capture would invalidate it
+        try:
+            begin()
+            try:
+                ent.report = self._step_body(x[0], x[1], x[2], x[3], sdraws, lrate, phases, boundary=boundary)
+                ent.keep = (getattr(self, '_d_keep', None), getattr(self, '_eg_inputs', None))
+            finally:
+                end()
+        finally:
+            if gc_was_on:
+                gc.enable()
+        ent.launches = rt.launch_count() - l0
+        ent.program = program
+        for net in list(self.nets.values()) + [self.G_fcn]:
+            net._owner()._prepared.clear()       # those planes live in the graph's pool; nobody else may keep them
+        return ent
