@@ -245,11 +245,15 @@ def run_ours(args):
 
     # ---- end to end through Network.run (host numpy in / out)
     E2E_MB = int(os.environ.get('TMX_E2E_MB', '32'))      # Network.run(minibatch_size=...) (tfutil.py:624-680): minibatches are pipelined H2D / compute / D2H
-    # the step's inputs wait in page-locked host memory (bench contract); Network.run DMAs straight from them
-    zg_p = torch.empty(zg_h.shape, dtype=torch.float32, pin_memory=True).numpy()
+    # the step's inputs wait in page-locked host memory (bench contract); Network.run DMAs straight from them.  The
+    # global code goes up as [N,128,1,1] and is tiled over the 32x32 canvas on the device (G_res accepts that; a
+    # caller's np.broadcast_to view is collapsed to the same by Network.run): half the H2D bytes of a host-side np.tile
+    zg_small = np.ascontiguousarray(zg_h[:, :, :1, :1])
+    zg_p = torch.empty(zg_small.shape, dtype=torch.float32, pin_memory=True).numpy()
     zl_p = torch.empty(zl_h.shape, dtype=torch.float32, pin_memory=True).numpy()
-    zg_p[...] = zg_h
+    zg_p[...] = zg_small
     zl_p[...] = zl_h
+    zl_pageable = zl_h.copy()
     zg_h, zl_h = zg_p, zl_p
     for _ in range(2):
         G.run(zg_h, zl_h, minibatch_size=E2E_MB)
@@ -259,6 +263,17 @@ def run_ours(args):
         out_h = G.run(zg_h, zl_h, minibatch_size=E2E_MB)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    barrier()
+    # the same call with ordinary (pageable) numpy arrays, as a drop-in caller of the reference's Network.run passes
+    # them: staged through page-locked slots by a few host threads
+    for _ in range(2):
+        G.run(zg_small, zl_pageable, minibatch_size=E2E_MB)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        G.run(zg_small, zl_pageable, minibatch_size=E2E_MB)
+    torch.cuda.synchronize()
+    e2e_pageable_s = time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
@@ -273,10 +288,10 @@ def run_ours(args):
     rt.profile_kernels = False
     trunk_ms = float(np.mean(trunk)) if trunk else None
 
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s, e2e_pageable_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s = float(t[0]), float(t[1])
+    dev_ms, e2e_s, e2e_pageable_s = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         pk = peaks()
@@ -304,7 +319,9 @@ def run_ours(args):
             'tflops_algorithmic': value * GFLOP_PER_IMAGE / 1e3,
             'e2e': {'value': e2e, 'unit': 'images/s', 'h2d_bytes_per_step': int(zg_h.nbytes + zl_h.nbytes),
                     'd2h_bytes_per_step': int(out_h.nbytes),
-                    'api': 'Network.run(zg, zl, minibatch_size=%d): numpy in (page-locked arrays), numpy out' % E2E_MB},
+                    'api': 'Network.run(zg [N,128,1,1], zl, minibatch_size=%d): numpy in (page-locked arrays), numpy out' % E2E_MB,
+                    'pageable_inputs': {'value': images / e2e_pageable_s, 'unit': 'images/s',
+                                        'note': 'same call with ordinary numpy arrays (staged through pinned slots)'}},
             'gpu_launches': int(launches),
             'roofline': roof,
             'cpu_baseline': {'value': cpu_ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',

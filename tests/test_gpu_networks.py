@@ -82,6 +82,22 @@ def test_generator_vs_oracle_with_taps(algo, monkeypatch):
     assert ok.mean() == 1.0
 
 
+def test_generator_global_code_tiled_on_the_device():
+    """A [N,C,1,1] global code - or the caller's stride-0 np.broadcast_to view of one - gives bit-identical images to
+    the host-tiled array (run.py:375 np.tile) at half the H2D bytes; get_output_for takes the same short form."""
+    rng = np.random.RandomState(4)
+    params = R.init_params('G_res', rng, **R.CONFIG['G_res'])
+    net = _make('G_res', params)
+    n = 5
+    zg1 = rng.randn(n, 128, 1, 1).astype(np.float32)
+    zl = rng.randn(n, 128, 32, 32).astype(np.float32)
+    want = net.run(np.tile(zg1, (1, 1, 32, 32)), zl, minibatch_size=2)
+    assert np.array_equal(net.run(zg1, zl, minibatch_size=2), want)
+    assert np.array_equal(net.run(np.broadcast_to(zg1, (n, 128, 32, 32)), zl, minibatch_size=3), want)
+    got = net.get_output_for(torch.from_numpy(zg1).cuda(), torch.from_numpy(zl).cuda()).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
 def test_generator_fully_convolutional_scale():
     """G_fcn view (run.py:273): same variables, scale_h x scale_w canvas."""
     from texturemixer_b200.network import Network

@@ -281,3 +281,31 @@ def test_app_mattes_match_reference_functions():
                 assert np.allclose(got, want, rtol=1e-14, atol=1e-300), (name, i)
             else:
                 assert np.array_equal(got, want), (name, i)
+
+
+def test_checkpoint_unpickler_refuses_foreign_globals(tmp_path):
+    """misc.load_pkl resolves only what a reference checkpoint can name; a reducer naming os.system (or any other
+    global) raises instead of being imported and called."""
+    import pickle
+    from texturemixer_b200 import misc
+
+    class Evil:
+        def __reduce__(self):
+            import os
+            return (os.system, ('echo pwned > %s' % (tmp_path / 'pwned'),))
+    p = tmp_path / 'evil.pkl'
+    with open(p, 'wb') as f:
+        pickle.dump((Evil(),), f)
+    with pytest.raises(pickle.UnpicklingError):
+        misc.load_pkl(str(p))
+    assert not (tmp_path / 'pwned').exists()
+
+
+def test_broadcast_inputs_collapse_to_one_pixel():
+    """Network.run uploads a host-tiled global code (np.broadcast_to of [N,C,1,1]) as [N,C,1,1]."""
+    from texturemixer_b200.network import _collapse_broadcast
+    zg = np.random.RandomState(0).randn(3, 8, 1, 1).astype(np.float32)
+    view = np.broadcast_to(zg, (3, 8, 32, 32))
+    assert _collapse_broadcast(view).shape == (3, 8, 1, 1) and np.array_equal(_collapse_broadcast(view), zg)
+    tiled = np.tile(zg, (1, 1, 4, 4))
+    assert _collapse_broadcast(tiled) is tiled and _collapse_broadcast(zg) is zg

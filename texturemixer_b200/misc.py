@@ -10,7 +10,9 @@ state layout, and carries a loaded network's original `build_module_src` through
 from the reference goes back to it intact (a network created here stores this package's own build source, which
 the reference's TensorFlow code cannot execute - stated limitation).
 
-Pickles are code: only load files you trust (any other global they name is resolved by the stock unpickler)."""
+`ReferenceUnpickler.find_class` is a WHITELIST: the Network stubs, numpy array reconstruction, OrderedDict and the
+plain-object reconstructor are everything a reference checkpoint names; any other global (os.system, builtins.eval,
+...) raises UnpicklingError instead of being imported."""
 import copyreg
 import pickle
 import sys
@@ -21,11 +23,25 @@ from .network import Network
 _REFERENCE_CLASSES = {('tfutil', 'Network'), ('network', 'Network')}
 
 
+# every global a checkpoint written by run.py:583 / misc.py:31-33 (or by save_pkl below) can name
+_ALLOWED_GLOBALS = {
+    ('numpy.core.multiarray', '_reconstruct'), ('numpy._core.multiarray', '_reconstruct'),
+    ('numpy.core.multiarray', 'scalar'), ('numpy._core.multiarray', 'scalar'),
+    ('numpy', 'ndarray'), ('numpy', 'dtype'),
+    ('numpy.core.numeric', '_frombuffer'), ('numpy._core.numeric', '_frombuffer'),      # protocol-5 array payloads
+    ('collections', 'OrderedDict'), ('copyreg', '_reconstructor'), ('copy_reg', '_reconstructor'),
+    ('builtins', 'object'), ('__builtin__', 'object'),
+}
+
+
 class ReferenceUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if (module, name) in _REFERENCE_CLASSES:
             return Network
-        return super().find_class(module, name)
+        if (module, name) in _ALLOWED_GLOBALS:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError('checkpoint names the global %s.%s, which a TextureMixer network pickle has no '
+                                     'business naming - refusing to import it' % (module, name))
 
 
 def load_pkl(filename):

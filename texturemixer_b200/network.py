@@ -24,12 +24,14 @@ def import_module(module_or_obj_name):
     parts[0] = {'np': 'numpy', 'tf': 'tensorflow'}.get(parts[0], parts[0])
     for i in range(len(parts), 0, -1):
         name = '.'.join(parts[:i])
-        for cand in (name, 'texturemixer_b200.' + name):      # 'networks.G_res' resolves to OUR networks module
+        # 'networks.G_res' / 'loss.EG_wgan' resolve to OUR modules: the prefixed candidate is tried FIRST for them, so
+        # that a bare `networks` on sys.path (e.g. the reference's TensorFlow file) is never imported, let alone run
+        ours_first = parts[0] in ('networks', 'loss', 'network', 'interp', 'train', 'optim', 'misc')
+        cands = ('texturemixer_b200.' + name,) if ours_first else (name, 'texturemixer_b200.' + name)
+        for cand in cands:
             try:
                 module = importlib.import_module(cand)
             except ImportError:
-                continue
-            if cand == name and parts[0] in ('networks', 'loss') and not module.__name__.startswith('texturemixer_b200'):
                 continue
             return module, '.'.join(parts[i:])
     raise ImportError(module_or_obj_name)
@@ -423,6 +425,9 @@ class Network:
         num_items = in_arrays[0].shape[0]
         if minibatch_size is None:
             minibatch_size = num_items
+        # a global code tiled on the host (np.tile / np.broadcast_to of a [N,C,1,1] array, run.py:375) crosses PCIe as
+        # [N,C,1,1] and is tiled on the device by the build function (G_res): stride-0 views are collapsed here
+        in_arrays = [_collapse_broadcast(a) for a in in_arrays]
         dev = self.rt.device
         out_arrays = None
         # Software pipeline over minibatches: (1) threaded host copy of minibatch k+1 into pinned staging,
@@ -524,7 +529,12 @@ class Network:
             if gc_was_on:
                 gc.enable()
         if len(self._graphs) > 8:
-            self._graphs.clear()
+            # evict: a dropped graph's private pool (its static inputs / outputs) may still be read by a replay or a
+            # D2H copy in flight - wait for the device before the memory can be handed out again
+            torch.cuda.synchronize(dev)
+            stale = [k for k, e in self._graphs.items() if e[3] != o._version]
+            for k in (stale or list(self._graphs)):
+                del self._graphs[k]
         ent = (g, static_in, static_out, o._version)
         self._graphs[key] = ent
         return ent
@@ -603,6 +613,13 @@ class Network:
 
     def setup_weight_histograms(self, title=None):
         pass  # TensorBoard summaries are outside the hot path
+
+
+def _collapse_broadcast(a):
+    """[N,C,1,1] view of an array whose last two axes are stride-0 broadcasts (np.broadcast_to), else `a`."""
+    if isinstance(a, np.ndarray) and a.ndim == 4 and a.shape[2] * a.shape[3] > 1 and a.strides[2] == 0 and a.strides[3] == 0:
+        return a[:, :, :1, :1]
+    return a
 
 
 def _as_pinned(a):

@@ -511,7 +511,12 @@ def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_bas
         latent_channels = nf(0)
     ctx = zg_latents_in.ctx
     ctx.pixelnorm = pixelnorm_epsilon if use_pixelnorm else None
-    zg_latents_in.set_shape([None, latent_channels, latent_res * scale_h, latent_res * scale_w])
+    # inference convenience (not in the reference): a [N,C,1,1] global code is tiled over the canvas ON THE DEVICE -
+    # what every caller does on the host first (run.py:375 np.tile, loss.py:130 tf.tile), at half the H2D bytes
+    zg_bcast = ctx.mode == 'run' and ctx.tape is None and list(zg_latents_in.shape[2:]) == [1, 1] and \
+        list(zl_latents_in.shape[2:]) != [1, 1]
+    if not zg_bcast:
+        zg_latents_in.set_shape([None, latent_channels, latent_res * scale_h, latent_res * scale_w])
     zl_latents_in.set_shape([None, latent_channels, latent_res * scale_h, latent_res * scale_w])
     c2 = latent_channels * 2
 
@@ -521,12 +526,12 @@ def G_res(zg_latents_in, zl_latents_in, num_channels=3, resolution=128, fmap_bas
         combo_in = T(combo_shape, ctx)
     else:
         rt = ctx.rt
-        n, _, h, w = zg_latents_in.nchw.shape
-        if tuple(zl_latents_in.nchw.shape) != (n, latent_channels, h, w):
+        n, _, h, w = zl_latents_in.nchw.shape
+        if tuple(zg_latents_in.nchw.shape) != ((n, latent_channels, 1, 1) if zg_bcast else (n, latent_channels, h, w)):
             raise ValueError('G_res: zg %s and zl %s disagree' % (tuple(zg_latents_in.nchw.shape),
                                                                   tuple(zl_latents_in.nchw.shape)))
         buf = rt.empty(n, h, w, c2)
-        rt.nchw_to_nhwc(zg_latents_in.nchw, out=buf, c_off=0, c_total=c2)
+        rt.nchw_to_nhwc(zg_latents_in.nchw, out=buf, c_off=0, c_total=c2, bcast_hw=(h, w) if zg_bcast else None)
         rt.nchw_to_nhwc(zl_latents_in.nchw, out=buf, c_off=latent_channels, c_total=c2)
         combo_shape[0] = n
         combo_in = T(combo_shape, ctx, act=Act(n, h, w, c2, f32=buf))
