@@ -32,9 +32,13 @@ def crop(images, yx, size):
 
 
 def EG_wgan(P, reals, idx, crop_interp, crop_blend, mixing_factors, scale_h=3, scale_w=3, rec_G_weight=1.0,
-            pixel_weight=200.0, kl_weight=0.0, interp_G_weight=1.0, blend_interp_G_weight=1.0, cfg=None):
+            pixel_weight=200.0, kl_weight=0.0, interp_G_weight=1.0, blend_interp_G_weight=1.0, cfg=None,
+            gram_weight=0.0, vgg=None, gram_alpha=None):
     """P: dict of parameter dicts for 'E_zg','E_zl','G','D_rec','D_interp','D_blend'.  Returns the per-sample
-    loss vector [N] (the optimizer differentiates its mean, run.py:321) and a dict of named terms."""
+    loss vector [N] (the optimizer differentiates its mean, run.py:321) and a dict of named terms.
+    gram_weight > 0 adds the VGG-19 Gram terms (loss.py:148-160, 206-213, 248-257) with `vgg` = the weight dict
+    ({layer: [filter, bias]}) and `gram_alpha` = the [N,1,1,1] draw of loss.py:253; the loss then has the
+    reference's [N,1,1,N] shape (see vgg_ref.blend_gram_term)."""
     cfg = cfg or R.CONFIG
     zg_mu, zg_ls = R.E_zg(reals, P['E_zg'], **cfg['E_zg'])                           # loss.py:119
     zl_mu, zl_ls = R.E_zl(reals, P['E_zl'], **cfg['E_zl'])                           # loss.py:126
@@ -48,6 +52,11 @@ def EG_wgan(P, reals, idx, crop_interp, crop_blend, mixing_factors, scale_h=3, s
     if pixel_weight > 0:
         terms['rec_pixel'] = (rec - reals).abs().mean(dim=(1, 2, 3)) * pixel_weight  # loss.py:143
         loss = loss + terms['rec_pixel']
+    if gram_weight > 0:                                                               # loss.py:149-160
+        from . import vgg_ref as V
+        real_gram = V.grams(reals, vgg)
+        terms['rec_gram'] = V.multi_layer_diff(V.grams(rec, vgg), real_gram) * gram_weight
+        loss = loss + terms['rec_gram']
     if kl_weight > 0:                                                                 # loss.py:163-171
         for tag, mu, ls in (('KL_zg', zg_mu, zg_ls), ('KL_zl', zl_mu, zl_ls)):
             terms[tag] = -0.5 * (1 + 2 * ls - mu ** 2 - torch.exp(2 * ls)).mean(dim=(1, 2, 3)) * kl_weight
@@ -58,9 +67,12 @@ def EG_wgan(P, reals, idx, crop_interp, crop_blend, mixing_factors, scale_h=3, s
     size = reals.shape[2:]
     if interp_G_weight > 0:
         interp = R.G_res(zg_c, zl_c, P['G'], **g_cfg)                                 # loss.py:197
-        terms['interp_G'] = (-R.D_patch(crop(interp, crop_interp, size), P['D_interp'], **cfg['D_patch'])
-                             ).mean(dim=(1, 2, 3)) * interp_G_weight
+        crop_i = crop(interp, crop_interp, size)
+        terms['interp_G'] = (-R.D_patch(crop_i, P['D_interp'], **cfg['D_patch'])).mean(dim=(1, 2, 3)) * interp_G_weight
         loss = loss + terms['interp_G']
+        if gram_weight > 0:                                                           # loss.py:206-213
+            terms['interp_gram'] = V.multi_layer_diff(V.grams(crop_i, vgg), real_gram) * gram_weight
+            loss = loss + terms['interp_gram']
     if blend_interp_G_weight > 0:
         zg_r = torch.flip(zg_mu, dims=[0]).repeat(1, 1, lat * scale_h, lat * scale_w)             # loss.py:218
         zl_r = tiling_permutation(torch.flip(zl_mu, dims=[0]), scale_h, scale_w, idx['h_backward'],
@@ -69,9 +81,12 @@ def EG_wgan(P, reals, idx, crop_interp, crop_blend, mixing_factors, scale_h=3, s
         bzg = zg_r + (zg_c - zg_r) * t                                                            # loss.py:238
         bzl = zl_r + (zl_c - zl_r) * t
         blend = R.G_res(bzg, bzl, P['G'], **g_cfg)                                                # loss.py:240
-        terms['blend_G'] = (-R.D_patch(crop(blend, crop_blend, size), P['D_blend'], **cfg['D_patch'])
-                            ).mean(dim=(1, 2, 3)) * blend_interp_G_weight
+        crop_b = crop(blend, crop_blend, size)
+        terms['blend_G'] = (-R.D_patch(crop_b, P['D_blend'], **cfg['D_patch'])).mean(dim=(1, 2, 3)) * blend_interp_G_weight
         loss = loss + terms['blend_G']
+        if gram_weight > 0:                                                                       # loss.py:248-257
+            terms['blend_gram'] = V.blend_gram_term(V.grams(crop_b, vgg), real_gram, gram_alpha, gram_weight)
+            loss = loss + terms['blend_gram']
     return loss, terms
 
 

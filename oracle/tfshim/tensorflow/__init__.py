@@ -346,6 +346,10 @@ def concat(values, axis):
     return Tensor(torch.cat([_raw(v) for v in values], dim=axis))
 
 
+def split(value, num_or_size_splits, axis=0):
+    return [Tensor(t) for t in torch.chunk(_raw(value), int(num_or_size_splits), dim=axis)]
+
+
 def expand_dims(x, axis):
     return Tensor(_raw(x).unsqueeze(axis))
 
@@ -468,7 +472,11 @@ class nn:
     @staticmethod
     def conv2d(x, w=None, strides=(1, 1, 1, 1), padding='VALID', data_format='NHWC', filter=None, name=None):  # noqa: A002
         w = w if w is not None else filter
-        assert data_format == 'NCHW' and padding in ('VALID', 'SAME'), 'shim: NCHW only'
+        assert data_format in ('NCHW', 'NHWC') and padding in ('VALID', 'SAME')
+        if data_format == 'NHWC':       # tensorflow_vgg's layers: same op on the transposed tensor
+            s = _ilist(strides)
+            y = nn.conv2d(Tensor(_raw(x).permute(0, 3, 1, 2)), w, (1, 1, s[1], s[2]), padding, 'NCHW')
+            return Tensor(y.t.permute(0, 2, 3, 1))
         s = _ilist(strides)
         xr, wr = _raw(x), _raw(w)
         if padding == 'SAME':
@@ -484,10 +492,20 @@ class nn:
         return Tensor(F.conv2d(xr, wr.permute(3, 2, 0, 1), stride=(s[2], s[3])))
 
     @staticmethod
-    def avg_pool(x, ksize, strides, padding='VALID', data_format='NHWC'):
-        assert data_format == 'NCHW' and padding == 'VALID'
+    def avg_pool(x, ksize, strides, padding='VALID', data_format='NHWC', name=None):
         k, s = _ilist(ksize), _ilist(strides)
+        if data_format == 'NHWC':
+            xr = _raw(x)
+            # SAME == VALID when the window tiles the map exactly (VGG on power-of-two crops)
+            assert padding == 'VALID' or (xr.shape[1] % s[1] == 0 and xr.shape[2] % s[2] == 0 and k[1:3] == s[1:3])
+            return Tensor(F.avg_pool2d(xr.permute(0, 3, 1, 2), (k[1], k[2]), (s[1], s[2])).permute(0, 2, 3, 1))
+        assert data_format == 'NCHW' and padding == 'VALID'
         return Tensor(F.avg_pool2d(_raw(x), (k[2], k[3]), (s[2], s[3])))
+
+    @staticmethod
+    def bias_add(x, b, data_format='NHWC'):
+        xr, br = _raw(x), _raw(b)
+        return Tensor(xr + (br if data_format == 'NHWC' else br.reshape(1, -1, 1, 1)))
 
     @staticmethod
     def relu(x):

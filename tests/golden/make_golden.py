@@ -227,7 +227,8 @@ def gen_schedule():
 
 # ---------------------------------------------------------------- losses (loss.py executed unmodified)
 sys.path.insert(0, os.path.dirname(HERE))
-from loss_case import LOSS_N, LOSS_GRAD_STRIDE, LOSS_NETS, loss_case_inputs  # noqa: E402  (tests/loss_case.py)
+from loss_case import (LOSS_N, LOSS_GRAD_STRIDE, LOSS_NETS, GRAM_WEIGHT, loss_case_inputs, vgg_standin_weights,  # noqa: E402
+                       gram_alpha)                                                                      # (tests/loss_case.py)
 
 
 def gen_losses():
@@ -282,7 +283,10 @@ def gen_losses():
     for k, v in mixes.items():
         out['draw_' + k] = v
 
-    def run(tag, fn, trainable_scopes, int_draws, float_draws):
+    out_all = out
+
+    def run(tag, fn, trainable_scopes, int_draws, float_draws, out=None):
+        out = out_all if out is None else out
         tf.reset_default_graph(values=values, requires_grad=True)
         terms = {}
 
@@ -331,6 +335,21 @@ def gen_losses():
         ('D_blend',), [c[0], c[1]], [mixes['d_blend_mix'], mixes['d_blend_gp']])
     np.savez_compressed(os.path.join(HERE, 'losses.npz'), **out)
     print('losses.npz: %d arrays, %.1f MB' % (len(out), os.path.getsize(os.path.join(HERE, 'losses.npz')) / 1e6))
+
+    # ---- the same E/G loss WITH the VGG-19 Gram terms (config.py:64 gram_weight = 0.002): custom_vgg19.py and the
+    # Gram branches of loss.py run unmodified; `tensorflow_vgg.vgg19.Vgg19` is the shim's restatement of the
+    # un-vendored base class and the weights are the seeded stand-in (vgg19.npy is not redistributable)
+    data_dict = vgg_standin_weights()
+    assert refcfg.gram_weight == GRAM_WEIGHT
+    lossmod.loadWeightsData = lambda path=None: data_dict           # np.load of tensorflow_vgg/vgg19.npy
+    gram = {'meta_n_sh_sw_stride': out['meta_n_sh_sw_stride'], 'draw_eg_gram_alpha': gram_alpha(n)}
+    eg_kw_gram = kw(refcfg.EG_loss)
+    run('EGgram', lambda x: lossmod.EG_wgan(
+        nets['E_zg'], nets['E_zl'], nets['G'], nets['D_rec'], nets['G_fcn'], nets['D_interp'], nets['D_blend'], n, x, x,
+        None, tf.convert_to_tensor(ph), tf.convert_to_tensor(pw), tf.convert_to_tensor(phb), tf.convert_to_tensor(pwb),
+        **eg_kw_gram), ('E_zg', 'E_zl', 'G'), [ci[0], ci[1], cb[0], cb[1]], [mixes['eg_mix'], gram_alpha(n)], out=gram)
+    np.savez_compressed(os.path.join(HERE, 'losses_gram.npz'), **gram)
+    print('losses_gram.npz: %d arrays, %.1f MB' % (len(gram), os.path.getsize(os.path.join(HERE, 'losses_gram.npz')) / 1e6))
 
 
 if __name__ == '__main__':

@@ -29,6 +29,31 @@ def loss_case_inputs(n=LOSS_N, scale_h=3, scale_w=3):
     return params, reals, idx, crops, mixes
 
 
+VGG_LAYERS = (('conv1_1', 3, 64), ('conv1_2', 64, 64), ('conv2_1', 64, 128), ('conv2_2', 128, 128),
+              ('conv3_1', 128, 256), ('conv3_2', 256, 256), ('conv3_3', 256, 256), ('conv3_4', 256, 256),
+              ('conv4_1', 256, 512), ('conv4_2', 512, 512), ('conv4_3', 512, 512), ('conv4_4', 512, 512),
+              ('conv5_1', 512, 512), ('conv5_2', 512, 512), ('conv5_3', 512, 512), ('conv5_4', 512, 512))
+GRAM_WEIGHT = 0.002        # config.py:64
+
+
+def vgg_standin_weights(seed=19):
+    """Stand-in for tensorflow_vgg/vgg19.npy (not redistributable): the same dict layout
+    {layer: [filter [3,3,Cin,Cout], bias [Cout]]} with seeded He-scaled random filters, so that the Gram-loss path
+    (custom_vgg19.py, loss.py:29-35,68-75,148-160,206-213,248-257) can be built and parity-tested; the real file
+    drops in through the same loader."""
+    rng = np.random.RandomState(seed)
+    out = {}
+    for name, cin, cout in VGG_LAYERS:
+        out[name] = [(rng.randn(3, 3, cin, cout) * np.sqrt(2.0 / (9 * cin))).astype(np.float32),
+                     (0.05 * rng.randn(cout)).astype(np.float32)]
+    return out
+
+
+def gram_alpha(n=LOSS_N):
+    """The extra uniform draw of the blend Gram term (loss.py:253)."""
+    return np.random.RandomState(77).uniform(0, 1, (n, 1, 1, 1)).astype(np.float32)
+
+
 def golden_gradient(g, tag, scope, name):
     """(subsample or whole gradient, its L2 norm over the WHOLE variable) as stored by gen_losses."""
     key = '%s_grad_%s_%s' % (tag, scope, name.replace('/', '.'))

@@ -10,7 +10,7 @@ import torch
 from oracle import loss_ref as L
 from oracle import networks_ref as R
 
-from loss_case import GOLDEN, loss_case_inputs, golden_gradient, subsample
+from loss_case import GOLDEN, GRAM_WEIGHT, loss_case_inputs, golden_gradient, gram_alpha, subsample, vgg_standin_weights
 
 
 def _rel(got, want):
@@ -86,3 +86,27 @@ def test_critic_losses_match_reference_loss_py(case, which):
         assert np.allclose(terms[mine].detach().numpy(), want, rtol=1e-4, atol=1e-5 * max(np.abs(want).max(), 1e-3)), mine
     worst = _check_grads(g, which, P, (which,), 1e-4)
     print(which, 'worst variable gradient rel-L2 vs the reference code', worst)
+
+
+def test_eg_wgan_with_gram_terms_matches_reference_code(case):
+    """EG_wgan WITH the VGG-19 Gram terms (config.py:64 gram_weight = 0.002): tests/golden/losses_gram.npz comes from
+    the reference's loss.py + custom_vgg19.py run unmodified on the shim (stand-in weights; tensorflow_vgg's base
+    class restated in oracle/tfshim/tensorflow_vgg) - incl. the [N,1,1,N] broadcast of loss.py:254."""
+    import os
+    _, params, reals, idx, crops, mixes, (sh, sw) = case
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), 'losses_gram.npz'))
+    alpha = gram_alpha(reals.shape[0])
+    assert np.array_equal(g['draw_eg_gram_alpha'], alpha)
+    P = {k: R.to_torch(params[k], requires_grad=k in ('E_zg', 'E_zl', 'G')) for k in params}
+    loss, terms = L.EG_wgan(P, reals, idx, crops['eg_crop_interp'], crops['eg_crop_blend'], mixes['eg_mix'],
+                            scale_h=sh, scale_w=sw, gram_weight=GRAM_WEIGHT, vgg=vgg_standin_weights(),
+                            gram_alpha=torch.from_numpy(alpha))
+    loss.mean().backward()
+    assert tuple(loss.shape) == tuple(g['EGgram_loss'].shape) == (4, 1, 1, 4)
+    assert np.allclose(loss.detach().numpy(), g['EGgram_loss'], rtol=1e-5, atol=0)
+    for mine, ref in (('rec_gram', 'rec_gram_loss'), ('interp_gram', 'crop_interp_gram_loss'),
+                      ('blend_gram', 'crop_blend_interp_gram_loss'), ('rec_G', 'rec_G_loss')):
+        want = g['EGgram_term_Loss_' + ref]
+        assert np.allclose(terms[mine].detach().numpy(), want, rtol=1e-4, atol=1e-5 * np.abs(want).max()), mine
+    worst = _check_grads(g, 'EGgram', P, ('E_zg', 'E_zl', 'G'), 2e-4)
+    print('EG_wgan + Gram: worst variable gradient rel-L2 vs the reference code', worst)

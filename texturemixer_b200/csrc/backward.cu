@@ -28,139 +28,131 @@ __device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
   v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-// One thread = 8 channels (fixed for the thread: its bias-gradient partial stays in registers) of the positions
-// lane, lane + ppb, ... of `rpb` consecutive rows of the OUTPUT grid [N][H+4][W+4] (zero ring included, so the
-// ring gets zeroed).  All index arithmetic is per row, 32-bit where it matters: the per-element 64-bit divisions of
-// the first version cost as much issue time as the memory traffic took (HBM-bound kernel at 0.44 of peak).
-__global__ void __launch_bounds__(256) grad_prepare_kernel(const GradPrepParams P) {
-  extern __shared__ float red[];   // [ppb][C8*8] bias-gradient partials
+// One thread = 8 channels (fixed for the thread: blockDim is a multiple of C8, so its bias-gradient partial stays in
+// registers) of the units t, t + grid size, ... of the OUTPUT grid [N][H+4][W+4] (zero ring included, so the ring
+// gets zeroed); a unit = (grid row, column, channel group), flattened over the whole grid so that narrow-channel
+// maps (C = 16: two groups per pixel) keep every lane busy and every CTA gets the same share.  Index arithmetic is 32-bit: the per-element 64-bit
+// divisions of the first version cost as much issue time as the memory traffic took.
+__global__ void __launch_bounds__(256, 4) grad_prepare_kernel(const GradPrepParams P) {
+  extern __shared__ float red[];   // [blockDim / C8][C] bias-gradient partials
   const tmx_grad_desc_t& d = P.d;
-  const int cg = threadIdx.x % P.C8;
-  const int lane = threadIdx.x / P.C8;
+  const int C8 = P.C8;
+  const int cg = threadIdx.x % C8;
   const int H = d.H, W = d.W, C = d.C;
   const int Hq = H + 4, Wq = W + 4;
   const int rows_total = d.N * Hq;
   const int co = cg * 8;
+  const int units_per_row = Wq * C8;
+  const int units = rows_total * units_per_row;            // < 2^31 (host check)
+  const int ustride = gridDim.x * blockDim.x;              // a multiple of C8: u % C8 == cg for every unit of a thread
+  const float* __restrict__ gsrc = P.io.g;
+  const float* __restrict__ addp = P.io.add;
   float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int rr = 0; rr < P.rpb; ++rr) {
-    const int row = blockIdx.x * P.rpb + rr;
-    if (row >= rows_total) break;
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < units; u += ustride) {
+    const int row = u / units_per_row;
+    const int cq = (u - row * units_per_row) / C8;
     const int n = row / Hq;
     const int r = row - n * Hq - 2;
-    const bool row_in = r >= 0 && r < H;
-    // source rows of the dgrad grid that land on interior row r (itself + the folded ring)
-    int rs[2], nr = 0;
-    rs[nr++] = r + 2;
-    if (d.src_kind == 0 && row_in) {
-      if (d.fold == 0) {         // REFLECT adjoint: padded row -1 -> row 1, padded row H -> row H-2
-        if (r == 1) rs[nr++] = 1;
-        if (r == H - 2) rs[nr++] = H + 2;
-      } else if (d.fold == 1) {  // REPLICATE adjoint: padded row -1 -> row 0, padded row H -> row H-1
-        if (r == 0) rs[nr++] = 1;
-        if (r == H - 1) rs[nr++] = H + 2;
+    const int c = cq - 2;
+    const bool interior = r >= 0 && r < H && c >= 0 && c < W;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (interior) {
+      const long long in_pix = ((long long)n * H + r) * W + c;                 // NHWC pixel index
+      if (d.src_kind == 0) {
+        // rows / cols of the dgrad grid whose values land on (r, c): itself plus the folded ring
+        int rs[2], cs[2], nr = 0, nc = 0;
+        rs[nr++] = r + 2;
+        cs[nc++] = c + 2;
+        if (d.fold == 0) {         // REFLECT adjoint: padded row -1 -> row 1, padded row H -> row H-2
+          if (r == 1) rs[nr++] = 1;
+          if (r == H - 2) rs[nr++] = H + 2;
+          if (c == 1) cs[nc++] = 1;
+          if (c == W - 2) cs[nc++] = W + 2;
+        } else if (d.fold == 1) {  // REPLICATE adjoint: padded row -1 -> row 0, padded row H -> row H-1
+          if (r == 0) rs[nr++] = 1;
+          if (r == H - 1) rs[nr++] = H + 2;
+          if (c == 0) cs[nc++] = 1;
+          if (c == W - 1) cs[nc++] = W + 2;
+        }
+        for (int a = 0; a < nr; ++a)
+          for (int b = 0; b < nc; ++b) {
+            float t[8];
+            ld8(gsrc + (((long long)n * Hq + rs[a]) * Wq + cs[b]) * C + co, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += t[j];
+          }
+      } else if (d.src_kind == 1) {
+        ld8(gsrc + in_pix * C + co, v);
+      } else {                     // avg-pool adjoint: every pixel of a 2x2 window receives a quarter
+        ld8(gsrc + (((long long)n * (H / 2) + (r >> 1)) * (W / 2) + (c >> 1)) * C + co, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= 0.25f;
+      }
+      if (addp != nullptr) {
+        float t[8];
+        ld8(addp + in_pix * C + co, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += t[j];
+      }
+      if (d.mask_kind == 1) {
+        float y[8];
+        ld8(reinterpret_cast<const float*>(P.io.y_mask) + in_pix * C + co, y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= (y[j] > 0.f) ? 1.f : d.alpha;
+      } else if (d.mask_kind == 2) {
+        const uint4 yb = __ldg(reinterpret_cast<const uint4*>(
+            reinterpret_cast<const uint16_t*>(P.io.y_mask) + (((long long)n * (H + 2) + r + 1) * (W + 2) + c + 1) * C + co));
+        const uint32_t w4[4] = {yb.x, yb.y, yb.z, yb.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t hb = (w4[j >> 1] >> ((j & 1) * 16)) & 0xffffu;     // bf16 bits of hi(y)
+          const bool pos_y = hb != 0u && (hb & 0x8000u) == 0u;
+          v[j] *= pos_y ? 1.f : d.alpha;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bsum[j] += v[j];
+      if (P.io.dz_f32 != nullptr) {
+        float4* o = reinterpret_cast<float4*>(P.io.dz_f32 + in_pix * C + co);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
       }
     }
-    const float* g_row[2];
-    g_row[0] = P.io.g + ((long long)n * Hq + rs[0]) * Wq * C + co;
-    g_row[1] = P.io.g + ((long long)n * Hq + rs[nr - 1]) * Wq * C + co;
-    const long long in_row = ((long long)n * H + r) * W;                         // NHWC pixel index of (n, r, 0)
-    const long long pool_row = ((long long)n * (H / 2) + (r >> 1)) * (W / 2);
-    const long long ymask_row = ((long long)n * (H + 2) + r + 1) * (W + 2) + 1;  // hi plane of SPLIT_BF16_HALO
-    const long long out_row = (long long)row * Wq;
-    for (int cq = lane; cq < Wq; cq += P.ppb) {
-      const int c = cq - 2;
-      const bool interior = row_in && c >= 0 && c < W;
-      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (interior) {
-        if (d.src_kind == 0) {
-          int cs[2], nc = 0;
-          cs[nc++] = c + 2;
-          if (d.fold == 0) {
-            if (c == 1) cs[nc++] = 1;
-            if (c == W - 2) cs[nc++] = W + 2;
-          } else if (d.fold == 1) {
-            if (c == 0) cs[nc++] = 1;
-            if (c == W - 1) cs[nc++] = W + 2;
-          }
-          for (int a = 0; a < nr; ++a)
-            for (int b = 0; b < nc; ++b) {
-              float t[8];
-              ld8(g_row[a] + (long long)cs[b] * C, t);
+    if (P.io.dz_hi != nullptr) {
+      uint32_t ph[4], pl[4];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += t[j];
-            }
-        } else if (d.src_kind == 1) {
-          ld8(P.io.g + (in_row + c) * C + co, v);
-        } else {                     // avg-pool adjoint: every pixel of a 2x2 window receives a quarter
-          ld8(P.io.g + (pool_row + (c >> 1)) * C + co, v);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] *= 0.25f;
-        }
-        if (P.io.add != nullptr) {
-          float t[8];
-          ld8(P.io.add + (in_row + c) * C + co, t);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += t[j];
-        }
-        if (d.mask_kind == 1) {
-          float y[8];
-          ld8(reinterpret_cast<const float*>(P.io.y_mask) + (in_row + c) * C + co, y);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] *= (y[j] > 0.f) ? 1.f : d.alpha;
-        } else if (d.mask_kind == 2) {
-          const uint4 yb = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(P.io.y_mask) +
-                                                               (ymask_row + c) * C + co));
-          const uint32_t w4[4] = {yb.x, yb.y, yb.z, yb.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t hb = (w4[j >> 1] >> ((j & 1) * 16)) & 0xffffu;     // bf16 bits of hi(y)
-            const bool pos_y = hb != 0u && (hb & 0x8000u) == 0u;
-            v[j] *= pos_y ? 1.f : d.alpha;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) bsum[j] += v[j];
-        if (P.io.dz_f32 != nullptr) {
-          float4* o = reinterpret_cast<float4*>(P.io.dz_f32 + (in_row + c) * C + co);
-          o[0] = make_float4(v[0], v[1], v[2], v[3]);
-          o[1] = make_float4(v[4], v[5], v[6], v[7]);
-        }
+      for (int j = 0; j < 4; ++j) {
+        uint32_t h0, l0, h1, l1;
+        tmx_split_bf16(v[2 * j], h0, l0);
+        tmx_split_bf16(v[2 * j + 1], h1, l1);
+        ph[j] = h0 | (h1 << 16);
+        pl[j] = l0 | (l1 << 16);
       }
-      if (P.io.dz_hi != nullptr) {
-        uint32_t ph[4], pl[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t h0, l0, h1, l1;
-          tmx_split_bf16(v[2 * j], h0, l0);
-          tmx_split_bf16(v[2 * j + 1], h1, l1);
-          ph[j] = h0 | (h1 << 16);
-          pl[j] = l0 | (l1 << 16);
-        }
-        long long o;
-        if (!d.phase_pack) {
-          o = (out_row + cq) * C + co;
-        } else {
-          // half-resolution grid [N][H/2+4][W/2+4][4C]; position (r,c) -> low-res (r>>1, c>>1), phase (r&1, c&1).
-          // Ring positions of the full-res grid have no image there; the low-res ring is zeroed by the host.
-          if (!interior) continue;
-          const int Hl = H / 2 + 4, Wl = W / 2 + 4;
-          const int phs = ((r & 1) << 1) | (c & 1);
-          o = ((((long long)n * Hl + (r >> 1) + 2) * Wl + (c >> 1) + 2) * 4 + phs) * C + co;
-        }
-        *reinterpret_cast<uint4*>(P.io.dz_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-        *reinterpret_cast<uint4*>(P.io.dz_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+      long long o;
+      if (!d.phase_pack) {
+        o = ((long long)row * Wq + cq) * C + co;
+      } else {
+        // half-resolution grid [N][H/2+4][W/2+4][4C]; position (r,c) -> low-res (r>>1, c>>1), phase (r&1, c&1).
+        // Ring positions of the full-res grid have no image there; the low-res ring is zeroed by the host.
+        if (!interior) continue;
+        const int Hl = H / 2 + 4, Wl = W / 2 + 4;
+        const int phs = ((r & 1) << 1) | (c & 1);
+        o = ((((long long)n * Hl + (r >> 1) + 2) * Wl + (c >> 1) + 2) * 4 + phs) * C + co;
       }
+      *reinterpret_cast<uint4*>(P.io.dz_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      *reinterpret_cast<uint4*>(P.io.dz_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     }
   }
   if (P.io.dbias != nullptr) {
-    float* mine = red + (lane * P.C8 + cg) * 8;
+    const int lanes = blockDim.x / C8;
+    float* mine = red + (threadIdx.x / C8) * C + co;
 #pragma unroll
     for (int j = 0; j < 8; ++j) mine[j] = bsum[j];
     __syncthreads();
-    // all threads reduce: thread t sums channel t of the block's lanes (C <= 2048, threads = ppb * C8 >= C / 8)
+    // all threads reduce: thread t sums channel t of the block's lanes
     for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
       float s = 0.f;
-      for (int l = 0; l < P.ppb; ++l) s += red[l * C + ch];
+      for (int l = 0; l < lanes; ++l) s += red[l * C + ch];
       atomicAdd(P.io.dbias + ch, s * d.dbias_scale);
     }
   }
@@ -187,16 +179,17 @@ extern "C" int tmx_grad_prepare(tmx_handle_t h, const tmx_grad_desc_t* d, const 
   P.d = *d;
   P.io = *io;
   P.C8 = d->C / 8;
-  P.ppb = 256 / P.C8 > 0 ? 256 / P.C8 : 1;
-  if (P.ppb > d->W + 4) P.ppb = d->W + 4;      // narrow maps: no idle lanes
+  P.ppb = 256 / P.C8 > 0 ? 256 / P.C8 : 1;      // lanes: threads = lanes * C8 (a multiple of C8, <= 256)
   const int threads = P.ppb * P.C8;
-  // rows per block: amortise the bias-gradient atomics on the big maps, but keep >= 8 CTAs per SM in flight on the
-  // small ones (most of the ~390 calls of a train step)
-  P.rpb = 8;
-  while (P.rpb > 1 && (rows + P.rpb - 1) / P.rpb < 8LL * h->sm_count) P.rpb >>= 1;
+  const long long units = rows * (long long)(d->W + 4) * P.C8;
+  TMX_REQUIRE(units < (1ll << 31) - (1 << 20), TMX_ERR_SHAPE, "tmx_grad_prepare: grid too large");
+  // persistent-style grid: 4 resident CTAs per SM (64 registers per thread), fewer when the map is small
+  long long blocks = (units + threads - 1) / threads;
+  if (blocks > 4LL * h->sm_count) blocks = 4LL * h->sm_count;
+  P.rpb = 0;
   const size_t smem = io->dbias ? (size_t)threads * 8 * sizeof(float) : 0;
   TMX_REQUIRE(threads <= 256 && smem <= 48 * 1024, TMX_ERR_SHAPE, "tmx_grad_prepare: C=%d not supported", d->C);
-  grad_prepare_kernel<<<tmx_ceil_div(rows, P.rpb), threads, smem, (cudaStream_t)s>>>(P);
+  grad_prepare_kernel<<<(unsigned)blocks, threads, smem, (cudaStream_t)s>>>(P);
   TMX_LAUNCHED(h, "grad_prepare_kernel");
   return TMX_OK;
 }

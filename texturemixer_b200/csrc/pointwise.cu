@@ -917,34 +917,39 @@ extern "C" int tmx_bias_act(tmx_handle_t h, const float* x, const float* bias, f
 // Tensors are [A][H][W][B] fp32: NCHW -> A = N*C, B = 1; NHWC -> A = N, B = C.
 //   embed == 0: dst[A][wh][ww][B] = src[A][oy + y][ox + x][B]
 //   embed == 1: dst[A][H][W][B]   = src[A][y - oy][x - ox][B] inside the window, 0 elsewhere (adjoint of the slice)
-__global__ void __launch_bounds__(256) window_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int A,
-                                                          int H, int W, int B, int wh, int ww, int oy_h, int ox_h,
-                                                          const int32_t* __restrict__ off_dev, int embed, int vec) {
+// One thread = 4 consecutive floats of a DESTINATION row (rows are W*B or ww*B floats long, a multiple of 4: the host
+// checks), stored as one float4; the source side is read with scalar loads (an NCHW window starts at any x) or one
+// float4 (NHWC: pixels are >= 16 B).
+__global__ void __launch_bounds__(256) window_copy_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                          long long quads, int H, int W, int B, int wh, int ww, int oy_h,
+                                                          int ox_h, const int32_t* __restrict__ off_dev, int embed,
+                                                          int vec) {
   const int oy = off_dev ? __ldg(off_dev) : oy_h, ox = off_dev ? __ldg(off_dev + 1) : ox_h;
-  // one block row = one (a, y) row of the DESTINATION; threads run along x*B (in float4 units when vec)
-  const int rows_h = embed ? H : wh;
-  const int row = blockIdx.x;
-  const int a = row / rows_h, y = row - a * rows_h;
-  const int dw = embed ? W : ww;                          // destination row width in pixels
-  const int unit = vec ? 4 : 1;
-  const int per_row = dw * B / unit;
-  if (!embed) {
-    const float* s = src + (((long long)a * H + oy + y) * W + ox) * B;
-    float* d = dst + ((long long)a * wh + y) * ww * B;
-    for (int i = threadIdx.x; i < per_row; i += blockDim.x) {
-      if (vec) reinterpret_cast<float4*>(d)[i] = __ldg(reinterpret_cast<const float4*>(s) + i);
-      else d[i] = __ldg(s + i);
+  const int rows_h = embed ? H : wh;                       // destination rows per slab a
+  const int q_per_row = (embed ? W : ww) * B / 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += stride) {
+    const long long row = q / q_per_row;
+    const int e0 = (int)(q - row * q_per_row) * 4;         // first float of the quad inside its row
+    const int a = (int)(row / rows_h), y = (int)(row - (long long)a * rows_h);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!embed) {
+      const float* sp = src + (((long long)a * H + oy + y) * W + ox) * B + e0;
+      if (vec) v = __ldg(reinterpret_cast<const float4*>(sp));
+      else v = make_float4(__ldg(sp), __ldg(sp + 1), __ldg(sp + 2), __ldg(sp + 3));
+    } else if (y >= oy && y < oy + wh) {
+      const float* sp = src + (((long long)a * wh + (y - oy)) * ww - ox) * B + e0;   // sp[i] valid inside the window
+      const int lo = ox * B, hi = (ox + ww) * B;
+      if (vec) {
+        if (e0 >= lo && e0 < hi) v = __ldg(reinterpret_cast<const float4*>(sp));
+      } else {
+        v.x = (e0 >= lo && e0 < hi) ? __ldg(sp) : 0.f;
+        v.y = (e0 + 1 >= lo && e0 + 1 < hi) ? __ldg(sp + 1) : 0.f;
+        v.z = (e0 + 2 >= lo && e0 + 2 < hi) ? __ldg(sp + 2) : 0.f;
+        v.w = (e0 + 3 >= lo && e0 + 3 < hi) ? __ldg(sp + 3) : 0.f;
+      }
     }
-  } else {
-    float* d = dst + ((long long)a * H + y) * W * B;
-    const bool row_in = y >= oy && y < oy + wh;
-    const float* s = src + (((long long)a * wh + (y - oy)) * ww - ox) * B;   // s[x*B + b] valid for x in [ox, ox+ww)
-    const int lo = ox * B / unit, hi = (ox + ww) * B / unit;
-    for (int i = threadIdx.x; i < per_row; i += blockDim.x) {
-      const bool in = row_in && i >= lo && i < hi;
-      if (vec) reinterpret_cast<float4*>(d)[i] = in ? __ldg(reinterpret_cast<const float4*>(s) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-      else d[i] = in ? __ldg(s + i) : 0.f;
-    }
+    reinterpret_cast<float4*>(dst)[q] = v;
   }
 }
 
@@ -955,14 +960,16 @@ extern "C" int tmx_window_copy(tmx_handle_t h, const float* src, float* dst, int
               "tmx_window_copy: bad shape A=%lld H=%d W=%d B=%d window %dx%d", (long long)A, H, W, B, wh, ww);
   TMX_REQUIRE(off_dev != nullptr || (oy >= 0 && ox >= 0 && oy + wh <= H && ox + ww <= W), TMX_ERR_SHAPE,
               "tmx_window_copy: window (%d,%d)+%dx%d outside %dx%d", oy, ox, wh, ww, H, W);
-  const long long rows = A * (embed ? H : wh);
-  TMX_REQUIRE(rows < (1ll << 31), TMX_ERR_SHAPE, "tmx_window_copy: too many rows");
-  const int vec = (B % 4 == 0) ? 1 : 0;          // NHWC rows are 16-B aligned at any pixel offset; NCHW are not
-  const int per_row = (embed ? W : ww) * B / (vec ? 4 : 1);
-  int threads = 32;
-  while (threads < 256 && threads < per_row) threads <<= 1;
-  window_copy_kernel<<<(unsigned)rows, threads, 0, (cudaStream_t)s>>>(src, dst, (int)A, H, W, B, wh, ww, oy, ox, off_dev,
-                                                                      embed, vec);
+  const long long row_len = (long long)(embed ? W : ww) * B;
+  TMX_REQUIRE(row_len % 4 == 0, TMX_ERR_SHAPE, "tmx_window_copy: destination rows of %lld floats (need a multiple of 4)",
+              row_len);
+  const long long quads = A * (embed ? H : wh) * row_len / 4;
+  const int vec = (B % 4 == 0) ? 1 : 0;          // NHWC pixels are 16-B aligned at any offset; NCHW windows are not
+  long long blocks = (quads + 255) / 256;
+  const long long cap = (long long)h->sm_count * 32;
+  if (blocks > cap) blocks = cap;
+  window_copy_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(src, dst, quads, H, W, B, wh, ww, oy, ox, off_dev,
+                                                                   embed, vec);
   TMX_LAUNCHED(h, "window_copy_kernel");
   return TMX_OK;
 }
