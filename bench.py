@@ -164,12 +164,14 @@ def run_reference_train(args):
     create_graph gradient penalty, TF1 Adam restatement) on all host cores.  One step = ONE whole train step on a
     bounded sample of CPU_TRAIN_SAMPLE images of the 32-image minibatch (whole 3x3 canvases: the reference decodes
     them whole), so that K steps end within minutes."""
-    ips, sec, cores = time_oracle_train_step(CPU_TRAIN_SAMPLE, steps=args.steps, warmup=args.warmup, budget_s=240.0)
+    gram = args.gram != 'off'
+    ips, sec, cores = time_oracle_train_step(CPU_TRAIN_SAMPLE, steps=args.steps, warmup=args.warmup, budget_s=240.0,
+                                             gram=gram)
     line = {
         'impl': 'reference', 'metric': TRAIN_METRIC, 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'steps_timed': time_oracle_train_step.steps_done, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': TRAIN_WORKLOAD, 'batch_per_gpu': TRAIN_BATCH,
+        'config': {'workload': train_workload(gram), 'batch_per_gpu': TRAIN_BATCH,
                    'note': 'CPU restatement of the TF1 graph (oracle/); TensorFlow 1.12 is not installable here'},
         'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': CPU_TRAIN_DESC},
         'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -336,8 +338,21 @@ def run_ours(args):
 # ------------------------------------------------------------------ train step (BASELINE configs[2] / [4])
 TRAIN_BATCH = 32
 TRAIN_METRIC = '128x128 texture images/sec (full train step: 3 critics + E/G + EMA)'
-TRAIN_WORKLOAD = ('cfg3/5: full train step (run.py:510-514), batch 32 per GPU, lod 0, gram_weight 0, 3x3 canvases, '
-                  'a fresh minibatch for the critic phase and for the E/G phase like the reference')
+TRAIN_WORKLOAD_FMT = ('cfg3/5: full train step (run.py:510-514), batch 32 per GPU, lod 0, %s, 3x3 canvases, '
+                      'a fresh minibatch for the critic phase and for the E/G phase like the reference')
+GRAM_DESC = {True: 'gram_weight 0.002 (config.py:64: the three VGG-19 Gram terms of EG_wgan; seeded stand-in weights with '
+                   "vgg19.npy's layout - the file is not redistributable - same arithmetic)",
+             False: 'gram_weight 0 (VGG-19 Gram terms off)'}
+
+
+def train_workload(gram):
+    return TRAIN_WORKLOAD_FMT % GRAM_DESC[bool(gram)]
+
+
+# VGG-19 Gram terms (custom_vgg19.py:42-65 up to conv5_1 on 128x128: 11.83 GFLOP forward per image; Gram matrices of
+# the five layers 0.57): features of the real minibatch once (forward) + of rec / interp crop / blend crop (forward
+# and data gradient) = 7 x 11.83, Gram products 4 forward + 3 backward x 0.57
+GRAM_GFLOP = 7 * 11.83 + 7 * 0.57
 # Algorithmic GFLOP per sample of one train step (gram off).  The critic phase and the E/G phase each
 # consume their own minibatch like the reference (run.py:286,511-512), so the encoders and the reconstruction run
 # forward once more for the critics' fakes: E 4 F-units 7.47 + G (scale 1) 4 units 51.6 + three D 51.2 = 110.3, plus
@@ -347,18 +362,20 @@ TRAIN_WORKLOAD = ('cfg3/5: full train step (run.py:510-514), batch 32 per GPU, l
 #                    (identical results, SURVEY Appendix C note), the last 4 latent-resolution convs on 48x48
 #                    (loss.mid_window) and the up-sampling blocks + ToRGB on 40x40 (loss.tail_window): per unit
 #                    8 x 1.208 x 4 + 2.7935 x (48/32)^2 + 0.4546 x (40/32)^2 = 45.65 -> 8 x 45.65 + 110.3 = 475.5
-TRAIN_GFLOP = {True: 475.5, False: 1039.9}
+TRAIN_GFLOP = {True: 475.5, False: 1039.9}     # + GRAM_GFLOP when the Gram terms are on
 # dominant kernel of the step: conv_tc_kernel<256,64,32,PAIR> on the 64x64 trunk windows (3x3, 256 -> 256, batch 32)
 TRUNK64_GFLOP = 2 * 9 * 256 * 256 * 64 * 64 * TRAIN_BATCH / 1e9          # 154.6 GFLOP per launch
 # dram__bytes_read.sum + dram__bytes_write.sum of one such launch from the committed `ncu --set full` capture
-TRUNK64_DRAM_BYTES = None
-TRUNK64_DRAM_SOURCE = None
+# (Residual_0 form - planes out: 145.7 MB read + 93.9 MB written; Residual_1 form - fp32 residual in, fp32 + planes
+# out: 284.3 + 227.1 MB; the step launches both forms equally often; algorithmic bytes 285 / 571 MB)
+TRUNK64_DRAM_BYTES = 0.5 * ((145.7408e6 + 93.9443e6) + (284.2550e6 + 227.1145e6))
+TRUNK64_DRAM_SOURCE = 'profiles/r02_ncu_kernels_summary.csv ids 0 and 14 (ncu --set full of profiles/kernel_targets.py)'
 CPU_TRAIN_SAMPLE = 2
 CPU_TRAIN_DESC = ('one whole train step per step on %d images (whole 3x3 canvases, autograd incl. the gradient penalty), '
                   'torch-CPU fp32 restatement (oracle/)' % CPU_TRAIN_SAMPLE)
 
 
-def time_oracle_train_step(sample=2, steps=1, warmup=0, budget_s=None):
+def time_oracle_train_step(sample=2, steps=1, warmup=0, budget_s=None, gram=True):
     """`steps` train steps of the CPU restatement (oracle/: autograd losses incl. the create_graph gradient penalty,
     TF1 Adam restatement) on `sample` images each, all host cores, after `warmup` untimed ones.
     -> (samples/s, seconds per step, cores)."""
@@ -375,6 +392,11 @@ def time_oracle_train_step(sample=2, steps=1, warmup=0, budget_s=None):
     params = {k: R.init_params(f, rng, **R.CONFIG[f]) for k, f in funcs.items()}
     mix = lambda: torch.from_numpy(rng.uniform(0, 1, (sample, 1, 1, 1)).astype(np.float32))   # noqa: E731
     crop = lambda: (int(rng.randint(0, 256)), int(rng.randint(0, 256)))                        # noqa: E731
+    gram_kw = {}
+    if gram:
+        from texturemixer_b200.vgg import standin_weights           # data only (numpy): the same stand-in as our arm
+        vgg = standin_weights()
+        gram_kw = lambda: dict(gram_weight=0.002, vgg=vgg, gram_alpha=mix())                   # noqa: E731
 
     def flat_grads(P):
         return np.concatenate([(t.grad.numpy() if t.grad is not None else np.zeros(tuple(t.shape), np.float32)).reshape(-1)
@@ -407,7 +429,7 @@ def time_oracle_train_step(sample=2, steps=1, warmup=0, budget_s=None):
             loss.mean().backward()
             adam(k, P[k])
         P = {k: R.to_torch(params[k], requires_grad=k in ('E_zg', 'E_zl', 'G')) for k in funcs}
-        loss, _ = L.EG_wgan(P, x, idx, crop(), crop(), mix())          # run.py:512
+        loss, _ = L.EG_wgan(P, x, idx, crop(), crop(), mix(), **(gram_kw() if gram else {}))          # run.py:512
         loss.mean().backward()
         for k in ('E_zg', 'E_zl', 'G'):
             adam(k, P[k])
@@ -446,8 +468,14 @@ def run_train(args):
     cfg['crop_aware'] = not args.whole_canvas
     if args.graphs is not None:
         cfg['cuda_graphs'] = {'step': 'step', 'critics': 'critics', 'off': False}[args.graphs]
-    TRAIN_GFLOP_PER_SAMPLE = TRAIN_GFLOP[cfg['crop_aware']]
-    tr = Trainer(cfg, seed=1000, device=local)
+    gram = args.gram != 'off'
+    TRAIN_GFLOP_PER_SAMPLE = TRAIN_GFLOP[cfg['crop_aware']] + (GRAM_GFLOP if gram else 0.0)
+    TRAIN_WORKLOAD = train_workload(gram)
+    vgg_weights = None
+    if gram:
+        from texturemixer_b200.vgg import load_vgg19_npy, standin_weights
+        vgg_weights = standin_weights() if args.gram == 'standin' else load_vgg19_npy(args.gram)
+    tr = Trainer(cfg, seed=1000, device=local, vgg_weights=vgg_weights)
     rt, dev = tr.rt, tr.rt.device
     rng = np.random.RandomState(1000 + rank)
     np.random.seed(1000 + rank)
@@ -538,7 +566,7 @@ def run_train(args):
         tf_step = value * TRAIN_GFLOP_PER_SAMPLE / 1e3 / world
         cpu_line = None
         if world == 1:
-            cpu_v, cpu_s, cores = time_oracle_train_step(CPU_TRAIN_SAMPLE, steps=2, warmup=1)
+            cpu_v, cpu_s, cores = time_oracle_train_step(CPU_TRAIN_SAMPLE, steps=2, warmup=1, gram=gram)
             cpu_line = {'value': cpu_v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                         'sample': CPU_TRAIN_DESC + '; 2 timed steps after 1 warm-up, %.1f s per step' % cpu_s}
         roof = None
@@ -857,6 +885,9 @@ def main():
                          'gradient all-reduce; gen_fwd = configs[1]: G_res forward, batch 64')
     ap.add_argument('--graphs', default=None, choices=['step', 'critics', 'off'],
                     help='train_step: how the step is issued (default: whole step as CUDA graphs)')
+    ap.add_argument('--gram', default='standin',
+                    help="train_step: 'standin' (default) = the VGG-19 Gram terms of EG_wgan (gram_weight 0.002, "
+                         "config.py:64) with seeded stand-in weights; 'off' = gram_weight 0; or a path to vgg19.npy")
     ap.add_argument('--shared-minibatch', action='store_true',
                     help='train_step: critic and E/G phases see the SAME minibatch (one E/G forward serves both; '
                          'deviation from run.py:511-512)')

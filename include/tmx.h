@@ -76,6 +76,8 @@ int tmx_launch_count(tmx_handle_t h, uint64_t* count);
 #define TMX_CONV_XMERGE 64u  /* TC, Cin == 16, k == 3: operand rows carry the 3 horizontal taps (4 pixels = 128 B) of
                               * an overlapping-stride view; weights from tmx_conv_weights_prepare with xmerge = 1.
                               * The x planes must be allocated (and zero-filled) 64 elements past their end. */
+#define TMX_CONV_HALO_ZERO 128u /* split-plane output keeps a ZERO halo: the kernel writes the interior only, the caller
+                                 * hands in zeroed planes (consumer is a SAME-padded conv: VGG-19, fused_scale) */
 
 #define TMX_ALGO_AUTO 0
 #define TMX_ALGO_FFMA 1 /* CUDA-core fp32 implicit GEMM, NHWC f32 in/out */
@@ -345,6 +347,22 @@ int tmx_kl_terms(tmx_handle_t h, const float* mu, const float* log_sigma, float*
  *   src[A][wh][ww][B] placed at (oy, ox), zeros elsewhere (every element of dst is written). */
 int tmx_window_copy(tmx_handle_t h, const float* src, float* dst, int64_t A, int H, int W, int B, int wh, int ww,
                     int oy, int ox, const int32_t* off_dev, int embed, tmx_stream_t s);
+
+/* ------------------------------------------------------------------ VGG-19 Gram-matrix loss
+ * custom_vgg19.py:31-40: out[n][y][x][0..2] = ((rgb + 1) / 2 * 255)[BGR] - (103.939, 116.779, 123.68), channels 3..15
+ *   zero (NHWC, 16 channels = one tensor-core K chunk), from an NCHW image in [-1, 1]; _bwd: its adjoint.
+ * tmx_gram_fwd   (loss.py:29-35): G[n][i][j] = sum_p F[n][i][p] F[n][j][p] / H / W, F = NCHW features [N][C][H*W].
+ * tmx_gram_l1    (loss.py:68-75 multi_layer_diff + its gradient): per sample n, sums[n] += val_scale * sum |G[n] - T[n']|
+ *                and S[n] = (accumulate ? S[n] : 0) + coef * sign(G[n] - T[n']), n' = N-1-n when reverse_t; both are
+ *                further scaled by w = 1 / *wdev / 1 - *wdev (wmode 0 / 1 / 2; the blend weight of loss.py:253-254).
+ * tmx_gram_bwd   dF[n][i][p] = sum_j (S[n][i][j] + S[n][j][i]) F[n][j][p] / H / W. */
+int tmx_vgg_preprocess(tmx_handle_t h, const float* img_nchw, float* out_nhwc16, int N, int H, int W, tmx_stream_t s);
+int tmx_vgg_preprocess_bwd(tmx_handle_t h, const float* dout_nhwc16, float* dimg_nchw, int N, int H, int W,
+                           tmx_stream_t s);
+int tmx_gram_fwd(tmx_handle_t h, const float* F, float* G, int N, int C, int H, int W, tmx_stream_t s);
+int tmx_gram_l1(tmx_handle_t h, const float* G, const float* T, float* S, float* sums, int N, int C, int reverse_t,
+                float coef, float val_scale, int accumulate, const float* wdev, int wmode, tmx_stream_t s);
+int tmx_gram_bwd(tmx_handle_t h, const float* S, const float* F, float* dF, int N, int C, int H, int W, tmx_stream_t s);
 
 /* out = a + b over n fp32 elements (two gradient contributions meeting at one tensor). */
 int tmx_add_f32(tmx_handle_t h, const float* a, const float* b, float* out, int64_t n, tmx_stream_t s);

@@ -15,6 +15,12 @@ VGG_ORDER = ('conv1_1', 'conv1_2', 'pool1', 'conv2_1', 'conv2_2', 'pool2', 'conv
 GRAM_LAYERS = ('conv1_1', 'conv2_1', 'conv3_1', 'conv4_1', 'conv5_1')                     # loss.py:153
 
 
+def relu(x):
+    """tensorflow_vgg's conv_layer activation; a module-level hook so that a test can feed the device's branch masks
+    (tests/test_gpu_gram.py), like networks_ref.leaky_relu."""
+    return torch.relu(x)
+
+
 def vgg_features(images, data_dict, upto='conv5_1'):
     """images: [N,3,H,W] RGB in [-1,1] (NCHW).  -> {layer: NCHW activation} for the layers of GRAM_LAYERS.
     custom_vgg19.py:31-40: x = (rgb + 1) / 2 * 255, BGR order, minus VGG_MEAN; then conv (SAME zero pad) + bias +
@@ -30,7 +36,7 @@ def vgg_features(images, data_dict, upto='conv5_1'):
             w, bias = data_dict[name]
             w = torch.as_tensor(w, dtype=x.dtype)
             bias = torch.as_tensor(bias, dtype=x.dtype)
-            x = torch.relu(F.conv2d(x, w.permute(3, 2, 0, 1), padding=1) + bias.reshape(1, -1, 1, 1))
+            x = relu(F.conv2d(x, w.permute(3, 2, 0, 1), padding=1) + bias.reshape(1, -1, 1, 1))
             if name in GRAM_LAYERS:
                 out[name] = x
         if name == upto:

@@ -49,7 +49,7 @@ def _mask_of(rt, y):
     return dict(y_f32=rt.split_unpack(y).f32)
 
 
-def _combine(rt, act, contribs, want_planes, want_f32, mask_y=None, dbias=None, phase_pack=False):
+def _combine(rt, act, contribs, want_planes, want_f32, mask_y=None, dbias=None, phase_pack=False, alpha=None):
     """All contributions to dL/d(act) -> (planes on the zero-ringed grid, fp32 NHWC), masked by lrelu'(mask_y);
     `mask_y` is an fp32 map or the dict returned by `_mask_of`."""
     mask_kw = mask_y if isinstance(mask_y, dict) else dict(y_f32=mask_y)
@@ -75,7 +75,7 @@ def _combine(rt, act, contribs, want_planes, want_f32, mask_y=None, dbias=None, 
         src, kind, fold = f32s[0], 1, 2
         add = f32s[1] if len(f32s) == 2 else None
     return rt.grad_prepare(src, n, h, w, c, kind, fold=fold, add=add, want_planes=want_planes,
-                           want_f32=want_f32, dbias=dbias, phase_pack=phase_pack, **mask_kw)
+                           want_f32=want_f32, dbias=dbias, phase_pack=phase_pack, alpha=alpha, **mask_kw)
 
 
 def _scaled(rt, x, a):
@@ -215,6 +215,17 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
                 _, g = _combine(rt, rec['y'], contribs, want_planes=False, want_f32=True)
                 x = rec['x']
                 grads.add(x, ('f32', rt.window_embed(g, rec['win'], x.h, x.w, nhwc=True)))
+        elif kind == 'vggpre':             # custom_vgg19.py:31-40 input scaling (16-channel padded NHWC)
+            contribs = grads.pop(rec['y'])
+            if contribs and want_input_grads:
+                y = rec['y']
+                _, g = _combine(rt, y, contribs, want_planes=False, want_f32=True)
+                img = rec['img']
+                n, _, h, w = img.shape
+                dimg = rt.empty(n, 3, h, w)
+                _lib.check(rt.lib.tmx_vgg_preprocess_bwd(rt.handle, _ptr(g), _ptr(dimg), n, h, w, rt.stream()),
+                           'tmx_vgg_preprocess_bwd')
+                _accumulate(rt, input_grads, ('img', id(img)), dimg)
         elif kind == 'imgpool':            # the input image pooled for a lower level of detail (networks.py:278,281)
             g = input_grads.pop(('img', id(rec['y'])), None)
             if g is not None:
@@ -314,7 +325,7 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
             zero_pad = rec.get('halo') == 'zero'        # fused_scale layers: SAME (zero) padding, nothing to fold
             dz, dz_f32 = _combine(rt, y, contribs, want_planes=True, want_f32=has_res, mask_y=mask,
                                   dbias=gview(rec['b']) if (param_grads and rec['b'] is not None) else None,
-                                  phase_pack=up2)
+                                  phase_pack=up2, alpha=rec.get('alpha'))
             if has_res:
                 grads.add(rec['residual'], ('f32', dz_f32))         # y = conv(x) + residual (networks.py:437)
             if adjoints is not None:

@@ -70,16 +70,18 @@ struct ConvTcParams {
   int lrelu, has_res, up2_out;
   int phase;      // UP2_IN sub-pixel form: GEMM column = (a*2+b)*cout_log + c, output pixel (2y+a, 2x+b)
   int cout_log;   // logical Cout of the layer (== Cout unless phase)
-  int halo_rep;   // written planes get a REPLICATE (clamp) halo instead of REFLECT
+  int halo_rep;   // halo of the written planes: 0 REFLECT, 1 REPLICATE (clamp), 2 ZERO (left as the caller zeroed it)
   // LIN mode (data gradient): pixels are the rows of ONE zero-ringed grid [N][H+4][W+4] shared by input and
   // output; a tile is 128 consecutive grid rows, tap (U,V) is the constant row shift (U-1)*pitch + (V-1), so the
   // A operand is a 2-D TMA box at row m0 + shift (out-of-range rows read zeros) and every grid position -
   // including the ring the reflect/replicate adjoint folds back - is produced.  Output: fp32 rows only.
   int lin, lin_pitch;
   long long lin_rows;
-  // PATCH mode (X-MERGED 3-tap layers, opt-in with TMX_XMERGE_PATCH=1; NOT yet validated on a GPU): one stage = one
-  // tile; the A operand of all three vertical taps is ONE haloed patch [(bh+2) rows][bw px][128 B] per plane, tap u
-  // reads it from row offset u*bw (a whole number of 8-row swizzle atoms), the three weight boxes follow it.
+  // PATCH mode (X-MERGED 3-tap layers; TMX_NO_XMERGE_PATCH=1 turns it off for A/B runs): one stage = one tile; the A
+  // operand of all three vertical taps is ONE haloed patch [(bh+2) rows][bw px][128 B] per plane, tap u reads it
+  // from row offset u*bw (a whole number of 8-row swizzle atoms), the three weight boxes follow it.  These layers
+  // run at the L2 throughput cap (~7.7 TB/s of L2->SM sectors, ncu): the patch cuts the sectors per tile by a third
+  // (21.2 M -> 14.3 M for 16->16 at 128x128, batch 32: 87 -> 62 us; profiles/r02_ncu_thin_patch_summary.csv).
   int patch, patch_bytes, patch_stage_bytes, patch_stages;
   float alpha;
   const float* bias;
@@ -360,8 +362,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int Ho = p.up2_out ? 2 * Hl : Hl, Wo = p.up2_out ? 2 * Wl : Wl;      // size of the written planes
     const long long Hp = Ho + 2, Wp = Wo + 2;
     const int CL = p.cout_log;
-    const int lo_edge = p.halo_rep ? 0 : 1;                // source row/col copied into halo slot 0
-    const int hi_off = p.halo_rep ? 1 : 2;                 // ... and (size - hi_off) into slot size+1
+    // source row/col copied into halo slot 0, and (size - hi_off) into slot size+1; ZERO halo: no pixel matches
+    const int lo_edge = p.halo_rep == 1 ? 0 : (p.halo_rep == 2 ? -7 : 1);
+    const int hi_off = p.halo_rep == 1 ? 1 : (p.halo_rep == 2 ? -7 : 2);
     const bool has_bias = p.bias != nullptr;
     const float slope = p.lrelu ? p.alpha : 1.f;
     const float4* rgb_s = reinterpret_cast<const float4*>(rgb_smem);
@@ -706,8 +709,10 @@ int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_i
               "tmx_conv2d_fwd[TC]: UP2_OUT applies to the split-plane output");
   TMX_REQUIRE(!(phase && (d->flags & TMX_CONV_UP2_OUT)), TMX_ERR_UNSUPPORTED,
               "tmx_conv2d_fwd[TC]: UP2_IN and UP2_OUT cannot be combined");
-  TMX_REQUIRE(!((d->flags & TMX_CONV_HALO_REPLICATE) && (d->flags & TMX_CONV_UP2_OUT)), TMX_ERR_UNSUPPORTED,
-              "tmx_conv2d_fwd[TC]: HALO_REPLICATE and UP2_OUT cannot be combined");
+  TMX_REQUIRE(!((d->flags & (TMX_CONV_HALO_REPLICATE | TMX_CONV_HALO_ZERO)) && (d->flags & TMX_CONV_UP2_OUT)),
+              TMX_ERR_UNSUPPORTED, "tmx_conv2d_fwd[TC]: HALO_REPLICATE / HALO_ZERO and UP2_OUT cannot be combined");
+  TMX_REQUIRE(!((d->flags & TMX_CONV_HALO_REPLICATE) && (d->flags & TMX_CONV_HALO_ZERO)), TMX_ERR_ARG,
+              "tmx_conv2d_fwd[TC]: HALO_REPLICATE and HALO_ZERO exclude each other");
   TMX_REQUIRE(!(d->flags & TMX_CONV_RESIDUAL) || io->residual, TMX_ERR_ARG,
               "tmx_conv2d_fwd[TC]: RESIDUAL flag without residual pointer");
   TMX_REQUIRE(!(phase && (d->flags & TMX_CONV_RESIDUAL)), TMX_ERR_UNSUPPORTED,
@@ -767,7 +772,7 @@ int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_i
   p.up2_out = (d->flags & TMX_CONV_UP2_OUT) != 0;
   p.phase = phase;
   p.cout_log = d->Cout;
-  p.halo_rep = (d->flags & TMX_CONV_HALO_REPLICATE) != 0;
+  p.halo_rep = (d->flags & TMX_CONV_HALO_REPLICATE) ? 1 : ((d->flags & TMX_CONV_HALO_ZERO) ? 2 : 0);
   p.alpha = d->lrelu_alpha;
   p.bias = io->bias;
   p.residual = io->residual;
@@ -784,17 +789,18 @@ int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_i
   CUtensorMap maps[6];
   int rc;
   const int xw = xmerge ? 4 : 1;
-  // PATCH mode (experimental, off unless TMX_XMERGE_PATCH=1): see ConvTcParams::patch
+  // PATCH mode: see ConvTcParams::patch
   p.patch = p.patch_bytes = p.patch_stage_bytes = p.patch_stages = 0;
   int box_h = p.bh;
-  if (xmerge && tmx_env_flag("TMX_XMERGE_PATCH") && p.bn == 1 && p.bw % 8 == 0 && bnc <= 64) {
+  if (xmerge && !tmx_env_flag("TMX_NO_XMERGE_PATCH") && p.bn == 1 && p.bw % 8 == 0 && bnc <= 64) {
     const int k_a = kTileM * 64 * 2, k_b = bnc * 64 * 2;                  // TcCfg<bnc, 64>: bytes per plane
     const int stage = 2 * k_a + 2 * k_b;
     int stages = (200 * 1024) / stage;
     if (stages > 12) stages = 12;
     const int patch_bytes = (p.bh + 2) * p.bw * 64 * 2;
     const int patch_stage = 2 * patch_bytes + 6 * k_b;
-    const int patch_stages = (stages * stage) / patch_stage;
+    int patch_stages = (stages * stage) / patch_stage;     // inside the launch's stage area (TcCfg::kStages * kStageBytes)
+    if (patch_stages > stages) patch_stages = stages;      // one full/empty barrier pair per stage exists
     if (patch_stages >= 2) {
       p.patch = 1;
       p.patch_bytes = patch_bytes;

@@ -1,7 +1,8 @@
 """E/G phase of the train step: `loss.EG_wgan` (loss.py:105-259) evaluated and
 differentiated on the device.  Reference config (config.py:50-68): zg 'hard', zl
-'permutational'; the KL term (kl_weight, 0 in the reference config) is supported; gram_weight is forced to 0 (VGG-19 weights are not
-redistributable, SURVEY §2 - stated deviation).
+'permutational'; the KL term (kl_weight, 0 in the reference config) is supported; the VGG-19 Gram terms
+(gram_weight, 0.002 in the reference config) run when a `vgg.GramLoss` is supplied - the weight file itself is not
+redistributable, so benchmarks state whether they ran with a stand-in or without the term.
 
 The forward builds exactly the reference graph (encoders once, G at scale 1, G_fcn
 twice on the 3x3 canvases, the three critics as fixed functions); the backward is the
@@ -370,11 +371,14 @@ def critic_input_gradient(D, images, weight):
 
 
 def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, rec_G_weight=1.0, pixel_weight=200.0,
-                interp_G_weight=1.0, blend_interp_G_weight=1.0, reals_fade=None, critic_grads=None, kl_weight=0.0):
+                interp_G_weight=1.0, blend_interp_G_weight=1.0, reals_fade=None, critic_grads=None, kl_weight=0.0,
+                gram=None, gram_weight=0.0, gram_alpha=None):
     """Loss terms of `EG_wgan` on the images of `fwd` and the whole reverse pass into `grads`.  `reals_fade`: the
     target of the pixel loss (loss.py:143) when it differs from what the encoders saw (fractional lod).
     `critic_grads`: optional {'rec' | 'interp' | 'blend': critic_input_gradient(...)} evaluated by the caller (the
-    trainer replays them as CUDA graphs on parallel streams)."""
+    trainer runs them on parallel streams).
+    `gram` (a vgg.GramLoss) with gram_weight > 0 adds the VGG-19 Gram terms of loss.py:148-160, 206-213, 248-257;
+    `gram_alpha` = the [N,1,1,1] uniform draw of loss.py:253."""
     rt = fwd.rt
     E_zg, E_zl, G, G_fcn = fwd.nets
     reals, n, c, lat, H, W, pins = fwd.reals, fwd.n, fwd.c, fwd.lat, fwd.H, fwd.W, fwd.pins
@@ -395,12 +399,21 @@ def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, r
                                            rec.numel(), pixel_weight * inv_n / per, rt.stream()), 'tmx_loss_l1_grad')
         report['rec_pixel'] = _row_sum(rt, lsum, 1, 1, scale=pixel_weight * inv_n / per)
         d_rec_img = l1 if d_rec_img is None else _add(rt, d_rec_img, l1)
+    use_gram = gram is not None and gram_weight > 0
+    if use_gram:                                                          # loss.py:149-160
+        _, real_gram = gram.grams(reals.contiguous())
+        report['rec_gram'], dg = gram.term(rec, [(real_gram, False, None, 0)], gram_weight)
+        d_rec_img = dg if d_rec_img is None else _add(rt, d_rec_img, dg)
     dzg_tiled, dzl = backward(G, fwd.t_rec, [d_rec_img], grads['G'])
     dzg = _row_sum(rt, dzg_tiled, n * c, lat * lat)                      # adjoint of the 32x32 tile of zg
     dzl = dzl.contiguous()
     if interp_G_weight > 0:
         report['interp_G'], dcr = cg['interp'] if 'interp' in cg else \
             critic_input_gradient(D_interp, fwd.crop('interp', crop_interp), interp_G_weight)
+        if use_gram:                                                      # loss.py:206-213
+            report['interp_gram'], dg = gram.term(fwd.crop('interp', crop_interp), [(real_gram, False, None, 0)],
+                                                  gram_weight)
+            dcr = _add(rt, dcr, dg)
         dzg_c, dzl_c = backward(G_fcn, fwd.t_int, [_crop_adjoint(rt, dcr, fwd.interp.shape[2:],
                                                                  fwd.image_window('interp', crop_interp))], grads['G'])
         _row_sum(rt, dzg_c, n * c, dzg_c.shape[2] * dzg_c.shape[3], out=dzg, accumulate=True)
@@ -409,6 +422,14 @@ def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, r
         t = fwd.t
         report['blend_G'], dcr = cg['blend'] if 'blend' in cg else \
             critic_input_gradient(D_blend, fwd.crop('blend', crop_blend), blend_interp_G_weight)
+        if use_gram:
+            # loss.py:252-255 AS WRITTEN: (1 - alpha) [N,1,1,1] * multi_layer_diff [N] broadcasts to [N,1,1,N], so what
+            # the optimizer differentiates is mean(1 - alpha) * mean_j A_j + mean(alpha) * mean_j B_j, A against the
+            # batch-reversed real Gram matrices, B against the real ones (kept as the reference has it)
+            abar = _row_sum(rt, gram_alpha.reshape(-1).contiguous(), 1, n, scale=inv_n)
+            report['blend_gram'], dg = gram.term(fwd.crop('blend', crop_blend),
+                                                 [(real_gram, True, abar, 2), (real_gram, False, abar, 1)], gram_weight)
+            dcr = _add(rt, dcr, dg)
         dbzg, dbzl = backward(G_fcn, fwd.t_bl, [_crop_adjoint(rt, dcr, fwd.blend.shape[2:],
                                                               fwd.image_window('blend', crop_blend))], grads['G'])
         zero_c = torch.zeros_like(dbzg)
@@ -448,7 +469,7 @@ def _kl(rt, mu, ls, dmu_in, kl_weight, name):
 
 def EG_wgan(E_zg, E_zl, G, D_rec, G_fcn, D_interp, D_blend, reals, idx, crop_interp, crop_blend, mixing_factors,
             grads, scale_h=3, scale_w=3, rec_G_weight=1.0, pixel_weight=200.0, interp_G_weight=1.0,
-            blend_interp_G_weight=1.0, crop_aware=True, kl_weight=0.0):
+            blend_interp_G_weight=1.0, crop_aware=True, kl_weight=0.0, gram=None, gram_weight=0.0, gram_alpha=None):
     """One evaluation + differentiation of mean(EG_loss) (loss.py:105-259, run.py:321).
     reals: [N,3,R,R] fp32 device tensor in [-1,1]; idx: dict of int32 index vectors (interp.sample_schedule_indices);
     crop_*: (y, x); mixing_factors: [N,1,1,1] fp32 device tensor; grads: {'E_zg','E_zl','G'} -> flat gradient
@@ -457,7 +478,8 @@ def EG_wgan(E_zg, E_zl, G, D_rec, G_fcn, D_interp, D_blend, reals, idx, crop_int
                     need_interp=interp_G_weight > 0, need_blend=blend_interp_G_weight > 0,
                     crop_interp=crop_interp if crop_aware else None, crop_blend=crop_blend if crop_aware else None)
     return EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, rec_G_weight, pixel_weight,
-                       interp_G_weight, blend_interp_G_weight, kl_weight=kl_weight)
+                       interp_G_weight, blend_interp_G_weight, kl_weight=kl_weight, gram=gram, gram_weight=gram_weight,
+                       gram_alpha=gram_alpha)
 
 
 def _add(rt, a, b):

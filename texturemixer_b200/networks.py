@@ -54,7 +54,8 @@ def _act_of(t):
 
 
 def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=False, next_tc=False,
-                 next_up2=False, keep_f32=False, torgb=None):
+                 next_up2=False, keep_f32=False, torgb=None, pad='reflect', alpha=None, wscale=None, trainable=True,
+                 next_pad=None):
     """act(apply_bias(conv2d(x))) [+ residual] under the current variable scope:
     networks.py:48-56 + 61-67 + 72-75 (+ :437).  `up2`: the logical input is
     upscale2d(x) (networks.py:448), never materialised.  `next_tc`/`next_up2` are
@@ -64,8 +65,8 @@ def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=Fals
     assert kernel >= 1 and kernel % 2 == 1                                # networks.py:49
     ctx = x.ctx
     cin = x.shape[1]
-    w = ctx.get_variable('weight', (kernel, kernel, cin, fmaps))
-    b = ctx.get_variable('bias', (fmaps,), init='zeros')
+    w = ctx.get_variable('weight', (kernel, kernel, cin, fmaps), trainable=trainable)
+    b = ctx.get_variable('bias', (fmaps,), init='zeros', trainable=trainable)
     f = 2 if up2 else 1
     shape = [x.shape[0], fmaps, _mul(x.shape[2], f), _mul(x.shape[3], f)]
     if ctx.mode == 'template':
@@ -74,7 +75,9 @@ def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=Fals
         raise NotImplementedError('conv2d kernel=%d: only 1 and 3 occur on the path' % kernel)
     rt = ctx.rt
     xa = _act_of(x)
-    ws = _wscale(w.shape, gain)
+    # `pad='zero'` (SAME), `alpha` (0 = ReLU) and `wscale` (1 = plain filters) are the VGG-19 layer of
+    # tensorflow_vgg's conv_layer; `next_pad`: halo kind the consumer wants on the written planes
+    ws = _wscale(w.shape, gain) if wscale is None else float(wscale)
     strip = None
     if kernel == 1 and (xa.h < 2 or xa.w < 2) and ctx.tape is not None:
         # a 1x1 conv couples no pixels: run it on the pixels laid out as one 2-row strip so that the
@@ -110,7 +113,8 @@ def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=Fals
         head = (wr.value, br.value, _wscale(wr.shape, 1.0), nch, tanh)
     out = rt.conv2d(xa, w.value, b.value, ws, kernel, fmaps, lrelu=act, residual=res, up2=up2,
                     want_f32=((not next_tc) and head is None) or keep_f32, want_split=next_tc,
-                    halo_out='replicate' if next_up2 else 'reflect', algo=algo, prepared=prepared, torgb=head)
+                    halo_out=next_pad or ('replicate' if next_up2 else 'reflect'), algo=algo, prepared=prepared,
+                    torgb=head, halo_in='zero' if pad == 'zero' else None, alpha=alpha)
     t = T(shape, ctx)
     if head is not None:
         t.act, images = out
@@ -119,7 +123,8 @@ def conv2d_layer(x, fmaps, kernel, gain=SQRT2, act=True, residual=None, up2=Fals
         t.act = out
     if rec:
         ctx.tape.append(dict(kind='conv', x=xa, y=t.act, w=w.name, b=b.name, wscale=ws, k=kernel, cin=cin, cout=fmaps,
-                             act=act, up2=up2, residual=None if residual is None else _act_of(residual)))
+                             act=act, up2=up2, residual=None if residual is None else _act_of(residual), alpha=alpha,
+                             halo='zero' if pad == 'zero' else None))
     if pn is not None:
         t = _pixel_norm(ctx, t, pn)
     if strip is not None:
@@ -752,6 +757,53 @@ def _dense_layer(x, fmaps, gain=SQRT2, act=True):
     if ctx.tape is not None:
         ctx.tape.append(dict(kind='dense', x=x.nchw, y=out, w=w.name, b=b.name, wscale=_wscale(w.shape, gain), act=act))
     return T(shape, ctx, nchw=out)
+
+
+# ---------------------------------------------------------------------- VGG-19 features (custom_vgg19.py:20-66)
+VGG19_LAYERS = (('conv1_1', 64), ('conv1_2', 64), ('pool1', 0), ('conv2_1', 128), ('conv2_2', 128), ('pool2', 0),
+                ('conv3_1', 256), ('conv3_2', 256), ('conv3_3', 256), ('conv3_4', 256), ('pool3', 0),
+                ('conv4_1', 512), ('conv4_2', 512), ('conv4_3', 512), ('conv4_4', 512), ('pool4', 0), ('conv5_1', 512))
+VGG19_GRAM_LAYERS = ('conv1_1', 'conv2_1', 'conv3_1', 'conv4_1', 'conv5_1')                # loss.py:153
+
+
+def Vgg19_features(images_in, num_channels=3, resolution=128, dtype='float32', is_template_graph=False, **kwargs):
+    """The feature extractor of the Gram loss: `custom_Vgg19` (custom_vgg19.py:20-66) up to conv5_1 - input scaling to
+    [0,255] BGR minus the VGG mean, then tensorflow_vgg's conv_layer = relu(conv2d SAME + bias) and 2x2 average
+    pooling - returning the five activations whose Gram matrices the loss compares (loss.py:153), NCHW.
+    Variables `<layer>/weight` [3,3,Cin,Cout] and `<layer>/bias` are non-trainable constants (vgg19.npy, see
+    texturemixer_b200.vgg.load_vgg19_npy).  (The reference's networks.Vgg19_gram_autocorrelation, networks.py:582-600,
+    wraps the same extractor; its autocorrelation output is used by no loss in the tree.)"""
+    ctx = images_in.ctx
+    ctx.pixelnorm = None
+    images_in.set_shape([None, num_channels, resolution, resolution])
+    assert num_channels == 3
+    if ctx.mode == 'template':
+        x = T([None, 3, resolution, resolution], ctx)
+    else:
+        import ctypes as C
+        from . import _lib
+        rt = ctx.rt
+        img = images_in.nchw
+        n, _, h, w = img.shape
+        pre = Act(n, h, w, 16, f32=rt.empty(n, h, w, 16))
+        _lib.check(rt.lib.tmx_vgg_preprocess(rt.handle, C.c_void_p(img.data_ptr()), C.c_void_p(pre.f32.data_ptr()), n, h,
+                                             w, rt.stream()), 'tmx_vgg_preprocess')
+        if ctx.tape is not None:
+            ctx.tape.append(dict(kind='vggpre', img=img, y=pre))
+        x = T([n, 3, h, w], ctx, act=pre)
+    outs = []
+    for i, (name, fmaps) in enumerate(VGG19_LAYERS):
+        if name.startswith('pool'):
+            x = downscale2d(x)                                             # avg_pool 2x2 (custom_vgg19.py:44)
+            continue
+        nxt = VGG19_LAYERS[i + 1][0] if i + 1 < len(VGG19_LAYERS) else 'end'
+        with ctx.variable_scope(name):
+            x = conv2d_layer(x, fmaps, 3, act=True, pad='zero', alpha=0.0, wscale=1.0, trainable=False,
+                             next_tc=nxt.startswith('conv'), next_pad='zero', keep_f32=name in VGG19_GRAM_LAYERS)
+        if name in VGG19_GRAM_LAYERS:
+            (o,) = _slice_outputs(x, fmaps, (name,))
+            outs.append(o)
+    return tuple(outs)
 
 
 # ---------------------------------------------------------------------- north_star aliases (SURVEY F2, §8b)

@@ -181,7 +181,7 @@ class Runtime:
 
     def conv2d(self, x, w, bias, wscale, k, cout, lrelu=False, residual=None, up2=False, want_f32=True,
                want_split=False, up2_out=False, halo_out='reflect', algo=None, prepared=None, torgb=None,
-               halo_in=None):
+               halo_in=None, alpha=None):
         """y = [residual +] lrelu(wscale*conv(x, w) + bias) on an Act.  `w` is the raw
         HWIO variable; `prepared` an optional (w_hi, w_lo) pair for the TC kernel
         (sub-pixel planes when up2).  `torgb` = (w_rgb [Cout,C], b_rgb, wscale, C, tanh)
@@ -191,7 +191,7 @@ class Runtime:
         if algo is None:
             algo = self.choose_algo(cin, cout, k, up2, (x.h, x.w))
         d = _lib.ConvDesc(N=x.n, H=h, W=w_, Cin=cin, Cout=cout, k=k, flags=0, algo=algo, wscale=float(wscale),
-                          lrelu_alpha=LRELU_ALPHA)
+                          lrelu_alpha=LRELU_ALPHA if alpha is None else float(alpha))     # alpha 0 = ReLU (VGG-19)
         io = _lib.ConvIO()
         flags = 0
         if lrelu:
@@ -243,8 +243,13 @@ class Runtime:
                 io.y_f32 = out.f32.data_ptr()
             if want_split:
                 ho, wo = (h * 2, w_ * 2) if up2_out else (h, w_)
-                out.hi = self.planes(x.n, ho + 2, wo + 2, cout)
-                out.lo = self.planes(x.n, ho + 2, wo + 2, cout)
+                if halo_out == 'zero':       # SAME-padded consumer: the kernel writes the interior, the ring stays 0
+                    out.hi = torch.zeros(x.n, ho + 2, wo + 2, cout, dtype=torch.bfloat16, device=self.device)
+                    out.lo = torch.zeros(x.n, ho + 2, wo + 2, cout, dtype=torch.bfloat16, device=self.device)
+                    flags |= _lib.CONV_HALO_ZERO
+                else:
+                    out.hi = self.planes(x.n, ho + 2, wo + 2, cout)
+                    out.lo = self.planes(x.n, ho + 2, wo + 2, cout)
                 out.halo = halo_out
                 io.y_hi, io.y_lo = out.hi.data_ptr(), out.lo.data_ptr()
                 if up2_out:
@@ -299,10 +304,10 @@ class Runtime:
         return dw
 
     def grad_prepare(self, g, n, h, w, c, src_kind, fold=2, add=None, y_f32=None, y_hi=None, want_planes=True,
-                     want_f32=False, dbias=None, dbias_scale=1.0, phase_pack=False):
+                     want_f32=False, dbias=None, dbias_scale=1.0, phase_pack=False, alpha=None):
         """See tmx_grad_prepare (include/tmx.h).  Returns (planes or None, f32 or None)."""
         d = _lib.GradDesc(N=n, H=h, W=w, C=c, src_kind=src_kind, fold=fold, mask_kind=0, phase_pack=int(phase_pack),
-                          alpha=LRELU_ALPHA, dbias_scale=float(dbias_scale))
+                          alpha=LRELU_ALPHA if alpha is None else float(alpha), dbias_scale=float(dbias_scale))
         io = _lib.GradIO()
         io.g = g.data_ptr()
         if add is not None:

@@ -192,7 +192,7 @@ class GraphedCriticGradient(GraphedCritic):
 
 
 CROP_KEYS = ('eg_crop_interp', 'eg_crop_blend', 'd_interp_crop', 'd_blend_crop')
-MIX_KEYS = ('eg_mix', 'd_rec_gp', 'd_interp_gp', 'd_blend_mix', 'd_blend_gp')
+MIX_KEYS = ('eg_mix', 'd_rec_gp', 'd_interp_gp', 'd_blend_mix', 'd_blend_gp', 'eg_gram_alpha')
 IDX_KEYS = ('h_forward', 'w_forward', 'h_backward', 'w_backward')
 
 
@@ -213,10 +213,20 @@ class Trainer:
     What makes the step capturable although `random_crop` moves every step: window SIZES are static, window OFFSETS
     are read by the kernels from device memory (loss.Window, tmx_window_copy)."""
 
-    def __init__(self, config=None, seed=1000, device=None):
+    def __init__(self, config=None, seed=1000, device=None, vgg_weights=None):
+        """vgg_weights: the tensorflow_vgg weight dict ({layer: [filter, bias]}, vgg.load_vgg19_npy) or a path to
+        vgg19.npy; with it and cfg['loss']['gram_weight'] > 0 (config.py:64: 0.002) the E/G loss includes the VGG-19
+        Gram terms.  Without it the term is off (the file is not redistributable: stated deviation)."""
         self.cfg = config or default_config()
         c = self.cfg
         self.rt = Runtime.get(device)
+        self.gram = None
+        if vgg_weights is not None:
+            from .vgg import GramLoss, load_vgg19_npy
+            if isinstance(vgg_weights, str):
+                vgg_weights = load_vgg19_npy(vgg_weights)
+            self.gram = GramLoss(vgg_weights, resolution=c['resolution'], device=self.rt.device)
+            c['loss'].setdefault('gram_weight', 0.002)
         res = c['resolution']
         self.nets = {}
         for i, (name, func) in enumerate(NET_FUNCS.items()):                       # run.py:264-269
@@ -477,7 +487,8 @@ class Trainer:
                 critic_grads = self._eg_critic_gradients(fwd, draws, critic_graphs)
             rep = loss.EG_backward(fwd, nets['D_rec'], nets['D_interp'], nets['D_blend'],
                                    draws['eg_crop_interp'], draws['eg_crop_blend'], self.grads, reals_fade=reals_fade,
-                                   critic_grads=critic_grads, **c['loss'])
+                                   critic_grads=critic_grads, gram=self.gram, gram_alpha=draws.get('eg_gram_alpha'),
+                                   **c['loss'])
             report.update({'EG/' + k: v for k, v in rep.items()})
             self.opts['EG'].mark()
             boundary('EG')
