@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TMX_ABI_VERSION 4
+#define TMX_ABI_VERSION 5
 
 typedef struct tmx_ctx* tmx_handle_t;
 typedef void* tmx_stream_t; /* cudaStream_t */
@@ -126,9 +126,10 @@ int tmx_conv2d_fwd(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_io_t
  * Cin_pad (a multiple of 16), e.g. the 513-channel minibatch-stddev output; K index = tap*Cin_pad + c. */
 int tmx_conv_weights_prepare(tmx_handle_t h, const float* w_hwio, float wscale, int k, int Cin, int Cin_pad, int Cout,
                              int up2_phase, uint16_t* w_hi, uint16_t* w_lo, tmx_stream_t s);
-/* XMERGE layout for 16-channel 3x3 layers: [Cout][3 (u)][64], K index u*64 + v*16 + c for v < 3, zeros for v == 3. */
-int tmx_conv_weights_prepare_xmerge(tmx_handle_t h, const float* w_hwio, float wscale, int Cout, uint16_t* w_hi,
-                                    uint16_t* w_lo, tmx_stream_t s);
+/* XMERGE layout for 16-channel 3x3 layers: [Cout][3 (u)][64], K index u*64 + v*16 + c for v < 3, zeros for v == 3
+ * and for c >= Cin (w_hwio is [3][3][Cin][Cout], Cin <= 16: an input zero-padded to 16 channels). */
+int tmx_conv_weights_prepare_xmerge(tmx_handle_t h, const float* w_hwio, float wscale, int Cin, int Cout,
+                                    uint16_t* w_hi, uint16_t* w_lo, tmx_stream_t s);
 
 /* NHWC f32 -> SPLIT_BF16_HALO (tf.pad REFLECT of networks.py:55 materialised; replicate != 0: edge-clamped halo). */
 int tmx_split_halo_pack(tmx_handle_t h, const float* x_nhwc, uint16_t* hi, uint16_t* lo, int N, int H, int W, int C,

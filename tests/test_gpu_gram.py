@@ -86,14 +86,14 @@ def test_vgg_preprocess_and_adjoint(rt):
     _lib.check(rt.lib.tmx_vgg_preprocess(rt.handle, _p(img), _p(out), n, h, w, rt.stream()), 'tmx_vgg_preprocess')
     x = (img + 1.0) / 2.0 * 255.0
     want = torch.stack([x[:, 2] - V.VGG_MEAN[0], x[:, 1] - V.VGG_MEAN[1], x[:, 0] - V.VGG_MEAN[2]], dim=-1)
-    assert torch.equal(out[..., :3], want)                  # same fp32 expression, same order (custom_vgg19.py:32-40)
+    assert torch.allclose(out[..., :3], want, rtol=0, atol=2e-5)   # values up to 255: 1 ulp = 1.5e-5 (fma contraction)
     assert float(out[..., 3:].abs().max()) == 0.0
     d = torch.randn(n, h, w, 16, generator=g).cuda()
     dimg = rt.empty(n, 3, h, w)
     _lib.check(rt.lib.tmx_vgg_preprocess_bwd(rt.handle, _p(d), _p(dimg), n, h, w, rt.stream()),
                'tmx_vgg_preprocess_bwd')
     want = torch.stack([d[..., 2], d[..., 1], d[..., 0]], dim=1) * 127.5
-    assert torch.equal(dimg, want)
+    assert torch.allclose(dimg, want, rtol=1e-6, atol=0)
 
 
 # ---------------------------------------------------------------------- (b) feature extractor + term vs the oracle
@@ -115,12 +115,13 @@ def test_vgg_features_and_grams_vs_oracle(gram):
     with torch.no_grad():
         want = V.vgg_features(img, vgg_standin_weights())
     assert [tuple(f.shape) for f in feats] == [tuple(want[k].shape) for k in V.GRAM_LAYERS]
+    errs = {}
     for f, g, k in zip(feats, gs, V.GRAM_LAYERS):
         ref = want[k].numpy()
-        err = float(np.abs(f.cpu().numpy() - ref).max() / np.abs(ref).max())
-        assert err <= 1e-3, (k, err)
-        gref = V.gram_matrix(want[k]).numpy()
-        assert _rel(g.cpu().numpy(), gref) <= 1e-3, k
+        errs[k] = (float(np.abs(f.cpu().numpy() - ref).max() / np.abs(ref).max()),
+                   _rel(g.cpu().numpy(), V.gram_matrix(want[k]).numpy()))
+    print('VGG-19 features (normalised max error) / Gram matrices (rel-L2) vs oracle:', errs)
+    assert all(a <= 1e-3 and b <= 1e-3 for a, b in errs.values()), errs
 
 
 def _oracle_term(img, real, weights, reverse=False, alpha_bar=None):

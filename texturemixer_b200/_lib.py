@@ -6,7 +6,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'libtmx.so')
 
-TMX_ABI_VERSION = 4
+TMX_ABI_VERSION = 5
 
 # flags / enums (include/tmx.h)
 CONV_LRELU, CONV_RESIDUAL, CONV_UP2_IN, CONV_UP2_OUT, CONV_HALO_REPLICATE, CONV_TORGB, CONV_XMERGE = 1, 2, 4, 8, 16, 32, 64
@@ -67,7 +67,7 @@ _SIGNATURES = {
     'tmx_launch_count': (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     'tmx_conv2d_fwd': (C.c_int, [_P, C.POINTER(ConvDesc), C.POINTER(ConvIO), _P]),
     'tmx_conv_weights_prepare': (C.c_int, [_P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P]),
-    'tmx_conv_weights_prepare_xmerge': (C.c_int, [_P, _P, _F, _I, _P, _P, _P]),
+    'tmx_conv_weights_prepare_xmerge': (C.c_int, [_P, _P, _F, _I, _I, _P, _P, _P]),
     'tmx_mbstd_fwd': (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'tmx_dense_workspace_bytes': (C.c_int, [_I, _I, _I, C.POINTER(C.c_size_t)]),
     'tmx_dense_fwd': (C.c_int, [_P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _F, _P]),

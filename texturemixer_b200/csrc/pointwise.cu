@@ -401,23 +401,26 @@ extern "C" int tmx_conv_weights_prepare(tmx_handle_t h, const float* w, float ws
 
 __global__ void __launch_bounds__(256) weights_prepare_xmerge_kernel(const float* __restrict__ w, float wscale,
                                                                      uint16_t* __restrict__ hi,
-                                                                     uint16_t* __restrict__ lo, int Cout) {
+                                                                     uint16_t* __restrict__ lo, int Cin, int Cout) {
   const int total = Cout * 192;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int kk = t % 192, o = t / 192;
   const int u = kk / 64, r = kk % 64, v = r / 16, c = r % 16;
-  const float val = v < 3 ? __ldg(w + ((long long)((u * 3 + v) * 16 + c)) * Cout + o) * wscale : 0.f;
+  // channels >= Cin are the zero padding of a narrower input (VGG-19's conv1_1: 3 -> 16)
+  const float val = (v < 3 && c < Cin) ? __ldg(w + ((long long)((u * 3 + v) * Cin + c)) * Cout + o) * wscale : 0.f;
   uint32_t a, b;
   tmx_split_bf16(val, a, b);
   hi[t] = (uint16_t)a;
   lo[t] = (uint16_t)b;
 }
 
-extern "C" int tmx_conv_weights_prepare_xmerge(tmx_handle_t h, const float* w, float wscale, int Cout, uint16_t* w_hi,
-                                               uint16_t* w_lo, tmx_stream_t s) {
-  TMX_REQUIRE(h && w && w_hi && w_lo && Cout > 0, TMX_ERR_ARG, "tmx_conv_weights_prepare_xmerge: bad argument");
-  weights_prepare_xmerge_kernel<<<tmx_ceil_div(Cout * 192, 256), 256, 0, (cudaStream_t)s>>>(w, wscale, w_hi, w_lo, Cout);
+extern "C" int tmx_conv_weights_prepare_xmerge(tmx_handle_t h, const float* w, float wscale, int Cin, int Cout,
+                                               uint16_t* w_hi, uint16_t* w_lo, tmx_stream_t s) {
+  TMX_REQUIRE(h && w && w_hi && w_lo && Cout > 0 && Cin > 0 && Cin <= 16, TMX_ERR_ARG,
+              "tmx_conv_weights_prepare_xmerge: bad argument");
+  weights_prepare_xmerge_kernel<<<tmx_ceil_div(Cout * 192, 256), 256, 0, (cudaStream_t)s>>>(w, wscale, w_hi, w_lo, Cin,
+                                                                                            Cout);
   TMX_LAUNCHED(h, "weights_prepare_xmerge_kernel");
   return TMX_OK;
 }

@@ -165,8 +165,9 @@ class Runtime:
     def prepare_weights_xmerge(self, w, wscale, cout):
         hi = self.empty(cout, 192, dtype=torch.bfloat16)
         lo = self.empty(cout, 192, dtype=torch.bfloat16)
-        _lib.check(self.lib.tmx_conv_weights_prepare_xmerge(self.handle, _ptr(w), float(wscale), cout, _ptr(hi),
-                                                            _ptr(lo), self.stream()), 'tmx_conv_weights_prepare_xmerge')
+        _lib.check(self.lib.tmx_conv_weights_prepare_xmerge(self.handle, _ptr(w), float(wscale), int(w.shape[2]), cout,
+                                                            _ptr(hi), _ptr(lo), self.stream()),
+                   'tmx_conv_weights_prepare_xmerge')
         return hi, lo
 
     def prepare_weights(self, w, wscale, k, cin, cout, up2_phase=False, cin_pad=None):
