@@ -79,6 +79,10 @@ int tmx_launch_count(tmx_handle_t h, uint64_t* count);
 #define TMX_CONV_HALO_ZERO 128u /* split-plane output keeps a ZERO halo: the kernel writes the interior only, the caller
                                  * hands in zeroed planes (consumer is a SAME-padded conv: VGG-19, fused_scale) */
 
+#define TMX_CONV_W_PER_SAMPLE 256u /* TC: w_hi / w_lo hold N weight sets [N][Cout][k*k*Cin], image n is convolved with
+                                    * set n (a batched GEMM: the Gram-loss gradient dF[n] = F[n] (S[n] + S[n]^T)).  Needs
+                                    * >= 128 pixels per image; no UP2_IN / XMERGE / TORGB. */
+
 #define TMX_ALGO_AUTO 0
 #define TMX_ALGO_FFMA 1 /* CUDA-core fp32 implicit GEMM, NHWC f32 in/out */
 #define TMX_ALGO_TC 2   /* tcgen05 bf16x3 implicit GEMM, SPLIT_BF16_HALO in; K chunk = 64/32/16 channels by Cin */
@@ -361,6 +365,16 @@ int tmx_vgg_preprocess(tmx_handle_t h, const float* img_nchw, float* out_nhwc16,
 int tmx_vgg_preprocess_bwd(tmx_handle_t h, const float* dout_nhwc16, float* dimg_nchw, int N, int H, int W,
                            tmx_stream_t s);
 int tmx_gram_fwd(tmx_handle_t h, const float* F, float* G, int N, int C, int H, int W, tmx_stream_t s);
+/* The same Gram matrices on the tensor cores from the SPLIT_BF16_HALO feature planes [N][H+2][W+2][C] (any halo):
+ * the weight-gradient kernel with the sample as the tap and F as both operands (bf16x3, fp32 accumulate, split-K
+ * over pixels, fixed-order reduction).  *bytes == 0: shape not served (H*W % 64 != 0 or < 64) - use tmx_gram_fwd. */
+int tmx_gram_fwd_tc_workspace_bytes(tmx_handle_t h, int N, int C, int H, int W, size_t* bytes);
+int tmx_gram_fwd_tc(tmx_handle_t h, const uint16_t* f_hi, const uint16_t* f_lo, float* G, float* workspace, int N,
+                    int C, int H, int W, tmx_stream_t s);
+/* Per-sample weight planes of the Gram-loss gradient as a 1x1 conv (TMX_CONV_W_PER_SAMPLE):
+ * w[n][i][j] = (S[n][i][j] + S[n][j][i]) * scale, split into bf16 hi / lo, [N][C][C]. */
+int tmx_gram_sym_split(tmx_handle_t h, const float* S, uint16_t* w_hi, uint16_t* w_lo, int N, int C, float scale,
+                       tmx_stream_t s);
 int tmx_gram_l1(tmx_handle_t h, const float* G, const float* T, float* S, float* sums, int N, int C, int reverse_t,
                 float coef, float val_scale, int accumulate, const float* wdev, int wmode, tmx_stream_t s);
 int tmx_gram_bwd(tmx_handle_t h, const float* S, const float* F, float* dF, int N, int C, int H, int W, tmx_stream_t s);

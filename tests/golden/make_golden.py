@@ -60,6 +60,38 @@ def gen_perm():
     print('perm_sampler.npz', {k: v.shape for k, v in out.items() if not k.endswith('meta')})
 
 
+def gen_perm_options():
+    """The config-off branches of run.py:436-507: config.block_size > 0 and config.perm (np.random.permutation),
+    driven like the reference's loops (h matrices first, then w), reduced to index vectors."""
+    f = refload.reference_functions('run.py', ['my_swap_h', 'my_swap_w', 'block_permutation'])
+    out = {}
+    for tag, length, levels, count, seed, block_size, perm in [('bs4', 96, 5, 2, 5, 4, False), ('perm', 96, 5, 2, 6, 0, True),
+                                                               ('bs8perm', 96, 5, 2, 7, 8, True), ('bs32', 64, 5, 3, 8, 32, False)]:
+        np.random.seed(seed)
+        hs, ws = [], []
+        for axis, acc in (('h', hs), ('w', ws)):
+            swap = f['my_swap_h'] if axis == 'h' else f['my_swap_w']
+            for _ in range(count):
+                if block_size == 0:
+                    p = np.eye(length)
+                    for idx in range(levels):
+                        bs = int(2 ** idx)
+                        pm = np.random.permutation(np.eye(length // bs)) if perm else swap(np.eye(length // bs))
+                        blk = f['block_permutation'](pm, bs)
+                        p = np.matmul(p, blk) if axis == 'h' else np.matmul(blk, p)
+                else:
+                    pm = np.random.permutation(np.eye(length // block_size)) if perm else swap(np.eye(length // block_size))
+                    p = f['block_permutation'](pm, block_size)
+                assert (p.sum(0) == 1).all() and (p.sum(1) == 1).all()
+                acc.append(np.argmax(p, axis=1 if axis == 'h' else 0).astype(np.int32))
+        out[tag + '_h'] = np.stack(hs)
+        out[tag + '_w'] = np.stack(ws)
+        out[tag + '_meta'] = np.array([length, levels, count, seed, block_size, int(perm)], np.int64)
+        out[tag + '_next_uniform'] = np.array([np.random.uniform()])
+    np.savez_compressed(os.path.join(HERE, 'perm_sampler_options.npz'), **out)
+    print('perm_sampler_options.npz', {k: v.shape for k, v in out.items() if not k.endswith('meta')})
+
+
 def gen_mattes():
     f = refload.reference_functions('util_scripts.py',
                                     ['linkern_for_weight_horizontal', 'linkern_for_weight_arbitrary_shape'])
@@ -366,10 +398,14 @@ if __name__ == '__main__':
     if 'apps' in sys.argv[1:]:
         gen_app_mattes()
         sys.exit(0)
+    if 'perm_options' in sys.argv[1:]:
+        gen_perm_options()
+        sys.exit(0)
     if 'fused' in sys.argv[1:]:
         gen_network_fused()
         sys.exit(0)
     gen_perm()
+    gen_perm_options()
     gen_mattes()
     gen_networks()
     gen_network_variants()

@@ -77,6 +77,30 @@ def test_gram_kernels_vs_torch(rt, n, c, h, w):
     assert _rel(dF.cpu().numpy().reshape(n, c, h * w), Fd.grad.cpu().numpy()) <= 1e-5
 
 
+@pytest.mark.parametrize('n,c,h,w', [(3, 64, 16, 16), (2, 128, 8, 8), (2, 256, 32, 32), (3, 512, 16, 16),
+                                     (2, 64, 128, 128), (2, 512, 8, 8)])
+def test_gram_tensor_core_kernels_vs_torch(rt, n, c, h, w):
+    """tmx_gram_fwd_tc (weight-gradient kernel, sample = tap) and the per-sample-weight 1x1 conv of the gradient
+    (TMX_CONV_W_PER_SAMPLE) against fp64 torch, from split-bf16 planes with a zero halo."""
+    import types
+    from texturemixer_b200.runtime import Act
+    from texturemixer_b200.vgg import GramLoss
+    g = torch.Generator().manual_seed(n * 77 + c + h)
+    F = torch.relu(torch.randn(n, h, w, c, generator=g)).cuda()          # NHWC, like a VGG activation
+    S = torch.randn(n, c, c, generator=g).cuda() * 1e-3
+    act = rt.split_pack(Act(n, h, w, c, f32=F.clone()), 'zero')
+    me = types.SimpleNamespace(rt=rt, use_tc=True)
+    G = GramLoss._gram_of(me, act)
+    dF = GramLoss._feature_gradient(me, act, S)
+    torch.cuda.synchronize()
+    Fd = F.double().reshape(n, h * w, c)
+    Gd = torch.matmul(Fd.transpose(1, 2), Fd) / h / w
+    assert _rel(G.cpu().numpy(), Gd.cpu().numpy()) <= 2e-5
+    Sd = S.double()
+    want = torch.matmul(Fd, (Sd + Sd.transpose(1, 2)).transpose(1, 2)) / h / w          # [n, p, i]
+    assert _rel(dF.reshape(n, h * w, c).cpu().numpy(), want.cpu().numpy()) <= 2e-5
+
+
 def test_vgg_preprocess_and_adjoint(rt):
     from texturemixer_b200 import _lib
     n, h, w = 2, 12, 20
@@ -97,10 +121,14 @@ def test_vgg_preprocess_and_adjoint(rt):
 
 
 # ---------------------------------------------------------------------- (b) feature extractor + term vs the oracle
-@pytest.fixture(scope='module')
-def gram():
+@pytest.fixture(scope='module', params=['tc', 'ffma'])
+def gram(request):
+    """'tc': Gram matrices and their gradient GEMMs on the tensor cores (the default); 'ffma': the fp32 CUDA-core
+    kernels on NCHW copies (what odd shapes fall back to)."""
     from texturemixer_b200.vgg import GramLoss
-    return GramLoss(vgg_standin_weights(), resolution=128, device=0)
+    g = GramLoss(vgg_standin_weights(), resolution=128, device=0)
+    g.use_tc = request.param == 'tc'
+    return g
 
 
 def _images(n, seed):
@@ -110,7 +138,9 @@ def _images(n, seed):
 
 def test_vgg_features_and_grams_vs_oracle(gram):
     img = _images(2, 11)
-    feats, gs = gram.grams(img.cuda())
+    acts, gs = gram.grams(img.cuda())
+    rt = gram.rt
+    feats = [rt.nhwc_to_nchw(rt.split_unpack(a).f32) for a in acts]
     torch.cuda.synchronize()
     with torch.no_grad():
         want = V.vgg_features(img, vgg_standin_weights())
@@ -184,7 +214,7 @@ def test_gram_term_gradient_with_shared_relu_masks(gram, monkeypatch):
     rt = gram.rt
     _, real_gram = gram.grams(real.cuda())
     tape = []
-    feats, gs = gram.grams(fake.cuda(), tape=tape)
+    gram.grams(fake.cuda(), tape=tape)
     masks = []
     for rec in tape:
         if rec['kind'] == 'conv':

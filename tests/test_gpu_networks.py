@@ -214,6 +214,39 @@ def test_network_run_output_conversion():
     assert u.dtype == np.uint8 and np.abs(u.astype(np.int32) - want.astype(np.int32)).max() <= 1
 
 
+def test_network_run_num_gpus():
+    """tfutil.py:644-661: Network.run(num_gpus=k) splits every minibatch over k devices of the process; the result
+    equals the single-device run bit for bit (same kernels, same per-image arithmetic).  With one visible device
+    k = 2 must fail loudly instead of silently running on one."""
+    rng = np.random.RandomState(4)
+    params = R.init_params('G_res', rng, **R.CONFIG['G_res'])
+    net = _make('G_res', params)
+    zg, zl = _inputs('G_res', rng, 6)
+    if torch.cuda.device_count() < 2:
+        with pytest.raises(RuntimeError, match='CUDA device'):
+            net.run(zg, zl, num_gpus=2)
+        one = net.run(zg, zl, num_gpus=1, minibatch_size=4)
+        assert one.shape == (6, 3, 128, 128)
+        return
+    one = net.run(zg, zl, minibatch_size=4)
+    two = net.run(zg, zl, num_gpus=2, minibatch_size=4)              # minibatches of 4 + 2, each split 2 ways
+    assert two.shape == one.shape and np.array_equal(one, two)
+    net.set_var('64x64/Residual_0/weight', net.get_var('64x64/Residual_0/weight') * 1.5) if \
+        '64x64/Residual_0/weight' in net.vars else None
+    name = next(iter(net.trainables))
+    net.set_var(name, net.get_var(name) * 1.25)                      # replicas must follow a weight change
+    assert np.array_equal(net.run(zg, zl), net.run(zg, zl, num_gpus=2))
+    u = net.run(zg, zl, num_gpus=2, out_mul=127.5, out_add=127.5, out_dtype=np.uint8)
+    assert u.dtype == np.uint8 and np.array_equal(u, net.run(zg, zl, out_mul=127.5, out_add=127.5, out_dtype=np.uint8))
+    # a minibatch-dependent network: the critic's minibatch-stddev groups are formed inside each device's part
+    pd = R.init_params('D_patch', rng, **R.CONFIG['D_patch'])
+    D = _make('D_patch', pd)
+    x = rng.uniform(-1, 1, (16, 3, 128, 128)).astype(np.float32)
+    got = D.run(x, num_gpus=2, minibatch_size=16)
+    want = np.concatenate([D.run(x[:8]), D.run(x[8:])], axis=0)
+    assert np.array_equal(got, want)
+
+
 def _variant_table():
     src = open(os.path.join(GOLDEN, 'make_golden.py')).read()
     ns = {}

@@ -55,6 +55,21 @@ def test_c_sampler_bit_exact_vs_reference_golden(built, tag):
     assert np.random.uniform() == g[tag + '_next_uniform'][0]      # same number of draws consumed
 
 
+@pytest.mark.parametrize('tag', ['bs4', 'perm', 'bs8perm', 'bs32'])
+def test_sampler_block_size_and_perm_options_vs_reference_golden(built, tag):
+    """config.block_size > 0 / config.perm (run.py:436-507, off in the reference config): index vectors and the number
+    of np.random draws equal to the reference's loops (tests/golden/make_golden.py gen_perm_options)."""
+    from texturemixer_b200 import interp
+    g = np.load(os.path.join(GOLDEN, 'perm_sampler_options.npz'))
+    length, levels, count, seed, block_size, perm = (int(v) for v in g[tag + '_meta'])
+    np.random.seed(seed)
+    hs = interp.sample_permutation_indices_general(count, length, levels, 'h', block_size, bool(perm))
+    ws = interp.sample_permutation_indices_general(count, length, levels, 'w', block_size, bool(perm))
+    assert hs.dtype == np.int32 and np.array_equal(hs, g[tag + '_h'])
+    assert np.array_equal(ws, g[tag + '_w'])
+    assert np.random.uniform() == g[tag + '_next_uniform'][0]
+
+
 def test_c_sampler_schedule_order_and_errors(built):
     from texturemixer_b200 import interp
     from texturemixer_b200.runtime import perm_indices_from_uniforms, uniforms_per_matrix

@@ -11,6 +11,7 @@ TMX_ABI_VERSION = 5
 # flags / enums (include/tmx.h)
 CONV_LRELU, CONV_RESIDUAL, CONV_UP2_IN, CONV_UP2_OUT, CONV_HALO_REPLICATE, CONV_TORGB, CONV_XMERGE = 1, 2, 4, 8, 16, 32, 64
 CONV_HALO_ZERO = 128
+CONV_W_PER_SAMPLE = 256
 ALGO_AUTO, ALGO_FFMA, ALGO_TC, ALGO_TC_K32 = 0, 1, 2, 3
 BLEND_COPY, BLEND_MATTE, BLEND_LERP = 0, 1, 2
 WGRAD_X_SLACK = 1
@@ -115,6 +116,9 @@ _SIGNATURES = {
     'tmx_vgg_preprocess': (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),
     'tmx_vgg_preprocess_bwd': (C.c_int, [_P, _P, _P, _I, _I, _I, _P]),
     'tmx_gram_fwd': (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    'tmx_gram_fwd_tc_workspace_bytes': (C.c_int, [_P, _I, _I, _I, _I, C.POINTER(C.c_size_t)]),
+    'tmx_gram_fwd_tc': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    'tmx_gram_sym_split': (C.c_int, [_P, _P, _P, _P, _I, _I, _F, _P]),
     'tmx_gram_l1': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P, _I, _P]),
     'tmx_gram_bwd': (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     'tmx_window_copy': (C.c_int, [_P, _P, _P, C.c_int64, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),

@@ -166,7 +166,7 @@ int tmx_conv2d_fwd_ffma(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv
               "tmx_conv2d_fwd[FFMA]: UP2_IN needs even H, W (got %d x %d)", d->H, d->W);
   TMX_REQUIRE(!(d->flags & TMX_CONV_RESIDUAL) || io->residual, TMX_ERR_ARG,
               "tmx_conv2d_fwd[FFMA]: RESIDUAL flag without residual pointer");
-  TMX_REQUIRE(!(d->flags & (TMX_CONV_UP2_OUT | TMX_CONV_HALO_REPLICATE | TMX_CONV_HALO_ZERO | TMX_CONV_TORGB)) && !io->y_hi && !io->y_lo,
+  TMX_REQUIRE(!(d->flags & (TMX_CONV_UP2_OUT | TMX_CONV_HALO_REPLICATE | TMX_CONV_HALO_ZERO | TMX_CONV_TORGB | TMX_CONV_W_PER_SAMPLE)) && !io->y_hi && !io->y_lo,
               TMX_ERR_UNSUPPORTED,
               "tmx_conv2d_fwd[FFMA]: split-plane / ToRGB outputs are produced by the TC path (or tmx_split_halo_pack)");
   ConvFfmaParams p;

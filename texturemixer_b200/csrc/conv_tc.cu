@@ -83,6 +83,9 @@ struct ConvTcParams {
   // run at the L2 throughput cap (~7.7 TB/s of L2->SM sectors, ncu): the patch cuts the sectors per tile by a third
   // (21.2 M -> 14.3 M for 16->16 at 128x128, batch 32: 87 -> 62 us; profiles/r02_ncu_thin_patch_summary.csv).
   int patch, patch_bytes, patch_stage_bytes, patch_stages;
+  // TMX_CONV_W_PER_SAMPLE: the weight planes hold one [Cout][K] set per image; image n reads rows n*w_sample_rows + ..
+  // (tiles lie inside one image: bn == 1; a CTA pair shares one weight tile, so tiles per image are even)
+  int w_sample_rows;
   float alpha;
   const float* bias;
   const float* residual;
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const CUtensorMap* mb_hi = parts > 1 ? &tm_bs_hi : &tm_b_hi;
         const CUtensorMap* mb_lo = parts > 1 ? &tm_bs_lo : &tm_b_lo;
         const int brows = kBRowsFull / parts;
-        const int brow = cblk * BN + part * (BN / parts) + rank * brows;
+        const int brow = cblk * BN + part * (BN / parts) + rank * brows + n0 * p.w_sample_rows;
         const uint32_t bytes = 2 * Cfg::kABytes + 2 * brows * KC * 2;
         if (!PAIR && p.patch) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -637,7 +640,7 @@ int encode_rows_map(tmx_handle_t h, CUtensorMap* m, const uint16_t* base, long l
 // Common tail of the forward and data-gradient launches: tile schedule (CTA pairs, last-wave split), weight
 // tensor maps, kernel selection.  `tiles_m` = number of 128-row tiles, Ng = GEMM N, Kc = GEMM K per tap.
 int schedule_and_launch(tmx_handle_t h, ConvTcParams& p, CUtensorMap* maps, const uint16_t* w_hi, const uint16_t* w_lo,
-                        long long tiles_m, int Ng, int Kc, int bnc, int kc, int gw, cudaStream_t st) {
+                        long long tiles_m, int Ng, int Kc, int bnc, int kc, int gw, cudaStream_t st, int w_sets = 1) {
   p.tiles_c = Ng / bnc;
   // CTA pairs (cta_group::2) for the wide layers: two pixel tiles share one weight tile split over the pair
   const bool pair = bnc == 256 && kc == 64 && tiles_m >= 2 && !tmx_env_flag("TMX_NO_PAIR");
@@ -665,10 +668,10 @@ int schedule_and_launch(tmx_handle_t h, ConvTcParams& p, CUtensorMap* maps, cons
   }
   int rc;
   const int brows = pair ? bnc / 2 : bnc;   // weight rows one CTA loads per stage
-  if ((rc = encode_wgt_map(h, &maps[2], w_hi, Ng, p.taps * Kc, kc, brows))) return rc;
-  if ((rc = encode_wgt_map(h, &maps[3], w_lo, Ng, p.taps * Kc, kc, brows))) return rc;
-  if ((rc = encode_wgt_map(h, &maps[4], w_hi, Ng, p.taps * Kc, kc, brows / p.split))) return rc;
-  if ((rc = encode_wgt_map(h, &maps[5], w_lo, Ng, p.taps * Kc, kc, brows / p.split))) return rc;
+  if ((rc = encode_wgt_map(h, &maps[2], w_hi, Ng * w_sets, p.taps * Kc, kc, brows))) return rc;
+  if ((rc = encode_wgt_map(h, &maps[3], w_lo, Ng * w_sets, p.taps * Kc, kc, brows))) return rc;
+  if ((rc = encode_wgt_map(h, &maps[4], w_hi, Ng * w_sets, p.taps * Kc, kc, brows / p.split))) return rc;
+  if ((rc = encode_wgt_map(h, &maps[5], w_lo, Ng * w_sets, p.taps * Kc, kc, brows / p.split))) return rc;
   if (pair) return launch_tc<256, 64, 32, true>(h, maps, p, st);
 
 #define TMX_TC_CASE(BN_, KC_, GW_) \
@@ -767,6 +770,13 @@ int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_i
   p.lin_pitch = 0;
   p.lin_rows = 0;
   const long long tiles_m = (long long)p.tiles_x * p.tiles_y * p.tiles_n;
+  const bool per_sample = (d->flags & TMX_CONV_W_PER_SAMPLE) != 0;
+  TMX_REQUIRE(!per_sample || (p.bn == 1 && !phase && !xmerge && !torgb &&
+                              (bnc != 256 || kc != 64 || (p.tiles_x * p.tiles_y) % 2 == 0)),
+              TMX_ERR_UNSUPPORTED,
+              "tmx_conv2d_fwd[TC]: W_PER_SAMPLE needs >= 128 pixels per image (an even number of 128-pixel tiles for "
+              "the 256-column kernel), no UP2_IN / XMERGE / TORGB (got %d x %d)", Hs, Ws);
+  p.w_sample_rows = per_sample ? Ng : 0;
   p.lrelu = (d->flags & TMX_CONV_LRELU) != 0;
   p.has_res = (d->flags & TMX_CONV_RESIDUAL) != 0;
   p.up2_out = (d->flags & TMX_CONV_UP2_OUT) != 0;
@@ -811,7 +821,8 @@ int tmx_conv2d_fwd_tc(tmx_handle_t h, const tmx_conv_desc_t* d, const tmx_conv_i
   }
   if ((rc = encode_act_map(h, &maps[0], io->x_hi, d->N, Hs + 2, Ws + 2, d->Cin, kc, p.bw, box_h, p.bn, xw))) return rc;
   if ((rc = encode_act_map(h, &maps[1], io->x_lo, d->N, Hs + 2, Ws + 2, d->Cin, kc, p.bw, box_h, p.bn, xw))) return rc;
-  return schedule_and_launch(h, p, maps, io->w_hi, io->w_lo, tiles_m, Ng, p.Cin, bnc, kc, gw, st);
+  return schedule_and_launch(h, p, maps, io->w_hi, io->w_lo, tiles_m, Ng, p.Cin, bnc, kc, gw, st,
+                             per_sample ? d->N : 1);
 }
 
 // ---------------------------------------------------------------- data gradient (LIN mode)

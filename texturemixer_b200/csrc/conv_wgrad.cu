@@ -48,6 +48,9 @@ struct WgradParams {
   int splits, chunks_per_split;
   float* partial;                  // [splits][taps][ci_tiles*128][Cout]
   int packed, xwin, bpu, nblocks;  // PACKED-M mode: taps == tap groups; blocks per vertical tap, total blocks
+  // GRAM mode (tmx_gram_fwd_tc): the "tap" index is the SAMPLE, the pixel chunks stay inside that sample, and both
+  // operands are the same feature planes (halo layout, interior at offset 1): partial[split][n] = F[n]^T F[n]
+  int gram, zoff;                  // zoff: interior offset of the B operand's grid (2: zero-ringed dz, 1: halo planes)
 };
 
 // MN-major SWIZZLE_128B operand: 8 K-rows of 128 B per atom (SBO = 1024 B), 64-channel blocks LBO apart.
@@ -98,8 +101,9 @@ __global__ void __launch_bounds__(kWThreads, 1)
   item /= p.ci_tiles;
   const int tap = item % p.taps;
   const int split = item / p.taps;
-  const int u = tap / p.k, v = tap - u * p.k;
+  const int u = p.gram ? 0 : tap / p.k, v = p.gram ? 0 : tap - u * p.k;
   const int pad_off = 1 - p.k / 2;
+  const int n_base = p.gram ? tap : 0;
   const int chunk0 = split * p.chunks_per_split;
   const int chunk1 = min(p.chunks, chunk0 + p.chunks_per_split);
   const int nchunks = max(0, chunk1 - chunk0);
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(kWThreads, 1)
         const int x0 = (t % p.tiles_x) * p.bw;
         t /= p.tiles_x;
         const int y0 = (t % p.tiles_y) * p.bh;
-        const int n0 = (t / p.tiles_y) * p.bn;
+        const int n0 = (t / p.tiles_y) * p.bn + n_base;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -155,9 +159,9 @@ __global__ void __launch_bounds__(kWThreads, 1)
 #pragma unroll
         for (int b = 0; b < BN / 64; ++b) {
           const int c0 = co_t * BN + b * 64;
-          tma_load_4d(sa + 2 * Cfg::kABytes + b * kBlk, &tm_z_hi, &full_bar[stage], c0, x0 + 2, y0 + 2, n0);
-          tma_load_4d(sa + 2 * Cfg::kABytes + Cfg::kBBytes + b * kBlk, &tm_z_lo, &full_bar[stage], c0, x0 + 2, y0 + 2,
-                      n0);
+          tma_load_4d(sa + 2 * Cfg::kABytes + b * kBlk, &tm_z_hi, &full_bar[stage], c0, x0 + p.zoff, y0 + p.zoff, n0);
+          tma_load_4d(sa + 2 * Cfg::kABytes + Cfg::kBBytes + b * kBlk, &tm_z_lo, &full_bar[stage], c0, x0 + p.zoff,
+                      y0 + p.zoff, n0);
         }
         if (++stage == S) {
           stage = 0;
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(kWThreads, 1)
 // dw[tap][ci][co] += scale * sum_s partial[s][tap][ci][co]   (fixed order -> deterministic)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                                            int splits, int taps, int Cin, int cin_pad, int Cout,
-                                                           int co_pad, float scale) {
+                                                           int co_pad, float scale, int overwrite) {
   const long long total4 = (long long)taps * Cin * Cout / 4;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total4) return;
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     acc.w += v.w;
   }
   float4* o = reinterpret_cast<float4*>(dw + e);
-  float4 cur = *o;
+  float4 cur = overwrite ? make_float4(0.f, 0.f, 0.f, 0.f) : *o;
   cur.x = fmaf(acc.x, scale, cur.x);
   cur.y = fmaf(acc.y, scale, cur.y);
   cur.z = fmaf(acc.z, scale, cur.z);
@@ -342,6 +346,8 @@ void wgrad_plan(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, i
   p.ci_tiles = (Cin + kWM - 1) / kWM;
   p.co_tiles = (Cout + bn_cols - 1) / bn_cols;
   p.co_pad = p.co_tiles * bn_cols;
+  p.gram = 0;
+  p.zoff = 2;
   p.packed = wgrad_packed(Cin, k, flags) ? 1 : 0;
   p.xwin = p.bpu = p.nblocks = 1;
   if (p.packed) {
@@ -419,7 +425,68 @@ extern "C" int tmx_conv2d_wgrad(tmx_handle_t h, int N, int H, int W, int Cin, in
                                                                           p.co_pad, p.xwin, p.bpu, wscale);
   else
     wgrad_reduce_kernel<<<tmx_ceil_div(total4, 256), 256, 0, st>>>(workspace, dw, p.splits, p.taps, Cin,
-                                                                   p.ci_tiles * kWM, Cout, p.co_pad, wscale);
+                                                                   p.ci_tiles * kWM, Cout, p.co_pad, wscale, 0);
+  TMX_LAUNCHED(h, "wgrad_reduce_kernel");
+  return TMX_OK;
+}
+
+// ---------------------------------------------------------------- Gram matrices on the tensor cores (loss.py:29-35)
+// G[n][i][j] = sum_p F[n][p][i] F[n][p][j] / (H W) from the split-bf16 feature planes [N][H+2][W+2][C] the VGG conv
+// epilogue wrote: the weight-gradient kernel with k = 1 where the "tap" is the sample and both operands are F.
+namespace {
+bool gram_plan(tmx_handle_t h, int N, int C, int H, int W, int bn_cols, WgradParams& p) {
+  wgrad_plan(h, 1, H, W, C, C, 1, bn_cols, 0, p);
+  if (p.bn != 1) return false;             // a 64-pixel chunk must lie inside one sample
+  p.N = N;
+  p.gram = 1;
+  p.zoff = 1;
+  p.taps = N;
+  const int tiles = p.taps * p.ci_tiles * p.co_tiles;
+  int splits = h->sm_count / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > p.chunks) splits = p.chunks;
+  p.chunks_per_split = (p.chunks + splits - 1) / splits;
+  p.splits = (p.chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+  return true;
+}
+}  // namespace
+
+extern "C" int tmx_gram_fwd_tc_workspace_bytes(tmx_handle_t h, int N, int C, int H, int W, size_t* bytes) {
+  TMX_REQUIRE(h && bytes && N > 0 && C > 0 && H > 0 && W > 0, TMX_ERR_ARG, "tmx_gram_fwd_tc_workspace_bytes: bad argument");
+  WgradParams p;
+  // 0 bytes = this shape is not served by the tensor-core path (use tmx_gram_fwd on the NCHW features)
+  if (C % 8 != 0 || (H * W) % kWKP != 0 || !gram_plan(h, N, C, H, W, wgrad_bn(C), p)) {
+    *bytes = 0;
+    return TMX_OK;
+  }
+  *bytes = (size_t)p.splits * p.taps * p.ci_tiles * kWM * p.co_pad * sizeof(float);
+  return TMX_OK;
+}
+
+extern "C" int tmx_gram_fwd_tc(tmx_handle_t h, const uint16_t* f_hi, const uint16_t* f_lo, float* G, float* workspace,
+                               int N, int C, int H, int W, tmx_stream_t s) {
+  TMX_REQUIRE(h && f_hi && f_lo && G && workspace, TMX_ERR_ARG, "tmx_gram_fwd_tc: NULL argument");
+  TMX_REQUIRE(N > 0 && C % 8 == 0 && H >= 2 && W >= 2 && (H * W) % kWKP == 0, TMX_ERR_SHAPE,
+              "tmx_gram_fwd_tc: needs C %% 8 == 0 and H*W a multiple of %d (got C=%d %dx%d)", kWKP, C, H, W);
+  const int bn_cols = wgrad_bn(C);
+  WgradParams p;
+  TMX_REQUIRE(gram_plan(h, N, C, H, W, bn_cols, p), TMX_ERR_UNSUPPORTED,
+              "tmx_gram_fwd_tc: a 64-pixel chunk does not fit one %dx%d sample", H, W);
+  p.partial = workspace;
+  CUtensorMap maps[4];
+  int rc;
+  if ((rc = encode_map4(h, &maps[0], f_hi, N, H + 2, W + 2, C, p.bw, p.bh, p.bn))) return rc;
+  if ((rc = encode_map4(h, &maps[1], f_lo, N, H + 2, W + 2, C, p.bw, p.bh, p.bn))) return rc;
+  maps[2] = maps[0];
+  maps[3] = maps[1];
+  cudaStream_t st = (cudaStream_t)s;
+  if (bn_cols == 256) rc = launch_wgrad<256>(h, maps, p, st);
+  else if (bn_cols == 128) rc = launch_wgrad<128>(h, maps, p, st);
+  else rc = launch_wgrad<64>(h, maps, p, st);
+  if (rc) return rc;
+  const long long total4 = (long long)N * C * C / 4;
+  wgrad_reduce_kernel<<<tmx_ceil_div(total4, 256), 256, 0, st>>>(workspace, G, p.splits, p.taps, C, p.ci_tiles * kWM, C,
+                                                                 p.co_pad, 1.0f / ((float)H * (float)W), 1);
   TMX_LAUNCHED(h, "wgrad_reduce_kernel");
   return TMX_OK;
 }

@@ -241,3 +241,39 @@ extern "C" int tmx_gram_bwd(tmx_handle_t h, const float* S, const float* F, floa
   TMX_LAUNCHED(h, "gram_bwd_kernel");
   return TMX_OK;
 }
+
+// ---------------------------------------------------------------- per-sample weight planes of the gradient GEMM
+// w[n][i][j] = (S[n][i][j] + S[n][j][i]) * scale -> bf16 hi / lo (the B operand of the TMX_CONV_W_PER_SAMPLE 1x1 conv
+// dF[n][p][i] = sum_j F[n][p][j] w[n][i][j]).  32x32 tiles through shared memory: both reads are row-contiguous.
+__global__ void __launch_bounds__(256) gram_sym_split_kernel(const float* __restrict__ S, uint16_t* __restrict__ hi,
+                                                             uint16_t* __restrict__ lo, int C, float scale) {
+  __shared__ float t[32][33];
+  const float* Sn = S + (long long)blockIdx.z * C * C;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int j = j0 + r, i = i0 + tx;
+    t[r][tx] = (j < C && i < C) ? __ldg(Sn + (long long)j * C + i) : 0.f;       // S[j][i]
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r, j = j0 + tx;
+    if (i < C && j < C) {
+      const float v = (__ldg(Sn + (long long)i * C + j) + t[tx][r]) * scale;
+      uint32_t a, b;
+      tmx_split_bf16(v, a, b);
+      const long long o = ((long long)blockIdx.z * C + i) * C + j;
+      hi[o] = (uint16_t)a;
+      lo[o] = (uint16_t)b;
+    }
+  }
+}
+
+extern "C" int tmx_gram_sym_split(tmx_handle_t h, const float* S, uint16_t* w_hi, uint16_t* w_lo, int N, int C,
+                                  float scale, tmx_stream_t s) {
+  TMX_REQUIRE(h && S && w_hi && w_lo && N > 0 && C > 0, TMX_ERR_ARG, "tmx_gram_sym_split: bad argument");
+  dim3 grid(tmx_ceil_div(C, 32), tmx_ceil_div(C, 32), N);
+  gram_sym_split_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(S, w_hi, w_lo, C, scale);
+  TMX_LAUNCHED(h, "gram_sym_split_kernel");
+  return TMX_OK;
+}

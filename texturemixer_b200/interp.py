@@ -31,16 +31,68 @@ def sample_permutation_indices(count, length, levels, uniform=None):
     return idx
 
 
-def sample_schedule_indices(minibatch, latent_res=32, scale_h=3, scale_w=3, levels=None, uniform=None):
+def _block_expand(r, block_size):
+    """Row map of block_permutation(perm, block_size) (run.py:176-182) from the row map of `perm`."""
+    r = np.asarray(r, np.int64)
+    return (r[:, None] * block_size + np.arange(block_size)[None, :]).reshape(-1)
+
+
+def sample_permutation_indices_general(count, length, levels, axis, block_size=0, perm=False, uniform=None):
+    """The config-off branches of the scheduler loop (run.py:436-507) in index form:
+    `block_size` > 0 (config.block_size: ONE swap / permutation of length/block_size blocks instead of the hierarchy)
+    and `perm` (config.perm: np.random.permutation of the identity instead of the local swaps my_swap_h/w).
+    axis 'h': row map r with P[i, r[i]] = 1 (matrices composed as temp @ block, run.py:447);
+    axis 'w': column map c with P[c[j], j] = 1 (composed as block @ temp, run.py:464).
+    Draws from the same legacy np.random stream, in the same order, as the reference's loops."""
+    assert axis in ('h', 'w')
+    if not perm and block_size == 0:
+        return sample_permutation_indices(count, length, levels, uniform)
+    out = np.empty((count, length), np.int32)
+
+    def one_level(n):
+        """Row map of `perm` for one level over n blocks."""
+        if perm:
+            # np.random.permutation(np.eye(n)) shuffles arange(n) and gathers rows: mat[i] = eye[p[i]]
+            return np.random.permutation(n).astype(np.int64)
+        idx = sample_permutation_indices(1, n, 1, uniform)[0].astype(np.int64)   # my_swap_h / my_swap_w of eye(n)
+        # sample_permutation_indices returns the map its axis convention reads; with one level the h and w forms
+        # describe the same matrix family: for 'w' it is the column map, whose inverse is the row map
+        return idx
+
+    for k in range(count):
+        if block_size > 0:
+            m = one_level(length // block_size)
+            if perm or axis == 'h':
+                r = _block_expand(m, block_size)
+                out[k] = r if axis == 'h' else np.argsort(r)
+            else:
+                out[k] = _block_expand(m, block_size)      # already the column map of my_swap_w's matrix
+            continue
+        r = np.arange(length, dtype=np.int64)               # row map of temp_perm
+        for lvl in range(levels):
+            bs = 1 << lvl
+            m = one_level(length // bs)
+            rb = _block_expand(m, bs)
+            r = rb[r] if axis == 'h' else r[rb]             # temp @ blk : blk @ temp
+        out[k] = r if axis == 'h' else np.argsort(r)
+    return out
+
+
+def sample_schedule_indices(minibatch, latent_res=32, scale_h=3, scale_w=3, levels=None, uniform=None, block_size=0,
+                            perm=False):
     """One scheduler iteration (run.py:436-507): h_forward, w_forward, h_backward,
     w_backward, each int32 [minibatch, latent_res*scale]; levels = int(log2(latent_res))
-    as run.py:440 (the inference apps use int(np.log(latent_res)), util_scripts.py:405)."""
+    as run.py:440 (the inference apps use int(np.log(latent_res)), util_scripts.py:405).
+    `block_size` / `perm`: config.block_size / config.perm (0 / False in the reference config)."""
     if levels is None:
         levels = int(np.log2(latent_res))
     lh, lw = latent_res * scale_h, latent_res * scale_w
     out = {}
     for name, ln in (('h_forward', lh), ('w_forward', lw), ('h_backward', lh), ('w_backward', lw)):
-        out[name] = sample_permutation_indices(minibatch, ln, levels, uniform)
+        if block_size or perm:
+            out[name] = sample_permutation_indices_general(minibatch, ln, levels, name[0], block_size, perm, uniform)
+        else:
+            out[name] = sample_permutation_indices(minibatch, ln, levels, uniform)
     return out
 
 

@@ -7,6 +7,7 @@ HWIO/[in,out] shapes, so `__getstate__` produces the reference's version-2
 pickle dict (tfutil.py:543-550)."""
 import contextlib
 import gc
+import threading
 import os
 import importlib
 import inspect
@@ -140,6 +141,9 @@ class BuildContext:
         return true_fn() if pred else false_fn()
 
 
+_CAPTURE_LOCK = threading.Lock()
+
+
 # ---------------------------------------------------------------------- Network
 class Network:
     def __init__(self, name=None, func=None, reuse=False, share_vars_with=None, device=None, seed=None,
@@ -189,6 +193,7 @@ class Network:
         self._staging = {}
         self._copy_stream = None
         self._graphs = {}
+        self._replicas = {}            # device index -> [copy of this network there, variable version] (run(num_gpus=k))
 
     @property
     def rt(self):
@@ -416,12 +421,14 @@ class Network:
     def run(self, *in_arrays, return_as_list=False, print_progress=False, minibatch_size=None, num_gpus=1,
             out_mul=1.0, out_add=0.0, out_shrink=1, out_dtype=None, **dynamic_kwargs):
         """tfutil.py:624-680: NumPy in, NumPy out, minibatched.  Host buffers are
-        staged through pinned memory; one process drives one GPU (num_gpus > 1
-        in the reference's in-process sense is expressed as one rank per GPU,
-        see texturemixer_b200.parallel)."""
+        staged through pinned memory.  num_gpus = k > 1 (tfutil.py:644-661): every minibatch is split into k
+        contiguous parts which run concurrently on k devices of this process (`_run_multi_gpu`); training jobs use one
+        rank per GPU instead (texturemixer_b200.parallel)."""
         assert len(in_arrays) == self.num_inputs
         if num_gpus != 1:
-            raise NotImplementedError('Network.run: one process drives one GPU; shard the batch across ranks')
+            return self._run_multi_gpu(in_arrays, return_as_list, print_progress, minibatch_size, int(num_gpus),
+                                       dict(out_mul=out_mul, out_add=out_add, out_shrink=out_shrink,
+                                            out_dtype=out_dtype), dynamic_kwargs)
         num_items = in_arrays[0].shape[0]
         if minibatch_size is None:
             minibatch_size = num_items
@@ -497,6 +504,95 @@ class Network:
             out_arrays = out_arrays[0] if len(out_arrays) == 1 else tuple(out_arrays)
         return out_arrays
 
+    # -------------------------------------------------------------- run(num_gpus=k): in-process device replicas
+    def _replica_on(self, index):
+        """This network on cuda:`index`: itself, or a cached copy whose variables follow this network's (refreshed
+        by one device-to-device copy of the flat buffer whenever the variable version changed)."""
+        if index == self.rt.device.index:
+            return self
+        owner = self._owner()
+        ent = self._replicas.get(index)
+        if ent is None:
+            net = object.__new__(Network)
+            net._init_fields()
+            net.name = self.name
+            net.static_kwargs = dict(self.static_kwargs)
+            net._build_module_src = self._build_module_src
+            net._build_func_name = self._build_func_name
+            net._build_func = self._build_func
+            net._device = index
+            with torch.cuda.device(index):
+                net._init_graph()
+            assert net._flat.numel() == owner._flat.numel(), 'replica layout differs'
+            ent = self._replicas[index] = [net, -1]
+        if ent[1] != owner._version or ent[0]._lod_host != owner._lod_host:
+            with torch.cuda.device(index):
+                ent[0]._flat.copy_(owner._flat)
+                ent[0]._lod_host = owner._lod_host
+                ent[0]._touch()
+            ent[1] = owner._version
+        return ent[0]
+
+    def _run_multi_gpu(self, in_arrays, return_as_list, print_progress, minibatch_size, num_gpus, conv_kwargs,
+                       dynamic_kwargs):
+        """tfutil.py:644-661: `tf.split(x, num_gpus)` of every minibatch, one part per device, outputs concatenated
+        in order.  Device g gets part g of EVERY minibatch (so minibatch-dependent layers - the critic's minibatch
+        stddev groups - see the same sub-batches as in the reference); the k devices run concurrently, each through
+        the single-device `run` (pinned staging, copy/compute overlap, CUDA-graphed forward) in its own host thread.
+        A minibatch that k does not divide is split as evenly as possible (tf.split would refuse it)."""
+        import concurrent.futures
+        avail = torch.cuda.device_count()
+        if num_gpus < 1 or num_gpus > avail:
+            raise RuntimeError('Network.run(num_gpus=%d): this process sees %d CUDA device(s)' % (num_gpus, avail))
+        base = self.rt.device.index
+        devices = [base] + [i for i in range(avail) if i != base][:num_gpus - 1]
+        num_items = in_arrays[0].shape[0]
+        if minibatch_size is None:
+            minibatch_size = num_items
+        bounds = [(b, min(b + minibatch_size, num_items)) for b in range(0, num_items, minibatch_size)]
+        # item ranges of device g: part g of each minibatch
+        parts = [[] for _ in devices]
+        for b, e in bounds:
+            cuts = np.linspace(b, e, num_gpus + 1).round().astype(np.int64) if (e - b) % num_gpus else \
+                np.arange(b, e + 1, (e - b) // num_gpus)
+            for g in range(num_gpus):
+                if cuts[g + 1] > cuts[g]:
+                    parts[g].append((int(cuts[g]), int(cuts[g + 1])))
+        per_dev_mb = max(1, -(-minibatch_size // num_gpus))
+
+        def job(g):
+            if not parts[g]:
+                return None
+            with torch.cuda.device(devices[g]):
+                net = self._replica_on(devices[g])
+                if len(parts[g]) == 1:
+                    b, e = parts[g][0]
+                    ins = [a[b:e] for a in in_arrays]
+                else:
+                    ins = [np.concatenate([a[b:e] for b, e in parts[g]], axis=0) for a in in_arrays]
+                return net.run(*ins, return_as_list=True, minibatch_size=per_dev_mb, num_gpus=1, **conv_kwargs,
+                               **dynamic_kwargs)
+        for d in devices:                      # replicas (and their weight copies) are made on the calling thread
+            with torch.cuda.device(d):
+                self._replica_on(d)
+        with concurrent.futures.ThreadPoolExecutor(max_workers=num_gpus) as ex:
+            results = list(ex.map(job, range(num_gpus)))
+        first = next(r for r in results if r is not None)
+        out_arrays = [np.empty((num_items,) + tuple(x.shape[1:]), x.dtype) for x in first]
+        for g, res in enumerate(results):
+            if res is None:
+                continue
+            off = 0
+            for b, e in parts[g]:
+                for dst, src in zip(out_arrays, res):
+                    dst[b:e] = src[off:off + (e - b)]
+                off += e - b
+        if print_progress:
+            print('\r%d / %d' % (num_items, num_items))
+        if not return_as_list:
+            out_arrays = out_arrays[0] if len(out_arrays) == 1 else tuple(out_arrays)
+        return out_arrays
+
     def _forward_graph(self, slot, shapes, conv, dynamic_kwargs):
         """CUDA graph of get_output_for (+ output conversion) for fixed input shapes and the current weight version:
         (graph, static inputs, static outputs).  ~20 kernel launches and as many allocations become one replay, which
@@ -517,17 +613,20 @@ class Network:
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
         # no cyclic garbage collection inside the capture: finalising unrelated CUDA objects (older graphs, events)
-        # from another test or caller while the stream is capturing invalidates it
-        gc.collect()
-        gc_was_on = gc.isenabled()
-        gc.disable()
-        try:
-            with torch.cuda.graph(g):
-                outs = self.get_output_for(*static_in, return_as_list=True, **dynamic_kwargs)
-                static_out = [_convert_output(x, *conv) for x in outs]
-        finally:
-            if gc_was_on:
-                gc.enable()
+        # from another test or caller while the stream is capturing invalidates it.  One capture at a time per
+        # process, in thread-local error mode: run(num_gpus=k) builds its replicas' graphs from k host threads while
+        # the other devices already copy and compute
+        with _CAPTURE_LOCK:
+            gc.collect()
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                    outs = self.get_output_for(*static_in, return_as_list=True, **dynamic_kwargs)
+                    static_out = [_convert_output(x, *conv) for x in outs]
+            finally:
+                if gc_was_on:
+                    gc.enable()
         if len(self._graphs) > 8:
             # evict: a dropped graph's private pool (its static inputs / outputs) may still be read by a replay or a
             # D2H copy in flight - wait for the device before the memory can be handed out again

@@ -766,13 +766,16 @@ VGG19_LAYERS = (('conv1_1', 64), ('conv1_2', 64), ('pool1', 0), ('conv2_1', 128)
 VGG19_GRAM_LAYERS = ('conv1_1', 'conv2_1', 'conv3_1', 'conv4_1', 'conv5_1')                # loss.py:153
 
 
-def Vgg19_features(images_in, num_channels=3, resolution=128, dtype='float32', is_template_graph=False, **kwargs):
+def Vgg19_features(images_in, num_channels=3, resolution=128, dtype='float32', is_template_graph=False, gram_sink=None,
+                   **kwargs):
     """The feature extractor of the Gram loss: `custom_Vgg19` (custom_vgg19.py:20-66) up to conv5_1 - input scaling to
     [0,255] BGR minus the VGG mean, then tensorflow_vgg's conv_layer = relu(conv2d SAME + bias) and 2x2 average
     pooling - returning the five activations whose Gram matrices the loss compares (loss.py:153), NCHW.
     Variables `<layer>/weight` [3,3,Cin,Cout] and `<layer>/bias` are non-trainable constants (vgg19.npy, see
     texturemixer_b200.vgg.load_vgg19_npy).  (The reference's networks.Vgg19_gram_autocorrelation, networks.py:582-600,
-    wraps the same extractor; its autocorrelation output is used by no loss in the tree.)"""
+    wraps the same extractor; its autocorrelation output is used by no loss in the tree.)
+    `gram_sink` (a list; not a reference argument): receives the five activations in their internal form (split-bf16
+    planes, NHWC) for the tensor-core Gram kernels and the NCHW outputs are not materialised (vgg.GramLoss)."""
     ctx = images_in.ctx
     ctx.pixelnorm = None
     images_in.set_shape([None, num_channels, resolution, resolution])
@@ -797,10 +800,16 @@ def Vgg19_features(images_in, num_channels=3, resolution=128, dtype='float32', i
             x = downscale2d(x)                                             # avg_pool 2x2 (custom_vgg19.py:44)
             continue
         nxt = VGG19_LAYERS[i + 1][0] if i + 1 < len(VGG19_LAYERS) else 'end'
+        is_gram = name in VGG19_GRAM_LAYERS
+        internal = gram_sink is not None and ctx.mode != 'template'
         with ctx.variable_scope(name):
             x = conv2d_layer(x, fmaps, 3, act=True, pad='zero', alpha=0.0, wscale=1.0, trainable=False,
-                             next_tc=nxt.startswith('conv'), next_pad='zero', keep_f32=name in VGG19_GRAM_LAYERS)
-        if name in VGG19_GRAM_LAYERS:
+                             next_tc=nxt.startswith('conv') or (is_gram and internal), next_pad='zero',
+                             keep_f32=is_gram and not internal)
+        if is_gram and internal:
+            gram_sink.append(x.act)
+            outs.append(T(list(x.shape), ctx, name=name))
+        elif is_gram:
             (o,) = _slice_outputs(x, fmaps, (name,))
             outs.append(o)
     return tuple(outs)

@@ -182,11 +182,12 @@ class Runtime:
 
     def conv2d(self, x, w, bias, wscale, k, cout, lrelu=False, residual=None, up2=False, want_f32=True,
                want_split=False, up2_out=False, halo_out='reflect', algo=None, prepared=None, torgb=None,
-               halo_in=None, alpha=None):
+               halo_in=None, alpha=None, per_sample_weights=False):
         """y = [residual +] lrelu(wscale*conv(x, w) + bias) on an Act.  `w` is the raw
         HWIO variable; `prepared` an optional (w_hi, w_lo) pair for the TC kernel
         (sub-pixel planes when up2).  `torgb` = (w_rgb [Cout,C], b_rgb, wscale, C, tanh)
-        fuses the 1x1 image head behind the conv (TC only) and returns (out, images)."""
+        fuses the 1x1 image head behind the conv (TC only) and returns (out, images).
+        `per_sample_weights`: `prepared` holds one weight set per image, [N*Cout][k*k*Cin] (TMX_CONV_W_PER_SAMPLE)."""
         cin = x.c
         h, w_ = (x.h * 2, x.w * 2) if up2 else (x.h, x.w)
         if algo is None:
@@ -202,6 +203,9 @@ class Runtime:
             io.residual = residual.data_ptr()
         if up2:
             flags |= _lib.CONV_UP2_IN
+        if per_sample_weights:
+            assert prepared is not None and algo != _lib.ALGO_FFMA
+            flags |= _lib.CONV_W_PER_SAMPLE
         io.bias = None if bias is None else bias.data_ptr()
         keep = []
         images = None
@@ -219,7 +223,8 @@ class Runtime:
             # halo_in='zero': the SAME (zero) padding of the fused_scale convs instead of the REFLECT default
             self.split_pack(x, halo_in or ('replicate' if up2 else 'reflect'))
             io.x_hi, io.x_lo = x.hi.data_ptr(), x.lo.data_ptr()
-            xmerge = self.use_xmerge(cin, k, up2) and x.hi.untyped_storage().nbytes() >= (x.hi.numel() + 64) * 2
+            xmerge = self.use_xmerge(cin, k, up2) and x.hi.untyped_storage().nbytes() >= (x.hi.numel() + 64) * 2 \
+                and not per_sample_weights
             if xmerge:
                 flags |= _lib.CONV_XMERGE
                 if prepared is None or prepared[0].shape[1] != 192:

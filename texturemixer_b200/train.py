@@ -48,7 +48,9 @@ def default_config(train_size=128, fmap_base=1024, fmap_max=512, latent_channels
         #                       the critic evaluations (GraphedCritic); False: every launch from Python
         crop_aware=True,      # G_fcn decodes only the latent window each random_crop depends on (loss.crop_window)
         loss=dict(rec_G_weight=1.0, pixel_weight=200.0, interp_G_weight=1.0, blend_interp_G_weight=1.0),
-        levels=int(np.log2(latent_res)))
+        levels=int(np.log2(latent_res)),
+        block_size=0, perm=False,                              # config.py:69-70: the permutation sampler's variants
+        lr_mirror_augment=False, ud_mirror_augment=False)      # config.py:96 (Trainer.step_from_dataset)
 
 
 class TrainingSchedule:
@@ -269,7 +271,8 @@ class Trainer:
         per-sample mixing factors (loss.py:237,329,405,489,505); and, derived from the crop offsets, the crop-aware
         window plans (loss.plan_crop) whose offsets travel to the device with the index vectors."""
         c = self.cfg
-        idx = interp.sample_schedule_indices(minibatch, c['latent_res'], c['scale_h'], c['scale_w'], c['levels'], uniform)
+        idx = interp.sample_schedule_indices(minibatch, c['latent_res'], c['scale_h'], c['scale_w'], c['levels'], uniform,
+                                             block_size=c.get('block_size', 0), perm=c.get('perm', False))
         res, lat = c['resolution'], c['latent_res']
         H, W = lat * c['scale_h'], lat * c['scale_w']
         hi_y, hi_x = res * c['scale_h'] - res, res * c['scale_w'] - res
@@ -401,6 +404,22 @@ class Trainer:
             return self._step_graphed(reals_fade, reals_orig, d_fade, d_orig, draws, lrate, tuple(phases), lod_now)
         return self._step_body(reals_fade, reals_orig, d_fade, d_orig, draws, lrate, phases,
                                critic_graphs=(mode == 'critics'))
+
+    def step_from_dataset(self, images, draws, images_d=None, lod=None, rng=None, drange_data=(0, 255), **step_kwargs):
+        """One step from minibatches as the dataset delivers them (run.py:306-312 then 510-513): `images` (and
+        `images_d` for the critic phase) are uint8 / float device tensors [n,3,r,r] at the dataset's current resolution
+        r = R / 2^floor(lod); `process_reals` applies the dynamic range, the mirror augmentation selected by
+        cfg['lr_mirror_augment'] / cfg['ud_mirror_augment'] (config.py:96, run.py:237-238, 311), FadeLOD and
+        UpscaleLOD, then `step` runs."""
+        c = self.cfg
+        lod_now = float(self.nets['G'].lod if lod is None else lod)
+        kw = dict(lr_mirror_augment=bool(c.get('lr_mirror_augment', False)),
+                  ud_mirror_augment=bool(c.get('ud_mirror_augment', False)), drange_data=drange_data, rng=rng)
+        fade, orig = process_reals(images, lod_now, **kw)
+        d_fade = d_orig = None
+        if images_d is not None:
+            d_fade, d_orig = process_reals(images_d, lod_now, **kw)
+        return self.step(fade, draws, lod=lod, reals_orig=orig, reals_d=d_fade, reals_d_orig=d_orig, **step_kwargs)
 
     def _allreduce(self, name):
         b = self.buckets[name]
