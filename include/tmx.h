@@ -76,8 +76,8 @@ int tmx_launch_count(tmx_handle_t h, uint64_t* count);
 #define TMX_CONV_XMERGE 64u  /* TC, Cin == 16, k == 3: operand rows carry the 3 horizontal taps (4 pixels = 128 B) of
                               * an overlapping-stride view; weights from tmx_conv_weights_prepare with xmerge = 1.
                               * The x planes must be allocated (and zero-filled) 64 elements past their end. */
-#define TMX_CONV_HALO_ZERO 128u /* split-plane output keeps a ZERO halo: the kernel writes the interior only, the caller
-                                 * hands in zeroed planes (consumer is a SAME-padded conv: VGG-19, fused_scale) */
+#define TMX_CONV_HALO_ZERO 128u /* split-plane output gets a ZERO halo (written by the border pixels' threads; the
+                                 * consumer is a SAME-padded conv: VGG-19, fused_scale) */
 
 #define TMX_CONV_W_PER_SAMPLE 256u /* TC: w_hi / w_lo hold N weight sets [N][Cout][k*k*Cin], image n is convolved with
                                     * set n (a batched GEMM: the Gram-loss gradient dF[n] = F[n] (S[n] + S[n]^T)).  Needs

@@ -134,6 +134,35 @@ def main():
                                                               0.0015, 0.0, 0.99, 1e-8, 1.0, C.c_void_p(powers.data_ptr()),
                                                               None, C.c_void_p(mark.data_ptr()), rt.stream()))))
 
+    # dense head of D_patch (8192 -> 512, batch 32): weight-streaming bound (16.8 MB of fp32 weights per launch)
+    xd, wd, bd = rand(32, 8192), rand(8192, 512), rand(512)
+    yd = rt.dense(xd, wd, bd, 0.0156, True)
+    dyd = rand(32, 512)
+    dwd, dbd = torch.zeros(8192, 512, device=dev), torch.zeros(512, device=dev)
+    dxd = torch.empty(32, 8192, device=dev)
+    wbytes = 8192 * 512 * 4
+    P = lambda t_: C.c_void_p(t_.data_ptr())                                                     # noqa: E731
+    targets.append(('dense fwd 8192->512 batch 32 (split-K partial + finish)', 'hbm', 0.0, wbytes + 32 * 8192 * 4,
+                    lambda: rt.dense(xd, wd, bd, 0.0156, True)))
+    targets.append(('dense wgrad 8192->512 batch 32', 'hbm', 0.0, 2 * wbytes + 32 * 8192 * 4,
+                    lambda: _lib.check(rt.lib.tmx_dense_wgrad(rt.handle, P(xd), P(dyd), P(yd), P(dwd), P(dbd), 32, 8192, 512,
+                                                              0.0156, 1, 0.2, rt.stream()))))
+    targets.append(('dense bwd_input 8192->512 batch 32', 'hbm', 0.0, wbytes + 32 * 8192 * 4,
+                    lambda: _lib.check(rt.lib.tmx_dense_bwd_input(rt.handle, P(dyd), P(yd), P(wd), 0.0156, P(dxd), 32, 8192,
+                                                                  512, 1, 0.2, rt.stream()))))
+    # VGG-19 Gram loss: Gram matrices (wgrad kernel, sample = tap) and the per-sample-weight 1x1 conv of their gradient
+    import types
+    from texturemixer_b200.vgg import GramLoss
+    me = types.SimpleNamespace(rt=rt, use_tc=True)
+    for (c_, hw_) in ((64, 128), (256, 32)):
+        fa = rt.split_pack(Act(n, hw_, hw_, c_, f32=torch.relu(rand(n, hw_, hw_, c_))), 'zero')
+        Sg = rand(n, c_, c_)
+        gf = 2.0 * c_ * c_ * hw_ * hw_ * n
+        targets.append(('gram fwd (tensor cores) [32,%d,%d,%d]' % (c_, hw_, hw_), 'tensor', gf, n * hw_ * hw_ * c_ * 4,
+                        (lambda a=fa: GramLoss._gram_of(me, a))))
+        targets.append(('gram bwd (per-sample-weight 1x1 conv) [32,%d,%d,%d]' % (c_, hw_, hw_), 'tensor', gf,
+                        n * hw_ * hw_ * c_ * 8, (lambda a=fa, S_=Sg: GramLoss._feature_gradient(me, a, S_))))
+
     hbm, bf16, src = peaks()
     rows = []
     for tag, bound, flops, byts, fn in targets:

@@ -56,6 +56,14 @@ DGRAD_CASES = [
     (9, 512, 512, 2, 2, 3, True),
     (2, 64, 256, 8, 8, 1, False),
     (1, 256, 64, 96, 96, 3, True),
+    # thin layers: LIN-PATCH kernel (conv_lin.cu: one haloed patch per tile, no-swizzle operands, resident weights)
+    (2, 16, 16, 128, 128, 3, True),      # patch of 394 grid rows = two TMA boxes
+    (2, 16, 32, 128, 128, 3, True),
+    (2, 32, 32, 64, 64, 3, True),
+    (2, 32, 64, 64, 64, 3, False),
+    (3, 64, 16, 20, 12, 3, True),
+    (2, 64, 32, 32, 32, 3, True),
+    (2, 64, 64, 8, 8, 3, True),          # weights too large to stay resident: general LIN mode
 ]
 
 
@@ -224,19 +232,26 @@ def test_generator_backward_vs_autograd(sh, sw, alpha, monkeypatch):
     _set_alpha(monkeypatch, alpha)
     rng = np.random.RandomState(1000)
     params = R.init_params('G_res', rng, **R.CONFIG['G_res'])
-    net, cfg = _net('G_res', params, scale_h=sh, scale_w=sw)
+    # alpha = 1 makes the 17 stacked layers an undamped LINEAR chain (pre-tanh values of several hundred): behind a
+    # saturated tanh the gradient would pass through the few pixels near a zero crossing only and measure the forward
+    # rounding there, not the backward kernels - the exact-chain case therefore ends at the linear image head
+    extra = dict(tanh_at_end=False) if alpha == 1.0 else {}
+    net, cfg = _net('G_res', params, scale_h=sh, scale_w=sw, **extra)
     n = 2
     zg = rng.randn(n, 128, 32 * sh, 32 * sw).astype(np.float32)
     zl = rng.randn(n, 128, 32 * sh, 32 * sw).astype(np.float32)
     dimg = rng.randn(n, 3, 128 * sh, 128 * sw).astype(np.float32)
-    P = R.to_torch(params, requires_grad=True)
-    zg_t = torch.from_numpy(zg).requires_grad_(True)
-    zl_t = torch.from_numpy(zl).requires_grad_(True)
+    # alpha = 1 is the exact-chain case (no activation damping: 17 stacked linear layers): the oracle runs in fp64 so
+    # that the 1e-3 bound measures the device and not the fp32 oracle's own summation error
+    dt = torch.float64 if alpha == 1.0 else torch.float32
+    P = R.to_torch(params, dtype=dt, requires_grad=True)
+    zg_t = torch.from_numpy(zg).to(dt).requires_grad_(True)
+    zl_t = torch.from_numpy(zl).to(dt).requires_grad_(True)
     out = R.G_res(zg_t, zl_t, P, **cfg)
-    (out * torch.from_numpy(dimg)).sum().backward()
+    (out * torch.from_numpy(dimg).to(dt)).sum().backward()
     tape = []
     img = net.get_output_for(torch.from_numpy(zg).cuda(), torch.from_numpy(zl).cuda(), tape=tape)
-    assert _nmax(img.cpu().numpy(), out.detach().numpy()) <= (5e-4 if alpha != 1.0 else 1e-2)   # alpha=1: no damping
+    assert _nmax(img.cpu().numpy(), out.detach().numpy()) <= 5e-4
     flat_grad = torch.zeros_like(net.flat)
     dzg, dzl = backward(net, tape, [torch.from_numpy(dimg).cuda()], flat_grad)
     torch.cuda.synchronize()

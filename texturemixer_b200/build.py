@@ -8,7 +8,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
 LIB_PATH = os.path.join(PKG_DIR, 'libtmx.so')
-SOURCES = ['context.cu', 'pointwise.cu', 'conv_ffma.cu', 'conv_tc.cu', 'conv_api.cu', 'perm_host.cu', 'optim.cu', 'backward.cu', 'conv_wgrad.cu', 'gram.cu']
+SOURCES = ['context.cu', 'pointwise.cu', 'conv_ffma.cu', 'conv_tc.cu', 'conv_api.cu', 'perm_host.cu', 'optim.cu', 'backward.cu', 'conv_wgrad.cu', 'gram.cu', 'conv_lin.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--use_fast_math=false', '-Xcompiler', '-fPIC,-O2,-fvisibility=default', '-shared']
 

@@ -483,10 +483,62 @@ __global__ void __launch_bounds__(256) dense_bwd_input_kernel(const float* __res
   }
 }
 
+// Fast path (Cout % 64 == 0, K % 32 == 0): 32 features per block (twice the blocks of the kernel above: the 8192-feature
+// head fills the SMs), 64-output chunks, 128-bit loads of the weight rows; thread (kk, ng) owns feature kk and samples
+// ng*4 .. ng*4+3.
+__global__ void __launch_bounds__(256) dense_bwd_input4_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                               const float* __restrict__ w, float wscale,
+                                                               float* __restrict__ dx, int N, int K, int Cout,
+                                                               int lrelu, float alpha) {
+  __shared__ float ws[32][65];
+  __shared__ float zs[32][65];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int kk = threadIdx.x & 31, ng = threadIdx.x >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int o0 = 0; o0 < Cout; o0 += 64) {
+    for (int e = threadIdx.x; e < 32 * 16; e += 256) {
+      const int r = e >> 4, c4 = (e & 15) * 4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(w + (long long)(k0 + r) * Cout + o0 + c4));
+      ws[r][c4] = v.x; ws[r][c4 + 1] = v.y; ws[r][c4 + 2] = v.z; ws[r][c4 + 3] = v.w;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + r < N) {
+        g = __ldg(reinterpret_cast<const float4*>(dy + (long long)(n0 + r) * Cout + o0 + c4));
+        if (lrelu) {
+          const float4 yv = __ldg(reinterpret_cast<const float4*>(y + (long long)(n0 + r) * Cout + o0 + c4));
+          g.x *= yv.x > 0.f ? 1.f : alpha;
+          g.y *= yv.y > 0.f ? 1.f : alpha;
+          g.z *= yv.z > 0.f ? 1.f : alpha;
+          g.w *= yv.w > 0.f ? 1.f : alpha;
+        }
+      }
+      zs[r][c4] = g.x; zs[r][c4 + 1] = g.y; zs[r][c4 + 2] = g.z; zs[r][c4 + 3] = g.w;
+    }
+    __syncthreads();
+#pragma unroll 16
+    for (int c = 0; c < 64; ++c) {
+      const float wv = ws[kk][c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(zs[ng * 4 + i][c], wv, acc[i]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ng * 4 + i;
+    if (n < N) dx[(long long)n * K + k0 + kk] = acc[i] * wscale;
+  }
+}
+
 extern "C" int tmx_dense_bwd_input(tmx_handle_t h, const float* dy, const float* y, const float* w, float wscale,
                                    float* dx, int N, int K, int Cout, int lrelu, float alpha, tmx_stream_t s) {
   TMX_REQUIRE(h && dy && w && dx && (!lrelu || y), TMX_ERR_ARG, "tmx_dense_bwd_input: NULL argument");
   TMX_REQUIRE(N > 0 && K > 0 && Cout > 0, TMX_ERR_SHAPE, "tmx_dense_bwd_input: bad shape");
+  if (Cout % 64 == 0 && K % 32 == 0 && (((uintptr_t)dy | (uintptr_t)y | (uintptr_t)w) & 15) == 0) {
+    dim3 grid4(K / 32, tmx_ceil_div(N, 32));
+    dense_bwd_input4_kernel<<<grid4, 256, 0, (cudaStream_t)s>>>(dy, y, w, wscale, dx, N, K, Cout, lrelu, alpha);
+    TMX_LAUNCHED(h, "dense_bwd_input_kernel");
+    return TMX_OK;
+  }
   dim3 grid(tmx_ceil_div(K, 64), tmx_ceil_div(N, 32));
   dense_bwd_input_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(dy, y, w, wscale, dx, N, K, Cout, lrelu, alpha);
   TMX_LAUNCHED(h, "dense_bwd_input_kernel");
@@ -676,10 +728,96 @@ __global__ void __launch_bounds__(256) dense_wgrad_kernel(const float* __restric
   if (db != nullptr && k == 0) db[o] += bacc;
 }
 
+// Fast path (Cout % 128 == 0, K % 64 == 0): block = 128 outputs x 64 features, thread = 4 outputs x 8 features
+// (32 accumulators); the masked dz tile and the x tile of 32 samples at a time sit in shared memory, dw is updated
+// with 128-bit read-modify-writes: the 16.8 MB gradient of the 8192 -> 512 head moves once.
+__global__ void __launch_bounds__(256) dense_wgrad4_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                           const float* __restrict__ y, float* __restrict__ dw,
+                                                           float* __restrict__ db, int N, int K, int Cout, float wscale,
+                                                           int lrelu, float alpha) {
+  __shared__ float zs[32][128];      // masked dz: [sample][output]
+  __shared__ float xs[32][64 + 4];   // x: [sample][feature]
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int o0 = blockIdx.x * 128, k0 = blockIdx.y * 64;
+  float4 acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int n0 = 0; n0 < N; n0 += 32) {
+    for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+      const int n = e >> 5, c4 = (e & 31) * 4;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + n < N) {
+        g = __ldg(reinterpret_cast<const float4*>(dy + (long long)(n0 + n) * Cout + o0 + c4));
+        if (lrelu) {
+          const float4 yv = __ldg(reinterpret_cast<const float4*>(y + (long long)(n0 + n) * Cout + o0 + c4));
+          g.x *= yv.x > 0.f ? 1.f : alpha;
+          g.y *= yv.y > 0.f ? 1.f : alpha;
+          g.z *= yv.z > 0.f ? 1.f : alpha;
+          g.w *= yv.w > 0.f ? 1.f : alpha;
+        }
+      }
+      *reinterpret_cast<float4*>(&zs[n][c4]) = g;
+    }
+    for (int e = threadIdx.x; e < 32 * 16; e += 256) {
+      const int n = e >> 4, k4 = (e & 15) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + n < N) v = __ldg(reinterpret_cast<const float4*>(x + (long long)(n0 + n) * K + k0 + k4));
+      *reinterpret_cast<float4*>(&xs[n][k4]) = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int n = 0; n < 32; ++n) {
+      const float4 g = *reinterpret_cast<const float4*>(&zs[n][tx * 4]);
+      const float4 xa = *reinterpret_cast<const float4*>(&xs[n][ty * 8]);
+      const float4 xb = *reinterpret_cast<const float4*>(&xs[n][ty * 8 + 4]);
+      const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i].x = fmaf(xv[i], g.x, acc[i].x);
+        acc[i].y = fmaf(xv[i], g.y, acc[i].y);
+        acc[i].z = fmaf(xv[i], g.z, acc[i].z);
+        acc[i].w = fmaf(xv[i], g.w, acc[i].w);
+      }
+      bacc.x += g.x;
+      bacc.y += g.y;
+      bacc.z += g.z;
+      bacc.w += g.w;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4* o = reinterpret_cast<float4*>(dw + (long long)(k0 + ty * 8 + i) * Cout + o0 + tx * 4);
+    float4 cur = *o;
+    cur.x = fmaf(acc[i].x, wscale, cur.x);
+    cur.y = fmaf(acc[i].y, wscale, cur.y);
+    cur.z = fmaf(acc[i].z, wscale, cur.z);
+    cur.w = fmaf(acc[i].w, wscale, cur.w);
+    *o = cur;
+  }
+  if (db != nullptr && blockIdx.y == 0 && ty == 0) {
+    float4* o = reinterpret_cast<float4*>(db + o0 + tx * 4);
+    float4 cur = *o;
+    cur.x += bacc.x;
+    cur.y += bacc.y;
+    cur.z += bacc.z;
+    cur.w += bacc.w;
+    *o = cur;
+  }
+}
+
 extern "C" int tmx_dense_wgrad(tmx_handle_t h, const float* x, const float* dy, const float* y, float* dw, float* db, int N,
                                int K, int Cout, float wscale, int lrelu, float alpha, tmx_stream_t s) {
   TMX_REQUIRE(h && x && dy && dw && (!lrelu || y), TMX_ERR_ARG, "tmx_dense_wgrad: NULL argument");
   TMX_REQUIRE(N > 0 && K > 0 && Cout > 0, TMX_ERR_SHAPE, "tmx_dense_wgrad: bad shape");
+  if (Cout % 128 == 0 && K % 64 == 0 &&
+      (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)y | (uintptr_t)dw | (uintptr_t)db) & 15) == 0) {
+    dense_wgrad4_kernel<<<dim3(Cout / 128, K / 64), 256, 0, (cudaStream_t)s>>>(x, dy, y, dw, db, N, K, Cout, wscale, lrelu,
+                                                                               alpha);
+    TMX_LAUNCHED(h, "dense_wgrad_kernel");
+    return TMX_OK;
+  }
   dense_wgrad_kernel<<<tmx_ceil_div((long long)K * Cout, 256), 256, 0, (cudaStream_t)s>>>(x, dy, y, dw, db, N, K, Cout,
                                                                                          wscale, lrelu, alpha);
   TMX_LAUNCHED(h, "dense_wgrad_kernel");
@@ -862,6 +1000,9 @@ extern "C" int tmx_add_f32(tmx_handle_t h, const float* a, const float* b, float
   return TMX_OK;
 }
 
+int tmx_conv2d_dgrad_lin_patch(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, const uint16_t* dz_hi,
+                               const uint16_t* dz_lo, const uint16_t* wt_hi, const uint16_t* wt_lo, float* g_f32,
+                               cudaStream_t st, int* served);
 int tmx_conv2d_dgrad_tc(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, const uint16_t* dz_hi,
                         const uint16_t* dz_lo, const uint16_t* wt_hi, const uint16_t* wt_lo, float* g_f32,
                         cudaStream_t st);
@@ -873,6 +1014,13 @@ extern "C" int tmx_conv2d_dgrad(tmx_handle_t h, int N, int H, int W, int Cin, in
   const void* ptrs[] = {dz_hi, dz_lo, wt_hi, wt_lo, g_f32};
   for (const void* q : ptrs)
     TMX_REQUIRE(((uintptr_t)q & 15) == 0, TMX_ERR_ARG, "tmx_conv2d_dgrad: buffers must be 16-byte aligned (%p)", q);
+  if (k == 3 && dz_hi && dz_lo && wt_hi && wt_lo && g_f32 && N > 0 && H > 0 && W > 0) {
+    // thin layers (Cin, Cout in {16, 32, 64}): one haloed patch per tile instead of nine tap boxes (conv_lin.cu)
+    int served = 0;
+    const int rc = tmx_conv2d_dgrad_lin_patch(h, N, H, W, Cin, Cout, dz_hi, dz_lo, wt_hi, wt_lo, g_f32, (cudaStream_t)s,
+                                              &served);
+    if (rc != TMX_OK || served) return rc;
+  }
   return tmx_conv2d_dgrad_tc(h, N, H, W, Cin, Cout, k, dz_hi, dz_lo, wt_hi, wt_lo, g_f32, (cudaStream_t)s);
 }
 

@@ -70,7 +70,7 @@ struct ConvTcParams {
   int lrelu, has_res, up2_out;
   int phase;      // UP2_IN sub-pixel form: GEMM column = (a*2+b)*cout_log + c, output pixel (2y+a, 2x+b)
   int cout_log;   // logical Cout of the layer (== Cout unless phase)
-  int halo_rep;   // halo of the written planes: 0 REFLECT, 1 REPLICATE (clamp), 2 ZERO (left as the caller zeroed it)
+  int halo_rep;   // halo of the written planes: 0 REFLECT, 1 REPLICATE (clamp), 2 ZERO (zeros written next to the border)
   // LIN mode (data gradient): pixels are the rows of ONE zero-ringed grid [N][H+4][W+4] shared by input and
   // output; a tile is 128 consecutive grid rows, tap (U,V) is the constant row shift (U-1)*pitch + (V-1), so the
   // A operand is a 2-D TMA box at row m0 + shift (out-of-range rows read zeros) and every grid position -
@@ -108,7 +108,15 @@ struct TcCfg {
   static constexpr int kSmemBudget = 200 * 1024;
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 12 ? 12 : kStagesRaw;
-  static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
+  // STACK (single CTA, BN <= 64): bf16x3 as TWO MMAs per K step instead of three - the weight tile's hi and lo rows
+  // sit next to each other in shared memory, so ONE MMA with N = 2*BN gives x_hi*w_hi and x_hi*w_lo, a second one
+  // x_lo*w_hi; the accumulator has 3*BN columns which the epilogue adds.  A tcgen05.mma with a small N costs ~80-115
+  // cycles whatever N is (the shared-memory read of its 4 KB A operand, measured in conv_lin.cu), so the thin layers'
+  // main loop gets 1.5x shorter; at BN >= 128 the MMAs are math-bound and 2*BN would not fit a second accumulator.
+  static constexpr bool kStack = !PAIR && BN <= 64;
+  static constexpr int kAccCols = kStack ? 3 * BN : BN;
+  static constexpr int kTmemRaw = 2 * kAccCols;
+  static constexpr int kTmemCols = kTmemRaw <= 32 ? 32 : (kTmemRaw <= 64 ? 64 : (kTmemRaw <= 128 ? 128 : (kTmemRaw <= 256 ? 256 : 512)));
   static constexpr int kAuxBytes = 1024;  // barriers + tmem ptr
   static constexpr int kSmemBytes = kStages * kStageBytes + kAuxBytes + 1024 /*align slack*/;
   static_assert(kStages >= 2, "need at least a double buffer");
@@ -226,9 +234,9 @@ __global__ void __launch_bounds__(kThreads, 1)
           tma_load_4d(sa, &tm_a_hi, &full_bar[stage], 0, x0, y0, n0);            // halo rows y0 .. y0 + bh + 1
           tma_load_4d(sa + p.patch_bytes, &tm_a_lo, &full_bar[stage], 0, x0, y0, n0);
 #pragma unroll
-          for (int u = 0; u < 3; ++u) {
-            tma_load_2d(sb + u * brows * KC * 2, mb_hi, &full_bar[stage], u * p.Cin, brow);
-            tma_load_2d(sb + (3 + u) * brows * KC * 2, mb_lo, &full_bar[stage], u * p.Cin, brow);
+          for (int u = 0; u < 3; ++u) {     // per vertical tap: [hi rows | lo rows] (one stacked B operand)
+            tma_load_2d(sb + (2 * u) * brows * KC * 2, mb_hi, &full_bar[stage], u * p.Cin, brow);
+            tma_load_2d(sb + (2 * u + 1) * brows * KC * 2, mb_lo, &full_bar[stage], u * p.Cin, brow);
           }
           if (++stage == p.patch_stages) {
             stage = 0;
@@ -265,8 +273,10 @@ __global__ void __launch_bounds__(kThreads, 1)
               tma_load_4d(sa, &tm_a_hi, &full_bar[stage], c0, ax, ay, n0);
               tma_load_4d(sa + Cfg::kABytes, &tm_a_lo, &full_bar[stage], c0, ax, ay, n0);
             }
+            // the lo rows directly behind the hi rows (a column slice of a split item has fewer rows than BN)
             tma_load_2d(sa + 2 * Cfg::kABytes, mb_hi, &full_bar[stage], bk, brow);
-            tma_load_2d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, mb_lo, &full_bar[stage], bk, brow);
+            tma_load_2d(sa + 2 * Cfg::kABytes + (Cfg::kStack ? brows * KC * 2 : Cfg::kBBytes), mb_lo, &full_bar[stage], bk,
+                        brow);
           }
           if (++stage == S) {
             stage = 0;
@@ -287,9 +297,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * Cfg::kAccCols);
+        const int bn_i = item < p.full_items ? BN : BN / p.split;          // columns of this item
+        const uint32_t idesc2 = make_idesc(2 * bn_i, kTileM);                 // STACK: N = hi rows + lo rows
         if (!PAIR && p.patch) {
-          const int brows_i = item < p.full_items ? BN : BN / p.split;
+          const int brows_i = bn_i;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + (size_t)stage * p.patch_stage_bytes);
@@ -299,14 +311,12 @@ __global__ void __launch_bounds__(kThreads, 1)
             const uint32_t aoff = (uint32_t)(u * p.bw * KC * 2);           // u patch rows down: whole swizzle atoms
             const uint64_t a_hi = make_smem_desc<KC>(sa + aoff);
             const uint64_t a_lo = make_smem_desc<KC>(sa + p.patch_bytes + aoff);
-            const uint64_t b_hi = make_smem_desc<KC>(sb + u * brows_i * KC * 2);
-            const uint64_t b_lo = make_smem_desc<KC>(sb + (3 + u) * brows_i * KC * 2);
+            const uint64_t b_hi = make_smem_desc<KC>(sb + (2 * u) * brows_i * KC * 2);
 #pragma unroll
-            for (int kk = 0; kk < KC / 16; ++kk) {
+            for (int kk = 0; kk < KC / 16; ++kk) {      // (patch mode implies BN <= 64: always STACK)
               const uint64_t adv = (uint64_t)(kk * 2);
-              umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, (u | kk) != 0);
-              umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
-              umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, 1);
+              umma_bf16(tmem_d + 2 * bn_i, a_lo + adv, b_hi + adv, idesc, (u | kk) != 0);
+              umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc2, (u | kk) != 0);
             }
           }
           umma_commit(&empty_bar[stage]);
@@ -333,6 +343,9 @@ __global__ void __launch_bounds__(kThreads, 1)
               umma2_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, (ks | kk) != 0);
               umma2_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
               umma2_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, 1);
+            } else if (Cfg::kStack) {
+              umma_bf16(tmem_d + 2 * bn_i, a_lo + adv, b_hi + adv, idesc, (ks | kk) != 0);
+              umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc2, (ks | kk) != 0);      // b_hi + the lo rows behind it
             } else {
               umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, (ks | kk) != 0);
               umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
@@ -365,9 +378,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int Ho = p.up2_out ? 2 * Hl : Hl, Wo = p.up2_out ? 2 * Wl : Wl;      // size of the written planes
     const long long Hp = Ho + 2, Wp = Wo + 2;
     const int CL = p.cout_log;
-    // source row/col copied into halo slot 0, and (size - hi_off) into slot size+1; ZERO halo: no pixel matches
-    const int lo_edge = p.halo_rep == 1 ? 0 : (p.halo_rep == 2 ? -7 : 1);
-    const int hi_off = p.halo_rep == 1 ? 1 : (p.halo_rep == 2 ? -7 : 2);
+    // source row/col copied into halo slot 0, and (size - hi_off) into slot size+1; ZERO halo: the border pixels
+    // write zeros into the slots next to them (so the planes need no memset)
+    const int lo_edge = p.halo_rep >= 1 ? 0 : 1;
+    const int hi_off = p.halo_rep >= 1 ? 1 : 2;
+    const bool halo_zero = p.halo_rep == 2;
     const bool has_bias = p.bias != nullptr;
     const float slope = p.lrelu ? p.alpha : 1.f;
     const float4* rgb_s = reinterpret_cast<const float4*>(rgb_smem);
@@ -389,8 +404,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-      const int ngroups = BN / parts / GW;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * Cfg::kAccCols);
+      const int bn_i = BN / parts;
+      const int ngroups = bn_i / GW;
       // residual stream (networks.py:437; never combined with the sub-pixel form): the loads of group g+1 are
       // issued before the TMEM read of group g so that their latency hides behind it
       const bool res_on = p.has_res && valid;
@@ -409,9 +425,29 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int j = 0; j < GW / 4; ++j) rnext[j] = __ldg(res_base + (g + 1) * (GW / 4) + j);
         }
         uint32_t acc[32];
-        if (GW == 32) tmem_ld32(taddr0 + g * GW, acc);
-        else tmem_ld16(taddr0 + g * GW, acc);
-        tmem_ld_wait();
+        if (Cfg::kStack) {
+          // three column groups of the accumulator: x_lo*w_hi + x_hi*w_lo first, then the dominant x_hi*w_hi
+          uint32_t tmp[32];
+          if (GW == 32) {
+            tmem_ld32(taddr0 + 2 * bn_i + g * GW, acc);
+            tmem_ld32(taddr0 + bn_i + g * GW, tmp);
+          } else {
+            tmem_ld16(taddr0 + 2 * bn_i + g * GW, acc);
+            tmem_ld16(taddr0 + bn_i + g * GW, tmp);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < GW; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(tmp[j]));
+          if (GW == 32) tmem_ld32(taddr0 + g * GW, tmp);
+          else tmem_ld16(taddr0 + g * GW, tmp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < GW; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(tmp[j]));
+        } else {
+          if (GW == 32) tmem_ld32(taddr0 + g * GW, acc);
+          else tmem_ld16(taddr0 + g * GW, acc);
+          tmem_ld_wait();
+        }
         if (valid) {
           const int col0 = cblk * BN + part * (BN / parts) + g * GW;
           int cbase = col0, oy = y, ox = x;
@@ -465,14 +501,15 @@ __global__ void __launch_bounds__(kThreads, 1)
               ph[j] = h0 | (h1 << 16);
               pl[j] = l0 | (l1 << 16);
             }
-            auto store_px = [&](int prow, int pcol) {
+            auto store_px = [&](int prow, int pcol, bool halo = true) {
               const long long o = (((long long)n * Hp + prow) * Wp + pcol) * CL + cbase;
               uint4* oh = reinterpret_cast<uint4*>(p.y_hi + o);
               uint4* ol = reinterpret_cast<uint4*>(p.y_lo + o);
+              const bool z = halo && halo_zero;
 #pragma unroll
               for (int j = 0; j < GW / 8; ++j) {
-                oh[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-                ol[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+                oh[j] = z ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+                ol[j] = z ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
               }
             };
             if (!p.up2_out) {
@@ -480,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, 1)
               const int r0 = oy + 1, c0 = ox + 1;
               const int r1 = oy == lo_edge ? 0 : (oy == Ho - hi_off ? Ho + 1 : -1);
               const int c1 = ox == lo_edge ? 0 : (ox == Wo - hi_off ? Wo + 1 : -1);
-              store_px(r0, c0);
+              store_px(r0, c0, false);
               if (r1 >= 0) store_px(r1, c0);
               if (c1 >= 0) {
                 store_px(r0, c1);
@@ -494,7 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 for (int e = 0; e < 2; ++e) {
                   const int X = 2 * ox + e;
                   const int c1 = X == lo_edge ? 0 : (X == Wo - hi_off ? Wo + 1 : -1);
-                  store_px(Y + 1, X + 1);
+                  store_px(Y + 1, X + 1, false);
                   if (r1 >= 0) store_px(r1, X + 1);
                   if (c1 >= 0) {
                     store_px(Y + 1, c1);

@@ -71,7 +71,12 @@ struct WCfg {
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  // STACK (BN <= 128): two MMAs per K step instead of three - the dz tile's hi and lo column blocks are consecutive
+  // 64-channel blocks LBO apart, so one MMA with N = 2*BN gives x_hi*dz_hi and x_hi*dz_lo; a second one x_lo*dz_hi;
+  // 3*BN accumulator columns, added by the epilogue (small-N MMAs are bound by the A-operand read, see conv_lin.cu)
+  static constexpr bool kStack = BN <= 128;
+  static constexpr int kAccCols = kStack ? 3 * BN : BN;
+  static constexpr int kTmemCols = kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512)));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
   static_assert(kStages >= 2, "need at least a double buffer");
 };
@@ -186,9 +191,14 @@ __global__ void __launch_bounds__(kWThreads, 1)
           const uint64_t a_lo = make_desc_mn(sa + Cfg::kABytes + koff, kBlk);
           const uint64_t b_hi = make_desc_mn(sa + 2 * Cfg::kABytes + koff, kBlk);
           const uint64_t b_lo = make_desc_mn(sa + 2 * Cfg::kABytes + Cfg::kBBytes + koff, kBlk);
-          umma_bf16(tmem_base, a_lo, b_hi, idesc, (c | kk) != 0);
-          umma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
-          umma_bf16(tmem_base, a_hi, b_hi, idesc, 1);
+          if (Cfg::kStack) {
+            umma_bf16(tmem_base + 2 * BN, a_lo, b_hi, idesc, (c | kk) != 0);
+            umma_bf16(tmem_base, a_hi, b_hi, make_idesc_mn(2 * BN), (c | kk) != 0);   // [dz_hi | dz_lo] blocks
+          } else {
+            umma_bf16(tmem_base, a_lo, b_hi, idesc, (c | kk) != 0);
+            umma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
+            umma_bf16(tmem_base, a_hi, b_hi, idesc, 1);
+          }
         }
         umma_commit(&empty_bar[stage]);
         if (++stage == S) {
@@ -213,7 +223,18 @@ __global__ void __launch_bounds__(kWThreads, 1)
 #pragma unroll 1
     for (int g = 0; g < BN / 32; ++g) {
       uint32_t acc[32];
-      if (nchunks > 0) {
+      if (nchunks > 0 && Cfg::kStack) {
+        uint32_t tmp[32];
+        tmem_ld32(taddr0 + 2 * BN + g * 32, acc);
+        tmem_ld32(taddr0 + BN + g * 32, tmp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(tmp[j]));
+        tmem_ld32(taddr0 + g * 32, tmp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(tmp[j]));
+      } else if (nchunks > 0) {
         tmem_ld32(taddr0 + g * 32, acc);
         tmem_ld_wait();
       } else {

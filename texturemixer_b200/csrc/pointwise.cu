@@ -662,6 +662,50 @@ __global__ void __launch_bounds__(256) dense_partial_kernel(const float* __restr
   }
 }
 
+// Fast path (Cout % 128 == 0, K % 128 == 0: the 8192 -> 512 head): the weight matrix is streamed ONCE with 128-bit
+// loads.  Block = (128 outputs, 128-long k-slice, 32 samples); lane tx owns 4 consecutive outputs, warp ty owns
+// samples ty*4 .. ty*4+3; x of the slice sits in shared memory (broadcast reads).  Same partial layout as above.
+constexpr int kDenseKS4 = 128;
+__global__ void __launch_bounds__(256) dense_partial4_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             float* __restrict__ part, int N, int K, int Cout) {
+  __shared__ float xs[kDenseNT][kDenseKS4 + 4];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int o = blockIdx.x * 128 + tx * 4;
+  const int k0 = blockIdx.y * kDenseKS4;
+  const int n0 = blockIdx.z * kDenseNT;
+  for (int e = threadIdx.x; e < kDenseNT * (kDenseKS4 / 4); e += 256) {
+    const int n = e / (kDenseKS4 / 4), k4 = (e % (kDenseKS4 / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 + n < N) v = __ldg(reinterpret_cast<const float4*>(x + (long long)(n0 + n) * K + k0 + k4));
+    *reinterpret_cast<float4*>(&xs[n][k4]) = v;
+  }
+  __syncthreads();
+  float4 acc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* wp = reinterpret_cast<const float4*>(w + (long long)k0 * Cout + o);
+  const long long wstride = Cout / 4;
+#pragma unroll 8
+  for (int k = 0; k < kDenseKS4; ++k) {
+    const float4 wv = __ldg(wp + k * wstride);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float xv = xs[ty * 4 + i][k];
+      acc[i].x = fmaf(xv, wv.x, acc[i].x);
+      acc[i].y = fmaf(xv, wv.y, acc[i].y);
+      acc[i].z = fmaf(xv, wv.z, acc[i].z);
+      acc[i].w = fmaf(xv, wv.w, acc[i].w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    if (n < N) *reinterpret_cast<float4*>(part + ((long long)blockIdx.y * N + n) * Cout + o) = acc[i];
+  }
+}
+
+static bool dense_fast(int K, int Cout) { return Cout % 128 == 0 && K % kDenseKS4 == 0; }
+
 __global__ void __launch_bounds__(256) dense_finish_kernel(const float* __restrict__ part, const float* __restrict__ bias,
                                                            float* __restrict__ y, int N, int Cout, int slices,
                                                            float wscale, int lrelu, float alpha) {
@@ -676,7 +720,7 @@ __global__ void __launch_bounds__(256) dense_finish_kernel(const float* __restri
 
 extern "C" int tmx_dense_workspace_bytes(int N, int K, int Cout, size_t* bytes) {
   TMX_REQUIRE(bytes && N > 0 && K > 0 && Cout > 0, TMX_ERR_ARG, "tmx_dense_workspace_bytes: bad argument");
-  *bytes = (size_t)tmx_ceil_div(K, kDenseKS) * N * Cout * sizeof(float);
+  *bytes = (size_t)tmx_ceil_div(K, dense_fast(K, Cout) ? kDenseKS4 : kDenseKS) * N * Cout * sizeof(float);
   return TMX_OK;
 }
 
@@ -684,10 +728,12 @@ extern "C" int tmx_dense_fwd(tmx_handle_t h, const float* x, const float* w, con
                              float* workspace, int N, int K, int Cout, int lrelu, float alpha, tmx_stream_t s) {
   TMX_REQUIRE(h && x && w && y && workspace, TMX_ERR_ARG, "tmx_dense_fwd: NULL argument");
   TMX_REQUIRE(N > 0 && K > 0 && Cout > 0, TMX_ERR_SHAPE, "tmx_dense_fwd: bad shape N=%d K=%d Cout=%d", N, K, Cout);
-  const int slices = tmx_ceil_div(K, kDenseKS);
-  dim3 grid(tmx_ceil_div(Cout, 64), slices, tmx_ceil_div(N, kDenseNT));
+  const bool fast = dense_fast(K, Cout) && (((uintptr_t)x | (uintptr_t)w | (uintptr_t)workspace) & 15) == 0;
+  const int slices = tmx_ceil_div(K, fast ? kDenseKS4 : kDenseKS);
+  dim3 grid(tmx_ceil_div(Cout, fast ? 128 : 64), slices, tmx_ceil_div(N, kDenseNT));
   TMX_REQUIRE(grid.y <= 65535 && grid.z <= 65535, TMX_ERR_SHAPE, "tmx_dense_fwd: problem too large");
-  dense_partial_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, w, workspace, N, K, Cout);
+  if (fast) dense_partial4_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, w, workspace, N, K, Cout);
+  else dense_partial_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, w, workspace, N, K, Cout);
   TMX_LAUNCHED(h, "dense_partial_kernel");
   dense_finish_kernel<<<tmx_ceil_div((long long)N * Cout, 256), 256, 0, (cudaStream_t)s>>>(
       workspace, bias, y, N, Cout, slices, wscale, lrelu, alpha);

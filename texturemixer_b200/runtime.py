@@ -249,13 +249,10 @@ class Runtime:
                 io.y_f32 = out.f32.data_ptr()
             if want_split:
                 ho, wo = (h * 2, w_ * 2) if up2_out else (h, w_)
-                if halo_out == 'zero':       # SAME-padded consumer: the kernel writes the interior, the ring stays 0
-                    out.hi = torch.zeros(x.n, ho + 2, wo + 2, cout, dtype=torch.bfloat16, device=self.device)
-                    out.lo = torch.zeros(x.n, ho + 2, wo + 2, cout, dtype=torch.bfloat16, device=self.device)
+                out.hi = self.planes(x.n, ho + 2, wo + 2, cout)
+                out.lo = self.planes(x.n, ho + 2, wo + 2, cout)
+                if halo_out == 'zero':       # SAME-padded consumer: the border pixels' threads write the zero ring
                     flags |= _lib.CONV_HALO_ZERO
-                else:
-                    out.hi = self.planes(x.n, ho + 2, wo + 2, cout)
-                    out.lo = self.planes(x.n, ho + 2, wo + 2, cout)
                 out.halo = halo_out
                 io.y_hi, io.y_lo = out.hi.data_ptr(), out.lo.data_ptr()
                 if up2_out:
