@@ -572,9 +572,19 @@ class Network:
                     ins = [np.concatenate([a[b:e] for b, e in parts[g]], axis=0) for a in in_arrays]
                 return net.run(*ins, return_as_list=True, minibatch_size=per_dev_mb, num_gpus=1, **conv_kwargs,
                                **dynamic_kwargs)
-        for d in devices:                      # replicas (and their weight copies) are made on the calling thread
+        # replicas, their weight copies and their CUDA graphs are made on the calling thread, one after the other: a
+        # stream capture does not tolerate another host thread synchronising or allocating meanwhile
+        conv = (conv_kwargs['out_mul'], conv_kwargs['out_add'], conv_kwargs['out_shrink'], conv_kwargs['out_dtype'])
+        for g, d in enumerate(devices):
             with torch.cuda.device(d):
-                self._replica_on(d)
+                net = self._replica_on(d)
+                n_g = sum(e - b for b, e in parts[g])
+                if n_g and not os.environ.get('TMX_NO_GRAPH'):
+                    for k, b in enumerate(range(0, n_g, per_dev_mb)):
+                        shapes = [(min(b + per_dev_mb, n_g) - b,) + tuple(_collapse_broadcast(a).shape[1:])
+                                  for a in in_arrays]
+                        net._forward_graph(k & 1, shapes, conv, dynamic_kwargs)
+                    torch.cuda.synchronize(d)
         with concurrent.futures.ThreadPoolExecutor(max_workers=num_gpus) as ex:
             results = list(ex.map(job, range(num_gpus)))
         first = next(r for r in results if r is not None)
@@ -621,7 +631,8 @@ class Network:
             gc_was_on = gc.isenabled()
             gc.disable()
             try:
-                with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                # (an explicit capture stream: torch's default one is created once, on whatever device was current)
+                with torch.cuda.graph(g, stream=side, capture_error_mode='thread_local'):
                     outs = self.get_output_for(*static_in, return_as_list=True, **dynamic_kwargs)
                     static_out = [_convert_output(x, *conv) for x in outs]
             finally:
