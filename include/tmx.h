@@ -286,6 +286,12 @@ int tmx_loss_l1_grad(tmx_handle_t h, const float* a, const float* b, float* grad
 int tmx_latent_gather_bwd(tmx_handle_t h, const float* dcanvas, float* dsrc, const int32_t* idx_h, const int32_t* idx_w,
                           int N, int C, int sh, int sw, int H, int W, uint64_t pin_rows, uint64_t pin_cols, int reverse,
                           tmx_stream_t s);
+/* The same for a gradient that is non-zero only inside the [wh x ww] window of the canvas at (oy, ox) (crop-aware
+ * G_fcn, loss.crop_window): dwin is NCHW [N][C][wh][ww]; off_dev, when non-NULL, holds {oy, ox} on the device. */
+int tmx_latent_gather_bwd_window(tmx_handle_t h, const float* dwin, float* dsrc, const int32_t* idx_h,
+                                 const int32_t* idx_w, int N, int C, int sh, int sw, int H, int W, int wh, int ww, int oy,
+                                 int ox, const int32_t* off_dev, uint64_t pin_rows, uint64_t pin_cols, int reverse,
+                                 tmx_stream_t s);
 /* out[row] (+)= scale * sum_i f(in[row][i]), f = identity or square: adjoint of tiling a [N][C][1][1] code over a
  * canvas (loss.py:176), loss means, per-sample squared gradient norms (loss.py:334). */
 int tmx_row_sum(tmx_handle_t h, const float* in, float* out, int rows, int len, float scale, int accumulate, int square,

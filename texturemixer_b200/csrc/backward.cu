@@ -183,7 +183,8 @@ extern "C" int tmx_grad_prepare(tmx_handle_t h, const tmx_grad_desc_t* d, const 
   const int threads = P.ppb * P.C8;
   const long long units = rows * (long long)(d->W + 4) * P.C8;
   TMX_REQUIRE(units < (1ll << 31) - (1 << 20), TMX_ERR_SHAPE, "tmx_grad_prepare: grid too large");
-  // persistent-style grid: 4 resident CTAs per SM (64 registers per thread), fewer when the map is small
+  // persistent-style grid: 4 resident CTAs per SM (64 registers per thread), fewer when the map is small.  (Two units
+  // in flight per thread at 3 CTAs per SM was tried: 95 -> 113 us for the 64x64 c256 case - fewer threads, not more bytes)
   long long blocks = (units + threads - 1) / threads;
   if (blocks > 4LL * h->sm_count) blocks = 4LL * h->sm_count;
   P.rpb = 0;
@@ -676,6 +677,54 @@ extern "C" int tmx_latent_gather_bwd(tmx_handle_t h, const float* dcanvas, float
   blend_copy_bwd_kernel<<<tmx_ceil_div(total, 256), 256, 0, (cudaStream_t)s>>>(dcanvas, dsrc, idx_h, idx_w, N, C, sh, sw,
                                                                                 H, W, pin_rows, pin_cols, reverse);
   TMX_LAUNCHED(h, "blend_copy_bwd_kernel");
+  return TMX_OK;
+}
+
+// The same scatter restricted to a [wh x ww] window of the canvas at (oy, ox) - `dwin` is the gradient w.r.t. that
+// window only (crop-aware G_fcn: everything outside it is zero), the offset comes from `off_dev` = {oy, ox} on the
+// device when given (CUDA-graph replays): no zero canvas is built and only wh*ww of the H*W positions issue an atomic.
+__global__ void __launch_bounds__(256) blend_copy_bwd_window_kernel(const float* __restrict__ dwin, float* __restrict__ dsrc,
+                                                                    const int32_t* __restrict__ idx_h,
+                                                                    const int32_t* __restrict__ idx_w, int N, int C,
+                                                                    int h, int w, int H, int W, int wh, int ww, int oy,
+                                                                    int ox, const int32_t* __restrict__ off_dev,
+                                                                    unsigned long long pin_rows,
+                                                                    unsigned long long pin_cols, int reverse) {
+  const long long total = (long long)N * C * wh * ww;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  if (off_dev != nullptr) {
+    oy = __ldg(off_dev);
+    ox = __ldg(off_dev + 1);
+  }
+  const int j = ox + (int)(t % ww);
+  long long q = t / ww;
+  const int i = oy + (int)(q % wh);
+  q /= wh;
+  const int c = (int)(q % C);
+  const int n = (int)(q / C);
+  if (i < 0 || i >= H || j < 0 || j >= W) return;
+  const bool pinned = pin_rows != 0 && ((pin_rows >> (i / h)) & 1ull) && ((pin_cols >> (j / w)) & 1ull);
+  int yy = i, xx = j;
+  if (!pinned) {
+    if (idx_h) yy = __ldg(idx_h + (long long)n * H + i);
+    if (idx_w) xx = __ldg(idx_w + (long long)n * W + j);
+  }
+  const int nn = reverse ? N - 1 - n : n;
+  atomicAdd(dsrc + (((long long)nn * C + c) * h + yy % h) * w + xx % w, __ldg(dwin + t));
+}
+
+extern "C" int tmx_latent_gather_bwd_window(tmx_handle_t h, const float* dwin, float* dsrc, const int32_t* idx_h,
+                                            const int32_t* idx_w, int N, int C, int sh, int sw, int H, int W, int wh,
+                                            int ww, int oy, int ox, const int32_t* off_dev, uint64_t pin_rows,
+                                            uint64_t pin_cols, int reverse, tmx_stream_t s) {
+  TMX_REQUIRE(h && dwin && dsrc, TMX_ERR_ARG, "tmx_latent_gather_bwd_window: NULL argument");
+  TMX_REQUIRE(N > 0 && C > 0 && sh > 0 && sw > 0 && H > 0 && W > 0 && wh > 0 && ww > 0 && wh <= H && ww <= W,
+              TMX_ERR_SHAPE, "tmx_latent_gather_bwd_window: bad shape");
+  const long long total = (long long)N * C * wh * ww;
+  blend_copy_bwd_window_kernel<<<tmx_ceil_div(total, 256), 256, 0, (cudaStream_t)s>>>(
+      dwin, dsrc, idx_h, idx_w, N, C, sh, sw, H, W, wh, ww, oy, ox, off_dev, pin_rows, pin_cols, reverse);
+  TMX_LAUNCHED(h, "blend_copy_bwd_window_kernel");
   return TMX_OK;
 }
 

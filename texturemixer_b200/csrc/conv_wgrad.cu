@@ -287,6 +287,60 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   *o = cur;
 }
 
+// Many-slice form of the two reductions (thin layers: few outputs, up to ~70 pixel slices): one WARP per float4 of
+// outputs, the lanes stride over the slices and a fixed xor-tree adds them (deterministic), lane 0 accumulates into dw.
+// The one-thread-per-output kernels above serialise the slices: 17 us per launch for a 16 -> 16 layer.
+template <bool PACKED>
+__global__ void __launch_bounds__(256) wgrad_reduce_warp_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                                                int splits, int taps, int Cin, int cin_pad, int Cout,
+                                                                int co_pad, int xwin, int bpu, float scale,
+                                                                int overwrite) {
+  const long long total4 = (long long)(PACKED ? 9 : taps) * Cin * Cout / 4;
+  const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (t >= total4) return;
+  const long long e = t * 4;
+  const int co = (int)(e % Cout);
+  const long long q = e / Cout;
+  const int ci = (int)(q % Cin);
+  const int tap = (int)(q / Cin);
+  long long base, sstride;
+  if (PACKED) {
+    const int u = tap / 3, v = tap - u * 3;
+    const int bi = u * bpu + v / xwin;
+    const int row = (bi & 1) * 64 + (v % xwin) * Cin + ci;
+    base = ((long long)(bi >> 1) * kWM + row) * co_pad + co;
+    sstride = (long long)taps * kWM * co_pad;          // taps == tap groups
+  } else {
+    base = ((long long)tap * cin_pad + ci) * co_pad + co;
+    sstride = (long long)taps * cin_pad * co_pad;
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = lane; s < splits; s += 32) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(partial + s * sstride + base));
+    acc.x += v.x;
+    acc.y += v.y;
+    acc.z += v.z;
+    acc.w += v.w;
+  }
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, sft);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, sft);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, sft);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, sft);
+  }
+  if (lane == 0) {
+    float4* o = reinterpret_cast<float4*>(dw + e);
+    float4 cur = overwrite ? make_float4(0.f, 0.f, 0.f, 0.f) : *o;
+    cur.x = fmaf(acc.x, scale, cur.x);
+    cur.y = fmaf(acc.y, scale, cur.y);
+    cur.z = fmaf(acc.z, scale, cur.z);
+    cur.w = fmaf(acc.w, scale, cur.w);
+    *o = cur;
+  }
+}
+
 // PACKED-M reduction: dw[u][v][ci][co] += scale * sum_s partial[s][group][row][co] with
 // block bi = u*bpu + v/xwin, group = bi/2, row = (bi&1)*64 + (v%xwin)*Cin + ci
 __global__ void __launch_bounds__(256) wgrad_reduce_packed_kernel(const float* __restrict__ partial,
@@ -441,9 +495,17 @@ extern "C" int tmx_conv2d_wgrad(tmx_handle_t h, int N, int H, int W, int Cin, in
   else rc = launch_wgrad<64>(h, maps, p, st);
   if (rc) return rc;
   const long long total4 = (long long)k * k * Cin * Cout / 4;
-  if (p.packed)
+  // thin layers (few outputs, many pixel slices): slices in parallel, one warp per float4 of outputs
+  const bool many = p.splits >= 8 && total4 <= 16384;
+  if (p.packed && many)
+    wgrad_reduce_warp_kernel<true><<<tmx_ceil_div(total4 * 32, 256), 256, 0, st>>>(
+        workspace, dw, p.splits, p.taps, Cin, p.ci_tiles * kWM, Cout, p.co_pad, p.xwin, p.bpu, wscale, 0);
+  else if (p.packed)
     wgrad_reduce_packed_kernel<<<tmx_ceil_div(total4, 256), 256, 0, st>>>(workspace, dw, p.splits, p.taps, Cin, Cout,
                                                                           p.co_pad, p.xwin, p.bpu, wscale);
+  else if (many)
+    wgrad_reduce_warp_kernel<false><<<tmx_ceil_div(total4 * 32, 256), 256, 0, st>>>(
+        workspace, dw, p.splits, p.taps, Cin, p.ci_tiles * kWM, Cout, p.co_pad, 1, 1, wscale, 0);
   else
     wgrad_reduce_kernel<<<tmx_ceil_div(total4, 256), 256, 0, st>>>(workspace, dw, p.splits, p.taps, Cin,
                                                                    p.ci_tiles * kWM, Cout, p.co_pad, wscale, 0);

@@ -49,6 +49,20 @@ def _gather_bwd(rt, dcanvas, dsrc, idx_h, idx_w, pins=(0, 0), reverse=False):
                'tmx_latent_gather_bwd')
 
 
+def _gather_bwd_win(rt, d, win, H, W, dsrc, idx_h, idx_w, pins=(0, 0), reverse=False):
+    """`_gather_bwd(_embed(d, win))` without the zero canvas: scatter the window gradient from where it lies."""
+    if win is None:
+        return _gather_bwd(rt, d, dsrc, idx_h, idx_w, pins, reverse)
+    n, c, wh, ww = d.shape
+    h, w = dsrc.shape[2:]
+    oy, ox = win[0], win[1]
+    assert (wh, ww) == tuple(win[2:]), ((wh, ww), tuple(win))
+    _lib.check(rt.lib.tmx_latent_gather_bwd_window(rt.handle, _ptr(d.contiguous()), _ptr(dsrc), _ptr(idx_h), _ptr(idx_w),
+                                                   n, c, h, w, H, W, wh, ww, int(oy), int(ox),
+                                                   _ptr(getattr(win, 'dev', None)), pins[0], pins[1], int(reverse),
+                                                   rt.stream()), 'tmx_latent_gather_bwd_window')
+
+
 def _dev_idx(rt, a):
     if isinstance(a, torch.Tensor):
         return a.to(device=rt.device, dtype=torch.int32).contiguous()
@@ -203,11 +217,6 @@ def plan_on_device(plan, dev_offsets):
 
 def _win(rt, x, win):
     return x if win is None else rt.window(x, win)
-
-
-def _embed(rt, d, win, H, W):
-    """Adjoint of `_win`: the window gradient inside a zero canvas."""
-    return d if win is None else rt.window_embed(d, win, H, W)
 
 
 def fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, ih_f, iw_f, win, blend=None):
@@ -417,7 +426,7 @@ def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, r
         dzg_c, dzl_c = backward(G_fcn, fwd.t_int, [_crop_adjoint(rt, dcr, fwd.interp.shape[2:],
                                                                  fwd.image_window('interp', crop_interp))], grads['G'])
         _row_sum(rt, dzg_c, n * c, dzg_c.shape[2] * dzg_c.shape[3], out=dzg, accumulate=True)
-        _gather_bwd(rt, _embed(rt, dzl_c, fwd.win['interp'], H, W), dzl, fwd.ih_f, fwd.iw_f, pins)
+        _gather_bwd_win(rt, dzl_c, fwd.win['interp'], H, W, dzl, fwd.ih_f, fwd.iw_f, pins)
     if blend_interp_G_weight > 0:
         t = fwd.t
         report['blend_G'], dcr = cg['blend'] if 'blend' in cg else \
@@ -444,8 +453,8 @@ def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, r
                 tmp = _row_sum(rt, d_rev, n * c, wh * ww).view(n, c, 1, 1)
                 _gather_bwd(rt, tmp, dzg.view(n, c, 1, 1), None, None, (0, 0), reverse=True)
             else:
-                _gather_bwd(rt, _embed(rt, d_fwd, win, H, W), dzl, fwd.ih_f, fwd.iw_f, pins)
-                _gather_bwd(rt, _embed(rt, d_rev, win, H, W), dzl, fwd.ih_b, fwd.iw_b, pins, reverse=True)
+                _gather_bwd_win(rt, d_fwd, win, H, W, dzl, fwd.ih_f, fwd.iw_f, pins)
+                _gather_bwd_win(rt, d_rev, win, H, W, dzl, fwd.ih_b, fwd.iw_b, pins, reverse=True)
     dzl_ls = dzg_ls = None
     dzg = dzg.view(n, c, 1, 1)
     if kl_weight > 0:                                                     # loss.py:163-171
