@@ -2,9 +2,10 @@
 full replica, the batch is split contiguously over ranks (run.py:287-296), and the
 only collective is a SUM all-reduce of gradients followed by x 1/num_ranks
 (tfutil.py:326-344).  The reference issues one nccl.all_sum per variable (96 for
-the E+G optimizer); here a network's gradients live in ONE flat fp32 buffer laid
-out like its variable buffer, so an optimizer step is one NCCL all-reduce per
-network over NVLink 5 / NVSwitch.  One process per GPU (torchrun / torch.distributed)."""
+the E+G optimizer); here the gradients of ALL networks of an optimizer phase live in
+ONE flat fp32 bucket (optim.GradientBucket, non-finite marks in its tail), so a train
+step is two NCCL all-reduces over NVLink 5 / NVSwitch.  One process per GPU (torchrun /
+torch.distributed)."""
 import os
 
 import torch
