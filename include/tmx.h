@@ -286,6 +286,16 @@ int tmx_loss_l1_grad(tmx_handle_t h, const float* a, const float* b, float* grad
 int tmx_latent_gather_bwd(tmx_handle_t h, const float* dcanvas, float* dsrc, const int32_t* idx_h, const int32_t* idx_w,
                           int N, int C, int sh, int sw, int H, int W, uint64_t pin_rows, uint64_t pin_cols, int reverse,
                           tmx_stream_t s);
+/* Sampled latent canvases of the config-off interpolation modes (loss.py:176-193, 218-235:
+ * zg_/zl_interp_variational = 'variational' | 'random'; the reference config uses 'hard' / 'permutational').
+ * mu, ls: [N][C][sh][sw]; eps: [N][C][eh][ew] standard-normal draws (1 x 1 or H x W); out / g: [N][C][H][W].
+ * mode 1: out = eps * exp(ls) + mu (sources tiled);  mode 2: mu on the four corner tiles, eps elsewhere.
+ * reverse: sources read batch-reversed.  _bwd ACCUMULATES d out / d mu and (mode 1) d out / d ls. */
+int tmx_latent_noise_fwd(tmx_handle_t h, int mode, const float* mu, const float* ls, const float* eps, float* out, int N,
+                         int C, int sh, int sw, int eh, int ew, int H, int W, int reverse, tmx_stream_t s);
+int tmx_latent_noise_bwd(tmx_handle_t h, int mode, const float* g, const float* ls, const float* eps, float* dmu,
+                         float* dls, int N, int C, int sh, int sw, int eh, int ew, int H, int W, int reverse,
+                         tmx_stream_t s);
 /* The same for a gradient that is non-zero only inside the [wh x ww] window of the canvas at (oy, ox) (crop-aware
  * G_fcn, loss.crop_window): dwin is NCHW [N][C][wh][ww]; off_dev, when non-NULL, holds {oy, ox} on the device. */
 int tmx_latent_gather_bwd_window(tmx_handle_t h, const float* dwin, float* dsrc, const int32_t* idx_h,

@@ -31,15 +31,43 @@ def crop(images, yx, size):
     return images[:, :, y:y + size[0], x:x + size[1]]
 
 
+def zg_canvas(zg_mu, zg_ls, H, W, mode='hard', eps=None):
+    """loss.py:175-180 / 217-222 (callers pass the batch-reversed codes for the blend's second branch)."""
+    if mode == 'hard':
+        return zg_mu.repeat(1, 1, H, W)
+    assert mode == 'variational'
+    return (eps * torch.exp(zg_ls) + zg_mu).repeat(1, 1, H, W)
+
+
+def zl_canvas(zl_mu, zl_ls, scale_h, scale_w, idx_h, idx_w, mode='permutational', eps=None):
+    """loss.py:181-194 / 223-236.  `eps` [N,C,H,W]: the tf.random_normal draws laid out on the canvas ('random' uses
+    the non-corner regions: the reference concatenates three separately drawn blocks, loss.py:189-192)."""
+    if mode == 'permutational':
+        return tiling_permutation(zl_mu, scale_h, scale_w, idx_h, idx_w)
+    if mode == 'hard':
+        return zl_mu.repeat(1, 1, scale_h, scale_w)
+    if mode == 'variational':
+        return eps * torch.exp(zl_ls.repeat(1, 1, scale_h, scale_w)) + zl_mu.repeat(1, 1, scale_h, scale_w)
+    assert mode == 'random'
+    h, w = zl_mu.shape[2:]
+    r1 = torch.cat([zl_mu, eps[:, :, :h, w:-w], zl_mu], dim=3)
+    r2 = eps[:, :, h:-h, :]
+    r3 = torch.cat([zl_mu, eps[:, :, -h:, w:-w], zl_mu], dim=3)
+    return torch.cat([r1, r2, r3], dim=2)
+
+
 def EG_wgan(P, reals, idx, crop_interp, crop_blend, mixing_factors, scale_h=3, scale_w=3, rec_G_weight=1.0,
             pixel_weight=200.0, kl_weight=0.0, interp_G_weight=1.0, blend_interp_G_weight=1.0, cfg=None,
-            gram_weight=0.0, vgg=None, gram_alpha=None):
+            gram_weight=0.0, vgg=None, gram_alpha=None, zg_mode='hard', zl_mode='permutational', noise=None):
     """P: dict of parameter dicts for 'E_zg','E_zl','G','D_rec','D_interp','D_blend'.  Returns the per-sample
     loss vector [N] (the optimizer differentiates its mean, run.py:321) and a dict of named terms.
     gram_weight > 0 adds the VGG-19 Gram terms (loss.py:148-160, 206-213, 248-257) with `vgg` = the weight dict
     ({layer: [filter, bias]}) and `gram_alpha` = the [N,1,1,1] draw of loss.py:253; the loss then has the
-    reference's [N,1,1,N] shape (see vgg_ref.blend_gram_term)."""
+    reference's [N,1,1,N] shape (see vgg_ref.blend_gram_term).
+    zg_mode / zl_mode: zg_interp_variational / zl_interp_variational (config.py:61-62: 'hard' / 'permutational');
+    `noise`: {'zg_f', 'zl_f', 'zg_b', 'zl_b'} standard-normal tensors for the sampling modes (see zl_canvas)."""
     cfg = cfg or R.CONFIG
+    noise = noise or {}
     zg_mu, zg_ls = R.E_zg(reals, P['E_zg'], **cfg['E_zg'])                           # loss.py:119
     zl_mu, zl_ls = R.E_zl(reals, P['E_zl'], **cfg['E_zl'])                           # loss.py:126
     lat = zl_mu.shape[2]
@@ -62,8 +90,9 @@ def EG_wgan(P, reals, idx, crop_interp, crop_blend, mixing_factors, scale_h=3, s
             terms[tag] = -0.5 * (1 + 2 * ls - mu ** 2 - torch.exp(2 * ls)).mean(dim=(1, 2, 3)) * kl_weight
             loss = loss + terms[tag]
     g_cfg = dict(cfg['G_res'], scale_h=scale_h, scale_w=scale_w)
-    zg_c = zg_mu.repeat(1, 1, lat * scale_h, lat * scale_w)                           # loss.py:176 'hard'
-    zl_c = tiling_permutation(zl_mu, scale_h, scale_w, idx['h_forward'], idx['w_forward'])   # loss.py:194
+    zg_c = zg_canvas(zg_mu, zg_ls, lat * scale_h, lat * scale_w, zg_mode, noise.get('zg_f'))       # loss.py:175-180
+    zl_c = zl_canvas(zl_mu, zl_ls, scale_h, scale_w, idx['h_forward'], idx['w_forward'], zl_mode,
+                     noise.get('zl_f'))                                                             # loss.py:181-194
     size = reals.shape[2:]
     if interp_G_weight > 0:
         interp = R.G_res(zg_c, zl_c, P['G'], **g_cfg)                                 # loss.py:197
@@ -74,9 +103,10 @@ def EG_wgan(P, reals, idx, crop_interp, crop_blend, mixing_factors, scale_h=3, s
             terms['interp_gram'] = V.multi_layer_diff(V.grams(crop_i, vgg), real_gram) * gram_weight
             loss = loss + terms['interp_gram']
     if blend_interp_G_weight > 0:
-        zg_r = torch.flip(zg_mu, dims=[0]).repeat(1, 1, lat * scale_h, lat * scale_w)             # loss.py:218
-        zl_r = tiling_permutation(torch.flip(zl_mu, dims=[0]), scale_h, scale_w, idx['h_backward'],
-                                  idx['w_backward'])                                              # loss.py:236
+        zg_r = zg_canvas(torch.flip(zg_mu, dims=[0]), torch.flip(zg_ls, dims=[0]), lat * scale_h, lat * scale_w,
+                         zg_mode, noise.get('zg_b'))                                              # loss.py:217-222
+        zl_r = zl_canvas(torch.flip(zl_mu, dims=[0]), torch.flip(zl_ls, dims=[0]), scale_h, scale_w,
+                         idx['h_backward'], idx['w_backward'], zl_mode, noise.get('zl_b'))        # loss.py:223-236
         t = mixing_factors
         bzg = zg_r + (zg_c - zg_r) * t                                                            # loss.py:238
         bzl = zl_r + (zl_c - zl_r) * t

@@ -259,7 +259,8 @@ def gen_schedule():
 
 # ---------------------------------------------------------------- losses (loss.py executed unmodified)
 sys.path.insert(0, os.path.dirname(HERE))
-from loss_case import (LOSS_N, LOSS_GRAD_STRIDE, LOSS_NETS, GRAM_WEIGHT, loss_case_inputs, vgg_standin_weights,  # noqa: E402
+from loss_case import (LOSS_N, LOSS_GRAD_STRIDE, LOSS_NETS, GRAM_WEIGHT, MODE_CASES, MODES_N, mode_noise,  # noqa: E402
+                       loss_case_inputs, vgg_standin_weights,
                        gram_alpha)                                                                      # (tests/loss_case.py)
 
 
@@ -317,7 +318,7 @@ def gen_losses():
 
     out_all = out
 
-    def run(tag, fn, trainable_scopes, int_draws, float_draws, out=None):
+    def run(tag, fn, trainable_scopes, int_draws, float_draws, out=None, x_np=None, normal_draws=()):
         out = out_all if out is None else out
         tf.reset_default_graph(values=values, requires_grad=True)
         terms = {}
@@ -329,10 +330,17 @@ def gen_losses():
         ints, floats = list(int_draws), list(float_draws)
         tf.RANDOM['uniform_int'] = lambda shp, lo, hi: np.full(shp, ints.pop(0), np.int64)
         tf.RANDOM['uniform'] = lambda shp, lo, hi: floats.pop(0).reshape(shp)
-        x = tf.convert_to_tensor(reals)
+        normals = list(normal_draws)
+
+        def next_normal(shp):
+            a = normals.pop(0)
+            assert tuple(a.shape) == tuple(int(v) for v in shp), (tag, 'tf.random_normal shape', a.shape, shp)
+            return a
+        tf.RANDOM['normal'] = next_normal
+        x = tf.convert_to_tensor(reals if x_np is None else x_np)
         loss = fn(x)
-        assert not ints and not floats, (tag, 'unused random draws', ints, floats)
-        tf.RANDOM['uniform_int'] = tf.RANDOM['uniform'] = None
+        assert not ints and not floats and not normals, (tag, 'unused random draws', ints, floats, len(normals))
+        tf.RANDOM['uniform_int'] = tf.RANDOM['uniform'] = tf.RANDOM['normal'] = None
         loss.t.mean().backward()                                        # tf.reduce_mean(loss), run.py:321-324
         out[tag + '_loss'] = loss.numpy().astype(np.float32)
         for name, val in terms.items():
@@ -382,6 +390,39 @@ def gen_losses():
         **eg_kw_gram), ('E_zg', 'E_zl', 'G'), [ci[0], ci[1], cb[0], cb[1]], [mixes['eg_mix'], gram_alpha(n)], out=gram)
     np.savez_compressed(os.path.join(HERE, 'losses_gram.npz'), **gram)
     print('losses_gram.npz: %d arrays, %.1f MB' % (len(gram), os.path.getsize(os.path.join(HERE, 'losses_gram.npz')) / 1e6))
+
+    # ---- EG_wgan with the config-off interpolation modes (zg_/zl_interp_variational, loss.py:176-193, 218-235); the
+    # graph's tf.random_normal draws are fed in the reference's own call order from canvas-shaped noise tensors
+    n2 = MODES_N
+    _, reals2, idx2, crops2, mixes2 = loss_case_inputs(n2, sh, sw)
+    mats2 = [tf.convert_to_tensor(np.stack([f(r) for r in idx2[k]])[:, None].astype(np.float32))
+             for k, f in (('h_forward', I.index_to_matrix_h), ('w_forward', I.index_to_matrix_w),
+                          ('h_backward', I.index_to_matrix_h), ('w_backward', I.index_to_matrix_w))]
+    noise = mode_noise(n2, C, lat, sh, sw)
+    H2, W2 = lat * sh, lat * sw
+    modes = {'meta_n_sh_sw_stride': np.array([n2, sh, sw, LOSS_GRAD_STRIDE], np.int64)}
+
+    def normals_for(zg, zl, which):
+        out_ = []
+        if zg == 'variational':
+            out_.append(noise['zg_' + which])
+        e = noise['zl_' + which]
+        if zl == 'variational':
+            out_.append(e)
+        elif zl == 'random':                                             # loss.py:189-191: three separately drawn blocks
+            out_ += [e[:, :, :lat, lat:W2 - lat], e[:, :, lat:H2 - lat, :], e[:, :, H2 - lat:, lat:W2 - lat]]
+        return out_
+    ci2, cb2 = crops2['eg_crop_interp'], crops2['eg_crop_blend']
+    for tag, zg, zl in MODE_CASES:
+        kw_m = kw(refcfg.EG_loss)
+        kw_m['gram_weight'] = 0.0
+        kw_m['zg_interp_variational'], kw_m['zl_interp_variational'] = zg, zl
+        run('EG' + tag, lambda x: lossmod.EG_wgan(
+            nets['E_zg'], nets['E_zl'], nets['G'], nets['D_rec'], nets['G_fcn'], nets['D_interp'], nets['D_blend'], n2,
+            x, x, None, *mats2, **kw_m), ('E_zg', 'E_zl', 'G'), [ci2[0], ci2[1], cb2[0], cb2[1]], [mixes2['eg_mix']],
+            out=modes, x_np=reals2, normal_draws=normals_for(zg, zl, 'f') + normals_for(zg, zl, 'b'))
+    np.savez_compressed(os.path.join(HERE, 'losses_modes.npz'), **modes)
+    print('losses_modes.npz: %d arrays, %.1f MB' % (len(modes), os.path.getsize(os.path.join(HERE, 'losses_modes.npz')) / 1e6))
 
 
 if __name__ == '__main__':

@@ -63,3 +63,18 @@ def golden_gradient(g, tag, scope, name):
 def subsample(flat):
     flat = np.asarray(flat).reshape(-1)
     return flat if flat.size <= 4096 else flat[::LOSS_GRAD_STRIDE]
+
+
+# config-off interpolation modes (loss.py:176-193, 218-235): (tag, zg_interp_variational, zl_interp_variational)
+MODE_CASES = (('var', 'variational', 'variational'), ('rnd', 'hard', 'random'), ('hard', 'hard', 'hard'))
+MODES_N = 2                # (two samples: one reverse pair for the blend)
+
+
+def mode_noise(n=MODES_N, c=128, lat=32, scale_h=3, scale_w=3, seed=4242):
+    """The tf.random_normal draws of the sampling modes as canvas-shaped tensors (see oracle.loss_ref.zl_canvas)."""
+    rng = np.random.RandomState(seed)
+    H, W = lat * scale_h, lat * scale_w
+    return {'zg_f': rng.standard_normal((n, c, 1, 1)).astype(np.float32),
+            'zl_f': rng.standard_normal((n, c, H, W)).astype(np.float32),
+            'zg_b': rng.standard_normal((n, c, 1, 1)).astype(np.float32),
+            'zl_b': rng.standard_normal((n, c, H, W)).astype(np.float32)}

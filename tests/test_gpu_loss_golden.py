@@ -16,7 +16,7 @@ import torch
 from oracle import loss_ref as L
 from oracle import networks_ref as R
 
-from loss_case import GOLDEN, LOSS_FUNCS, LOSS_NETS, loss_case_inputs, golden_gradient, subsample
+from loss_case import GOLDEN, LOSS_FUNCS, LOSS_NETS, MODE_CASES, loss_case_inputs, golden_gradient, mode_noise, subsample
 
 pytestmark = pytest.mark.gpu
 
@@ -254,3 +254,40 @@ def test_critic_gradients_with_shared_masks(case, which, monkeypatch):
         assert err <= TOL_GRAD_MASKED, (which, name, err)
     print(which, 'shared masks (%d of %d branches differ): worst variable gradient rel-L2' % (feed.flips, feed.total),
           worst)
+
+
+# ---------------------------------------------------------------------- (c) config-off interpolation modes
+@pytest.mark.parametrize('crop_aware', [True, False])
+@pytest.mark.parametrize('tag,zg,zl', MODE_CASES)
+def test_eg_wgan_interp_modes_vs_reference_golden(tag, zg, zl, crop_aware):
+    """zg_interp_variational = 'variational', zl_interp_variational = 'hard' | 'variational' | 'random'
+    (loss.py:176-193, 218-235) on the device - sampled canvases (tmx_latent_noise_fwd / _bwd), gradients into the
+    encoders' mu AND log_sigma outputs - against tests/golden/losses_modes.npz (the reference's loss.py on the shim)."""
+    import os
+    from texturemixer_b200 import loss as dev_loss
+    from texturemixer_b200.network import Network
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), 'losses_modes.npz'))
+    n, sh, sw, _ = (int(v) for v in g['meta_n_sh_sw_stride'])
+    params, reals, idx, crops, mixes = loss_case_inputs(n, sh, sw)
+    nets = {}
+    for k in LOSS_NETS:
+        f = LOSS_FUNCS[k]
+        nets[k] = Network(k, func='networks.' + f, seed=0, num_channels=3, resolution=128, **R.CONFIG[f])
+        nets[k].set_vars(params[k])
+    nets['G_fcn'] = Network('G', func='networks.G_res', reuse=True, share_vars_with=nets['G'], num_channels=3,
+                            resolution=128, scale_h=sh, scale_w=sw, **R.CONFIG['G_res'])
+    modes = dev_loss.interp_modes(zg, zl, {k: _dev(v) for k, v in mode_noise(n, 128, 32, sh, sw).items()})
+    grads = {k: torch.zeros_like(nets[k].flat) for k in ('E_zg', 'E_zl', 'G')}
+    rep = dev_loss.EG_wgan(nets['E_zg'], nets['E_zl'], nets['G'], nets['D_rec'], nets['G_fcn'], nets['D_interp'],
+                           nets['D_blend'], _dev(reals), idx, crops['eg_crop_interp'], crops['eg_crop_blend'],
+                           _dev(mixes['eg_mix']), grads, scale_h=sh, scale_w=sw, crop_aware=crop_aware, modes=modes)
+    torch.cuda.synchronize()
+    rep = {k: float(v.reshape(-1)[0]) for k, v in rep.items()}
+    for mine, ref in (('rec_G', 'rec_G_loss'), ('rec_pixel', 'rec_pixel_loss'), ('interp_G', 'crop_interp_G_loss'),
+                      ('blend_G', 'crop_blend_interp_G_loss')):
+        want = float(g['EG%s_term_Loss_%s' % (tag, ref)].mean())
+        assert abs(rep[mine] - want) <= TOL_TERM * max(1.0, abs(want)), (mine, rep[mine], want)
+    c = dict(g=g, nets=nets)
+    worst = _grads_vs_golden(c, 'EG' + tag, ('E_zg', 'E_zl', 'G'), grads, TOL_GRAD_FLIPS)
+    print('EG_wgan zg=%s zl=%s crop_aware=%s vs reference fixture: worst variable gradient rel-L2 (flip-limited)'
+          % (zg, zl, crop_aware), worst)

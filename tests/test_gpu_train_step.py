@@ -209,3 +209,39 @@ def test_graphed_step_equals_eager_step():
         err = float((a - b).norm() / a.norm())
         print('graphed vs eager, step 4 gradient of', k, err)
         assert err <= 5e-2, (k, err)
+
+
+@pytest.mark.parametrize('zg,zl', [('variational', 'variational'), ('hard', 'random'), ('hard', 'hard')])
+def test_train_step_with_config_off_interpolation_modes(zg, zl):
+    """Trainer with zg_/zl_interp_variational other than the reference config (loss.py:176-193, 218-235, 371-391,
+    446-488): the critics' fakes and the E/G loss sample their canvases from per-graph noise draws; the step runs
+    launch by launch (no CUDA graph), every optimizer applies its update and the encoders receive log_sigma gradients
+    in the 'variational' modes."""
+    from texturemixer_b200.train import Trainer, default_config
+    cfg = default_config()
+    cfg['zg_interp_variational'], cfg['zl_interp_variational'] = zg, zl
+    tr = Trainer(cfg, seed=1000)
+    rng = np.random.RandomState(11)
+    np.random.seed(11)
+    n = 4
+    before = {k: tr.nets[k].flat.clone() for k in ('E_zg', 'E_zl', 'G', 'D_interp', 'D_blend')}
+    for it in range(2):
+        draws = tr.sample_draws(n, rng)
+        assert bool(draws['eg_noise']) == ((zg, zl) != ('hard', 'hard'))       # noise only where a mode samples
+        x = torch.from_numpy(rng.uniform(-1, 1, (n, 3, 128, 128)).astype(np.float32)).cuda()
+        xd = torch.from_numpy(rng.uniform(-1, 1, (n, 3, 128, 128)).astype(np.float32)).cuda()
+        rep = tr.step(x, draws, reals_d=xd)
+        torch.cuda.synchronize()
+        vals = {k: float(v.reshape(-1)[0]) for k, v in rep.items()}
+        assert all(np.isfinite(v) for v in vals.values()), vals
+        assert all(vals[k + '/skipped'] == 0 for k in ('D_rec', 'D_interp', 'D_blend', 'EG'))
+    assert not tr._step_graphs                                       # these modes run eagerly
+    for k, w0 in before.items():
+        assert float((tr.nets[k].flat - w0).abs().max()) > 0, k
+    # d loss / d log_sigma: the second half of the encoders' last-layer channels (networks.py:289-290, 381-382) gets
+    # a gradient exactly when the mode samples with exp(log_sigma) (kl_weight is 0 in the reference config)
+    gz = tr.nets['E_zg'].grad_view(tr.grads['E_zg'], '4x4/zg_Conv3/bias')
+    gl = tr.nets['E_zl'].grad_view(tr.grads['E_zl'], '32x32/z_Conv1/bias')
+    assert (float(gz[128:].abs().max()) > 0) == (zg == 'variational')
+    assert (float(gl[128:].abs().max()) > 0) == (zl == 'variational')
+    assert float(gz[:128].abs().max()) > 0 and float(gl[:128].abs().max()) > 0

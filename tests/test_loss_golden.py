@@ -10,7 +10,8 @@ import torch
 from oracle import loss_ref as L
 from oracle import networks_ref as R
 
-from loss_case import GOLDEN, GRAM_WEIGHT, loss_case_inputs, golden_gradient, gram_alpha, subsample, vgg_standin_weights
+from loss_case import (GOLDEN, GRAM_WEIGHT, MODE_CASES, loss_case_inputs, golden_gradient, gram_alpha, mode_noise, subsample,
+                       vgg_standin_weights)
 
 
 def _rel(got, want):
@@ -110,3 +111,26 @@ def test_eg_wgan_with_gram_terms_matches_reference_code(case):
         assert np.allclose(terms[mine].detach().numpy(), want, rtol=1e-4, atol=1e-5 * np.abs(want).max()), mine
     worst = _check_grads(g, 'EGgram', P, ('E_zg', 'E_zl', 'G'), 2e-4)
     print('EG_wgan + Gram: worst variable gradient rel-L2 vs the reference code', worst)
+
+
+@pytest.mark.parametrize('tag,zg,zl', MODE_CASES)
+def test_eg_wgan_interp_modes_match_reference_code(tag, zg, zl):
+    """The config-off interpolation modes (zg_interp_variational = 'variational'; zl_interp_variational = 'hard' |
+    'variational' | 'random', loss.py:176-193, 218-235): tests/golden/losses_modes.npz comes from the reference's
+    loss.py with its tf.random_normal draws fed from tests/loss_case.mode_noise in the graph's own call order."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), 'losses_modes.npz'))
+    n, sh, sw, _ = (int(v) for v in g['meta_n_sh_sw_stride'])
+    params, reals, idx, crops, mixes = loss_case_inputs(n, sh, sw)
+    noise = {k: torch.from_numpy(v) for k, v in mode_noise(n, 128, 32, sh, sw).items()}
+    P = {k: R.to_torch(params[k], requires_grad=k in ('E_zg', 'E_zl', 'G')) for k in params}
+    loss, terms = L.EG_wgan(P, torch.from_numpy(reals), idx, crops['eg_crop_interp'], crops['eg_crop_blend'],
+                            torch.from_numpy(mixes['eg_mix']), scale_h=sh, scale_w=sw, zg_mode=zg, zl_mode=zl,
+                            noise=noise)
+    loss.mean().backward()
+    assert np.allclose(loss.detach().numpy(), g['EG%s_loss' % tag], rtol=1e-5, atol=0)
+    for mine, ref in (('rec_G', 'rec_G_loss'), ('interp_G', 'crop_interp_G_loss'), ('blend_G', 'crop_blend_interp_G_loss')):
+        want = g['EG%s_term_Loss_%s' % (tag, ref)]
+        assert np.allclose(terms[mine].detach().numpy(), want, rtol=1e-4, atol=1e-5 * np.abs(want).max()), mine
+    worst = _check_grads(g, 'EG' + tag, P, ('E_zg', 'E_zl', 'G'), 2e-4)
+    print('EG_wgan zg=%s zl=%s: worst variable gradient rel-L2 vs the reference code' % (zg, zl), worst)

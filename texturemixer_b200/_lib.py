@@ -90,6 +90,8 @@ _SIGNATURES = {
     'tmx_mbstd_bwd': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'tmx_loss_l1_grad': (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _F, _P]),
     'tmx_latent_gather_bwd': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, C.c_uint64, C.c_uint64, _I, _P]),
+    'tmx_latent_noise_fwd': (C.c_int, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'tmx_latent_noise_bwd': (C.c_int, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'tmx_latent_gather_bwd_window': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, C.c_uint64,
                                                C.c_uint64, _I, _P]),
     'tmx_row_sum': (C.c_int, [_P, _P, _P, _I, _I, _F, _I, _I, _P]),

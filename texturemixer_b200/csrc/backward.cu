@@ -728,6 +728,97 @@ extern "C" int tmx_latent_gather_bwd_window(tmx_handle_t h, const float* dwin, f
   return TMX_OK;
 }
 
+// ---------------------------------------------------------------- sampled latent canvases (config-off interpolation modes)
+// loss.py:176-193, 218-235 with zg_/zl_interp_variational = 'variational' / 'random' (the reference config uses 'hard' /
+// 'permutational').  Sources mu, ls: [N][C][sh][sw] (the encoder's two outputs); eps: [N][C][eh][ew] standard-normal
+// draws (eh x ew = 1 x 1 for the global code, H x W for the local one); canvas [N][C][H][W]; reverse: the sources are
+// read batch-reversed (tf.reverse(axis=[0]) of the blend branch).
+//   mode 1 'variational': out = eps[i % eh][j % ew] * exp(ls[i % sh][j % sw]) + mu[i % sh][j % sw]
+//   mode 2 'random'     : out = mu[i % sh][j % sw] on the four corner tiles, eps[i][j] elsewhere
+__global__ void __launch_bounds__(256) latent_noise_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ ls,
+                                                               const float* __restrict__ eps, float* __restrict__ out,
+                                                               long long total, int N, int C, int sh, int sw, int eh,
+                                                               int ew, int H, int W, int mode, int reverse) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int j = (int)(t % W);
+  long long q = t / W;
+  const int i = (int)(q % H);
+  q /= H;
+  const int c = (int)(q % C);
+  const int n = (int)(q / C);
+  const int ns = reverse ? N - 1 - n : n;
+  const long long so = (((long long)ns * C + c) * sh + i % sh) * sw + j % sw;
+  const float e = __ldg(eps + (((long long)n * C + c) * eh + i % eh) * ew + j % ew);
+  if (mode == 1) {
+    out[t] = e * expf(__ldg(ls + so)) + __ldg(mu + so);
+  } else {
+    const bool corner = (i < sh || i >= H - sh) && (j < sw || j >= W - sw);
+    out[t] = corner ? __ldg(mu + so) : e;
+  }
+}
+
+// adjoint: one thread per source element (ns, c, y, x); dmu / dls are ACCUMULATED (+=), dls may be NULL in mode 2
+__global__ void __launch_bounds__(256) latent_noise_bwd_kernel(const float* __restrict__ g, const float* __restrict__ ls,
+                                                               const float* __restrict__ eps, float* __restrict__ dmu,
+                                                               float* __restrict__ dls, long long total, int N, int C,
+                                                               int sh, int sw, int eh, int ew, int H, int W, int mode,
+                                                               int reverse) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int x = (int)(t % sw);
+  long long q = t / sw;
+  const int y = (int)(q % sh);
+  q /= sh;
+  const int c = (int)(q % C);
+  const int ns = (int)(q / C);
+  const int n = reverse ? N - 1 - ns : ns;
+  const float* gn = g + ((long long)n * C + c) * H * W;
+  const float* en = eps + ((long long)n * C + c) * eh * ew;
+  float am = 0.f, al = 0.f;
+  const float sig = mode == 1 ? expf(__ldg(ls + t)) : 0.f;
+  for (int i = y; i < H; i += sh)
+    for (int j = x; j < W; j += sw) {
+      const float gv = __ldg(gn + (long long)i * W + j);
+      if (mode == 1) {
+        am += gv;
+        al += gv * __ldg(en + (long long)(i % eh) * ew + j % ew) * sig;
+      } else if ((i < sh || i >= H - sh) && (j < sw || j >= W - sw)) {
+        am += gv;
+      }
+    }
+  dmu[t] += am;
+  if (mode == 1 && dls != nullptr) dls[t] += al;
+}
+
+extern "C" int tmx_latent_noise_fwd(tmx_handle_t h, int mode, const float* mu, const float* ls, const float* eps,
+                                    float* out, int N, int C, int sh, int sw, int eh, int ew, int H, int W, int reverse,
+                                    tmx_stream_t s) {
+  TMX_REQUIRE(h && mu && eps && out && (mode == 2 || ls), TMX_ERR_ARG, "tmx_latent_noise_fwd: NULL argument");
+  TMX_REQUIRE((mode == 1 || mode == 2) && N > 0 && C > 0 && sh > 0 && sw > 0 && eh > 0 && ew > 0 && H % sh == 0 &&
+                  W % sw == 0 && H % eh == 0 && W % ew == 0 && (mode == 1 || (eh == H && ew == W)),
+              TMX_ERR_SHAPE, "tmx_latent_noise_fwd: bad shape / mode");
+  const long long total = (long long)N * C * H * W;
+  latent_noise_fwd_kernel<<<tmx_ceil_div(total, 256), 256, 0, (cudaStream_t)s>>>(mu, ls, eps, out, total, N, C, sh, sw, eh,
+                                                                                 ew, H, W, mode, reverse);
+  TMX_LAUNCHED(h, "latent_noise_fwd_kernel");
+  return TMX_OK;
+}
+
+extern "C" int tmx_latent_noise_bwd(tmx_handle_t h, int mode, const float* g, const float* ls, const float* eps,
+                                    float* dmu, float* dls, int N, int C, int sh, int sw, int eh, int ew, int H, int W,
+                                    int reverse, tmx_stream_t s) {
+  TMX_REQUIRE(h && g && eps && dmu && (mode == 2 || (ls && dls)), TMX_ERR_ARG, "tmx_latent_noise_bwd: NULL argument");
+  TMX_REQUIRE((mode == 1 || mode == 2) && N > 0 && C > 0 && sh > 0 && sw > 0 && eh > 0 && ew > 0 && H % sh == 0 &&
+                  W % sw == 0 && H % eh == 0 && W % ew == 0 && (mode == 1 || (eh == H && ew == W)),
+              TMX_ERR_SHAPE, "tmx_latent_noise_bwd: bad shape / mode");
+  const long long total = (long long)N * C * sh * sw;
+  latent_noise_bwd_kernel<<<tmx_ceil_div(total, 256), 256, 0, (cudaStream_t)s>>>(g, ls, eps, dmu, dls, total, N, C, sh, sw,
+                                                                                 eh, ew, H, W, mode, reverse);
+  TMX_LAUNCHED(h, "latent_noise_bwd_kernel");
+  return TMX_OK;
+}
+
 // tf.tile of a [N][C][1][1] code over the canvas (loss.py:176): adjoint = sum over the canvas, one block per (n, c).
 // out[row] (+)= scale * sum_i in[row][i]
 __global__ void __launch_bounds__(256) row_sum_kernel(const float* __restrict__ in, float* __restrict__ out, int len,

@@ -219,20 +219,75 @@ def _win(rt, x, win):
     return x if win is None else rt.window(x, win)
 
 
-def fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, ih_f, iw_f, win, blend=None):
-    """The latent canvases G_fcn decodes (loss.py:176-186 interpolation; :218-239 blend when `blend` =
-    (ih_b, iw_b, t)), restricted to `win`."""
+ZG_MODES = ('hard', 'variational')
+ZL_MODES = ('permutational', 'hard', 'variational', 'random')
+
+
+def interp_modes(zg='hard', zl='permutational', noise=None):
+    """zg_interp_variational / zl_interp_variational of loss.py:105-259, 351-521 (config.py:61-62: 'hard' /
+    'permutational').  `noise`: the graph's tf.random_normal draws made explicit, standard-normal device tensors -
+    'zg_f' [N,C,1,1] (zg 'variational'), 'zl_f' [N,C,H,W] (zl 'variational' | 'random': the draws of the
+    non-corner tiles at their canvas positions), and 'zg_b' / 'zl_b' for the reversed branch of the blend."""
+    if zg not in ZG_MODES or zl not in ZL_MODES:
+        raise ValueError('interpolation modes: zg in %r, zl in %r (got %r, %r)' % (ZG_MODES, ZL_MODES, zg, zl))
+    return dict(zg=zg, zl=zl, noise=dict(noise or {}))
+
+
+def _noise(rt, mode, mu, ls, eps, H, W, reverse):
+    n, c, sh, sw = mu.shape
+    eh, ew = eps.shape[2:]
+    out = rt.empty(n, c, H, W)
+    _lib.check(rt.lib.tmx_latent_noise_fwd(rt.handle, mode, _ptr(mu.contiguous()), _ptr(None if ls is None else
+                                                                                         ls.contiguous()),
+                                           _ptr(eps.contiguous()), _ptr(out), n, c, sh, sw, eh, ew, H, W, int(reverse),
+                                           rt.stream()), 'tmx_latent_noise_fwd')
+    return out
+
+
+def _noise_bwd(rt, mode, g, ls, eps, dmu, dls, reverse):
+    n, c, sh, sw = dmu.shape
+    eh, ew = eps.shape[2:]
+    H, W = g.shape[2:]
+    _lib.check(rt.lib.tmx_latent_noise_bwd(rt.handle, mode, _ptr(g.contiguous()), _ptr(None if ls is None else
+                                                                                       ls.contiguous()),
+                                           _ptr(eps.contiguous()), _ptr(dmu), _ptr(dls), n, c, sh, sw, eh, ew, H, W,
+                                           int(reverse), rt.stream()), 'tmx_latent_noise_bwd')
+
+
+def _zg_canvas(rt, zg_mu, zg_ls, wh, ww, modes, which, reverse):
+    """The global-code canvas (window-sized: a 1x1 code tiles any extent) of the forward ('f') / reversed ('b') branch."""
+    if modes is None or modes['zg'] == 'hard':                            # loss.py:176, 218
+        return rt.latent_blend([zg_mu.contiguous()], wh, ww, _lib.BLEND_COPY, src_reverse=int(reverse))
+    return _noise(rt, 1, zg_mu, zg_ls, modes['noise']['zg_' + which], wh, ww, reverse)      # loss.py:178-180, 220-222
+
+
+def _zl_canvas(rt, zl_mu, zl_ls, H, W, pins, ih, iw, win, modes, which, reverse):
+    mode = 'permutational' if modes is None else modes['zl']
+    if mode == 'permutational':                                           # loss.py:194, 236
+        full = rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[ih], idx_w=[iw], pin_rows=pins[0],
+                               pin_cols=pins[1], src_reverse=int(reverse))
+    elif mode == 'hard':                                                  # tf.tile, loss.py:182, 224
+        n = zl_mu.shape[0]
+        ident = lambda L: torch.arange(L, dtype=torch.int32, device=rt.device).repeat(n, 1).contiguous()   # noqa: E731
+        full = rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[ident(H)], idx_w=[ident(W)],
+                               src_reverse=int(reverse))
+    else:                                                                 # loss.py:183-193, 225-235
+        full = _noise(rt, 1 if mode == 'variational' else 2, zl_mu, zl_ls, modes['noise']['zl_' + which], H, W, reverse)
+    return _win(rt, full, win)
+
+
+def fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, ih_f, iw_f, win, blend=None, modes=None, zg_ls=None, zl_ls=None):
+    """The latent canvases G_fcn decodes (loss.py:176-194 interpolation; :218-239 blend when `blend` =
+    (ih_b, iw_b, t)), restricted to `win`; `modes` = interp_modes(...) for the config-off variants."""
     wh, ww = (H, W) if win is None else win[2:]
-    zg_c = _tile_code(rt, zg_mu, wh, ww)
-    zl_c = _win(rt, rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[ih_f], idx_w=[iw_f],
-                                    pin_rows=pins[0], pin_cols=pins[1]), win)
+    zg_c = _zg_canvas(rt, zg_mu, zg_ls, wh, ww, modes, 'f', False)
+    zl_c = _zl_canvas(rt, zl_mu, zl_ls, H, W, pins, ih_f, iw_f, win, modes, 'f', False)
     if blend is None:
         return zg_c, zl_c
     ih_b, iw_b, t = blend
     # tf.reverse(axis=[0]) of the sources is folded into the gather (src_reverse)
-    zg_r = rt.latent_blend([zg_mu.contiguous()], wh, ww, _lib.BLEND_COPY, src_reverse=1)
-    zl_r = _win(rt, rt.latent_blend([zl_mu.contiguous()], H, W, _lib.BLEND_COPY, idx_h=[ih_b], idx_w=[iw_b],
-                                    pin_rows=pins[0], pin_cols=pins[1], src_reverse=1), win)
+    zg_r = _zg_canvas(rt, zg_mu, zg_ls, wh, ww, modes, 'b', True)
+    zl_r = _zl_canvas(rt, zl_mu, zl_ls, H, W, pins, ih_b, iw_b, win, modes, 'b', True)
     bzg = rt.latent_blend([zg_r, zg_c], wh, ww, _lib.BLEND_LERP, t=t)      # lerp(reverse, forward, t), loss.py:238
     bzl = rt.latent_blend([zl_r, zl_c], wh, ww, _lib.BLEND_LERP, t=t)
     return bzg, bzl
@@ -265,13 +320,15 @@ class EGForward:
     phase's)."""
 
     def __init__(self, E_zg, E_zl, G, G_fcn, reals, idx, mixing_factors, scale_h=3, scale_w=3, need_interp=True,
-                 need_blend=True, crop_interp=None, crop_blend=None, defer_canvases=False, plans=None, record=True):
+                 need_blend=True, crop_interp=None, crop_blend=None, defer_canvases=False, plans=None, record=True,
+                 modes=None):
         """crop_interp / crop_blend: the (y, x) offsets the E/G loss will crop at; when given, G_fcn decodes only the
         latent window those crops depend on (`crop_window`) - same crop pixels, same gradients, 44 % of the work at
         the reference's 3x3 canvases.  None decodes the whole canvas.  `plans` = {'interp' | 'blend': plan_crop(...)}
         supplies the windows ready-made (the trainer's: their offsets live in device memory)."""
         rt = self.rt = Runtime.get(reals.device)
         self.nets = (E_zg, E_zl, G, G_fcn)
+        self.modes = modes               # interp_modes(...) or None = the reference config ('hard', 'permutational')
         self.reals, self.scale = reals, (scale_h, scale_w)
         self.n = reals.shape[0]
         res = reals.shape[2]
@@ -317,13 +374,15 @@ class EGForward:
         zg_mu, zl_mu, H, W, pins, lat = self.zg_mu, self.zl_mu, self.H, self.W, self.pins, self.lat
         need_interp, need_blend = self._need
         if need_interp and self.interp is None:
-            zg_c, zl_c = fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, self.ih_f, self.iw_f, self.win['interp'])
+            zg_c, zl_c = fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, self.ih_f, self.iw_f, self.win['interp'],
+                                      modes=self.modes, zg_ls=self.zg_ls, zl_ls=self.zl_ls)
             self.interp = G_fcn.get_output_for(zg_c, zl_c, tape=self.t_int, mid_window=self.mid['interp'],
                                                tail_window=self.tail['interp'], **fcn_scale(zl_c, lat))
             _sink('G_interp', G_fcn, self.t_int)
         if need_blend and self.blend is None:
             bzg, bzl = fcn_canvases(rt, zg_mu, zl_mu, H, W, pins, self.ih_f, self.iw_f, self.win['blend'],
-                                    blend=(self.ih_b, self.iw_b, self.t))
+                                    blend=(self.ih_b, self.iw_b, self.t), modes=self.modes, zg_ls=self.zg_ls,
+                                    zl_ls=self.zl_ls)
             self.blend = G_fcn.get_output_for(bzg, bzl, tape=self.t_bl, mid_window=self.mid['blend'],
                                               tail_window=self.tail['blend'], **fcn_scale(bzl, lat))
             _sink('G_blend', G_fcn, self.t_bl)
@@ -349,7 +408,7 @@ class EGForward:
         return self.rt.window(img, self.image_window(which, yx))
 
 
-def fcn_fake(G_fcn, fwd, which, yx, mix=None, crop_aware=True, plan=None):
+def fcn_fake(G_fcn, fwd, which, yx, mix=None, crop_aware=True, plan=None, modes=None):
     """Fake images of the canvas critics (no tape): the crop at `yx` of G_fcn's image of the interpolated (`which` =
     'interp', loss.py:391-395) or blended ('blend', loss.py:466-495) canvas built from the codes of `fwd`, decoding
     only the latent window the crop depends on (`crop_window`).  D_blend_wgangp draws its own mixing factors
@@ -360,7 +419,8 @@ def fcn_fake(G_fcn, fwd, which, yx, mix=None, crop_aware=True, plan=None):
     if plan is None:
         plan = plan_crop(yx, res, fwd.lat, fwd.H, fwd.W, crop_aware=crop_aware, lod=G_fcn.lod)
     blend = None if which == 'interp' else (fwd.ih_b, fwd.iw_b, mix.reshape(-1).contiguous())
-    zg_c, zl_c = fcn_canvases(rt, fwd.zg_mu, fwd.zl_mu, fwd.H, fwd.W, fwd.pins, fwd.ih_f, fwd.iw_f, plan['win'], blend)
+    zg_c, zl_c = fcn_canvases(rt, fwd.zg_mu, fwd.zl_mu, fwd.H, fwd.W, fwd.pins, fwd.ih_f, fwd.iw_f, plan['win'], blend,
+                              modes=modes if modes is not None else fwd.modes, zg_ls=fwd.zg_ls, zl_ls=fwd.zl_ls)
     img = G_fcn.get_output_for(zg_c, zl_c, mid_window=plan['mid'], tail_window=plan['tail'],
                                **fcn_scale(zl_c, fwd.lat))
     return rt.window(img, plan['img'])
@@ -377,6 +437,39 @@ def critic_input_gradient(D, images, weight):
     term = _row_sum(rt, s, 1, n, scale=-weight / n)
     (d,) = backward(D, tape, [torch.full_like(s, -weight / n)], None, param_grads=False)
     return term, d
+
+
+def _zg_canvas_bwd(rt, fwd, d, dzg, lsg, which, reverse):
+    """Adjoint of `_zg_canvas`: d [N,C,wh,ww] -> dzg [N*C] (+ lsg['zg'] for the 'variational' mode)."""
+    n, c = fwd.n, fwd.c
+    wh, ww = d.shape[2:]
+    modes = fwd.modes
+    if modes is None or modes['zg'] == 'hard':
+        if not reverse:
+            _row_sum(rt, d, n * c, wh * ww, out=dzg, accumulate=True)
+        else:
+            tmp = _row_sum(rt, d, n * c, wh * ww).view(n, c, 1, 1)
+            _gather_bwd(rt, tmp, dzg.view(n, c, 1, 1), None, None, (0, 0), reverse=True)
+        return
+    if 'zg' not in lsg:
+        lsg['zg'] = torch.zeros_like(fwd.zg_ls)
+    _noise_bwd(rt, 1, d, fwd.zg_ls, modes['noise']['zg_' + which], dzg.view(n, c, 1, 1), lsg['zg'], reverse)
+
+
+def _zl_canvas_bwd(rt, fwd, d, win, dzl, lsg, ih, iw, which, reverse):
+    """Adjoint of `_zl_canvas`: d = gradient w.r.t. the window `win` of the canvas -> dzl (+ lsg['zl'])."""
+    H, W, pins = fwd.H, fwd.W, fwd.pins
+    mode = 'permutational' if fwd.modes is None else fwd.modes['zl']
+    if mode == 'permutational':
+        _gather_bwd_win(rt, d, win, H, W, dzl, ih, iw, pins, reverse=reverse)
+    elif mode == 'hard':
+        _gather_bwd_win(rt, d, win, H, W, dzl, None, None, (0, 0), reverse=reverse)
+    else:
+        g = d if win is None else rt.window_embed(d, win, H, W)
+        if mode == 'variational' and 'zl' not in lsg:
+            lsg['zl'] = torch.zeros_like(fwd.zl_ls)
+        _noise_bwd(rt, 1 if mode == 'variational' else 2, g, fwd.zl_ls, fwd.modes['noise']['zl_' + which], dzl,
+                   lsg.get('zl'), reverse)
 
 
 def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, rec_G_weight=1.0, pixel_weight=200.0,
@@ -416,6 +509,7 @@ def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, r
     dzg_tiled, dzl = backward(G, fwd.t_rec, [d_rec_img], grads['G'])
     dzg = _row_sum(rt, dzg_tiled, n * c, lat * lat)                      # adjoint of the 32x32 tile of zg
     dzl = dzl.contiguous()
+    lsg = {}                             # gradients w.r.t. the encoders' log_sigma outputs ('variational' modes only)
     if interp_G_weight > 0:
         report['interp_G'], dcr = cg['interp'] if 'interp' in cg else \
             critic_input_gradient(D_interp, fwd.crop('interp', crop_interp), interp_G_weight)
@@ -425,8 +519,8 @@ def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, r
             dcr = _add(rt, dcr, dg)
         dzg_c, dzl_c = backward(G_fcn, fwd.t_int, [_crop_adjoint(rt, dcr, fwd.interp.shape[2:],
                                                                  fwd.image_window('interp', crop_interp))], grads['G'])
-        _row_sum(rt, dzg_c, n * c, dzg_c.shape[2] * dzg_c.shape[3], out=dzg, accumulate=True)
-        _gather_bwd_win(rt, dzl_c, fwd.win['interp'], H, W, dzl, fwd.ih_f, fwd.iw_f, pins)
+        _zg_canvas_bwd(rt, fwd, dzg_c, dzg, lsg, 'f', False)
+        _zl_canvas_bwd(rt, fwd, dzl_c, fwd.win['interp'], dzl, lsg, fwd.ih_f, fwd.iw_f, 'f', False)
     if blend_interp_G_weight > 0:
         t = fwd.t
         report['blend_G'], dcr = cg['blend'] if 'blend' in cg else \
@@ -449,17 +543,18 @@ def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, r
             d_fwd = rt.latent_blend([zero_c, d.contiguous()], wh, ww, _lib.BLEND_LERP, t=t)
             d_rev = rt.latent_blend([d.contiguous(), zero_c], wh, ww, _lib.BLEND_LERP, t=t)
             if dsrc_kind == 'zg':
-                _row_sum(rt, d_fwd, n * c, wh * ww, out=dzg, accumulate=True)
-                tmp = _row_sum(rt, d_rev, n * c, wh * ww).view(n, c, 1, 1)
-                _gather_bwd(rt, tmp, dzg.view(n, c, 1, 1), None, None, (0, 0), reverse=True)
+                _zg_canvas_bwd(rt, fwd, d_fwd, dzg, lsg, 'f', False)
+                _zg_canvas_bwd(rt, fwd, d_rev, dzg, lsg, 'b', True)
             else:
-                _gather_bwd_win(rt, d_fwd, win, H, W, dzl, fwd.ih_f, fwd.iw_f, pins)
-                _gather_bwd_win(rt, d_rev, win, H, W, dzl, fwd.ih_b, fwd.iw_b, pins, reverse=True)
-    dzl_ls = dzg_ls = None
+                _zl_canvas_bwd(rt, fwd, d_fwd, win, dzl, lsg, fwd.ih_f, fwd.iw_f, 'f', False)
+                _zl_canvas_bwd(rt, fwd, d_rev, win, dzl, lsg, fwd.ih_b, fwd.iw_b, 'b', True)
+    dzg_ls, dzl_ls = lsg.get('zg'), lsg.get('zl')       # d loss / d log_sigma from the 'variational' canvases, if any
     dzg = dzg.view(n, c, 1, 1)
     if kl_weight > 0:                                                     # loss.py:163-171
-        (report['KL_zg'], dzg, dzg_ls) = _kl(rt, fwd.zg_mu, fwd.zg_ls, dzg, kl_weight, 'KL_zg')
-        (report['KL_zl'], dzl, dzl_ls) = _kl(rt, fwd.zl_mu, fwd.zl_ls, dzl, kl_weight, 'KL_zl')
+        (report['KL_zg'], dzg, kg) = _kl(rt, fwd.zg_mu, fwd.zg_ls, dzg, kl_weight, 'KL_zg')
+        (report['KL_zl'], dzl, kl_) = _kl(rt, fwd.zl_mu, fwd.zl_ls, dzl, kl_weight, 'KL_zl')
+        dzg_ls = kg if dzg_ls is None else _add(rt, dzg_ls, kg)
+        dzl_ls = kl_ if dzl_ls is None else _add(rt, dzl_ls, kl_)
     backward(E_zl, fwd.t_zl, [dzl, dzl_ls], grads['E_zl'], want_input_grads=False)
     backward(E_zg, fwd.t_zg, [dzg, dzg_ls], grads['E_zg'], want_input_grads=False)
     return report
@@ -478,14 +573,16 @@ def _kl(rt, mu, ls, dmu_in, kl_weight, name):
 
 def EG_wgan(E_zg, E_zl, G, D_rec, G_fcn, D_interp, D_blend, reals, idx, crop_interp, crop_blend, mixing_factors,
             grads, scale_h=3, scale_w=3, rec_G_weight=1.0, pixel_weight=200.0, interp_G_weight=1.0,
-            blend_interp_G_weight=1.0, crop_aware=True, kl_weight=0.0, gram=None, gram_weight=0.0, gram_alpha=None):
+            blend_interp_G_weight=1.0, crop_aware=True, kl_weight=0.0, gram=None, gram_weight=0.0, gram_alpha=None,
+            modes=None):
     """One evaluation + differentiation of mean(EG_loss) (loss.py:105-259, run.py:321).
     reals: [N,3,R,R] fp32 device tensor in [-1,1]; idx: dict of int32 index vectors (interp.sample_schedule_indices);
     crop_*: (y, x); mixing_factors: [N,1,1,1] fp32 device tensor; grads: {'E_zg','E_zl','G'} -> flat gradient
     buffers (accumulated into).  Returns a dict of per-term batch means (device scalars)."""
     fwd = EGForward(E_zg, E_zl, G, G_fcn, reals, idx, mixing_factors, scale_h, scale_w,
                     need_interp=interp_G_weight > 0, need_blend=blend_interp_G_weight > 0,
-                    crop_interp=crop_interp if crop_aware else None, crop_blend=crop_blend if crop_aware else None)
+                    crop_interp=crop_interp if crop_aware else None, crop_blend=crop_blend if crop_aware else None,
+                    modes=modes)
     return EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, rec_G_weight, pixel_weight,
                        interp_G_weight, blend_interp_G_weight, kl_weight=kl_weight, gram=gram, gram_weight=gram_weight,
                        gram_alpha=gram_alpha)

@@ -49,6 +49,7 @@ def default_config(train_size=128, fmap_base=1024, fmap_max=512, latent_channels
         crop_aware=True,      # G_fcn decodes only the latent window each random_crop depends on (loss.crop_window)
         loss=dict(rec_G_weight=1.0, pixel_weight=200.0, interp_G_weight=1.0, blend_interp_G_weight=1.0),
         levels=int(np.log2(latent_res)),
+        zg_interp_variational='hard', zl_interp_variational='permutational',      # config.py:61-62 (loss.interp_modes)
         block_size=0, perm=False,                              # config.py:69-70: the permutation sampler's variants
         lr_mirror_augment=False, ud_mirror_augment=False)      # config.py:96 (Trainer.step_from_dataset)
 
@@ -295,7 +296,30 @@ class Trainer:
         out = dict(idx=idx, crops=crops, host_plans=plans, _packed=packed, _mixes=mixes)
         out.update(crops)
         out.update(self._draw_views(idx, plans, packed, mixes))
+        if self._custom_modes():
+            # the tf.random_normal draws of the config-off interpolation modes (loss.py:178,185,187-190, ...): one set
+            # per loss graph that samples (D_interp_wgangp, D_blend_wgangp, EG_wgan), forward and reversed branch each
+            C = c['E_zl']['latent_channels']
+            for phase in ('d_interp', 'd_blend', 'eg'):
+                noise = {}
+                for which in ('f', 'b'):
+                    if c['zg_interp_variational'] == 'variational':
+                        noise['zg_' + which] = rng.standard_normal((minibatch, C, 1, 1)).astype(np.float32)
+                    if c['zl_interp_variational'] in ('variational', 'random'):
+                        noise['zl_' + which] = rng.standard_normal((minibatch, C, H, W)).astype(np.float32)
+                out[phase + '_noise'] = {k: torch.from_numpy(v).to(self.rt.device) for k, v in noise.items()}
         return out
+
+    def _custom_modes(self):
+        c = self.cfg
+        return (c.get('zg_interp_variational', 'hard'), c.get('zl_interp_variational', 'permutational')) != \
+            ('hard', 'permutational')
+
+    def _modes(self, draws, phase):
+        if not self._custom_modes():
+            return None
+        c = self.cfg
+        return loss.interp_modes(c['zg_interp_variational'], c['zl_interp_variational'], draws.get(phase + '_noise'))
 
     @staticmethod
     def _draw_views(idx, plans, packed, mixes):
@@ -313,8 +337,9 @@ class Trainer:
         return out
 
     # ------------------------------------------------------------------ fake images of the canvas critics (no tape)
-    def _fcn_fake(self, fwd, which, yx, mix=None, plan=None):
-        return loss.fcn_fake(self.G_fcn, fwd, which, yx, mix, crop_aware=self.cfg.get('crop_aware', True), plan=plan)
+    def _fcn_fake(self, fwd, which, yx, mix=None, plan=None, modes=None):
+        return loss.fcn_fake(self.G_fcn, fwd, which, yx, mix, crop_aware=self.cfg.get('crop_aware', True), plan=plan,
+                             modes=modes)
 
     def _critic(self, name, n):
         key = (name, n, self.nets[name].lod)
@@ -396,8 +421,9 @@ class Trainer:
             d_fade, d_orig = reals_d, (reals_d if reals_d_orig is None else reals_d_orig)
         mode = c.get('cuda_graphs', True)
         mode = 'step' if mode is True else mode
-        if os.environ.get('TMX_NO_GRAPH') or lod_now != int(lod_now):
-            mode = None      # (a fractional lod changes every step and is baked into the launches)
+        if os.environ.get('TMX_NO_GRAPH') or lod_now != int(lod_now) or self._custom_modes():
+            mode = None      # (a fractional lod changes every step and is baked into the launches; the config-off
+            #                   interpolation modes bring per-step noise tensors that have no static graph buffers)
         if os.environ.get('TMX_GRAPH_MODE'):
             mode = os.environ['TMX_GRAPH_MODE']
         if mode == 'step' and 'plans' in draws:
@@ -452,7 +478,8 @@ class Trainer:
         def eg_forward():
             return loss.EGForward(nets['E_zg'], nets['E_zl'], nets['G'], self.G_fcn, reals_orig, idx, draws['eg_mix'],
                                   c['scale_h'], c['scale_w'], defer_canvases=True,
-                                  plans={'interp': plans['eg_crop_interp'], 'blend': plans['eg_crop_blend']})
+                                  plans={'interp': plans['eg_crop_interp'], 'blend': plans['eg_crop_blend']},
+                                  modes=self._modes(draws, 'eg'))
         fwd = None
         if 'D' in phases:
             if shared:
@@ -462,10 +489,11 @@ class Trainer:
                                        c['scale_h'], c['scale_w'], defer_canvases=True, record=False,
                                        plans={'interp': plans['d_interp_crop'], 'blend': plans['d_blend_crop']})
             fakes = (('D_rec', fwd_d.rec, 'd_rec_gp'),
-                     ('D_interp', self._fcn_fake(fwd_d, 'interp', draws['d_interp_crop'], plan=plans['d_interp_crop']),
-                      'd_interp_gp'),
+                     ('D_interp', self._fcn_fake(fwd_d, 'interp', draws['d_interp_crop'], plan=plans['d_interp_crop'],
+                                                 modes=self._modes(draws, 'd_interp')), 'd_interp_gp'),
                      ('D_blend', self._fcn_fake(fwd_d, 'blend', draws['d_blend_crop'], draws['d_blend_mix'],
-                                                plan=plans['d_blend_crop']), 'd_blend_gp'))
+                                                plan=plans['d_blend_crop'], modes=self._modes(draws, 'd_blend')),
+                      'd_blend_gp'))
             if critic_graphs:
                 self.buckets['D'].marks.zero_()      # (each critic graph zeroes its own gradient view)
             else:
