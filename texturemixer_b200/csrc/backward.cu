@@ -19,6 +19,7 @@ struct GradPrepParams {
   int C8;          // channel groups of 8
   int ppb;         // pixel lanes per block
   int rpb;         // grid rows (n, r) per block
+  int c8_shift;    // log2(C8) when C8 is a power of two (every layer of the path but the 513 -> 576 padded one), else -1
 };
 
 __device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
@@ -48,13 +49,38 @@ __global__ void __launch_bounds__(256, 4) grad_prepare_kernel(const GradPrepPara
   const float* __restrict__ gsrc = P.io.g;
   const float* __restrict__ addp = P.io.add;
   float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < units; u += ustride) {
-    const int row = u / units_per_row;
-    const int cq = (u - row * units_per_row) / C8;
-    const int n = row / Hq;
-    const int r = row - n * Hq - 2;
+  // index walk without divisions: u advances by the constant ustride = d_row rows + d_rem units, a row by row/Hq
+  const int u0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int d_row = ustride / units_per_row, d_rem = ustride - d_row * units_per_row;
+  int row = u0 / units_per_row, rem = u0 - row * units_per_row;
+  const int d_n = d_row / Hq, d_rr = d_row - d_n * Hq;
+  int n = row / Hq, rr = row - n * Hq;
+  for (int u = u0; u < units; u += ustride) {
+    const int cq = P.c8_shift >= 0 ? (rem >> P.c8_shift) : rem / C8;
+    const int r = rr - 2;
     const int c = cq - 2;
     const bool interior = r >= 0 && r < H && c >= 0 && c < W;
+    const int row_now = row, n_now = n;
+    // advance to the next unit of this thread
+    rem += d_rem;
+    row += d_row;
+    rr += d_rr;
+    n += d_n;
+    if (rem >= units_per_row) {
+      rem -= units_per_row;
+      ++row;
+      ++rr;
+    }
+    if (rr >= Hq) {
+      rr -= Hq;
+      ++n;
+    }
+    if (rr >= Hq) {          // (d_rr + carry can pass Hq twice only when d_rr == Hq - 1 and both carries hit)
+      rr -= Hq;
+      ++n;
+    }
+    {
+    const int row = row_now, n = n_now;       // (shadow the walkers: the body below works on the CURRENT unit)
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (interior) {
       const long long in_pix = ((long long)n * H + r) * W + c;                 // NHWC pixel index
@@ -104,10 +130,9 @@ __global__ void __launch_bounds__(256, 4) grad_prepare_kernel(const GradPrepPara
             reinterpret_cast<const uint16_t*>(P.io.y_mask) + (((long long)n * (H + 2) + r + 1) * (W + 2) + c + 1) * C + co));
         const uint32_t w4[4] = {yb.x, yb.y, yb.z, yb.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t hb = (w4[j >> 1] >> ((j & 1) * 16)) & 0xffffu;     // bf16 bits of hi(y)
-          const bool pos_y = hb != 0u && (hb & 0x8000u) == 0u;
-          v[j] *= pos_y ? 1.f : d.alpha;
+        for (int j = 0; j < 4; ++j) {      // y > 0  <=>  the bf16 word, moved to the top half, is a positive int32
+          v[2 * j] *= ((int)(w4[j] << 16) > 0) ? 1.f : d.alpha;
+          v[2 * j + 1] *= ((int)(w4[j] & 0xffff0000u) > 0) ? 1.f : d.alpha;
         }
       }
 #pragma unroll
@@ -122,11 +147,7 @@ __global__ void __launch_bounds__(256, 4) grad_prepare_kernel(const GradPrepPara
       uint32_t ph[4], pl[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        uint32_t h0, l0, h1, l1;
-        tmx_split_bf16(v[2 * j], h0, l0);
-        tmx_split_bf16(v[2 * j + 1], h1, l1);
-        ph[j] = h0 | (h1 << 16);
-        pl[j] = l0 | (l1 << 16);
+        tmx_split_bf16x2(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
       }
       long long o;
       if (!d.phase_pack) {
@@ -141,6 +162,7 @@ __global__ void __launch_bounds__(256, 4) grad_prepare_kernel(const GradPrepPara
       }
       *reinterpret_cast<uint4*>(P.io.dz_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
       *reinterpret_cast<uint4*>(P.io.dz_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
     }
   }
   if (P.io.dbias != nullptr) {
@@ -188,6 +210,9 @@ extern "C" int tmx_grad_prepare(tmx_handle_t h, const tmx_grad_desc_t* d, const 
   long long blocks = (units + threads - 1) / threads;
   if (blocks > 4LL * h->sm_count) blocks = 4LL * h->sm_count;
   P.rpb = 0;
+  P.c8_shift = -1;
+  for (int b = 0; b < 12; ++b)
+    if ((1 << b) == P.C8) P.c8_shift = b;
   const size_t smem = io->dbias ? (size_t)threads * 8 * sizeof(float) : 0;
   TMX_REQUIRE(threads <= 256 && smem <= 48 * 1024, TMX_ERR_SHAPE, "tmx_grad_prepare: C=%d not supported", d->C);
   grad_prepare_kernel<<<(unsigned)blocks, threads, smem, (cudaStream_t)s>>>(P);

@@ -495,11 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             uint32_t ph[GW / 2], pl[GW / 2];
 #pragma unroll
             for (int j = 0; j < GW / 2; ++j) {
-              uint32_t h0, l0, h1, l1;
-              tmx_split_bf16(v[2 * j], h0, l0);
-              tmx_split_bf16(v[2 * j + 1], h1, l1);
-              ph[j] = h0 | (h1 << 16);
-              pl[j] = l0 | (l1 << 16);
+              tmx_split_bf16x2(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
             }
             auto store_px = [&](int prow, int pcol, bool halo = true) {
               const long long o = (((long long)n * Hp + prow) * Wp + pcol) * CL + cbase;

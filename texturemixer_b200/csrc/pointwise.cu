@@ -237,11 +237,7 @@ __global__ void __launch_bounds__(256) split_halo_pack_kernel(const float* __res
   uint32_t ph[4], pl[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    uint32_t h0, l0, h1, l1;
-    tmx_split_bf16(v[2 * i], h0, l0);
-    tmx_split_bf16(v[2 * i + 1], h1, l1);
-    ph[i] = h0 | (h1 << 16);
-    pl[i] = l0 | (l1 << 16);
+    tmx_split_bf16x2(v[2 * i], v[2 * i + 1], ph[i], pl[i]);
   }
   reinterpret_cast<uint4*>(hi)[t] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
   reinterpret_cast<uint4*>(lo)[t] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
