@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(256) dense_partial_kernel(const float* __restr
 // Fast path (Cout % 128 == 0, K % 128 == 0: the 8192 -> 512 head): the weight matrix is streamed ONCE with 128-bit
 // loads.  Block = (128 outputs, 128-long k-slice, 32 samples); lane tx owns 4 consecutive outputs, warp ty owns
 // samples ty*4 .. ty*4+3; x of the slice sits in shared memory (broadcast reads).  Same partial layout as above.
-constexpr int kDenseKS4 = 128;
+constexpr int kDenseKS4 = 64;    // short slices + 16 weight rows in flight per thread: the k loop is a chain of DRAM round trips
 __global__ void __launch_bounds__(256) dense_partial4_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              float* __restrict__ part, int N, int K, int Cout) {
   __shared__ float xs[kDenseNT][kDenseKS4 + 4];
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(256) dense_partial4_kernel(const float* __rest
   for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float4* wp = reinterpret_cast<const float4*>(w + (long long)k0 * Cout + o);
   const long long wstride = Cout / 4;
-#pragma unroll 8
+#pragma unroll 16
   for (int k = 0; k < kDenseKS4; ++k) {
     const float4 wv = __ldg(wp + k * wstride);
 #pragma unroll
@@ -778,7 +778,7 @@ extern "C" int tmx_convert_output(tmx_handle_t h, const float* x, void* y, int64
               "tmx_convert_output: bad shape planes=%lld H=%d W=%d shrink=%d", (long long)planes, H, W, shrink);
   TMX_REQUIRE(out_kind >= 0 && out_kind <= 2, TMX_ERR_ARG, "tmx_convert_output: out_kind %d", out_kind);
   const long long total = planes * (H / shrink) * (W / shrink);
-  const int grid = (int)(total / 256 + 1 < 148LL * 16 ? total / 256 + 1 : 148LL * 16);
+  const int grid = (int)(total / 256 + 1 < (long long)h->sm_count * 16 ? total / 256 + 1 : (long long)h->sm_count * 16);
   if (out_kind == 1)
     convert_output_kernel<1><<<grid, 256, 0, (cudaStream_t)s>>>(x, y, total, H, W, shrink, mul, add, 1);
   else
@@ -796,7 +796,7 @@ __global__ void __launch_bounds__(256) tanh_kernel(const float* __restrict__ in,
 
 extern "C" int tmx_tanh_f32(tmx_handle_t h, const float* in, float* out, int64_t n, tmx_stream_t s) {
   TMX_REQUIRE(h && in && out && n > 0, TMX_ERR_ARG, "tmx_tanh_f32: bad argument");
-  const int grid = (int)(n / 256 + 1 < 148LL * 16 ? n / 256 + 1 : 148LL * 16);
+  const int grid = (int)(n / 256 + 1 < (long long)h->sm_count * 16 ? n / 256 + 1 : (long long)h->sm_count * 16);
   tanh_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(in, out, n);
   TMX_LAUNCHED(h, "tanh_kernel");
   return TMX_OK;
@@ -814,7 +814,7 @@ __global__ void __launch_bounds__(256) tanh_bwd_kernel(const float* __restrict__
 
 extern "C" int tmx_tanh_bwd(tmx_handle_t h, const float* dy, const float* y, float* dx, int64_t n, tmx_stream_t s) {
   TMX_REQUIRE(h && dy && y && dx && n > 0, TMX_ERR_ARG, "tmx_tanh_bwd: bad argument");
-  const int grid = (int)(n / 256 + 1 < 148LL * 16 ? n / 256 + 1 : 148LL * 16);
+  const int grid = (int)(n / 256 + 1 < (long long)h->sm_count * 16 ? n / 256 + 1 : (long long)h->sm_count * 16);
   tanh_bwd_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(dy, y, dx, n);
   TMX_LAUNCHED(h, "tanh_bwd_kernel");
   return TMX_OK;
@@ -871,7 +871,7 @@ extern "C" int tmx_pixel_norm_bwd(tmx_handle_t h, const float* x, const float* d
                                   float eps, tmx_stream_t s) {
   TMX_REQUIRE(h && x && dy && dx && npix > 0 && C > 0, TMX_ERR_ARG, "tmx_pixel_norm_bwd: bad argument");
   const long long blocks = (npix + 7) / 8;
-  const int grid = (int)(blocks < 148LL * 16 ? blocks : 148LL * 16);
+  const int grid = (int)(blocks < (long long)h->sm_count * 16 ? blocks : (long long)h->sm_count * 16);
   pixel_norm_bwd_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, dy, dx, npix, C, eps);
   TMX_LAUNCHED(h, "pixel_norm_bwd_kernel");
   return TMX_OK;
@@ -880,7 +880,7 @@ extern "C" int tmx_pixel_norm_bwd(tmx_handle_t h, const float* x, const float* d
 extern "C" int tmx_pixel_norm(tmx_handle_t h, const float* x, float* y, int64_t npix, int C, float eps, tmx_stream_t s) {
   TMX_REQUIRE(h && x && y && npix > 0 && C > 0, TMX_ERR_ARG, "tmx_pixel_norm: bad argument");
   const long long blocks = (npix + 7) / 8;
-  const int grid = (int)(blocks < 148LL * 16 ? blocks : 148LL * 16);
+  const int grid = (int)(blocks < (long long)h->sm_count * 16 ? blocks : (long long)h->sm_count * 16);
   pixel_norm_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, y, npix, C, eps);
   TMX_LAUNCHED(h, "pixel_norm_kernel");
   return TMX_OK;
@@ -925,7 +925,7 @@ extern "C" int tmx_weighted_sum(tmx_handle_t h, const float* const* srcs, const 
   TMX_REQUIRE(K >= 1 && N > 0 && C > 0 && H > 0 && W > 0, TMX_ERR_SHAPE, "tmx_weighted_sum: bad shape K=%d N=%d C=%d %dx%d",
               K, N, C, H, W);
   const long long total = (long long)N * C * H * W;
-  const int grid = (int)(total / 256 + 1 < 148LL * 16 ? total / 256 + 1 : 148LL * 16);
+  const int grid = (int)(total / 256 + 1 < (long long)h->sm_count * 16 ? total / 256 + 1 : (long long)h->sm_count * 16);
   weighted_sum_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(srcs, bcast, weights, out, K, (long long)N * C, H * W, math_f32);
   TMX_LAUNCHED(h, "weighted_sum_kernel");
   return TMX_OK;
@@ -948,7 +948,7 @@ extern "C" int tmx_bias_act(tmx_handle_t h, const float* x, const float* bias, f
                             float alpha, tmx_stream_t s) {
   TMX_REQUIRE(h && x && y && npix > 0 && C > 0, TMX_ERR_ARG, "tmx_bias_act: bad argument");
   const long long total = npix * C;
-  const int grid = (int)(total / 256 + 1 < 148LL * 16 ? total / 256 + 1 : 148LL * 16);
+  const int grid = (int)(total / 256 + 1 < (long long)h->sm_count * 16 ? total / 256 + 1 : (long long)h->sm_count * 16);
   bias_act_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, bias, y, total, C, lrelu, alpha);
   TMX_LAUNCHED(h, "bias_act_kernel");
   return TMX_OK;
