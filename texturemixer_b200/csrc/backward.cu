@@ -36,6 +36,7 @@ __device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
 // divisions of the first version cost as much issue time as the memory traffic took.
 __global__ void __launch_bounds__(256, 4) grad_prepare_kernel(const GradPrepParams P) {
   extern __shared__ float red[];   // [blockDim / C8][C] bias-gradient partials
+  tmx_pdl_trigger();
   const tmx_grad_desc_t& d = P.d;
   const int C8 = P.C8;
   const int cg = threadIdx.x % C8;
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(256, 4) grad_prepare_kernel(const GradPrepPara
   int row = u0 / units_per_row, rem = u0 - row * units_per_row;
   const int d_n = d_row / Hq, d_rr = d_row - d_n * Hq;
   int n = row / Hq, rr = row - n * Hq;
+  tmx_pdl_wait();      // (the index set-up above overlaps the previous kernel's tail)
   for (int u = u0; u < units; u += ustride) {
     const int cq = P.c8_shift >= 0 ? (rem >> P.c8_shift) : rem / C8;
     const int r = rr - 2;
@@ -215,7 +217,7 @@ extern "C" int tmx_grad_prepare(tmx_handle_t h, const tmx_grad_desc_t* d, const 
     if ((1 << b) == P.C8) P.c8_shift = b;
   const size_t smem = io->dbias ? (size_t)threads * 8 * sizeof(float) : 0;
   TMX_REQUIRE(threads <= 256 && smem <= 48 * 1024, TMX_ERR_SHAPE, "tmx_grad_prepare: C=%d not supported", d->C);
-  grad_prepare_kernel<<<(unsigned)blocks, threads, smem, (cudaStream_t)s>>>(P);
+  TMX_CUDA(tmx_launch_pdl(grad_prepare_kernel, dim3((unsigned)blocks), dim3(threads), smem, (cudaStream_t)s, 1, P));
   TMX_LAUNCHED(h, "grad_prepare_kernel");
   return TMX_OK;
 }

@@ -59,6 +59,48 @@ static inline bool tmx_env_flag(const char* name) {
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 
+// Programmatic dependent launch (PDL), OPT-IN with TMX_PDL=1: a kernel launched with tmx_launch_pdl may start while its
+// predecessor on the stream is still running - its CTAs take the SMs the predecessor's CTAs leave, set up their
+// barriers / TMEM / index arithmetic, and block in tmx_pdl_wait() until the predecessor grid has completed and its
+// writes are visible.  Every kernel launched that way calls tmx_pdl_trigger() first (lets ITS successor be scheduled
+// early) and tmx_pdl_wait() before its first global-memory access; both are no-ops in an ordinary launch.
+// Measured on the train step (conv_tc / conv_lin / conv_wgrad / wgrad_reduce / grad_prepare, ~1 700 of the 2 700
+// launches of a step, inside the CUDA graph; all 211 GPU tests pass with it on): 73.9 ms with PDL vs 72.9 ms without
+// (profiles/r02_pdl_ab.txt) - the step runs under the board's power cap (SM clocks ~1 780 of 1 965 MHz), so closing
+// the ~1 us gaps between kernels buys no time.  Hence off by default.
+__device__ __forceinline__ void tmx_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void tmx_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// cudaLaunchKernelEx with an optional cluster width and, with TMX_PDL=1, the programmatic-stream-serialization
+// attribute.  Works under stream capture: the edge to the previous kernel node becomes a programmatic dependency.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t tmx_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                         int cluster_x, Args... args) {
+  static const bool pdl = tmx_env_flag("TMX_PDL");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster_x;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 __device__ __forceinline__ int tmx_reflect(int i, int n) {
   // tf.pad(mode='REFLECT') by one pixel: -1 -> 1, n -> n-2 (networks.py:55)
   i = i < 0 ? -i : i;

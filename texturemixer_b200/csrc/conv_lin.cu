@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int kchunks = p.K / 8;
+  tmx_pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi);
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr_s);
+  tmx_pdl_wait();      // set-up above overlaps the previous kernel's tail; its results are read from here on
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -265,7 +267,8 @@ int launch_lin_patch(tmx_handle_t h, const CUtensorMap* maps, const LinPatchPara
     configured_device = h->device;
   }
   const int grid = p.tiles < h->sm_count ? p.tiles : h->sm_count;
-  kern<<<grid, kLinThreads, smem_bytes, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  TMX_CUDA(tmx_launch_pdl(kern, dim3(grid), dim3(kLinThreads), (size_t)smem_bytes, st, 1, maps[0], maps[1], maps[2],
+                          maps[3], p));
   TMX_LAUNCHED(h, "conv_lin_patch_kernel");
   return TMX_OK;
 }

@@ -164,15 +164,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int cchunks = p.Cin / KC;
-  if (p.y_rgb != nullptr && threadIdx.x >= 128) {
-    for (int e = threadIdx.x - 128; e < (GW + 1) * 4; e += 128) {   // visible after the setup barrier below
-      const int c = e >> 2, o = e & 3;
-      float val = 0.f;
-      if (o < p.rgb_c) val = c < GW ? __ldg(p.rgb_w + c * p.rgb_c + o) : (p.rgb_b ? __ldg(p.rgb_b + o) : 0.f);
-      rgb_smem[e] = val;
-    }
-  }
   const int ksteps = p.taps * cchunks;
+  tmx_pdl_trigger();   // the next kernel of the stream may be scheduled as SMs free up (it blocks in its own wait)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi);
@@ -198,6 +191,17 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 2) {
     if (PAIR) tmem_alloc2<Cfg::kTmemCols>(tmem_ptr_s);
     else tmem_alloc<Cfg::kTmemCols>(tmem_ptr_s);
+  }
+  // everything above touched no global memory: it overlaps the tail of the previous kernel (PDL); from here on the
+  // previous kernel's results are read
+  tmx_pdl_wait();
+  if (p.y_rgb != nullptr && threadIdx.x >= 128) {
+    for (int e = threadIdx.x - 128; e < (GW + 1) * 4; e += 128) {   // visible after the setup barrier below
+      const int c = e >> 2, o = e & 3;
+      float val = 0.f;
+      if (o < p.rgb_c) val = c < GW ? __ldg(p.rgb_w + c * p.rgb_c + o) : (p.rgb_b ? __ldg(p.rgb_b + o) : 0.f);
+      rgb_smem[e] = val;
+    }
   }
   tc_fence_before();
   if (PAIR) cluster_sync_all();   // barrier inits + TMEM allocation visible in both CTAs
@@ -639,19 +643,8 @@ int launch_tc(tmx_handle_t h, const CUtensorMap* maps, const ConvTcParams& p, cu
               h->max_smem_optin);
   const int units = PAIR ? h->sm_count / 2 : h->sm_count;   // CTAs, or CTA pairs
   const int n = p.num_items < units ? p.num_items : units;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(PAIR ? 2 * n : n);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  TMX_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p));
+  TMX_CUDA(tmx_launch_pdl(kern, dim3(PAIR ? 2 * n : n), dim3(kThreads), (size_t)Cfg::kSmemBytes, st, PAIR ? 2 : 1,
+                          maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p));
   TMX_LAUNCHED(h, "conv_tc_kernel");
   return TMX_OK;
 }

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(kWThreads, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  tmx_pdl_trigger();
 
   // work item of this CTA: (split, tap, ci tile, co tile)
   int item = blockIdx.x;
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(kWThreads, 1)
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_s);
+  tmx_pdl_wait();      // set-up above overlaps the previous kernel's tail; its results are read from here on
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -261,6 +263,8 @@ __global__ void __launch_bounds__(kWThreads, 1)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                                            int splits, int taps, int Cin, int cin_pad, int Cout,
                                                            int co_pad, float scale, int overwrite) {
+  tmx_pdl_trigger();
+  tmx_pdl_wait();
   const long long total4 = (long long)taps * Cin * Cout / 4;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total4) return;
@@ -295,6 +299,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_warp_kernel(const float* __r
                                                                 int splits, int taps, int Cin, int cin_pad, int Cout,
                                                                 int co_pad, int xwin, int bpu, float scale,
                                                                 int overwrite) {
+  tmx_pdl_trigger();
+  tmx_pdl_wait();
   const long long total4 = (long long)(PACKED ? 9 : taps) * Cin * Cout / 4;
   const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -346,6 +352,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_warp_kernel(const float* __r
 __global__ void __launch_bounds__(256) wgrad_reduce_packed_kernel(const float* __restrict__ partial,
                                                                   float* __restrict__ dw, int splits, int groups, int Cin,
                                                                   int Cout, int co_pad, int xwin, int bpu, float scale) {
+  tmx_pdl_trigger();
+  tmx_pdl_wait();
   const long long total4 = 9LL * Cin * Cout / 4;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total4) return;
@@ -451,7 +459,8 @@ int launch_wgrad(tmx_handle_t h, const CUtensorMap* maps, const WgradParams& p, 
     configured_device = h->device;
   }
   const int grid = p.splits * p.taps * p.ci_tiles * p.co_tiles;
-  kern<<<grid, kWThreads, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  TMX_CUDA(tmx_launch_pdl(kern, dim3(grid), dim3(kWThreads), (size_t)Cfg::kSmemBytes, st, 1, maps[0], maps[1], maps[2],
+                          maps[3], p));
   TMX_LAUNCHED(h, "conv_wgrad_kernel");
   return TMX_OK;
 }
@@ -497,18 +506,19 @@ extern "C" int tmx_conv2d_wgrad(tmx_handle_t h, int N, int H, int W, int Cin, in
   const long long total4 = (long long)k * k * Cin * Cout / 4;
   // thin layers (few outputs, many pixel slices): slices in parallel, one warp per float4 of outputs
   const bool many = p.splits >= 8 && total4 <= 16384;
+  const float* ws_c = workspace;
   if (p.packed && many)
-    wgrad_reduce_warp_kernel<true><<<tmx_ceil_div(total4 * 32, 256), 256, 0, st>>>(
-        workspace, dw, p.splits, p.taps, Cin, p.ci_tiles * kWM, Cout, p.co_pad, p.xwin, p.bpu, wscale, 0);
+    TMX_CUDA(tmx_launch_pdl(wgrad_reduce_warp_kernel<true>, dim3(tmx_ceil_div(total4 * 32, 256)), dim3(256), 0, st, 1,
+                            ws_c, dw, p.splits, p.taps, Cin, p.ci_tiles * kWM, Cout, p.co_pad, p.xwin, p.bpu, wscale, 0));
   else if (p.packed)
-    wgrad_reduce_packed_kernel<<<tmx_ceil_div(total4, 256), 256, 0, st>>>(workspace, dw, p.splits, p.taps, Cin, Cout,
-                                                                          p.co_pad, p.xwin, p.bpu, wscale);
+    TMX_CUDA(tmx_launch_pdl(wgrad_reduce_packed_kernel, dim3(tmx_ceil_div(total4, 256)), dim3(256), 0, st, 1, ws_c, dw,
+                            p.splits, p.taps, Cin, Cout, p.co_pad, p.xwin, p.bpu, wscale));
   else if (many)
-    wgrad_reduce_warp_kernel<false><<<tmx_ceil_div(total4 * 32, 256), 256, 0, st>>>(
-        workspace, dw, p.splits, p.taps, Cin, p.ci_tiles * kWM, Cout, p.co_pad, 1, 1, wscale, 0);
+    TMX_CUDA(tmx_launch_pdl(wgrad_reduce_warp_kernel<false>, dim3(tmx_ceil_div(total4 * 32, 256)), dim3(256), 0, st, 1,
+                            ws_c, dw, p.splits, p.taps, Cin, p.ci_tiles * kWM, Cout, p.co_pad, 1, 1, wscale, 0));
   else
-    wgrad_reduce_kernel<<<tmx_ceil_div(total4, 256), 256, 0, st>>>(workspace, dw, p.splits, p.taps, Cin,
-                                                                   p.ci_tiles * kWM, Cout, p.co_pad, wscale, 0);
+    TMX_CUDA(tmx_launch_pdl(wgrad_reduce_kernel, dim3(tmx_ceil_div(total4, 256)), dim3(256), 0, st, 1, ws_c, dw, p.splits,
+                            p.taps, Cin, p.ci_tiles * kWM, Cout, p.co_pad, wscale, 0));
   TMX_LAUNCHED(h, "wgrad_reduce_kernel");
   return TMX_OK;
 }
