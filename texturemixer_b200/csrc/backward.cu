@@ -557,10 +557,95 @@ __global__ void __launch_bounds__(256) dense_bwd_input4_kernel(const float* __re
   }
 }
 
+// Streaming path of the 8192 <- 512 head (Cout == 512, K % 64 == 0, N <= 32 per block): dx[n][k] = wscale *
+// sum_o g[n][o] * w[k][o] with g = dy * act'(y).  The kernel above walks the 512 outputs in eight load / barrier /
+// compute rounds with 8 KB of weights in flight per block (35 us for 16.8 MB).  Here g of all 32 samples sits in
+// shared memory (64 KB), a block streams 64 weight rows in two passes of 32 - sixteen threads per row, each holding 8
+// interleaved float4 of it in registers, the second pass already in flight while the first is multiplied - and a
+// row's 32 dot products are finished by four xor-shuffles.
+constexpr int kDbiRows = 64;
+__global__ void __launch_bounds__(512, 1) dense_bwd_input_stream_kernel(const float* __restrict__ dy,
+                                                                       const float* __restrict__ y,
+                                                                       const float* __restrict__ w, float wscale,
+                                                                       float* __restrict__ dx, int N, int K, int lrelu,
+                                                                       float alpha) {
+  // 512 threads = 32 rows x 16 threads per row (the 256-thread version issued 1.0 instructions per cycle: FFMA-issue
+  // bound with eight warps per SM, ncu)
+  extern __shared__ __align__(16) float g_s[];     // [32][512]
+  constexpr int Cout = 512;
+  const int t = threadIdx.x, r = t >> 4, sg = t & 15;
+  const int k0 = blockIdx.x * kDbiRows, n0 = blockIdx.y * 32;
+  const float4* w0 = reinterpret_cast<const float4*>(w + (long long)(k0 + r) * Cout) + sg;
+  const float4* w1 = reinterpret_cast<const float4*>(w + (long long)(k0 + 32 + r) * Cout) + sg;
+  float4 wa[8], wb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) wa[j] = __ldg(w0 + j * 16);           // float4 column j*16 + sg of the row
+  // g = dy * act'(y) of the 32 samples: 8 float4 per thread, all loads in flight together (not a chain of L2 round trips)
+  {
+    const int nvalid4 = min(32, N - n0) * (Cout / 4);             // rows of dy / y are contiguous: [n0 .. n0+32) x Cout
+    const float4* dyp = reinterpret_cast<const float4*>(dy + (long long)n0 * Cout);
+    const float4* yp = reinterpret_cast<const float4*>(y + (long long)n0 * Cout);
+    float4 gv[8], yv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int e = t + 512 * i;
+      gv[i] = e < nvalid4 ? __ldg(dyp + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+      yv[i] = (lrelu && e < nvalid4) ? __ldg(yp + e) : make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      gv[i].x *= yv[i].x > 0.f ? 1.f : alpha;
+      gv[i].y *= yv[i].y > 0.f ? 1.f : alpha;
+      gv[i].z *= yv[i].z > 0.f ? 1.f : alpha;
+      gv[i].w *= yv[i].w > 0.f ? 1.f : alpha;
+      reinterpret_cast<float4*>(g_s)[t + 512 * i] = gv[i];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) wb[j] = __ldg(w1 + j * 16);
+  __syncthreads();
+  auto pass = [&](const float4 (&wv)[8], int row) {
+#pragma unroll 4
+    for (int n = 0; n < 32; ++n) {
+      const float4* gp = reinterpret_cast<const float4*>(g_s + n * Cout) + sg;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 gv = gp[j * 16];
+        a0 = fmaf(gv.x, wv[j].x, a0);
+        a1 = fmaf(gv.y, wv[j].y, a1);
+        a2 = fmaf(gv.z, wv[j].z, a2);
+        a3 = fmaf(gv.w, wv[j].w, a3);
+      }
+      float a = (a0 + a1) + (a2 + a3);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      if ((n & 15) == sg && n0 + n < N) dx[(long long)(n0 + n) * K + row] = a * wscale;
+    }
+  };
+  pass(wa, k0 + r);
+  pass(wb, k0 + 32 + r);
+}
+
 extern "C" int tmx_dense_bwd_input(tmx_handle_t h, const float* dy, const float* y, const float* w, float wscale,
                                    float* dx, int N, int K, int Cout, int lrelu, float alpha, tmx_stream_t s) {
   TMX_REQUIRE(h && dy && w && dx && (!lrelu || y), TMX_ERR_ARG, "tmx_dense_bwd_input: NULL argument");
   TMX_REQUIRE(N > 0 && K > 0 && Cout > 0, TMX_ERR_SHAPE, "tmx_dense_bwd_input: bad shape");
+  if (Cout == 512 && K % kDbiRows == 0 && (((uintptr_t)dy | (uintptr_t)y | (uintptr_t)w) & 15) == 0 &&
+      !tmx_env_flag("TMX_DENSE_NO_STREAM")) {
+    auto kern = dense_bwd_input_stream_kernel;
+    const int smem = 32 * 512 * (int)sizeof(float);
+    static thread_local int configured_device = -1;
+    if (configured_device != h->device) {
+      TMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured_device = h->device;
+    }
+    kern<<<dim3(K / kDbiRows, tmx_ceil_div(N, 32)), 512, smem, (cudaStream_t)s>>>(dy, y, w, wscale, dx, N, K, lrelu, alpha);
+    TMX_LAUNCHED(h, "dense_bwd_input_stream_kernel");
+    return TMX_OK;
+  }
   if (Cout % 64 == 0 && K % 32 == 0 && (((uintptr_t)dy | (uintptr_t)y | (uintptr_t)w) & 15) == 0) {
     dim3 grid4(K / 32, tmx_ceil_div(N, 32));
     dense_bwd_input4_kernel<<<grid4, 256, 0, (cudaStream_t)s>>>(dy, y, w, wscale, dx, N, K, Cout, lrelu, alpha);
@@ -910,6 +995,12 @@ __global__ void __launch_bounds__(256) dense_wgrad4_kernel(const float* __restri
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // the gradient rows this thread accumulates into: fetched now, so that the DRAM round trip of the read-modify-write
+  // overlaps the staging and the products instead of following them
+  float4 cur[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    cur[i] = *reinterpret_cast<const float4*>(dw + (long long)(k0 + ty * 8 + i) * Cout + o0 + tx * 4);
   for (int n0 = 0; n0 < N; n0 += 32) {
     for (int e = threadIdx.x; e < 32 * 32; e += 256) {
       const int n = e >> 5, c4 = (e & 31) * 4;
@@ -956,12 +1047,12 @@ __global__ void __launch_bounds__(256) dense_wgrad4_kernel(const float* __restri
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float4* o = reinterpret_cast<float4*>(dw + (long long)(k0 + ty * 8 + i) * Cout + o0 + tx * 4);
-    float4 cur = *o;
-    cur.x = fmaf(acc[i].x, wscale, cur.x);
-    cur.y = fmaf(acc[i].y, wscale, cur.y);
-    cur.z = fmaf(acc[i].z, wscale, cur.z);
-    cur.w = fmaf(acc[i].w, wscale, cur.w);
-    *o = cur;
+    float4 c = cur[i];
+    c.x = fmaf(acc[i].x, wscale, c.x);
+    c.y = fmaf(acc[i].y, wscale, c.y);
+    c.z = fmaf(acc[i].z, wscale, c.z);
+    c.w = fmaf(acc[i].w, wscale, c.w);
+    *o = c;
   }
   if (db != nullptr && blockIdx.y == 0 && ty == 0) {
     float4* o = reinterpret_cast<float4*>(db + o0 + tx * 4);

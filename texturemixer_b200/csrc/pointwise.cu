@@ -527,6 +527,133 @@ __global__ void __launch_bounds__(256) latent_blend_kernel(const BlendParams P) 
   }
 }
 
+// TILED form for NCHW outputs whose source tiles fit in shared memory (h*w floats per channel: the 32 x 32 latent
+// tiles of the path).  The row-per-block kernel above re-reads every source line once per canvas position it feeds
+// (K = 4 sources: four 128-B lines from L2 per 128-B line written) and spends ~90 instructions per output on 64-bit
+// address arithmetic.  Here a block owns (sample n, `cg` consecutive channels, 32 canvas columns): it stages the
+// K * cg source tiles once (contiguous in NCHW) plus per-row tables (source row offset, row ramp, re-pin flag), then
+// walks ALL canvas rows out of shared memory - every source byte crosses L2 -> SM once per column tile, and the
+// index work of a canvas position is shared by its cg channels.  Column indices / column ramps are per-lane
+// constants of the block.  Same arithmetic, same order as the kernel above (bit-identical results).
+template <int MODE, bool F32>
+__global__ void __launch_bounds__(256) latent_blend_tiled_kernel(const BlendParams P, int cg) {
+  extern __shared__ __align__(16) uint8_t blend_smem[];
+  const tmx_blend_desc_t& d = P.d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.z, c0 = blockIdx.y * cg, j0 = blockIdx.x * 32, j = j0 + lane;
+  const int cn = min(cg, d.C - c0);
+  const int hw = d.h * d.w;
+  const bool jv = j < d.W;
+  float* src_s = reinterpret_cast<float*>(blend_smem);                                   // [K][cg][h*w]
+  double* rh_s = reinterpret_cast<double*>(blend_smem + (size_t)d.K * cg * hw * 4);      // [K][H] row ramps
+  int* syw_s = reinterpret_cast<int*>(rh_s + (size_t)d.K * d.H);                         // [K][H] (source row) * w
+  int* piw_s = syw_s + (size_t)d.K * d.H;                                                // [H] (i % h) * w, < 0: row not re-pinned
+  for (int k = 0; k < d.K; ++k) {
+    const int nn = ((d.src_reverse >> k) & 1u) ? d.N - 1 - n : n;
+    const float4* g = reinterpret_cast<const float4*>(P.io.src[k] + ((long long)nn * d.C + c0) * hw);
+    float4* t = reinterpret_cast<float4*>(src_s + (size_t)k * cg * hw);
+    for (int e = threadIdx.x; e < cn * hw / 4; e += 256) t[e] = __ldg(g + e);
+  }
+  for (int e = threadIdx.x; e < d.K * d.H; e += 256) {
+    const int k = e / d.H, i = e - k * d.H;
+    const int yy = P.io.idx_h[k] ? __ldg(P.io.idx_h[k] + (long long)n * d.H + i) : i;
+    syw_s[e] = (yy % d.h) * d.w;
+    rh_s[e] = MODE == TMX_BLEND_MATTE ? __ldg(P.io.ramp_h[k] + i) : 0.0;
+  }
+  for (int i = threadIdx.x; i < d.H; i += 256)
+    piw_s[i] = (d.pin_rows != 0 && ((d.pin_rows >> (i / d.h)) & 1ull)) ? (i % d.h) * d.w : -1;
+  // per-lane constants of this column tile
+  int sxf[4], sxp = 0;
+  double rwd[4];
+  bool pcol = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    sxf[k] = 0;
+    rwd[k] = 0.0;
+  }
+  if (jv) {
+    pcol = d.pin_rows != 0 && ((d.pin_cols >> (j / d.w)) & 1ull);
+    sxp = j % d.w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < d.K) {
+        const int xx = P.io.idx_w[k] ? __ldg(P.io.idx_w[k] + (long long)n * d.W + j) : j;
+        sxf[k] = xx % d.w;
+        if (MODE == TMX_BLEND_MATTE) rwd[k] = __ldg(P.io.ramp_w[k] + j);
+      }
+    }
+  }
+  float tl = 0.f;
+  if (MODE == TMX_BLEND_LERP) tl = __ldg(P.io.t + n);
+  __syncthreads();
+  if (!jv) return;
+  float* out0 = P.io.out_nchw + ((long long)n * d.C + c0) * d.H * d.W + j;
+  const int plane = d.H * d.W;
+  for (int i = warp; i < d.H; i += 8) {
+    const int piw = piw_s[i];
+    const bool pinned = pcol && piw >= 0;
+    int off[4];
+    double wgt[4];
+    float wgtf[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      off[k] = 0;
+      wgt[k] = 0.0;
+      wgtf[k] = 0.f;
+      if (k < d.K) {
+        off[k] = pinned ? piw + sxp : syw_s[k * d.H + i] + sxf[k];
+        if (MODE == TMX_BLEND_MATTE) {
+          const double rh = rh_s[k * d.H + i];
+          if (F32) wgtf[k] = __fmul_rn((float)rh, (float)rwd[k]);
+          else wgt[k] = __dmul_rn(rh, rwd[k]);
+        }
+      }
+    }
+    float* o = out0 + i * d.W;
+    for (int cc = 0; cc < cn; ++cc) {
+      const float* sc = src_s + cc * hw;
+      float sv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < d.K) sv[k] = sc[k * cg * hw + off[k]];
+      float v;
+      if (MODE == TMX_BLEND_MATTE) {
+        if (F32) {
+          float acc = __fmul_rn(sv[0], wgtf[0]);
+#pragma unroll
+          for (int k = 1; k < 4; ++k)
+            if (k < d.K) acc = __fadd_rn(acc, __fmul_rn(sv[k], wgtf[k]));
+          v = acc;
+        } else {
+          double acc = __dmul_rn((double)sv[0], wgt[0]);
+#pragma unroll
+          for (int k = 1; k < 4; ++k)
+            if (k < d.K) acc = __dadd_rn(acc, __dmul_rn((double)sv[k], wgt[k]));
+          v = (float)acc;
+        }
+      } else if (MODE == TMX_BLEND_LERP) {
+        v = __fadd_rn(sv[0], __fmul_rn(__fsub_rn(sv[1], sv[0]), tl));  // tfutil.py:41-43, unfused
+      } else {
+        v = sv[0];
+      }
+      o[(long long)cc * plane] = v;
+    }
+  }
+}
+
+template <int MODE, bool F32>
+int launch_blend_tiled(tmx_handle_t h, const BlendParams& P, int cg, dim3 grid, size_t smem, cudaStream_t st) {
+  auto kern = latent_blend_tiled_kernel<MODE, F32>;
+  static thread_local int configured_device = -1;
+  if (configured_device != h->device) {
+    TMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured_device = h->device;
+  }
+  kern<<<grid, 256, smem, st>>>(P, cg);
+  TMX_LAUNCHED(h, "latent_blend_tiled_kernel");
+  return TMX_OK;
+}
+
 extern "C" int tmx_latent_blend(tmx_handle_t h, const tmx_blend_desc_t* d, const tmx_blend_io_t* io, tmx_stream_t s) {
   TMX_REQUIRE(h && d && io, TMX_ERR_ARG, "tmx_latent_blend: NULL argument");
   TMX_REQUIRE(d->N > 0 && d->C > 0 && d->h > 0 && d->w > 0 && d->H > 0 && d->W > 0 && d->N <= 65535 && d->H <= 65535,
@@ -552,9 +679,31 @@ extern "C" int tmx_latent_blend(tmx_handle_t h, const tmx_blend_desc_t* d, const
   BlendParams P;
   P.d = *d;
   P.io = *io;
+  cudaStream_t st = (cudaStream_t)s;
+  // tiled form: NCHW output only, real (not broadcast) source tiles; K * cg tiles + the row tables in <= 96 KB
+  {
+    const long long hw = (long long)d->h * d->w;
+    bool aligned = hw % 4 == 0 && (long long)d->H * d->W < (1ll << 31) / 8;
+    for (int k = 0; k < d->K; ++k) aligned = aligned && ((uintptr_t)io->src[k] & 15) == 0;
+    const long long tables = (long long)d->K * d->H * 12 + (long long)d->H * 4;
+    int cg = 0;
+    if (!io->out_nhwc && !d->src_bcast && aligned && !tmx_env_flag("TMX_BLEND_ROWS"))
+      for (int c = 4; c >= 1; c /= 2)
+        if ((long long)d->K * c * hw * 4 + tables <= 80 * 1024 && c <= d->C) {
+          cg = c;
+          break;
+        }
+    if (cg > 0 && tmx_ceil_div(d->C, cg) <= 65535) {
+      dim3 grid(tmx_ceil_div(d->W, 32), tmx_ceil_div(d->C, cg), d->N);
+      const size_t smem = (size_t)d->K * cg * hw * sizeof(float) + (size_t)tables;
+      if (d->mode == TMX_BLEND_COPY) return launch_blend_tiled<TMX_BLEND_COPY, false>(h, P, cg, grid, smem, st);
+      if (d->mode == TMX_BLEND_LERP) return launch_blend_tiled<TMX_BLEND_LERP, false>(h, P, cg, grid, smem, st);
+      if (d->math_f32) return launch_blend_tiled<TMX_BLEND_MATTE, true>(h, P, cg, grid, smem, st);
+      return launch_blend_tiled<TMX_BLEND_MATTE, false>(h, P, cg, grid, smem, st);
+    }
+  }
   dim3 grid(tmx_ceil_div(d->W, 32), d->H, d->N);
   size_t smem = io->out_nhwc ? (size_t)128 * 33 * sizeof(float) : 0;
-  cudaStream_t st = (cudaStream_t)s;
   if (d->mode == TMX_BLEND_COPY) latent_blend_kernel<TMX_BLEND_COPY, false><<<grid, 256, smem, st>>>(P);
   else if (d->mode == TMX_BLEND_LERP) latent_blend_kernel<TMX_BLEND_LERP, false><<<grid, 256, smem, st>>>(P);
   else if (d->math_f32) latent_blend_kernel<TMX_BLEND_MATTE, true><<<grid, 256, smem, st>>>(P);
@@ -700,6 +849,124 @@ __global__ void __launch_bounds__(256) dense_partial4_kernel(const float* __rest
   }
 }
 
+// Streaming path of the 8192 -> 512 head (Cout % 512 == 0, K % 64 == 0).  The kernel above keeps only
+// (rows in flight) x 512 B of DISTINCT weight bytes in flight per block - its eight warps all fetch the same rows - which
+// is ~1 MB over the whole GPU: 27 us for 16.8 MB (0.07 of the HBM peak, ncu: DRAM 8 % busy).  Here a thread owns TWO
+// outputs of 16 samples: 256 threads cover a whole 2-KB weight row (the block's two halves take 16 samples each), and
+// the k loop is software-pipelined in batches of 16 rows (32 KB of distinct weights in flight per block).
+// x of the slice sits in shared memory transposed ([k][sample]: one broadcast LDS.128 feeds 4 samples).
+constexpr int kDenseKSS = 64;      // == kDenseKS4: same partial layout / workspace size
+static_assert(kDenseKSS == kDenseKS4, "the streaming and the 128-bit dense kernels share one workspace layout");
+__global__ void __launch_bounds__(512, 1) dense_partial_stream_kernel(const float* __restrict__ x,
+                                                                     const float* __restrict__ w,
+                                                                     float* __restrict__ part, int N, int K, int Cout) {
+  // 512 threads: thread (half, tt) owns outputs 2*tt, 2*tt+1 of samples half*16 .. half*16+15 (32 accumulators).  With
+  // all 32 samples per thread (256 threads, 64 accumulators, 255 registers) the eight resident warps of an SM issued
+  // 1.2 instructions per cycle: the kernel was FFMA-issue bound at 22 us, not memory bound (ncu).
+  __shared__ __align__(16) float xs[kDenseKSS][kDenseNT + 4];
+  const int t = threadIdx.x, half = t >> 8, tt = t & 255;
+  const int o = blockIdx.x * 512 + tt * 2;
+  const int k0 = blockIdx.y * kDenseKSS;
+  const int n0 = blockIdx.z * kDenseNT;
+  const float2* wp = reinterpret_cast<const float2*>(w + (long long)k0 * Cout + o);
+  const long long ws2 = Cout / 2;
+  float2 wa[16], wb[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) wa[j] = __ldg(wp + j * ws2);          // first batch in flight while x is staged
+  {
+    const int e = t;                                                   // 32 samples x 16 float4 == 512 threads
+    const int n = e / (kDenseKSS / 4), k4 = (e % (kDenseKSS / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 + n < N) v = __ldg(reinterpret_cast<const float4*>(x + (long long)(n0 + n) * K + k0 + k4));
+    xs[k4][n] = v.x;
+    xs[k4 + 1][n] = v.y;
+    xs[k4 + 2][n] = v.z;
+    xs[k4 + 3][n] = v.w;
+  }
+  __syncthreads();
+  constexpr int NH = kDenseNT / 2;
+  float2 acc[NH];
+#pragma unroll
+  for (int n = 0; n < NH; ++n) acc[n] = make_float2(0.f, 0.f);
+  auto fma_batch = [&](const float2 (&wv)[16], int kb) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+#pragma unroll
+      for (int n4 = 0; n4 < NH / 4; ++n4) {
+        const float4 xv = *reinterpret_cast<const float4*>(&xs[kb + j][half * NH + n4 * 4]);
+        acc[4 * n4].x = fmaf(xv.x, wv[j].x, acc[4 * n4].x);
+        acc[4 * n4].y = fmaf(xv.x, wv[j].y, acc[4 * n4].y);
+        acc[4 * n4 + 1].x = fmaf(xv.y, wv[j].x, acc[4 * n4 + 1].x);
+        acc[4 * n4 + 1].y = fmaf(xv.y, wv[j].y, acc[4 * n4 + 1].y);
+        acc[4 * n4 + 2].x = fmaf(xv.z, wv[j].x, acc[4 * n4 + 2].x);
+        acc[4 * n4 + 2].y = fmaf(xv.z, wv[j].y, acc[4 * n4 + 2].y);
+        acc[4 * n4 + 3].x = fmaf(xv.w, wv[j].x, acc[4 * n4 + 3].x);
+        acc[4 * n4 + 3].y = fmaf(xv.w, wv[j].y, acc[4 * n4 + 3].y);
+      }
+    }
+  };
+#pragma unroll
+  for (int j = 0; j < 16; ++j) wb[j] = __ldg(wp + (16 + j) * ws2);
+  fma_batch(wa, 0);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) wa[j] = __ldg(wp + (32 + j) * ws2);
+  fma_batch(wb, 16);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) wb[j] = __ldg(wp + (48 + j) * ws2);
+  fma_batch(wa, 32);
+  fma_batch(wb, 48);
+#pragma unroll
+  for (int n = 0; n < NH; ++n) {
+    const int nn = n0 + half * NH + n;
+    if (nn < N) *reinterpret_cast<float2*>(part + ((long long)blockIdx.y * N + nn) * Cout + o) = acc[n];
+  }
+}
+
+// y = act(wscale * sum_s part[s] + bias) with the slices spread over four thread groups (the one-thread-per-output
+// kernel below walks 128 slices one after the other: 11 us of chained L2 round trips).
+__global__ void __launch_bounds__(256) dense_finish4_kernel(const float* __restrict__ part, const float* __restrict__ bias,
+                                                            float* __restrict__ y, int N, int Cout, int slices,
+                                                            float wscale, int lrelu, float alpha) {
+  __shared__ float4 red[3][64];
+  const int q = threadIdx.x >> 6, e = threadIdx.x & 63;
+  const long long total4 = (long long)N * Cout / 4;
+  const long long t4 = (long long)blockIdx.x * 64 + e;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t4 < total4) {
+    const float4* p = reinterpret_cast<const float4*>(part) + t4;
+#pragma unroll 8
+    for (int sl = q; sl < slices; sl += 4) {
+      const float4 v = __ldg(p + (long long)sl * total4);
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+  }
+  if (q > 0) red[q - 1][e] = acc;
+  __syncthreads();
+  if (q == 0 && t4 < total4) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      acc.x += red[r][e].x;
+      acc.y += red[r][e].y;
+      acc.z += red[r][e].z;
+      acc.w += red[r][e].w;
+    }
+    const int c = (int)((t4 * 4) % Cout);
+    const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = make_float4(fmaf(acc.x, wscale, b.x), fmaf(acc.y, wscale, b.y), fmaf(acc.z, wscale, b.z),
+                           fmaf(acc.w, wscale, b.w));
+    if (lrelu) {
+      v.x = fmaxf(v.x * alpha, v.x);
+      v.y = fmaxf(v.y * alpha, v.y);
+      v.z = fmaxf(v.z * alpha, v.z);
+      v.w = fmaxf(v.w * alpha, v.w);
+    }
+    reinterpret_cast<float4*>(y)[t4] = v;
+  }
+}
+
 static bool dense_fast(int K, int Cout) { return Cout % 128 == 0 && K % kDenseKS4 == 0; }
 
 __global__ void __launch_bounds__(256) dense_finish_kernel(const float* __restrict__ part, const float* __restrict__ bias,
@@ -728,11 +995,22 @@ extern "C" int tmx_dense_fwd(tmx_handle_t h, const float* x, const float* w, con
   const int slices = tmx_ceil_div(K, fast ? kDenseKS4 : kDenseKS);
   dim3 grid(tmx_ceil_div(Cout, fast ? 128 : 64), slices, tmx_ceil_div(N, kDenseNT));
   TMX_REQUIRE(grid.y <= 65535 && grid.z <= 65535, TMX_ERR_SHAPE, "tmx_dense_fwd: problem too large");
-  if (fast) dense_partial4_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, w, workspace, N, K, Cout);
-  else dense_partial_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, w, workspace, N, K, Cout);
+  const bool stream = fast && Cout % 512 == 0 && !tmx_env_flag("TMX_DENSE_NO_STREAM");
+  if (stream) {
+    dim3 gs(Cout / 512, slices, tmx_ceil_div(N, kDenseNT));
+    dense_partial_stream_kernel<<<gs, 512, 0, (cudaStream_t)s>>>(x, w, workspace, N, K, Cout);
+  } else if (fast) {
+    dense_partial4_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, w, workspace, N, K, Cout);
+  } else {
+    dense_partial_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(x, w, workspace, N, K, Cout);
+  }
   TMX_LAUNCHED(h, "dense_partial_kernel");
-  dense_finish_kernel<<<tmx_ceil_div((long long)N * Cout, 256), 256, 0, (cudaStream_t)s>>>(
-      workspace, bias, y, N, Cout, slices, wscale, lrelu, alpha);
+  if (fast && (((uintptr_t)y | (uintptr_t)bias) & 15) == 0)
+    dense_finish4_kernel<<<tmx_ceil_div((long long)N * Cout / 4, 64), 256, 0, (cudaStream_t)s>>>(
+        workspace, bias, y, N, Cout, slices, wscale, lrelu, alpha);
+  else
+    dense_finish_kernel<<<tmx_ceil_div((long long)N * Cout, 256), 256, 0, (cudaStream_t)s>>>(
+        workspace, bias, y, N, Cout, slices, wscale, lrelu, alpha);
   TMX_LAUNCHED(h, "dense_finish_kernel");
   return TMX_OK;
 }
