@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TMX_ABI_VERSION 5
+#define TMX_ABI_VERSION 6
 
 typedef struct tmx_ctx* tmx_handle_t;
 typedef void* tmx_stream_t; /* cudaStream_t */
@@ -425,6 +425,21 @@ typedef struct {
 } tmx_grad_io_t;
 
 int tmx_grad_prepare(tmx_handle_t h, const tmx_grad_desc_t* d, const tmx_grad_io_t* io, tmx_stream_t s);
+
+/* tmx_conv2d_dgrad_gp: tmx_conv2d_dgrad (same first twelve arguments) FOLLOWED BY tmx_grad_prepare(src_kind 0) on its
+ * output, as one tensor-core kernel plus a border pass: `gd` / `gio` describe the [N][H][W][Cin] INPUT activation of this
+ * layer exactly as they would for tmx_grad_prepare (fold, mask of the layer that produced it, add, dz_hi / dz_lo
+ * [required], dz_f32, dbias; gio->g is ignored - the gradient comes from the accumulators).  The epilogue of the data
+ * gradient finishes every interior pixel that receives no folded ring value (add, mask, bias gradient, re-split into
+ * the planes); g_f32 - still a full [N][H+4][W+4][Cin] scratch buffer - only receives the ring and the rows / columns
+ * the REFLECT / REPLICATE adjoint folds onto, which a small second kernel finishes.  Planes and dz_f32 are bit-identical
+ * to the two-call sequence; dbias is summed in another order.  Replaces what tf.gradients emits for
+ * pad -> conv2d -> bias -> leaky_relu chains (networks.py:48-75; tfutil.py:299).
+ * *served = 1: done.  *served = 0: nothing was launched (shape served better elsewhere: Cin, Cout <= 64 thin layers,
+ * Cin not a multiple of 32, maps smaller than 4 x 4 with a fold, TMX_NO_FUSED_GP=1) - call the two functions. */
+int tmx_conv2d_dgrad_gp(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, const uint16_t* dz_hi,
+                        const uint16_t* dz_lo, const uint16_t* wt_hi, const uint16_t* wt_lo, float* g_f32,
+                        const tmx_grad_desc_t* gd, const tmx_grad_io_t* gio, int* served, tmx_stream_t s);
 
 /* ------------------------------------------------------------------ optimizer (tfutil.py:246-399, 611-621)
  * All over flat fp32 buffers (a network's variables are one contiguous, 256-B aligned buffer).

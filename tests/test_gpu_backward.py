@@ -422,3 +422,63 @@ def test_variant_backward_vs_autograd(func, extra, monkeypatch):
         for d, t in zip(din, tin):
             assert _rel_l2(d.cpu().numpy(), t.grad.numpy()) <= 1e-3
     print('worst variable gradient (rel L2):', _check_param_grads(net, flat_grad, P, 1e-3, 1e-2))
+
+
+# Fused data gradient + grad_prepare (tmx_conv2d_dgrad_gp): the epilogue of the LIN-mode kernel finishes every interior
+# pixel no ring value folds onto, a border kernel the rest.  Same arithmetic in the same order as the two-call
+# sequence -> planes and the fp32 output must be BIT-identical; the bias gradient is summed in another order.
+GP_CASES = [
+    # n, cin, cout, h, w, k, fold, mask, add, want_f32, dbias
+    (2, 256, 256, 32, 32, 3, 0, 'hi', True, True, True),       # trunk residual form (CTA pairs)
+    (3, 256, 256, 12, 20, 3, 0, 'f32', False, False, True),    # ragged last tile
+    (5, 256, 512, 8, 8, 3, 0, 'hi', False, False, True),       # last-wave column split
+    (2, 64, 128, 16, 16, 3, 0, 'hi', False, False, True),      # 64 columns: stacked hi/lo accumulators
+    (2, 128, 64, 8, 12, 3, 1, None, True, True, False),        # REPLICATE adjoint (input of a sub-pixel conv)
+    (2, 128, 256, 8, 8, 1, 2, 'hi', False, True, True),        # 1x1: nothing to fold, no border pass
+    (1, 512, 512, 4, 4, 3, 0, 'hi', True, False, True),        # every interior pixel is a border pixel
+    (2, 96, 128, 10, 6, 3, 0, 'f32', True, True, True),        # 32-column tiles
+    (2, 128, 96, 16, 16, 3, 0, 'hi', False, False, True),      # K chunks of 32
+]
+
+
+@pytest.mark.parametrize('n,cin,cout,h,w,k,fold,mask,add,want_f32,dbias', GP_CASES)
+def test_fused_dgrad_grad_prepare_equals_two_calls(rt, n, cin, cout, h, w, k, fold, mask, add, want_f32, dbias):
+    from texturemixer_b200.runtime import Act
+    rng = np.random.RandomState(n + cin + cout + h + w)
+    dy = rng.randn(n, h, w, cout).astype(np.float32)
+    wt = rng.randn(k, k, cin, cout).astype(np.float32)
+    dz, _ = rt.grad_prepare(_dev(dy), n, h, w, cout, src_kind=1, want_planes=True)
+    fwd = rt.prepare_weights(_dev(wt), float(R.wscale_of(wt.shape)), k, cin, cout)
+    wtp = rt.transpose_weights(fwd, cout, k * k, cin)
+    y = rng.randn(n, h, w, cin).astype(np.float32)
+    kw = {}
+    if mask == 'hi':
+        kw['y_hi'] = rt.split_pack(Act(n, h, w, cin, f32=_dev(y))).hi
+    elif mask == 'f32':
+        kw['y_f32'] = _dev(y)
+    addt = _dev(rng.randn(n, h, w, cin).astype(np.float32)) if add else None
+    db_a = torch.zeros(cin, device='cuda') if dbias else None
+    db_b = torch.zeros(cin, device='cuda') if dbias else None
+    g = rt.conv_dgrad(dz, n, h, w, cin, cout, k, wtp)
+    planes_a, f32_a = rt.grad_prepare(g, n, h, w, cin, src_kind=0, fold=fold, add=addt, want_planes=True,
+                                      want_f32=want_f32, dbias=db_a, **kw)
+    out = rt.conv_dgrad_gp(dz, n, h, w, cin, cout, k, wtp, fold, add=addt, want_f32=want_f32, dbias=db_b, **kw)
+    assert out is not None, 'shape not served by the fused kernel'
+    planes_b, f32_b = out
+    torch.cuda.synchronize()
+    for a, b in zip(planes_a, planes_b):
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+    if want_f32:
+        assert torch.equal(f32_a, f32_b)
+    if dbias:
+        assert _nmax(db_b.cpu().numpy(), db_a.cpu().numpy()) <= 2e-6 * np.sqrt(n * h * w)
+
+
+def test_fused_dgrad_declines_thin_layers(rt):
+    """Cin, Cout <= 64 3x3 layers stay on the LIN-PATCH kernel: the fused entry launches nothing and says so."""
+    n, c, h, w = 2, 32, 16, 16
+    z = torch.zeros(n, h + 4, w + 4, c, dtype=torch.bfloat16, device='cuda')
+    wtp = (torch.zeros(c, 9 * c, dtype=torch.bfloat16, device='cuda'),) * 2
+    before = rt.launch_count()
+    assert rt.conv_dgrad_gp((z, z), n, h, w, c, c, 3, wtp, 0) is None
+    assert rt.launch_count() == before

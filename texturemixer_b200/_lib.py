@@ -6,7 +6,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'libtmx.so')
 
-TMX_ABI_VERSION = 5
+TMX_ABI_VERSION = 6
 
 # flags / enums (include/tmx.h)
 CONV_LRELU, CONV_RESIDUAL, CONV_UP2_IN, CONV_UP2_OUT, CONV_HALO_REPLICATE, CONV_TORGB, CONV_XMERGE = 1, 2, 4, 8, 16, 32, 64
@@ -80,6 +80,8 @@ _SIGNATURES = {
     'tmx_nchw_to_nhwc': (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'tmx_nhwc_to_nchw': (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'tmx_conv2d_dgrad': (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    'tmx_conv2d_dgrad_gp': (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, C.POINTER(GradDesc),
+                                      C.POINTER(GradIO), C.POINTER(C.c_int), _P]),
     'tmx_conv_weights_transpose': (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     'tmx_conv2d_wgrad_workspace_bytes': (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_size_t)]),
     'tmx_conv2d_wgrad': (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _I, _P]),

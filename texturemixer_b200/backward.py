@@ -14,7 +14,9 @@ activation travels in one of three forms:
     ('f32', t)            NHWC fp32 at the activation's resolution
     ('grid', g, fold)     a consumer's dgrad output on the zero-ringed grid, to be folded
                           (0 REFLECT, 1 REPLICATE [consumer read through upscale2d], 2 none)
-    ('pool', t)           NHWC fp32 at half resolution (consumer was downscale2d)"""
+    ('pool', t)           NHWC fp32 at half resolution (consumer was downscale2d)
+    ('ready', planes, t)  already combined, masked and split by the consumer's fused data gradient
+                          (tmx_conv2d_dgrad_gp): dz planes on the zero-ringed grid (+ fp32 NHWC when needed)"""
 import ctypes as C
 import os
 
@@ -167,6 +169,42 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
         return scratch[v.size]
 
     tgrads = {}        # gradients w.r.t. plain tensors (dense head), keyed by tensor identity
+
+    # fused data gradient + grad_prepare (tmx_conv2d_dgrad_gp): possible when the conv at hand is the LAST contributor
+    # to its input activation (every other consumer sits later on the tape, i.e. has already been differentiated) and
+    # that activation is the plain output of another conv record, whose mask / bias gradient / residual need are then
+    # known at the time of the data gradient
+    first_use, producer = {}, {}
+    fuse_gp = not os.environ.get('TMX_NO_FUSED_GP')
+    if fuse_gp:
+        for pos_, rec_ in enumerate(tape):
+            for key in ('x', 'residual', 'a', 'b'):
+                a_ = rec_.get(key)
+                if isinstance(a_, runtime.Act):
+                    first_use.setdefault(id(a_), pos_)
+            for a_ in (rec_.get('inputs') or ()):
+                if isinstance(a_, runtime.Act):
+                    first_use.setdefault(id(a_), pos_)
+            if rec_['kind'] == 'conv':
+                producer[id(rec_['y'])] = rec_
+
+    def fused_dgrad(pos, rec, x, dz, wt, hs, ws_, cin_g, ng, k, fold):
+        """Data gradient of `rec` w.r.t. `x` with x's grad_prepare folded in; False when not applicable."""
+        prod = producer.get(id(x)) if fuse_gp else None
+        if prod is None or prod['up2'] or first_use.get(id(x)) != pos:
+            return False
+        pending = grads.by_id.get(id(x), [])
+        if any(cn[0] != 'f32' for cn in pending) or len(pending) > 1:
+            return False
+        mask = _mask_of(rt, x) if prod['act'] else {}
+        dbias = gview(prod['b']) if (param_grads and prod['b'] is not None) else None
+        out = rt.conv_dgrad_gp(dz, x.n, hs, ws_, cin_g, ng, k, wt, fold, add=pending[0][1] if pending else None,
+                               want_f32=prod['residual'] is not None, dbias=dbias, alpha=prod.get('alpha'), **mask)
+        if out is None:
+            return False
+        grads.pop(x)
+        grads.add(x, ('ready', out[0], out[1]))
+        return True
 
     for pos in range(len(tape) - 2, -1, -1):
         rec = tape[pos]
@@ -323,9 +361,12 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
             has_res = rec['residual'] is not None
             mask = _mask_of(rt, y) if rec['act'] else None
             zero_pad = rec.get('halo') == 'zero'        # fused_scale layers: SAME (zero) padding, nothing to fold
-            dz, dz_f32 = _combine(rt, y, contribs, want_planes=True, want_f32=has_res, mask_y=mask,
-                                  dbias=gview(rec['b']) if (param_grads and rec['b'] is not None) else None,
-                                  phase_pack=up2, alpha=rec.get('alpha'))
+            if len(contribs) == 1 and contribs[0][0] == 'ready':
+                dz, dz_f32 = contribs[0][1], contribs[0][2]      # the consumer's fused data gradient did all of it
+            else:
+                dz, dz_f32 = _combine(rt, y, contribs, want_planes=True, want_f32=has_res, mask_y=mask,
+                                      dbias=gview(rec['b']) if (param_grads and rec['b'] is not None) else None,
+                                      phase_pack=up2, alpha=rec.get('alpha'))
             if has_res:
                 grads.add(rec['residual'], ('f32', dz_f32))         # y = conv(x) + residual (networks.py:437)
             if adjoints is not None:
@@ -352,14 +393,17 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
                         _lib.check(rt.lib.tmx_conv_wgrad_unphase(rt.handle, _ptr(dwp), _ptr(gview(rec['w'])), cin_g,
                                                                  cout, rt.stream()), 'tmx_conv_wgrad_unphase')
                 wt = net.cached(('wt', rec['w'], True), lambda: rt.transpose_weights(fwd, ng, 9, cin_g))
-                g = rt.conv_dgrad(dz, x.n, hs, ws_, cin_g, ng, 3, wt)
-                grads.add(x, ('grid', g, 2 if zero_pad else 1))
+                if not fused_dgrad(pos, rec, x, dz, wt, hs, ws_, cin_g, ng, 3, 2 if zero_pad else 1):
+                    g = rt.conv_dgrad(dz, x.n, hs, ws_, cin_g, ng, 3, wt)
+                    grads.add(x, ('grid', g, 2 if zero_pad else 1))
             else:
                 if param_grads:
                     conv_wgrad_into(rt, net, rec, (x.hi, x.lo), dz, gview(rec['w']))
                 wt = net.cached(('wt', rec['w'], False), lambda: rt.transpose_weights(fwd, cout, k * k, cin_g))
-                g = rt.conv_dgrad(dz, x.n, x.h, x.w, cin_g, cout, k, wt)
-                grads.add(x, ('grid', g, 0 if (k == 3 and not zero_pad) else 2))
+                fold = 0 if (k == 3 and not zero_pad) else 2
+                if not fused_dgrad(pos, rec, x, dz, wt, x.h, x.w, cin_g, cout, k, fold):
+                    g = rt.conv_dgrad(dz, x.n, x.h, x.w, cin_g, cout, k, wt)
+                    grads.add(x, ('grid', g, fold))
         elif kind == 'fromrgb':
             y = rec['y']
             contribs = grads.pop(y)

@@ -1282,6 +1282,151 @@ extern "C" int tmx_conv2d_dgrad(tmx_handle_t h, int N, int H, int W, int Cin, in
   return tmx_conv2d_dgrad_tc(h, N, H, W, Cin, Cout, k, dz_hi, dz_lo, wt_hi, wt_lo, g_f32, (cudaStream_t)s);
 }
 
+// ---------------------------------------------------------------- fused data gradient + grad_prepare (GP)
+// tmx_conv2d_dgrad_gp = tmx_conv2d_dgrad followed by tmx_grad_prepare(src_kind 0) with the second one folded into
+// the epilogue of the first (conv_tc.cu, GP) for every interior pixel that receives no folded ring value; the border
+// kernel below finishes the others - rows / columns {1, H-2} (REFLECT) or {0, H-1} (REPLICATE) - with the arithmetic
+// of grad_prepare_kernel in the same order, so planes and fp32 output are bit-identical to the two-kernel path (the
+// bias gradient is summed in another order).
+int tmx_conv2d_dgrad_gp_tc(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, const uint16_t* dz_hi,
+                           const uint16_t* dz_lo, const uint16_t* wt_hi, const uint16_t* wt_lo, float* g_f32,
+                           const tmx_grad_desc_t* gd, const tmx_grad_io_t* gio, cudaStream_t st, int* served);
+
+__global__ void __launch_bounds__(256) grad_border_kernel(const GradPrepParams P, int D) {
+  extern __shared__ float red[];   // [blockDim / C8][C] bias-gradient partials
+  const tmx_grad_desc_t& d = P.d;
+  const int C8 = P.C8, C = d.C, H = d.H, W = d.W;
+  const int Hq = H + 4, Wq = W + 4;
+  const int cg = threadIdx.x % C8, co = cg * 8;
+  const int lane_px = threadIdx.x / C8, lanes = blockDim.x / C8;
+  const long long pixels = (long long)d.N * D;
+  float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int e0 = d.fold == 0 ? 1 : 0;          // first folded row / column; the other one is H-1-e0 / W-1-e0
+  for (long long px = (long long)blockIdx.x * lanes + lane_px; px < pixels; px += (long long)gridDim.x * lanes) {
+    const int n = (int)(px / D);
+    const int q = (int)(px - (long long)n * D);
+    int r, c;
+    if (q < W) {
+      r = e0;
+      c = q;
+    } else if (q < 2 * W) {
+      r = H - 1 - e0;
+      c = q - W;
+    } else {
+      const int e = q - 2 * W, ri = e >> 1;       // ri-th row that is not a folded row
+      r = d.fold == 0 ? (ri == 0 ? 0 : (ri <= H - 4 ? ri + 1 : H - 1)) : ri + 1;
+      c = (e & 1) ? W - 1 - e0 : e0;
+    }
+    int rs[2], cs[2], nr = 0, nc = 0;
+    rs[nr++] = r + 2;
+    cs[nc++] = c + 2;
+    if (d.fold == 0) {
+      if (r == 1) rs[nr++] = 1;
+      if (r == H - 2) rs[nr++] = H + 2;
+      if (c == 1) cs[nc++] = 1;
+      if (c == W - 2) cs[nc++] = W + 2;
+    } else {
+      if (r == 0) rs[nr++] = 1;
+      if (r == H - 1) rs[nr++] = H + 2;
+      if (c == 0) cs[nc++] = 1;
+      if (c == W - 1) cs[nc++] = W + 2;
+    }
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int a = 0; a < nr; ++a)
+      for (int b = 0; b < nc; ++b) {
+        float t[8];
+        ld8(P.io.g + (((long long)n * Hq + rs[a]) * Wq + cs[b]) * C + co, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += t[j];
+      }
+    const long long in_pix = ((long long)n * H + r) * W + c;
+    if (P.io.add != nullptr) {
+      float t[8];
+      ld8(P.io.add + in_pix * C + co, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += t[j];
+    }
+    if (d.mask_kind == 1) {
+      float y[8];
+      ld8(reinterpret_cast<const float*>(P.io.y_mask) + in_pix * C + co, y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= (y[j] > 0.f) ? 1.f : d.alpha;
+    } else if (d.mask_kind == 2) {
+      const uint4 yb = __ldg(reinterpret_cast<const uint4*>(
+          reinterpret_cast<const uint16_t*>(P.io.y_mask) + (((long long)n * (H + 2) + r + 1) * (W + 2) + c + 1) * C + co));
+      const uint32_t w4[4] = {yb.x, yb.y, yb.z, yb.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[2 * j] *= ((int)(w4[j] << 16) > 0) ? 1.f : d.alpha;
+        v[2 * j + 1] *= ((int)(w4[j] & 0xffff0000u) > 0) ? 1.f : d.alpha;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bsum[j] += v[j];
+    if (P.io.dz_f32 != nullptr) {
+      float4* o = reinterpret_cast<float4*>(P.io.dz_f32 + in_pix * C + co);
+      o[0] = make_float4(v[0], v[1], v[2], v[3]);
+      o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tmx_split_bf16x2(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
+    const long long o = (((long long)n * Hq + r + 2) * Wq + c + 2) * C + co;
+    *reinterpret_cast<uint4*>(P.io.dz_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    *reinterpret_cast<uint4*>(P.io.dz_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+  if (P.io.dbias != nullptr) {
+    float* mine = red + lane_px * C + co;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mine[j] = bsum[j];
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += red[l * C + ch];
+      if (s != 0.f) atomicAdd(P.io.dbias + ch, s * d.dbias_scale);
+    }
+  }
+}
+
+extern "C" int tmx_conv2d_dgrad_gp(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, const uint16_t* dz_hi,
+                                   const uint16_t* dz_lo, const uint16_t* wt_hi, const uint16_t* wt_lo, float* g_f32,
+                                   const tmx_grad_desc_t* gd, const tmx_grad_io_t* gio, int* served, tmx_stream_t s) {
+  TMX_REQUIRE(h && dz_hi && dz_lo && wt_hi && wt_lo && g_f32 && gd && gio && served, TMX_ERR_ARG,
+              "tmx_conv2d_dgrad_gp: NULL argument");
+  TMX_REQUIRE(gd->N == N && gd->H == H && gd->W == W && gd->C == Cin && gd->src_kind == 0 && !gd->phase_pack &&
+                  gd->fold >= 0 && gd->fold <= 2 && gd->mask_kind >= 0 && gd->mask_kind <= 2,
+              TMX_ERR_ARG, "tmx_conv2d_dgrad_gp: the grad descriptor must describe the [N][H][W][Cin] input of this layer "
+              "(src_kind 0, no phase_pack)");
+  TMX_REQUIRE(gio->dz_hi && gio->dz_lo, TMX_ERR_ARG, "tmx_conv2d_dgrad_gp: dz_hi / dz_lo outputs are required");
+  TMX_REQUIRE(gd->mask_kind == 0 || gio->y_mask, TMX_ERR_ARG, "tmx_conv2d_dgrad_gp: mask requested without y_mask");
+  TMX_REQUIRE((k == 1 || k == 3) && N > 0 && H > 0 && W > 0, TMX_ERR_SHAPE, "tmx_conv2d_dgrad_gp: bad shape");
+  const void* ptrs[] = {dz_hi, dz_lo, wt_hi, wt_lo, g_f32, gio->add, gio->y_mask, gio->dz_hi, gio->dz_lo, gio->dz_f32,
+                        gio->dbias};
+  for (const void* q : ptrs)
+    TMX_REQUIRE(((uintptr_t)q & 15) == 0, TMX_ERR_ARG, "tmx_conv2d_dgrad_gp: buffers must be 16-byte aligned (%p)", q);
+  int rc = tmx_conv2d_dgrad_gp_tc(h, N, H, W, Cin, Cout, k, dz_hi, dz_lo, wt_hi, wt_lo, g_f32, gd, gio, (cudaStream_t)s,
+                                  served);
+  if (rc != TMX_OK || !*served || gd->fold == 2) return rc;
+  GradPrepParams P;
+  P.d = *gd;
+  P.io = *gio;
+  P.io.g = g_f32;
+  P.C8 = Cin / 8;
+  P.ppb = 256 / P.C8 > 0 ? 256 / P.C8 : 1;
+  P.rpb = 0;
+  P.c8_shift = -1;
+  const int threads = P.ppb * P.C8;
+  const int D = 2 * W + 2 * (H - 2);
+  const long long pixels = (long long)N * D;
+  long long blocks = (pixels + P.ppb - 1) / P.ppb;
+  if (blocks > 4LL * h->sm_count) blocks = 4LL * h->sm_count;
+  const size_t smem = gio->dbias ? (size_t)threads * 8 * sizeof(float) : 0;
+  TMX_REQUIRE(threads <= 256 && smem <= 48 * 1024, TMX_ERR_SHAPE, "tmx_conv2d_dgrad_gp: C=%d not supported", Cin);
+  grad_border_kernel<<<(unsigned)blocks, threads, smem, (cudaStream_t)s>>>(P, D);
+  TMX_LAUNCHED(h, "grad_border_kernel");
+  return TMX_OK;
+}
+
 // ---------------------------------------------------------------- KL regulariser of EG_wgan (loss.py:163-171)
 // KL = -0.5 * kl_weight * mean(1 + 2 ls - mu^2 - exp(2 ls)) per sample; with gscale = kl_weight / (elements per
 // sample * batch) the gradient of the batch mean is dmu = gscale * mu, dls = gscale * (exp(2 ls) - 1);

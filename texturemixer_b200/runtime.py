@@ -289,6 +289,39 @@ class Runtime:
                                              _ptr(wt[0]), _ptr(wt[1]), _ptr(g), self.stream()), 'tmx_conv2d_dgrad')
         return g
 
+    def conv_dgrad_gp(self, dz, n, h, w, cin, cout, k, wt, fold, add=None, y_f32=None, y_hi=None, want_f32=False,
+                      dbias=None, alpha=None):
+        """tmx_conv2d_dgrad_gp: the data gradient of a conv AND the grad_prepare of its input activation [n,h,w,cin]
+        (padding adjoint `fold`, addend, mask of the layer that produced the activation, bias gradient, planes) in one
+        tensor-core kernel plus a border pass.  Returns (planes, f32 or None), or None when the library does not serve
+        the shape that way (nothing was launched: run conv_dgrad + grad_prepare)."""
+        d = _lib.GradDesc(N=n, H=h, W=w, C=cin, src_kind=0, fold=fold, mask_kind=0, phase_pack=0,
+                          alpha=LRELU_ALPHA if alpha is None else float(alpha), dbias_scale=1.0)
+        io = _lib.GradIO()
+        if add is not None:
+            io.add = add.data_ptr()
+        if y_f32 is not None:
+            d.mask_kind, io.y_mask = 1, y_f32.data_ptr()
+        elif y_hi is not None:
+            d.mask_kind, io.y_mask = 2, y_hi.data_ptr()
+        g = self.empty(n, h + 4, w + 4, cin)
+        planes = (self.empty(n, h + 4, w + 4, cin, dtype=torch.bfloat16),
+                  self.empty(n, h + 4, w + 4, cin, dtype=torch.bfloat16))
+        io.dz_hi, io.dz_lo = planes[0].data_ptr(), planes[1].data_ptr()
+        f32 = None
+        if want_f32:
+            f32 = self.empty(n, h, w, cin)
+            io.dz_f32 = f32.data_ptr()
+        if dbias is not None:
+            io.dbias = dbias.data_ptr()
+        served = C.c_int(0)
+        _lib.check(self.lib.tmx_conv2d_dgrad_gp(self.handle, n, h, w, cin, cout, k, _ptr(dz[0]), _ptr(dz[1]),
+                                                _ptr(wt[0]), _ptr(wt[1]), _ptr(g), C.byref(d), C.byref(io),
+                                                C.byref(served), self.stream()), 'tmx_conv2d_dgrad_gp')
+        if not served.value:
+            return None
+        return planes, f32
+
     def conv_wgrad(self, x, dz, n, h, w, cin, cout, k, wscale, dw):
         """dw (HWIO fp32 view of the gradient buffer) += wscale * x^T dz; x = (hi, lo) forward input planes
         [n][h+2][w+2][cin], dz = (hi, lo) planes on the zero-ringed grid [n][h+4][w+4][cout]."""
