@@ -438,6 +438,13 @@ GP_CASES = [
     (1, 512, 512, 4, 4, 3, 0, 'hi', True, False, True),        # every interior pixel is a border pixel
     (2, 96, 128, 10, 6, 3, 0, 'f32', True, True, True),        # 32-column tiles
     (2, 128, 96, 16, 16, 3, 0, 'hi', False, False, True),      # K chunks of 32
+    # thin layers: the LIN-PATCH kernel (conv_lin.cu) with the same epilogue
+    (2, 16, 16, 128, 128, 3, 0, 'f32', False, False, True),
+    (2, 16, 32, 64, 40, 3, 0, 'hi', True, True, True),
+    (3, 32, 32, 20, 12, 3, 0, 'hi', False, False, True),
+    (2, 32, 64, 64, 64, 3, 0, None, False, True, False),
+    (2, 64, 64, 32, 32, 3, 0, 'hi', True, True, True),
+    (2, 64, 32, 16, 16, 3, 1, 'hi', False, False, True),
 ]
 
 
@@ -470,13 +477,17 @@ def test_fused_dgrad_grad_prepare_equals_two_calls(rt, n, cin, cout, h, w, k, fo
         assert torch.equal(a.view(torch.int16), b.view(torch.int16))
     if want_f32:
         assert torch.equal(f32_a, f32_b)
+        # fp32-only form (the gradient of a FromRGB / pooled / windowed activation): no planes are written
+        out2 = rt.conv_dgrad_gp(dz, n, h, w, cin, cout, k, wtp, fold, add=addt, want_f32=True, want_planes=False, **kw)
+        assert out2 is not None and out2[0] is None and torch.equal(out2[1], f32_a)
     if dbias:
         assert _nmax(db_b.cpu().numpy(), db_a.cpu().numpy()) <= 2e-6 * np.sqrt(n * h * w)
 
 
-def test_fused_dgrad_declines_thin_layers(rt):
-    """Cin, Cout <= 64 3x3 layers stay on the LIN-PATCH kernel: the fused entry launches nothing and says so."""
-    n, c, h, w = 2, 32, 16, 16
+def test_fused_dgrad_declines_tiny_maps(rt):
+    """Maps smaller than 4 x 4 with a padding adjoint (every pixel is a border pixel several times over) stay on the
+    two-call path: the fused entry launches nothing and says so."""
+    n, c, h, w = 2, 256, 2, 2
     z = torch.zeros(n, h + 4, w + 4, c, dtype=torch.bfloat16, device='cuda')
     wtp = (torch.zeros(c, 9 * c, dtype=torch.bfloat16, device='cuda'),) * 2
     before = rt.launch_count()

@@ -54,6 +54,8 @@ def _mask_of(rt, y):
 def _combine(rt, act, contribs, want_planes, want_f32, mask_y=None, dbias=None, phase_pack=False, alpha=None):
     """All contributions to dL/d(act) -> (planes on the zero-ringed grid, fp32 NHWC), masked by lrelu'(mask_y);
     `mask_y` is an fp32 map or the dict returned by `_mask_of`."""
+    if len(contribs) == 1 and contribs[0][0] == 'ready':     # the consumer's fused data gradient did all of it
+        return contribs[0][1], contribs[0][2]
     mask_kw = mask_y if isinstance(mask_y, dict) else dict(y_f32=mask_y)
     n, h, w, c = act.n, act.h, act.w, act.c
     main = [x for x in contribs if x[0] in ('grid', 'pool')]
@@ -78,6 +80,10 @@ def _combine(rt, act, contribs, want_planes, want_f32, mask_y=None, dbias=None, 
         add = f32s[1] if len(f32s) == 2 else None
     return rt.grad_prepare(src, n, h, w, c, kind, fold=fold, add=add, want_planes=want_planes,
                            want_f32=want_f32, dbias=dbias, phase_pack=phase_pack, alpha=alpha, **mask_kw)
+
+
+# records whose output gradient a consuming conv's fused data gradient may prepare (backward.fused_dgrad)
+_GP_PRODUCERS = ('conv', 'fromrgb', 'pool', 'window', 'concat')
 
 
 def _scaled(rt, x, a):
@@ -185,21 +191,28 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
             for a_ in (rec_.get('inputs') or ()):
                 if isinstance(a_, runtime.Act):
                     first_use.setdefault(id(a_), pos_)
-            if rec_['kind'] == 'conv':
+            if rec_['kind'] in _GP_PRODUCERS and isinstance(rec_.get('y'), runtime.Act):
                 producer[id(rec_['y'])] = rec_
 
     def fused_dgrad(pos, rec, x, dz, wt, hs, ws_, cin_g, ng, k, fold):
         """Data gradient of `rec` w.r.t. `x` with x's grad_prepare folded in; False when not applicable."""
         prod = producer.get(id(x)) if fuse_gp else None
-        if prod is None or prod['up2'] or first_use.get(id(x)) != pos:
+        if prod is None or prod.get('up2') or first_use.get(id(x)) != pos:
             return False
         pending = grads.by_id.get(id(x), [])
         if any(cn[0] != 'f32' for cn in pending) or len(pending) > 1:
             return False
-        mask = _mask_of(rt, x) if prod['act'] else {}
-        dbias = gview(prod['b']) if (param_grads and prod['b'] is not None) else None
+        kind = prod['kind']
+        if kind == 'conv':          # what the producer's own record would ask of _combine
+            mask = _mask_of(rt, x) if prod['act'] else {}
+            dbias = gview(prod['b']) if (param_grads and prod['b'] is not None) else None
+            planes, f32 = True, prod['residual'] is not None
+        elif kind == 'fromrgb':     # fp32 only: the 1x1 image head differentiates on the fp32 map
+            mask, dbias, planes, f32 = dict(y_f32=x.f32), (gview(prod['b']) if param_grads else None), False, True
+        else:                       # pool / window / concat: the plain fp32 gradient
+            mask, dbias, planes, f32 = {}, None, False, True
         out = rt.conv_dgrad_gp(dz, x.n, hs, ws_, cin_g, ng, k, wt, fold, add=pending[0][1] if pending else None,
-                               want_f32=prod['residual'] is not None, dbias=dbias, alpha=prod.get('alpha'), **mask)
+                               want_f32=f32, want_planes=planes, dbias=dbias, alpha=prod.get('alpha'), **mask)
         if out is None:
             return False
         grads.pop(x)
@@ -361,12 +374,9 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
             has_res = rec['residual'] is not None
             mask = _mask_of(rt, y) if rec['act'] else None
             zero_pad = rec.get('halo') == 'zero'        # fused_scale layers: SAME (zero) padding, nothing to fold
-            if len(contribs) == 1 and contribs[0][0] == 'ready':
-                dz, dz_f32 = contribs[0][1], contribs[0][2]      # the consumer's fused data gradient did all of it
-            else:
-                dz, dz_f32 = _combine(rt, y, contribs, want_planes=True, want_f32=has_res, mask_y=mask,
-                                      dbias=gview(rec['b']) if (param_grads and rec['b'] is not None) else None,
-                                      phase_pack=up2, alpha=rec.get('alpha'))
+            dz, dz_f32 = _combine(rt, y, contribs, want_planes=True, want_f32=has_res, mask_y=mask,
+                                  dbias=gview(rec['b']) if (param_grads and rec['b'] is not None) else None,
+                                  phase_pack=up2, alpha=rec.get('alpha'))
             if has_res:
                 grads.add(rec['residual'], ('f32', dz_f32))         # y = conv(x) + residual (networks.py:437)
             if adjoints is not None:

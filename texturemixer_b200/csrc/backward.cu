@@ -1260,7 +1260,8 @@ extern "C" int tmx_add_f32(tmx_handle_t h, const float* a, const float* b, float
 
 int tmx_conv2d_dgrad_lin_patch(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, const uint16_t* dz_hi,
                                const uint16_t* dz_lo, const uint16_t* wt_hi, const uint16_t* wt_lo, float* g_f32,
-                               cudaStream_t st, int* served);
+                               cudaStream_t st, int* served, const tmx_grad_desc_t* gd = nullptr,
+                               const tmx_grad_io_t* gio = nullptr);
 int tmx_conv2d_dgrad_tc(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, int k, const uint16_t* dz_hi,
                         const uint16_t* dz_lo, const uint16_t* wt_hi, const uint16_t* wt_lo, float* g_f32,
                         cudaStream_t st);
@@ -1368,12 +1369,14 @@ __global__ void __launch_bounds__(256) grad_border_kernel(const GradPrepParams P
       o[0] = make_float4(v[0], v[1], v[2], v[3]);
       o[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
-    uint32_t ph[4], pl[4];
+    if (P.io.dz_hi != nullptr) {
+      uint32_t ph[4], pl[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) tmx_split_bf16x2(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
-    const long long o = (((long long)n * Hq + r + 2) * Wq + c + 2) * C + co;
-    *reinterpret_cast<uint4*>(P.io.dz_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-    *reinterpret_cast<uint4*>(P.io.dz_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+      for (int j = 0; j < 4; ++j) tmx_split_bf16x2(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
+      const long long o = (((long long)n * Hq + r + 2) * Wq + c + 2) * C + co;
+      *reinterpret_cast<uint4*>(P.io.dz_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      *reinterpret_cast<uint4*>(P.io.dz_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
   }
   if (P.io.dbias != nullptr) {
     float* mine = red + lane_px * C + co;
@@ -1397,15 +1400,23 @@ extern "C" int tmx_conv2d_dgrad_gp(tmx_handle_t h, int N, int H, int W, int Cin,
                   gd->fold >= 0 && gd->fold <= 2 && gd->mask_kind >= 0 && gd->mask_kind <= 2,
               TMX_ERR_ARG, "tmx_conv2d_dgrad_gp: the grad descriptor must describe the [N][H][W][Cin] input of this layer "
               "(src_kind 0, no phase_pack)");
-  TMX_REQUIRE(gio->dz_hi && gio->dz_lo, TMX_ERR_ARG, "tmx_conv2d_dgrad_gp: dz_hi / dz_lo outputs are required");
+  TMX_REQUIRE((gio->dz_hi == nullptr) == (gio->dz_lo == nullptr), TMX_ERR_ARG, "tmx_conv2d_dgrad_gp: dz_hi/dz_lo go together");
+  TMX_REQUIRE(gio->dz_hi || gio->dz_f32, TMX_ERR_ARG, "tmx_conv2d_dgrad_gp: no output (dz planes and / or dz_f32)");
   TMX_REQUIRE(gd->mask_kind == 0 || gio->y_mask, TMX_ERR_ARG, "tmx_conv2d_dgrad_gp: mask requested without y_mask");
   TMX_REQUIRE((k == 1 || k == 3) && N > 0 && H > 0 && W > 0, TMX_ERR_SHAPE, "tmx_conv2d_dgrad_gp: bad shape");
   const void* ptrs[] = {dz_hi, dz_lo, wt_hi, wt_lo, g_f32, gio->add, gio->y_mask, gio->dz_hi, gio->dz_lo, gio->dz_f32,
                         gio->dbias};
   for (const void* q : ptrs)
     TMX_REQUIRE(((uintptr_t)q & 15) == 0, TMX_ERR_ARG, "tmx_conv2d_dgrad_gp: buffers must be 16-byte aligned (%p)", q);
-  int rc = tmx_conv2d_dgrad_gp_tc(h, N, H, W, Cin, Cout, k, dz_hi, dz_lo, wt_hi, wt_lo, g_f32, gd, gio, (cudaStream_t)s,
-                                  served);
+  *served = 0;
+  if (tmx_env_flag("TMX_NO_FUSED_GP") || (gd->fold != 2 && (H < 4 || W < 4))) return TMX_OK;
+  int rc = TMX_OK;
+  if (k == 3)      // thin layers (Cin, Cout in {16, 32, 64}): the LIN-PATCH kernel with the same epilogue
+    rc = tmx_conv2d_dgrad_lin_patch(h, N, H, W, Cin, Cout, dz_hi, dz_lo, wt_hi, wt_lo, g_f32, (cudaStream_t)s, served, gd,
+                                    gio);
+  if (rc == TMX_OK && !*served)
+    rc = tmx_conv2d_dgrad_gp_tc(h, N, H, W, Cin, Cout, k, dz_hi, dz_lo, wt_hi, wt_lo, g_f32, gd, gio, (cudaStream_t)s,
+                                served);
   if (rc != TMX_OK || !*served || gd->fold == 2) return rc;
   GradPrepParams P;
   P.d = *gd;

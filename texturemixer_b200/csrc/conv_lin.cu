@@ -34,6 +34,7 @@ struct LinPatchParams {
   int b_bytes;         // both planes: 2 * BN * 9 * K * 2
   int stages;
   float* y;
+  GpParams gp;         // GP epilogue (tmx_conv2d_dgrad_gp): tmx_grad_prepare fused in, see tc_common.cuh
 };
 
 // no-swizzle K-major shared-memory descriptor (cute::UMMA Major-K INTERLEAVE: ((8,n),2):((1,SBO),LBO) in 16-B units)
@@ -45,7 +46,7 @@ __host__ __device__ constexpr uint32_t make_idesc_lin(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kLinM >> 4) << 24);
 }
 
-template <int BN>
+template <int BN, bool GP = false>
 __global__ void __launch_bounds__(kLinThreads, 1)
     conv_lin_patch_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                           const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* b_bar = tempty_bar + 2;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(b_bar + 1);
+  float* gp_bias_s = reinterpret_cast<float*>(full_bar) + 128;      // 512 B into the 1-KB barrier block: [BN <= 64]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr_s);
+  if (GP && threadIdx.x >= 128 && threadIdx.x < 128 + BN) gp_bias_s[threadIdx.x - 128] = 0.f;
   tmx_pdl_wait();      // set-up above overlaps the previous kernel's tail; its results are read from here on
   tc_fence_before();
   __syncthreads();
@@ -178,6 +181,8 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       const bool valid = mlin < p.rows;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      GpRow gp_row;
+      if (GP) gp_row = gp_classify(p.gp, mlin, valid);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kAccCols);
@@ -194,7 +199,13 @@ __global__ void __launch_bounds__(kLinThreads, 1)
           tmem_ld16(taddr0 + 2 * BN + g * GW, a2);
         }
         tmem_ld_wait();
-        if (valid) {
+        if constexpr (GP) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = j < GW ? (__uint_as_float(a2[j]) + __uint_as_float(a1[j])) + __uint_as_float(a0[j]) : 0.f;
+          gp_group<GW>(p.gp, gp_row, mlin, BN, g * GW, v, gp_bias_s, lane);
+        } else if (valid) {
           float v[GW];
 #pragma unroll
           for (int j = 0; j < GW; ++j)      // small terms first, then the dominant hi*hi product
@@ -208,6 +219,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
     }
+    if (GP) gp_flush_bias(p.gp, gp_bias_s, BN);
   }
 
   tc_fence_before();
@@ -258,9 +270,9 @@ bool lin_patch_plan(int W, int Cin, int Cout, long long rows, LinPatchParams& p,
   return true;
 }
 
-template <int BN>
+template <int BN, bool GP = false>
 int launch_lin_patch(tmx_handle_t h, const CUtensorMap* maps, const LinPatchParams& p, int smem_bytes, cudaStream_t st) {
-  auto kern = conv_lin_patch_kernel<BN>;
+  auto kern = conv_lin_patch_kernel<BN, GP>;
   static thread_local int configured_device = -1;
   if (configured_device != h->device) {
     TMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinSmemBudget + 4096));
@@ -276,9 +288,10 @@ int launch_lin_patch(tmx_handle_t h, const CUtensorMap* maps, const LinPatchPara
 }  // namespace
 
 // returns TMX_OK and sets *served = 1 when the shape was handled here; *served = 0: use the general LIN mode
+// gd / gio != NULL: GP form (tmx_conv2d_dgrad_gp) - the epilogue runs tmx_grad_prepare on the accumulators
 int tmx_conv2d_dgrad_lin_patch(tmx_handle_t h, int N, int H, int W, int Cin, int Cout, const uint16_t* dz_hi,
                                const uint16_t* dz_lo, const uint16_t* wt_hi, const uint16_t* wt_lo, float* g_f32,
-                               cudaStream_t st, int* served) {
+                               cudaStream_t st, int* served, const tmx_grad_desc_t* gd, const tmx_grad_io_t* gio) {
   *served = 0;
   if (tmx_env_flag("TMX_NO_LIN_PATCH")) return TMX_OK;
   const long long rows = (long long)N * (H + 4) * (W + 4);
@@ -293,7 +306,12 @@ int tmx_conv2d_dgrad_lin_patch(tmx_handle_t h, int N, int H, int W, int Cin, int
   if ((rc = encode_chunk_map(h, &maps[1], dz_lo, rows, Cout, p.rbox))) return rc;
   if ((rc = encode_chunk_map(h, &maps[2], wt_hi, Cin, 9 * Cout, Cin))) return rc;
   if ((rc = encode_chunk_map(h, &maps[3], wt_lo, Cin, 9 * Cout, Cin))) return rc;
-  if (Cin == 16) rc = launch_lin_patch<16>(h, maps, p, smem_bytes, st);
+  if (gd != nullptr) {
+    p.gp = tmx_gp_params(H, W, g_f32, gd, gio);
+    if (Cin == 16) rc = launch_lin_patch<16, true>(h, maps, p, smem_bytes, st);
+    else if (Cin == 32) rc = launch_lin_patch<32, true>(h, maps, p, smem_bytes, st);
+    else rc = launch_lin_patch<64, true>(h, maps, p, smem_bytes, st);
+  } else if (Cin == 16) rc = launch_lin_patch<16>(h, maps, p, smem_bytes, st);
   else if (Cin == 32) rc = launch_lin_patch<32>(h, maps, p, smem_bytes, st);
   else rc = launch_lin_patch<64>(h, maps, p, smem_bytes, st);
   if (rc) return rc;

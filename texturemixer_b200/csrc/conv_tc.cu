@@ -92,16 +92,8 @@ struct ConvTcParams {
   float* y_f32;
   uint16_t* y_hi;
   uint16_t* y_lo;
-  // GP epilogue (LIN mode, tmx_conv2d_dgrad_gp): tmx_grad_prepare fused into the data gradient.  y_f32 = the grid
-  // buffer (only the ring next to the interior and the interior pixels the padding adjoint folds onto are written),
-  // y_hi / y_lo = the dz planes on the zero-ringed grid, gp_f32 = masked gradient as fp32 NHWC (optional), gp_add =
-  // second addend (fp32 NHWC, optional), gp_mask = forward output (fp32 NHWC: kind 1, bf16 hi plane with halo: kind 2)
-  int gp_fold, gp_mask_kind;
-  float gp_dbias_scale;
-  const float* gp_add;
-  const void* gp_mask;
-  float* gp_f32;
-  float* gp_dbias;
+  // GP epilogue (LIN mode, tmx_conv2d_dgrad_gp): tmx_grad_prepare fused into the data gradient (tc_common.cuh)
+  GpParams gp;
   // fused ToRGB head
   int rgb_c, rgb_tanh;
   float rgb_wscale;
@@ -144,22 +136,6 @@ __device__ __forceinline__ void decode_item(const ConvTcParams& p, int item, int
     part = q - (q / p.split) * p.split;
     parts = p.split;
   }
-}
-
-// column sums of a 32 x 32 tile held one row per lane: lane L returns sum over the warp's lanes of v[L] (31 shuffles:
-// each stage keeps the half of the columns whose index has the stage's bit equal to the lane's)
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int j = 0; j < o; ++j) {
-      const float send = up ? v[j] : v[j + o];
-      const float keep = up ? v[j + o] : v[j];
-      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-    }
-  }
-  return v[0];
 }
 
 template <int BN, int KC, int GW, bool PAIR, bool GP = false>
@@ -434,27 +410,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       const bool valid = p.lin ? (mlin < p.lin_rows) : (n < p.N);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      // GP: what this grid row is - 0 outer ring / unused ring (zero planes), 1 ring next to the interior that the
-      // padding adjoint reads (raw value to the grid buffer + zero planes), 2 interior pixel a ring value folds onto
-      // (raw value to the grid buffer; tmx_grad_border finishes it), 3 any other interior pixel (finished here)
-      int gp_cls = -1;
-      long long gp_pix = 0, gp_mpix = 0;
-      if (GP && valid) {
-        const int Wq = p.W + 4, HWq = (p.H + 4) * Wq;
-        const int n_ = (int)(mlin / HWq);
-        const int rem2 = (int)(mlin - (long long)n_ * HWq);
-        const int rr = rem2 / Wq;
-        const int r_ = rr - 2, c_ = rem2 - rr * Wq - 2;
-        if (r_ >= 0 && r_ < p.H && c_ >= 0 && c_ < p.W) {
-          const bool dirty = p.gp_fold == 0 ? (r_ == 1 || r_ == p.H - 2 || c_ == 1 || c_ == p.W - 2)
-                                            : (p.gp_fold == 1 ? (r_ == 0 || r_ == p.H - 1 || c_ == 0 || c_ == p.W - 1) : false);
-          gp_cls = dirty ? 2 : 3;
-          gp_pix = ((long long)n_ * p.H + r_) * p.W + c_;
-          gp_mpix = ((long long)n_ * (p.H + 2) + r_ + 1) * (p.W + 2) + c_ + 1;
-        } else {
-          gp_cls = (p.gp_fold != 2 && r_ >= -1 && r_ <= p.H && c_ >= -1 && c_ <= p.W) ? 1 : 0;
-        }
-      }
+      GpRow gp_row;
+      if (GP) gp_row = gp_classify(p.gp, mlin, valid);
 
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
@@ -507,78 +464,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = j < GW ? __uint_as_float(acc[j]) : 0.f;
-          if (gp_cls == 1 || gp_cls == 2) {
-            float4* op = reinterpret_cast<float4*>(p.y_f32 + mlin * CL + col0);
-#pragma unroll
-            for (int j = 0; j < GW / 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (gp_cls == 0 || gp_cls == 1) {
-            uint4* oh = reinterpret_cast<uint4*>(p.y_hi + mlin * CL + col0);
-            uint4* ol = reinterpret_cast<uint4*>(p.y_lo + mlin * CL + col0);
-#pragma unroll
-            for (int j = 0; j < GW / 8; ++j) {
-              oh[j] = make_uint4(0u, 0u, 0u, 0u);
-              ol[j] = make_uint4(0u, 0u, 0u, 0u);
-            }
-          }
-          if (gp_cls == 3) {
-            if (p.gp_add != nullptr) {
-              const float4* ap = reinterpret_cast<const float4*>(p.gp_add + gp_pix * CL + col0);
-#pragma unroll
-              for (int j = 0; j < GW / 4; ++j) {
-                const float4 a4 = __ldg(ap + j);
-                v[4 * j] += a4.x;
-                v[4 * j + 1] += a4.y;
-                v[4 * j + 2] += a4.z;
-                v[4 * j + 3] += a4.w;
-              }
-            }
-            if (p.gp_mask_kind == 1) {
-              const float4* yp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.gp_mask) + gp_pix * CL + col0);
-#pragma unroll
-              for (int j = 0; j < GW / 4; ++j) {
-                const float4 y4 = __ldg(yp + j);
-                v[4 * j] *= y4.x > 0.f ? 1.f : p.alpha;
-                v[4 * j + 1] *= y4.y > 0.f ? 1.f : p.alpha;
-                v[4 * j + 2] *= y4.z > 0.f ? 1.f : p.alpha;
-                v[4 * j + 3] *= y4.w > 0.f ? 1.f : p.alpha;
-              }
-            } else if (p.gp_mask_kind == 2) {
-              const uint4* yp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.gp_mask) + gp_mpix * CL + col0);
-#pragma unroll
-              for (int j = 0; j < GW / 8; ++j) {
-                const uint4 yb = __ldg(yp + j);
-                const uint32_t w4[4] = {yb.x, yb.y, yb.z, yb.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {   // y > 0  <=>  the bf16 word, moved to the top half, is a positive int32
-                  v[8 * j + 2 * q] *= ((int)(w4[q] << 16) > 0) ? 1.f : p.alpha;
-                  v[8 * j + 2 * q + 1] *= ((int)(w4[q] & 0xffff0000u) > 0) ? 1.f : p.alpha;
-                }
-              }
-            }
-            if (p.gp_f32 != nullptr) {
-              float4* op = reinterpret_cast<float4*>(p.gp_f32 + gp_pix * CL + col0);
-#pragma unroll
-              for (int j = 0; j < GW / 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            uint4* oh = reinterpret_cast<uint4*>(p.y_hi + mlin * CL + col0);
-            uint4* ol = reinterpret_cast<uint4*>(p.y_lo + mlin * CL + col0);
-#pragma unroll
-            for (int j = 0; j < GW / 8; ++j) {
-              uint32_t ph[4], pl[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) tmx_split_bf16x2(v[8 * j + 2 * q], v[8 * j + 2 * q + 1], ph[q], pl[q]);
-              oh[j] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-              ol[j] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-          }
-          if (p.gp_dbias != nullptr) {      // (uniform branch: every lane takes part in the shuffles)
-            const float cs = warp_colsum32(v, lane);
-            if (lane < GW) atomicAdd(&gp_bias_s[col0 + lane], cs);
-          }
+          gp_group<GW>(p.gp, gp_row, mlin, CL, col0, v, gp_bias_s, lane);
         } else if (valid) {
           const int col0 = cblk * BN + part * (BN / parts) + g * GW;
           int cbase = col0, oy = y, ox = x;
@@ -699,14 +585,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         else mbar_arrive(&tempty_bar[as]);
       }
     }
-    if (GP && p.gp_dbias != nullptr) {
-      // bias gradient of this CTA's pixels: one global atomic per channel (the four epilogue warps meet first)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = threadIdx.x - 128; c < p.Cout; c += 128) {
-        const float bs = gp_bias_s[c];
-        if (bs != 0.f) atomicAdd(p.gp_dbias + c, bs * p.gp_dbias_scale);
-      }
-    }
+    if (GP) gp_flush_bias(p.gp, gp_bias_s, p.Cout);
   }
 
   tc_fence_before();
@@ -1063,10 +942,7 @@ int tmx_conv2d_dgrad_gp_tc(tmx_handle_t h, int N, int H, int W, int Cin, int Cou
                            const uint16_t* dz_lo, const uint16_t* wt_hi, const uint16_t* wt_lo, float* g_f32,
                            const tmx_grad_desc_t* gd, const tmx_grad_io_t* gio, cudaStream_t st, int* served) {
   *served = 0;
-  if (tmx_env_flag("TMX_NO_FUSED_GP")) return TMX_OK;
   if (!(k == 1 || k == 3) || Cin % 32 != 0 || Cin > 512 || Cout % 32 != 0) return TMX_OK;
-  if (k == 3 && Cin <= 64 && Cout <= 64) return TMX_OK;            // thin layers: the LIN-PATCH kernel is the faster one
-  if (gd->fold != 2 && (H < 4 || W < 4)) return TMX_OK;
   const int kc = Cout % 64 == 0 ? 64 : 32;
   int bnc;
   if (Cin % 256 == 0) bnc = 256;
@@ -1094,17 +970,7 @@ int tmx_conv2d_dgrad_gp_tc(tmx_handle_t h, int N, int H, int W, int Cin, int Cou
   p.lin = 1;
   p.lin_pitch = W + 4;
   p.lin_rows = rows;
-  p.y_f32 = g_f32;
-  p.y_hi = gio->dz_hi;
-  p.y_lo = gio->dz_lo;
-  p.alpha = gd->alpha;
-  p.gp_fold = gd->fold;
-  p.gp_mask_kind = gd->mask_kind;
-  p.gp_dbias_scale = gd->dbias_scale;
-  p.gp_add = gio->add;
-  p.gp_mask = gio->y_mask;
-  p.gp_f32 = gio->dz_f32;
-  p.gp_dbias = gio->dbias;
+  p.gp = tmx_gp_params(H, W, g_f32, gd, gio);
   const long long tiles_m = (rows + kTileM - 1) / kTileM;
   CUtensorMap maps[6];
   int rc;

@@ -167,4 +167,176 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+
+// ---------------------------------------------------------------- GP: tmx_grad_prepare inside a data-gradient epilogue
+// Shared by conv_tc.cu (LIN mode) and conv_lin.cu (LIN-PATCH): the thread that owns grid row `mlin` of the zero-ringed
+// grid [N][H+4][W+4] finishes, GW channels at a time, what tmx_grad_prepare(src_kind 0) would do with the accumulator:
+// see tmx_conv2d_dgrad_gp in include/tmx.h.
+struct GpParams {
+  int H, W, fold, mask_kind;     // fold: 0 REFLECT, 1 REPLICATE, 2 none; mask_kind: 0 none, 1 fp32 NHWC, 2 bf16 hi plane
+  float alpha, dbias_scale;
+  const float* add;              // fp32 NHWC [N][H][W][C] or NULL
+  const void* mask;
+  float* grid;                   // fp32 [N][H+4][W+4][C]: ring next to the interior + the pixels it folds onto
+  uint16_t* dz_hi;               // planes on the grid (may be NULL: fp32 output only)
+  uint16_t* dz_lo;
+  float* f32;                    // fp32 NHWC output or NULL
+  float* dbias;                  // [C] or NULL
+};
+
+// what a grid row is: -1 past the end, 0 outer / unused ring (zero planes), 1 ring next to the interior that the padding
+// adjoint reads (raw value to the grid buffer + zero planes), 2 interior pixel a ring value folds onto (raw value to
+// the grid buffer; grad_border_kernel finishes it), 3 any other interior pixel (finished by the epilogue)
+struct GpRow {
+  int cls;
+  long long pix, mpix;           // NHWC pixel index; pixel index inside the haloed [N][H+2][W+2] mask planes
+};
+
+__device__ __forceinline__ GpRow gp_classify(const GpParams& q, long long mlin, bool valid) {
+  GpRow row;
+  row.cls = -1;
+  row.pix = row.mpix = 0;
+  if (!valid) return row;
+  const int Wq = q.W + 4, HWq = (q.H + 4) * Wq;
+  const int n_ = (int)(mlin / HWq);
+  const int rem = (int)(mlin - (long long)n_ * HWq);
+  const int rr = rem / Wq;
+  const int r_ = rr - 2, c_ = rem - rr * Wq - 2;
+  if (r_ >= 0 && r_ < q.H && c_ >= 0 && c_ < q.W) {
+    const bool dirty = q.fold == 0 ? (r_ == 1 || r_ == q.H - 2 || c_ == 1 || c_ == q.W - 2)
+                                   : (q.fold == 1 ? (r_ == 0 || r_ == q.H - 1 || c_ == 0 || c_ == q.W - 1) : false);
+    row.cls = dirty ? 2 : 3;
+    row.pix = ((long long)n_ * q.H + r_) * q.W + c_;
+    row.mpix = ((long long)n_ * (q.H + 2) + r_ + 1) * (q.W + 2) + c_ + 1;
+  } else {
+    row.cls = (q.fold != 2 && r_ >= -1 && r_ <= q.H && c_ >= -1 && c_ <= q.W) ? 1 : 0;
+  }
+  return row;
+}
+
+// column sums of a 32 x 32 tile held one row per lane: lane L returns sum over the warp's lanes of v[L] (31 shuffles:
+// each stage keeps the half of the columns whose index has the stage's bit equal to the lane's)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < o; ++j) {
+      const float send = up ? v[j] : v[j + o];
+      const float keep = up ? v[j + o] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+// One group of GW channels [col0, col0 + GW) of grid row mlin; v[0..GW) = the data gradient (v[GW..32) = 0), C = channel
+// count of the activation; bias_s = the CTA's shared bias-gradient partials [C].  Called by all 32 lanes of a warp.
+template <int GW>
+__device__ __forceinline__ void gp_group(const GpParams& q, const GpRow& row, long long mlin, int C, int col0,
+                                         float (&v)[32], float* bias_s, int lane) {
+  if (row.cls == 1 || row.cls == 2) {
+    float4* op = reinterpret_cast<float4*>(q.grid + mlin * C + col0);
+#pragma unroll
+    for (int j = 0; j < GW / 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+  if ((row.cls == 0 || row.cls == 1) && q.dz_hi != nullptr) {
+    uint4* oh = reinterpret_cast<uint4*>(q.dz_hi + mlin * C + col0);
+    uint4* ol = reinterpret_cast<uint4*>(q.dz_lo + mlin * C + col0);
+#pragma unroll
+    for (int j = 0; j < GW / 8; ++j) {
+      oh[j] = make_uint4(0u, 0u, 0u, 0u);
+      ol[j] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  if (row.cls == 3) {
+    if (q.add != nullptr) {
+      const float4* ap = reinterpret_cast<const float4*>(q.add + row.pix * C + col0);
+#pragma unroll
+      for (int j = 0; j < GW / 4; ++j) {
+        const float4 a4 = __ldg(ap + j);
+        v[4 * j] += a4.x;
+        v[4 * j + 1] += a4.y;
+        v[4 * j + 2] += a4.z;
+        v[4 * j + 3] += a4.w;
+      }
+    }
+    if (q.mask_kind == 1) {
+      const float4* yp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(q.mask) + row.pix * C + col0);
+#pragma unroll
+      for (int j = 0; j < GW / 4; ++j) {
+        const float4 y4 = __ldg(yp + j);
+        v[4 * j] *= y4.x > 0.f ? 1.f : q.alpha;
+        v[4 * j + 1] *= y4.y > 0.f ? 1.f : q.alpha;
+        v[4 * j + 2] *= y4.z > 0.f ? 1.f : q.alpha;
+        v[4 * j + 3] *= y4.w > 0.f ? 1.f : q.alpha;
+      }
+    } else if (q.mask_kind == 2) {
+      const uint4* yp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(q.mask) + row.mpix * C + col0);
+#pragma unroll
+      for (int j = 0; j < GW / 8; ++j) {
+        const uint4 yb = __ldg(yp + j);
+        const uint32_t w4[4] = {yb.x, yb.y, yb.z, yb.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {   // y > 0  <=>  the bf16 word, moved to the top half, is a positive int32
+          v[8 * j + 2 * t] *= ((int)(w4[t] << 16) > 0) ? 1.f : q.alpha;
+          v[8 * j + 2 * t + 1] *= ((int)(w4[t] & 0xffff0000u) > 0) ? 1.f : q.alpha;
+        }
+      }
+    }
+    if (q.f32 != nullptr) {
+      float4* op = reinterpret_cast<float4*>(q.f32 + row.pix * C + col0);
+#pragma unroll
+      for (int j = 0; j < GW / 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    if (q.dz_hi != nullptr) {
+      uint4* oh = reinterpret_cast<uint4*>(q.dz_hi + mlin * C + col0);
+      uint4* ol = reinterpret_cast<uint4*>(q.dz_lo + mlin * C + col0);
+#pragma unroll
+      for (int j = 0; j < GW / 8; ++j) {
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) tmx_split_bf16x2(v[8 * j + 2 * t], v[8 * j + 2 * t + 1], ph[t], pl[t]);
+        oh[j] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        ol[j] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  }
+  if (q.dbias != nullptr) {      // (uniform branch: every lane takes part in the shuffles)
+    const float cs = warp_colsum32(v, lane);
+    if (lane < GW) atomicAdd(&bias_s[col0 + lane], cs);
+  }
+}
+
+// after the last tile: one global atomic per channel and CTA (the 128 epilogue threads, warps 4-7, meet first)
+__device__ __forceinline__ void gp_flush_bias(const GpParams& q, const float* bias_s, int C) {
+  if (q.dbias == nullptr) return;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  for (int c = threadIdx.x - 128; c < C; c += 128) {
+    const float bs = bias_s[c];
+    if (bs != 0.f) atomicAdd(q.dbias + c, bs * q.dbias_scale);
+  }
+}
+
+static inline GpParams tmx_gp_params(int H, int W, float* grid, const tmx_grad_desc_t* gd, const tmx_grad_io_t* gio) {
+  GpParams q;
+  q.H = H;
+  q.W = W;
+  q.fold = gd->fold;
+  q.mask_kind = gd->mask_kind;
+  q.alpha = gd->alpha;
+  q.dbias_scale = gd->dbias_scale;
+  q.add = gio->add;
+  q.mask = gio->y_mask;
+  q.grid = grid;
+  q.dz_hi = gio->dz_hi;
+  q.dz_lo = gio->dz_lo;
+  q.f32 = gio->dz_f32;
+  q.dbias = gio->dbias;
+  return q;
+}
+
 }  // namespace

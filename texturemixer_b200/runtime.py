@@ -290,7 +290,7 @@ class Runtime:
         return g
 
     def conv_dgrad_gp(self, dz, n, h, w, cin, cout, k, wt, fold, add=None, y_f32=None, y_hi=None, want_f32=False,
-                      dbias=None, alpha=None):
+                      dbias=None, alpha=None, want_planes=True):
         """tmx_conv2d_dgrad_gp: the data gradient of a conv AND the grad_prepare of its input activation [n,h,w,cin]
         (padding adjoint `fold`, addend, mask of the layer that produced the activation, bias gradient, planes) in one
         tensor-core kernel plus a border pass.  Returns (planes, f32 or None), or None when the library does not serve
@@ -305,10 +305,11 @@ class Runtime:
         elif y_hi is not None:
             d.mask_kind, io.y_mask = 2, y_hi.data_ptr()
         g = self.empty(n, h + 4, w + 4, cin)
-        planes = (self.empty(n, h + 4, w + 4, cin, dtype=torch.bfloat16),
-                  self.empty(n, h + 4, w + 4, cin, dtype=torch.bfloat16))
-        io.dz_hi, io.dz_lo = planes[0].data_ptr(), planes[1].data_ptr()
-        f32 = None
+        planes = f32 = None
+        if want_planes:
+            planes = (self.empty(n, h + 4, w + 4, cin, dtype=torch.bfloat16),
+                      self.empty(n, h + 4, w + 4, cin, dtype=torch.bfloat16))
+            io.dz_hi, io.dz_lo = planes[0].data_ptr(), planes[1].data_ptr()
         if want_f32:
             f32 = self.empty(n, h, w, cin)
             io.dz_f32 = f32.data_ptr()
