@@ -153,6 +153,11 @@ int tmx_torgb_fwd(tmx_handle_t h, const float* x_nhwc, const float* w /*[Cin][Co
                   tmx_stream_t s);
 /* downscale2d (networks.py:131-136): 2x2 mean, NHWC f32 [N][H][W][C] -> [N][H/2][W/2][C]. */
 int tmx_avgpool2_fwd(tmx_handle_t h, const float* x, float* y, int N, int H, int W, int C, tmx_stream_t s);
+/* the same pooling with the result ALSO (y may be NULL: only) written as SPLIT_BF16_HALO planes [N][H/2+2][W/2+2][C] for a
+ * tensor-core consumer (halo_kind as in tmx_split_halo_pack): downscale2d -> conv2d of networks.py:131-136, 48-56 without
+ * the intermediate layout pass.  H, W even and >= 4, C % 8 == 0. */
+int tmx_avgpool2_pack(tmx_handle_t h, const float* x, float* y, uint16_t* hi, uint16_t* lo, int N, int H, int W, int C,
+                      int halo_kind, tmx_stream_t s);
 /* Layout moves between the reference's NCHW and the internal NHWC.  The NHWC
  * side may be a channel slice [c_off, c_off+C) of a tensor with C_total channels
  * (tf.concat of networks.py:423; mu/log_sigma split of :289-290, :381-382).

@@ -84,6 +84,11 @@ def main():
                         n * gh * cin * 4 + n * h * w * cin * 2 + n * gh * cin * 4,
                         lambda: rt.grad_prepare(gg, n, h, w, cin, src_kind=0, fold=0, y_hi=xb.hi, want_planes=True,
                                                 dbias=dbias)))
+        # the two launches above as ONE (tmx_conv2d_dgrad_gp: grad_prepare in the data-gradient epilogue + border pass)
+        dbias2 = torch.zeros(cin, device=dev)
+        targets.append((tag + ' dgrad + grad_prepare fused (GP epilogue + border kernel)', 'tensor', flops,
+                        n * gh * 4 * cout + n * h * w * cin * 2 + n * gh * cin * 4,
+                        lambda: rt.conv_dgrad_gp(dz, n, h, w, cin, cout, 3, wt, 0, y_hi=xb.hi, dbias=dbias2)))
 
     n = 32
     t = conv_case('conv fwd 64x64 256->256 (Residual_0: planes out)', n, 64, 64, 256, 256)

@@ -75,6 +75,23 @@ def test_split_halo_pack_unpack(rt):
     assert np.abs(b.f32.cpu().numpy() - x).max() <= 2.0 ** -16 * np.abs(x).max()
 
 
+@pytest.mark.parametrize('halo', ['reflect', 'replicate', 'zero'])
+def test_avgpool2_pack_equals_pool_then_pack(rt, halo):
+    """downscale2d whose consumer is a tensor-core conv: one kernel writes the pooled fp32 map AND its split planes with
+    the consumer's halo - bit-identical to avgpool2 followed by split_halo_pack, and equal to the oracle's pooling."""
+    from texturemixer_b200.runtime import Act
+    x = (np.random.RandomState(5).randn(3, 12, 20, 24) * 2).astype(np.float32)       # NHWC
+    a = rt.avgpool2(Act(3, 12, 20, 24, f32=_dev(x)))
+    rt.split_pack(a, halo)
+    b = rt.avgpool2(Act(3, 12, 20, 24, f32=_dev(x)), pack=halo)
+    assert b.hi is not None and b.halo == halo and tuple(b.hi.shape) == (3, 8, 12, 24)
+    assert torch.equal(a.f32, b.f32)
+    assert torch.equal(a.hi.view(torch.int16), b.hi.view(torch.int16))
+    assert torch.equal(a.lo.view(torch.int16), b.lo.view(torch.int16))
+    want = R.downscale2d(torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2)))).numpy().transpose(0, 2, 3, 1)
+    assert np.abs(b.f32.cpu().numpy() - want).max() <= 1e-6 * np.abs(want).max()
+
+
 # ---------------------------------------------------------------------- convs
 def _oracle_conv(x, w, b, gain, lrelu, residual=None, up2=False):
     xt = torch.from_numpy(x)

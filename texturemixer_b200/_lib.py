@@ -77,6 +77,7 @@ _SIGNATURES = {
     'tmx_fromrgb_fwd': (C.c_int, [_P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     'tmx_torgb_fwd': (C.c_int, [_P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _I, _P]),
     'tmx_avgpool2_fwd': (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    'tmx_avgpool2_pack': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'tmx_nchw_to_nhwc': (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'tmx_nhwc_to_nchw': (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'tmx_conv2d_dgrad': (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),

@@ -142,6 +142,68 @@ extern "C" int tmx_avgpool2_fwd(tmx_handle_t h, const float* x, float* y, int N,
   return TMX_OK;
 }
 
+// downscale2d (networks.py:131-136) whose consumer is a tensor-core conv: the pooled map as fp32 NHWC (optional) AND as
+// split bf16 planes with the consumer's halo in ONE pass (was: avgpool2 -> fp32, then split_halo_pack re-reading it).
+// One thread = one PADDED output pixel x 8 channels; halo threads average the 2x2 window of their mirrored / clamped
+// source pixel again (a ring's worth of extra reads).
+__global__ void __launch_bounds__(256) avgpool2_pack_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                            uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                                            long long total, int Ho, int Wo, int C8, int halo_kind) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c8 = (int)(t % C8);
+  long long p = t / C8;
+  const int Wp = Wo + 2, Hp = Ho + 2;
+  const int xp = (int)(p % Wp);
+  long long q = p / Wp;
+  const int yp = (int)(q % Hp);
+  const long long n = q / Hp;
+  const bool ring = yp == 0 || yp == Hp - 1 || xp == 0 || xp == Wp - 1;
+  const int ys = halo_kind == 1 ? min(max(yp - 1, 0), Ho - 1) : tmx_reflect(yp - 1, Ho);
+  const int xs = halo_kind == 1 ? min(max(xp - 1, 0), Wo - 1) : tmx_reflect(xp - 1, Wo);
+  const int W = Wo * 2;
+  const float4* base = reinterpret_cast<const float4*>(x) + ((n * (Ho * 2) + ys * 2) * W + xs * 2) * (C8 * 2) + c8 * 2;
+  float v[8];
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const float4 a = __ldg(base + half), b = __ldg(base + C8 * 2 + half),
+                 c = __ldg(base + (long long)W * C8 * 2 + half), d = __ldg(base + (long long)W * C8 * 2 + C8 * 2 + half);
+    // TF/Eigen avg-pool sums the window then divides by its size (same order as avgpool2_kernel)
+    v[4 * half] = (a.x + b.x + c.x + d.x) * 0.25f;
+    v[4 * half + 1] = (a.y + b.y + c.y + d.y) * 0.25f;
+    v[4 * half + 2] = (a.z + b.z + c.z + d.z) * 0.25f;
+    v[4 * half + 3] = (a.w + b.w + c.w + d.w) * 0.25f;
+  }
+  if (!ring && y != nullptr) {
+    float4* o = reinterpret_cast<float4*>(y) + ((n * Ho + ys) * Wo + xs) * (C8 * 2) + c8 * 2;
+    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (halo_kind == 2 && ring) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  }
+  uint32_t ph[4], pl[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) tmx_split_bf16x2(v[2 * i], v[2 * i + 1], ph[i], pl[i]);
+  reinterpret_cast<uint4*>(hi)[t] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  reinterpret_cast<uint4*>(lo)[t] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+
+extern "C" int tmx_avgpool2_pack(tmx_handle_t h, const float* x, float* y, uint16_t* hi, uint16_t* lo, int N, int H, int W,
+                                 int C, int halo_kind, tmx_stream_t s) {
+  TMX_REQUIRE(h && x && hi && lo, TMX_ERR_ARG, "tmx_avgpool2_pack: NULL argument");
+  TMX_REQUIRE(halo_kind >= 0 && halo_kind <= 2, TMX_ERR_ARG, "tmx_avgpool2_pack: halo kind %d not in 0..2", halo_kind);
+  TMX_REQUIRE(N > 0 && H >= 4 && W >= 4 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0, TMX_ERR_SHAPE,
+              "tmx_avgpool2_pack: bad shape N=%d H=%d W=%d C=%d (even H, W >= 4: the pooled map needs 2 x 2 pixels for its "
+              "halo; C %% 8 == 0)", N, H, W, C);
+  const long long total = (long long)N * (H / 2 + 2) * (W / 2 + 2) * (C / 8);
+  avgpool2_pack_kernel<<<tmx_ceil_div(total, 256), 256, 0, (cudaStream_t)s>>>(x, y, hi, lo, total, H / 2, W / 2, C / 8,
+                                                                              halo_kind);
+  TMX_LAUNCHED(h, "avgpool2_pack_kernel");
+  return TMX_OK;
+}
+
 // ---------------------------------------------------------------- NCHW <-> NHWC
 // 32x32 smem tile transpose per image between [C][HW] and [HW][C_total] (+c_off).
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C,

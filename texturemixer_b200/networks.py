@@ -239,7 +239,10 @@ def downscale2d(x, factor=2):
     f = factor
     while f > 1:
         assert f % 2 == 0
-        b = ctx.rt.avgpool2(a)
+        # the last pooling step feeds the next block's 3x3 conv (networks.py:238-256, 340-350, 530-548): written as
+        # split planes with the REFLECT halo by the pooling kernel itself when that conv runs on the tensor cores
+        tc_next = f == 2 and a.c % 16 == 0 and a.h >= 4 and a.w >= 4
+        b = ctx.rt.avgpool2(a, pack='reflect' if tc_next else None)
         if ctx.tape is not None:
             ctx.tape.append(dict(kind='pool', x=a, y=b))
         a = b

@@ -387,8 +387,19 @@ class Runtime:
                                           x.n, x.h, x.w, x.c, cout, int(apply_tanh), self.stream()), 'tmx_torgb_fwd')
         return out
 
-    def avgpool2(self, x):
+    def avgpool2(self, x, pack=None):
+        """downscale2d by 2.  `pack` = halo kind ('reflect' | 'replicate' | 'zero'): the consumer is a tensor-core conv -
+        the pooled map is also written as split planes with that halo by the same kernel (tmx_avgpool2_pack)."""
         self.split_unpack(x)
+        if pack is not None and x.h >= 4 and x.w >= 4 and x.c % 8 == 0 and not os.environ.get('TMX_NO_POOL_PACK'):
+            out = Act(x.n, x.h // 2, x.w // 2, x.c, f32=self.empty(x.n, x.h // 2, x.w // 2, x.c))
+            out.hi = self.planes(out.n, out.h + 2, out.w + 2, out.c)
+            out.lo = self.planes(out.n, out.h + 2, out.w + 2, out.c)
+            out.halo = pack
+            _lib.check(self.lib.tmx_avgpool2_pack(self.handle, _ptr(x.f32), _ptr(out.f32), _ptr(out.hi), _ptr(out.lo),
+                                                  x.n, x.h, x.w, x.c, HALO_KINDS[pack], self.stream()),
+                       'tmx_avgpool2_pack')
+            return out
         out = Act(x.n, x.h // 2, x.w // 2, x.c, f32=self.empty(x.n, x.h // 2, x.w // 2, x.c))
         _lib.check(self.lib.tmx_avgpool2_fwd(self.handle, _ptr(x.f32), _ptr(out.f32), x.n, x.h, x.w, x.c,
                                              self.stream()), 'tmx_avgpool2_fwd')
