@@ -366,10 +366,10 @@ TRAIN_GFLOP = {True: 475.5, False: 1039.9}     # + GRAM_GFLOP when the Gram term
 # dominant kernel of the step: conv_tc_kernel<256,64,32,PAIR> on the 64x64 trunk windows (3x3, 256 -> 256, batch 32)
 TRUNK64_GFLOP = 2 * 9 * 256 * 256 * 64 * 64 * TRAIN_BATCH / 1e9          # 154.6 GFLOP per launch
 # dram__bytes_read.sum + dram__bytes_write.sum of one such launch from the committed `ncu --set full` capture
-# (Residual_0 form - planes out: 145.9 MB read + 96.3 MB written; Residual_1 form - fp32 residual in, fp32 + planes
-# out: 283.5 + 225.0 MB; the step launches both forms equally often; algorithmic bytes 285 / 571 MB)
-TRUNK64_DRAM_BYTES = 0.5 * ((145.9e6 + 96.3e6) + (283.5e6 + 225.0e6))
-TRUNK64_DRAM_SOURCE = 'profiles/r02_ncu_kernels_summary_v2.csv ids 0 and 16 (ncu --set full of profiles/kernel_targets.py)'
+# (Residual_0 form - planes out: 146.0 MB read + 92.2 MB written; Residual_1 form - fp32 residual in, fp32 + planes
+# out: 283.8 + 225.9 MB; the step launches both forms equally often; algorithmic bytes 285 / 571 MB)
+TRUNK64_DRAM_BYTES = 0.5 * ((146.0e6 + 92.2e6) + (283.8e6 + 225.9e6))
+TRUNK64_DRAM_SOURCE = 'profiles/r02_ncu_kernels_summary_v3.csv ids 0 and 14 (ncu --set full of profiles/kernel_targets.py)'
 CPU_TRAIN_SAMPLE = 2
 CPU_TRAIN_DESC = ('one whole train step per step on %d images (whole 3x3 canvases, autograd incl. the gradient penalty), '
                   'torch-CPU fp32 restatement (oracle/)' % CPU_TRAIN_SAMPLE)
