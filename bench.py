@@ -595,7 +595,8 @@ def run_train(args):
                        'batch_per_gpu': TRAIN_BATCH, 'global_batch': TRAIN_BATCH * world,
                        'l2': 'working set per step (>20 GB) far exceeds the 126 MB L2',
                        'parallelism': 'dp%d: ONE flat-bucket NCCL all-reduce per optimizer phase (2 per step), non-finite '
-                                      'marks in the bucket tail' % world,
+                                      'marks in the bucket tail; the critics\' all-reduce overlaps the VGG-19 Gram terms '
+                                      '(collective_ms_per_step = the part the compute stream waits for)' % world,
                        'cuda_graphs': str(cfg['cuda_graphs']),
                        'g_fcn': 'crop-aware: decodes the 64x64 latent window of each random_crop, the last 4 latent convs on 48x48, the '
                                 'up-sampling blocks on 40x40 of it '

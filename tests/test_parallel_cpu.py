@@ -33,7 +33,14 @@ def _worker(rank, world, port, out):
     n = parallel.allreduce_sum_([g1, g2, empty])
     w = torch.full((10,), float(rank))
     parallel.broadcast_([w], src=0)
-    out[rank] = dict(bounds=(b, e), g1=g1.numpy().copy(), g2=g2.numpy().copy(), n=n, w=w.numpy().copy())
+    # the non-blocking form the trainer uses (issue, do independent work, wait): same SUM
+    g3 = torch.from_numpy(np.random.RandomState(200 + rank).randn(333).astype(np.float32))
+    wait = parallel.allreduce_sum_async_(g3)
+    busy = float(torch.ones(16).sum())           # (work that does not touch the buffer)
+    wait()
+    assert busy == 16.0
+    out[rank] = dict(bounds=(b, e), g1=g1.numpy().copy(), g2=g2.numpy().copy(), n=n, w=w.numpy().copy(),
+                     g3=g3.numpy().copy())
     torch.distributed.destroy_process_group()
 
 
@@ -50,6 +57,8 @@ def test_two_rank_allreduce_and_sharding():
         assert out[r]['n'] == 2                                   # the zero-sized buffer is skipped (tfutil.py:329)
         assert np.array_equal(out[r]['g1'], want)                 # both ranks hold the same SUM
         assert np.array_equal(out[r]['w'], np.zeros(10, np.float32))
+        assert np.array_equal(out[r]['g3'], sum(np.random.RandomState(200 + q).randn(333).astype(np.float32)
+                                                 for q in range(world)))
     # the summed gradient x 1/N drives the same Adam step as the oracle's tower list
     w_ref = np.ones(1000, np.float32)
     st = O.AdamState(1000, 0.0, 0.99)

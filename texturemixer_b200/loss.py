@@ -472,15 +472,38 @@ def _zl_canvas_bwd(rt, fwd, d, win, dzl, lsg, ih, iw, which, reverse):
                    lsg.get('zl'), reverse)
 
 
+def gram_terms(fwd, crop_interp, crop_blend, gram, gram_weight, gram_alpha, interp_G_weight=1.0,
+               blend_interp_G_weight=1.0, reals_fade=None):
+    """The VGG-19 Gram terms of EG_wgan (loss.py:148-160, 206-213, 248-257) and their image gradients:
+    {'rec' | 'interp' | 'blend': (term, d term / d image)}.  They depend on the generated images and the reals only -
+    not on the critics - so the trainer evaluates them while the critics' gradient all-reduce is in flight."""
+    rt = fwd.rt
+    reals = fwd.reals if reals_fade is None else reals_fade
+    n = fwd.n
+    out = {}
+    _, real_gram = gram.grams(reals.contiguous())
+    out['rec'] = gram.term(fwd.rec, [(real_gram, False, None, 0)], gram_weight)
+    if interp_G_weight > 0:
+        out['interp'] = gram.term(fwd.crop('interp', crop_interp), [(real_gram, False, None, 0)], gram_weight)
+    if blend_interp_G_weight > 0:
+        # loss.py:252-255 AS WRITTEN: (1 - alpha) [N,1,1,1] * multi_layer_diff [N] broadcasts to [N,1,1,N], so what
+        # the optimizer differentiates is mean(1 - alpha) * mean_j A_j + mean(alpha) * mean_j B_j, A against the
+        # batch-reversed real Gram matrices, B against the real ones (kept as the reference has it)
+        abar = _row_sum(rt, gram_alpha.reshape(-1).contiguous(), 1, n, scale=1.0 / n)
+        out['blend'] = gram.term(fwd.crop('blend', crop_blend),
+                                 [(real_gram, True, abar, 2), (real_gram, False, abar, 1)], gram_weight)
+    return out
+
+
 def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, rec_G_weight=1.0, pixel_weight=200.0,
                 interp_G_weight=1.0, blend_interp_G_weight=1.0, reals_fade=None, critic_grads=None, kl_weight=0.0,
-                gram=None, gram_weight=0.0, gram_alpha=None):
+                gram=None, gram_weight=0.0, gram_alpha=None, gram_grads=None):
     """Loss terms of `EG_wgan` on the images of `fwd` and the whole reverse pass into `grads`.  `reals_fade`: the
     target of the pixel loss (loss.py:143) when it differs from what the encoders saw (fractional lod).
     `critic_grads`: optional {'rec' | 'interp' | 'blend': critic_input_gradient(...)} evaluated by the caller (the
     trainer runs them on parallel streams).
     `gram` (a vgg.GramLoss) with gram_weight > 0 adds the VGG-19 Gram terms of loss.py:148-160, 206-213, 248-257;
-    `gram_alpha` = the [N,1,1,1] uniform draw of loss.py:253."""
+    `gram_alpha` = the [N,1,1,1] uniform draw of loss.py:253; `gram_grads` = gram_terms(...) evaluated by the caller."""
     rt = fwd.rt
     E_zg, E_zl, G, G_fcn = fwd.nets
     reals, n, c, lat, H, W, pins = fwd.reals, fwd.n, fwd.c, fwd.lat, fwd.H, fwd.W, fwd.pins
@@ -503,8 +526,10 @@ def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, r
         d_rec_img = l1 if d_rec_img is None else _add(rt, d_rec_img, l1)
     use_gram = gram is not None and gram_weight > 0
     if use_gram:                                                          # loss.py:149-160
-        _, real_gram = gram.grams(reals.contiguous())
-        report['rec_gram'], dg = gram.term(rec, [(real_gram, False, None, 0)], gram_weight)
+        gt = gram_grads if gram_grads is not None else gram_terms(
+            fwd, crop_interp, crop_blend, gram, gram_weight, gram_alpha, interp_G_weight, blend_interp_G_weight,
+            reals_fade=reals_fade)
+        report['rec_gram'], dg = gt['rec']
         d_rec_img = dg if d_rec_img is None else _add(rt, d_rec_img, dg)
     dzg_tiled, dzl = backward(G, fwd.t_rec, [d_rec_img], grads['G'])
     dzg = _row_sum(rt, dzg_tiled, n * c, lat * lat)                      # adjoint of the 32x32 tile of zg
@@ -514,8 +539,7 @@ def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, r
         report['interp_G'], dcr = cg['interp'] if 'interp' in cg else \
             critic_input_gradient(D_interp, fwd.crop('interp', crop_interp), interp_G_weight)
         if use_gram:                                                      # loss.py:206-213
-            report['interp_gram'], dg = gram.term(fwd.crop('interp', crop_interp), [(real_gram, False, None, 0)],
-                                                  gram_weight)
+            report['interp_gram'], dg = gt['interp']
             dcr = _add(rt, dcr, dg)
         dzg_c, dzl_c = backward(G_fcn, fwd.t_int, [_crop_adjoint(rt, dcr, fwd.interp.shape[2:],
                                                                  fwd.image_window('interp', crop_interp))], grads['G'])
@@ -526,12 +550,7 @@ def EG_backward(fwd, D_rec, D_interp, D_blend, crop_interp, crop_blend, grads, r
         report['blend_G'], dcr = cg['blend'] if 'blend' in cg else \
             critic_input_gradient(D_blend, fwd.crop('blend', crop_blend), blend_interp_G_weight)
         if use_gram:
-            # loss.py:252-255 AS WRITTEN: (1 - alpha) [N,1,1,1] * multi_layer_diff [N] broadcasts to [N,1,1,N], so what
-            # the optimizer differentiates is mean(1 - alpha) * mean_j A_j + mean(alpha) * mean_j B_j, A against the
-            # batch-reversed real Gram matrices, B against the real ones (kept as the reference has it)
-            abar = _row_sum(rt, gram_alpha.reshape(-1).contiguous(), 1, n, scale=inv_n)
-            report['blend_gram'], dg = gram.term(fwd.crop('blend', crop_blend),
-                                                 [(real_gram, True, abar, 2), (real_gram, False, abar, 1)], gram_weight)
+            report['blend_gram'], dg = gt['blend']
             dcr = _add(rt, dcr, dg)
         dbzg, dbzl = backward(G_fcn, fwd.t_bl, [_crop_adjoint(rt, dcr, fwd.blend.shape[2:],
                                                               fwd.image_window('blend', crop_blend))], grads['G'])

@@ -63,6 +63,11 @@ class GradientBucket:
         """ONE SUM all-reduce for the phase (no-op in a single-process job)."""
         self.collectives += parallel.allreduce_sum_([self.flat])
 
+    def allreduce_async(self):
+        """The same collective, issued without blocking the current stream; returns wait() (parallel.allreduce_sum_async_)."""
+        self.collectives += 1 if parallel.world_size() > 1 else 0
+        return parallel.allreduce_sum_async_(self.flat)
+
 
 class Optimizer:
     def __init__(self, name='Train', tf_optimizer='tf.train.AdamOptimizer', learning_rate=0.001,

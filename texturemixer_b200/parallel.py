@@ -64,6 +64,17 @@ def allreduce_sum_(flat_buffers):
     return n
 
 
+def allreduce_sum_async_(flat_buffer):
+    """Issue the in-place SUM all-reduce of one flat buffer WITHOUT making the current stream wait for it: the
+    collective starts once the kernels enqueued so far have finished and runs on the communicator's own stream, so
+    kernels launched next overlap it.  Returns wait() - call it before anything reads the buffer (it makes the current
+    stream wait, the host does not block).  Single-process job: nothing is issued, wait() is a no-op."""
+    if world_size() == 1 or flat_buffer.numel() == 0:
+        return lambda: None
+    work = dist.all_reduce(flat_buffer, op=dist.ReduceOp.SUM, async_op=True)
+    return work.wait
+
+
 def broadcast_(flat_buffers, src=0):
     """Make replicas bit-identical at start-up (the reference clones variables per tower, run.py:303-309)."""
     if world_size() == 1:

@@ -447,21 +447,28 @@ class Trainer:
             d_fade, d_orig = process_reals(images_d, lod_now, **kw)
         return self.step(fade, draws, lod=lod, reals_orig=orig, reals_d=d_fade, reals_d_orig=d_orig, **step_kwargs)
 
-    def _allreduce(self, name):
-        b = self.buckets[name]
-        if self.time_collectives and parallel.world_size() > 1:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            b.allreduce()
-            e1.record()
-            self.allreduce_events.append((name, e0, e1))
-        else:
-            b.allreduce()
+    def _allreduce(self, name, overlap=True):
+        """Issue the SUM all-reduce of gradient bucket `name` on the communicator's stream and return wait(): kernels
+        launched before wait() overlap the collective (the VGG-19 Gram terms ride on the critics' all-reduce), wait()
+        makes the compute stream wait for it.  The recorded events bracket the EXPOSED part only (wait entry -> done)."""
+        done = self.buckets[name].allreduce_async()
+
+        def wait():
+            if self.time_collectives and parallel.world_size() > 1:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                done()
+                e1.record()
+                self.allreduce_events.append((name, e0, e1))
+            else:
+                done()
+        return wait
 
     def _step_body(self, reals_fade, reals_orig, d_fade, d_orig, draws, lrate, phases, critic_graphs=False,
                    boundary=None):
-        """The launches of one step.  `boundary(name)`: where the all-reduce of gradient bucket `name` goes (default:
-        issue it; the graph capture cuts the step there)."""
+        """The launches of one step.  `boundary(name)`: where the all-reduce of gradient bucket `name` is ISSUED; it
+        returns wait(), called where the reduced gradients are needed (default: Trainer._allreduce; the graph capture
+        cuts the step at both points)."""
         boundary = boundary or self._allreduce
         report = {}
         c = self.cfg
@@ -480,7 +487,7 @@ class Trainer:
                                   c['scale_h'], c['scale_w'], defer_canvases=True,
                                   plans={'interp': plans['eg_crop_interp'], 'blend': plans['eg_crop_blend']},
                                   modes=self._modes(draws, 'eg'))
-        fwd = None
+        fwd = gram_grads = None
         if 'D' in phases:
             if shared:
                 fwd = fwd_d = eg_forward()
@@ -520,7 +527,16 @@ class Trainer:
                 report.update({name + '/' + k: v for k, v in rep.items()})
             for name in ('D_rec', 'D_interp', 'D_blend'):                           # one session.run (run.py:511)
                 self.opts[name].mark()
-            boundary('D')
+            wait_d = boundary('D')
+            # in flight now: the critics' gradient all-reduce.  The VGG-19 Gram terms of the E/G loss need the generated
+            # images and the reals, not the critics: they run while the collective does
+            if 'EG' in phases and self.gram is not None and c['loss'].get('gram_weight', 0.0) > 0:
+                lw = c['loss']
+                gram_grads = loss.gram_terms(fwd, draws['eg_crop_interp'], draws['eg_crop_blend'], self.gram,
+                                             lw['gram_weight'], draws.get('eg_gram_alpha'),
+                                             lw.get('interp_G_weight', 1.0), lw.get('blend_interp_G_weight', 1.0),
+                                             reals_fade=reals_fade)
+            wait_d()
             for name in ('D_rec', 'D_interp', 'D_blend'):
                 report[name + '/skipped'] = self.opts[name].update(lrate)
             self._d_keep = fakes
@@ -535,10 +551,10 @@ class Trainer:
             rep = loss.EG_backward(fwd, nets['D_rec'], nets['D_interp'], nets['D_blend'],
                                    draws['eg_crop_interp'], draws['eg_crop_blend'], self.grads, reals_fade=reals_fade,
                                    critic_grads=critic_grads, gram=self.gram, gram_alpha=draws.get('eg_gram_alpha'),
-                                   **c['loss'])
+                                   gram_grads=gram_grads, **c['loss'])
             report.update({'EG/' + k: v for k, v in rep.items()})
             self.opts['EG'].mark()
-            boundary('EG')
+            boundary('EG', overlap=False)()         # (nothing of this step is left to overlap with the E/G all-reduce)
             report['EG/skipped'] = self.opts['EG'].update(lrate)
         del fwd
         if 'EMA' in phases:
@@ -574,11 +590,14 @@ class Trainer:
             dst.copy_(src, non_blocking=True)
         ent.packed.copy_(draws['_packed'], non_blocking=True)
         ent.mixes.copy_(draws['_mixes'], non_blocking=True)
+        pending = {}
         for kind, obj in ent.program:
             if kind == 'graph':
                 obj.replay()
-            else:
-                self._allreduce(obj)
+            elif kind == 'allreduce':
+                pending[obj] = self._allreduce(obj)
+            else:                                # 'wait'
+                pending.pop(obj)()
         self.graph_launches += ent.launches
         for net in self.nets.values():      # the graph re-derives its weight planes itself; eager users must too
             net._touch()
@@ -616,11 +635,22 @@ class Trainer:
             state['ctx'].__exit__(None, None, None)
             program.append(('graph', state['g']))
 
-        def boundary(name):
-            if parallel.world_size() > 1:        # the all-reduce stays an ordinary NCCL call between two graphs
-                end()
-                program.append(('allreduce', name))
+        def boundary(name, overlap=True):
+            if parallel.world_size() == 1:
+                return lambda: None
+            end()                                # the all-reduce stays an ordinary NCCL call between two graphs
+            program.append(('allreduce', name))
+            if not overlap:                      # waited for at once: no (empty) graph in between
+                program.append(('wait', name))
                 begin()
+                return lambda: None
+            begin()
+
+            def wait():                          # ... and so does the point where the compute stream waits for it
+                end()
+                program.append(('wait', name))
+                begin()
+            return wait
         l0 = rt.launch_count()
         gc.collect()
         gc_was_on = gc.isenabled()
