@@ -324,3 +324,29 @@ def test_broadcast_inputs_collapse_to_one_pixel():
     assert _collapse_broadcast(view).shape == (3, 8, 1, 1) and np.array_equal(_collapse_broadcast(view), zg)
     tiled = np.tile(zg, (1, 1, 4, 4))
     assert _collapse_broadcast(tiled) is tiled and _collapse_broadcast(zg) is zg
+
+
+def test_fused_dgrad_tape_analysis():
+    """backward.gp_fusion_maps: the conv that may prepare an activation's gradient inside its data gradient is the
+    activation's EARLIEST consumer (every later consumer has already been differentiated when the reverse pass gets
+    there), and only activations produced by conv / FromRGB / pool / window / concat records qualify."""
+    from texturemixer_b200.backward import gp_fusion_maps
+    from texturemixer_b200.runtime import Act
+    a0, a1, a2, a3, p3, m4 = (Act(2, 8, 8, 32) for _ in range(6))
+    img = object()
+    tape = [
+        dict(kind='fromrgb', img=img, y=a0),                          # 0
+        dict(kind='conv', x=a0, y=a1, residual=None, up2=False),      # 1  Residual_0
+        dict(kind='conv', x=a1, y=a2, residual=a0, up2=False),        # 2  Residual_1: + a0
+        dict(kind='conv', x=a2, y=a3, residual=None, up2=False),      # 3
+        dict(kind='pool', x=a3, y=p3),                                # 4
+        dict(kind='mbstd', x=p3, y=m4, group=4),                      # 5
+        dict(kind='outputs', tensors=[]),
+    ]
+    first_use, producer = gp_fusion_maps(tape)
+    assert first_use[id(a0)] == 1          # conv 1 reads it before conv 2 adds it back as the residual
+    assert first_use[id(a1)] == 2 and first_use[id(a2)] == 3 and first_use[id(a3)] == 4 and first_use[id(p3)] == 5
+    assert producer[id(a0)]['kind'] == 'fromrgb' and producer[id(a1)] is tape[1] and producer[id(a2)] is tape[2]
+    assert producer[id(p3)]['kind'] == 'pool'
+    assert id(m4) not in producer          # minibatch stddev: not a producer the fused kernel stands in for
+    assert id(img) not in first_use        # plain tensors (images) are not activations

@@ -86,6 +86,24 @@ def _combine(rt, act, contribs, want_planes, want_f32, mask_y=None, dbias=None, 
 _GP_PRODUCERS = ('conv', 'fromrgb', 'pool', 'window', 'concat')
 
 
+def gp_fusion_maps(tape):
+    """Tape pre-pass of the fused data gradient: ({id(activation): tape position of its EARLIEST consumer},
+    {id(activation): the record that produced it, for the producer kinds the fused kernel can stand in for}).  The
+    reverse pass walks the tape backwards, so the earliest consumer is the last one to contribute a gradient."""
+    first_use, producer = {}, {}
+    for pos, rec in enumerate(tape):
+        for key in ('x', 'residual', 'a', 'b'):
+            a = rec.get(key)
+            if isinstance(a, runtime.Act):
+                first_use.setdefault(id(a), pos)
+        for a in (rec.get('inputs') or ()):
+            if isinstance(a, runtime.Act):
+                first_use.setdefault(id(a), pos)
+        if rec['kind'] in _GP_PRODUCERS and isinstance(rec.get('y'), runtime.Act):
+            producer[id(rec['y'])] = rec
+    return first_use, producer
+
+
 def _scaled(rt, x, a):
     """a * x (fp32, any shape)."""
     x = x.contiguous()
@@ -180,19 +198,8 @@ def backward(net, tape, out_grads, flat_grad, want_input_grads=True, param_grads
     # to its input activation (every other consumer sits later on the tape, i.e. has already been differentiated) and
     # that activation is the plain output of another conv record, whose mask / bias gradient / residual need are then
     # known at the time of the data gradient
-    first_use, producer = {}, {}
     fuse_gp = not os.environ.get('TMX_NO_FUSED_GP')
-    if fuse_gp:
-        for pos_, rec_ in enumerate(tape):
-            for key in ('x', 'residual', 'a', 'b'):
-                a_ = rec_.get(key)
-                if isinstance(a_, runtime.Act):
-                    first_use.setdefault(id(a_), pos_)
-            for a_ in (rec_.get('inputs') or ()):
-                if isinstance(a_, runtime.Act):
-                    first_use.setdefault(id(a_), pos_)
-            if rec_['kind'] in _GP_PRODUCERS and isinstance(rec_.get('y'), runtime.Act):
-                producer[id(rec_['y'])] = rec_
+    first_use, producer = gp_fusion_maps(tape) if fuse_gp else ({}, {})
 
     def fused_dgrad(pos, rec, x, dz, wt, hs, ws_, cin_g, ng, k, fold):
         """Data gradient of `rec` w.r.t. `x` with x's grad_prepare folded in; False when not applicable."""
