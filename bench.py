@@ -872,6 +872,30 @@ def throttled(line):
     return bool(sm and mx and sm < 0.7 * mx and not c.get('reasons'))
 
 
+def supervise():
+    """Run the measurement in a child process (same command line, same environment: under torchrun every rank does
+    this) with a time limit, once more if the first attempt stalls or fails, and pass its JSON line through.  One bench
+    run in ~60 of this round's stopped making progress on a fresh box for reasons that left no trace; a stalled run
+    must not cost the whole measurement."""
+    limit = float(os.environ.get('TMX_BENCH_TIMEOUT', '900'))
+    env = dict(os.environ, TMX_BENCH_CHILD='1')
+    for attempt in (1, 2):
+        proc = subprocess.Popen([sys.executable] + sys.argv, env=env, stdout=subprocess.PIPE, text=True)
+        try:
+            out, _ = proc.communicate(timeout=limit)
+        except subprocess.TimeoutExpired:
+            proc.kill()
+            proc.communicate()
+            sys.stderr.write('bench.py: attempt %d made no progress for %.0f s and was stopped\n' % (attempt, limit))
+            continue
+        if proc.returncode == 0:
+            sys.stdout.write(out)
+            sys.stdout.flush()
+            return 0
+        sys.stderr.write('bench.py: attempt %d exited with code %d\n' % (attempt, proc.returncode))
+    return 1
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -896,6 +920,11 @@ def main():
     if args.impl == 'reference':
         run_reference(args)
         return
+    if not os.environ.get('TMX_BENCH_CHILD') and not args.device_only and os.environ.get('TMX_BENCH_SUPERVISE', '1') != '0':
+        sys.exit(supervise())
+    if os.environ.get('TMX_BENCH_CHILD'):
+        import faulthandler      # a stalled run leaves the stack of every thread on stderr shortly before it is stopped
+        faulthandler.dump_traceback_later(max(60.0, float(os.environ.get('TMX_BENCH_TIMEOUT', '900')) - 30.0), exit=False)
     fn = {'train_step': run_train, 'interp': run_interp, 'recon': run_recon}.get(args.workload, run_ours)
     fn(args)
     if RESULT and throttled(RESULT[-1]) and int(os.environ.get('WORLD_SIZE', '1')) == 1 and not args.device_only:
