@@ -8,6 +8,9 @@ texture images/sec (whole job, all ranks; one step consumes one minibatch per ra
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload ...]
 
+Our arm measures in a supervised child process (time limit TMX_BENCH_TIMEOUT = 900 s, one retry, see supervise());
+TMX_BENCH_SUPERVISE=0 or --device-only measure in-process (profiler runs).
+
 The gen_fwd workload: generator `G_res` forward, batch 64 random
 latents per GPU (zg tiled to 32x32, zl ~ N(0,1)), fp32 in/out, 128x128x3 out.
 
